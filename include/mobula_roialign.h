@@ -1,0 +1,152 @@
+/*
+ * mobula_roialign.h -- C ABI of libmobula_roialign_sm100.so
+ *
+ * The B200 (sm_100a) replacement for the native side of MobulaOP's ROIAlign
+ * operator.  Plain C: pointers, ints and floats only; no C++/torch types.
+ *
+ * Two groups of entry points:
+ *
+ *  1. DROP-IN symbols.  Exactly the extern "C" functions the reference's JIT code
+ *     generator emits for opzoo/ROIAlign/ROIAlign.cpp and that
+ *     mobula/func.py:155-156 calls through ctypes (wrapper template
+ *     mobula/op/templates/kernel_code.cpp:1-5, symbol naming func.py:13-50,
+ *     `set_device` from mobula/cpp/include/context/context.h:15-17).  Same names,
+ *     same argument order, same synchronous semantics.
+ *
+ *  2. `mobula_roialign_*` v2 entry points: explicit CUDA stream, status return,
+ *     number of images (needed to fuse the dX zero-fill of ROIAlign.py:33-34 into
+ *     the backward kernel), backward mode and algorithm selection.  The Python
+ *     host layer (mobulaop_b200/func.py) uses these.
+ *
+ * Tensor conventions (reference: opzoo/ROIAlign/ROIAlign.cpp:9-16, 78-83):
+ *   bottom_data / bottom_diff : [N, C, H, W]   fp32, contiguous (NCHW)
+ *   bottom_rois               : [R, 5]         fp32, rows = [batch_idx, x1, y1, x2, y2]
+ *   top_data / top_diff       : [R, C, PH, PW] fp32, contiguous
+ * The caller owns every buffer.  The library keeps a small per-device workspace
+ * (ROI order tables, staging buffers for the host-buffer path) that is released by
+ * mobula_roialign_release().
+ */
+#ifndef MOBULA_ROIALIGN_H_
+#define MOBULA_ROIALIGN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOBULA_ROIALIGN_ABI_VERSION 1
+
+/* status codes returned by the v2 entry points */
+#define MOBULA_OK 0
+#define MOBULA_ERR_INVALID_ARGUMENT 1
+#define MOBULA_ERR_CUDA 2
+#define MOBULA_ERR_UNSUPPORTED 3
+
+/* backward `mode` */
+#define MOBULA_ROIALIGN_BWD_ATOMIC 0        /* fastest; rounding order not reproducible   */
+#define MOBULA_ROIALIGN_BWD_DETERMINISTIC 1 /* bit-exact: canonical ascending-index order */
+
+/* `flags` (bit mask) */
+#define MOBULA_ROIALIGN_ACCUMULATE 1u   /* fwd: top_data += result; bwd: do not zero-fill dX */
+#define MOBULA_ROIALIGN_HOST_BUFFERS 2u /* all pointers are HOST memory: the library stages
+                                           them to the device, runs, copies the result back
+                                           and synchronises before returning               */
+/* algorithm selection, bits 8..11 (0 = automatic) */
+#define MOBULA_ROIALIGN_ALGO_SHIFT 8
+#define MOBULA_ROIALIGN_ALGO_MASK (0xFu << MOBULA_ROIALIGN_ALGO_SHIFT)
+#define MOBULA_ROIALIGN_ALGO_AUTO 0u
+#define MOBULA_ROIALIGN_ALGO_GATHER 1u /* per-(roi,bin) threads, taps from global memory   */
+#define MOBULA_ROIALIGN_ALGO_PLANE 2u  /* one CTA owns a whole (image, channel) plane in
+                                          shared memory (TMA bulk copy in / out)           */
+
+/* ------------------------------------------------------------------------- *
+ * 1. Drop-in symbols (reference ABI)                                         *
+ * ------------------------------------------------------------------------- */
+
+/* Replaces the generated wrapper around roi_align_forward_kernel<float>
+ * (/root/reference/opzoo/ROIAlign/ROIAlign.cpp:9-16).  device_id >= 0: device
+ * pointers on that GPU; device_id < 0 (the reference's CPU context,
+ * mobula/func.py:139-141): HOST pointers, staged through the current GPU.
+ * Synchronous: returns after the result is complete (reference:
+ * mobula/cpp/include/context/hip_ctx.h:71-86).  Errors print to stderr and
+ * abort like the reference's CHECK macros (logging.h:23-26). */
+void roi_align_forward_ab78de3c(const int device_id, const int nthreads,
+                                const float* bottom_data, const float spatial_scale,
+                                const int channels, const int height, const int width,
+                                const int pooled_height, const int pooled_width,
+                                const int sampling_ratio, const float* bottom_rois,
+                                float* top_data);
+
+/* Replaces the wrapper around roi_align_backward_kernel<float>
+ * (ROIAlign.cpp:78-83).  Adds into bottom_diff, which the caller has zeroed
+ * (ROIAlign.py:33-34) -- note the argument order: bottom_diff BEFORE bottom_rois. */
+void roi_align_backward_f318a24e(const int device_id, const int nthreads,
+                                 const float* top_diff, const float spatial_scale,
+                                 const int channels, const int height, const int width,
+                                 const int pooled_height, const int pooled_width,
+                                 const int sampling_ratio, float* bottom_diff,
+                                 const float* bottom_rois);
+
+/* mobula/cpp/src/context.cpp:9-16 */
+void set_device(const int device_id);
+
+/* ------------------------------------------------------------------------- *
+ * 2. v2 entry points                                                         *
+ * ------------------------------------------------------------------------- */
+
+int mobula_roialign_abi_version(void);
+
+/* Human-readable description of the last failure on the calling thread. */
+const char* mobula_last_error(void);
+
+/* Forward bilinear pool.  `stream` is a cudaStream_t (NULL = legacy default
+ * stream); the call is asynchronous unless MOBULA_ROIALIGN_HOST_BUFFERS is set.
+ * `num_images` = N, or -1 if unknown (disables the batch-index range check and the
+ * PLANE algorithm). */
+int mobula_roialign_forward_f32(int device_id, void* stream, const float* bottom_data,
+                                const float* bottom_rois, float* top_data, int num_rois,
+                                int num_images, int channels, int height, int width,
+                                int pooled_height, int pooled_width, float spatial_scale,
+                                int sampling_ratio, unsigned flags);
+
+/* Backward gradient scatter.  Unless MOBULA_ROIALIGN_ACCUMULATE is set the result
+ * REPLACES bottom_diff (the zero-fill is fused), which requires num_images >= 0.
+ * The ROI gradient is identically zero (ROIAlign.py:41-42) and is not produced. */
+int mobula_roialign_backward_f32(int device_id, void* stream, const float* top_diff,
+                                 const float* bottom_rois, float* bottom_diff, int num_rois,
+                                 int num_images, int channels, int height, int width,
+                                 int pooled_height, int pooled_width, float spatial_scale,
+                                 int sampling_ratio, int mode, unsigned flags);
+
+/* ROI bookkeeping as the kernels compute it, for bit-exact checking against the
+ * oracle (same layout as oracle_roi_align_bookkeeping_f32):
+ *   geom_i [R,4]  = batch, grid_h, grid_w, 0
+ *   geom_f [R,5]  = start_w, start_h, bin_w, bin_h, count
+ *   tap_i / tap_f [R, 2 (y,x), max(PH,PW), max_grid, 2] = (lo, hi) / (pos, frac);
+ *   lo = hi = -1 for a coordinate outside the plane.  Device pointers. */
+int mobula_roialign_bookkeeping_f32(int device_id, void* stream, const float* bottom_rois,
+                                    int num_rois, int height, int width, int pooled_height,
+                                    int pooled_width, float spatial_scale, int sampling_ratio,
+                                    int32_t* geom_i, float* geom_f, int max_grid,
+                                    int32_t* tap_i, float* tap_f);
+
+/* Pinned host memory for callers that use MOBULA_ROIALIGN_HOST_BUFFERS. */
+void* mobula_host_alloc(size_t bytes);
+void mobula_host_free(void* ptr);
+
+/* Number of kernel launches issued by this library since load (all threads). */
+uint64_t mobula_roialign_launch_count(void);
+
+/* Name of the kernel family the last forward / backward call on this thread used
+ * ("gather", "plane", "deterministic", ...). */
+const char* mobula_roialign_last_algo(int backward);
+
+/* Frees the per-device workspaces. */
+void mobula_roialign_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOBULA_ROIALIGN_H_ */

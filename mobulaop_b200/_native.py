@@ -1,0 +1,118 @@
+"""ctypes binding of libmobula_roialign_sm100.so (ABI: include/mobula_roialign.h).
+
+There is no CPU, HIP or TVM fallback: if the library is missing or cannot be loaded the
+import of the launch path fails loudly.  (The reference picks a context per call and
+JIT-builds it, /root/reference/mobula/func.py:138-164.)
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+OK = 0
+ERR_INVALID_ARGUMENT = 1
+ERR_CUDA = 2
+ERR_UNSUPPORTED = 3
+
+BWD_ATOMIC = 0
+BWD_DETERMINISTIC = 1
+
+FLAG_ACCUMULATE = 1
+FLAG_HOST_BUFFERS = 2
+ALGO_SHIFT = 8
+ALGO_AUTO, ALGO_GATHER, ALGO_PLANE = 0, 1, 2
+ALGOS = {'auto': ALGO_AUTO, 'gather': ALGO_GATHER, 'plane': ALGO_PLANE}
+
+# every symbol include/mobula_roialign.h declares
+EXPORTED_SYMBOLS = (
+    'roi_align_forward_ab78de3c', 'roi_align_backward_f318a24e', 'set_device',
+    'mobula_roialign_abi_version', 'mobula_last_error', 'mobula_roialign_forward_f32',
+    'mobula_roialign_backward_f32', 'mobula_roialign_bookkeeping_f32', 'mobula_host_alloc',
+    'mobula_host_free', 'mobula_roialign_launch_count', 'mobula_roialign_last_algo',
+    'mobula_roialign_release',
+)
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def _declare(lib):
+    i32, f32, vp, u32 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_uint
+    lib.mobula_roialign_abi_version.restype = i32
+    lib.mobula_last_error.restype = ctypes.c_char_p
+    lib.mobula_roialign_forward_f32.restype = i32
+    lib.mobula_roialign_forward_f32.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32,
+                                                i32, f32, i32, u32]
+    lib.mobula_roialign_backward_f32.restype = i32
+    lib.mobula_roialign_backward_f32.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32,
+                                                 i32, f32, i32, i32, u32]
+    lib.mobula_roialign_bookkeeping_f32.restype = i32
+    lib.mobula_roialign_bookkeeping_f32.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, f32, i32,
+                                                    vp, vp, i32, vp, vp]
+    lib.mobula_host_alloc.restype = vp
+    lib.mobula_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.mobula_host_free.restype = None
+    lib.mobula_host_free.argtypes = [vp]
+    lib.mobula_roialign_launch_count.restype = ctypes.c_uint64
+    lib.mobula_roialign_last_algo.restype = ctypes.c_char_p
+    lib.mobula_roialign_last_algo.argtypes = [i32]
+    lib.mobula_roialign_release.restype = None
+    lib.set_device.restype = None
+    lib.set_device.argtypes = [i32]
+    # the two drop-in symbols keep the reference convention: no argtypes, callers pass
+    # explicit ctypes instances (mobula/func.py:248-255, 335-337)
+    lib.roi_align_forward_ab78de3c.restype = None
+    lib.roi_align_backward_f318a24e.restype = None
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Returns the loaded library; raises NativeLibraryError when it is not usable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise NativeLibraryError(
+            '%s is not built: run `python -m mobulaop_b200.build` (needs nvcc). '
+            'There is no CPU fallback for the ROIAlign path.' % path)
+    try:
+        lib = ctypes.CDLL(path)
+    except OSError as err:
+        raise NativeLibraryError('cannot load %s: %s' % (path, err))
+    missing = [s for s in EXPORTED_SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise NativeLibraryError('%s lacks symbols %s' % (path, missing))
+    _declare(lib)
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != OK:
+        msg = load().mobula_last_error().decode('utf-8', 'replace')
+        if status == ERR_INVALID_ARGUMENT:
+            raise ValueError(msg)
+        if status == ERR_UNSUPPORTED:
+            raise NotImplementedError(msg)
+        raise RuntimeError('CUDA failure in libmobula_roialign_sm100: ' + msg)
+
+
+def make_flags(accumulate=False, host=False, algo='auto'):
+    flags = (FLAG_ACCUMULATE if accumulate else 0) | (FLAG_HOST_BUFFERS if host else 0)
+    return flags | (ALGOS[algo] << ALGO_SHIFT)
+
+
+def launch_count():
+    return int(load().mobula_roialign_launch_count())
+
+
+def last_algo(backward=False):
+    return load().mobula_roialign_last_algo(1 if backward else 0).decode()

@@ -1,0 +1,448 @@
+// C-ABI of libmobula_roialign_sm100.so (see include/mobula_roialign.h).
+//
+// This file owns everything that is not a kernel: argument validation, the device
+// guard (reference: mobula/cpp/include/context/hip_ctx.h:95-103), the per-device
+// workspace, the host-buffer staging path, algorithm selection and the drop-in
+// symbols the reference's ctypes caller binds (mobula/func.py:155-156).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/mobula_roialign.h"
+#include "roialign_kernels.h"
+
+#define MOBULA_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace mobula_b200 {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static thread_local std::string t_error;
+static thread_local const char* t_algo[2] = {"none", "none"};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(MOBULA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
+                  __FILE__, __LINE__);                                                       \
+  } while (0)
+
+// Switches to `device` for the lifetime of the object and restores the previous one.
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(int device) : prev_(-1), status_(cudaSuccess) {
+    status_ = cudaGetDevice(&prev_);
+    if (status_ == cudaSuccess && device >= 0 && device != prev_) {
+      status_ = cudaSetDevice(device);
+      switched_ = status_ == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched_) cudaSetDevice(prev_);
+  }
+  cudaError_t status() const { return status_; }
+  int current(int requested) const { return requested >= 0 ? requested : prev_; }
+
+ private:
+  int prev_;
+  cudaError_t status_;
+  bool switched_ = false;
+};
+
+// ---- per-device state ------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+
+struct Buffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  // Grow-only; the old block is released on the stream so in-flight work finishes first.
+  cudaError_t reserve(size_t need, cudaStream_t stream) {
+    if (need <= bytes) return cudaSuccess;
+    if (ptr) {
+      cudaError_t e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess) return e;
+      e = cudaFree(ptr);
+      if (e != cudaSuccess) return e;
+      ptr = nullptr;
+      bytes = 0;
+    }
+    const size_t rounded = (need + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    cudaError_t e = cudaMalloc(&ptr, rounded);
+    if (e == cudaSuccess) bytes = rounded;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+};
+
+struct DeviceState {
+  std::mutex mu;
+  bool probed = false;
+  int num_sms = 0;
+  int smem_optin = 0;
+  Buffer workspace;            // ROI order tables / axis tables of the plane + det kernels
+  Buffer stage[4];             // host-buffer path: data/dy, rois, out/dx, spare
+};
+static DeviceState g_dev[kMaxDevices];
+
+static int probe(DeviceState& st, int device) {
+  if (st.probed) return MOBULA_OK;
+  CUDA_TRY(cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, device));
+  CUDA_TRY(cudaDeviceGetAttribute(&st.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  st.probed = true;
+  return MOBULA_OK;
+}
+
+static int check_common(const void* a, const void* b, const void* c, int num_rois, int channels,
+                        int height, int width, int pooled_h, int pooled_w) {
+  if (num_rois < 0 || channels < 0 || height <= 0 || width <= 0 || pooled_h <= 0 || pooled_w <= 0)
+    return fail(MOBULA_ERR_INVALID_ARGUMENT,
+                "bad shape: rois=%d channels=%d plane=%dx%d pooled=%dx%d", num_rois, channels,
+                height, width, pooled_h, pooled_w);
+  if ((long long)height * width > 0x7fffffffLL / 4)
+    return fail(MOBULA_ERR_UNSUPPORTED, "feature-map plane %dx%d too large", height, width);
+  if (num_rois > 0 && channels > 0 && (!a || !b || !c))
+    return fail(MOBULA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  return MOBULA_OK;
+}
+
+// Largest batch index + 1 over host-resident rois: the reference ABI never passes N
+// (ROIAlign.cpp:9-16), the host-buffer path needs it to size its copies.
+static int images_from_host_rois(const float* rois, int num_rois) {
+  int n = 0;
+  for (int r = 0; r < num_rois; ++r) {
+    const int b = (int)rois[(size_t)r * 5];
+    if (b + 1 > n) n = b + 1;
+  }
+  return n;
+}
+
+static unsigned algo_of(unsigned flags) {
+  return (flags & MOBULA_ROIALIGN_ALGO_MASK) >> MOBULA_ROIALIGN_ALGO_SHIFT;
+}
+
+// ---- device-pointer implementations --------------------------------------------------
+static int forward_device(DeviceState& st, int device, cudaStream_t stream, const float* data,
+                          const float* rois, float* out, const RoiAlignArgs& a, unsigned flags) {
+  (void)st;
+  (void)device;
+  const int accumulate = (flags & MOBULA_ROIALIGN_ACCUMULATE) ? 1 : 0;
+  const unsigned algo = algo_of(flags);
+  if (algo != MOBULA_ROIALIGN_ALGO_AUTO && algo != MOBULA_ROIALIGN_ALGO_GATHER)
+    return fail(MOBULA_ERR_UNSUPPORTED, "forward algorithm %u is not available", algo);
+  t_algo[0] = "gather";
+  CUDA_TRY(launch_fwd_gather(a, data, out, accumulate, stream));
+  return MOBULA_OK;
+}
+
+static int backward_device(DeviceState& st, int device, cudaStream_t stream, const float* dy,
+                           const float* rois, float* dx, const RoiAlignArgs& a, int mode,
+                           unsigned flags) {
+  (void)st;
+  (void)device;
+  (void)rois;
+  const int accumulate = (flags & MOBULA_ROIALIGN_ACCUMULATE) ? 1 : 0;
+  const unsigned algo = algo_of(flags);
+  if (mode != MOBULA_ROIALIGN_BWD_ATOMIC && mode != MOBULA_ROIALIGN_BWD_DETERMINISTIC)
+    return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward mode %d", mode);
+  if (!accumulate && a.num_images < 0)
+    return fail(MOBULA_ERR_INVALID_ARGUMENT,
+                "backward without MOBULA_ROIALIGN_ACCUMULATE needs num_images >= 0");
+  if (mode == MOBULA_ROIALIGN_BWD_DETERMINISTIC)
+    return fail(MOBULA_ERR_UNSUPPORTED, "deterministic backward is not available yet");
+  if (algo != MOBULA_ROIALIGN_ALGO_AUTO && algo != MOBULA_ROIALIGN_ALGO_GATHER)
+    return fail(MOBULA_ERR_UNSUPPORTED, "backward algorithm %u is not available", algo);
+  t_algo[1] = "gather";
+  if (!accumulate) {
+    const size_t bytes = (size_t)a.num_images * a.channels * a.height * a.width * sizeof(float);
+    if (bytes) CUDA_TRY(cudaMemsetAsync(dx, 0, bytes, stream));
+  }
+  CUDA_TRY(launch_bwd_gather(a, dy, dx, stream));
+  return MOBULA_OK;
+}
+
+static RoiAlignArgs make_args(const float* rois, int num_rois, int num_images, int channels,
+                              int height, int width, int pooled_h, int pooled_w, float scale,
+                              int sampling_ratio) {
+  RoiAlignArgs a;
+  a.rois = rois;
+  a.num_rois = num_rois;
+  a.num_images = num_images;
+  a.channels = channels;
+  a.height = height;
+  a.width = width;
+  a.pooled_h = pooled_h;
+  a.pooled_w = pooled_w;
+  a.scale = scale;
+  a.sampling_ratio = sampling_ratio;
+  return a;
+}
+
+}  // namespace mobula_b200
+
+using namespace mobula_b200;
+
+// ---------------------------------------------------------------------------------------
+// v2 entry points
+// ---------------------------------------------------------------------------------------
+MOBULA_EXPORT int mobula_roialign_abi_version(void) { return MOBULA_ROIALIGN_ABI_VERSION; }
+
+MOBULA_EXPORT const char* mobula_last_error(void) { return t_error.c_str(); }
+
+MOBULA_EXPORT uint64_t mobula_roialign_launch_count(void) {
+  return g_launches.load(std::memory_order_relaxed);
+}
+
+MOBULA_EXPORT const char* mobula_roialign_last_algo(int backward) { return t_algo[backward ? 1 : 0]; }
+
+MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, const float* bottom_data,
+                                              const float* bottom_rois, float* top_data,
+                                              int num_rois, int num_images, int channels, int height,
+                                              int width, int pooled_height, int pooled_width,
+                                              float spatial_scale, int sampling_ratio,
+                                              unsigned flags) {
+  int rc = check_common(bottom_data, bottom_rois, top_data, num_rois, channels, height, width,
+                        pooled_height, pooled_width);
+  if (rc) return rc;
+  if (num_rois == 0 || channels == 0) return MOBULA_OK;
+  DeviceGuard guard(device_id);
+  if (guard.status() != cudaSuccess)
+    return fail(MOBULA_ERR_CUDA, "cannot select device %d: %s", device_id,
+                cudaGetErrorString(guard.status()));
+  const int device = guard.current(device_id);
+  if (device < 0 || device >= kMaxDevices) return fail(MOBULA_ERR_INVALID_ARGUMENT, "device %d", device);
+  DeviceState& st = g_dev[device];
+  std::lock_guard<std::mutex> lock(st.mu);
+  if ((rc = probe(st, device))) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+
+  if (!(flags & MOBULA_ROIALIGN_HOST_BUFFERS)) {
+    const RoiAlignArgs a = make_args(bottom_rois, num_rois, num_images, channels, height, width,
+                                     pooled_height, pooled_width, spatial_scale, sampling_ratio);
+    return forward_device(st, device, stream, bottom_data, bottom_rois, top_data, a, flags);
+  }
+
+  // host buffers: stage in, run, stage out, synchronise
+  const int n_img = num_images >= 0 ? num_images : images_from_host_rois(bottom_rois, num_rois);
+  const size_t data_bytes = (size_t)n_img * channels * height * width * sizeof(float);
+  const size_t rois_bytes = (size_t)num_rois * 5 * sizeof(float);
+  const size_t out_bytes = (size_t)num_rois * channels * pooled_height * pooled_width * sizeof(float);
+  CUDA_TRY(st.stage[0].reserve(data_bytes, stream));
+  CUDA_TRY(st.stage[1].reserve(rois_bytes, stream));
+  CUDA_TRY(st.stage[2].reserve(out_bytes, stream));
+  float* d_data = (float*)st.stage[0].ptr;
+  float* d_rois = (float*)st.stage[1].ptr;
+  float* d_out = (float*)st.stage[2].ptr;
+  if (data_bytes) CUDA_TRY(cudaMemcpyAsync(d_data, bottom_data, data_bytes, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(d_rois, bottom_rois, rois_bytes, cudaMemcpyHostToDevice, stream));
+  if (flags & MOBULA_ROIALIGN_ACCUMULATE)
+    CUDA_TRY(cudaMemcpyAsync(d_out, top_data, out_bytes, cudaMemcpyHostToDevice, stream));
+  const RoiAlignArgs a = make_args(d_rois, num_rois, n_img, channels, height, width, pooled_height,
+                                   pooled_width, spatial_scale, sampling_ratio);
+  if ((rc = forward_device(st, device, stream, d_data, d_rois, d_out, a, flags))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(top_data, d_out, out_bytes, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  return MOBULA_OK;
+}
+
+MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream_, const float* top_diff,
+                                               const float* bottom_rois, float* bottom_diff,
+                                               int num_rois, int num_images, int channels,
+                                               int height, int width, int pooled_height,
+                                               int pooled_width, float spatial_scale,
+                                               int sampling_ratio, int mode, unsigned flags) {
+  int rc = check_common(top_diff, bottom_rois, bottom_diff, num_rois, channels, height, width,
+                        pooled_height, pooled_width);
+  if (rc) return rc;
+  const bool accumulate = flags & MOBULA_ROIALIGN_ACCUMULATE;
+  if (channels == 0) return MOBULA_OK;
+  if (num_rois == 0 && (accumulate || num_images <= 0)) return MOBULA_OK;
+  if (!bottom_diff) return fail(MOBULA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  DeviceGuard guard(device_id);
+  if (guard.status() != cudaSuccess)
+    return fail(MOBULA_ERR_CUDA, "cannot select device %d: %s", device_id,
+                cudaGetErrorString(guard.status()));
+  const int device = guard.current(device_id);
+  if (device < 0 || device >= kMaxDevices) return fail(MOBULA_ERR_INVALID_ARGUMENT, "device %d", device);
+  DeviceState& st = g_dev[device];
+  std::lock_guard<std::mutex> lock(st.mu);
+  if ((rc = probe(st, device))) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+
+  if (!(flags & MOBULA_ROIALIGN_HOST_BUFFERS)) {
+    const RoiAlignArgs a = make_args(bottom_rois, num_rois, num_images, channels, height, width,
+                                     pooled_height, pooled_width, spatial_scale, sampling_ratio);
+    return backward_device(st, device, stream, top_diff, bottom_rois, bottom_diff, a, mode, flags);
+  }
+
+  const int n_img = num_images >= 0 ? num_images : images_from_host_rois(bottom_rois, num_rois);
+  const size_t dx_bytes = (size_t)n_img * channels * height * width * sizeof(float);
+  const size_t rois_bytes = (size_t)num_rois * 5 * sizeof(float);
+  const size_t dy_bytes = (size_t)num_rois * channels * pooled_height * pooled_width * sizeof(float);
+  CUDA_TRY(st.stage[0].reserve(dy_bytes, stream));
+  CUDA_TRY(st.stage[1].reserve(rois_bytes, stream));
+  CUDA_TRY(st.stage[2].reserve(dx_bytes, stream));
+  float* d_dy = (float*)st.stage[0].ptr;
+  float* d_rois = (float*)st.stage[1].ptr;
+  float* d_dx = (float*)st.stage[2].ptr;
+  if (dy_bytes) CUDA_TRY(cudaMemcpyAsync(d_dy, top_diff, dy_bytes, cudaMemcpyHostToDevice, stream));
+  if (rois_bytes) CUDA_TRY(cudaMemcpyAsync(d_rois, bottom_rois, rois_bytes, cudaMemcpyHostToDevice, stream));
+  if (accumulate && dx_bytes)
+    CUDA_TRY(cudaMemcpyAsync(d_dx, bottom_diff, dx_bytes, cudaMemcpyHostToDevice, stream));
+  const RoiAlignArgs a = make_args(d_rois, num_rois, n_img, channels, height, width, pooled_height,
+                                   pooled_width, spatial_scale, sampling_ratio);
+  if ((rc = backward_device(st, device, stream, d_dy, d_rois, d_dx, a, mode, flags))) return rc;
+  if (dx_bytes) CUDA_TRY(cudaMemcpyAsync(bottom_diff, d_dx, dx_bytes, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  return MOBULA_OK;
+}
+
+MOBULA_EXPORT int mobula_roialign_bookkeeping_f32(int device_id, void* stream_, const float* bottom_rois,
+                                                  int num_rois, int height, int width,
+                                                  int pooled_height, int pooled_width,
+                                                  float spatial_scale, int sampling_ratio,
+                                                  int32_t* geom_i, float* geom_f, int max_grid,
+                                                  int32_t* tap_i, float* tap_f) {
+  if (num_rois < 0 || height <= 0 || width <= 0 || pooled_height <= 0 || pooled_width <= 0)
+    return fail(MOBULA_ERR_INVALID_ARGUMENT, "bad shape");
+  if (num_rois == 0) return MOBULA_OK;
+  if (!bottom_rois || !geom_i || !geom_f || (max_grid > 0 && (!tap_i || !tap_f)))
+    return fail(MOBULA_ERR_INVALID_ARGUMENT, "null pointer");
+  DeviceGuard guard(device_id);
+  if (guard.status() != cudaSuccess)
+    return fail(MOBULA_ERR_CUDA, "cannot select device %d: %s", device_id,
+                cudaGetErrorString(guard.status()));
+  const RoiAlignArgs a = make_args(bottom_rois, num_rois, -1, 0, height, width, pooled_height,
+                                   pooled_width, spatial_scale, sampling_ratio);
+  CUDA_TRY(launch_bookkeeping(a, geom_i, geom_f, max_grid, tap_i, tap_f, (cudaStream_t)stream_));
+  return MOBULA_OK;
+}
+
+MOBULA_EXPORT void* mobula_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+MOBULA_EXPORT void mobula_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+MOBULA_EXPORT void mobula_roialign_release(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (int d = 0; d < count && d < kMaxDevices; ++d) {
+    DeviceState& st = g_dev[d];
+    std::lock_guard<std::mutex> lock(st.mu);
+    if (!st.workspace.ptr && !st.stage[0].ptr && !st.stage[1].ptr && !st.stage[2].ptr &&
+        !st.stage[3].ptr)
+      continue;
+    cudaSetDevice(d);
+    cudaDeviceSynchronize();
+    st.workspace.release();
+    for (Buffer& b : st.stage) b.release();
+  }
+  cudaSetDevice(prev);
+}
+
+// ---------------------------------------------------------------------------------------
+// drop-in symbols of the reference ABI
+// ---------------------------------------------------------------------------------------
+// The reference aborts the process on a native error (logging.h:23-26, hip_ctx.h:49-60).
+static void die_like_reference(const char* where, int rc) {
+  fprintf(stderr, "[mobula_roialign] %s failed (%d): %s\n", where, rc, mobula_last_error());
+  fflush(stderr);
+  exit(-1);
+}
+
+static bool host_context(int device_id) { return device_id < 0; }
+
+MOBULA_EXPORT void roi_align_forward_ab78de3c(const int device_id, const int nthreads,
+                                              const float* bottom_data, const float spatial_scale,
+                                              const int channels, const int height, const int width,
+                                              const int pooled_height, const int pooled_width,
+                                              const int sampling_ratio, const float* bottom_rois,
+                                              float* top_data) {
+  const long long per_roi = (long long)channels * pooled_height * pooled_width;
+  if (nthreads <= 0 || per_roi <= 0) return;
+  const int num_rois = (int)(nthreads / per_roi);   // R is implicit in the reference ABI
+  unsigned flags = host_context(device_id) ? MOBULA_ROIALIGN_HOST_BUFFERS : 0u;
+  int rc = mobula_roialign_forward_f32(device_id, nullptr, bottom_data, bottom_rois, top_data,
+                                       num_rois, -1, channels, height, width, pooled_height,
+                                       pooled_width, spatial_scale, sampling_ratio, flags);
+  if (rc == MOBULA_OK && !host_context(device_id)) {
+    DeviceGuard guard(device_id);
+    if (cudaStreamSynchronize(nullptr) != cudaSuccess) {
+      fail(MOBULA_ERR_CUDA, "synchronize: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = MOBULA_ERR_CUDA;
+    }
+  }
+  if (rc != MOBULA_OK) die_like_reference("roi_align_forward", rc);
+}
+
+MOBULA_EXPORT void roi_align_backward_f318a24e(const int device_id, const int nthreads,
+                                               const float* top_diff, const float spatial_scale,
+                                               const int channels, const int height, const int width,
+                                               const int pooled_height, const int pooled_width,
+                                               const int sampling_ratio, float* bottom_diff,
+                                               const float* bottom_rois) {
+  const long long per_roi = (long long)channels * pooled_height * pooled_width;
+  if (nthreads <= 0 || per_roi <= 0) return;
+  const int num_rois = (int)(nthreads / per_roi);
+  // The reference kernel adds into a buffer its caller zeroed (ROIAlign.py:33-34).
+  unsigned flags = MOBULA_ROIALIGN_ACCUMULATE;
+  if (host_context(device_id)) flags |= MOBULA_ROIALIGN_HOST_BUFFERS;
+  int rc = mobula_roialign_backward_f32(device_id, nullptr, top_diff, bottom_rois, bottom_diff,
+                                        num_rois, -1, channels, height, width, pooled_height,
+                                        pooled_width, spatial_scale, sampling_ratio,
+                                        MOBULA_ROIALIGN_BWD_ATOMIC, flags);
+  if (rc == MOBULA_OK && !host_context(device_id)) {
+    DeviceGuard guard(device_id);
+    if (cudaStreamSynchronize(nullptr) != cudaSuccess) {
+      fail(MOBULA_ERR_CUDA, "synchronize: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = MOBULA_ERR_CUDA;
+    }
+  }
+  if (rc != MOBULA_OK) die_like_reference("roi_align_backward", rc);
+}
+
+MOBULA_EXPORT void set_device(const int device_id) {
+  if (device_id < 0) return;
+  int current = -1;
+  if (cudaGetDevice(&current) != cudaSuccess || current != device_id) {
+    if (cudaSetDevice(device_id) != cudaSuccess) {
+      fail(MOBULA_ERR_CUDA, "cudaSetDevice(%d): %s", device_id,
+           cudaGetErrorString(cudaGetLastError()));
+      die_like_reference("set_device", MOBULA_ERR_CUDA);
+    }
+  }
+}

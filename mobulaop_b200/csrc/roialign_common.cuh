@@ -1,0 +1,101 @@
+// ROI / sample decoding shared by every ROIAlign kernel.
+//
+// The integer results of this arithmetic (grid sizes, tap indices, the
+// inside/outside decision) are discontinuous in the inputs, so it has to round
+// exactly like the reference's CPU build, which has no FMA contraction:
+// every operation below is an explicit round-to-nearest intrinsic and the
+// translation unit is compiled with -fmad=false as a second line of defence.
+//
+// Reference arithmetic: /root/reference/opzoo/ROIAlign/ROIAlign.cpp:24-65 and
+// /root/reference/opzoo/ROIAlign/bilinear.h:15-54.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mobula_b200 {
+
+struct RoiGeom {
+  int batch;            // ROIAlign.cpp:25
+  float start_w, start_h;
+  float bin_w, bin_h;   // ROIAlign.cpp:40-41
+  int grid_h, grid_w;   // ROIAlign.cpp:47-51
+  float count;          // ROIAlign.cpp:54
+};
+
+__device__ __forceinline__ RoiGeom roi_decode(const float* __restrict__ roi, float scale,
+                                              int pooled_h, int pooled_w, int sampling_ratio) {
+  RoiGeom g;
+  const float r0 = __ldg(roi + 0), r1 = __ldg(roi + 1), r2 = __ldg(roi + 2);
+  const float r3 = __ldg(roi + 3), r4 = __ldg(roi + 4);
+  g.batch = __float2int_rz(r0);
+  g.start_w = __fmul_rn(r1, scale);
+  g.start_h = __fmul_rn(r2, scale);
+  const float end_w = __fmul_rn(r3, scale);
+  const float end_h = __fmul_rn(r4, scale);
+  const float roi_w = fmaxf(__fsub_rn(end_w, g.start_w), 1.0f);
+  const float roi_h = fmaxf(__fsub_rn(end_h, g.start_h), 1.0f);
+  g.bin_h = __fdiv_rn(roi_h, (float)pooled_h);
+  g.bin_w = __fdiv_rn(roi_w, (float)pooled_w);
+  if (sampling_ratio > 0) {
+    g.grid_h = g.grid_w = sampling_ratio;
+  } else {
+    g.grid_h = __float2int_rz(ceilf(g.bin_h));
+    g.grid_w = __float2int_rz(ceilf(g.bin_w));
+  }
+  g.count = (float)(g.grid_h * g.grid_w);
+  return g;
+}
+
+// (start + p*bin) + (((i + .5) * bin) / grid), ROIAlign.cpp:59-65
+__device__ __forceinline__ float sample_pos(float start, int p, float bin, int i, int grid) {
+  const float base = __fadd_rn(start, __fmul_rn((float)p, bin));
+  const float off = __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)grid);
+  return __fadd_rn(base, off);
+}
+
+struct AxisTap {
+  int lo, hi;     // pixel indices
+  float wl, wh;   // weight of hi (fraction) and of lo (1 - fraction)
+  bool valid;     // false: bilinear.h:15-18 rejects the sample
+};
+
+__device__ __forceinline__ AxisTap axis_decode(float pos, int extent) {
+  AxisTap t;
+  t.valid = !(pos < -1.0f || pos > (float)extent);
+  if (pos <= 0.0f) pos = 0.0f;
+  t.lo = __float2int_rz(pos);
+  if (t.lo >= extent - 1) {
+    t.hi = t.lo = extent - 1;
+    pos = (float)t.lo;
+  } else {
+    t.hi = t.lo + 1;
+  }
+  t.wl = __fsub_rn(pos, (float)t.lo);
+  t.wh = __fsub_rn(1.0f, t.wl);
+  return t;
+}
+
+// w1*v1 + w2*v2 + w3*v3 + w4*v4, left to right, no contraction (bilinear.h:56)
+__device__ __forceinline__ float tap_sum(float w1, float v1, float w2, float v2, float w3,
+                                         float v3, float w4, float v4) {
+  float s = __fadd_rn(__fmul_rn(w1, v1), __fmul_rn(w2, v2));
+  s = __fadd_rn(s, __fmul_rn(w3, v3));
+  return __fadd_rn(s, __fmul_rn(w4, v4));
+}
+
+// (dtop * w) / count, ROIAlign.cpp:143-146.  When count is a power of two the
+// division is an exact scaling and equals multiplication by the exact reciprocal.
+struct CountDiv {
+  float count, inv;
+  bool pow2;
+  __device__ __forceinline__ explicit CountDiv(int n) {
+    count = (float)n;
+    pow2 = n > 0 && (n & (n - 1)) == 0;
+    inv = pow2 ? __fdiv_rn(1.0f, count) : 0.0f;
+  }
+  __device__ __forceinline__ float operator()(float x) const {
+    return pow2 ? __fmul_rn(x, inv) : __fdiv_rn(x, count);
+  }
+};
+
+}  // namespace mobula_b200

@@ -1,0 +1,209 @@
+"""`mobula.func.<kernel>` launch path for the ROIAlign kernels.
+
+Keeps the calling convention of the reference's dispatcher
+(/root/reference/mobula/func.py:190-265 `MobulaFunc.__call__`, :138-164
+`CFuncDef.__call__`): positional/keyword arguments in the order of the C++ kernel
+signature (/root/reference/opzoo/ROIAlign/ROIAlign.cpp:9-16, 78-83), template type T
+bound from the first tensor and enforced on the others, every tensor on one device,
+non-contiguous tensors copied and (if written) copied back.
+
+What changed: there is no JIT, no per-context loader and no CPU/HIP/TVM branch -- both
+kernels resolve to libmobula_roialign_sm100.so (include/mobula_roialign.h).  Device
+tensors are launched on the framework's current CUDA stream without a synchronise;
+host tensors (NumPy, CPU torch) are staged through the GPU by the library and the call
+returns when the result is in host memory.
+
+Extra keyword-only arguments (absent from the reference): `mode` ('atomic' |
+'deterministic', backward only), `accumulate` (default True for backward = the
+reference semantics "adds into a caller-zeroed buffer", False for forward), `algo`.
+"""
+import ctypes
+
+from . import _native
+from . import glue
+from .config import config
+
+__all__ = ['MobulaFunc', 'bind']
+
+_INT, _SCALAR_T, _IN_T, _OUT_T = 'int', 'T', 'const T*', 'T*'
+
+_COMMON = [('spatial_scale', _SCALAR_T), ('channels', _INT), ('height', _INT), ('width', _INT),
+           ('pooled_height', _INT), ('pooled_width', _INT), ('sampling_ratio', _INT)]
+
+# name -> (parameters in reference order, launcher)
+_SIGNATURES = {
+    'roi_align_forward': [('nthreads', _INT), ('bottom_data', _IN_T)] + _COMMON +
+                         [('bottom_rois', _IN_T), ('top_data', _OUT_T)],
+    'roi_align_backward': [('nthreads', _INT), ('top_diff', _IN_T)] + _COMMON +
+                          [('bottom_diff', _OUT_T), ('bottom_rois', _IN_T)],
+}
+
+_SUPPORTED_T = (ctypes.c_float,)
+
+
+class _TensorArg(object):
+    __slots__ = ('var', 'view', 'ptr', 'keep', 'writeback')
+
+    def __init__(self, var, view):
+        self.var = var
+        self.view = view
+        self.ptr = None
+        self.keep = None
+        self.writeback = False
+
+    def resolve(self, mutable):
+        p = self.view.data_ptr
+        if isinstance(p, (tuple, list)):
+            p, self.keep = p
+            self.writeback = mutable
+        self.ptr = p
+        return p
+
+    def finish(self):
+        if self.writeback:
+            self.var[:] = self.keep
+
+
+class MobulaFunc(object):
+    """One native kernel, callable with framework tensors."""
+
+    def __init__(self, name, params):
+        self.name = name
+        self.params = list(params)
+        self.arg_names = [p[0] for p in self.params]
+
+    def __repr__(self):
+        return '<mobula.func.%s(%s)>' % (self.name, ', '.join('%s %s' % (k, n) for n, k in self.params))
+
+    def _collect(self, args, kwargs):
+        args = list(args)
+        if len(args) > len(self.params):
+            raise TypeError('%s takes %d arguments, %d given' % (self.name, len(self.params), len(args)))
+        for name in self.arg_names[len(args):]:
+            if name not in kwargs:
+                raise TypeError('%s: missing argument `%s`' % (self.name, name))
+            args.append(kwargs.pop(name))
+        return args
+
+    def __call__(self, *args, **kwargs):
+        mode = kwargs.pop('mode', None)
+        accumulate = kwargs.pop('accumulate', None)
+        algo = kwargs.pop('algo', None)
+        args = self._collect(args, kwargs)
+        if kwargs:
+            raise TypeError('%s: unexpected arguments %s' % (self.name, sorted(kwargs)))
+
+        values = {}
+        tensors = {}
+        bound_t = None
+        dev_id = None
+        any_tensor_dev = False
+        stream = 0
+        for (name, kind), var in zip(self.params, args):
+            if kind in (_IN_T, _OUT_T):
+                glue_mod = glue.backend.get_var_glue(var)
+                if glue_mod is None:
+                    raise TypeError('Unmatched parameters list of the function `%s`: `%s` must be a '
+                                    'tensor, got %s' % (self.name, name, type(var)))
+                view = glue_mod.Tensor(var)
+                ctype = view.ctype
+                if bound_t is None:
+                    bound_t = ctype
+                elif ctype is not bound_t:
+                    raise TypeError('Expected Type %s instead of %s for `%s`' % (bound_t, ctype, name))
+                tdev = view.dev_id
+                if tdev is not None:
+                    if dev_id is not None and tdev != dev_id:
+                        raise ValueError("Don't use multiple devices in a call :-(")
+                    dev_id = tdev
+                    stream = view.stream
+                    any_tensor_dev = True
+                tensors[name] = _TensorArg(var, view)
+            elif kind == _INT:
+                values[name] = int(var)
+            else:
+                values[name] = float(var.value) if hasattr(var, '_type_') else float(var)
+        if bound_t not in _SUPPORTED_T:
+            raise TypeError('%s is instantiated for float only (no %s kernel in '
+                            'libmobula_roialign_sm100)' % (self.name, bound_t))
+        host = not any_tensor_dev
+        if not host:
+            for t in tensors.values():
+                if t.view.dev_id is None:
+                    raise ValueError('%s: host and device tensors mixed in one call' % self.name)
+        launcher = _launch_forward if self.name == 'roi_align_forward' else _launch_backward
+        launcher(values, tensors, -1 if dev_id is None else dev_id, stream, host, mode, accumulate,
+                 algo or config.ROIALIGN_ALGO)
+        for t in tensors.values():
+            t.finish()
+        return None
+
+    def build(self, ctx=None, template_types=None):
+        """The reference pre-compiles a template instance here (func.py:351-405); the
+        library is prebuilt, so this only checks that it loads."""
+        _native.load()
+
+
+def _rows(values, per_roi_name='nthreads'):
+    per_roi = values['channels'] * values['pooled_height'] * values['pooled_width']
+    return values[per_roi_name] // per_roi if per_roi > 0 else 0
+
+
+def _vp(p):
+    return p if isinstance(p, ctypes.c_void_p) else ctypes.c_void_p(p)
+
+
+def _launch_forward(v, t, dev_id, stream, host, mode, accumulate, algo):
+    if mode is not None:
+        raise TypeError('roi_align_forward has no `mode`')
+    lib = _native.load()
+    data, rois, out = t['bottom_data'], t['bottom_rois'], t['top_data']
+    num_rois = _rows(v)
+    shape = data.view.shape
+    num_images = shape[0] if len(shape) == 4 else -1
+    flags = _native.make_flags(accumulate=bool(accumulate), host=host, algo=algo)
+    _native.check(lib.mobula_roialign_forward_f32(
+        dev_id, _vp(stream), _vp(data.resolve(False)), _vp(rois.resolve(False)),
+        _vp(out.resolve(True)), num_rois, num_images, v['channels'], v['height'], v['width'],
+        v['pooled_height'], v['pooled_width'], v['spatial_scale'], v['sampling_ratio'], flags))
+
+
+def _launch_backward(v, t, dev_id, stream, host, mode, accumulate, algo):
+    lib = _native.load()
+    dy, rois, dx = t['top_diff'], t['bottom_rois'], t['bottom_diff']
+    if mode is None:
+        mode = 'deterministic' if config.ROIALIGN_DETERMINISTIC else 'atomic'
+    if mode not in ('atomic', 'deterministic'):
+        raise ValueError("mode must be 'atomic' or 'deterministic'")
+    if accumulate is None:
+        accumulate = True       # reference kernel semantics (ROIAlign.cpp:148-157)
+    num_rois = _rows(v)
+    shape = dx.view.shape
+    num_images = shape[0] if len(shape) == 4 else -1
+    flags = _native.make_flags(accumulate=bool(accumulate), host=host, algo=algo)
+    _native.check(lib.mobula_roialign_backward_f32(
+        dev_id, _vp(stream), _vp(dy.resolve(False)), _vp(rois.resolve(False)),
+        _vp(dx.resolve(True)), num_rois, num_images, v['channels'], v['height'], v['width'],
+        v['pooled_height'], v['pooled_width'], v['spatial_scale'], v['sampling_ratio'],
+        _native.BWD_DETERMINISTIC if mode == 'deterministic' else _native.BWD_ATOMIC, flags))
+
+
+_bound = {}
+
+
+def bind(names=None):
+    """Publishes kernels as module attributes, like the reference's `bind`
+    (func.py:411-425) does after parsing an operator's .cpp file."""
+    for name in (names or _SIGNATURES):
+        if name not in _SIGNATURES:
+            raise KeyError('no prebuilt kernel named %s' % name)
+        if name not in _bound:
+            _bound[name] = MobulaFunc(name, _SIGNATURES[name])
+        globals()[name] = _bound[name]
+    return _bound
+
+
+def __getattr__(name):
+    # kernels become visible after mobula.op.load('ROIAlign'), as in the reference
+    raise AttributeError("module 'mobula.func' has no attribute %r (did you call "
+                         "mobula.op.load('ROIAlign')?)" % name)

@@ -1,0 +1,47 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+def golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz'))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+    return dict(data=z['data'], rois=z['rois'], dy=z['dy'], pooled=tuple(int(v) for v in z['pooled']),
+                scale=float(z['scale']), sr=int(z['sr']), y=z['y'], dx=z['dx'])
+
+
+@pytest.fixture(scope='session')
+def oracle():
+    from oracle.roialign import COracle
+    return COracle()
+
+
+@pytest.fixture(scope='session')
+def native():
+    """The CUDA library through ctypes; building it needs nvcc, loading it needs no GPU."""
+    from mobulaop_b200 import _native, build
+    build.build()
+    return _native.load()
+
+
+def has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False

@@ -1,0 +1,211 @@
+"""Host-side mirror of the reference interface, exercised without a GPU: registry,
+adapters' argument handling, the launch path's type checks, config, sharding."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope='module')
+def mobula(native):
+    import mobula
+    mobula.op.load('ROIAlign')
+    return mobula
+
+
+def test_alias_package_is_the_implementation(mobula):
+    import mobulaop_b200
+    import mobula.func as f1
+    import mobula.glue.backend as b1
+    assert mobula is mobulaop_b200
+    assert f1 is mobulaop_b200.func and b1 is mobulaop_b200.glue.backend
+    assert mobula.operator is mobula.op and mobula.function is mobula.func
+
+
+def test_load_publishes_op_and_kernels(mobula):
+    assert isinstance(mobula.op.ROIAlign, mobula.glue.MobulaOperator)
+    assert mobula.func.roi_align_forward.arg_names[:2] == ['nthreads', 'bottom_data']
+    # argument order of backward differs from forward (ROIAlign.cpp:82-83 vs :15-16)
+    assert mobula.func.roi_align_backward.arg_names[-2:] == ['bottom_diff', 'bottom_rois']
+    assert mobula.func.roi_align_forward.arg_names[-2:] == ['bottom_rois', 'top_data']
+    with pytest.raises(IOError):
+        mobula.op.load('NoSuchOperator')
+    with pytest.raises(AttributeError):
+        mobula.func.softmax_forward
+
+
+def test_infer_shape_and_ctor(mobula):
+    op = mobula.op.ROIAlign[np.ndarray](pooled_size=(3, 4), spatial_scale=0.5, sampling_ratio=0)
+    assert op.infer_shape([(5, 3, 16, 16), (7, 5)])[1] == [[7, 3, 3, 4]]
+    with pytest.raises(AssertionError):
+        op.infer_shape([(5, 3, 16, 16), (7, 4)])
+    with pytest.raises(AssertionError):
+        op.infer_shape([(3, 16, 16), (7, 5)])
+    assert mobula.op.ROIAlign[np.ndarray](pooled_size=7, spatial_scale=1., sampling_ratio=2).pooled_size == (7, 7)
+
+
+def test_split_inputs():
+    from mobulaop_b200.glue.common import split_inputs
+
+    class Op:
+        def forward(self, data, rois):
+            pass
+    a, b = object(), object()
+    assert split_inputs(Op, (a, b, 7), dict(k=1)) == ([a, b], [7], dict(k=1))
+    assert split_inputs(Op, (a,), dict(rois=b, k=1)) == ([a, b], [], dict(k=1))
+    assert split_inputs(Op, (), dict(data=a, rois=b)) == ([a, b], [], {})
+    with pytest.raises(AssertionError):
+        split_inputs(Op, (a,), dict(k=1))
+
+
+def test_backend_resolution(mobula):
+    import torch
+    be = mobula.glue.backend
+    assert be.get_var_glue(np.zeros(1)).__name__.endswith('numpy_glue')
+    assert be.get_var_glue(torch.zeros(1)).__name__.endswith('torch_glue')
+    assert be.get_var_glue(torch.nn.Parameter(torch.zeros(1))).__name__.endswith('torch_glue')
+    # the reference raises KeyError for numpy scalars; here: not a tensor
+    assert be.get_var_glue(np.int64(3)) is None
+    assert be.get_var_glue(3.5) is None
+    with pytest.raises(TypeError):
+        be.get_args_glue(np.zeros(1), torch.zeros(1))
+    with pytest.raises(ValueError):
+        mobula.op.ROIAlign(pooled_size=(7, 7), spatial_scale=1.0, sampling_ratio=2)
+
+
+def test_func_type_checks_happen_before_launch(mobula):
+    f = mobula.func.roi_align_forward
+    data = np.zeros((1, 2, 4, 4), np.float32)
+    rois = np.zeros((1, 5), np.float32)
+    out = np.zeros((1, 2, 2, 2), np.float32)
+    with pytest.raises(TypeError):          # template T bound to float, rois is double
+        f(out.size, data, 1.0, 2, 4, 4, 2, 2, 1, rois.astype(np.float64), out)
+    with pytest.raises(TypeError):          # double is not instantiated
+        f(out.size, data.astype(np.float64), 1.0, 2, 4, 4, 2, 2, 1, rois.astype(np.float64),
+          out.astype(np.float64))
+    with pytest.raises(TypeError):          # a scalar where a tensor is expected
+        f(out.size, 3, 1.0, 2, 4, 4, 2, 2, 1, rois, out)
+    with pytest.raises(TypeError):
+        f(out.size, data, 1.0, 2, 4, 4, 2, 2, 1, rois)
+    with pytest.raises(TypeError):
+        f(out.size, data, 1.0, 2, 4, 4, 2, 2, 1, rois, out, mode='atomic')
+    with pytest.raises(ValueError):
+        mobula.func.roi_align_backward(out.size, out, 1.0, 2, 4, 4, 2, 2, 1, data, rois, mode='fast')
+
+
+def test_config_contract(mobula):
+    cfg = mobula.config
+    assert cfg.GPU_BACKEND == 'cuda' and cfg.ROIALIGN_DETERMINISTIC is False
+    with pytest.raises(AttributeError):
+        cfg.NO_SUCH_FLAG = 1
+    with pytest.raises(TypeError):
+        cfg.ROIALIGN_DETERMINISTIC = 1
+    with pytest.raises(ValueError):
+        cfg.GPU_BACKEND = 'hip'
+    cfg.HOST_NUM_THREADS = 1            # reference build flag: accepted, inert
+    cfg.HOST_NUM_THREADS = 0
+    with cfg.TempConfig(ROIALIGN_DETERMINISTIC=True):
+        assert cfg.ROIALIGN_DETERMINISTIC is True
+    assert cfg.ROIALIGN_DETERMINISTIC is False
+    with pytest.raises(AttributeError):
+        with cfg.TempConfig(NOPE=1):
+            pass
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from mobulaop_b200 import _native, build
+    monkeypatch.setattr(_native, '_lib', None)
+    monkeypatch.setattr(build, 'LIB_PATH', str(tmp_path / 'absent.so'))
+    with pytest.raises(_native.NativeLibraryError):
+        _native.load()
+
+
+def test_testing_helpers():
+    from mobulaop_b200 import testing as T
+    a = np.array([1.0, -2.0, 0.0], np.float32)
+    assert T.ulp_distance(a, a).max() == 0
+    assert T.ulp_distance(a, np.nextafter(a, np.float32(9))).tolist() == [1, 1, 1]
+    assert T.ulp_distance(np.float32([0.0]), np.float32([-0.0])).tolist() == [0]
+    T.assert_within_ulp_or_rel(a, np.nextafter(np.nextafter(a, np.float32(9)), np.float32(9)))
+    with pytest.raises(AssertionError):
+        T.assert_within_ulp_or_rel(np.float32([1e-3]), np.float32([1.1e-3]))
+    with pytest.raises(AssertionError):
+        T.assert_bit_exact(np.float32([0.0]), np.float32([-0.0]))
+    T.assert_almost_equal(a, a, rtol=0, atol=0)
+    T.assert_almost_equal(a[:2], a[:2] * (1 + 1e-7), atol=1e-6)
+    with pytest.raises(AssertionError):
+        T.assert_almost_equal(a, a + 1e-3)
+
+
+# ---- sharding ----------------------------------------------------------------------
+def _random_rois(rng, R, N):
+    rois = rng.uniform(0, 100, (R, 5)).astype(np.float32)
+    rois[:, 0] = rng.integers(-1, N + 1, R)          # some out of range on both sides
+    return rois
+
+
+@pytest.mark.parametrize('N,G', [(1, 1), (2, 2), (5, 2), (8, 4), (64, 8), (3, 8)])
+def test_shards_partition_rois_exactly(N, G):
+    from mobulaop_b200 import sharding as S
+    rng = np.random.default_rng(N * 31 + G)
+    rois = _random_rois(rng, 200, N)
+    shards = S.make_shards(rois, N, G)
+    assert [s.image_begin for s in shards] == [(g * N) // G for g in range(G)]
+    assert shards[-1].image_end == N and shards[0].image_begin == 0
+    seen = np.concatenate([s.roi_index for s in shards])
+    valid = np.nonzero((rois[:, 0] >= 0) & (rois[:, 0] < N))[0]
+    assert sorted(seen.tolist()) == valid.tolist()             # every valid ROI exactly once
+    for s in shards:
+        assert (np.diff(s.roi_index) > 0).all()                 # stable: original order kept
+        np.testing.assert_array_equal(s.rois[:, 1:], rois[s.roi_index, 1:])
+        np.testing.assert_array_equal(s.rois[:, 0] + s.image_begin, rois[s.roi_index, 0])
+        assert ((s.rois[:, 0] >= 0) & (s.rois[:, 0] < max(s.num_images, 1))).all()
+        own = S.owner_of_images(S.batch_indices(rois[s.roi_index]), G, N)
+        assert (own == s.rank).all()
+    rows = rng.standard_normal((200, 3)).astype(np.float32)
+    back = S.assemble_rows(shards, [S.scatter_rows(s, rows) for s in shards], 200)
+    np.testing.assert_array_equal(back[valid], rows[valid])
+    assert not back[np.setdiff1d(np.arange(200), valid)].any()
+
+
+def test_sharded_result_equals_unsharded_bitwise(oracle):
+    """Per-image ROI ownership must not change a single bit of y or dX."""
+    from mobulaop_b200 import sharding as S
+    rng = np.random.default_rng(5)
+    N, C, H, W, R = 5, 3, 12, 15, 64
+    data = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    rois = _random_rois(rng, R, N)
+    rois[:, 1:] *= 0.6
+    dy = rng.standard_normal((R, C, 3, 3)).astype(np.float32)
+    keep = (rois[:, 0] >= 0) & (rois[:, 0] < N)
+    rois[~keep, 1:] = 1e6                   # make unowned ROIs contribute nothing anywhere
+    full_rois = rois.copy()
+    full_rois[~keep, 0] = 0
+    y = oracle.forward(data, full_rois, (3, 3), 0.25, 2)
+    dx = oracle.backward(dy, full_rois, data.shape, 0.25, 2)
+    for G in (2, 3):
+        shards = S.make_shards(rois, N, G)
+        ys, dxs = [], []
+        for s in shards:
+            local = np.ascontiguousarray(data[s.image_begin:s.image_end])
+            ys.append(oracle.forward(local, s.rois, (3, 3), 0.25, 2))
+            dxs.append(oracle.backward(S.scatter_rows(s, dy), s.rois, local.shape, 0.25, 2))
+        np.testing.assert_array_equal(S.assemble_rows(shards, ys, R), np.where(keep[:, None, None, None], y, 0))
+        np.testing.assert_array_equal(S.assemble_images(shards, dxs), dx)
+
+
+def test_two_rank_gloo_driver(tmp_path):
+    """world_size-2 run of the sharded driver on CPU (gloo): each rank computes its shard
+    with the oracle standing in for the kernels, results are gathered and compared."""
+    script = os.path.join(ROOT, 'tests', 'gloo_shard_worker.py')
+    env = dict(os.environ, PYTHONPATH=ROOT, MASTER_ADDR='127.0.0.1')
+    out = subprocess.run(
+        [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+         '--master-addr', '127.0.0.1', '--master-port', '29611', script, str(tmp_path)],
+        capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert 'SHARD-OK' in out.stdout

@@ -1,0 +1,391 @@
+"""Parity of the CUDA path against the oracle -- runs on the B200 box (`-m gpu`).
+
+All compute goes through the C-ABI of libmobula_roialign_sm100.so: directly with ctypes
+(v2 entry points and the reference's drop-in symbols) and through the mobula API.
+Gates (BASELINE.json): forward within 2 ULP or 1e-6 relative (the kernels are in fact
+bit-exact, which is asserted where it holds by construction), backward within 1e-5
+relative to the summand magnitude in atomic mode and bit-exact in deterministic mode,
+ROI bookkeeping bit-exact.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, has_cuda
+from mobulaop_b200 import workloads as WL
+from mobulaop_b200.testing import (assert_bit_exact, assert_scatter_close,
+                                   assert_within_ulp_or_rel)
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not has_cuda(), reason='needs a CUDA device')]
+
+ALGOS = ['gather', 'plane', 'auto']
+
+
+@pytest.fixture(scope='module')
+def torch():
+    import torch
+    return torch
+
+
+@pytest.fixture(scope='module')
+def api(native):
+    import mobula
+    mobula.op.load('ROIAlign')
+    return mobula
+
+
+class Direct(object):
+    """v2 C-ABI with device pointers held by torch tensors."""
+
+    def __init__(self, lib, torch, device=0):
+        self.lib, self.torch = lib, torch
+        self.device = device
+        self.dev = torch.device('cuda', device)
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def forward(self, data, rois, pooled, scale, sr, algo='auto', accumulate_into=None):
+        from mobulaop_b200 import _native
+        t = self.torch
+        d = t.from_numpy(data).to(self.dev)
+        r = t.from_numpy(rois).to(self.dev)
+        N, C, H, W = data.shape
+        R = rois.shape[0]
+        if accumulate_into is None:
+            out = t.full((R, C, pooled[0], pooled[1]), float('nan'), device=self.dev)
+        else:
+            out = t.from_numpy(accumulate_into).to(self.dev)
+        flags = _native.make_flags(accumulate=accumulate_into is not None, algo=algo)
+        _native.check(self.lib.mobula_roialign_forward_f32(
+            self.device, self._stream(), self._p(d), self._p(r), self._p(out), R, N, C, H, W,
+            pooled[0], pooled[1], scale, sr, flags))
+        t.cuda.synchronize(self.dev)
+        return out.cpu().numpy()
+
+    def backward(self, dy, rois, shape, scale, sr, mode='atomic', algo='auto', accumulate_into=None):
+        from mobulaop_b200 import _native
+        t = self.torch
+        g = t.from_numpy(dy).to(self.dev)
+        r = t.from_numpy(rois).to(self.dev)
+        N, C, H, W = shape
+        R, _, PH, PW = dy.shape
+        if accumulate_into is None:
+            dx = t.full(shape, float('nan'), device=self.dev)    # the zero-fill is the op's job
+        else:
+            dx = t.from_numpy(accumulate_into).to(self.dev)
+        flags = _native.make_flags(accumulate=accumulate_into is not None, algo=algo)
+        m = _native.BWD_DETERMINISTIC if mode == 'deterministic' else _native.BWD_ATOMIC
+        _native.check(self.lib.mobula_roialign_backward_f32(
+            self.device, self._stream(), self._p(g), self._p(r), self._p(dx), R, N, C, H, W, PH, PW,
+            scale, sr, m, flags))
+        t.cuda.synchronize(self.dev)
+        return dx.cpu().numpy()
+
+
+@pytest.fixture(scope='module')
+def direct(native, torch):
+    return Direct(native, torch)
+
+
+def _abs_sum(oracle, g):
+    return oracle.backward(np.abs(g['dy']), g['rois'], g['data'].shape, g['scale'], g['sr'])
+
+
+# ---- golden vectors produced by the unmodified reference -------------------------------
+@pytest.mark.parametrize('algo', ALGOS)
+@pytest.mark.parametrize('name', golden_names())
+def test_forward_golden(direct, name, algo):
+    g = load_golden(name)
+    y = direct.forward(g['data'], g['rois'], g['pooled'], g['scale'], g['sr'], algo=algo)
+    assert_within_ulp_or_rel(y, g['y'], ulp=2, rtol=1e-6)
+    assert_bit_exact(y, g['y'])         # same operations in the same order as the reference
+
+
+@pytest.mark.parametrize('algo', ALGOS)
+@pytest.mark.parametrize('name', golden_names())
+def test_backward_atomic_golden(direct, oracle, name, algo):
+    g = load_golden(name)
+    dx = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], algo=algo)
+    assert_scatter_close(dx, g['dx'], _abs_sum(oracle, g), rtol=1e-5)
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_backward_deterministic_golden_bit_exact(direct, name):
+    g = load_golden(name)
+    dx = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], mode='deterministic')
+    assert_bit_exact(dx, g['dx'])
+    again = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], mode='deterministic')
+    assert_bit_exact(dx, again)
+
+
+# ---- seeded workloads shaped like the BASELINE configs, oracle-sized -------------------
+def _sample(key, **kw):
+    return WL.CONFIGS[key].scaled(**kw)
+
+
+SAMPLES = {
+    'C2': lambda: _sample('C2', C=6, rois_per_image=96),
+    'C3': lambda: _sample('C3', N=3, C=4, rois_per_image=40),
+    'C5': lambda: _sample('C5', C=3, rois_per_image=150),
+    'C1': lambda: _sample('C1', C=24),
+}
+
+
+@pytest.mark.parametrize('algo', ALGOS)
+@pytest.mark.parametrize('key', sorted(SAMPLES))
+def test_seeded_workload_parity(direct, oracle, key, algo):
+    wl = SAMPLES[key]()
+    data, rois, dy = WL.make_inputs(wl, seed=17)
+    y_ref = oracle.forward(data, rois, wl.pooled, wl.scale, wl.sampling_ratio, threads=0)
+    y = direct.forward(data, rois, wl.pooled, wl.scale, wl.sampling_ratio, algo=algo)
+    assert_bit_exact(y, y_ref)
+    dx_ref = oracle.backward(dy, rois, data.shape, wl.scale, wl.sampling_ratio)
+    dx_abs = oracle.backward(np.abs(dy), rois, data.shape, wl.scale, wl.sampling_ratio)
+    dx = direct.backward(dy, rois, data.shape, wl.scale, wl.sampling_ratio, algo=algo)
+    assert_scatter_close(dx, dx_ref, dx_abs, rtol=1e-5)
+    dxd = direct.backward(dy, rois, data.shape, wl.scale, wl.sampling_ratio, mode='deterministic')
+    assert_bit_exact(dxd, dx_ref)
+
+
+# ---- ROI bookkeeping --------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['edges_sr0', 'edges_sr2', 'ref_value_test', 'fpn_14x14_sr2'])
+def test_bookkeeping_bit_exact(native, torch, oracle, name):
+    from mobulaop_b200 import _native
+    g = load_golden(name)
+    H, W = g['data'].shape[2:]
+    max_grid = 16
+    gi, gf, ti, tf = oracle.bookkeeping(g['rois'], (H, W), g['pooled'], g['scale'], g['sr'], max_grid)
+    dev = torch.device('cuda', 0)
+    R = len(g['rois'])
+    d_gi = torch.zeros(gi.shape, dtype=torch.int32, device=dev)
+    d_gf = torch.zeros(gf.shape, dtype=torch.float32, device=dev)
+    d_ti = torch.full(ti.shape, -7, dtype=torch.int32, device=dev)
+    d_tf = torch.full(tf.shape, float('nan'), dtype=torch.float32, device=dev)
+    r = torch.from_numpy(g['rois']).to(dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _native.check(native.mobula_roialign_bookkeeping_f32(
+        0, ctypes.c_void_p(0), p(r), R, H, W, g['pooled'][0], g['pooled'][1], g['scale'], g['sr'],
+        p(d_gi), p(d_gf), max_grid, p(d_ti), p(d_tf)))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d_gi.cpu().numpy(), gi)
+    assert_bit_exact(d_gf.cpu().numpy(), gf)
+    np.testing.assert_array_equal(d_ti.cpu().numpy(), ti)
+    assert_bit_exact(d_tf.cpu().numpy(), tf)
+
+
+# ---- edge cases ---------------------------------------------------------------------------
+def test_empty_and_tiny_inputs(direct, oracle):
+    data = np.random.default_rng(0).standard_normal((2, 3, 9, 11)).astype(np.float32)
+    none = np.zeros((0, 5), np.float32)
+    assert direct.forward(data, none, (7, 7), 0.5, 2).shape == (0, 3, 7, 7)
+    dx = direct.backward(np.zeros((0, 3, 7, 7), np.float32), none, data.shape, 0.5, 2)
+    assert dx.shape == data.shape and not dx.any()          # still zero-fills dX
+    dxd = direct.backward(np.zeros((0, 3, 7, 7), np.float32), none, data.shape, 0.5, 2,
+                          mode='deterministic')
+    assert not dxd.any()
+    one = np.array([[1, 2.5, 1.5, 14.0, 12.0]], np.float32)
+    for algo in ALGOS:
+        y = direct.forward(data[:, :1], one, (1, 1), 0.5, 1, algo=algo)
+        assert_bit_exact(y, oracle.forward(np.ascontiguousarray(data[:, :1]), one, (1, 1), 0.5, 1))
+
+
+@pytest.mark.parametrize('algo', ALGOS)
+def test_batch_index_out_of_range_is_ignored(direct, oracle, algo):
+    """With N known, ROIs pointing outside [0, N) read nothing and scatter nothing
+    (the reference would read out of bounds, ROIAlign.cpp:43-44)."""
+    rng = np.random.default_rng(1)
+    data = rng.standard_normal((2, 2, 10, 10)).astype(np.float32)
+    rois = np.array([[0, 1, 1, 8, 8], [2, 1, 1, 8, 8], [-1, 0, 0, 5, 5], [1, 0, 0, 9, 9]], np.float32)
+    dy = rng.standard_normal((4, 2, 2, 2)).astype(np.float32)
+    y = direct.forward(data, rois, (2, 2), 1.0, 2, algo=algo)
+    good = np.array([0, 3])
+    assert_bit_exact(y[good], oracle.forward(data, rois[good], (2, 2), 1.0, 2))
+    assert not y[[1, 2]].any()
+    for mode in ('atomic', 'deterministic'):
+        dx = direct.backward(dy, rois, data.shape, 1.0, 2, mode=mode, algo=algo)
+        ref = oracle.backward(np.ascontiguousarray(dy[good]), rois[good], data.shape, 1.0, 2)
+        np.testing.assert_allclose(dx, ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('algo', ALGOS)
+def test_accumulate_flags(direct, oracle, algo):
+    g = load_golden('edges_sr2')
+    base = np.random.default_rng(2).standard_normal(g['y'].shape).astype(np.float32)
+    y = direct.forward(g['data'], g['rois'], g['pooled'], g['scale'], g['sr'], algo=algo,
+                       accumulate_into=base)
+    assert_bit_exact(y, (base + g['y']).astype(np.float32))
+    dbase = np.random.default_rng(3).standard_normal(g['dx'].shape).astype(np.float32)
+    dx = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], algo=algo,
+                         accumulate_into=dbase)
+    np.testing.assert_allclose(dx, dbase + g['dx'], rtol=1e-5, atol=1e-5)
+
+
+# ---- the reference's drop-in symbols ---------------------------------------------------------
+def test_dropin_symbols_device_pointers(native, torch, oracle):
+    g = load_golden('fpn_14x14_sr2')
+    dev = torch.device('cuda', 0)
+    N, C, H, W = g['data'].shape
+    R = len(g['rois'])
+    PH, PW = g['pooled']
+    d = torch.from_numpy(g['data']).to(dev)
+    r = torch.from_numpy(g['rois']).to(dev)
+    out = torch.empty(g['y'].shape, device=dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    i32, f32 = ctypes.c_int, ctypes.c_float
+    torch.cuda.synchronize()
+    # exactly how mobula/func.py:155-156 calls it: explicit ctypes instances, device_id first
+    native.roi_align_forward_ab78de3c(i32(0), i32(out.numel()), p(d), f32(g['scale']), i32(C), i32(H),
+                                      i32(W), i32(PH), i32(PW), i32(g['sr']), p(r), p(out))
+    assert_bit_exact(out.cpu().numpy(), g['y'])       # synchronous: no explicit sync needed
+    dy = torch.from_numpy(g['dy']).to(dev)
+    dx = torch.zeros(g['dx'].shape, device=dev)       # caller zero-fills (ROIAlign.py:33-34)
+    torch.cuda.synchronize()
+    native.roi_align_backward_f318a24e(i32(0), i32(dy.numel()), p(dy), f32(g['scale']), i32(C), i32(H),
+                                       i32(W), i32(PH), i32(PW), i32(g['sr']), p(dx), p(r))
+    assert_scatter_close(dx.cpu().numpy(), g['dx'], _abs_sum(oracle, g), rtol=1e-5)
+    native.set_device(i32(0))
+
+
+def test_dropin_symbols_host_pointers(native, oracle):
+    """device_id = -1 is the reference's CPU context (func.py:139-141): host pointers."""
+    g = load_golden('edges_sr0')
+    N, C, H, W = g['data'].shape
+    PH, PW = g['pooled']
+    out = np.full(g['y'].shape, np.nan, np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    i32, f32 = ctypes.c_int, ctypes.c_float
+    native.roi_align_forward_ab78de3c(i32(-1), i32(out.size), p(g['data']), f32(g['scale']), i32(C),
+                                      i32(H), i32(W), i32(PH), i32(PW), i32(g['sr']), p(g['rois']), p(out))
+    assert_bit_exact(out, g['y'])
+    dx = np.zeros(g['dx'].shape, np.float32)
+    native.roi_align_backward_f318a24e(i32(-1), i32(g['dy'].size), p(g['dy']), f32(g['scale']), i32(C),
+                                       i32(H), i32(W), i32(PH), i32(PW), i32(g['sr']), p(dx), p(g['rois']))
+    assert_scatter_close(dx, g['dx'], _abs_sum(oracle, g), rtol=1e-5)
+
+
+# ---- through the mobula API -----------------------------------------------------------------
+@pytest.mark.parametrize('deterministic', [False, True])
+def test_torch_operator_forward_backward(api, torch, oracle, deterministic):
+    g = load_golden('fpn_14x14_sr2')
+    dev = torch.device('cuda', 0)
+    x = torch.from_numpy(g['data']).to(dev).requires_grad_(True)
+    rois = torch.from_numpy(g['rois']).to(dev).requires_grad_(True)
+    y = api.op.ROIAlign(x, rois, pooled_size=g['pooled'], spatial_scale=g['scale'],
+                        sampling_ratio=g['sr'], deterministic=deterministic)
+    assert_bit_exact(y.detach().cpu().numpy(), g['y'])
+    y.backward(torch.from_numpy(g['dy']).to(dev))
+    if deterministic:
+        assert_bit_exact(x.grad.cpu().numpy(), g['dx'])
+    else:
+        assert_scatter_close(x.grad.cpu().numpy(), g['dx'], _abs_sum(oracle, g), rtol=1e-5)
+    assert rois.grad is not None and not rois.grad.any().item()     # ROIAlign.py:41-42
+    # the reference's own tolerance (test_roialign.py:278-282)
+    api.testing.assert_almost_equal(y, g['y'], rtol=1e-3, atol=1e-3)
+
+
+def test_torch_module_form_noncontiguous_and_accumulating_grads(api, torch):
+    g = load_golden('edges_sr2')
+    dev = torch.device('cuda', 0)
+    layer = api.op.ROIAlign[torch.Tensor](pooled_size=g['pooled'], spatial_scale=g['scale'],
+                                          sampling_ratio=g['sr'])
+    assert isinstance(layer, torch.nn.Module)
+    nhwc = torch.from_numpy(g['data']).to(dev).permute(0, 2, 3, 1).contiguous()
+    x = nhwc.permute(0, 3, 1, 2).requires_grad_(True)              # NCHW view, not contiguous
+    assert not x.is_contiguous()
+    rois = torch.from_numpy(g['rois']).to(dev)
+    y1 = layer(x, rois)
+    y2 = layer(x, rois)                                            # same layer twice before backward
+    assert_bit_exact(y1.detach().cpu().numpy(), g['y'])
+    (y1.sum() + y2.sum()).backward()
+    ones = np.ones_like(g['dy'])
+    from oracle.roialign import COracle
+    ref = COracle().backward(ones, g['rois'], g['data'].shape, g['scale'], g['sr'])
+    np.testing.assert_allclose(x.grad.cpu().numpy(), 2 * ref, rtol=1e-5, atol=1e-5)
+
+
+def test_numpy_operator_both_call_forms(api, oracle):
+    g = load_golden('ref_value_test')
+    op = api.op.ROIAlign[np.ndarray](pooled_size=g['pooled'], spatial_scale=g['scale'],
+                                     sampling_ratio=g['sr'])
+    y = op(g['data'], g['rois'])
+    assert isinstance(y, np.ndarray)
+    assert_bit_exact(y, g['y'])
+    dx, drois = op.backward(g['dy'])
+    assert_scatter_close(dx, g['dx'], _abs_sum(oracle, g), rtol=1e-5)
+    assert not drois.any()
+    # req='add' accumulates into the given gradient buffers
+    acc = [np.ones_like(g['data']), np.ones_like(g['rois'])]
+    op.backward(g['dy'], in_grad=acc, req=['add', 'null'])
+    np.testing.assert_allclose(acc[0], 1 + g['dx'], rtol=1e-5, atol=1e-5)
+    assert (acc[1] == 1).all()
+    # plain call form (broken in the reference, numpy_glue.py:39-41)
+    y2 = api.op.ROIAlign(g['data'], g['rois'], pooled_size=g['pooled'], spatial_scale=g['scale'],
+                         sampling_ratio=g['sr'])
+    assert_bit_exact(y2, g['y'])
+    # func-level call with a non-contiguous output is copied back (test_func.py:9-22)
+    wide = np.zeros(g['y'].shape[:3] + (2 * g['y'].shape[3],), np.float32)
+    view = wide[..., ::2]
+    api.func.roi_align_forward(view.size, g['data'], g['scale'], g['data'].shape[1], g['data'].shape[2],
+                               g['data'].shape[3], g['pooled'][0], g['pooled'][1], g['sr'], g['rois'], view)
+    assert_bit_exact(np.ascontiguousarray(view), g['y'])
+    assert not wide[..., 1::2].any()
+
+
+def test_mixed_devices_rejected(api, torch):
+    dev = torch.device('cuda', 0)
+    data = torch.zeros((1, 1, 4, 4), device=dev)
+    rois = torch.zeros((1, 5))                                     # host tensor
+    with pytest.raises(ValueError):
+        api.op.ROIAlign(data, rois, pooled_size=(2, 2), spatial_scale=1.0, sampling_ratio=1)
+
+
+def test_same_result_on_every_gpu(direct, native, torch):
+    """tests/gpu/test_gpu.py:19-43 of the reference: the op on two devices agrees."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('one GPU')
+    g = load_golden('fpn_14x14_sr2')
+    other = Direct(native, torch, device=1)
+    assert_bit_exact(direct.forward(g['data'], g['rois'], g['pooled'], g['scale'], g['sr']),
+                     other.forward(g['data'], g['rois'], g['pooled'], g['scale'], g['sr']))
+    assert_bit_exact(
+        direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], mode='deterministic'),
+        other.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], mode='deterministic'))
+
+
+# ---- full BASELINE sizes: size-independent properties ----------------------------------------
+@pytest.mark.parametrize('key', ['C2', 'C3'])
+def test_full_size_properties(direct, oracle, torch, key):
+    wl = WL.CONFIGS[key]
+    data, rois, dy = WL.make_inputs(wl, seed=0)
+    y = direct.forward(data, rois, wl.pooled, wl.scale, wl.sampling_ratio)
+    dx = direct.backward(dy, rois, data.shape, wl.scale, wl.sampling_ratio)
+    # (1) a channel slice of the full-size result equals the oracle on that slice, all ROIs
+    cs = [0, wl.C // 2, wl.C - 1]
+    sub = np.ascontiguousarray(data[:, cs])
+    assert_bit_exact(np.ascontiguousarray(y[:, cs]),
+                     oracle.forward(sub, rois, wl.pooled, wl.scale, wl.sampling_ratio, threads=0))
+    dys = np.ascontiguousarray(dy[:, cs])
+    ref = oracle.backward(dys, rois, sub.shape, wl.scale, wl.sampling_ratio)
+    ref_abs = oracle.backward(np.abs(dys), rois, sub.shape, wl.scale, wl.sampling_ratio)
+    assert_scatter_close(np.ascontiguousarray(dx[:, cs]), ref, ref_abs, rtol=1e-5)
+    # (2) adjoint identity <fwd(x), dy> == <x, bwd(dy)> ties the two kernels together
+    lhs = float(np.vdot(y.astype(np.float64), dy.astype(np.float64)))
+    rhs = float(np.vdot(data.astype(np.float64), dx.astype(np.float64)))
+    scale = float(np.linalg.norm(y.astype(np.float64)) * np.linalg.norm(dy.astype(np.float64)))
+    assert abs(lhs - rhs) <= 1e-5 * scale, (lhs, rhs, scale)
+    # (3) deterministic mode: bit-reproducible and equal to the canonical order
+    d1 = direct.backward(dy, rois, data.shape, wl.scale, wl.sampling_ratio, mode='deterministic')
+    d2 = direct.backward(dy, rois, data.shape, wl.scale, wl.sampling_ratio, mode='deterministic')
+    assert_bit_exact(d1, d2)
+    assert_bit_exact(np.ascontiguousarray(d1[:, cs]), ref)
+    # (4) linearity of the scatter in dy (exact for power-of-two factors)
+    d4 = direct.backward(dy * np.float32(4), rois, data.shape, wl.scale, wl.sampling_ratio,
+                         mode='deterministic')
+    assert_bit_exact(d4, d1 * np.float32(4))

@@ -53,6 +53,8 @@ extern "C" {
 #define MOBULA_ROIALIGN_HOST_BUFFERS 2u /* all pointers are HOST memory: the library stages
                                            them to the device, runs, copies the result back
                                            and synchronises before returning               */
+/* testing aid: build no ROI tables, every kernel decodes ROIs on the fly (slow path) */
+#define MOBULA_ROIALIGN_DEBUG_NO_TABLES 0x10000u
 /* algorithm selection, bits 8..11 (0 = automatic) */
 #define MOBULA_ROIALIGN_ALGO_SHIFT 8
 #define MOBULA_ROIALIGN_ALGO_MASK (0xFu << MOBULA_ROIALIGN_ALGO_SHIFT)

@@ -105,8 +105,13 @@ def check(status):
         raise RuntimeError('CUDA failure in libmobula_roialign_sm100: ' + msg)
 
 
-def make_flags(accumulate=False, host=False, algo='auto'):
+FLAG_DEBUG_NO_TABLES = 0x10000
+
+
+def make_flags(accumulate=False, host=False, algo='auto', no_tables=False):
     flags = (FLAG_ACCUMULATE if accumulate else 0) | (FLAG_HOST_BUFFERS if host else 0)
+    if no_tables:
+        flags |= FLAG_DEBUG_NO_TABLES
     return flags | (ALGOS[algo] << ALGO_SHIFT)
 
 

@@ -16,8 +16,8 @@ LIB_DIR = os.path.join(PKG_DIR, 'lib')
 LIB_NAME = 'libmobula_roialign_sm100.so'
 LIB_PATH = os.path.join(LIB_DIR, LIB_NAME)
 
-SOURCES = ['roialign_api.cu', 'roialign_gather.cu', 'roialign_plane.cu', 'roialign_det.cu']
-HEADERS = ['roialign_kernels.h', 'roialign_common.cuh',
+SOURCES = ['roialign_api.cu', 'roialign_gather.cu', 'roialign_tables.cu', 'roialign_plane.cu']
+HEADERS = ['roialign_kernels.h', 'roialign_common.cuh', 'ptx_sm100.cuh',
            os.path.join('..', '..', 'include', 'mobula_roialign.h')]
 
 NVCC_FLAGS = [

@@ -101,7 +101,10 @@ struct DeviceState {
   bool probed = false;
   int num_sms = 0;
   int smem_optin = 0;
-  Buffer workspace;            // ROI order tables / axis tables of the plane + det kernels
+  Buffer workspace;            // ROI tables of the plane kernels (one call at a time)
+  cudaEvent_t ws_done = nullptr;   // recorded after the last kernel that reads the workspace
+  cudaStream_t ws_stream = nullptr;
+  bool ws_used = false;
   Buffer stage[4];             // host-buffer path: data/dy, rois, out/dx, spare
 };
 static DeviceState g_dev[kMaxDevices];
@@ -143,43 +146,97 @@ static unsigned algo_of(unsigned flags) {
 }
 
 // ---- device-pointer implementations --------------------------------------------------
+// Builds the ROI tables for this call in the per-device workspace.
+static int prepare_tables(DeviceState& st, const RoiAlignArgs& a, bool need_cells, unsigned flags,
+                          cudaStream_t stream, RoiTables* tables) {
+  // the workspace is shared by every stream of the device: a call on another stream waits
+  // for the previous user to finish with it
+  if (st.ws_used && st.ws_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, st.ws_done, 0));
+  roi_tables_set_arena_override((flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) ? 0 : -1);
+  const size_t bytes = roi_tables_bytes(a);
+  if (bytes > st.workspace.bytes && st.ws_used) CUDA_TRY(cudaEventSynchronize(st.ws_done));
+  CUDA_TRY(st.workspace.reserve(bytes, stream));
+  *tables = roi_tables_carve(a, st.workspace.ptr);
+  roi_tables_set_arena_override(-1);
+  CUDA_TRY(launch_roi_tables(a, *tables, need_cells, stream));
+  return MOBULA_OK;
+}
+
+static int release_tables(DeviceState& st, cudaStream_t stream) {
+  if (!st.ws_done) CUDA_TRY(cudaEventCreateWithFlags(&st.ws_done, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(st.ws_done, stream));
+  st.ws_stream = stream;
+  st.ws_used = true;
+  return MOBULA_OK;
+}
+
 static int forward_device(DeviceState& st, int device, cudaStream_t stream, const float* data,
                           const float* rois, float* out, const RoiAlignArgs& a, unsigned flags) {
-  (void)st;
   (void)device;
+  (void)rois;
   const int accumulate = (flags & MOBULA_ROIALIGN_ACCUMULATE) ? 1 : 0;
   const unsigned algo = algo_of(flags);
-  if (algo != MOBULA_ROIALIGN_ALGO_AUTO && algo != MOBULA_ROIALIGN_ALGO_GATHER)
-    return fail(MOBULA_ERR_UNSUPPORTED, "forward algorithm %u is not available", algo);
-  t_algo[0] = "gather";
-  CUDA_TRY(launch_fwd_gather(a, data, out, accumulate, stream));
-  return MOBULA_OK;
+  if (algo > MOBULA_ROIALIGN_ALGO_PLANE)
+    return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown forward algorithm %u", algo);
+  PlanePlan plan;
+  const bool plane_ok = plane_supported(a, data, st.smem_optin, &plan);
+  if (algo == MOBULA_ROIALIGN_ALGO_PLANE && !plane_ok)
+    return fail(MOBULA_ERR_UNSUPPORTED,
+                "plane algorithm needs num_images in [0, 4096] and a %dx%d fp32 plane within %d bytes "
+                "of shared memory", a.height, a.width, st.smem_optin);
+  if (algo == MOBULA_ROIALIGN_ALGO_GATHER || !plane_ok) {
+    t_algo[0] = "gather";
+    CUDA_TRY(launch_fwd_gather(a, data, out, accumulate, stream));
+    return MOBULA_OK;
+  }
+  t_algo[0] = "plane";
+  RoiTables tables;
+  int rc = prepare_tables(st, a, false, flags, stream, &tables);
+  if (rc) return rc;
+  CUDA_TRY(launch_fwd_plane(a, plan, tables, data, out, accumulate, st.num_sms, stream));
+  return release_tables(st, stream);
 }
 
 static int backward_device(DeviceState& st, int device, cudaStream_t stream, const float* dy,
                            const float* rois, float* dx, const RoiAlignArgs& a, int mode,
                            unsigned flags) {
-  (void)st;
   (void)device;
   (void)rois;
   const int accumulate = (flags & MOBULA_ROIALIGN_ACCUMULATE) ? 1 : 0;
   const unsigned algo = algo_of(flags);
   if (mode != MOBULA_ROIALIGN_BWD_ATOMIC && mode != MOBULA_ROIALIGN_BWD_DETERMINISTIC)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward mode %d", mode);
+  if (algo > MOBULA_ROIALIGN_ALGO_PLANE)
+    return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward algorithm %u", algo);
   if (!accumulate && a.num_images < 0)
     return fail(MOBULA_ERR_INVALID_ARGUMENT,
                 "backward without MOBULA_ROIALIGN_ACCUMULATE needs num_images >= 0");
-  if (mode == MOBULA_ROIALIGN_BWD_DETERMINISTIC)
-    return fail(MOBULA_ERR_UNSUPPORTED, "deterministic backward is not available yet");
-  if (algo != MOBULA_ROIALIGN_ALGO_AUTO && algo != MOBULA_ROIALIGN_ALGO_GATHER)
-    return fail(MOBULA_ERR_UNSUPPORTED, "backward algorithm %u is not available", algo);
-  t_algo[1] = "gather";
-  if (!accumulate) {
-    const size_t bytes = (size_t)a.num_images * a.channels * a.height * a.width * sizeof(float);
-    if (bytes) CUDA_TRY(cudaMemsetAsync(dx, 0, bytes, stream));
+  PlanePlan plan;
+  const bool plane_ok = plane_supported(a, dx, st.smem_optin, &plan);
+  const bool deterministic = mode == MOBULA_ROIALIGN_BWD_DETERMINISTIC;
+  if (deterministic && algo == MOBULA_ROIALIGN_ALGO_GATHER)
+    return fail(MOBULA_ERR_UNSUPPORTED, "the gather backward uses global atomics: not deterministic");
+  if ((deterministic || algo == MOBULA_ROIALIGN_ALGO_PLANE) && !plane_ok)
+    return fail(MOBULA_ERR_UNSUPPORTED,
+                "%s needs num_images in [0, 4096] and a %dx%d fp32 plane within %d bytes of shared "
+                "memory", deterministic ? "deterministic backward" : "plane algorithm", a.height,
+                a.width, st.smem_optin);
+  if (algo == MOBULA_ROIALIGN_ALGO_GATHER || !plane_ok) {
+    t_algo[1] = "gather";
+    if (!accumulate) {
+      const size_t bytes = (size_t)a.num_images * a.channels * a.height * a.width * sizeof(float);
+      if (bytes) CUDA_TRY(cudaMemsetAsync(dx, 0, bytes, stream));
+    }
+    CUDA_TRY(launch_bwd_gather(a, dy, dx, stream));
+    return MOBULA_OK;
   }
-  CUDA_TRY(launch_bwd_gather(a, dy, dx, stream));
-  return MOBULA_OK;
+  // owner-computes plane kernel: canonical order, so it serves both modes
+  t_algo[1] = "plane";
+  RoiTables tables;
+  int rc = prepare_tables(st, a, true, flags, stream, &tables);
+  if (rc) return rc;
+  CUDA_TRY(launch_bwd_plane(a, plan, tables, dy, dx, accumulate, st.num_sms, stream));
+  return release_tables(st, stream);
 }
 
 static RoiAlignArgs make_args(const float* rois, int num_rois, int num_images, int channels,
@@ -369,6 +426,9 @@ MOBULA_EXPORT void mobula_roialign_release(void) {
     cudaSetDevice(d);
     cudaDeviceSynchronize();
     st.workspace.release();
+    if (st.ws_done) cudaEventDestroy(st.ws_done);
+    st.ws_done = nullptr;
+    st.ws_used = false;
     for (Buffer& b : st.stage) b.release();
   }
   cudaSetDevice(prev);

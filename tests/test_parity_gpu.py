@@ -51,7 +51,7 @@ class Direct(object):
     def _p(t):
         return ctypes.c_void_p(t.data_ptr())
 
-    def forward(self, data, rois, pooled, scale, sr, algo='auto', accumulate_into=None):
+    def forward(self, data, rois, pooled, scale, sr, algo='auto', accumulate_into=None, no_tables=False):
         from mobulaop_b200 import _native
         t = self.torch
         d = t.from_numpy(data).to(self.dev)
@@ -62,14 +62,15 @@ class Direct(object):
             out = t.full((R, C, pooled[0], pooled[1]), float('nan'), device=self.dev)
         else:
             out = t.from_numpy(accumulate_into).to(self.dev)
-        flags = _native.make_flags(accumulate=accumulate_into is not None, algo=algo)
+        flags = _native.make_flags(accumulate=accumulate_into is not None, algo=algo, no_tables=no_tables)
         _native.check(self.lib.mobula_roialign_forward_f32(
             self.device, self._stream(), self._p(d), self._p(r), self._p(out), R, N, C, H, W,
             pooled[0], pooled[1], scale, sr, flags))
         t.cuda.synchronize(self.dev)
         return out.cpu().numpy()
 
-    def backward(self, dy, rois, shape, scale, sr, mode='atomic', algo='auto', accumulate_into=None):
+    def backward(self, dy, rois, shape, scale, sr, mode='atomic', algo='auto', accumulate_into=None,
+                 no_tables=False):
         from mobulaop_b200 import _native
         t = self.torch
         g = t.from_numpy(dy).to(self.dev)
@@ -80,7 +81,7 @@ class Direct(object):
             dx = t.full(shape, float('nan'), device=self.dev)    # the zero-fill is the op's job
         else:
             dx = t.from_numpy(accumulate_into).to(self.dev)
-        flags = _native.make_flags(accumulate=accumulate_into is not None, algo=algo)
+        flags = _native.make_flags(accumulate=accumulate_into is not None, algo=algo, no_tables=no_tables)
         m = _native.BWD_DETERMINISTIC if mode == 'deterministic' else _native.BWD_ATOMIC
         _native.check(self.lib.mobula_roialign_backward_f32(
             self.device, self._stream(), self._p(g), self._p(r), self._p(dx), R, N, C, H, W, PH, PW,
@@ -152,6 +153,17 @@ def test_seeded_workload_parity(direct, oracle, key, algo):
     assert_scatter_close(dx, dx_ref, dx_abs, rtol=1e-5)
     dxd = direct.backward(dy, rois, data.shape, wl.scale, wl.sampling_ratio, mode='deterministic')
     assert_bit_exact(dxd, dx_ref)
+
+
+@pytest.mark.parametrize('name', ['edges_sr0', 'edges_sr2', 'edges_sr3_p5x3', 'ref_value_test'])
+def test_untabled_rois_take_the_on_the_fly_path(direct, name):
+    """ROIs that do not fit the table arena are decoded inside the kernels; forced here."""
+    g = load_golden(name)
+    y = direct.forward(g['data'], g['rois'], g['pooled'], g['scale'], g['sr'], algo='plane', no_tables=True)
+    assert_bit_exact(y, g['y'])
+    dx = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], mode='deterministic',
+                         no_tables=True)
+    assert_bit_exact(dx, g['dx'])
 
 
 # ---- ROI bookkeeping --------------------------------------------------------------------

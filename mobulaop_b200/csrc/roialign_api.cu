@@ -147,18 +147,18 @@ static unsigned algo_of(unsigned flags) {
 
 // ---- device-pointer implementations --------------------------------------------------
 // Builds the ROI tables for this call in the per-device workspace.
-static int prepare_tables(DeviceState& st, const RoiAlignArgs& a, bool need_cells, unsigned flags,
-                          cudaStream_t stream, RoiTables* tables) {
+static int prepare_tables(DeviceState& st, const RoiAlignArgs& a, unsigned need, int pitch,
+                          unsigned flags, cudaStream_t stream, RoiTables* tables) {
   // the workspace is shared by every stream of the device: a call on another stream waits
   // for the previous user to finish with it
   if (st.ws_used && st.ws_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, st.ws_done, 0));
   roi_tables_set_arena_override((flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) ? 0 : -1);
-  const size_t bytes = roi_tables_bytes(a);
+  const size_t bytes = roi_tables_bytes(a, need);
   if (bytes > st.workspace.bytes && st.ws_used) CUDA_TRY(cudaEventSynchronize(st.ws_done));
   CUDA_TRY(st.workspace.reserve(bytes, stream));
-  *tables = roi_tables_carve(a, st.workspace.ptr);
+  *tables = roi_tables_carve(a, need, pitch, st.workspace.ptr);
   roi_tables_set_arena_override(-1);
-  CUDA_TRY(launch_roi_tables(a, *tables, need_cells, stream));
+  CUDA_TRY(launch_roi_tables(a, *tables, need, stream));
   return MOBULA_OK;
 }
 
@@ -191,7 +191,7 @@ static int forward_device(DeviceState& st, int device, cudaStream_t stream, cons
   }
   t_algo[0] = "plane";
   RoiTables tables;
-  int rc = prepare_tables(st, a, false, flags, stream, &tables);
+  int rc = prepare_tables(st, a, 0u, plan.pitch, flags, stream, &tables);
   if (rc) return rc;
   CUDA_TRY(launch_fwd_plane(a, plan, tables, data, out, accumulate, st.num_sms, stream));
   return release_tables(st, stream);
@@ -230,12 +230,15 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
     CUDA_TRY(launch_bwd_gather(a, dy, dx, stream));
     return MOBULA_OK;
   }
-  // owner-computes plane kernel: canonical order, so it serves both modes
-  t_algo[1] = "plane";
+  // owner-computes plane kernels: canonical order for the deterministic mode (also the
+  // fall-back when the merged tables cannot be used), merged weights otherwise
+  const bool canonical = deterministic || !plan.fast_bwd || (flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES);
+  t_algo[1] = canonical ? "plane-canonical" : "plane";
   RoiTables tables;
-  int rc = prepare_tables(st, a, true, flags, stream, &tables);
+  int rc = prepare_tables(st, a, canonical ? kNeedCells : (kNeedCells | kNeedFast), plan.bwd_pitch, flags,
+                          stream, &tables);
   if (rc) return rc;
-  CUDA_TRY(launch_bwd_plane(a, plan, tables, dy, dx, accumulate, st.num_sms, stream));
+  CUDA_TRY(launch_bwd_plane(a, plan, tables, dy, dx, accumulate, canonical ? 1 : 0, st.num_sms, stream));
   return release_tables(st, stream);
 }
 

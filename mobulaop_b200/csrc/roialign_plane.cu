@@ -23,25 +23,65 @@ namespace mobula_b200 {
 namespace {
 
 constexpr int kMaxThreads = 1024;
-constexpr uint32_t kBulkChunk = 32768;
 
-__device__ __forceinline__ void load_plane(float* plane, const float* __restrict__ src, int elems,
-                                           uint64_t* bar, uint32_t& parity, int use_bulk) {
+// Moves a [height x width] fp32 plane between global memory (dense rows) and shared memory
+// (rows `pitch` floats apart).  With use_bulk every row is one cp.async.bulk issued by a lane
+// of warp 0; completion is tracked by `bar` (loads) or the bulk async-group (stores).
+__device__ __forceinline__ void load_plane(float* plane, const float* __restrict__ src, int height,
+                                           int width, int pitch, uint64_t* bar, uint32_t& parity,
+                                           int use_bulk) {
   if (use_bulk) {
-    if (threadIdx.x == 0) {
-      ptx::fence_proxy_async();
-      const uint32_t bytes = (uint32_t)elems * 4u;
-      ptx::mbar_arrive_expect_tx(bar, bytes);
-      for (uint32_t off = 0; off < bytes; off += kBulkChunk) {
-        const uint32_t n = bytes - off < kBulkChunk ? bytes - off : kBulkChunk;
-        ptx::bulk_g2s((char*)plane + off, (const char*)src + off, n, bar);
+    if (threadIdx.x < 32) {
+      const uint32_t row_bytes = (uint32_t)width * 4u;
+      if (threadIdx.x == 0) {
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)height);
+      }
+      __syncwarp();
+      if (pitch == width) {
+        // dense: a few large copies
+        const uint32_t bytes = row_bytes * (uint32_t)height, chunk = 32768u;
+        for (uint32_t off = threadIdx.x * chunk; off < bytes; off += 32u * chunk)
+          ptx::bulk_g2s((char*)plane + off, (const char*)src + off, min(chunk, bytes - off), bar);
+      } else {
+        for (int r = threadIdx.x; r < height; r += 32)
+          ptx::bulk_g2s(plane + (size_t)r * pitch, src + (size_t)r * width, row_bytes, bar);
       }
     }
     ptx::mbar_wait(bar, parity);
     parity ^= 1u;
   } else {
-    for (int i = threadIdx.x; i < elems; i += blockDim.x) plane[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < height * width; i += blockDim.x) {
+      const int r = i / width;
+      plane[r * pitch + (i - r * width)] = __ldg(src + i);
+    }
     __syncthreads();
+  }
+}
+
+// Call with every thread, after a __syncthreads() that followed the last shared-memory write
+// (each writer having executed fence_proxy_async() when use_bulk is set).
+__device__ __forceinline__ void store_plane(float* __restrict__ dst, const float* plane, int height,
+                                            int width, int pitch, int use_bulk) {
+  if (use_bulk) {
+    if (threadIdx.x < 32) {
+      const uint32_t row_bytes = (uint32_t)width * 4u;
+      if (pitch == width) {
+        const uint32_t bytes = row_bytes * (uint32_t)height, chunk = 32768u;
+        for (uint32_t off = threadIdx.x * chunk; off < bytes; off += 32u * chunk)
+          ptx::bulk_s2g((char*)dst + off, (const char*)plane + off, min(chunk, bytes - off));
+      } else {
+        for (int r = threadIdx.x; r < height; r += 32)
+          ptx::bulk_s2g(dst + (size_t)r * width, plane + (size_t)r * pitch, row_bytes);
+      }
+      ptx::bulk_commit();
+      ptx::bulk_wait_read();   // the shared-memory source may be overwritten afterwards
+    }
+  } else {
+    for (int i = threadIdx.x; i < height * width; i += blockDim.x) {
+      const int r = i / width;
+      dst[i] = plane[r * pitch + (i - r * width)];
+    }
   }
 }
 
@@ -99,14 +139,52 @@ __device__ __forceinline__ float sample_plane(const float* plane, const AxisEntr
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
-// GRID > 0: sampling_ratio known at compile time (loops unrolled, x entries kept in
-// registers); GRID == 0: any grid, including the adaptive one.
+// One pooled output.  GRID > 0: sampling_ratio known at compile time (unrolled, x entries in
+// registers, no branch when every sample is inside the plane); GRID == 0: any grid.
+template <int GRID>
+__device__ __forceinline__ float pool_bin(const float* plane, const AxisEntry* __restrict__ ye,
+                                          const AxisEntry* __restrict__ xe, int gh, int gw) {
+  float acc = 0.0f;
+  if (GRID > 0) {
+    AxisEntry ey[GRID > 0 ? GRID : 1], ex[GRID > 0 ? GRID : 1];
+    int any_invalid = 0;
+#pragma unroll
+    for (int i = 0; i < GRID; ++i) {
+      ey[i] = load_entry(ye + i);
+      ex[i] = load_entry(xe + i);
+      any_invalid |= ey[i].lo | ex[i].lo;      // invalid entries carry lo = -1
+    }
+    if (any_invalid >= 0) {
+#pragma unroll
+      for (int iy = 0; iy < GRID; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < GRID; ++ix) acc = __fadd_rn(acc, sample_plane(plane, ey[iy], ex[ix]));
+    } else {
+#pragma unroll
+      for (int iy = 0; iy < GRID; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < GRID; ++ix)
+          if ((ey[iy].lo | ex[ix].lo) >= 0) acc = __fadd_rn(acc, sample_plane(plane, ey[iy], ex[ix]));
+    }
+  } else {
+    for (int iy = 0; iy < gh; ++iy) {
+      const AxisEntry ey = load_entry(ye + iy);
+      if (ey.lo < 0) continue;
+      for (int ix = 0; ix < gw; ++ix) {
+        const AxisEntry ex = load_entry(xe + ix);
+        if (ex.lo >= 0) acc = __fadd_rn(acc, sample_plane(plane, ey, ex));
+      }
+    }
+  }
+  return acc;
+}
+
 template <int GRID>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 roialign_fwd_plane_kernel(const float* __restrict__ data, float* __restrict__ out,
                           const float* __restrict__ rois, const RoiRec* __restrict__ recs,
                           const AxisEntry* __restrict__ axis, const int* __restrict__ img_start,
-                          int num_images, int channels, int height, int width, int pooled_h,
+                          int num_images, int channels, int height, int width, int pitch, int pooled_h,
                           int pooled_w, float scale, int sampling_ratio, int accumulate, int use_bulk) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
@@ -122,7 +200,7 @@ roialign_fwd_plane_kernel(const float* __restrict__ data, float* __restrict__ ou
     slots = blockDim.x / bins;
     slot = tid / bins;
     bin0 = tid - slot * bins;
-    bstride = bins;
+    bstride = bins;              // a single bin per thread
     if (slot >= slots) slot = -1;
   } else {
     slots = 1;
@@ -130,6 +208,7 @@ roialign_fwd_plane_kernel(const float* __restrict__ data, float* __restrict__ ou
     bin0 = tid;
     bstride = blockDim.x;
   }
+  const int ph0 = bin0 / pooled_w, pw0 = bin0 - ph0 * pooled_w;
 
   if (tid == 0 && use_bulk) {
     ptx::mbar_init(&bar, 1);
@@ -153,7 +232,8 @@ roialign_fwd_plane_kernel(const float* __restrict__ data, float* __restrict__ ou
       continue;
     }
     __syncthreads();   // every thread is done reading the previous plane
-    load_plane(plane, data + ((size_t)n * channels + c) * plane_elems, plane_elems, &bar, parity, use_bulk);
+    load_plane(plane, data + ((size_t)n * channels + c) * plane_elems, height, width, pitch, &bar, parity,
+               use_bulk);
     if (slot < 0) continue;
 
     for (int jj = slot; jj < j1 - j0; jj += slots) {
@@ -161,39 +241,21 @@ roialign_fwd_plane_kernel(const float* __restrict__ data, float* __restrict__ ou
       const int gh = GRID > 0 ? GRID : r.grid_h, gw = GRID > 0 ? GRID : r.grid_w;
       const CountDiv div(gh * gw);
       float* orow = out + ((size_t)r.roi * channels + c) * bins;
+      int ph = ph0, pw = pw0;
       for (int b = bin0; b < bins; b += bstride) {
-        const int ph = b / pooled_w, pw = b - ph * pooled_w;
-        float acc = 0.0f;
+        if (b != bin0) {
+          ph = b / pooled_w;
+          pw = b - ph * pooled_w;
+        }
+        float acc;
         if (r.yoff >= 0) {
-          const AxisEntry* ye = axis + r.yoff + ph * gh;
-          const AxisEntry* xe = axis + r.xoff + pw * gw;
-          if (GRID > 0) {
-            AxisEntry ex[GRID > 0 ? GRID : 1];
-#pragma unroll
-            for (int ix = 0; ix < GRID; ++ix) ex[ix] = load_entry(xe + ix);
-#pragma unroll
-            for (int iy = 0; iy < GRID; ++iy) {
-              const AxisEntry ey = load_entry(ye + iy);
-              if (ey.lo < 0) continue;
-#pragma unroll
-              for (int ix = 0; ix < GRID; ++ix)
-                if (ex[ix].lo >= 0) acc = __fadd_rn(acc, sample_plane(plane, ey, ex[ix]));
-            }
-          } else {
-            for (int iy = 0; iy < gh; ++iy) {
-              const AxisEntry ey = load_entry(ye + iy);
-              if (ey.lo < 0) continue;
-              for (int ix = 0; ix < gw; ++ix) {
-                const AxisEntry ex = load_entry(xe + ix);
-                if (ex.lo >= 0) acc = __fadd_rn(acc, sample_plane(plane, ey, ex));
-              }
-            }
-          }
+          acc = pool_bin<GRID>(plane, axis + r.yoff + ph * gh, axis + r.xoff + pw * gw, gh, gw);
         } else {
           // not tabled (arena exhausted): decode on the fly
+          acc = 0.0f;
           const RoiGeom g = roi_decode(rois + (size_t)r.roi * 5, scale, pooled_h, pooled_w, sampling_ratio);
           for (int iy = 0; iy < g.grid_h; ++iy) {
-            const AxisEntry ey = decode_entry(g.start_h, ph, g.bin_h, iy, g.grid_h, height, width);
+            const AxisEntry ey = decode_entry(g.start_h, ph, g.bin_h, iy, g.grid_h, height, pitch);
             if (ey.lo < 0) continue;
             for (int ix = 0; ix < g.grid_w; ++ix) {
               const AxisEntry ex = decode_entry(g.start_w, pw, g.bin_w, ix, g.grid_w, width, 1);
@@ -209,24 +271,136 @@ roialign_fwd_plane_kernel(const float* __restrict__ data, float* __restrict__ ou
   }
 }
 
+// Forward for a compile-time sampling ratio with every ROI tabled: the tables are then
+// regular (roi j owns entries [j*E, (j+1)*E), E = (PH+PW)*GRID), so no per-ROI record has to
+// be read before the sample entries, and the loads of U consecutive items of a thread are all
+// issued before the first one is used (the table latency, not the arithmetic, bounds this
+// kernel otherwise).  512 threads leave each thread 128 registers for that.
+constexpr int kRegularThreads = 512;
+
+template <int GRID, int U>
+__global__ void __launch_bounds__(kRegularThreads, 1)
+roialign_fwd_plane_regular_kernel(const float* __restrict__ data, float* __restrict__ out,
+                                  const int* __restrict__ order, const AxisEntry* __restrict__ axis,
+                                  const int* __restrict__ img_start, int num_images, int channels,
+                                  int height, int width, int pitch, int pooled_h, int pooled_w,
+                                  int accumulate, int use_bulk) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  float* plane = reinterpret_cast<float*>(smem_raw);
+  const int plane_elems = height * width;
+  const int bins = pooled_h * pooled_w;
+  const int tid = threadIdx.x;
+  const int slots = blockDim.x / bins;          // launcher guarantees bins <= blockDim.x
+  int slot = tid / bins;
+  const int bin = tid - slot * bins;
+  if (slot >= slots) slot = -1;
+  const int ph = bin / pooled_w, pw = bin - ph * pooled_w;
+  const int per_roi = (pooled_h + pooled_w) * GRID;
+  const AxisEntry* ybase = axis + ph * GRID;
+  const AxisEntry* xbase = axis + pooled_h * GRID + pw * GRID;
+  const CountDiv div(GRID * GRID);
+
+  if (tid == 0 && use_bulk) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+
+  const int planes = (num_images + 1) * channels;
+  for (int p = blockIdx.x; p < planes; p += gridDim.x) {
+    const int n = p / channels, c = p - n * channels;
+    const int j0 = __ldg(img_start + n), j1 = __ldg(img_start + n + 1);
+    const int nroi = j1 - j0;
+    if (nroi == 0) continue;
+    if (n == num_images) {
+      if (!accumulate && slot >= 0)
+        for (int jj = slot; jj < nroi; jj += slots)
+          out[((size_t)__ldg(order + j0 + jj) * channels + c) * bins + bin] = 0.0f;
+      continue;
+    }
+    __syncthreads();   // every thread is done reading the previous plane
+    load_plane(plane, data + ((size_t)n * channels + c) * plane_elems, height, width, pitch, &bar, parity,
+               use_bulk);
+    if (slot < 0) continue;
+
+    for (int jj = slot; jj < nroi; jj += U * slots) {
+      AxisEntry ey[U][GRID], ex[U][GRID];
+      int roi[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = jj + u * slots;
+        roi[u] = -1;
+        if (j < nroi) {
+          const size_t base = (size_t)(j0 + j) * per_roi;
+          roi[u] = __ldg(order + j0 + j);
+#pragma unroll
+          for (int i = 0; i < GRID; ++i) {
+            ey[u][i] = load_entry(ybase + base + i);
+            ex[u][i] = load_entry(xbase + base + i);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (roi[u] < 0) continue;
+        int any_invalid = 0;
+#pragma unroll
+        for (int i = 0; i < GRID; ++i) any_invalid |= ey[u][i].lo | ex[u][i].lo;
+        float acc = 0.0f;
+        if (any_invalid >= 0) {
+#pragma unroll
+          for (int iy = 0; iy < GRID; ++iy)
+#pragma unroll
+            for (int ix = 0; ix < GRID; ++ix) acc = __fadd_rn(acc, sample_plane(plane, ey[u][iy], ex[u][ix]));
+        } else {
+#pragma unroll
+          for (int iy = 0; iy < GRID; ++iy)
+#pragma unroll
+            for (int ix = 0; ix < GRID; ++ix)
+              if ((ey[u][iy].lo | ex[u][ix].lo) >= 0)
+                acc = __fadd_rn(acc, sample_plane(plane, ey[u][iy], ex[u][ix]));
+        }
+        const float y = div(acc);
+        float* o = out + ((size_t)roi[u] * channels + c) * bins + bin;
+        if (accumulate) *o = __fadd_rn(*o, y);
+        else *o = y;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
-// backward (owner computes, canonical order)
+// backward (owner computes): kBands warps per CTA, warp w owns rows [w*H/kBands, (w+1)*H/kBands)
+// of the plane and nobody else touches them -> plain shared-memory read-modify-write.
 // ---------------------------------------------------------------------------------------
+constexpr int kBwdThreads = kBands * 32;
+
 struct CellRegs {
   int pix, k_first, k_last, p_first;
 };
 
 __device__ __forceinline__ CellRegs load_cell(const AxisCell* __restrict__ c) {
-  const int4 v = __ldg(reinterpret_cast<const int4*>(c));
+  const int4 b = __ldg(reinterpret_cast<const int4*>(c) + 1);   // h1p, h1w, hit_first, p_first
+  const int4 k = __ldg(reinterpret_cast<const int4*>(c) + 2);   // k_first, k_last
   CellRegs r;
-  r.pix = v.x;
-  r.k_first = v.y;
-  r.k_last = v.z;
-  r.p_first = v.w;
+  r.pix = __ldg(&c->pix);
+  r.k_first = k.x;
+  r.k_last = k.y;
+  r.p_first = b.w;
   return r;
 }
 
-// Adds, in canonical order, every contribution of one ROI to the pixel (rowpix / width, col).
+__device__ __forceinline__ AxisHit load_hit(const AxisHit* __restrict__ h) {
+  const int2 v = __ldg(reinterpret_cast<const int2*>(h));
+  AxisHit r;
+  r.p = v.x;
+  r.w = __int_as_float(v.y);
+  return r;
+}
+
+// Adds, in canonical order, every contribution of one ROI to the pixel (rowpix / pitch, col).
 // yc / xc give the sample ranges that can touch the pixel's row / column.
 template <typename EntryY, typename EntryX>
 __device__ __forceinline__ float accumulate_pixel(float acc, const float* __restrict__ dtop, int pooled_w,
@@ -239,7 +413,7 @@ __device__ __forceinline__ float accumulate_pixel(float acc, const float* __rest
     int kx = xc.k_first;
     for (int pw = xc.p_first; kx <= xc.k_last; ++pw) {
       const int kx_end = min(xc.k_last, (pw + 1) * gw - 1);
-      const float d = __ldg(dtop + ph * pooled_w + pw);
+      const float d = dtop[ph * pooled_w + pw];
       for (int a = ky; a <= ky_end; ++a) {
         const AxisEntry ey = entry_y(a);
         const bool y_lo = ey.lo == rowpix, y_hi = ey.hi == rowpix;
@@ -261,23 +435,44 @@ __device__ __forceinline__ float accumulate_pixel(float acc, const float* __rest
   return acc;
 }
 
-__global__ void __launch_bounds__(kMaxThreads, 1)
-roialign_bwd_plane_kernel(const float* __restrict__ dy, float* __restrict__ dx,
-                          const float* __restrict__ rois, const RoiRec* __restrict__ recs,
-                          const AxisEntry* __restrict__ axis, const AxisCell* __restrict__ cells,
-                          const int* __restrict__ img_start, int num_images, int channels, int height,
-                          int width, int pooled_h, int pooled_w, float scale, int sampling_ratio,
-                          int accumulate, int use_bulk) {
+// Copies dy[roi, c, :, :] (bins floats) into the warp's slot; returns the pointer to read from.
+__device__ __forceinline__ const float* stage_dtop(const float* __restrict__ dtop, float* gslot, int bins,
+                                                   int lane) {
+  if (gslot == nullptr) return dtop;
+  __syncwarp();                       // the previous tile is no longer being read
+  for (int i = lane; i < bins; i += 32) gslot[i] = __ldg(dtop + i);
+  __syncwarp();
+  return gslot;
+}
+
+// ---- plane prologue / epilogue shared by both backward kernels ----
+struct BwdPlane {
+  float* plane;
+  float* gslot;
+  uint64_t* bar;
+  uint32_t parity;
+};
+
+// Canonical order: every contribution added separately, in the order of the single-thread
+// reference -> bit-exact dX ("deterministic" mode).
+__global__ void __launch_bounds__(kBwdThreads, 1)
+roialign_bwd_plane_canonical_kernel(const float* __restrict__ dy, float* __restrict__ dx,
+                                    const float* __restrict__ rois, const RoiRec* __restrict__ recs,
+                                    const AxisEntry* __restrict__ axis, const AxisCell* __restrict__ cells,
+                                    const int* __restrict__ img_start, int num_images, int channels,
+                                    int height, int width, int pitch, int pooled_h, int pooled_w,
+                                    float scale, int sampling_ratio, int accumulate, int use_bulk,
+                                    int gslot_floats) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
   float* plane = reinterpret_cast<float*>(smem_raw);
   const int plane_elems = height * width;
   const int bins = pooled_h * pooled_w;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  // rows [b0, b1) of every plane belong to this warp and to nobody else
-  const int b0 = (int)(((long long)warp * height) / nwarps);
-  const int b1 = (int)(((long long)(warp + 1) * height) / nwarps);
-  const int pix0 = b0 * width, pix1 = b1 * width;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* gslot = gslot_floats > 0 ? plane + (size_t)height * pitch + (size_t)warp * gslot_floats : nullptr;
+  const int b0 = (int)(((long long)warp * height) / kBands);
+  const int b1 = (int)(((long long)(warp + 1) * height) / kBands);
+  const int pix0 = b0 * pitch, pix1 = b1 * pitch;
 
   if (tid == 0 && use_bulk) {
     ptx::mbar_init(&bar, 1);
@@ -298,9 +493,9 @@ roialign_bwd_plane_kernel(const float* __restrict__ dy, float* __restrict__ dx,
     }
     __syncthreads();   // the previous plane has left shared memory
     if (accumulate) {
-      load_plane(plane, gplane, plane_elems, &bar, parity, use_bulk);
+      load_plane(plane, gplane, height, width, pitch, &bar, parity, use_bulk);
     } else {
-      for (int i = tid; i < plane_elems; i += blockDim.x) plane[i] = 0.0f;
+      for (int i = tid; i < height * pitch; i += blockDim.x) plane[i] = 0.0f;
       __syncthreads();
     }
 
@@ -320,7 +515,6 @@ roialign_bwd_plane_kernel(const float* __restrict__ dy, float* __restrict__ dx,
           todo &= todo - 1;
           const RoiRec* rec = recs + jb + s;
           const RecHead r = load_rec_head(rec);
-          const float* dtop = dy + ((size_t)r.roi * channels + c) * bins;
           const CountDiv div(r.grid_h * r.grid_w);
           if (r.yoff >= 0) {
             const int4 cinfo = __ldg(reinterpret_cast<const int4*>(rec) + 2);  // ycell,xcell,nycell,nxcell
@@ -330,11 +524,15 @@ roialign_bwd_plane_kernel(const float* __restrict__ dy, float* __restrict__ dx,
             const AxisEntry* xtab = axis + r.xoff;
             auto entry_y = [&](int k) { return load_entry(ytab + k); };
             auto entry_x = [&](int k) { return load_entry(xtab + k); };
+            const float* dtop = nullptr;
             for (int yb = 0; yb < cinfo.z; yb += 32) {
               CellRegs mine;
               mine.pix = -1;
+              mine.k_first = mine.k_last = mine.p_first = 0;
               if (yb + lane < cinfo.z) mine = load_cell(ycells + yb + lane);
               unsigned rows = __ballot_sync(0xffffffffu, mine.pix >= pix0 && mine.pix < pix1);
+              if (rows && dtop == nullptr)
+                dtop = stage_dtop(dy + ((size_t)r.roi * channels + c) * bins, gslot, bins, lane);
               while (rows) {
                 const int q = __ffs(rows) - 1;
                 rows &= rows - 1;
@@ -354,8 +552,9 @@ roialign_bwd_plane_kernel(const float* __restrict__ dy, float* __restrict__ dx,
           } else {
             // not tabled: decode every sample on the fly (correct for any grid, slow)
             const RoiGeom g = roi_decode(rois + (size_t)r.roi * 5, scale, pooled_h, pooled_w, sampling_ratio);
+            const float* dtop = stage_dtop(dy + ((size_t)r.roi * channels + c) * bins, gslot, bins, lane);
             auto entry_y = [&](int k) {
-              return decode_entry(g.start_h, k / g.grid_h, g.bin_h, k % g.grid_h, g.grid_h, height, width);
+              return decode_entry(g.start_h, k / g.grid_h, g.bin_h, k % g.grid_h, g.grid_h, height, pitch);
             };
             auto entry_x = [&](int k) {
               return decode_entry(g.start_w, k / g.grid_w, g.bin_w, k % g.grid_w, g.grid_w, width, 1);
@@ -369,8 +568,8 @@ roialign_bwd_plane_kernel(const float* __restrict__ dy, float* __restrict__ dx,
             xc.p_first = 0;
             for (int row = b0; row < b1; ++row)
               for (int col = lane; col < width; col += 32) {
-                float* px = plane + row * width + col;
-                *px = accumulate_pixel(*px, dtop, pooled_w, g.grid_h, g.grid_w, div, row * width, col, yc,
+                float* px = plane + row * pitch + col;
+                *px = accumulate_pixel(*px, dtop, pooled_w, g.grid_h, g.grid_w, div, row * pitch, col, yc,
                                        xc, entry_y, entry_x);
               }
           }
@@ -381,21 +580,182 @@ roialign_bwd_plane_kernel(const float* __restrict__ dy, float* __restrict__ dx,
     if (use_bulk) ptx::fence_proxy_async();   // my shared-memory writes -> visible to the copy engine
     __syncthreads();
     // the finished plane leaves for HBM: each dX element is written exactly once
-    if (use_bulk) {
-      if (tid == 0) {
-        const uint32_t bytes = (uint32_t)plane_elems * 4u;
-        for (uint32_t off = 0; off < bytes; off += kBulkChunk) {
-          const uint32_t nb = bytes - off < kBulkChunk ? bytes - off : kBulkChunk;
-          ptx::bulk_s2g((char*)gplane + off, (const char*)plane + off, nb);
-        }
-        ptx::bulk_commit();
-        ptx::bulk_wait_read();
+    store_plane(gplane, plane, height, width, pitch, use_bulk);
+  }
+  if (use_bulk && tid < 32) ptx::bulk_wait_all();
+}
+
+// Everything a warp needs for one (roi, band) pair, held in registers so that the loads of
+// pair i+1 are in flight while pair i is computed.
+template <int GR>
+struct PairRegs {
+  int nrows, nxcell;
+  const AxisCell* xcells;
+  float g[GR > 0 ? GR : 1];   // lane's share of the dy tile
+  int4 ya, yb;                // row cell `lane` of the band: chunks A and B
+  int4 xa, xb;                // column cell `lane`: chunks A and B
+};
+
+template <int GR>
+__device__ __forceinline__ void issue_pair_loads(PairRegs<GR>& r, const int4 p0, const int4 p1,
+                                                 const float* __restrict__ dy, const AxisCell* __restrict__ cells,
+                                                 int channels, int c, int bins, int lane) {
+  // p0 = {roi, nrows, ycell, xcell}, p1 = {nxcell, -, -, -}
+  r.nrows = p0.y;
+  r.nxcell = p1.x;
+  r.xcells = cells + p0.w;
+  const float* dtop = dy + ((size_t)p0.x * channels + c) * bins;
+#pragma unroll
+  for (int i = 0; i < GR; ++i) r.g[i] = (lane + 32 * i < bins) ? __ldg(dtop + lane + 32 * i) : 0.0f;
+  const int yrow = lane < r.nrows ? lane : 0;
+  const int4* yc = reinterpret_cast<const int4*>(cells + p0.z + yrow);
+  r.ya = __ldg(yc);
+  r.yb = __ldg(yc + 1);
+  const int xcol = lane < r.nxcell ? lane : 0;
+  const int4* xc = reinterpret_cast<const int4*>(r.xcells + xcol);
+  r.xa = __ldg(xc);
+  r.xb = __ldg(xc + 1);
+}
+
+// One column cell (this lane) against the rows of the band (held one per lane in ya/yb).
+// `simple` is warp-uniform: no lane has more than two merged column hits.
+__device__ __forceinline__ void fast_rows(float* plane, const float* g, int pooled_w, int nrows, const int4 ya,
+                                          const int4 yb, const AxisHit* __restrict__ hits, bool simple,
+                                          bool active, int col, int nxh, int x0p, float x0w, int x1p,
+                                          float x1w, int xhit_first) {
+  for (int r = 0; r < nrows; ++r) {
+    const int rowpix = __shfl_sync(0xffffffffu, ya.x, r);
+    const int nyh = __shfl_sync(0xffffffffu, ya.y, r);
+    if (simple && nyh <= 2) {        // warp-uniform: the common shape, at most two hits per axis
+      const int y0p = __shfl_sync(0xffffffffu, ya.z, r);
+      const float y0w = __int_as_float(__shfl_sync(0xffffffffu, ya.w, r));
+      const float* g0 = g + y0p * pooled_w;
+      float acc = (y0w * x0w) * g0[x0p];
+      if (nxh > 1) acc = fmaf(y0w * x1w, g0[x1p], acc);
+      if (nyh > 1) {
+        const int y1p = __shfl_sync(0xffffffffu, yb.x, r);
+        const float y1w = __int_as_float(__shfl_sync(0xffffffffu, yb.y, r));
+        const float* g1 = g + y1p * pooled_w;
+        acc = fmaf(y1w * x0w, g1[x0p], acc);
+        if (nxh > 1) acc = fmaf(y1w * x1w, g1[x1p], acc);
       }
+      if (active) plane[rowpix + col] += acc;
     } else {
-      for (int i = tid; i < plane_elems; i += blockDim.x) gplane[i] = plane[i];
+      // many bins fold onto this pixel (tiny ROIs): walk the full hit lists
+      const int yhit_first = __shfl_sync(0xffffffffu, yb.z, r);
+      if (active) {
+        float acc = 0.0f;
+        for (int a = 0; a < nyh; ++a) {
+          const AxisHit hy = load_hit(hits + yhit_first + a);
+          const float* ga = g + hy.p * pooled_w;
+          for (int b = 0; b < nxh; ++b) {
+            const AxisHit hx = load_hit(hits + xhit_first + b);
+            acc = fmaf(hy.w * hx.w, ga[hx.p], acc);
+          }
+        }
+        plane[rowpix + col] += acc;
+      }
     }
   }
-  if (use_bulk && tid == 0) ptx::bulk_wait_all();
+}
+
+// Merged weights, FMA, loads of the next (roi, band) pair prefetched: the default backward.
+// Results are reproducible run to run (fixed ownership, fixed order) but the contributions
+// of a ROI to a pixel are summed before they are added, so they are not bit-identical to
+// the single-thread reference (use the canonical kernel for that).
+template <int GR>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+roialign_bwd_plane_fast_kernel(const float* __restrict__ dy, float* __restrict__ dx,
+                               const AxisCell* __restrict__ cells, const AxisHit* __restrict__ hits,
+                               const BandPair* __restrict__ pairs, const int* __restrict__ pair_count,
+                               const int* __restrict__ img_start, int num_images, int channels, int height,
+                               int width, int pooled_h, int pooled_w, int accumulate, int use_bulk,
+                               int gslot_floats) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  float* plane = reinterpret_cast<float*>(smem_raw);
+  const int pitch = width;                      // dense rows: one row per warp instruction
+  const int plane_elems = height * width;
+  const int bins = pooled_h * pooled_w;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* gslot = plane + (size_t)height * pitch + (size_t)warp * gslot_floats;
+
+  if (tid == 0 && use_bulk) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+
+  const int planes = num_images * channels;
+  for (int p = blockIdx.x; p < planes; p += gridDim.x) {
+    const int n = p / channels, c = p - n * channels;
+    const int j0 = __ldg(img_start + n), j1 = __ldg(img_start + n + 1);
+    float* gplane = dx + ((size_t)n * channels + c) * plane_elems;
+    if (j0 == j1) {
+      if (!accumulate)
+        for (int i = tid; i < plane_elems; i += blockDim.x) gplane[i] = 0.0f;
+      continue;
+    }
+    const int npairs = __ldg(pair_count + n * kBands + warp);
+    const int4* plist = reinterpret_cast<const int4*>(pairs + (size_t)kBands * j0 + (size_t)warp * (j1 - j0));
+    // the first pair's loads overlap the plane initialisation
+    PairRegs<GR> cur, nxt;
+    int4 q0 = make_int4(0, 0, 0, 0), q1 = q0;       // pair record after next
+    if (npairs > 0) issue_pair_loads<GR>(cur, __ldg(plist), __ldg(plist + 1), dy, cells, channels, c, bins, lane);
+    if (npairs > 1) {
+      q0 = __ldg(plist + 2);
+      q1 = __ldg(plist + 3);
+    }
+
+    __syncthreads();   // the previous plane has left shared memory
+    if (accumulate) {
+      load_plane(plane, gplane, height, width, pitch, &bar, parity, use_bulk);
+    } else {
+      float4* p4 = reinterpret_cast<float4*>(plane);
+      const int n4 = (height * pitch) >> 2;
+      for (int i = tid; i < n4; i += blockDim.x) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = (n4 << 2) + tid; i < height * pitch; i += blockDim.x) plane[i] = 0.0f;
+      __syncthreads();
+    }
+
+    for (int i = 0; i < npairs; ++i) {
+      if (i + 1 < npairs) {
+        issue_pair_loads<GR>(nxt, q0, q1, dy, cells, channels, c, bins, lane);
+        if (i + 2 < npairs) {
+          q0 = __ldg(plist + 2 * (i + 2));
+          q1 = __ldg(plist + 2 * (i + 2) + 1);
+        }
+      }
+      // dy tile of the current pair -> this warp's slot
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < GR; ++k)
+        if (lane + 32 * k < bins) gslot[lane + 32 * k] = cur.g[k];
+      __syncwarp();
+
+      {
+        const bool active = lane < cur.nxcell;
+        const bool simple = __all_sync(0xffffffffu, !active || cur.xa.y <= 2);
+        fast_rows(plane, gslot, pooled_w, cur.nrows, cur.ya, cur.yb, hits, simple, active, cur.xa.x, cur.xa.y,
+                  cur.xa.z, __int_as_float(cur.xa.w), cur.xb.x, __int_as_float(cur.xb.y), cur.xb.z);
+      }
+      for (int xs = 32; xs < cur.nxcell; xs += 32) {      // more than 32 touched columns
+        const bool active = xs + lane < cur.nxcell;
+        const int4* xc = reinterpret_cast<const int4*>(cur.xcells + (active ? xs + lane : 0));
+        const int4 xa = __ldg(xc), xb = __ldg(xc + 1);
+        const bool simple = __all_sync(0xffffffffu, !active || xa.y <= 2);
+        fast_rows(plane, gslot, pooled_w, cur.nrows, cur.ya, cur.yb, hits, simple, active, xa.x, xa.y, xa.z,
+                  __int_as_float(xa.w), xb.x, __int_as_float(xb.y), xb.z);
+      }
+      __syncwarp();   // the next ROI may hand a pixel to another lane
+      cur = nxt;
+    }
+    if (use_bulk) ptx::fence_proxy_async();   // my shared-memory writes -> visible to the copy engine
+    __syncthreads();
+    store_plane(gplane, plane, height, width, pitch, use_bulk);
+  }
+  if (use_bulk && tid < 32) ptx::bulk_wait_all();
 }
 
 template <typename K>
@@ -411,18 +771,38 @@ int ctas_per_sm(size_t smem_bytes, int threads, int smem_optin) {
   return n < 1 ? 1 : (n > 8 ? 8 : n);
 }
 
+// Row pitch against shared-memory bank conflicts: lanes of a warp read the same columns of
+// several rows, so consecutive rows must start in different banks.  A pitch that is 4 mod 8
+// floats gives 8 distinct row phases and keeps rows 16-byte aligned for the bulk copies.
+int pick_pitch(int width) {
+  int p = (width + 3) / 4 * 4;
+  if ((p / 4) % 2 == 0) p += 4;
+  return p;
+}
+
 }  // namespace
 
 bool plane_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_optin, PlanePlan* plan) {
   if (a.num_images < 0 || a.num_images > 4096) return false;
   if ((long long)(a.num_images + 1) * a.num_rois > (1ll << 27)) return false;   // grouping cost
-  const size_t plane_bytes = (size_t)a.height * a.width * sizeof(float);
-  const size_t smem = (plane_bytes + 127) / 128 * 128;
-  if (smem + 64 > (size_t)smem_optin) return false;
-  plan->smem_bytes = smem;
-  plan->threads = kMaxThreads;
-  plan->use_bulk = (plane_bytes % 16 == 0) && ((uintptr_t)plane_ptr % 16 == 0) ? 1 : 0;
-  plan->ctas_per_sm = ctas_per_sm(smem, kMaxThreads, smem_optin);
+  const size_t budget = (size_t)smem_optin - 64;      // static shared memory of the kernels
+  const size_t dense = (size_t)a.height * a.width * sizeof(float);
+  if (dense > budget) return false;
+  int pitch = pick_pitch(a.width);
+  if ((size_t)a.height * pitch * sizeof(float) > budget) pitch = a.width;   // dense rows as a last resort
+  plan->pitch = pitch;
+  plan->plane_bytes = (size_t)a.height * pitch * sizeof(float);
+  plan->bwd_pitch = a.width;
+  plan->bwd_plane_bytes = dense;
+  const int bins = a.pooled_h * a.pooled_w;
+  const size_t gslot = (size_t)((bins + 31) / 32 * 32);
+  plan->gslot_floats = dense + gslot * sizeof(float) * kBands <= budget ? (int)gslot : 0;
+  // the fast kernel keeps the lane's share of a dy tile in at most 7 registers
+  plan->fast_bwd = (plan->gslot_floats > 0 && bins <= 7 * 32 && a.height <= 32 * kBands) ? 1 : 0;
+  plan->use_bulk = (a.width % 4 == 0) && ((uintptr_t)plane_ptr % 16 == 0) ? 1 : 0;
+  plan->ctas_per_sm = ctas_per_sm(plan->plane_bytes, kRegularThreads, smem_optin);
+  plan->bwd_ctas_per_sm =
+      ctas_per_sm(dense + (size_t)plan->gslot_floats * sizeof(float) * kBands, kBwdThreads, smem_optin);
   return true;
 }
 
@@ -433,38 +813,70 @@ cudaError_t launch_fwd_plane(const RoiAlignArgs& a, const PlanePlan& plan, const
   if (planes == 0 || a.num_rois == 0) return cudaSuccess;
   long long grid = (long long)num_sms * plan.ctas_per_sm;
   if (grid > planes) grid = planes;
+  const int bins = a.pooled_h * a.pooled_w;
+  const bool regular = t.regular && bins <= kRegularThreads && a.sampling_ratio >= 1 && a.sampling_ratio <= 4;
+#define MOBULA_FWD_REG(G, U)                                                                        \
+  do {                                                                                              \
+    cudaError_t e = set_smem(roialign_fwd_plane_regular_kernel<G, U>, plan.plane_bytes);            \
+    if (e != cudaSuccess) return e;                                                                 \
+    roialign_fwd_plane_regular_kernel<G, U><<<(unsigned)grid, kRegularThreads, plan.plane_bytes,    \
+                                              stream>>>(                                            \
+        data, out, t.order, t.axis, t.img_start, a.num_images, a.channels, a.height, a.width,       \
+        plan.pitch, a.pooled_h, a.pooled_w, accumulate, plan.use_bulk);                             \
+  } while (0)
 #define MOBULA_FWD(G)                                                                            \
   do {                                                                                           \
-    cudaError_t e = set_smem(roialign_fwd_plane_kernel<G>, plan.smem_bytes);                     \
+    cudaError_t e = set_smem(roialign_fwd_plane_kernel<G>, plan.plane_bytes);                    \
     if (e != cudaSuccess) return e;                                                              \
-    roialign_fwd_plane_kernel<G><<<(unsigned)grid, plan.threads, plan.smem_bytes, stream>>>(     \
+    roialign_fwd_plane_kernel<G><<<(unsigned)grid, kMaxThreads, plan.plane_bytes, stream>>>(    \
         data, out, a.rois, t.recs, t.axis, t.img_start, a.num_images, a.channels, a.height,      \
-        a.width, a.pooled_h, a.pooled_w, a.scale, a.sampling_ratio, accumulate, plan.use_bulk);  \
+        a.width, plan.pitch, a.pooled_h, a.pooled_w, a.scale, a.sampling_ratio, accumulate,      \
+        plan.use_bulk);                                                                          \
   } while (0)
-  switch (a.sampling_ratio) {
-    case 1: MOBULA_FWD(1); break;
-    case 2: MOBULA_FWD(2); break;
-    case 3: MOBULA_FWD(3); break;
-    case 4: MOBULA_FWD(4); break;
-    default: MOBULA_FWD(0); break;
+  if (regular) {
+    switch (a.sampling_ratio) {
+      case 1: MOBULA_FWD_REG(1, 4); break;
+      case 2: MOBULA_FWD_REG(2, 4); break;
+      case 3: MOBULA_FWD_REG(3, 2); break;
+      default: MOBULA_FWD_REG(4, 2); break;
+    }
+  } else {
+    MOBULA_FWD(0);
   }
 #undef MOBULA_FWD
+#undef MOBULA_FWD_REG
   count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_bwd_plane(const RoiAlignArgs& a, const PlanePlan& plan, const RoiTables& t,
-                             const float* dy, float* dx, int accumulate, int num_sms,
+                             const float* dy, float* dx, int accumulate, int canonical, int num_sms,
                              cudaStream_t stream) {
   const long long planes = (long long)a.num_images * a.channels;
   if (planes == 0) return cudaSuccess;
-  long long grid = (long long)num_sms * plan.ctas_per_sm;
+  long long grid = (long long)num_sms * plan.bwd_ctas_per_sm;
   if (grid > planes) grid = planes;
-  cudaError_t e = set_smem(roialign_bwd_plane_kernel, plan.smem_bytes);
-  if (e != cudaSuccess) return e;
-  roialign_bwd_plane_kernel<<<(unsigned)grid, plan.threads, plan.smem_bytes, stream>>>(
-      dy, dx, a.rois, t.recs, t.axis, t.cells, t.img_start, a.num_images, a.channels, a.height, a.width,
-      a.pooled_h, a.pooled_w, a.scale, a.sampling_ratio, accumulate, plan.use_bulk);
+  const size_t smem = plan.bwd_plane_bytes + (size_t)plan.gslot_floats * sizeof(float) * kBands;
+  if (canonical) {
+    cudaError_t e = set_smem(roialign_bwd_plane_canonical_kernel, smem);
+    if (e != cudaSuccess) return e;
+    roialign_bwd_plane_canonical_kernel<<<(unsigned)grid, kBwdThreads, smem, stream>>>(
+        dy, dx, a.rois, t.recs, t.axis, t.cells, t.img_start, a.num_images, a.channels, a.height, a.width,
+        plan.bwd_pitch, a.pooled_h, a.pooled_w, a.scale, a.sampling_ratio, accumulate, plan.use_bulk,
+        plan.gslot_floats);
+  } else {
+    const int bins = a.pooled_h * a.pooled_w;
+#define MOBULA_BWD_FAST(GR)                                                                         \
+  do {                                                                                              \
+    cudaError_t e = set_smem(roialign_bwd_plane_fast_kernel<GR>, smem);                             \
+    if (e != cudaSuccess) return e;                                                                 \
+    roialign_bwd_plane_fast_kernel<GR><<<(unsigned)grid, kBwdThreads, smem, stream>>>(              \
+        dy, dx, t.cells, t.hits, t.pairs, t.pair_count, t.img_start, a.num_images, a.channels,      \
+        a.height, a.width, a.pooled_h, a.pooled_w, accumulate, plan.use_bulk, plan.gslot_floats);   \
+  } while (0)
+    if (bins <= 64) MOBULA_BWD_FAST(2); else MOBULA_BWD_FAST(7);
+#undef MOBULA_BWD_FAST
+  }
   count_launch();
   return cudaGetLastError();
 }

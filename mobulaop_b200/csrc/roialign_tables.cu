@@ -6,7 +6,10 @@
 //                          image = the canonical accumulation order of the backward)
 //   2. roi_records_kernel  per-ROI geometry + arena offsets (exclusive scan)
 //   3. roi_fill_kernel     per-axis sample tables and, for the backward, the inverse map
-//                          row/column -> contiguous range of samples touching it
+//                          row/column -> contiguous range of samples touching it (plus the
+//                          per-pooled-index merged weights of the fast backward)
+//   4. roi_pairs_kernel    (fast backward) per image and row band, the ordered list of ROIs
+//                          with touched rows in the band
 // All arithmetic goes through roialign_common.cuh, i.e. rounds like the reference.
 #include "roialign_kernels.h"
 #include "roialign_common.cuh"
@@ -115,9 +118,10 @@ roi_records_kernel(const float* __restrict__ rois, int num_rois, int num_images,
 
 // One thread per (roi, axis): walks the samples of the axis in order.
 __global__ void __launch_bounds__(128)
-roi_fill_kernel(const float* __restrict__ rois, int num_rois, int height, int width, int pooled_h,
-                int pooled_w, float scale, int sampling_ratio, RoiRec* __restrict__ recs,
-                AxisEntry* __restrict__ axis, AxisCell* __restrict__ cells, int need_cells) {
+roi_fill_kernel(const float* __restrict__ rois, int num_rois, int height, int width, int pitch,
+                int pooled_h, int pooled_w, float scale, int sampling_ratio, RoiRec* __restrict__ recs,
+                AxisEntry* __restrict__ axis, AxisCell* __restrict__ cells, AxisHit* __restrict__ hits,
+                unsigned need) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = t >> 1, ax = t & 1;        // ax 0: y (rows), 1: x (columns)
   if (j >= num_rois) return;
@@ -130,9 +134,10 @@ roi_fill_kernel(const float* __restrict__ rois, int num_rois, int height, int wi
   const float start = ax ? g.start_w : g.start_h;
   const float bin = ax ? g.bin_w : g.bin_h;
   const int extent = ax ? width : height;
-  const int mult = ax ? 1 : width;
+  const int mult = ax ? 1 : pitch;
   AxisEntry* e = axis + off;
-  AxisCell* c = cells + (ax ? rec->xcell : rec->ycell);
+  const int cell_base = ax ? rec->xcell : rec->ycell;
+  AxisCell* c = cells + cell_base;
   int ncell = 0;
   int p = 0, i = 0;
   int pix_min = 0x7fffffff, pix_max = -1;
@@ -144,7 +149,7 @@ roi_fill_kernel(const float* __restrict__ rois, int num_rois, int height, int wi
     en.w_hi = tap.valid ? tap.wl : 0.0f;
     en.w_lo = tap.valid ? tap.wh : 0.0f;
     e[k] = en;
-    if (need_cells && tap.valid) {
+    if (need && tap.valid) {
       // lo and hi are non-decreasing in k and hi <= lo + 1, so a touched pixel is normally
       // the newest cell, the one before it, or a new one; the search only goes further back
       // if rounding ever made the positions non-monotonic (cells stay unique per pixel)
@@ -160,6 +165,10 @@ roi_fill_kernel(const float* __restrict__ rois, int num_rois, int height, int wi
           cell.pix = pix;
           cell.k_first = cell.k_last = k;
           cell.p_first = p;
+          cell.hit_first = cell.nhits = 0;
+          cell.h0p = cell.h1p = 0;
+          cell.h0w = cell.h1w = 0.0f;
+          cell.pad0 = cell.pad1 = 0;
           c[ncell++] = cell;
           pix_min = min(pix_min, pix);
           pix_max = max(pix_max, pix);
@@ -171,7 +180,50 @@ roi_fill_kernel(const float* __restrict__ rois, int num_rois, int height, int wi
       ++p;
     }
   }
-  if (need_cells) {
+  if (need & kNeedFast) {
+    // merged weights: for every touched pixel, one hit per pooled index
+    const float inv_count = ax ? 1.0f : __fdiv_rn(1.0f, g.count);
+    int nh = cell_base;                      // hits of this axis start at the cell base
+    for (int q = 0; q < ncell; ++q) {
+      AxisCell cell = c[q];
+      cell.hit_first = nh;
+      int cur_p = -1;
+      float w = 0.0f;
+      for (int k = cell.k_first; k <= cell.k_last; ++k) {
+        const AxisEntry en = e[k];
+        float wk = 0.0f;
+        if (en.lo == cell.pix) wk += en.w_lo;
+        if (en.hi == cell.pix) wk += en.w_hi;
+        const int pk = k / grid;
+        if (pk != cur_p) {
+          if (cur_p >= 0 && w != 0.0f) {
+            hits[nh].p = cur_p;
+            hits[nh].w = w * inv_count;
+            ++nh;
+          }
+          cur_p = pk;
+          w = 0.0f;
+        }
+        w += wk;
+      }
+      if (cur_p >= 0 && w != 0.0f) {
+        hits[nh].p = cur_p;
+        hits[nh].w = w * inv_count;
+        ++nh;
+      }
+      cell.nhits = nh - cell.hit_first;
+      if (cell.nhits > 0) {
+        cell.h0p = hits[cell.hit_first].p;
+        cell.h0w = hits[cell.hit_first].w;
+      }
+      if (cell.nhits > 1) {
+        cell.h1p = hits[cell.hit_first + 1].p;
+        cell.h1w = hits[cell.hit_first + 1].w;
+      }
+      c[q] = cell;
+    }
+  }
+  if (need) {
     const int first = ncell ? pix_min / mult : 0;
     const int last = ncell ? pix_max / mult : -1;
     if (ax) {
@@ -186,6 +238,50 @@ roi_fill_kernel(const float* __restrict__ rois, int num_rois, int height, int wi
   }
 }
 
+// One warp per (image, band): the ordered list of ROIs with cells in the band.
+__global__ void __launch_bounds__(128)
+roi_pairs_kernel(const RoiRec* __restrict__ recs, const AxisCell* __restrict__ cells,
+                 const int* __restrict__ img_start, int num_images, int height, int pitch,
+                 BandPair* __restrict__ pairs, int* __restrict__ pair_count) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= num_images * kBands) return;
+  const int n = w / kBands, b = w - n * kBands;
+  const int j0 = img_start[n], j1 = img_start[n + 1];
+  const int row0 = (int)(((long long)b * height) / kBands);
+  const int row1 = (int)(((long long)(b + 1) * height) / kBands);
+  const int pix0 = row0 * pitch, pix1 = row1 * pitch;
+  BandPair* out = pairs + (size_t)kBands * j0 + (size_t)b * (j1 - j0);
+  int count = 0;
+  for (int jb = j0; jb < j1; jb += 32) {
+    const int j = jb + lane;
+    BandPair pr;
+    pr.roi = 0;
+    pr.nrows = 0;
+    pr.ycell = pr.xcell = pr.nxcell = 0;
+    pr.pad0 = pr.pad1 = pr.pad2 = 0;
+    if (j < j1 && row1 > row0) {
+      const RoiRec r = recs[j];
+      if (r.yoff >= 0 && r.y_first < row1 && r.y_last >= row0 && r.nxcell > 0) {
+        const AxisCell* c = cells + r.ycell;
+        int a = 0;
+        while (a < r.nycell && c[a].pix < pix0) ++a;
+        int z = a;
+        while (z < r.nycell && c[z].pix < pix1) ++z;
+        pr.roi = r.roi;
+        pr.nrows = z - a;
+        pr.ycell = r.ycell + a;
+        pr.xcell = r.xcell;
+        pr.nxcell = r.nxcell;
+      }
+    }
+    const bool keep = pr.nrows > 0;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) out[count + __popc(m & ((1u << lane) - 1u))] = pr;
+    count += __popc(m);
+  }
+  if (lane == 0) pair_count[w] = count;
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 thread_local long long t_arena_override = -1;
@@ -194,51 +290,67 @@ long long arena_entries(const RoiAlignArgs& a) {
   if (t_arena_override >= 0) return t_arena_override;
   const long long per_grid = (long long)a.pooled_h + a.pooled_w;
   if (a.sampling_ratio > 0) return per_grid * a.sampling_ratio * a.num_rois;
-  // adaptive grids: room for an average grid of 16 samples per bin side; ROIs that do not
+  // adaptive grids: room for an average grid of 12 samples per bin side; ROIs that do not
   // fit stay untabled and are decoded on the fly by the kernels
-  long long e = per_grid * 16 * a.num_rois;
+  long long e = per_grid * 12 * a.num_rois;
   if (e < (1ll << 20)) e = 1ll << 20;
   if (e > (1ll << 27)) e = 1ll << 27;
   return e;
+}
+
+struct Layout {
+  size_t img_start, order, recs, axis, cells, hits, pairs, pair_count, total;
+};
+
+Layout layout_of(const RoiAlignArgs& a, unsigned need) {
+  const size_t R = (size_t)a.num_rois, N = (size_t)(a.num_images > 0 ? a.num_images : 0);
+  const size_t arena = (size_t)arena_entries(a);
+  Layout l;
+  size_t p = 0;
+  l.img_start = p;  p += align_up((N + 2) * sizeof(int), 256);
+  l.order = p;      p += align_up(R * sizeof(int), 256);
+  l.recs = p;       p += align_up(R * sizeof(RoiRec), 256);
+  l.axis = p;       p += align_up(arena * sizeof(AxisEntry), 256);
+  l.cells = p;      p += need ? align_up(2 * arena * sizeof(AxisCell), 256) : 0;
+  l.hits = p;       p += (need & kNeedFast) ? align_up(2 * arena * sizeof(AxisHit), 256) : 0;
+  l.pairs = p;      p += (need & kNeedFast) ? align_up(R * kBands * sizeof(BandPair), 256) : 0;
+  l.pair_count = p; p += (need & kNeedFast) ? align_up(N * kBands * sizeof(int), 256) : 0;
+  l.total = p;
+  return l;
 }
 
 }  // namespace
 
 void roi_tables_set_arena_override(long long entries) { t_arena_override = entries; }
 
-size_t roi_tables_bytes(const RoiAlignArgs& a) {
-  const size_t R = (size_t)a.num_rois, N = (size_t)(a.num_images > 0 ? a.num_images : 0);
-  const size_t arena = (size_t)arena_entries(a);
-  size_t bytes = 0;
-  bytes += align_up((N + 2) * sizeof(int), 256);
-  bytes += align_up(R * sizeof(int), 256);
-  bytes += align_up(R * sizeof(RoiRec), 256);
-  bytes += align_up(arena * sizeof(AxisEntry), 256);
-  bytes += align_up(2 * arena * sizeof(AxisCell), 256);
-  bytes += align_up((R + 1) * sizeof(int), 256);
-  return bytes;
-}
+size_t roi_tables_bytes(const RoiAlignArgs& a, unsigned need) { return layout_of(a, need).total; }
 
-RoiTables roi_tables_carve(const RoiAlignArgs& a, void* base) {
-  const size_t R = (size_t)a.num_rois, N = (size_t)(a.num_images > 0 ? a.num_images : 0);
-  const size_t arena = (size_t)arena_entries(a);
+RoiTables roi_tables_carve(const RoiAlignArgs& a, unsigned need, int pitch, void* base) {
+  const Layout l = layout_of(a, need);
   char* p = (char*)base;
   RoiTables t;
-  t.img_start = (int*)p;   p += align_up((N + 2) * sizeof(int), 256);
-  t.order = (int*)p;       p += align_up(R * sizeof(int), 256);
-  t.recs = (RoiRec*)p;     p += align_up(R * sizeof(RoiRec), 256);
-  t.axis = (AxisEntry*)p;  p += align_up(arena * sizeof(AxisEntry), 256);
-  t.cells = (AxisCell*)p;  p += align_up(2 * arena * sizeof(AxisCell), 256);
-  t.scan_tmp = (int*)p;
-  t.arena = (long long)arena;
+  t.img_start = (int*)(p + l.img_start);
+  t.order = (int*)(p + l.order);
+  t.recs = (RoiRec*)(p + l.recs);
+  t.axis = (AxisEntry*)(p + l.axis);
+  t.cells = (AxisCell*)(p + l.cells);
+  t.hits = (AxisHit*)(p + l.hits);
+  t.pairs = (BandPair*)(p + l.pairs);
+  t.pair_count = (int*)(p + l.pair_count);
+  t.arena = arena_entries(a);
+  t.pitch = pitch;
+  t.regular = (a.sampling_ratio > 0 && t_arena_override < 0) ? 1 : 0;
   return t;
 }
 
-cudaError_t launch_roi_tables(const RoiAlignArgs& a, const RoiTables& t, bool need_cells,
+cudaError_t launch_roi_tables(const RoiAlignArgs& a, const RoiTables& t, unsigned need,
                               cudaStream_t stream) {
   if (a.num_rois == 0) {
     // every segment is empty
-    return cudaMemsetAsync(t.img_start, 0, (size_t)(a.num_images + 2) * sizeof(int), stream);
+    cudaError_t e = cudaMemsetAsync(t.img_start, 0, (size_t)(a.num_images + 2) * sizeof(int), stream);
+    if (e == cudaSuccess && (need & kNeedFast) && a.num_images > 0)
+      e = cudaMemsetAsync(t.pair_count, 0, (size_t)a.num_images * kBands * sizeof(int), stream);
+    return e;
   }
   roi_group_kernel<<<a.num_images + 1, kGroupThreads, 0, stream>>>(a.rois, a.num_rois, a.num_images,
                                                                    t.img_start, t.order);
@@ -249,9 +361,15 @@ cudaError_t launch_roi_tables(const RoiAlignArgs& a, const RoiTables& t, bool ne
   count_launch();
   const int threads = 2 * a.num_rois;
   roi_fill_kernel<<<(threads + 127) / 128, 128, 0, stream>>>(
-      a.rois, a.num_rois, a.height, a.width, a.pooled_h, a.pooled_w, a.scale, a.sampling_ratio,
-      t.recs, t.axis, t.cells, need_cells ? 1 : 0);
+      a.rois, a.num_rois, a.height, a.width, t.pitch, a.pooled_h, a.pooled_w, a.scale,
+      a.sampling_ratio, t.recs, t.axis, t.cells, t.hits, need);
   count_launch();
+  if ((need & kNeedFast) && a.num_images > 0) {
+    const int warps = a.num_images * kBands;
+    roi_pairs_kernel<<<(warps * 32 + 127) / 128, 128, 0, stream>>>(
+        t.recs, t.cells, t.img_start, a.num_images, a.height, t.pitch, t.pairs, t.pair_count);
+    count_launch();
+  }
   return cudaGetLastError();
 }
 

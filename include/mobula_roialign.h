@@ -61,7 +61,12 @@ extern "C" {
 #define MOBULA_ROIALIGN_ALGO_AUTO 0u
 #define MOBULA_ROIALIGN_ALGO_GATHER 1u /* per-(roi,bin) threads, taps from global memory   */
 #define MOBULA_ROIALIGN_ALGO_PLANE 2u  /* one CTA owns a whole (image, channel) plane in
-                                          shared memory (TMA bulk copy in / out)           */
+                                          shared memory (TMA bulk copy in / out); handles
+                                          adaptive sampling grids; its canonical-order
+                                          backward is the deterministic mode                */
+#define MOBULA_ROIALIGN_ALGO_RESIDENT 3u /* fixed sampling ratio: padded plane resident in
+                                          shared memory, lean per-call ROI tables, work split
+                                          evenly over the SMs; the default when it applies  */
 
 /* ------------------------------------------------------------------------- *
  * 1. Drop-in symbols (reference ABI)                                         *

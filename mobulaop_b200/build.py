@@ -16,7 +16,7 @@ LIB_DIR = os.path.join(PKG_DIR, 'lib')
 LIB_NAME = 'libmobula_roialign_sm100.so'
 LIB_PATH = os.path.join(LIB_DIR, LIB_NAME)
 
-SOURCES = ['roialign_api.cu', 'roialign_gather.cu', 'roialign_tables.cu', 'roialign_plane.cu']
+SOURCES = ['roialign_api.cu', 'roialign_gather.cu', 'roialign_tables.cu', 'roialign_plane.cu', 'roialign_resident.cu']
 HEADERS = ['roialign_kernels.h', 'roialign_common.cuh', 'ptx_sm100.cuh',
            os.path.join('..', '..', 'include', 'mobula_roialign.h')]
 
@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [find_nvcc()] + NVCC_FLAGS
+    cmd = [find_nvcc()] + NVCC_FLAGS + os.environ.get('MOBULA_NVCC_EXTRA', '').split()
     if os.path.exists('/usr/bin/g++'):
         cmd += ['-ccbin', '/usr/bin/g++']     # the image's $CC wrapper lacks libgomp specs
     if verbose:

@@ -170,31 +170,55 @@ static int release_tables(DeviceState& st, cudaStream_t stream) {
   return MOBULA_OK;
 }
 
+// Workspace of the resident kernels: same buffer, same hand-over rules as prepare_tables.
+static int prepare_workspace(DeviceState& st, size_t bytes, cudaStream_t stream, void** ws) {
+  if (st.ws_used && st.ws_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, st.ws_done, 0));
+  if (bytes > st.workspace.bytes && st.ws_used) CUDA_TRY(cudaEventSynchronize(st.ws_done));
+  CUDA_TRY(st.workspace.reserve(bytes, stream));
+  *ws = st.workspace.ptr;
+  return MOBULA_OK;
+}
+
 static int forward_device(DeviceState& st, int device, cudaStream_t stream, const float* data,
                           const float* rois, float* out, const RoiAlignArgs& a, unsigned flags) {
   (void)device;
   (void)rois;
   const int accumulate = (flags & MOBULA_ROIALIGN_ACCUMULATE) ? 1 : 0;
   const unsigned algo = algo_of(flags);
-  if (algo > MOBULA_ROIALIGN_ALGO_PLANE)
+  if (algo > MOBULA_ROIALIGN_ALGO_RESIDENT)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown forward algorithm %u", algo);
-  PlanePlan plan;
-  const bool plane_ok = plane_supported(a, data, st.smem_optin, &plan);
-  if (algo == MOBULA_ROIALIGN_ALGO_PLANE && !plane_ok)
+  const bool no_tables = (flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) != 0;
+  ResidentPlan rplan;
+  const bool resident_ok = !no_tables && resident_supported(a, data, st.smem_optin, &rplan);
+  if (algo == MOBULA_ROIALIGN_ALGO_RESIDENT && !resident_ok)
     return fail(MOBULA_ERR_UNSUPPORTED,
-                "plane algorithm needs num_images in [0, 4096] and a %dx%d fp32 plane within %d bytes "
-                "of shared memory", a.height, a.width, st.smem_optin);
-  if (algo == MOBULA_ROIALIGN_ALGO_GATHER || !plane_ok) {
-    t_algo[0] = "gather";
-    CUDA_TRY(launch_fwd_gather(a, data, out, accumulate, stream));
-    return MOBULA_OK;
+                "resident algorithm needs num_images in [0, 4096], sampling_ratio in [1, 4], at most "
+                "64 samples per ROI axis pair and a padded %dx%d fp32 plane within %d bytes of shared "
+                "memory", a.height, a.width, st.smem_optin);
+  if (resident_ok && (algo == MOBULA_ROIALIGN_ALGO_RESIDENT || algo == MOBULA_ROIALIGN_ALGO_AUTO)) {
+    t_algo[0] = "resident";
+    void* ws = nullptr;
+    int rc = prepare_workspace(st, resident_fwd_workspace(a, rplan), stream, &ws);
+    if (rc) return rc;
+    CUDA_TRY(launch_fwd_resident(a, rplan, ws, data, out, accumulate, st.num_sms, stream));
+    return release_tables(st, stream);
   }
-  t_algo[0] = "plane";
-  RoiTables tables;
-  int rc = prepare_tables(st, a, 0u, plan.pitch, flags, stream, &tables);
-  if (rc) return rc;
-  CUDA_TRY(launch_fwd_plane(a, plan, tables, data, out, accumulate, st.num_sms, stream));
-  return release_tables(st, stream);
+  if (algo == MOBULA_ROIALIGN_ALGO_PLANE) {
+    PlanePlan plan;
+    if (!plane_supported(a, data, st.smem_optin, &plan))
+      return fail(MOBULA_ERR_UNSUPPORTED,
+                  "plane algorithm needs num_images in [0, 4096] and a %dx%d fp32 plane within %d "
+                  "bytes of shared memory", a.height, a.width, st.smem_optin);
+    t_algo[0] = "plane";
+    RoiTables tables;
+    int rc = prepare_tables(st, a, 0u, plan.pitch, flags, stream, &tables);
+    if (rc) return rc;
+    CUDA_TRY(launch_fwd_plane(a, plan, tables, data, out, accumulate, st.num_sms, stream));
+    return release_tables(st, stream);
+  }
+  t_algo[0] = "gather";      // any shape, any sampling grid
+  CUDA_TRY(launch_fwd_gather(a, data, out, accumulate, stream));
+  return MOBULA_OK;
 }
 
 static int backward_device(DeviceState& st, int device, cudaStream_t stream, const float* dy,
@@ -206,40 +230,39 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
   const unsigned algo = algo_of(flags);
   if (mode != MOBULA_ROIALIGN_BWD_ATOMIC && mode != MOBULA_ROIALIGN_BWD_DETERMINISTIC)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward mode %d", mode);
-  if (algo > MOBULA_ROIALIGN_ALGO_PLANE)
+  if (algo > MOBULA_ROIALIGN_ALGO_RESIDENT)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward algorithm %u", algo);
   if (!accumulate && a.num_images < 0)
     return fail(MOBULA_ERR_INVALID_ARGUMENT,
                 "backward without MOBULA_ROIALIGN_ACCUMULATE needs num_images >= 0");
-  PlanePlan plan;
-  const bool plane_ok = plane_supported(a, dx, st.smem_optin, &plan);
   const bool deterministic = mode == MOBULA_ROIALIGN_BWD_DETERMINISTIC;
   if (deterministic && algo == MOBULA_ROIALIGN_ALGO_GATHER)
     return fail(MOBULA_ERR_UNSUPPORTED, "the gather backward uses global atomics: not deterministic");
-  if ((deterministic || algo == MOBULA_ROIALIGN_ALGO_PLANE) && !plane_ok)
-    return fail(MOBULA_ERR_UNSUPPORTED,
-                "%s needs num_images in [0, 4096] and a %dx%d fp32 plane within %d bytes of shared "
-                "memory", deterministic ? "deterministic backward" : "plane algorithm", a.height,
-                a.width, st.smem_optin);
-  if (algo == MOBULA_ROIALIGN_ALGO_GATHER || !plane_ok) {
-    t_algo[1] = "gather";
-    if (!accumulate) {
-      const size_t bytes = (size_t)a.num_images * a.channels * a.height * a.width * sizeof(float);
-      if (bytes) CUDA_TRY(cudaMemsetAsync(dx, 0, bytes, stream));
-    }
-    CUDA_TRY(launch_bwd_gather(a, dy, dx, stream));
-    return MOBULA_OK;
+  if (deterministic || algo == MOBULA_ROIALIGN_ALGO_PLANE) {
+    PlanePlan plan;
+    if (!plane_supported(a, dx, st.smem_optin, &plan))
+      return fail(MOBULA_ERR_UNSUPPORTED,
+                  "%s needs num_images in [0, 4096] and a %dx%d fp32 plane within %d bytes of shared "
+                  "memory", deterministic ? "deterministic backward" : "plane algorithm", a.height,
+                  a.width, st.smem_optin);
+    // owner-computes plane kernels: canonical order for the deterministic mode (also the
+    // fall-back when the merged tables cannot be used), merged weights otherwise
+    const bool canonical = deterministic || !plan.fast_bwd || (flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES);
+    t_algo[1] = canonical ? "plane-canonical" : "plane";
+    RoiTables tables;
+    int rc = prepare_tables(st, a, canonical ? kNeedCells : (kNeedCells | kNeedFast), plan.bwd_pitch, flags,
+                            stream, &tables);
+    if (rc) return rc;
+    CUDA_TRY(launch_bwd_plane(a, plan, tables, dy, dx, accumulate, canonical ? 1 : 0, st.num_sms, stream));
+    return release_tables(st, stream);
   }
-  // owner-computes plane kernels: canonical order for the deterministic mode (also the
-  // fall-back when the merged tables cannot be used), merged weights otherwise
-  const bool canonical = deterministic || !plan.fast_bwd || (flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES);
-  t_algo[1] = canonical ? "plane-canonical" : "plane";
-  RoiTables tables;
-  int rc = prepare_tables(st, a, canonical ? kNeedCells : (kNeedCells | kNeedFast), plan.bwd_pitch, flags,
-                          stream, &tables);
-  if (rc) return rc;
-  CUDA_TRY(launch_bwd_plane(a, plan, tables, dy, dx, accumulate, canonical ? 1 : 0, st.num_sms, stream));
-  return release_tables(st, stream);
+  t_algo[1] = "gather";
+  if (!accumulate) {
+    const size_t bytes = (size_t)a.num_images * a.channels * a.height * a.width * sizeof(float);
+    if (bytes) CUDA_TRY(cudaMemsetAsync(dx, 0, bytes, stream));
+  }
+  CUDA_TRY(launch_bwd_gather(a, dy, dx, stream));
+  return MOBULA_OK;
 }
 
 static RoiAlignArgs make_args(const float* rois, int num_rois, int num_images, int channels,

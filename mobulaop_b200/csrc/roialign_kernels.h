@@ -141,4 +141,27 @@ cudaError_t launch_bwd_plane(const RoiAlignArgs& a, const PlanePlan& plan, const
                              const float* dy, float* dx, int accumulate, int canonical, int num_sms,
                              cudaStream_t stream);
 
+// ---- resident family (roialign_resident.cu): fixed sampling ratio, padded plane resident in
+// shared memory, lean tables; the default whenever it applies ------------------------------
+// Stable partition of the ROI rows by image (roialign_tables.cu): img_start[N+2], order[R].
+cudaError_t launch_roi_group(const RoiAlignArgs& a, int* img_start, int* order, cudaStream_t stream);
+
+struct ResidentPlan {
+  int grid;            // sampling ratio
+  int pitch;           // floats between rows of the padded plane in shared memory
+  int per_roi;         // sample entries per ROI: (PH + PW) * grid
+  int fwd_two;         // the sampling_ratio == 2 forward (lane = sample column) applies
+  int ypairs, xslots;  // its table: row records (pairs) and column records per ROI
+  size_t plane_bytes;  // (H + 1) * pitch * 4
+  size_t fwd_smem;
+  size_t bwd_smem;
+  int use_bulk;        // rows can be moved with cp.async.bulk (16-byte alignment holds)
+};
+
+bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_optin, ResidentPlan* plan);
+size_t resident_fwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan);
+cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan, void* workspace,
+                                const float* data, float* out, int accumulate, int num_sms,
+                                cudaStream_t stream);
+
 }  // namespace mobula_b200

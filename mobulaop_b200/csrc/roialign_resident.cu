@@ -1,0 +1,637 @@
+// "resident" kernels: the fast path for a fixed sampling ratio (ROIAlign.cpp:47-51 with
+// sampling_ratio > 0) when one padded (image, channel) plane fits the shared memory of an SM.
+//
+// HBM sees the algorithmic traffic only: a CTA brings a plane global->shared once with the
+// bulk copy engine (one cp.async.bulk per row, completion on an mbarrier), every bilinear tap
+// of every ROI of that image is then a shared-memory access, and the plane never goes back
+// (forward) or goes back exactly once (backward, zero-fill fused).  What bounds these kernels
+// is the shared-memory pipe and the issue slots around it: a bilinear tap is a 4-byte gather
+// with ~2.3 bank conflicts per warp access whatever the lane mapping, so everything else is
+// kept off the critical path:
+//
+//   * ROI decoding is channel independent and is done once per call by a table kernel, in
+//     exactly the reference's rounding (roialign_common.cuh); entries hold ready-to-use byte
+//     offsets and weights and are fetched one ROI ahead of their use.
+//   * Padded plane: rows 0..H-1 / columns 0..W-1 hold the data, row H / column W repeat the
+//     last row / column, rows H+1, H+2 and columns W+1.. are zero.  The high tap of a sample
+//     is then ALWAYS one row below / one column right of the low tap (the reference's clamp
+//     y_high = y_low = H-1, bilinear.h:32-44, reads the repeated row with weight 0), and a
+//     sample outside the plane (bilinear.h:15-18) needs no branch: its entry points into the
+//     zero rows / columns, so it contributes exactly +0.
+//   * The work -- (plane, ROI) pairs -- is split evenly over the CTAs, not plane by plane:
+//     512 planes over 148 SMs would otherwise leave a 14% tail.
+//
+// forward : products and sums in the reference's order (bilinear.h:50-56, ROIAlign.cpp:56-74)
+//           -> bit-identical output.
+#include "roialign_kernels.h"
+#include "roialign_common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace mobula_b200 {
+
+namespace {
+
+constexpr int kFwdWarps = 16;
+constexpr int kFwdThreads = kFwdWarps * 32;
+constexpr int kMaxEntries = 64;      // generic forward: (PH + PW) * G entries, two per lane
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// One sample coordinate along one axis: byte offset of the low tap (rows: row * pitch * 4,
+// columns: col * 4) and the fraction l = weight of the high tap.  Rejected samples point at
+// the first zero row / column of the padded plane.
+struct AxisSample {
+  unsigned lo_off;
+  float l;
+};
+
+__device__ __forceinline__ AxisSample make_sample(float start, int p, float bin, int i, int grid, int extent,
+                                                  int stride_bytes) {
+  const AxisTap t = axis_decode(sample_pos(start, p, bin, i, grid), extent);
+  AxisSample s;
+  s.lo_off = (unsigned)((t.valid ? t.lo : extent + 1) * stride_bytes);
+  s.l = t.valid ? t.wl : 0.0f;
+  return s;
+}
+
+// ---- tables ------------------------------------------------------------------------------
+// generic forward: thread (j, k) writes entry k of the ROI at grouped position j, y entries
+// first; x = lo_off, y = hi_off (always lo_off + one row / column), z = l, w = 1 - l
+__global__ void __launch_bounds__(256)
+resident_fwd_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
+                          const int* __restrict__ img_start, int num_images, int height, int width,
+                          int pitch, int pooled_h, int pooled_w, float scale, int grid,
+                          uint4* __restrict__ entries) {
+  const int per_roi = (pooled_h + pooled_w) * grid;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int valid = __ldg(img_start + num_images);
+  if (t >= (long long)valid * per_roi) return;
+  const int j = (int)(t / per_roi), k = (int)(t - (long long)j * per_roi);
+  const int roi = __ldg(order + j);
+  const RoiGeom g = roi_decode(rois + (size_t)roi * 5, scale, pooled_h, pooled_w, grid);
+  const int ny = pooled_h * grid;
+  AxisSample s;
+  int stride;
+  if (k < ny) {
+    const int p = k / grid;
+    stride = pitch * 4;
+    s = make_sample(g.start_h, p, g.bin_h, k - p * grid, grid, height, stride);
+  } else {
+    const int kk = k - ny, p = kk / grid;
+    stride = 4;
+    s = make_sample(g.start_w, p, g.bin_w, kk - p * grid, grid, width, stride);
+  }
+  entries[t] = make_uint4(s.lo_off, s.lo_off + (unsigned)stride, __float_as_uint(s.l),
+                          __float_as_uint(__fsub_rn(1.0f, s.l)));
+}
+
+// sampling_ratio == 2 forward: per ROI `ypairs` 16-byte records {lo_off(iy=0), l, lo_off(iy=1), l}
+// -- one per bin row, padded with zero-row records -- followed by `xslots` 8-byte records
+// {lo_off, l}, one per sample column, padded with zero-column records.
+__global__ void __launch_bounds__(256)
+resident_fwd2_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
+                           const int* __restrict__ img_start, int num_images, int height, int width,
+                           int pitch, int pooled_h, int pooled_w, float scale, int ypairs, int xslots,
+                           uint2* __restrict__ entries) {
+  const int per_roi = 2 * ypairs + xslots;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int valid = __ldg(img_start + num_images);
+  if (t >= (long long)valid * per_roi) return;
+  const int j = (int)(t / per_roi), k = (int)(t - (long long)j * per_roi);
+  const int roi = __ldg(order + j);
+  const RoiGeom g = roi_decode(rois + (size_t)roi * 5, scale, pooled_h, pooled_w, 2);
+  AxisSample s;
+  if (k < 2 * ypairs) {
+    s.lo_off = (unsigned)((height + 1) * pitch * 4);
+    s.l = 0.0f;
+    if (k < 2 * pooled_h) s = make_sample(g.start_h, k >> 1, g.bin_h, k & 1, 2, height, pitch * 4);
+  } else {
+    const int kk = k - 2 * ypairs;
+    s.lo_off = (unsigned)((width + 1) * 4);
+    s.l = 0.0f;
+    if (kk < 2 * pooled_w) s = make_sample(g.start_w, kk >> 1, g.bin_w, kk & 1, 2, width, 4);
+  }
+  entries[t] = make_uint2(s.lo_off, __float_as_uint(s.l));
+}
+
+// ---- plane movement ----------------------------------------------------------------------
+// zero padding the loads never touch: columns [W + 1, pitch) of rows [0, H] and rows H+1, H+2
+__device__ __forceinline__ void zero_padding(float* plane, int height, int width, int pitch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  for (int r = warp; r <= height; r += warps)
+    for (int x = width + 1 + lane; x < pitch; x += 32) plane[r * pitch + x] = 0.0f;
+  for (int x = threadIdx.x; x < 2 * pitch; x += blockDim.x) plane[(height + 1) * pitch + x] = 0.0f;
+}
+
+// rows of `width` floats, dense in global memory, `pitch` floats apart in shared memory;
+// then the repeated column W and the repeated row H.  Ends with the plane visible to all.
+// `next` (may be null): the plane this CTA loads after this one -- the L2 is asked for it now,
+// so that its load finds it there.
+__device__ __forceinline__ void load_padded_plane(float* plane, const float* __restrict__ src,
+                                                  const float* __restrict__ next, int height, int width,
+                                                  int pitch, uint64_t* bar, uint32_t& parity, int use_bulk) {
+  (void)bar;
+  (void)parity;
+  (void)next;
+  if (use_bulk) {
+    // 16-byte asynchronous copies, every thread a strided share: thousands in flight per SM
+    // (the per-row cp.async.bulk variant reached 3 TB/s over the chip, this one is HBM bound)
+    const int w4 = width >> 2, total = height * w4;
+    int r = threadIdx.x / w4, c4 = threadIdx.x - r * w4;
+    const int dr = blockDim.x / w4, dc = blockDim.x - dr * w4;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      ptx::cp_async16(plane + (size_t)r * pitch + 4 * c4, src + (size_t)r * width + 4 * c4);
+      r += dr;
+      c4 += dc;
+      if (c4 >= w4) {
+        c4 -= w4;
+        ++r;
+      }
+    }
+    ptx::cp_async_wait_all();
+    __syncthreads();
+  } else {
+    for (int i = threadIdx.x; i < height * width; i += blockDim.x) {
+      const int r = i / width;
+      plane[r * pitch + (i - r * width)] = __ldg(src + i);
+    }
+    __syncthreads();
+  }
+  for (int r = threadIdx.x; r < height; r += blockDim.x) plane[r * pitch + width] = plane[r * pitch + width - 1];
+  __syncthreads();
+  for (int x = threadIdx.x; x <= width; x += blockDim.x)
+    plane[height * pitch + x] = plane[(height - 1) * pitch + x];
+  __syncthreads();
+}
+
+__device__ __forceinline__ float lds_f32(const unsigned char* plane, unsigned off) {
+  return *reinterpret_cast<const float*>(plane + off);
+}
+
+// The contiguous share [u0, u1) of this CTA out of `total` work units.
+__device__ __forceinline__ void cta_share(long long total, long long& u0, long long& u1) {
+  u0 = total * blockIdx.x / gridDim.x;
+  u1 = total * (blockIdx.x + 1) / gridDim.x;
+}
+
+// Output rows of the ROIs whose batch index is outside [0, N): they read nothing, the rows
+// are zero (the reference would read out of bounds, ROIAlign.cpp:43-44).
+__device__ __forceinline__ void zero_rows_of_invalid_rois(float* __restrict__ out, const int* __restrict__ order,
+                                                          const int* __restrict__ img_start, int num_images,
+                                                          long long per_roi_out) {
+  const int i0 = __ldg(img_start + num_images), i1 = __ldg(img_start + num_images + 1);
+  long long z0, z1;
+  cta_share((long long)(i1 - i0) * per_roi_out, z0, z1);
+  for (long long z = z0 + threadIdx.x; z < z1; z += blockDim.x) {
+    const int jj = (int)(z / per_roi_out);
+    out[(size_t)__ldg(order + i0 + jj) * per_roi_out + (size_t)(z - jj * per_roi_out)] = 0.0f;
+  }
+}
+
+// The next (plane, ROI range) of this CTA's share: plane (n, c), ROIs [jj0, jj1) of image n.
+struct PlaneWork {
+  int n, c, j0, jj0, jj1;
+};
+
+__device__ __forceinline__ PlaneWork next_plane(const int* __restrict__ img_start, int channels, long long& u,
+                                                long long u1, int& n) {
+  while ((long long)channels * __ldg(img_start + n + 1) <= u) ++n;
+  PlaneWork w;
+  w.n = n;
+  w.j0 = __ldg(img_start + n);
+  const int nroi = __ldg(img_start + n + 1) - w.j0;
+  const long long rel = u - (long long)channels * w.j0;
+  w.c = (int)(rel / nroi);
+  w.jj0 = (int)(rel - (long long)w.c * nroi);
+  w.jj1 = (int)min((long long)nroi, w.jj0 + (u1 - u));
+  u += w.jj1 - w.jj0;
+  return w;
+}
+
+// Plane of the work unit `u` (the one next_plane would return next), or null at the end.
+__device__ __forceinline__ const float* next_plane_ptr(const float* __restrict__ data,
+                                                       const int* __restrict__ img_start, int channels,
+                                                       size_t plane_elems, long long u, long long u1, int n) {
+  if (u >= u1) return nullptr;
+  while ((long long)channels * __ldg(img_start + n + 1) <= u) ++n;
+  const int j0 = __ldg(img_start + n), nroi = __ldg(img_start + n + 1) - j0;
+  const int c = (int)((u - (long long)channels * j0) / nroi);
+  return data + ((size_t)n * channels + c) * plane_elems;
+}
+
+// ---- generic forward (sampling ratio 1, 3, 4 and wide pooled shapes): lane = pooled bin ----
+template <int G>
+__device__ __forceinline__ float pool_bin(const unsigned char* plane, const uint4* __restrict__ ye,
+                                          const uint4* __restrict__ xe) {
+  uint4 ey[G], ex[G];
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    ey[i] = ye[i];
+    ex[i] = xe[i];
+  }
+  float acc = 0.0f;
+#pragma unroll
+  for (int iy = 0; iy < G; ++iy) {
+    const float ly = __uint_as_float(ey[iy].z), hy = __uint_as_float(ey[iy].w);
+#pragma unroll
+    for (int ix = 0; ix < G; ++ix) {
+      const float lx = __uint_as_float(ex[ix].z), hx = __uint_as_float(ex[ix].w);
+      const float v1 = lds_f32(plane, ey[iy].x + ex[ix].x), v2 = lds_f32(plane, ey[iy].x + ex[ix].y);
+      const float v3 = lds_f32(plane, ey[iy].y + ex[ix].x), v4 = lds_f32(plane, ey[iy].y + ex[ix].y);
+      // bilinear.h:50-56
+      const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx);
+      const float w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
+      acc = __fadd_rn(acc, tap_sum(w1, v1, w2, v2, w3, v3, w4, v4));
+    }
+  }
+  return acc;
+}
+
+// A warp owns one ROI at a time: its lanes fetch the ROI's entries (16 bytes each, coalesced,
+// one ROI ahead), park them in the warp's slot of shared memory and every lane then picks
+// the entries of its own bins.
+template <int G>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+resident_fwd_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
+                    const int* __restrict__ img_start, const uint4* __restrict__ entries, int num_images,
+                    int channels, int height, int width, int pitch, int pooled_h, int pooled_w,
+                    int accumulate, int use_bulk) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  float* plane = reinterpret_cast<float*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bins = pooled_h * pooled_w;
+  const int per_roi = (pooled_h + pooled_w) * G;
+  const size_t plane_floats = (size_t)(height + 3) * pitch;
+  uint4* slot = reinterpret_cast<uint4*>(smem_raw + plane_floats * 4) + warp * per_roi;
+  const size_t plane_elems = (size_t)height * width;
+  const CountDiv div(G * G);
+
+  zero_padding(plane, height, width, pitch);
+  if (tid == 0 && use_bulk) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  if (!accumulate) zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins);
+
+  // this lane's first bin, and the step to its next one (bins lane, lane + 32, ...)
+  const int ph0 = lane / pooled_w, pw0 = lane - ph0 * pooled_w;
+  const int dph = 32 / pooled_w, dpw = 32 - dph * pooled_w;
+
+  long long u, u1;
+  cta_share((long long)channels * __ldg(img_start + num_images), u, u1);
+  int n = 0;
+  while (u < u1) {
+    const PlaneWork w = next_plane(img_start, channels, u, u1, n);
+    __syncthreads();   // every warp is done reading the previous plane
+    load_padded_plane(plane, data + ((size_t)w.n * channels + w.c) * plane_elems,
+                      next_plane_ptr(data, img_start, channels, plane_elems, u, u1, n), height, width, pitch,
+                      &bar, parity, use_bulk);
+
+    int jj = w.jj0 + warp;
+    uint4 e0 = make_uint4(0, 0, 0, 0), e1 = e0;
+    int roi_next = 0;
+    if (jj < w.jj1) {
+      const uint4* src = entries + (size_t)(w.j0 + jj) * per_roi;
+      if (lane < per_roi) e0 = __ldg(src + lane);
+      if (lane + 32 < per_roi) e1 = __ldg(src + lane + 32);
+      roi_next = __ldg(order + w.j0 + jj);
+    }
+    for (; jj < w.jj1; jj += kFwdWarps) {
+      __syncwarp();    // the previous ROI's entries are no longer being read
+      if (lane < per_roi) slot[lane] = e0;
+      if (lane + 32 < per_roi) slot[lane + 32] = e1;
+      const int roi = roi_next;
+      __syncwarp();
+      if (jj + kFwdWarps < w.jj1) {
+        const uint4* src = entries + (size_t)(w.j0 + jj + kFwdWarps) * per_roi;
+        if (lane < per_roi) e0 = __ldg(src + lane);
+        if (lane + 32 < per_roi) e1 = __ldg(src + lane + 32);
+        roi_next = __ldg(order + w.j0 + jj + kFwdWarps);
+      }
+      float* orow = out + ((size_t)roi * channels + w.c) * bins;
+      int ph = ph0, pw = pw0;
+      for (int b = lane; b < bins; b += 32) {
+        const float y = div(pool_bin<G>(smem_raw, slot + ph * G, slot + (pooled_h + pw) * G));
+        if (accumulate) orow[b] = __fadd_rn(orow[b], y);
+        else orow[b] = y;
+        ph += dph;
+        pw += dpw;
+        if (pw >= pooled_w) {
+          pw -= pooled_w;
+          ++ph;
+        }
+      }
+    }
+  }
+}
+
+// ---- sampling_ratio == 2 forward (every BASELINE configuration but the adaptive one) -------
+// lane = one sample column of one row of bins.  Half-warp h works on bin row ph = 2 * it + h,
+// its 16 lanes on the sample columns sx = 2 * pw + ix of a chunk of 8 bins; a lane computes the
+// two samples (iy = 0, 1) of its column.  One warp instruction therefore reads two
+// feature-map rows at <= 16 columns each; a lane's column record stays in registers for the
+// whole ROI; the row records (one 16-byte broadcast load per half-warp and iteration) of the
+// NEXT ROI are fetched while the current one is computed, so no load latency is exposed.  The
+// two samples of a lane share the packed fp32x2 multiplies of sm_100 (each half rounds exactly
+// like the scalar instruction).  The four samples of a bin meet in
+// the lane of its first sample through two shuffles, in the reference's order
+// ((s00 + s01) + s10) + s11 (ROIAlign.cpp:56-72).
+// ITERS = ceil(PH / 2), NCH = chunks of 16 sample columns, ACC = add into the output.
+__device__ __forceinline__ float lds_at(unsigned addr, unsigned epoch) {
+  float v;
+  // `epoch` changes with every plane: it only keeps loads of different planes apart
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr), "r"(epoch));
+  return v;
+}
+__device__ __forceinline__ float lds_at4(unsigned addr, unsigned epoch) {
+  float v;
+  asm("ld.shared.f32 %0, [%1+4];" : "=f"(v) : "r"(addr), "r"(epoch));
+  return v;
+}
+
+#ifndef MOBULA_FWD2_WARPS
+#define MOBULA_FWD2_WARPS 16
+#endif
+constexpr int kFwd2Warps = MOBULA_FWD2_WARPS;
+constexpr int kFwd2Threads = kFwd2Warps * 32;
+
+template <int ITERS, int NCH>
+struct Roi2Regs {
+  uint4 y[ITERS];
+  uint2 x[NCH];
+  int roi;
+};
+
+template <int ITERS, int NCH>
+__device__ __forceinline__ void load_roi2(Roi2Regs<ITERS, NCH>& r, const uint2* __restrict__ ent,
+                                          const int* __restrict__ order_j, int h, int q) {
+  const uint4* ent_y = reinterpret_cast<const uint4*>(ent);
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) r.y[it] = __ldg(ent_y + 2 * it + h);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) r.x[ch] = __ldg(ent + 4 * ITERS + 16 * ch + q);
+  r.roi = __ldg(order_j);
+}
+
+template <int ITERS, int NCH, bool ACC>
+__global__ void __launch_bounds__(kFwd2Threads, 1)
+resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
+                     const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
+                     int channels, int height, int width, int pitch, int pooled_h, int pooled_w,
+                     int use_bulk) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  float* plane = reinterpret_cast<float*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bins = pooled_h * pooled_w;
+  constexpr int kPerRoi = 4 * ITERS + 16 * NCH;       // uint2 records
+  const size_t plane_elems = (size_t)height * width;
+  const int h = lane >> 4, q = lane & 15;
+  const unsigned sbase = ptx::smem_addr(smem_raw);
+  const unsigned row_bytes = (unsigned)pitch * 4u;
+
+  zero_padding(plane, height, width, pitch);
+  if (tid == 0 && use_bulk) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  if (!ACC) zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins);
+
+  // which of this lane's results are outputs: the first sample column of a bin, of an
+  // existing bin row
+  bool stores[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) stores[ch] = (q & 1) == 0 && 8 * ch + (q >> 1) < pooled_w;
+
+  long long u, u1;
+  cta_share((long long)channels * __ldg(img_start + num_images), u, u1);
+  int n = 0;
+  unsigned epoch = 0;
+  while (u < u1) {
+    const PlaneWork w = next_plane(img_start, channels, u, u1, n);
+    __syncthreads();   // every warp is done reading the previous plane
+#ifndef MOBULA_EXP_NOLOAD
+    load_padded_plane(plane, data + ((size_t)w.n * channels + w.c) * plane_elems,
+                      next_plane_ptr(data, img_start, channels, plane_elems, u, u1, n), height, width, pitch,
+                      &bar, parity, use_bulk);
+#endif
+    ++epoch;
+#ifdef MOBULA_EXP_NOROI
+    continue;
+#endif
+
+    int jj = w.jj0 + warp;
+    Roi2Regs<ITERS, NCH> nxt;
+    if (jj < w.jj1) load_roi2(nxt, entries + (size_t)(w.j0 + jj) * kPerRoi, order + w.j0 + jj, h, q);
+    for (; jj < w.jj1; jj += kFwd2Warps) {
+      const Roi2Regs<ITERS, NCH> cur = nxt;
+      if (jj + kFwd2Warps < w.jj1)
+        load_roi2(nxt, entries + (size_t)(w.j0 + jj + kFwd2Warps) * kPerRoi, order + w.j0 + jj + kFwd2Warps, h, q);
+
+      unsigned xa[NCH], xb[NCH];      // shared-memory address of the low column in row 0 / row 1
+      float2 lx2[NCH], hx2[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        xa[ch] = sbase + cur.x[ch].x;
+        xb[ch] = xa[ch] + row_bytes;
+        const float lx = __uint_as_float(cur.x[ch].y), hx = __fsub_rn(1.0f, lx);
+        lx2[ch] = make_float2(lx, lx);
+        hx2[ch] = make_float2(hx, hx);
+      }
+      // this lane's first output: bin (h, q / 2) of chunk 0
+      float* optr = out + ((size_t)cur.roi * channels + w.c) * bins + h * pooled_w + (q >> 1);
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const uint4 ey = cur.y[it];
+        const float2 ly2 = make_float2(__uint_as_float(ey.y), __uint_as_float(ey.w));
+        const float2 hy2 = make_float2(__fsub_rn(1.0f, ly2.x), __fsub_rn(1.0f, ly2.y));
+        const bool row_ok = 2 * it + h < pooled_h;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          // taps of sample iy = 0 in .x, of iy = 1 in .y: v1 v2 / v3 v4 as in bilinear.h:50-53
+          const unsigned a0 = xa[ch] + ey.x, b0 = xb[ch] + ey.x, a1 = xa[ch] + ey.z, b1 = xb[ch] + ey.z;
+          const float2 v1 = make_float2(lds_at(a0, epoch), lds_at(a1, epoch));
+          const float2 v2 = make_float2(lds_at4(a0, epoch), lds_at4(a1, epoch));
+          const float2 v3 = make_float2(lds_at(b0, epoch), lds_at(b1, epoch));
+          const float2 v4 = make_float2(lds_at4(b0, epoch), lds_at4(b1, epoch));
+          const float2 w1 = __fmul2_rn(hy2, hx2[ch]), w2 = __fmul2_rn(hy2, lx2[ch]);
+          const float2 w3 = __fmul2_rn(ly2, hx2[ch]), w4 = __fmul2_rn(ly2, lx2[ch]);
+          // the sums stay scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+          // (it honours .rn only for the scalar forms), which would change the rounding
+          const float2 p1 = __fmul2_rn(w1, v1), p2 = __fmul2_rn(w2, v2);
+          const float2 p3 = __fmul2_rn(w3, v3), p4 = __fmul2_rn(w4, v4);
+          float2 s;
+          s.x = __fadd_rn(__fadd_rn(__fadd_rn(p1.x, p2.x), p3.x), p4.x);
+          s.y = __fadd_rn(__fadd_rn(__fadd_rn(p1.y, p2.y), p3.y), p4.y);
+          const float s0n = __shfl_down_sync(0xffffffffu, s.x, 1);
+          const float s1n = __shfl_down_sync(0xffffffffu, s.y, 1);
+          float t = __fadd_rn(0.0f, s.x);
+          t = __fadd_rn(t, s0n);
+          t = __fadd_rn(t, s.y);
+          t = __fadd_rn(t, s1n);
+          const float y = __fmul_rn(t, 0.25f);     // count = 4: an exact scaling
+          if (stores[ch] && row_ok) {
+            float* o = optr + (2 * it) * pooled_w + 8 * ch;
+            if (ACC) *o = __fadd_rn(*o, y);
+            else *o = y;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename K>
+cudaError_t set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+template <typename K>
+cudaError_t resident_grid(K kernel, int threads, size_t smem, int num_sms, long long work, unsigned* grid) {
+  cudaError_t e = set_smem(kernel, smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  long long g = (long long)num_sms * per_sm;
+  if (g > work) g = work;
+  *grid = (unsigned)g;
+  return cudaSuccess;
+}
+
+struct FwdLayout {
+  size_t img_start, order, entries, total;
+};
+
+FwdLayout fwd_layout(const RoiAlignArgs& a, size_t entry_bytes_per_roi) {
+  FwdLayout l;
+  size_t p = 0;
+  l.img_start = p;  p += align_up((size_t)(a.num_images + 2) * sizeof(int), 256);
+  l.order = p;      p += align_up((size_t)a.num_rois * sizeof(int), 256);
+  l.entries = p;    p += align_up((size_t)a.num_rois * entry_bytes_per_roi, 256);
+  l.total = p;
+  return l;
+}
+
+}  // namespace
+
+bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_optin, ResidentPlan* plan) {
+  if (a.num_images < 0 || a.num_images > 4096) return false;
+  if (a.sampling_ratio < 1 || a.sampling_ratio > 4) return false;
+  const int per_roi = (a.pooled_h + a.pooled_w) * a.sampling_ratio;
+  // row pitch: room for the repeated and the zero columns, rows 16-byte aligned for the bulk
+  // copies, and 4 mod 8 floats so that consecutive rows start in different banks
+  int pitch = (a.width + 3 + 3) / 4 * 4;
+  if ((pitch / 4) % 2 == 0) pitch += 4;
+  const size_t plane_bytes = (size_t)(a.height + 3) * pitch * sizeof(float);
+  // the sampling_ratio == 2 kernel keeps its records in registers: no per-warp slots
+  const bool two = a.sampling_ratio == 2 && a.pooled_w <= 16 && a.pooled_h <= 16;
+  if (!two && per_roi > kMaxEntries) return false;
+  const size_t fwd_smem = plane_bytes + (two ? 0 : (size_t)kFwdWarps * per_roi * sizeof(uint4));
+  if (fwd_smem + 64 > (size_t)smem_optin) return false;
+  plan->grid = a.sampling_ratio;
+  plan->pitch = pitch;
+  plan->per_roi = per_roi;
+  plan->fwd_two = two ? 1 : 0;
+  plan->ypairs = 2 * ((a.pooled_h + 1) / 2);
+  plan->xslots = 16 * ((2 * a.pooled_w + 15) / 16);
+  plan->plane_bytes = plane_bytes;
+  plan->fwd_smem = fwd_smem;
+  plan->use_bulk = (a.width % 4 == 0) && ((uintptr_t)plane_ptr % 16 == 0) ? 1 : 0;
+  return true;
+}
+
+size_t resident_fwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan) {
+  const size_t per_roi = plan.fwd_two ? (size_t)(2 * plan.ypairs + plan.xslots) * sizeof(uint2)
+                                      : (size_t)plan.per_roi * sizeof(uint4);
+  return fwd_layout(a, per_roi).total;
+}
+
+cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan, void* workspace,
+                                const float* data, float* out, int accumulate, int num_sms,
+                                cudaStream_t stream) {
+  if (a.num_rois == 0 || a.channels == 0) return cudaSuccess;
+  const size_t per_roi_bytes = plan.fwd_two ? (size_t)(2 * plan.ypairs + plan.xslots) * sizeof(uint2)
+                                            : (size_t)plan.per_roi * sizeof(uint4);
+  const FwdLayout l = fwd_layout(a, per_roi_bytes);
+  char* base = (char*)workspace;
+  int* img_start = (int*)(base + l.img_start);
+  int* order = (int*)(base + l.order);
+  cudaError_t e = launch_roi_group(a, img_start, order, stream);
+  if (e != cudaSuccess) return e;
+  const long long work = (long long)a.num_rois * a.channels;
+  unsigned grid = 0;
+  if (plan.fwd_two) {
+    uint2* entries = (uint2*)(base + l.entries);
+    const long long threads = (long long)a.num_rois * (2 * plan.ypairs + plan.xslots);
+    resident_fwd2_table_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+        a.rois, order, img_start, a.num_images, a.height, a.width, plan.pitch, a.pooled_h, a.pooled_w,
+        a.scale, plan.ypairs, plan.xslots, entries);
+    count_launch();
+#define MOBULA_FWD2(ITERS, NCH, ACC)                                                                 \
+  do {                                                                                               \
+    e = resident_grid(resident_fwd2_kernel<ITERS, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms,   \
+                      work, &grid);                                                                  \
+    if (e != cudaSuccess) return e;                                                                  \
+    resident_fwd2_kernel<ITERS, NCH, ACC><<<grid, kFwd2Threads, plan.fwd_smem, stream>>>(            \
+        data, out, order, img_start, entries, a.num_images, a.channels, a.height, a.width,           \
+        plan.pitch, a.pooled_h, a.pooled_w, plan.use_bulk);                                          \
+  } while (0)
+#define MOBULA_FWD2_NCH(ITERS, NCH)                  \
+  do {                                               \
+    if (accumulate) MOBULA_FWD2(ITERS, NCH, true);   \
+    else MOBULA_FWD2(ITERS, NCH, false);             \
+  } while (0)
+#define MOBULA_FWD2_ITERS(ITERS)                             \
+  do {                                                       \
+    if (plan.xslots == 16) MOBULA_FWD2_NCH(ITERS, 1);        \
+    else MOBULA_FWD2_NCH(ITERS, 2);                          \
+  } while (0)
+    switch (plan.ypairs / 2) {
+      case 1: MOBULA_FWD2_ITERS(1); break;
+      case 2: MOBULA_FWD2_ITERS(2); break;
+      case 3: MOBULA_FWD2_ITERS(3); break;
+      case 4: MOBULA_FWD2_ITERS(4); break;
+      case 5: MOBULA_FWD2_ITERS(5); break;
+      case 6: MOBULA_FWD2_ITERS(6); break;
+      case 7: MOBULA_FWD2_ITERS(7); break;
+      default: MOBULA_FWD2_ITERS(8); break;
+    }
+#undef MOBULA_FWD2_ITERS
+#undef MOBULA_FWD2_NCH
+#undef MOBULA_FWD2
+    count_launch();
+    return cudaGetLastError();
+  }
+  uint4* entries = (uint4*)(base + l.entries);
+  const long long threads = (long long)a.num_rois * plan.per_roi;
+  resident_fwd_table_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+      a.rois, order, img_start, a.num_images, a.height, a.width, plan.pitch, a.pooled_h, a.pooled_w,
+      a.scale, plan.grid, entries);
+  count_launch();
+#define MOBULA_RESIDENT_FWD(G)                                                                      \
+  do {                                                                                              \
+    e = resident_grid(resident_fwd_kernel<G>, kFwdThreads, plan.fwd_smem, num_sms, work, &grid);    \
+    if (e != cudaSuccess) return e;                                                                 \
+    resident_fwd_kernel<G><<<grid, kFwdThreads, plan.fwd_smem, stream>>>(                           \
+        data, out, order, img_start, entries, a.num_images, a.channels, a.height, a.width,          \
+        plan.pitch, a.pooled_h, a.pooled_w, accumulate, plan.use_bulk);                             \
+  } while (0)
+  switch (plan.grid) {
+    case 1: MOBULA_RESIDENT_FWD(1); break;
+    case 2: MOBULA_RESIDENT_FWD(2); break;
+    case 3: MOBULA_RESIDENT_FWD(3); break;
+    default: MOBULA_RESIDENT_FWD(4); break;
+  }
+#undef MOBULA_RESIDENT_FWD
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace mobula_b200

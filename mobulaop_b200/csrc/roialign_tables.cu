@@ -343,6 +343,14 @@ RoiTables roi_tables_carve(const RoiAlignArgs& a, unsigned need, int pitch, void
   return t;
 }
 
+cudaError_t launch_roi_group(const RoiAlignArgs& a, int* img_start, int* order, cudaStream_t stream) {
+  if (a.num_rois == 0) return cudaMemsetAsync(img_start, 0, (size_t)(a.num_images + 2) * sizeof(int), stream);
+  roi_group_kernel<<<a.num_images + 1, kGroupThreads, 0, stream>>>(a.rois, a.num_rois, a.num_images,
+                                                                   img_start, order);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_roi_tables(const RoiAlignArgs& a, const RoiTables& t, unsigned need,
                               cudaStream_t stream) {
   if (a.num_rois == 0) {

@@ -20,7 +20,14 @@ from mobulaop_b200.testing import (assert_bit_exact, assert_scatter_close,
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not has_cuda(), reason='needs a CUDA device')]
 
-ALGOS = ['gather', 'plane', 'auto']
+ALGOS = ['gather', 'plane', 'resident', 'auto']
+
+
+def _skip_unless_supported(algo, pooled, sr):
+    """The resident kernels exist for a fixed sampling ratio of 1..4 and at most 64 sample
+    entries per ROI; asking for them explicitly elsewhere is an error by design."""
+    if algo == 'resident' and not (1 <= sr <= 4 and (pooled[0] + pooled[1]) * sr <= 64):
+        pytest.skip('resident kernels: fixed sampling ratio 1..4 only')
 
 
 @pytest.fixture(scope='module')
@@ -104,6 +111,7 @@ def _abs_sum(oracle, g):
 @pytest.mark.parametrize('name', golden_names())
 def test_forward_golden(direct, name, algo):
     g = load_golden(name)
+    _skip_unless_supported(algo, g['pooled'], g['sr'])
     y = direct.forward(g['data'], g['rois'], g['pooled'], g['scale'], g['sr'], algo=algo)
     assert_within_ulp_or_rel(y, g['y'], ulp=2, rtol=1e-6)
     assert_bit_exact(y, g['y'])         # same operations in the same order as the reference
@@ -113,6 +121,7 @@ def test_forward_golden(direct, name, algo):
 @pytest.mark.parametrize('name', golden_names())
 def test_backward_atomic_golden(direct, oracle, name, algo):
     g = load_golden(name)
+    _skip_unless_supported(algo, g['pooled'], g['sr'])
     dx = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], algo=algo)
     assert_scatter_close(dx, g['dx'], _abs_sum(oracle, g), rtol=1e-5)
 
@@ -143,6 +152,7 @@ SAMPLES = {
 @pytest.mark.parametrize('key', sorted(SAMPLES))
 def test_seeded_workload_parity(direct, oracle, key, algo):
     wl = SAMPLES[key]()
+    _skip_unless_supported(algo, wl.pooled, wl.sampling_ratio)
     data, rois, dy = WL.make_inputs(wl, seed=17)
     y_ref = oracle.forward(data, rois, wl.pooled, wl.scale, wl.sampling_ratio, threads=0)
     y = direct.forward(data, rois, wl.pooled, wl.scale, wl.sampling_ratio, algo=algo)

@@ -256,6 +256,24 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
     CUDA_TRY(launch_bwd_plane(a, plan, tables, dy, dx, accumulate, canonical ? 1 : 0, st.num_sms, stream));
     return release_tables(st, stream);
   }
+  {
+    ResidentPlan rplan;
+    const bool resident_ok = !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && a.num_images >= 0 &&
+                             resident_supported(a, dx, st.smem_optin, &rplan) && rplan.bwd_ok;
+    if (algo == MOBULA_ROIALIGN_ALGO_RESIDENT && !resident_ok)
+      return fail(MOBULA_ERR_UNSUPPORTED,
+                  "resident backward needs num_images in [0, 4096], sampling_ratio 2, pooled_w <= 16 and "
+                  "a %dx%d fp32 plane slab within %d bytes of shared memory", a.height, a.width,
+                  st.smem_optin);
+    if (resident_ok && (algo == MOBULA_ROIALIGN_ALGO_RESIDENT || algo == MOBULA_ROIALIGN_ALGO_AUTO)) {
+      t_algo[1] = "resident";
+      void* ws = nullptr;
+      int rc = prepare_workspace(st, resident_bwd_workspace(a, rplan), stream, &ws);
+      if (rc) return rc;
+      CUDA_TRY(launch_bwd_resident(a, rplan, ws, dy, dx, accumulate, st.num_sms, stream));
+      return release_tables(st, stream);
+    }
+  }
   t_algo[1] = "gather";
   if (!accumulate) {
     const size_t bytes = (size_t)a.num_images * a.channels * a.height * a.width * sizeof(float);

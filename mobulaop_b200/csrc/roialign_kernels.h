@@ -154,6 +154,8 @@ struct ResidentPlan {
   int ypairs, xslots;  // its table: row records (pairs) and column records per ROI
   size_t plane_bytes;  // (H + 1) * pitch * 4
   size_t fwd_smem;
+  int bwd_ok;          // the resident backward applies
+  int bwd_slabs, bwd_slab_rows, bwd_maxc, bwd_pitch2;
   size_t bwd_smem;
   int use_bulk;        // rows can be moved with cp.async.bulk (16-byte alignment holds)
 };
@@ -162,6 +164,12 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
 size_t resident_fwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan);
 cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan, void* workspace,
                                 const float* data, float* out, int accumulate, int num_sms,
+                                cudaStream_t stream);
+size_t resident_bwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan);
+// dX := scatter (accumulate = 0, zero-fill fused) or dX += scatter; not bit-identical to the
+// reference's single-thread order, reproducible run to run
+cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan, void* workspace,
+                                const float* dy, float* dx, int accumulate, int num_sms,
                                 cudaStream_t stream);
 
 }  // namespace mobula_b200

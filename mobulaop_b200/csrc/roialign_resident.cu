@@ -164,6 +164,10 @@ __device__ __forceinline__ void load_padded_plane(float* plane, const float* __r
   __syncthreads();
 }
 
+__device__ __forceinline__ void sts_at(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ float lds_f32(const unsigned char* plane, unsigned off) {
   return *reinterpret_cast<const float*>(plane + off);
 }
@@ -505,6 +509,434 @@ cudaError_t resident_grid(K kernel, int threads, size_t smem, int num_sms, long 
   return cudaSuccess;
 }
 
+// ==========================================================================================
+// backward (sampling_ratio == 2), "atomic"-mode replacement without atomics
+// ==========================================================================================
+// A CTA owns a slab of consecutive rows of one (image, channel) plane of dX in shared memory;
+// warp w of the CTA owns a band of rows of the slab and nobody else touches them, so the
+// gradient is accumulated with plain shared-memory read-modify-writes and the finished slab
+// goes to HBM once, with plain stores (the zero-fill of ROIAlign.py:33-34 is fused: every dX
+// element is written exactly once and never read).
+//
+// The scatter of one ROI is separable: the 2*2*PW (column, weight) taps of its sample columns
+// are merged per touched column once per call (table kernel), a lane owns one touched column
+// and first folds the dy row of a bin row with its column weights,
+//     T[col] = sum_pw Wx[col][pw] * dy[ph][pw] / count,
+// then adds wy * T into the <= 4 feature-map rows the two sample rows of that bin row touch.
+// Per bin row and touched row that is ONE conflict-free-ish shared-memory read-modify-write
+// for all touched columns, instead of 2*2*PW atomics.  Contributions of one ROI to one pixel
+// are summed before they are added, and the order of ROIs is fixed (ownership is static), so
+// the result is reproducible run to run but not bit-identical to the reference's
+// single-thread order (that is the deterministic mode, roialign_plane.cu).
+constexpr int kBwdWarps = 8;
+constexpr int kBwdThreads = kBwdWarps * 32;
+constexpr int kMaxSlotFloats = 256;   // dy tile of one (roi, channel): PH * PW <= 256 floats
+constexpr int kMaxHitsPerCol = 16;    // = max pooled_w
+
+// scan record of a ROI for the backward: x = first | last << 16 touched plane row
+// (first > last: nothing to do), y = roi row
+// column record: x = col_off | nhits << 16 | pw0 << 24 | pw1 << 28 (nhits = 0: unused slot),
+//                y = w0, z = w1, w = index of the third hit in the ROI's extra-hit list
+// One warp per ROI: lanes decode the samples in parallel, lane 0 merges the column taps.
+__global__ void __launch_bounds__(128)
+resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
+                           const int* __restrict__ img_start, int num_images, int height, int width,
+                           int row_bytes, int col_bytes, int pooled_h, int pooled_w, float scale,
+                           int ypairs, int maxc, uint2* __restrict__ scan, uint4* __restrict__ ypair,
+                           uint4* __restrict__ cols, uint2* __restrict__ extra, int* __restrict__ counter) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
+  const int valid = __ldg(img_start + num_images);
+  if (j >= valid) return;
+  const int roi = __ldg(order + j);
+  const RoiGeom g = roi_decode(rois + (size_t)roi * 5, scale, pooled_h, pooled_w, 2);
+  // rows: per bin row the <= 4 distinct feature-map rows its two sample rows touch, ascending,
+  // with the merged row weights: {off0, w0, off1, w1}, {off2, w2, off3, w3}; byte offsets in the
+  // padded plane, unused slots have off = 0xffffffff (in no band) -- and the touched range
+  int row_first = height, row_last = -1;
+  for (int ph = lane; ph < ypairs; ph += 32) {
+    unsigned off[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    float wgt[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (ph < pooled_h) {
+      int nrow = 0, rows[4];
+      auto add = [&](int row, float w) {
+        if (row >= height) return;                     // the repeated row: weight 0 by construction
+        for (int k = 0; k < nrow; ++k)
+          if (rows[k] == row) {
+            wgt[k] += w;
+            return;
+          }
+        rows[nrow] = row;
+        wgt[nrow] = w;
+        ++nrow;
+      };
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const AxisTap t = axis_decode(sample_pos(g.start_h, ph, g.bin_h, i, 2), height);
+        if (t.valid) {
+          add(t.lo, t.wh);
+          if (t.hi != t.lo) add(t.hi, t.wl);
+          row_first = min(row_first, t.lo);
+          row_last = max(row_last, t.hi);
+        }
+      }
+      for (int k = 0; k < nrow; ++k) off[k] = (unsigned)(rows[k] * row_bytes);
+    }
+    uint4* dst = ypair + ((size_t)j * ypairs + ph) * 2;
+    dst[0] = make_uint4(off[0], __float_as_uint(wgt[0]), off[1], __float_as_uint(wgt[1]));
+    dst[1] = make_uint4(off[2], __float_as_uint(wgt[2]), off[3], __float_as_uint(wgt[3]));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    row_first = min(row_first, __shfl_xor_sync(0xffffffffu, row_first, d));
+    row_last = max(row_last, __shfl_xor_sync(0xffffffffu, row_last, d));
+  }
+  // columns: sample column s = lane (pooled_w <= 16); lane 0 then walks them in order with
+  // two open columns A (colA) and B (colA + 1)
+  AxisTap mine;
+  mine.valid = false;
+  mine.lo = mine.hi = 0;
+  mine.wl = mine.wh = 0.0f;
+  if (lane < 2 * pooled_w) mine = axis_decode(sample_pos(g.start_w, lane >> 1, g.bin_w, lane & 1, 2), width);
+  uint4* crow = cols + (size_t)j * maxc;
+  uint2* erow = extra + (size_t)j * maxc;
+  int ncols = 0;
+  {
+    int colA = -1, nA = 0, nB = 0, nextra = 0;
+    int pA[kMaxHitsPerCol] = {0}, pB[kMaxHitsPerCol] = {0};
+    float wA[kMaxHitsPerCol] = {0.0f}, wB[kMaxHitsPerCol] = {0.0f};
+    auto flushA = [&]() {
+      if (nA > 0 && colA < width && lane == 0) {
+        uint4 r;
+        r.x = (unsigned)(colA * col_bytes) | ((unsigned)nA << 16) | ((unsigned)pA[0] << 24) |
+              ((unsigned)(nA > 1 ? pA[1] : 0) << 28);
+        r.y = __float_as_uint(wA[0]);
+        r.z = __float_as_uint(nA > 1 ? wA[1] : 0.0f);
+        r.w = (unsigned)nextra;
+        for (int k = 2; k < nA; ++k) erow[nextra++] = make_uint2((unsigned)pA[k], __float_as_uint(wA[k]));
+        crow[ncols++] = r;
+      }
+      colA += 1;
+      nA = nB;
+      for (int k = 0; k < nB; ++k) {
+        pA[k] = pB[k];
+        wA[k] = wB[k];
+      }
+      nB = 0;
+    };
+    for (int s = 0; s < 2 * pooled_w; ++s) {
+      const bool ok = __shfl_sync(0xffffffffu, (int)mine.valid, s) != 0;
+      const int lo = __shfl_sync(0xffffffffu, mine.lo, s), hi = __shfl_sync(0xffffffffu, mine.hi, s);
+      const float l = __shfl_sync(0xffffffffu, mine.wl, s), h = __shfl_sync(0xffffffffu, mine.wh, s);
+      if (!ok) continue;
+      const int pw = s >> 1;
+      if (colA < 0) colA = lo;
+      while (colA < lo) {
+        if (nA == 0 && nB == 0) {
+          colA = lo;             // nothing open: jump
+          break;
+        }
+        flushA();
+      }
+      // 1/count folded into the column weights: count = 4, an exact scaling
+      const float wlo = __fmul_rn(h, 0.25f), whi = __fmul_rn(l, 0.25f);
+      if (nA > 0 && pA[nA - 1] == pw) wA[nA - 1] += wlo;
+      else { pA[nA] = pw; wA[nA] = wlo; ++nA; }
+      if (hi != lo) {            // the clamped sample has no second column (its weight is 0)
+        if (nB > 0 && pB[nB - 1] == pw) wB[nB - 1] += whi;
+        else { pB[nB] = pw; wB[nB] = whi; ++nB; }
+      }
+    }
+    flushA();
+    flushA();
+  }
+  ncols = __shfl_sync(0xffffffffu, ncols, 0);
+  for (int k = ncols + lane; k < maxc; k += 32) crow[k] = make_uint4(0u, 0u, 0u, 0u);   // unused slots
+  if (ncols == 0 || row_last < row_first) {
+    row_first = 1;
+    row_last = 0;
+  }
+  if (lane == 0) scan[j] = make_uint2((unsigned)row_first | ((unsigned)row_last << 16), (unsigned)roi);
+}
+
+// 8-byte shared-memory accesses on a 32-bit shared address; volatile: program order is kept
+__device__ __forceinline__ float2 lds64(unsigned addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts64(unsigned addr, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+
+// Everything a warp needs for one visit (ROI x band), fetched while the previous visit is
+// computed: NT floats of the dy tile pair per lane, the row records of bin row `lane`, NCK
+// column records.
+template <int NT, int NCK>
+struct VisitRegs {
+  float g[NT];
+  uint4 ya, yb;
+  uint4 col[NCK];
+};
+
+// The slab holds TWO channels interleaved (float2 per pixel): every table look-up, weight and
+// address of a visit then serves two channels, the read-modify-writes are 8 bytes wide.
+template <int NT, int NCK, bool ACC>
+__global__ void __launch_bounds__(kBwdThreads)
+resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const uint2* __restrict__ scan,
+                     const uint4* __restrict__ ypair, const uint4* __restrict__ cols,
+                     const uint2* __restrict__ extra, const int* __restrict__ img_start, int* __restrict__ counter,
+                     int num_images, int channels, int height, int width, int pitch2, int pooled_h, int pooled_w,
+                     int ypairs, int maxc, int slabs, int slab_rows) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int s_unit;
+  float2* slab = reinterpret_cast<float2*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bins = pooled_h * pooled_w;
+  const unsigned sbase = ptx::smem_addr(smem_raw);
+  const unsigned rb = (unsigned)pitch2 * 8u;                 // bytes per slab row
+  // per-warp slot: the dy tiles of the channel pair, interleaved per bin (NT * 32 floats), then
+  // the row records (ypairs * 32 bytes)
+  const unsigned slot_bytes = (unsigned)(NT * 32 + ypairs * 8) * 4u;
+  const unsigned slot_s = sbase + (unsigned)slab_rows * rb + (unsigned)warp * slot_bytes;
+  const unsigned yslot_s = slot_s + NT * 128u;
+  const size_t plane_elems = (size_t)height * width;
+  const int cpairs = (channels + 1) >> 1;
+  const int units = num_images * cpairs * slabs;
+  const int w4 = width >> 2;
+  const size_t cb = (size_t)channels * bins;
+
+  // lane constants: element e = lane + 32 * i of the 2 * bins tile floats goes to
+  // slot[(e % bins) * 2 + e / bins]
+  unsigned tdst[NT];
+  int tsrc[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const int e = lane + 32 * i;
+    tsrc[i] = e;
+    const int ch = e >= bins ? 1 : 0, bin = e - ch * bins;
+    tdst[i] = slot_s + (unsigned)(bin * 2 + ch) * 4u;
+  }
+  const int lane_y = 2 * min(lane, ypairs - 1);
+
+  for (;;) {
+    __syncthreads();                 // the previous slab has left shared memory; s_unit is free
+    if (tid == 0) s_unit = atomicAdd(counter, 1);
+    __syncthreads();
+    const int unit = s_unit;
+    if (unit >= units) break;
+    const int p = unit / slabs, sl = unit - p * slabs;
+    const int n = p / cpairs, c = 2 * (p - n * cpairs);
+    const bool two = c + 1 < channels;
+    const int tile_floats = two ? 2 * bins : bins;
+    const int r0 = sl * slab_rows, r1 = min(height, r0 + slab_rows);
+    float* gplane = dx + ((size_t)n * channels + c) * plane_elems;
+
+    // ---- slab := 0 (or the current dX rows when accumulating) ----
+    if (ACC) {
+      for (int i = tid; i < (r1 - r0) * width; i += kBwdThreads) {
+        const int r = i / width, x = i - r * width;
+        const size_t gi = (size_t)(r0 + r) * width + x;
+        slab[r * pitch2 + x] = make_float2(gplane[gi], two ? gplane[plane_elems + gi] : 0.0f);
+      }
+    } else {
+      float4* s4 = reinterpret_cast<float4*>(slab);
+      const int n4 = ((r1 - r0) * pitch2) >> 1;
+      for (int i = tid; i < n4; i += kBwdThreads) s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    // ---- this warp's band of rows, as byte offsets in a plane of `rb`-byte rows ----
+    const int b0 = r0 + ((r1 - r0) * warp) / kBwdWarps;
+    const int b1 = r0 + ((r1 - r0) * (warp + 1)) / kBwdWarps;
+    const unsigned band_lo = (unsigned)b0 * rb, band_span = (unsigned)(b1 - b0) * rb;
+    const unsigned col_base = sbase - (unsigned)r0 * rb;      // + row offset + column offset
+    const int j0 = __ldg(img_start + n), nroi = __ldg(img_start + n + 1) - j0;
+    const float* dy_c = dy + (size_t)c * bins;
+
+    if (b1 > b0 && nroi > 0) {
+      // ROIs are scanned 32 at a time, one chunk ahead of their use; a ROI is visited when its
+      // touched rows meet the band
+      const uint2 none = make_uint2(1u, 0u);                     // first > last
+      uint2 rec_cur = lane < nroi ? __ldg(scan + j0 + lane) : none;
+      uint2 rec_nxt = 32 + lane < nroi ? __ldg(scan + j0 + 32 + lane) : none;
+      int jb = 0;
+#define MOBULA_TOUCHES(rec) ((int)((rec).x & 0xffffu) < b1 && (int)((rec).x >> 16) >= b0 && \
+                             ((rec).x & 0xffffu) <= ((rec).x >> 16))
+      unsigned bits = __ballot_sync(0xffffffffu, MOBULA_TOUCHES(rec_cur));
+      int jv = -1, roi = 0;
+      // advance to the next visit: (grouped position jv, roi row) or jv = -1
+#define MOBULA_NEXT_VISIT()                                                                     \
+  do {                                                                                          \
+    jv = -1;                                                                                    \
+    while (bits == 0u) {                                                                        \
+      jb += 32;                                                                                 \
+      if (jb >= nroi) break;                                                                    \
+      rec_cur = rec_nxt;                                                                        \
+      rec_nxt = jb + 32 + lane < nroi ? __ldg(scan + j0 + jb + 32 + lane) : none;               \
+      bits = __ballot_sync(0xffffffffu, MOBULA_TOUCHES(rec_cur));                               \
+    }                                                                                           \
+    if (bits != 0u) {                                                                           \
+      const int k_ = __ffs(bits) - 1;                                                           \
+      bits &= bits - 1u;                                                                        \
+      jv = j0 + jb + k_;                                                                        \
+      roi = (int)__shfl_sync(0xffffffffu, rec_cur.y, k_);                                       \
+    }                                                                                           \
+  } while (0)
+#define MOBULA_LOAD_VISIT(v)                                                                    \
+  do {                                                                                          \
+    const float* tile_ = dy_c + (size_t)roi * cb;                                               \
+    _Pragma("unroll") for (int i = 0; i < NT; ++i)                                              \
+        (v).g[i] = tsrc[i] < tile_floats ? __ldg(tile_ + tsrc[i]) : 0.0f;                       \
+    const uint4* yr_ = ypair + (size_t)jv * (2 * ypairs) + lane_y;                              \
+    (v).ya = __ldg(yr_);                                                                        \
+    (v).yb = __ldg(yr_ + 1);                                                                    \
+    const uint4* cr_ = cols + (size_t)jv * maxc + lane;                                         \
+    _Pragma("unroll") for (int k = 0; k < NCK; ++k)(v).col[k] = __ldg(cr_ + 32 * k);            \
+  } while (0)
+
+      VisitRegs<NT, NCK> nxt;
+      MOBULA_NEXT_VISIT();
+      if (jv >= 0) MOBULA_LOAD_VISIT(nxt);
+      while (jv >= 0) {
+        const VisitRegs<NT, NCK> cur = nxt;
+        const int jcur = jv;
+        MOBULA_NEXT_VISIT();
+        if (jv >= 0) MOBULA_LOAD_VISIT(nxt);
+
+        // dy tiles and row records -> this warp's slot
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+          if (tsrc[i] < 2 * bins) sts_at(tdst[i], cur.g[i]);
+        if (lane < ypairs) {
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(yslot_s + lane * 32u), "r"(cur.ya.x),
+                       "r"(cur.ya.y), "r"(cur.ya.z), "r"(cur.ya.w)
+                       : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(yslot_s + lane * 32u + 16u),
+                       "r"(cur.yb.x), "r"(cur.yb.y), "r"(cur.yb.z), "r"(cur.yb.w)
+                       : "memory");
+        }
+        // which rows of which bin rows lie in the band?  slot q of bin row ph: bit ph of rq<q>
+        const bool live = lane < pooled_h;
+        const unsigned rq0 = __ballot_sync(0xffffffffu, live && cur.ya.x - band_lo < band_span);
+        const unsigned rq1 = __ballot_sync(0xffffffffu, live && cur.ya.z - band_lo < band_span);
+        const unsigned rq2 = __ballot_sync(0xffffffffu, live && cur.yb.x - band_lo < band_span);
+        const unsigned rq3 = __ballot_sync(0xffffffffu, live && cur.yb.z - band_lo < band_span);
+        __syncwarp();
+#pragma unroll
+        for (int ck = 0; ck < NCK; ++ck) {
+          const uint4 cr = cur.col[ck];
+          const int nh = (int)((cr.x >> 16) & 0xffu);
+          const bool act = nh > 0;
+          const unsigned caddr = col_base + (cr.x & 0xffffu);
+          const unsigned g0 = slot_s + ((cr.x >> 24) & 0xfu) * 8u, g1 = slot_s + (cr.x >> 28) * 8u;
+          const float w0 = __uint_as_float(cr.y), w1 = __uint_as_float(cr.z);
+          unsigned m = rq0 | rq1 | rq2 | rq3;
+          while (m) {
+            const int ph = __ffs(m) - 1;
+            m &= m - 1u;
+            const uint4 ya = lds128(yslot_s + ph * 32u), yb = lds128(yslot_s + ph * 32u + 16u);   // broadcast
+            const unsigned grow = (unsigned)(ph * pooled_w) * 8u;
+            float2 t = make_float2(0.0f, 0.0f);
+            if (act) {
+              const float2 ga = lds64(g0 + grow);
+              t.x = w0 * ga.x;
+              t.y = w0 * ga.y;
+              if (nh > 1) {
+                const float2 gb = lds64(g1 + grow);
+                t.x = fmaf(w1, gb.x, t.x);
+                t.y = fmaf(w1, gb.y, t.y);
+                for (int e = 2; e < nh; ++e) {
+                  const uint2 hx = __ldg(extra + (size_t)jcur * maxc + cr.w + (e - 2));
+                  const float2 ge = lds64(slot_s + hx.x * 8u + grow);
+                  t.x = fmaf(__uint_as_float(hx.y), ge.x, t.x);
+                  t.y = fmaf(__uint_as_float(hx.y), ge.y, t.y);
+                }
+              }
+            }
+            // the rows of a bin row are distinct: the read-modify-writes are independent
+            const bool p0 = act && ((rq0 >> ph) & 1u), p1 = act && ((rq1 >> ph) & 1u);
+            const bool p2 = act && ((rq2 >> ph) & 1u), p3 = act && ((rq3 >> ph) & 1u);
+            const unsigned a0 = caddr + ya.x, a1 = caddr + ya.z, a2 = caddr + yb.x, a3 = caddr + yb.z;
+            float2 v0, v1, v2, v3;
+            if (p0) v0 = lds64(a0);
+            if (p1) v1 = lds64(a1);
+            if (p2) v2 = lds64(a2);
+            if (p3) v3 = lds64(a3);
+            const float y0 = __uint_as_float(ya.y), y1 = __uint_as_float(ya.w);
+            const float y2 = __uint_as_float(yb.y), y3 = __uint_as_float(yb.w);
+            if (p0) sts64(a0, make_float2(fmaf(y0, t.x, v0.x), fmaf(y0, t.y, v0.y)));
+            if (p1) sts64(a1, make_float2(fmaf(y1, t.x, v1.x), fmaf(y1, t.y, v1.y)));
+            if (p2) sts64(a2, make_float2(fmaf(y2, t.x, v2.x), fmaf(y2, t.y, v2.y)));
+            if (p3) sts64(a3, make_float2(fmaf(y3, t.x, v3.x), fmaf(y3, t.y, v3.y)));
+          }
+        }
+      }
+#undef MOBULA_LOAD_VISIT
+#undef MOBULA_NEXT_VISIT
+#undef MOBULA_TOUCHES
+    }
+    __syncthreads();
+    // ---- the finished slab -> the two planes of dX, each element written once ----
+    float* gplane1 = gplane + plane_elems;
+    if ((width & 3) == 0 && ((uintptr_t)dx & 15u) == 0) {
+      const int total = (r1 - r0) * w4;
+      int r = tid / w4, c4 = tid - r * w4;
+      const int dr = kBwdThreads / w4, dc = kBwdThreads - dr * w4;
+      float4* ga = reinterpret_cast<float4*>(gplane + (size_t)r0 * width);
+      float4* gb = reinterpret_cast<float4*>(gplane1 + (size_t)r0 * width);
+      for (int i = tid; i < total; i += kBwdThreads) {
+        const float4* src = reinterpret_cast<const float4*>(slab + (size_t)r * pitch2 + 4 * c4);
+        const float4 lo = src[0], hi = src[1];       // (a0 b0 a1 b1) (a2 b2 a3 b3)
+        ga[i] = make_float4(lo.x, lo.z, hi.x, hi.z);
+        if (two) gb[i] = make_float4(lo.y, lo.w, hi.y, hi.w);
+        r += dr;
+        c4 += dc;
+        if (c4 >= w4) {
+          c4 -= w4;
+          ++r;
+        }
+      }
+    } else {
+      for (int i = tid; i < (r1 - r0) * width; i += kBwdThreads) {
+        const int r = i / width, x = i - r * width;
+        const float2 v = slab[r * pitch2 + x];
+        const size_t gi = (size_t)(r0 + r) * width + x;
+        gplane[gi] = v.x;
+        if (two) gplane1[gi] = v.y;
+      }
+    }
+  }
+}
+
+struct BwdLayout {
+  size_t img_start, order, scan, ypair, cols, extra, counter, total;
+};
+
+BwdLayout bwd_layout(const RoiAlignArgs& a, int ypairs, int maxc) {
+  BwdLayout l;
+  size_t p = 0;
+  const size_t R = (size_t)a.num_rois;
+  l.img_start = p;  p += align_up((size_t)(a.num_images + 2) * sizeof(int), 256);
+  l.order = p;      p += align_up(R * sizeof(int), 256);
+  l.scan = p;       p += align_up(R * sizeof(uint2), 256);
+  l.ypair = p;      p += align_up(R * ypairs * 2 * sizeof(uint4), 256);
+  l.cols = p;       p += align_up(R * maxc * sizeof(uint4), 256);
+  l.extra = p;      p += align_up(R * maxc * sizeof(uint2), 256);
+  l.counter = p;    p += 256;
+  l.total = p;
+  return l;
+}
+
 struct FwdLayout {
   size_t img_start, order, entries, total;
 };
@@ -544,6 +976,32 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
   plan->plane_bytes = plane_bytes;
   plan->fwd_smem = fwd_smem;
   plan->use_bulk = (a.width % 4 == 0) && ((uintptr_t)plane_ptr % 16 == 0) ? 1 : 0;
+  // backward: sampling_ratio 2, the dy tile of a (roi, channel) in a 256-float slot; the plane
+  // is cut into as few slabs of rows as let two CTAs share an SM
+  plan->bwd_ok = 0;
+  if (a.sampling_ratio == 2 && a.pooled_w <= kMaxHitsPerCol && a.pooled_h <= 16 &&
+      a.pooled_h * a.pooled_w <= kMaxSlotFloats && a.height < 65536 && a.width * 8 < 65536) {
+    const int nt_raw = (2 * a.pooled_h * a.pooled_w + 31) / 32;
+    const int nt = nt_raw <= 1 ? 1 : nt_raw <= 2 ? 2 : nt_raw <= 4 ? 4 : nt_raw <= 8 ? 8 : 16;
+    const size_t slots = (size_t)kBwdWarps * (nt * 32 + 8 * 2 * ((a.pooled_h + 1) / 2)) * sizeof(float);
+    // slab rows hold two channels (float2 per pixel); a warp instruction touches one row, so
+    // the pitch only has to keep rows 16-byte aligned
+    const int pitch2 = (a.width + 1) & ~1;
+    for (int slabs = 1; slabs <= a.height; ++slabs) {
+      const int rows = (a.height + slabs - 1) / slabs;
+      const size_t smem = align_up((size_t)rows * pitch2 * sizeof(float2), 16) + slots;
+      if (2 * (smem + 1024 + 64) <= (size_t)smem_optin + 1024 || rows <= kBwdWarps) {
+        if (smem + 64 > (size_t)smem_optin) break;
+        plan->bwd_ok = 1;
+        plan->bwd_slabs = (a.height + rows - 1) / rows;
+        plan->bwd_slab_rows = rows;
+        plan->bwd_smem = smem;
+        plan->bwd_pitch2 = pitch2;
+        plan->bwd_maxc = (4 * a.pooled_w + 31) / 32 * 32;
+        break;
+      }
+    }
+  }
   return true;
 }
 
@@ -630,6 +1088,66 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     default: MOBULA_RESIDENT_FWD(4); break;
   }
 #undef MOBULA_RESIDENT_FWD
+  count_launch();
+  return cudaGetLastError();
+}
+
+size_t resident_bwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan) {
+  return bwd_layout(a, plan.ypairs, plan.bwd_maxc).total;
+}
+
+cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan, void* workspace,
+                                const float* dy, float* dx, int accumulate, int num_sms,
+                                cudaStream_t stream) {
+  (void)num_sms;
+  if (a.num_images == 0 || a.channels == 0) return cudaSuccess;
+  const BwdLayout l = bwd_layout(a, plan.ypairs, plan.bwd_maxc);
+  char* base = (char*)workspace;
+  int* img_start = (int*)(base + l.img_start);
+  int* order = (int*)(base + l.order);
+  uint2* scan = (uint2*)(base + l.scan);
+  uint4* ypair = (uint4*)(base + l.ypair);
+  uint4* cols = (uint4*)(base + l.cols);
+  uint2* extra = (uint2*)(base + l.extra);
+  int* counter = (int*)(base + l.counter);
+  cudaError_t e = launch_roi_group(a, img_start, order, stream);
+  if (e != cudaSuccess) return e;
+  const int tb = a.num_rois > 0 ? (a.num_rois + 3) / 4 : 1;       // one warp per ROI
+  resident_bwd2_table_kernel<<<tb, 128, 0, stream>>>(a.rois, order, img_start, a.num_images, a.height, a.width,
+                                                     plan.bwd_pitch2 * 8, 8, a.pooled_h, a.pooled_w, a.scale,
+                                                     plan.ypairs, plan.bwd_maxc, scan, ypair, cols, extra,
+                                                     counter);
+  count_launch();
+  const long long units = (long long)a.num_images * ((a.channels + 1) / 2) * plan.bwd_slabs;
+  unsigned grid = 0;
+#define MOBULA_BWD2(NT, NCK, ACC)                                                                     \
+  do {                                                                                                \
+    e = resident_grid(resident_bwd2_kernel<NT, NCK, ACC>, kBwdThreads, plan.bwd_smem, num_sms, units, \
+                      &grid);                                                                         \
+    if (e != cudaSuccess) return e;                                                                   \
+    resident_bwd2_kernel<NT, NCK, ACC><<<grid, kBwdThreads, plan.bwd_smem, stream>>>(                 \
+        dy, dx, scan, ypair, cols, extra, img_start, counter, a.num_images, a.channels, a.height,     \
+        a.width, plan.bwd_pitch2, a.pooled_h, a.pooled_w, plan.ypairs, plan.bwd_maxc, plan.bwd_slabs, \
+        plan.bwd_slab_rows);                                                                          \
+  } while (0)
+#define MOBULA_BWD2_NT(NT)                                      \
+  do {                                                          \
+    if (plan.bwd_maxc == 32) {                                  \
+      if (accumulate) MOBULA_BWD2(NT, 1, true);                 \
+      else MOBULA_BWD2(NT, 1, false);                           \
+    } else {                                                    \
+      if (accumulate) MOBULA_BWD2(NT, 2, true);                 \
+      else MOBULA_BWD2(NT, 2, false);                           \
+    }                                                           \
+  } while (0)
+  const int nt = (2 * a.pooled_h * a.pooled_w + 31) / 32;
+  if (nt <= 1) MOBULA_BWD2_NT(1);
+  else if (nt <= 2) MOBULA_BWD2_NT(2);
+  else if (nt <= 4) MOBULA_BWD2_NT(4);
+  else if (nt <= 8) MOBULA_BWD2_NT(8);
+  else MOBULA_BWD2_NT(16);
+#undef MOBULA_BWD2_NT
+#undef MOBULA_BWD2
   count_launch();
   return cudaGetLastError();
 }

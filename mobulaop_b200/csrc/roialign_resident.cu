@@ -528,7 +528,10 @@ cudaError_t resident_grid(K kernel, int threads, size_t smem, int num_sms, long 
 // are summed before they are added, and the order of ROIs is fixed (ownership is static), so
 // the result is reproducible run to run but not bit-identical to the reference's
 // single-thread order (that is the deterministic mode, roialign_plane.cu).
-constexpr int kBwdWarps = 8;
+#ifndef MOBULA_BWD_WARPS
+#define MOBULA_BWD_WARPS 8
+#endif
+constexpr int kBwdWarps = MOBULA_BWD_WARPS;
 constexpr int kBwdThreads = kBwdWarps * 32;
 constexpr int kMaxSlotFloats = 256;   // dy tile of one (roi, channel): PH * PW <= 256 floats
 constexpr int kMaxHitsPerCol = 16;    // = max pooled_w
@@ -668,6 +671,11 @@ __device__ __forceinline__ float2 lds64(unsigned addr) {
 __device__ __forceinline__ void sts64(unsigned addr, float2 v) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
+__device__ __forceinline__ float lds_vol(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint4 lds128(unsigned addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -697,42 +705,33 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
                      int num_images, int channels, int height, int width, int pitch2, int pooled_h, int pooled_w,
                      int ypairs, int maxc, int slabs, int slab_rows) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ int s_unit;
-  float2* slab = reinterpret_cast<float2*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bins = pooled_h * pooled_w;
-  const unsigned sbase = ptx::smem_addr(smem_raw);
-  const unsigned rb = (unsigned)pitch2 * 8u;                 // bytes per slab row
-  // per-warp slot: the dy tiles of the channel pair, interleaved per bin (NT * 32 floats), then
-  // the row records (ypairs * 32 bytes)
+  const unsigned rb = (unsigned)pitch2 * 8u;                 // bytes per band row
+  // every warp is on its own: a private band of `slab_rows` rows, then its slot -- the dy tiles
+  // of the channel pair (NT * 32 floats) and the row records (ypairs * 32 bytes)
   const unsigned slot_bytes = (unsigned)(NT * 32 + ypairs * 8) * 4u;
-  const unsigned slot_s = sbase + (unsigned)slab_rows * rb + (unsigned)warp * slot_bytes;
+  const unsigned warp_bytes = (unsigned)slab_rows * rb + slot_bytes;
+  float2* slab = reinterpret_cast<float2*>(smem_raw + (size_t)warp * warp_bytes);
+  const unsigned sbase = ptx::smem_addr(slab);
+  const unsigned slot_s = sbase + (unsigned)slab_rows * rb;
   const unsigned yslot_s = slot_s + NT * 128u;
   const size_t plane_elems = (size_t)height * width;
   const int cpairs = (channels + 1) >> 1;
-  const int units = num_images * cpairs * slabs;
+  const int units = num_images * cpairs * slabs;             // (image, channel pair, band)
   const int w4 = width >> 2;
-  const size_t cb = (size_t)channels * bins;
 
-  // lane constants: element e = lane + 32 * i of the 2 * bins tile floats goes to
-  // slot[(e % bins) * 2 + e / bins]
-  unsigned tdst[NT];
-  int tsrc[NT];
-#pragma unroll
-  for (int i = 0; i < NT; ++i) {
-    const int e = lane + 32 * i;
-    tsrc[i] = e;
-    const int ch = e >= bins ? 1 : 0, bin = e - ch * bins;
-    tdst[i] = slot_s + (unsigned)(bin * 2 + ch) * 4u;
-  }
   const int lane_y = 2 * min(lane, ypairs - 1);
+  const unsigned tile_s = slot_s + (unsigned)lane * 4u;       // this lane's first tile float
+  const unsigned ch1 = (unsigned)bins * 4u;                   // second channel's tile follows the first
+  const unsigned cb = (unsigned)channels * (unsigned)bins;
 
+  int unit_next = 0;
+  if (lane == 0) unit_next = atomicAdd(counter, 1);
   for (;;) {
-    __syncthreads();                 // the previous slab has left shared memory; s_unit is free
-    if (tid == 0) s_unit = atomicAdd(counter, 1);
-    __syncthreads();
-    const int unit = s_unit;
+    const int unit = __shfl_sync(0xffffffffu, unit_next, 0);
     if (unit >= units) break;
+    if (lane == 0) unit_next = atomicAdd(counter, 1);          // in flight while this unit runs
     const int p = unit / slabs, sl = unit - p * slabs;
     const int n = p / cpairs, c = 2 * (p - n * cpairs);
     const bool two = c + 1 < channels;
@@ -740,9 +739,10 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     const int r0 = sl * slab_rows, r1 = min(height, r0 + slab_rows);
     float* gplane = dx + ((size_t)n * channels + c) * plane_elems;
 
-    // ---- slab := 0 (or the current dX rows when accumulating) ----
+    // ---- band := 0 (or the current dX rows when accumulating) ----
+    __syncwarp();
     if (ACC) {
-      for (int i = tid; i < (r1 - r0) * width; i += kBwdThreads) {
+      for (int i = lane; i < (r1 - r0) * width; i += 32) {
         const int r = i / width, x = i - r * width;
         const size_t gi = (size_t)(r0 + r) * width + x;
         slab[r * pitch2 + x] = make_float2(gplane[gi], two ? gplane[plane_elems + gi] : 0.0f);
@@ -750,17 +750,19 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     } else {
       float4* s4 = reinterpret_cast<float4*>(slab);
       const int n4 = ((r1 - r0) * pitch2) >> 1;
-      for (int i = tid; i < n4; i += kBwdThreads) s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = lane; i < n4; i += 32) s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- this warp's band of rows, as byte offsets in a plane of `rb`-byte rows ----
-    const int b0 = r0 + ((r1 - r0) * warp) / kBwdWarps;
-    const int b1 = r0 + ((r1 - r0) * (warp + 1)) / kBwdWarps;
+    // ---- the band's rows as byte offsets in a plane of `rb`-byte rows ----
+    const int b0 = r0, b1 = r1;
     const unsigned band_lo = (unsigned)b0 * rb, band_span = (unsigned)(b1 - b0) * rb;
     const unsigned col_base = sbase - (unsigned)r0 * rb;      // + row offset + column offset
     const int j0 = __ldg(img_start + n), nroi = __ldg(img_start + n + 1) - j0;
     const float* dy_c = dy + (size_t)c * bins;
+    bool tok[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) tok[i] = lane + 32 * i < tile_floats;
 
     if (b1 > b0 && nroi > 0) {
       // ROIs are scanned 32 at a time, one chunk ahead of their use; a ROI is visited when its
@@ -793,44 +795,37 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
   } while (0)
 #define MOBULA_LOAD_VISIT(v)                                                                    \
   do {                                                                                          \
-    const float* tile_ = dy_c + (size_t)roi * cb;                                               \
-    _Pragma("unroll") for (int i = 0; i < NT; ++i)                                              \
-        (v).g[i] = tsrc[i] < tile_floats ? __ldg(tile_ + tsrc[i]) : 0.0f;                       \
-    const uint4* yr_ = ypair + (size_t)jv * (2 * ypairs) + lane_y;                              \
+    const float* tile_ = dy_c + (size_t)((unsigned)roi) * cb + lane;                            \
+    _Pragma("unroll") for (int i = 0; i < NT; ++i)(v).g[i] = tok[i] ? __ldg(tile_ + 32 * i) : 0.0f; \
+    const uint4* yr_ = ypair + ((unsigned)jv * (unsigned)(2 * ypairs) + (unsigned)lane_y);      \
     (v).ya = __ldg(yr_);                                                                        \
     (v).yb = __ldg(yr_ + 1);                                                                    \
-    const uint4* cr_ = cols + (size_t)jv * maxc + lane;                                         \
+    const uint4* cr_ = cols + ((unsigned)jv * (unsigned)maxc + (unsigned)lane);                 \
     _Pragma("unroll") for (int k = 0; k < NCK; ++k)(v).col[k] = __ldg(cr_ + 32 * k);            \
   } while (0)
 
-      VisitRegs<NT, NCK> nxt;
-      MOBULA_NEXT_VISIT();
-      if (jv >= 0) MOBULA_LOAD_VISIT(nxt);
-      while (jv >= 0) {
-        const VisitRegs<NT, NCK> cur = nxt;
-        const int jcur = jv;
-        MOBULA_NEXT_VISIT();
-        if (jv >= 0) MOBULA_LOAD_VISIT(nxt);
-
-        // dy tiles and row records -> this warp's slot
+      // one visit: the ROI's dy tiles and row records go to the warp's slot, then every touched
+      // column (lane) adds its share to the rows of the band
+      auto visit = [&](const VisitRegs<NT, NCK>& cur, int jcur) {
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < NT; ++i)
-          if (tsrc[i] < 2 * bins) sts_at(tdst[i], cur.g[i]);
+        for (int i = 0; i < NT; ++i) sts_at(tile_s + 128u * i, cur.g[i]);
+        // rows outside the band get the sign bit: one compare per row in the loop below
+        uint4 ya = cur.ya, yb = cur.yb;
+        const bool live = lane < pooled_h;
+        if (!(live && ya.x - band_lo < band_span)) ya.x = 0x80000000u;
+        if (!(live && ya.z - band_lo < band_span)) ya.z = 0x80000000u;
+        if (!(live && yb.x - band_lo < band_span)) yb.x = 0x80000000u;
+        if (!(live && yb.z - band_lo < band_span)) yb.z = 0x80000000u;
         if (lane < ypairs) {
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(yslot_s + lane * 32u), "r"(cur.ya.x),
-                       "r"(cur.ya.y), "r"(cur.ya.z), "r"(cur.ya.w)
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(yslot_s + lane * 32u), "r"(ya.x),
+                       "r"(ya.y), "r"(ya.z), "r"(ya.w)
                        : "memory");
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(yslot_s + lane * 32u + 16u),
-                       "r"(cur.yb.x), "r"(cur.yb.y), "r"(cur.yb.z), "r"(cur.yb.w)
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(yslot_s + lane * 32u + 16u), "r"(yb.x),
+                       "r"(yb.y), "r"(yb.z), "r"(yb.w)
                        : "memory");
         }
-        // which rows of which bin rows lie in the band?  slot q of bin row ph: bit ph of rq<q>
-        const bool live = lane < pooled_h;
-        const unsigned rq0 = __ballot_sync(0xffffffffu, live && cur.ya.x - band_lo < band_span);
-        const unsigned rq1 = __ballot_sync(0xffffffffu, live && cur.ya.z - band_lo < band_span);
-        const unsigned rq2 = __ballot_sync(0xffffffffu, live && cur.yb.x - band_lo < band_span);
-        const unsigned rq3 = __ballot_sync(0xffffffffu, live && cur.yb.z - band_lo < band_span);
+        const unsigned any = __ballot_sync(0xffffffffu, (int)(ya.x & ya.z & yb.x & yb.z) >= 0);
         __syncwarp();
 #pragma unroll
         for (int ck = 0; ck < NCK; ++ck) {
@@ -838,63 +833,77 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
           const int nh = (int)((cr.x >> 16) & 0xffu);
           const bool act = nh > 0;
           const unsigned caddr = col_base + (cr.x & 0xffffu);
-          const unsigned g0 = slot_s + ((cr.x >> 24) & 0xfu) * 8u, g1 = slot_s + (cr.x >> 28) * 8u;
+          const unsigned g0 = slot_s + ((cr.x >> 24) & 0xfu) * 4u, g1 = slot_s + (cr.x >> 28) * 4u;
           const float w0 = __uint_as_float(cr.y), w1 = __uint_as_float(cr.z);
-          unsigned m = rq0 | rq1 | rq2 | rq3;
+          unsigned m = any;
           while (m) {
             const int ph = __ffs(m) - 1;
             m &= m - 1u;
-            const uint4 ya = lds128(yslot_s + ph * 32u), yb = lds128(yslot_s + ph * 32u + 16u);   // broadcast
-            const unsigned grow = (unsigned)(ph * pooled_w) * 8u;
+            const uint4 ra = lds128(yslot_s + ph * 32u), rb2 = lds128(yslot_s + ph * 32u + 16u);   // broadcast
+            const unsigned grow = (unsigned)(ph * pooled_w) * 4u;
             float2 t = make_float2(0.0f, 0.0f);
             if (act) {
-              const float2 ga = lds64(g0 + grow);
-              t.x = w0 * ga.x;
-              t.y = w0 * ga.y;
+              t.x = w0 * lds_vol(g0 + grow);
+              t.y = w0 * lds_vol(g0 + grow + ch1);
               if (nh > 1) {
-                const float2 gb = lds64(g1 + grow);
-                t.x = fmaf(w1, gb.x, t.x);
-                t.y = fmaf(w1, gb.y, t.y);
+                t.x = fmaf(w1, lds_vol(g1 + grow), t.x);
+                t.y = fmaf(w1, lds_vol(g1 + grow + ch1), t.y);
                 for (int e = 2; e < nh; ++e) {
                   const uint2 hx = __ldg(extra + (size_t)jcur * maxc + cr.w + (e - 2));
-                  const float2 ge = lds64(slot_s + hx.x * 8u + grow);
-                  t.x = fmaf(__uint_as_float(hx.y), ge.x, t.x);
-                  t.y = fmaf(__uint_as_float(hx.y), ge.y, t.y);
+                  const unsigned ge = slot_s + hx.x * 4u + grow;
+                  t.x = fmaf(__uint_as_float(hx.y), lds_vol(ge), t.x);
+                  t.y = fmaf(__uint_as_float(hx.y), lds_vol(ge + ch1), t.y);
                 }
               }
             }
             // the rows of a bin row are distinct: the read-modify-writes are independent
-            const bool p0 = act && ((rq0 >> ph) & 1u), p1 = act && ((rq1 >> ph) & 1u);
-            const bool p2 = act && ((rq2 >> ph) & 1u), p3 = act && ((rq3 >> ph) & 1u);
-            const unsigned a0 = caddr + ya.x, a1 = caddr + ya.z, a2 = caddr + yb.x, a3 = caddr + yb.z;
+            const bool p0 = act && (int)ra.x >= 0, p1 = act && (int)ra.z >= 0;
+            const bool p2 = act && (int)rb2.x >= 0, p3 = act && (int)rb2.z >= 0;
+            const unsigned a0 = caddr + ra.x, a1 = caddr + ra.z, a2 = caddr + rb2.x, a3 = caddr + rb2.z;
             float2 v0, v1, v2, v3;
             if (p0) v0 = lds64(a0);
             if (p1) v1 = lds64(a1);
             if (p2) v2 = lds64(a2);
             if (p3) v3 = lds64(a3);
-            const float y0 = __uint_as_float(ya.y), y1 = __uint_as_float(ya.w);
-            const float y2 = __uint_as_float(yb.y), y3 = __uint_as_float(yb.w);
+            const float y0 = __uint_as_float(ra.y), y1 = __uint_as_float(ra.w);
+            const float y2 = __uint_as_float(rb2.y), y3 = __uint_as_float(rb2.w);
             if (p0) sts64(a0, make_float2(fmaf(y0, t.x, v0.x), fmaf(y0, t.y, v0.y)));
             if (p1) sts64(a1, make_float2(fmaf(y1, t.x, v1.x), fmaf(y1, t.y, v1.y)));
             if (p2) sts64(a2, make_float2(fmaf(y2, t.x, v2.x), fmaf(y2, t.y, v2.y)));
             if (p3) sts64(a3, make_float2(fmaf(y3, t.x, v3.x), fmaf(y3, t.y, v3.y)));
           }
         }
+      };
+
+      // two register sets in turn: the loads of visit k + 1 are in flight while visit k runs
+      VisitRegs<NT, NCK> va, vb;
+      MOBULA_NEXT_VISIT();
+      if (jv >= 0) MOBULA_LOAD_VISIT(va);
+      while (jv >= 0) {
+        int jcur = jv;
+        MOBULA_NEXT_VISIT();
+        if (jv >= 0) MOBULA_LOAD_VISIT(vb);
+        visit(va, jcur);
+        if (jv < 0) break;
+        jcur = jv;
+        MOBULA_NEXT_VISIT();
+        if (jv >= 0) MOBULA_LOAD_VISIT(va);
+        visit(vb, jcur);
       }
 #undef MOBULA_LOAD_VISIT
 #undef MOBULA_NEXT_VISIT
 #undef MOBULA_TOUCHES
     }
-    __syncthreads();
-    // ---- the finished slab -> the two planes of dX, each element written once ----
+    __syncwarp();
+    // ---- the finished band -> the two planes of dX, each element written once ----
     float* gplane1 = gplane + plane_elems;
     if ((width & 3) == 0 && ((uintptr_t)dx & 15u) == 0) {
       const int total = (r1 - r0) * w4;
-      int r = tid / w4, c4 = tid - r * w4;
-      const int dr = kBwdThreads / w4, dc = kBwdThreads - dr * w4;
+      int r = lane / w4, c4 = lane - r * w4;
+      const int dr = 32 / w4, dc = 32 - dr * w4;
       float4* ga = reinterpret_cast<float4*>(gplane + (size_t)r0 * width);
       float4* gb = reinterpret_cast<float4*>(gplane1 + (size_t)r0 * width);
-      for (int i = tid; i < total; i += kBwdThreads) {
+      for (int i = lane; i < total; i += 32) {
         const float4* src = reinterpret_cast<const float4*>(slab + (size_t)r * pitch2 + 4 * c4);
         const float4 lo = src[0], hi = src[1];       // (a0 b0 a1 b1) (a2 b2 a3 b3)
         ga[i] = make_float4(lo.x, lo.z, hi.x, hi.z);
@@ -907,7 +916,7 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
         }
       }
     } else {
-      for (int i = tid; i < (r1 - r0) * width; i += kBwdThreads) {
+      for (int i = lane; i < (r1 - r0) * width; i += 32) {
         const int r = i / width, x = i - r * width;
         const float2 v = slab[r * pitch2 + x];
         const size_t gi = (size_t)(r0 + r) * width + x;
@@ -987,19 +996,19 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
     // slab rows hold two channels (float2 per pixel); a warp instruction touches one row, so
     // the pitch only has to keep rows 16-byte aligned
     const int pitch2 = (a.width + 1) & ~1;
-    for (int slabs = 1; slabs <= a.height; ++slabs) {
-      const int rows = (a.height + slabs - 1) / slabs;
-      const size_t smem = align_up((size_t)rows * pitch2 * sizeof(float2), 16) + slots;
-      if (2 * (smem + 1024 + 64) <= (size_t)smem_optin + 1024 || rows <= kBwdWarps) {
-        if (smem + 64 > (size_t)smem_optin) break;
-        plan->bwd_ok = 1;
-        plan->bwd_slabs = (a.height + rows - 1) / rows;
-        plan->bwd_slab_rows = rows;
-        plan->bwd_smem = smem;
-        plan->bwd_pitch2 = pitch2;
-        plan->bwd_maxc = (4 * a.pooled_w + 31) / 32 * 32;
-        break;
-      }
+    // every warp owns a private band of rows; two CTAs of kBwdWarps warps share an SM
+    const size_t slot = slots / kBwdWarps;
+    const size_t per_warp = (((size_t)smem_optin + 1024) / 2 - 1024 - 64) / kBwdWarps;
+    const size_t row_bytes = (size_t)pitch2 * sizeof(float2);
+    if (per_warp > slot + row_bytes) {
+      int rows = (int)((per_warp - slot) / row_bytes);
+      if (rows > a.height) rows = a.height;
+      plan->bwd_ok = 1;
+      plan->bwd_slabs = (a.height + rows - 1) / rows;
+      plan->bwd_slab_rows = rows;
+      plan->bwd_smem = (size_t)kBwdWarps * (rows * row_bytes + slot);
+      plan->bwd_pitch2 = pitch2;
+      plan->bwd_maxc = (4 * a.pooled_w + 31) / 32 * 32;
     }
   }
   return true;

@@ -389,7 +389,7 @@ def run_e2e(args, wl, shard, world, dev):
     return dict(value=wl.R * world / step_s, unit=UNIT, h2d_bytes_per_step=int(h2d),
                 d2h_bytes_per_step=int(d2h), ms_per_step=step_s * 1e3, steps=n,
                 api='mobula.op.ROIAlign[np.ndarray] (C-ABI, MOBULA_ROIALIGN_HOST_BUFFERS), '
-                    'inputs in pinned host memory, outputs in pageable NumPy arrays')
+                    'inputs and results in page-locked host memory (NumPy arrays)')
 
 
 def main():

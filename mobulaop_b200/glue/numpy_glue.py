@@ -45,6 +45,12 @@ Tensor = NumPyTensor
 
 def make_array_op_class(op, name, xp, suffix):
     """Operator class for array libraries with NumPy semantics (shared with CuPy)."""
+    if xp is np:
+        from . import pinned
+        new_empty = pinned.empty          # results land in page-locked memory
+    else:
+        def new_empty(shape, dtype):
+            return xp.empty(shape, dtype=dtype)
 
     def forward(self, *args, **kwargs):
         inputs, extra, extra_kw = split_inputs(op, args, kwargs)
@@ -53,7 +59,7 @@ def make_array_op_class(op, name, xp, suffix):
         dtype = self.in_data[0].dtype
         self.req = ['write'] * len(self.in_data)
         out_shapes = self.infer_shape(shapes_of(self.in_data))[1]
-        self.out_data = [xp.empty(tuple(s), dtype=dtype) for s in out_shapes]
+        self.out_data = [new_empty(tuple(s), dtype) for s in out_shapes]
         result = self._forward(*inputs)
         if result is not None:
             result = result if isinstance(result, (list, tuple)) else [result]
@@ -68,7 +74,7 @@ def make_array_op_class(op, name, xp, suffix):
             self.out_data = out_data
         dtype = self.in_data[0].dtype
         if in_grad is None:
-            in_grad = [xp.empty(d.shape, dtype=dtype) for d in self.in_data]
+            in_grad = [new_empty(d.shape, dtype) for d in self.in_data]
         elif not isinstance(in_grad, (list, tuple)):
             in_grad = [in_grad]
         self.in_grad = in_grad

@@ -107,11 +107,25 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------------------
 # reference arm / CPU baseline (the only place bench.py executes oracle/)
 # ---------------------------------------------------------------------------------------
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    import ctypes
+    n = os.cpu_count() or 1
+    os.environ['OMP_NUM_THREADS'] = str(n)
+    try:
+        gomp = ctypes.CDLL('libgomp.so.1')
+        gomp.omp_set_num_threads(ctypes.c_int(n))
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return n
+
+
 def reference_library():
     from oracle import roialign as O
+    threads = use_all_host_cores()
     if O.RefLib.available('omp'):
         ref = O.RefLib('omp')
-        return 'reference', ref.host_threads(), ref.forward, ref.backward
+        return 'reference', threads, ref.forward, ref.backward
     orc = O.COracle()
     threads = orc.max_threads()
     return ('port', threads,

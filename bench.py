@@ -306,8 +306,14 @@ def run_ours(args):
     else:
         kname, kbytes, kms = 'forward (%s)' % _native.last_algo(False), b_fwd, fwd_mean
     achieved = kbytes / (kms * 1e-3) / 1e9
+    traffic = None          # DRAM bytes of that kernel from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            traffic = json.load(f).get(wl.name, {}).get(kname, {}).get('bytes')
+    except (OSError, ValueError):
+        pass
     roofline = dict(bound='hbm', kernel=kname, achieved=achieved, peak=peak, unit='GB/s',
-                    frac=achieved / peak, traffic=None, peak_source=peak_src,
+                    frac=achieved / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes=kbytes,
                     fwd=dict(ms=fwd_mean, bytes=b_fwd, gbs=b_fwd / (fwd_mean * 1e-3) / 1e9,
                              frac=b_fwd / (fwd_mean * 1e-3) / 1e9 / peak,

@@ -155,7 +155,7 @@ struct ResidentPlan {
   size_t plane_bytes;  // (H + 1) * pitch * 4
   size_t fwd_smem;
   int bwd_ok;          // the resident backward applies
-  int bwd_slabs, bwd_slab_rows, bwd_maxc, bwd_pitch2;
+  int bwd_slabs, bwd_slab_rows, bwd_maxc, bwd_maxe, bwd_pitch2;   // bands per plane, rows per band, ...
   size_t bwd_smem;
   int use_bulk;        // rows can be moved with cp.async.bulk (16-byte alignment holds)
 };

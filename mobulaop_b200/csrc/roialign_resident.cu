@@ -536,66 +536,70 @@ constexpr int kBwdThreads = kBwdWarps * 32;
 constexpr int kMaxSlotFloats = 256;   // dy tile of one (roi, channel): PH * PW <= 256 floats
 constexpr int kMaxHitsPerCol = 16;    // = max pooled_w
 
-// scan record of a ROI for the backward: x = first | last << 16 touched plane row
-// (first > last: nothing to do), y = roi row
-// column record: x = col_off | nhits << 16 | pw0 << 24 | pw1 << 28 (nhits = 0: unused slot),
-//                y = w0, z = w1, w = index of the third hit in the ROI's extra-hit list
+// Tables of the backward, per ROI at grouped position j (channel independent):
+//   cols[j][maxc]   column records, one per touched column: x = col_off | nhits << 16 |
+//                   pw0 << 24 | pw1 << 28 (nhits = 0: unused slot), y = w0, z = w1, w = index of
+//                   the third hit in extra[j][]
+//   rows[j][maxe]   row entries sorted by feature-map row: x = row * row_bytes | ph (row_bytes is
+//                   a multiple of 16), y = merged row weight of bin row ph on that row
+//   bstart[b][j]    index of the first row entry in band b (rows [b * band_rows, ...)), for
+//                   b = 0 .. nbands; bstart[nbands][j] = number of entries
+// and per (image, band) the ordered list of visits (roialign_bwd2_visits_kernel).
 // One warp per ROI: lanes decode the samples in parallel, lane 0 merges the column taps.
 __global__ void __launch_bounds__(128)
 resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
-                           const int* __restrict__ img_start, int num_images, int height, int width,
-                           int row_bytes, int col_bytes, int pooled_h, int pooled_w, float scale,
-                           int ypairs, int maxc, uint2* __restrict__ scan, uint4* __restrict__ ypair,
-                           uint4* __restrict__ cols, uint2* __restrict__ extra, int* __restrict__ counter) {
-  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+                           const int* __restrict__ img_start, int num_images, int num_rois, int height,
+                           int width, int row_bytes, int col_bytes, int pooled_h, int pooled_w, float scale,
+                           int maxe, int maxc, int band_rows, int nbands, uint2* __restrict__ rows_out,
+                           unsigned char* __restrict__ bstart, uint4* __restrict__ cols,
+                           uint2* __restrict__ extra, int* __restrict__ counter) {
+  __shared__ unsigned s_key[4][64], s_srow[4][64];
+  __shared__ float s_w[4][64];
+  __shared__ int s_lo[4][32], s_hi[4][32], s_pa[4][kMaxHitsPerCol], s_pb[4][kMaxHitsPerCol];
+  __shared__ float s_fl[4][32], s_wa[4][kMaxHitsPerCol], s_wb[4][kMaxHitsPerCol];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 4 + wib;
   if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
   const int valid = __ldg(img_start + num_images);
   if (j >= valid) return;
   const int roi = __ldg(order + j);
   const RoiGeom g = roi_decode(rois + (size_t)roi * 5, scale, pooled_h, pooled_w, 2);
-  // rows: per bin row the <= 4 distinct feature-map rows its two sample rows touch, ascending,
-  // with the merged row weights: {off0, w0, off1, w1}, {off2, w2, off3, w3}; byte offsets in the
-  // padded plane, unused slots have off = 0xffffffff (in no band) -- and the touched range
-  int row_first = height, row_last = -1;
-  for (int ph = lane; ph < ypairs; ph += 32) {
-    unsigned off[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-    float wgt[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (ph < pooled_h) {
-      int nrow = 0, rows[4];
-      auto add = [&](int row, float w) {
-        if (row >= height) return;                     // the repeated row: weight 0 by construction
-        for (int k = 0; k < nrow; ++k)
-          if (rows[k] == row) {
-            wgt[k] += w;
-            return;
-          }
-        rows[nrow] = row;
-        wgt[nrow] = w;
-        ++nrow;
-      };
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const AxisTap t = axis_decode(sample_pos(g.start_h, ph, g.bin_h, i, 2), height);
-        if (t.valid) {
-          add(t.lo, t.wh);
-          if (t.hi != t.lo) add(t.hi, t.wl);
-          row_first = min(row_first, t.lo);
-          row_last = max(row_last, t.hi);
+
+  // ---- rows: bin row `lane` touches <= 4 distinct rows (ascending), weights merged ----
+  int nrow = 0, rrow[4] = {0, 0, 0, 0};
+  float rw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (lane < pooled_h) {
+    auto add = [&](int row, float w) {
+      for (int k = 0; k < nrow; ++k)
+        if (rrow[k] == row) {
+          rw[k] += w;
+          return;
         }
-      }
-      for (int k = 0; k < nrow; ++k) off[k] = (unsigned)(rows[k] * row_bytes);
-    }
-    uint4* dst = ypair + ((size_t)j * ypairs + ph) * 2;
-    dst[0] = make_uint4(off[0], __float_as_uint(wgt[0]), off[1], __float_as_uint(wgt[1]));
-    dst[1] = make_uint4(off[2], __float_as_uint(wgt[2]), off[3], __float_as_uint(wgt[3]));
-  }
+      rrow[nrow] = row;
+      rw[nrow] = w;
+      ++nrow;
+    };
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    row_first = min(row_first, __shfl_xor_sync(0xffffffffu, row_first, d));
-    row_last = max(row_last, __shfl_xor_sync(0xffffffffu, row_last, d));
+    for (int i = 0; i < 2; ++i) {
+      const AxisTap t = axis_decode(sample_pos(g.start_h, lane, g.bin_h, i, 2), height);
+      if (t.valid) {
+        add(t.lo, t.wh);
+        if (t.hi != t.lo) add(t.hi, t.wl);     // the clamped sample has no second row
+      }
+    }
   }
-  // columns: sample column s = lane (pooled_w <= 16); lane 0 then walks them in order with
-  // two open columns A (colA) and B (colA + 1)
+  // exclusive prefix over the lanes -> position of this bin row's entries in the ROI's list
+  int incl = nrow;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  int ne = __shfl_sync(0xffffffffu, incl, 31);
+  const int base = incl - nrow;
+
+  // ---- columns: sample column s = lane (pooled_w <= 16); lane 0 then walks them in order
+  // with two open columns A (colA) and B (colA + 1) ----
   AxisTap mine;
   mine.valid = false;
   mine.lo = mine.hi = 0;
@@ -604,12 +608,18 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   uint4* crow = cols + (size_t)j * maxc;
   uint2* erow = extra + (size_t)j * maxc;
   int ncols = 0;
-  {
+  s_lo[wib][lane] = mine.valid ? mine.lo : -1;
+  s_hi[wib][lane] = mine.hi;
+  s_fl[wib][lane] = mine.wl;
+  __syncwarp();
+  if (lane == 0) {
     int colA = -1, nA = 0, nB = 0, nextra = 0;
-    int pA[kMaxHitsPerCol] = {0}, pB[kMaxHitsPerCol] = {0};
-    float wA[kMaxHitsPerCol] = {0.0f}, wB[kMaxHitsPerCol] = {0.0f};
+    int* pA = s_pa[wib];
+    int* pB = s_pb[wib];
+    float* wA = s_wa[wib];
+    float* wB = s_wb[wib];
     auto flushA = [&]() {
-      if (nA > 0 && colA < width && lane == 0) {
+      if (nA > 0 && colA < width) {
         uint4 r;
         r.x = (unsigned)(colA * col_bytes) | ((unsigned)nA << 16) | ((unsigned)pA[0] << 24) |
               ((unsigned)(nA > 1 ? pA[1] : 0) << 28);
@@ -628,10 +638,10 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
       nB = 0;
     };
     for (int s = 0; s < 2 * pooled_w; ++s) {
-      const bool ok = __shfl_sync(0xffffffffu, (int)mine.valid, s) != 0;
-      const int lo = __shfl_sync(0xffffffffu, mine.lo, s), hi = __shfl_sync(0xffffffffu, mine.hi, s);
-      const float l = __shfl_sync(0xffffffffu, mine.wl, s), h = __shfl_sync(0xffffffffu, mine.wh, s);
-      if (!ok) continue;
+      const int lo = s_lo[wib][s];
+      if (lo < 0) continue;
+      const int hi = s_hi[wib][s];
+      const float l = s_fl[wib][s], h = __fsub_rn(1.0f, l);
       const int pw = s >> 1;
       if (colA < 0) colA = lo;
       while (colA < lo) {
@@ -655,11 +665,82 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   }
   ncols = __shfl_sync(0xffffffffu, ncols, 0);
   for (int k = ncols + lane; k < maxc; k += 32) crow[k] = make_uint4(0u, 0u, 0u, 0u);   // unused slots
-  if (ncols == 0 || row_last < row_first) {
-    row_first = 1;
-    row_last = 0;
+  if (ncols == 0) {
+    ne = 0;      // no column inside the plane: the ROI contributes nothing
+    nrow = 0;
   }
-  if (lane == 0) scan[j] = make_uint2((unsigned)row_first | ((unsigned)row_last << 16), (unsigned)roi);
+
+  // ---- row entries, sorted by (band, bin row, row) so that the entries of a band are
+  // contiguous and a bin row's entries follow each other ----
+  for (int k = 0; k < nrow; ++k) {
+    s_key[wib][base + k] = (unsigned)((rrow[k] / band_rows) * 16 + lane) * 65536u + (unsigned)rrow[k];
+    s_w[wib][base + k] = rw[k];
+  }
+  __syncwarp();
+  uint2* rout = rows_out + (size_t)j * maxe;
+  for (int e = lane; e < ne; e += 32) {
+    const unsigned key = s_key[wib][e];
+    int rank = 0;
+    for (int k = 0; k < ne; ++k) rank += s_key[wib][k] < key ? 1 : 0;
+    const unsigned row = key & 0xffffu, ph = (key >> 16) & 15u;
+    rout[rank] = make_uint2(row * (unsigned)row_bytes | ph, __float_as_uint(s_w[wib][e]));
+    s_srow[wib][rank] = row;
+  }
+  __syncwarp();
+  // first entry of every band: entries with row < b * band_rows (rows ascend with the rank)
+  for (int bnd = lane; bnd <= nbands; bnd += 32) {
+    const unsigned limit = (unsigned)(bnd * band_rows);
+    int lo = 0, hi = ne;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_srow[wib][mid] < limit) lo = mid + 1;
+      else hi = mid;
+    }
+    bstart[(size_t)bnd * num_rois + j] = (unsigned char)(bnd == nbands ? ne : lo);
+  }
+}
+
+// One block per (image, band): the visits of the band, in ROI order.  Thread t owns a
+// contiguous run of the image's ROIs; a block-wide prefix sum places its visits.
+// visit = x: grouped position | first entry << 20 | (entries - 1) << 26; y: roi row
+constexpr int kVisitThreads = 128;
+__global__ void __launch_bounds__(kVisitThreads)
+resident_bwd2_visits_kernel(const int* __restrict__ order, const int* __restrict__ img_start,
+                            const unsigned char* __restrict__ bstart, int num_images, int num_rois, int nbands,
+                            uint2* __restrict__ visits, int* __restrict__ vcount) {
+  __shared__ int s_warp[kVisitThreads / 32];
+  const int w = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int n = w / nbands, bnd = w - n * nbands;
+  const int j0 = __ldg(img_start + n), nroi = __ldg(img_start + n + 1) - j0;
+  uint2* list = visits + ((size_t)j0 * nbands + (size_t)bnd * nroi);
+  const unsigned char* s0 = bstart + (size_t)bnd * num_rois;
+  const unsigned char* s1 = s0 + num_rois;
+  const int per = (nroi + kVisitThreads - 1) / kVisitThreads;
+  const int jb = min(nroi, t * per), je = min(nroi, jb + per);
+  int mine = 0;
+  for (int jj = jb; jj < je; ++jj) mine += s1[j0 + jj] > s0[j0 + jj] ? 1 : 0;
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  int before = incl - mine, total = 0;
+  for (int k = 0; k < kVisitThreads / 32; ++k) {
+    const int v = s_warp[k];
+    if (k < wid) before += v;
+    total += v;
+  }
+  for (int jj = jb; jj < je; ++jj) {
+    const int j = j0 + jj;
+    const int first = s0[j], cnt = s1[j] - first;
+    if (cnt > 0)
+      list[before++] = make_uint2((unsigned)j | ((unsigned)first << 20) | ((unsigned)(cnt - 1) << 26),
+                                  (unsigned)__ldg(order + j));
+  }
+  if (t == 0) vcount[w] = total;
 }
 
 // 8-byte shared-memory accesses on a 32-bit shared address; volatile: program order is kept
@@ -676,52 +757,49 @@ __device__ __forceinline__ float lds_vol(unsigned addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ uint4 lds128(unsigned addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "r"(addr)
-               : "memory");
+__device__ __forceinline__ uint2 lds64u(unsigned addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
   return v;
 }
 
-// Everything a warp needs for one visit (ROI x band), fetched while the previous visit is
-// computed: NT floats of the dy tile pair per lane, the row records of bin row `lane`, NCK
-// column records.
-template <int NT, int NCK>
+// Everything a warp needs for one visit, fetched while the previous visit is computed: NT floats
+// of the dy tile pair per lane, NE row entries of the band, NCK column records.
+template <int NT, int NCK, int NE>
 struct VisitRegs {
   float g[NT];
-  uint4 ya, yb;
+  uint2 e[NE];
   uint4 col[NCK];
 };
 
-// The slab holds TWO channels interleaved (float2 per pixel): every table look-up, weight and
-// address of a visit then serves two channels, the read-modify-writes are 8 bytes wide.
-template <int NT, int NCK, bool ACC>
-__global__ void __launch_bounds__(kBwdThreads)
-resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const uint2* __restrict__ scan,
-                     const uint4* __restrict__ ypair, const uint4* __restrict__ cols,
-                     const uint2* __restrict__ extra, const int* __restrict__ img_start, int* __restrict__ counter,
-                     int num_images, int channels, int height, int width, int pitch2, int pooled_h, int pooled_w,
-                     int ypairs, int maxc, int slabs, int slab_rows) {
+// Every warp is on its own: it takes (image, channel pair, band) units from a queue, keeps the
+// band -- `band_rows` rows x two channels, float2 per pixel -- in its private shared memory,
+// walks the band's visit list and stores the finished band to the two dX planes.
+template <int NT, int NCK, int NE, bool ACC>
+__global__ void __launch_bounds__(kBwdThreads, 2)
+resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const uint2* __restrict__ visits,
+                     const int* __restrict__ vcount, const uint2* __restrict__ rows_in,
+                     const uint4* __restrict__ cols, const uint2* __restrict__ extra,
+                     const int* __restrict__ img_start, int* __restrict__ counter, int num_images,
+                     int channels, int height, int width, int pitch2, int pooled_h, int pooled_w, int maxe,
+                     int maxc, int nbands, int band_rows) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bins = pooled_h * pooled_w;
   const unsigned rb = (unsigned)pitch2 * 8u;                 // bytes per band row
-  // every warp is on its own: a private band of `slab_rows` rows, then its slot -- the dy tiles
-  // of the channel pair (NT * 32 floats) and the row records (ypairs * 32 bytes)
-  const unsigned slot_bytes = (unsigned)(NT * 32 + ypairs * 8) * 4u;
-  const unsigned warp_bytes = (unsigned)slab_rows * rb + slot_bytes;
-  float2* slab = reinterpret_cast<float2*>(smem_raw + (size_t)warp * warp_bytes);
-  const unsigned sbase = ptx::smem_addr(slab);
-  const unsigned slot_s = sbase + (unsigned)slab_rows * rb;
-  const unsigned yslot_s = slot_s + NT * 128u;
+  // per warp: the band, then the dy tiles of the channel pair (NT * 32 floats) and the row
+  // entries of the visit (NE * 32 * 8 bytes)
+  const unsigned slot_bytes = (unsigned)(NT * 32 + NE * 64 + 4) * 4u;     // + one spare entry
+  const unsigned warp_bytes = (unsigned)band_rows * rb + slot_bytes;
+  float2* band = reinterpret_cast<float2*>(smem_raw + (size_t)warp * warp_bytes);
+  const unsigned sbase = ptx::smem_addr(band);
+  const unsigned slot_s = sbase + (unsigned)band_rows * rb;
+  const unsigned eslot_s = slot_s + NT * 128u;
   const size_t plane_elems = (size_t)height * width;
   const int cpairs = (channels + 1) >> 1;
-  const int units = num_images * cpairs * slabs;             // (image, channel pair, band)
+  const int units = num_images * cpairs * nbands;
   const int w4 = width >> 2;
 
-  const int lane_y = 2 * min(lane, ypairs - 1);
   const unsigned tile_s = slot_s + (unsigned)lane * 4u;       // this lane's first tile float
   const unsigned ch1 = (unsigned)bins * 4u;                   // second channel's tile follows the first
   const unsigned cb = (unsigned)channels * (unsigned)bins;
@@ -732,12 +810,16 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     const int unit = __shfl_sync(0xffffffffu, unit_next, 0);
     if (unit >= units) break;
     if (lane == 0) unit_next = atomicAdd(counter, 1);          // in flight while this unit runs
-    const int p = unit / slabs, sl = unit - p * slabs;
+    const int p = unit / nbands, bnd = unit - p * nbands;
     const int n = p / cpairs, c = 2 * (p - n * cpairs);
     const bool two = c + 1 < channels;
     const int tile_floats = two ? 2 * bins : bins;
-    const int r0 = sl * slab_rows, r1 = min(height, r0 + slab_rows);
+    const int r0 = bnd * band_rows, r1 = min(height, r0 + band_rows);
     float* gplane = dx + ((size_t)n * channels + c) * plane_elems;
+    const int j0 = __ldg(img_start + n), nroi = __ldg(img_start + n + 1) - j0;
+    const int nvis = __ldg(vcount + n * nbands + bnd);
+    const uint2* vlist = visits + ((size_t)j0 * nbands + (size_t)bnd * nroi);
+    uint2 vrec = lane < nvis ? __ldg(vlist + lane) : make_uint2(0u, 0u);    // first 32 visits
 
     // ---- band := 0 (or the current dX rows when accumulating) ----
     __syncwarp();
@@ -745,155 +827,147 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
       for (int i = lane; i < (r1 - r0) * width; i += 32) {
         const int r = i / width, x = i - r * width;
         const size_t gi = (size_t)(r0 + r) * width + x;
-        slab[r * pitch2 + x] = make_float2(gplane[gi], two ? gplane[plane_elems + gi] : 0.0f);
+        band[r * pitch2 + x] = make_float2(gplane[gi], two ? gplane[plane_elems + gi] : 0.0f);
       }
     } else {
-      float4* s4 = reinterpret_cast<float4*>(slab);
+      float4* s4 = reinterpret_cast<float4*>(band);
       const int n4 = ((r1 - r0) * pitch2) >> 1;
       for (int i = lane; i < n4; i += 32) s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
 
-    // ---- the band's rows as byte offsets in a plane of `rb`-byte rows ----
-    const int b0 = r0, b1 = r1;
-    const unsigned band_lo = (unsigned)b0 * rb, band_span = (unsigned)(b1 - b0) * rb;
     const unsigned col_base = sbase - (unsigned)r0 * rb;      // + row offset + column offset
-    const int j0 = __ldg(img_start + n), nroi = __ldg(img_start + n + 1) - j0;
     const float* dy_c = dy + (size_t)c * bins;
-    bool tok[NT];
+    int tix[NT];              // tile floats past the pair's end re-read its last float (never used)
 #pragma unroll
-    for (int i = 0; i < NT; ++i) tok[i] = lane + 32 * i < tile_floats;
+    for (int i = 0; i < NT; ++i) tix[i] = min(lane + 32 * i, tile_floats - 1);
 
-    if (b1 > b0 && nroi > 0) {
-      // ROIs are scanned 32 at a time, one chunk ahead of their use; a ROI is visited when its
-      // touched rows meet the band
-      const uint2 none = make_uint2(1u, 0u);                     // first > last
-      uint2 rec_cur = lane < nroi ? __ldg(scan + j0 + lane) : none;
-      uint2 rec_nxt = 32 + lane < nroi ? __ldg(scan + j0 + 32 + lane) : none;
-      int jb = 0;
-#define MOBULA_TOUCHES(rec) ((int)((rec).x & 0xffffu) < b1 && (int)((rec).x >> 16) >= b0 && \
-                             ((rec).x & 0xffffu) <= ((rec).x >> 16))
-      unsigned bits = __ballot_sync(0xffffffffu, MOBULA_TOUCHES(rec_cur));
-      int jv = -1, roi = 0;
-      // advance to the next visit: (grouped position jv, roi row) or jv = -1
-#define MOBULA_NEXT_VISIT()                                                                     \
-  do {                                                                                          \
-    jv = -1;                                                                                    \
-    while (bits == 0u) {                                                                        \
-      jb += 32;                                                                                 \
-      if (jb >= nroi) break;                                                                    \
-      rec_cur = rec_nxt;                                                                        \
-      rec_nxt = jb + 32 + lane < nroi ? __ldg(scan + j0 + jb + 32 + lane) : none;               \
-      bits = __ballot_sync(0xffffffffu, MOBULA_TOUCHES(rec_cur));                               \
-    }                                                                                           \
-    if (bits != 0u) {                                                                           \
-      const int k_ = __ffs(bits) - 1;                                                           \
-      bits &= bits - 1u;                                                                        \
-      jv = j0 + jb + k_;                                                                        \
-      roi = (int)__shfl_sync(0xffffffffu, rec_cur.y, k_);                                       \
-    }                                                                                           \
-  } while (0)
-#define MOBULA_LOAD_VISIT(v)                                                                    \
-  do {                                                                                          \
-    const float* tile_ = dy_c + (size_t)((unsigned)roi) * cb + lane;                            \
-    _Pragma("unroll") for (int i = 0; i < NT; ++i)(v).g[i] = tok[i] ? __ldg(tile_ + 32 * i) : 0.0f; \
-    const uint4* yr_ = ypair + ((unsigned)jv * (unsigned)(2 * ypairs) + (unsigned)lane_y);      \
-    (v).ya = __ldg(yr_);                                                                        \
-    (v).yb = __ldg(yr_ + 1);                                                                    \
-    const uint4* cr_ = cols + ((unsigned)jv * (unsigned)maxc + (unsigned)lane);                 \
-    _Pragma("unroll") for (int k = 0; k < NCK; ++k)(v).col[k] = __ldg(cr_ + 32 * k);            \
+    // visit k: record in lane k % 32 of `vrec` (chunk k / 32)
+#define MOBULA_LOAD_VISIT(v, k)                                                                   \
+  do {                                                                                            \
+    const unsigned vx_ = __shfl_sync(0xffffffffu, vrec.x, (k) & 31);                              \
+    const unsigned roi_ = __shfl_sync(0xffffffffu, vrec.y, (k) & 31);                             \
+    const unsigned jv_ = vx_ & 0xfffffu, first_ = (vx_ >> 20) & 63u, cnt_ = (vx_ >> 26) + 1u;       \
+    const float* tile_ = dy_c + (size_t)roi_ * cb;                                                \
+    _Pragma("unroll") for (int i = 0; i < NT; ++i)(v).g[i] = __ldg(tile_ + tix[i]);               \
+    const uint2* er_ = rows_in + (jv_ * (unsigned)maxe + first_ + (unsigned)lane);                \
+    _Pragma("unroll") for (int i = 0; i < NE; ++i)                                                \
+        (v).e[i] = (unsigned)lane + 32u * i < cnt_ ? __ldg(er_ + 32 * i) : make_uint2(0u, 0u);    \
+    const uint4* cr_ = cols + (jv_ * (unsigned)maxc + (unsigned)lane);                            \
+    _Pragma("unroll") for (int i = 0; i < NCK; ++i)(v).col[i] = __ldg(cr_ + 32 * i);              \
   } while (0)
 
-      // one visit: the ROI's dy tiles and row records go to the warp's slot, then every touched
-      // column (lane) adds its share to the rows of the band
-      auto visit = [&](const VisitRegs<NT, NCK>& cur, int jcur) {
-        __syncwarp();
+    // one visit: the ROI's dy tiles and the band's row entries go to the warp's slot, then every
+    // touched column (lane) adds its share to the band's rows
+    auto visit = [&](const VisitRegs<NT, NCK, NE>& cur, unsigned vx) {
+      const unsigned jcur = vx & 0xfffffu, cnt = (vx >> 26) + 1u;
+      __syncwarp();
 #pragma unroll
-        for (int i = 0; i < NT; ++i) sts_at(tile_s + 128u * i, cur.g[i]);
-        // rows outside the band get the sign bit: one compare per row in the loop below
-        uint4 ya = cur.ya, yb = cur.yb;
-        const bool live = lane < pooled_h;
-        if (!(live && ya.x - band_lo < band_span)) ya.x = 0x80000000u;
-        if (!(live && ya.z - band_lo < band_span)) ya.z = 0x80000000u;
-        if (!(live && yb.x - band_lo < band_span)) yb.x = 0x80000000u;
-        if (!(live && yb.z - band_lo < band_span)) yb.z = 0x80000000u;
-        if (lane < ypairs) {
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(yslot_s + lane * 32u), "r"(ya.x),
-                       "r"(ya.y), "r"(ya.z), "r"(ya.w)
-                       : "memory");
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(yslot_s + lane * 32u + 16u), "r"(yb.x),
-                       "r"(yb.y), "r"(yb.z), "r"(yb.w)
-                       : "memory");
-        }
-        const unsigned any = __ballot_sync(0xffffffffu, (int)(ya.x & ya.z & yb.x & yb.z) >= 0);
-        __syncwarp();
+      for (int i = 0; i < NT; ++i) sts_at(tile_s + 128u * i, cur.g[i]);
 #pragma unroll
-        for (int ck = 0; ck < NCK; ++ck) {
-          const uint4 cr = cur.col[ck];
-          const int nh = (int)((cr.x >> 16) & 0xffu);
-          const bool act = nh > 0;
-          const unsigned caddr = col_base + (cr.x & 0xffffu);
-          const unsigned g0 = slot_s + ((cr.x >> 24) & 0xfu) * 4u, g1 = slot_s + (cr.x >> 28) * 4u;
-          const float w0 = __uint_as_float(cr.y), w1 = __uint_as_float(cr.z);
-          unsigned m = any;
-          while (m) {
-            const int ph = __ffs(m) - 1;
-            m &= m - 1u;
-            const uint4 ra = lds128(yslot_s + ph * 32u), rb2 = lds128(yslot_s + ph * 32u + 16u);   // broadcast
-            const unsigned grow = (unsigned)(ph * pooled_w) * 4u;
-            float2 t = make_float2(0.0f, 0.0f);
-            if (act) {
-              t.x = w0 * lds_vol(g0 + grow);
-              t.y = w0 * lds_vol(g0 + grow + ch1);
-              if (nh > 1) {
-                t.x = fmaf(w1, lds_vol(g1 + grow), t.x);
-                t.y = fmaf(w1, lds_vol(g1 + grow + ch1), t.y);
-                for (int e = 2; e < nh; ++e) {
-                  const uint2 hx = __ldg(extra + (size_t)jcur * maxc + cr.w + (e - 2));
-                  const unsigned ge = slot_s + hx.x * 4u + grow;
-                  t.x = fmaf(__uint_as_float(hx.y), lds_vol(ge), t.x);
-                  t.y = fmaf(__uint_as_float(hx.y), lds_vol(ge + ch1), t.y);
-                }
+      for (int i = 0; i < NE; ++i)
+        if ((unsigned)lane + 32u * i < cnt)
+          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(eslot_s + (lane + 32u * i) * 8u), "r"(cur.e[i].x),
+                       "r"(cur.e[i].y)
+                       : "memory");
+      __syncwarp();
+#pragma unroll
+      for (int ck = 0; ck < NCK; ++ck) {
+        const uint4 cr = cur.col[ck];
+        const int nh = (int)((cr.x >> 16) & 0xffu);
+        if (nh == 0) continue;                        // this lane has no column in this chunk
+        const unsigned caddr = col_base + (cr.x & 0xffffu);
+        const unsigned g0 = slot_s + ((cr.x >> 24) & 0xfu) * 4u, g1 = slot_s + (cr.x >> 28) * 4u;
+        const float w0 = __uint_as_float(cr.y), w1 = __uint_as_float(cr.z);
+        unsigned cur_ph = 0xffffffffu;
+        float2 t = make_float2(0.0f, 0.0f);
+        unsigned e = 0;
+        while (e < cnt) {
+          const uint2 re = lds64u(eslot_s + e * 8u);            // broadcast
+          const uint2 rn = lds64u(eslot_s + e * 8u + 8u);       // next entry (slot has room)
+          const unsigned ph = re.x & 15u;
+          if (ph != cur_ph) {                                   // warp-uniform
+            cur_ph = ph;
+            const unsigned grow = ph * (unsigned)pooled_w * 4u;
+            t.x = w0 * lds_vol(g0 + grow);
+            t.y = w0 * lds_vol(g0 + grow + ch1);
+            if (nh > 1) {
+              t.x = fmaf(w1, lds_vol(g1 + grow), t.x);
+              t.y = fmaf(w1, lds_vol(g1 + grow + ch1), t.y);
+              for (int x = 2; x < nh; ++x) {
+                const uint2 hx = __ldg(extra + (size_t)jcur * maxc + cr.w + (x - 2));
+                const unsigned ge = slot_s + hx.x * 4u + grow;
+                t.x = fmaf(__uint_as_float(hx.y), lds_vol(ge), t.x);
+                t.y = fmaf(__uint_as_float(hx.y), lds_vol(ge + ch1), t.y);
               }
             }
-            // the rows of a bin row are distinct: the read-modify-writes are independent
-            const bool p0 = act && (int)ra.x >= 0, p1 = act && (int)ra.z >= 0;
-            const bool p2 = act && (int)rb2.x >= 0, p3 = act && (int)rb2.z >= 0;
-            const unsigned a0 = caddr + ra.x, a1 = caddr + ra.z, a2 = caddr + rb2.x, a3 = caddr + rb2.z;
-            float2 v0, v1, v2, v3;
-            if (p0) v0 = lds64(a0);
-            if (p1) v1 = lds64(a1);
-            if (p2) v2 = lds64(a2);
-            if (p3) v3 = lds64(a3);
-            const float y0 = __uint_as_float(ra.y), y1 = __uint_as_float(ra.w);
-            const float y2 = __uint_as_float(rb2.y), y3 = __uint_as_float(rb2.w);
-            if (p0) sts64(a0, make_float2(fmaf(y0, t.x, v0.x), fmaf(y0, t.y, v0.y)));
-            if (p1) sts64(a1, make_float2(fmaf(y1, t.x, v1.x), fmaf(y1, t.y, v1.y)));
-            if (p2) sts64(a2, make_float2(fmaf(y2, t.x, v2.x), fmaf(y2, t.y, v2.y)));
-            if (p3) sts64(a3, make_float2(fmaf(y3, t.x, v3.x), fmaf(y3, t.y, v3.y)));
+          }
+          const unsigned a = caddr + (re.x & ~15u);
+          const float wy = __uint_as_float(re.y);
+          if (e + 1 < cnt && (rn.x & 15u) == ph) {
+            // two rows of one bin row: distinct addresses, the read-modify-writes overlap
+            const unsigned a2 = caddr + (rn.x & ~15u);
+            const float wy2 = __uint_as_float(rn.y);
+            const float2 v = lds64(a), v2 = lds64(a2);
+            sts64(a, make_float2(fmaf(wy, t.x, v.x), fmaf(wy, t.y, v.y)));
+            sts64(a2, make_float2(fmaf(wy2, t.x, v2.x), fmaf(wy2, t.y, v2.y)));
+            e += 2;
+          } else {
+            const float2 v = lds64(a);
+            sts64(a, make_float2(fmaf(wy, t.x, v.x), fmaf(wy, t.y, v.y)));
+            e += 1;
           }
         }
-      };
-
-      // two register sets in turn: the loads of visit k + 1 are in flight while visit k runs
-      VisitRegs<NT, NCK> va, vb;
-      MOBULA_NEXT_VISIT();
-      if (jv >= 0) MOBULA_LOAD_VISIT(va);
-      while (jv >= 0) {
-        int jcur = jv;
-        MOBULA_NEXT_VISIT();
-        if (jv >= 0) MOBULA_LOAD_VISIT(vb);
-        visit(va, jcur);
-        if (jv < 0) break;
-        jcur = jv;
-        MOBULA_NEXT_VISIT();
-        if (jv >= 0) MOBULA_LOAD_VISIT(va);
-        visit(vb, jcur);
       }
-#undef MOBULA_LOAD_VISIT
-#undef MOBULA_NEXT_VISIT
-#undef MOBULA_TOUCHES
+    };
+
+    // register sets in turn: the loads of the next visits are in flight while visit k runs
+    // (visit records come 32 at a time, the next chunk one chunk ahead)
+    uint2 vnext = 32 + lane < nvis ? __ldg(vlist + 32 + lane) : make_uint2(0u, 0u);
+    // STAGE(set, x, k): visit k (k < nvis) -> register set; its record comes from the current
+    // chunk, or from the next one when k has crossed into it
+#define MOBULA_STAGE(v, vx, k)                                                                    \
+  do {                                                                                            \
+    if ((k) < nvis) {                                                                             \
+      if (((k) & 31) == 0 && (k) > 0) {                                                           \
+        vrec = vnext;                                                                             \
+        vnext = (k) + 32 + lane < nvis ? __ldg(vlist + (k) + 32 + lane) : make_uint2(0u, 0u);     \
+      }                                                                                           \
+      vx = __shfl_sync(0xffffffffu, vrec.x, (k) & 31);                                            \
+      MOBULA_LOAD_VISIT(v, k);                                                                    \
+    }                                                                                             \
+  } while (0)
+    if constexpr (NT >= 8) {
+      // large tiles: two sets (three would not fit the register budget of two CTAs per SM)
+      VisitRegs<NT, NCK, NE> va, vb;
+      unsigned xa = 0u, xb = 0u;
+      MOBULA_STAGE(va, xa, 0);
+      for (int k = 0; k < nvis; k += 2) {
+        MOBULA_STAGE(vb, xb, k + 1);
+        visit(va, xa);
+        if (k + 1 >= nvis) break;
+        MOBULA_STAGE(va, xa, k + 2);
+        visit(vb, xb);
+      }
+    } else {
+      VisitRegs<NT, NCK, NE> va, vb, vc;
+      unsigned xa = 0u, xb = 0u, xc = 0u;
+      MOBULA_STAGE(va, xa, 0);
+      MOBULA_STAGE(vb, xb, 1);
+      for (int k = 0; k < nvis; k += 3) {
+        MOBULA_STAGE(vc, xc, k + 2);
+        visit(va, xa);
+        if (k + 1 >= nvis) break;
+        MOBULA_STAGE(va, xa, k + 3);
+        visit(vb, xb);
+        if (k + 2 >= nvis) break;
+        MOBULA_STAGE(vb, xb, k + 4);
+        visit(vc, xc);
+      }
     }
+#undef MOBULA_STAGE
+#undef MOBULA_LOAD_VISIT
+
     __syncwarp();
     // ---- the finished band -> the two planes of dX, each element written once ----
     float* gplane1 = gplane + plane_elems;
@@ -904,7 +978,7 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
       float4* ga = reinterpret_cast<float4*>(gplane + (size_t)r0 * width);
       float4* gb = reinterpret_cast<float4*>(gplane1 + (size_t)r0 * width);
       for (int i = lane; i < total; i += 32) {
-        const float4* src = reinterpret_cast<const float4*>(slab + (size_t)r * pitch2 + 4 * c4);
+        const float4* src = reinterpret_cast<const float4*>(band + (size_t)r * pitch2 + 4 * c4);
         const float4 lo = src[0], hi = src[1];       // (a0 b0 a1 b1) (a2 b2 a3 b3)
         ga[i] = make_float4(lo.x, lo.z, hi.x, hi.z);
         if (two) gb[i] = make_float4(lo.y, lo.w, hi.y, hi.w);
@@ -918,7 +992,7 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     } else {
       for (int i = lane; i < (r1 - r0) * width; i += 32) {
         const int r = i / width, x = i - r * width;
-        const float2 v = slab[r * pitch2 + x];
+        const float2 v = band[r * pitch2 + x];
         const size_t gi = (size_t)(r0 + r) * width + x;
         gplane[gi] = v.x;
         if (two) gplane1[gi] = v.y;
@@ -928,19 +1002,21 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
 }
 
 struct BwdLayout {
-  size_t img_start, order, scan, ypair, cols, extra, counter, total;
+  size_t img_start, order, rows, bstart, cols, extra, visits, vcount, counter, total;
 };
 
-BwdLayout bwd_layout(const RoiAlignArgs& a, int ypairs, int maxc) {
+BwdLayout bwd_layout(const RoiAlignArgs& a, int maxe, int maxc, int nbands) {
   BwdLayout l;
   size_t p = 0;
-  const size_t R = (size_t)a.num_rois;
-  l.img_start = p;  p += align_up((size_t)(a.num_images + 2) * sizeof(int), 256);
+  const size_t R = (size_t)a.num_rois, N = (size_t)(a.num_images > 0 ? a.num_images : 0);
+  l.img_start = p;  p += align_up((N + 2) * sizeof(int), 256);
   l.order = p;      p += align_up(R * sizeof(int), 256);
-  l.scan = p;       p += align_up(R * sizeof(uint2), 256);
-  l.ypair = p;      p += align_up(R * ypairs * 2 * sizeof(uint4), 256);
+  l.rows = p;       p += align_up(R * maxe * sizeof(uint2), 256);
+  l.bstart = p;     p += align_up(R * (size_t)(nbands + 1), 256);
   l.cols = p;       p += align_up(R * maxc * sizeof(uint4), 256);
   l.extra = p;      p += align_up(R * maxc * sizeof(uint2), 256);
+  l.visits = p;     p += align_up(R * (size_t)nbands * sizeof(uint2), 256);
+  l.vcount = p;     p += align_up(N * (size_t)nbands * sizeof(int), 256);
   l.counter = p;    p += 256;
   l.total = p;
   return l;
@@ -992,15 +1068,17 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
       a.pooled_h * a.pooled_w <= kMaxSlotFloats && a.height < 65536 && a.width * 8 < 65536) {
     const int nt_raw = (2 * a.pooled_h * a.pooled_w + 31) / 32;
     const int nt = nt_raw <= 1 ? 1 : nt_raw <= 2 ? 2 : nt_raw <= 4 ? 4 : nt_raw <= 8 ? 8 : 16;
-    const size_t slots = (size_t)kBwdWarps * (nt * 32 + 8 * 2 * ((a.pooled_h + 1) / 2)) * sizeof(float);
-    // slab rows hold two channels (float2 per pixel); a warp instruction touches one row, so
+    const int maxc = (4 * a.pooled_w + 31) / 32 * 32, maxe = (4 * a.pooled_h + 31) / 32 * 32;
+    const bool small = maxc == 32 && maxe == 32;
+    // per warp: dy tiles of the channel pair + the row entries of a visit
+    const size_t slot = (size_t)(nt * 32 + (small ? 1 : 2) * 64 + 4) * sizeof(float);
+    // band rows hold two channels (float2 per pixel); a warp instruction touches one row, so
     // the pitch only has to keep rows 16-byte aligned
     const int pitch2 = (a.width + 1) & ~1;
     // every warp owns a private band of rows; two CTAs of kBwdWarps warps share an SM
-    const size_t slot = slots / kBwdWarps;
-    const size_t per_warp = (((size_t)smem_optin + 1024) / 2 - 1024 - 64) / kBwdWarps;
+    const size_t per_warp = (((size_t)smem_optin + 1024) / 2 - 1024 - 64) / kBwdWarps / 16 * 16;
     const size_t row_bytes = (size_t)pitch2 * sizeof(float2);
-    if (per_warp > slot + row_bytes) {
+    if (per_warp > slot + row_bytes && a.num_rois <= (1 << 20)) {
       int rows = (int)((per_warp - slot) / row_bytes);
       if (rows > a.height) rows = a.height;
       plan->bwd_ok = 1;
@@ -1008,7 +1086,8 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
       plan->bwd_slab_rows = rows;
       plan->bwd_smem = (size_t)kBwdWarps * (rows * row_bytes + slot);
       plan->bwd_pitch2 = pitch2;
-      plan->bwd_maxc = (4 * a.pooled_w + 31) / 32 * 32;
+      plan->bwd_maxc = maxc;
+      plan->bwd_maxe = maxe;
     }
   }
   return true;
@@ -1102,52 +1181,58 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
 }
 
 size_t resident_bwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan) {
-  return bwd_layout(a, plan.ypairs, plan.bwd_maxc).total;
+  return bwd_layout(a, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slabs).total;
 }
 
 cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan, void* workspace,
                                 const float* dy, float* dx, int accumulate, int num_sms,
                                 cudaStream_t stream) {
-  (void)num_sms;
   if (a.num_images == 0 || a.channels == 0) return cudaSuccess;
-  const BwdLayout l = bwd_layout(a, plan.ypairs, plan.bwd_maxc);
+  const int nbands = plan.bwd_slabs;
+  const BwdLayout l = bwd_layout(a, plan.bwd_maxe, plan.bwd_maxc, nbands);
   char* base = (char*)workspace;
   int* img_start = (int*)(base + l.img_start);
   int* order = (int*)(base + l.order);
-  uint2* scan = (uint2*)(base + l.scan);
-  uint4* ypair = (uint4*)(base + l.ypair);
+  uint2* rows = (uint2*)(base + l.rows);
+  unsigned char* bstart = (unsigned char*)(base + l.bstart);
   uint4* cols = (uint4*)(base + l.cols);
   uint2* extra = (uint2*)(base + l.extra);
+  uint2* visits = (uint2*)(base + l.visits);
+  int* vcount = (int*)(base + l.vcount);
   int* counter = (int*)(base + l.counter);
   cudaError_t e = launch_roi_group(a, img_start, order, stream);
   if (e != cudaSuccess) return e;
   const int tb = a.num_rois > 0 ? (a.num_rois + 3) / 4 : 1;       // one warp per ROI
-  resident_bwd2_table_kernel<<<tb, 128, 0, stream>>>(a.rois, order, img_start, a.num_images, a.height, a.width,
-                                                     plan.bwd_pitch2 * 8, 8, a.pooled_h, a.pooled_w, a.scale,
-                                                     plan.ypairs, plan.bwd_maxc, scan, ypair, cols, extra,
-                                                     counter);
+  resident_bwd2_table_kernel<<<tb, 128, 0, stream>>>(
+      a.rois, order, img_start, a.num_images, a.num_rois, a.height, a.width, plan.bwd_pitch2 * 8, 8,
+      a.pooled_h, a.pooled_w, a.scale, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slab_rows, nbands, rows, bstart,
+      cols, extra, counter);
   count_launch();
-  const long long units = (long long)a.num_images * ((a.channels + 1) / 2) * plan.bwd_slabs;
+  resident_bwd2_visits_kernel<<<a.num_images * nbands, kVisitThreads, 0, stream>>>(
+      order, img_start, bstart, a.num_images, a.num_rois, nbands, visits, vcount);
+  count_launch();
+  const long long units = (long long)a.num_images * ((a.channels + 1) / 2) * nbands;
+  const long long cta_units = (units + kBwdWarps - 1) / kBwdWarps;
   unsigned grid = 0;
-#define MOBULA_BWD2(NT, NCK, ACC)                                                                     \
+#define MOBULA_BWD2(NT, NCK, NE, ACC)                                                                 \
   do {                                                                                                \
-    e = resident_grid(resident_bwd2_kernel<NT, NCK, ACC>, kBwdThreads, plan.bwd_smem, num_sms, units, \
-                      &grid);                                                                         \
+    e = resident_grid(resident_bwd2_kernel<NT, NCK, NE, ACC>, kBwdThreads, plan.bwd_smem, num_sms,    \
+                      cta_units, &grid);                                                              \
     if (e != cudaSuccess) return e;                                                                   \
-    resident_bwd2_kernel<NT, NCK, ACC><<<grid, kBwdThreads, plan.bwd_smem, stream>>>(                 \
-        dy, dx, scan, ypair, cols, extra, img_start, counter, a.num_images, a.channels, a.height,     \
-        a.width, plan.bwd_pitch2, a.pooled_h, a.pooled_w, plan.ypairs, plan.bwd_maxc, plan.bwd_slabs, \
-        plan.bwd_slab_rows);                                                                          \
+    resident_bwd2_kernel<NT, NCK, NE, ACC><<<grid, kBwdThreads, plan.bwd_smem, stream>>>(             \
+        dy, dx, visits, vcount, rows, cols, extra, img_start, counter, a.num_images, a.channels,      \
+        a.height, a.width, plan.bwd_pitch2, a.pooled_h, a.pooled_w, plan.bwd_maxe, plan.bwd_maxc,     \
+        nbands, plan.bwd_slab_rows);                                                                  \
   } while (0)
-#define MOBULA_BWD2_NT(NT)                                      \
-  do {                                                          \
-    if (plan.bwd_maxc == 32) {                                  \
-      if (accumulate) MOBULA_BWD2(NT, 1, true);                 \
-      else MOBULA_BWD2(NT, 1, false);                           \
-    } else {                                                    \
-      if (accumulate) MOBULA_BWD2(NT, 2, true);                 \
-      else MOBULA_BWD2(NT, 2, false);                           \
-    }                                                           \
+#define MOBULA_BWD2_ACC(NT, NCK, NE)                    \
+  do {                                                  \
+    if (accumulate) MOBULA_BWD2(NT, NCK, NE, true);     \
+    else MOBULA_BWD2(NT, NCK, NE, false);               \
+  } while (0)
+#define MOBULA_BWD2_NT(NT)                                                  \
+  do {                                                                      \
+    if (plan.bwd_maxc == 32 && plan.bwd_maxe == 32) MOBULA_BWD2_ACC(NT, 1, 1); \
+    else MOBULA_BWD2_ACC(NT, 2, 2);                                         \
   } while (0)
   const int nt = (2 * a.pooled_h * a.pooled_w + 31) / 32;
   if (nt <= 1) MOBULA_BWD2_NT(1);
@@ -1156,6 +1241,7 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   else if (nt <= 8) MOBULA_BWD2_NT(8);
   else MOBULA_BWD2_NT(16);
 #undef MOBULA_BWD2_NT
+#undef MOBULA_BWD2_ACC
 #undef MOBULA_BWD2
   count_launch();
   return cudaGetLastError();

@@ -96,6 +96,8 @@ struct Buffer {
   }
 };
 
+constexpr int kHostChunks = 8;
+
 struct DeviceState {
   std::mutex mu;
   bool probed = false;
@@ -106,6 +108,9 @@ struct DeviceState {
   cudaStream_t ws_stream = nullptr;
   bool ws_used = false;
   Buffer stage[4];             // host-buffer path: data/dy, rois, out/dx, spare
+  // host-buffer path, pipelined over channel chunks: copy-in / copy-out streams and events
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_in[kHostChunks] = {nullptr}, ev_done[kHostChunks] = {nullptr};
 };
 static DeviceState g_dev[kMaxDevices];
 
@@ -291,6 +296,7 @@ static RoiAlignArgs make_args(const float* rois, int num_rois, int num_images, i
   a.num_rois = num_rois;
   a.num_images = num_images;
   a.channels = channels;
+  a.c_count = 0;
   a.height = height;
   a.width = width;
   a.pooled_h = pooled_h;
@@ -316,6 +322,46 @@ MOBULA_EXPORT uint64_t mobula_roialign_launch_count(void) {
 }
 
 MOBULA_EXPORT const char* mobula_roialign_last_algo(int backward) { return t_algo[backward ? 1 : 0]; }
+
+// ---- host-buffer path, pipelined -------------------------------------------------------
+// The staged tensors are cut into channel chunks; chunk k+1 is copied in and chunk k-1 copied
+// out (two more streams, both directions of the PCIe link) while chunk k is computed.  Needs
+// the resident kernels (they take a channel range); anything else runs unchunked.
+static int pipeline_setup(DeviceState& st) {
+  if (st.s_in) return MOBULA_OK;
+  CUDA_TRY(cudaStreamCreateWithFlags(&st.s_in, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&st.s_out, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&st.ev_start, cudaEventDisableTiming));
+  for (int k = 0; k < kHostChunks; ++k) {
+    CUDA_TRY(cudaEventCreateWithFlags(&st.ev_in[k], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&st.ev_done[k], cudaEventDisableTiming));
+  }
+  return MOBULA_OK;
+}
+
+// channels per chunk (even, so that the backward's channel pairs stay whole); 0: do not chunk
+static int host_chunk(int channels, size_t tensor_bytes) {
+  if (channels < 2 * kHostChunks || tensor_bytes < (size_t(16) << 20)) return 0;
+  int cc = (channels + kHostChunks - 1) / kHostChunks;
+  return (cc + 1) & ~1;
+}
+
+static bool resident_forward_applies(DeviceState& st, const RoiAlignArgs& a, const void* data, unsigned flags) {
+  const unsigned algo = algo_of(flags);
+  ResidentPlan plan;
+  return !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) &&
+         (algo == MOBULA_ROIALIGN_ALGO_AUTO || algo == MOBULA_ROIALIGN_ALGO_RESIDENT) &&
+         resident_supported(a, data, st.smem_optin, &plan);
+}
+
+static bool resident_backward_applies(DeviceState& st, const RoiAlignArgs& a, const void* dx, int mode,
+                                      unsigned flags) {
+  const unsigned algo = algo_of(flags);
+  ResidentPlan plan;
+  return mode == MOBULA_ROIALIGN_BWD_ATOMIC && !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) &&
+         (algo == MOBULA_ROIALIGN_ALGO_AUTO || algo == MOBULA_ROIALIGN_ALGO_RESIDENT) &&
+         resident_supported(a, dx, st.smem_optin, &plan) && plan.bwd_ok;
+}
 
 MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, const float* bottom_data,
                                               const float* bottom_rois, float* top_data,
@@ -355,12 +401,47 @@ MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, cons
   float* d_data = (float*)st.stage[0].ptr;
   float* d_rois = (float*)st.stage[1].ptr;
   float* d_out = (float*)st.stage[2].ptr;
+  RoiAlignArgs a = make_args(d_rois, num_rois, n_img, channels, height, width, pooled_height,
+                             pooled_width, spatial_scale, sampling_ratio);
+  const int cc = resident_forward_applies(st, a, d_data, flags) ? host_chunk(channels, data_bytes) : 0;
+  if (cc > 0) {
+    if ((rc = pipeline_setup(st))) return rc;
+    const size_t hw = (size_t)height * width, bins = (size_t)pooled_height * pooled_width;
+    const size_t row_pitch = (size_t)channels * bins * sizeof(float);
+    CUDA_TRY(cudaMemcpyAsync(d_rois, bottom_rois, rois_bytes, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaEventRecord(st.ev_start, stream));
+    CUDA_TRY(cudaStreamWaitEvent(st.s_in, st.ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(st.s_out, st.ev_start, 0));
+    int k = 0;
+    for (int c0 = 0; c0 < channels; c0 += cc, ++k) {
+      const int cn = channels - c0 < cc ? channels - c0 : cc;
+      for (int n = 0; n < n_img; ++n) {
+        const size_t off = ((size_t)n * channels + c0) * hw;
+        CUDA_TRY(cudaMemcpyAsync(d_data + off, bottom_data + off, (size_t)cn * hw * sizeof(float),
+                                 cudaMemcpyHostToDevice, st.s_in));
+      }
+      if ((flags & MOBULA_ROIALIGN_ACCUMULATE) && num_rois > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(d_out + c0 * bins, row_pitch, top_data + c0 * bins, row_pitch,
+                                   (size_t)cn * bins * sizeof(float), num_rois, cudaMemcpyHostToDevice, st.s_in));
+      CUDA_TRY(cudaEventRecord(st.ev_in[k], st.s_in));
+      CUDA_TRY(cudaStreamWaitEvent(stream, st.ev_in[k], 0));
+      a.c_count = cn;
+      if ((rc = forward_device(st, device, stream, d_data + c0 * hw, d_rois, d_out + c0 * bins, a, flags)))
+        return rc;
+      CUDA_TRY(cudaEventRecord(st.ev_done[k], stream));
+      CUDA_TRY(cudaStreamWaitEvent(st.s_out, st.ev_done[k], 0));
+      if (num_rois > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(top_data + c0 * bins, row_pitch, d_out + c0 * bins, row_pitch,
+                                   (size_t)cn * bins * sizeof(float), num_rois, cudaMemcpyDeviceToHost, st.s_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st.s_out));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return MOBULA_OK;
+  }
   if (data_bytes) CUDA_TRY(cudaMemcpyAsync(d_data, bottom_data, data_bytes, cudaMemcpyHostToDevice, stream));
   CUDA_TRY(cudaMemcpyAsync(d_rois, bottom_rois, rois_bytes, cudaMemcpyHostToDevice, stream));
   if (flags & MOBULA_ROIALIGN_ACCUMULATE)
     CUDA_TRY(cudaMemcpyAsync(d_out, top_data, out_bytes, cudaMemcpyHostToDevice, stream));
-  const RoiAlignArgs a = make_args(d_rois, num_rois, n_img, channels, height, width, pooled_height,
-                                   pooled_width, spatial_scale, sampling_ratio);
   if ((rc = forward_device(st, device, stream, d_data, d_rois, d_out, a, flags))) return rc;
   CUDA_TRY(cudaMemcpyAsync(top_data, d_out, out_bytes, cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
@@ -407,12 +488,50 @@ MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream_, con
   float* d_dy = (float*)st.stage[0].ptr;
   float* d_rois = (float*)st.stage[1].ptr;
   float* d_dx = (float*)st.stage[2].ptr;
+  RoiAlignArgs a = make_args(d_rois, num_rois, n_img, channels, height, width, pooled_height,
+                             pooled_width, spatial_scale, sampling_ratio);
+  const int cc = resident_backward_applies(st, a, d_dx, mode, flags) ? host_chunk(channels, dx_bytes) : 0;
+  if (cc > 0) {
+    if ((rc = pipeline_setup(st))) return rc;
+    const size_t hw = (size_t)height * width, bins = (size_t)pooled_height * pooled_width;
+    const size_t row_pitch = (size_t)channels * bins * sizeof(float);
+    if (rois_bytes) CUDA_TRY(cudaMemcpyAsync(d_rois, bottom_rois, rois_bytes, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaEventRecord(st.ev_start, stream));
+    CUDA_TRY(cudaStreamWaitEvent(st.s_in, st.ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(st.s_out, st.ev_start, 0));
+    int k = 0;
+    for (int c0 = 0; c0 < channels; c0 += cc, ++k) {
+      const int cn = channels - c0 < cc ? channels - c0 : cc;
+      if (num_rois > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(d_dy + c0 * bins, row_pitch, top_diff + c0 * bins, row_pitch,
+                                   (size_t)cn * bins * sizeof(float), num_rois, cudaMemcpyHostToDevice, st.s_in));
+      if (accumulate)
+        for (int n = 0; n < n_img; ++n) {
+          const size_t off = ((size_t)n * channels + c0) * hw;
+          CUDA_TRY(cudaMemcpyAsync(d_dx + off, bottom_diff + off, (size_t)cn * hw * sizeof(float),
+                                   cudaMemcpyHostToDevice, st.s_in));
+        }
+      CUDA_TRY(cudaEventRecord(st.ev_in[k], st.s_in));
+      CUDA_TRY(cudaStreamWaitEvent(stream, st.ev_in[k], 0));
+      a.c_count = cn;
+      if ((rc = backward_device(st, device, stream, d_dy + c0 * bins, d_rois, d_dx + c0 * hw, a, mode, flags)))
+        return rc;
+      CUDA_TRY(cudaEventRecord(st.ev_done[k], stream));
+      CUDA_TRY(cudaStreamWaitEvent(st.s_out, st.ev_done[k], 0));
+      for (int n = 0; n < n_img; ++n) {
+        const size_t off = ((size_t)n * channels + c0) * hw;
+        CUDA_TRY(cudaMemcpyAsync(bottom_diff + off, d_dx + off, (size_t)cn * hw * sizeof(float),
+                                 cudaMemcpyDeviceToHost, st.s_out));
+      }
+    }
+    CUDA_TRY(cudaStreamSynchronize(st.s_out));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return MOBULA_OK;
+  }
   if (dy_bytes) CUDA_TRY(cudaMemcpyAsync(d_dy, top_diff, dy_bytes, cudaMemcpyHostToDevice, stream));
   if (rois_bytes) CUDA_TRY(cudaMemcpyAsync(d_rois, bottom_rois, rois_bytes, cudaMemcpyHostToDevice, stream));
   if (accumulate && dx_bytes)
     CUDA_TRY(cudaMemcpyAsync(d_dx, bottom_diff, dx_bytes, cudaMemcpyHostToDevice, stream));
-  const RoiAlignArgs a = make_args(d_rois, num_rois, n_img, channels, height, width, pooled_height,
-                                   pooled_width, spatial_scale, sampling_ratio);
   if ((rc = backward_device(st, device, stream, d_dy, d_rois, d_dx, a, mode, flags))) return rc;
   if (dx_bytes) CUDA_TRY(cudaMemcpyAsync(bottom_diff, d_dx, dx_bytes, cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
@@ -474,6 +593,16 @@ MOBULA_EXPORT void mobula_roialign_release(void) {
     st.ws_done = nullptr;
     st.ws_used = false;
     for (Buffer& b : st.stage) b.release();
+    if (st.s_in) {
+      cudaStreamDestroy(st.s_in);
+      cudaStreamDestroy(st.s_out);
+      cudaEventDestroy(st.ev_start);
+      for (int k = 0; k < kHostChunks; ++k) {
+        cudaEventDestroy(st.ev_in[k]);
+        cudaEventDestroy(st.ev_done[k]);
+      }
+      st.s_in = st.s_out = nullptr;
+    }
   }
   cudaSetDevice(prev);
 }

@@ -10,6 +10,8 @@ struct RoiAlignArgs {
   int num_rois;
   int num_images;      // -1 = unknown
   int channels, height, width;
+  int c_count;         // resident kernels: work on channels [0, c_count) only (0 = all); `channels`
+                       // stays the stride, so a channel range is a pointer offset + c_count
   int pooled_h, pooled_w;
   float scale;
   int sampling_ratio;

@@ -182,13 +182,13 @@ __device__ __forceinline__ void cta_share(long long total, long long& u0, long l
 // are zero (the reference would read out of bounds, ROIAlign.cpp:43-44).
 __device__ __forceinline__ void zero_rows_of_invalid_rois(float* __restrict__ out, const int* __restrict__ order,
                                                           const int* __restrict__ img_start, int num_images,
-                                                          long long per_roi_out) {
+                                                          long long row_stride, long long row_count) {
   const int i0 = __ldg(img_start + num_images), i1 = __ldg(img_start + num_images + 1);
   long long z0, z1;
-  cta_share((long long)(i1 - i0) * per_roi_out, z0, z1);
+  cta_share((long long)(i1 - i0) * row_count, z0, z1);
   for (long long z = z0 + threadIdx.x; z < z1; z += blockDim.x) {
-    const int jj = (int)(z / per_roi_out);
-    out[(size_t)__ldg(order + i0 + jj) * per_roi_out + (size_t)(z - jj * per_roi_out)] = 0.0f;
+    const int jj = (int)(z / row_count);
+    out[(size_t)__ldg(order + i0 + jj) * row_stride + (size_t)(z - jj * row_count)] = 0.0f;
   }
 }
 
@@ -215,11 +215,12 @@ __device__ __forceinline__ PlaneWork next_plane(const int* __restrict__ img_star
 // Plane of the work unit `u` (the one next_plane would return next), or null at the end.
 __device__ __forceinline__ const float* next_plane_ptr(const float* __restrict__ data,
                                                        const int* __restrict__ img_start, int channels,
-                                                       size_t plane_elems, long long u, long long u1, int n) {
+                                                       int c_count, size_t plane_elems, long long u,
+                                                       long long u1, int n) {
   if (u >= u1) return nullptr;
-  while ((long long)channels * __ldg(img_start + n + 1) <= u) ++n;
+  while ((long long)c_count * __ldg(img_start + n + 1) <= u) ++n;
   const int j0 = __ldg(img_start + n), nroi = __ldg(img_start + n + 1) - j0;
-  const int c = (int)((u - (long long)channels * j0) / nroi);
+  const int c = (int)((u - (long long)c_count * j0) / nroi);
   return data + ((size_t)n * channels + c) * plane_elems;
 }
 
@@ -258,7 +259,7 @@ template <int G>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 resident_fwd_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                     const int* __restrict__ img_start, const uint4* __restrict__ entries, int num_images,
-                    int channels, int height, int width, int pitch, int pooled_h, int pooled_w,
+                    int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w,
                     int accumulate, int use_bulk) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
@@ -278,20 +279,23 @@ resident_fwd_kernel(const float* __restrict__ data, float* __restrict__ out, con
   }
   __syncthreads();
   uint32_t parity = 0;
-  if (!accumulate) zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins);
+  if (!accumulate)
+    zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
+                              (long long)c_count * bins);
 
   // this lane's first bin, and the step to its next one (bins lane, lane + 32, ...)
   const int ph0 = lane / pooled_w, pw0 = lane - ph0 * pooled_w;
   const int dph = 32 / pooled_w, dpw = 32 - dph * pooled_w;
 
   long long u, u1;
-  cta_share((long long)channels * __ldg(img_start + num_images), u, u1);
+  cta_share((long long)c_count * __ldg(img_start + num_images), u, u1);
   int n = 0;
   while (u < u1) {
-    const PlaneWork w = next_plane(img_start, channels, u, u1, n);
+    const PlaneWork w = next_plane(img_start, c_count, u, u1, n);
     __syncthreads();   // every warp is done reading the previous plane
     load_padded_plane(plane, data + ((size_t)w.n * channels + w.c) * plane_elems,
-                      next_plane_ptr(data, img_start, channels, plane_elems, u, u1, n), height, width, pitch,
+                      next_plane_ptr(data, img_start, channels, c_count, plane_elems, u, u1, n), height, width,
+                      pitch,
                       &bar, parity, use_bulk);
 
     int jj = w.jj0 + warp;
@@ -384,7 +388,7 @@ template <int ITERS, int NCH, bool ACC>
 __global__ void __launch_bounds__(kFwd2Threads, 1)
 resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                      const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
-                     int channels, int height, int width, int pitch, int pooled_h, int pooled_w,
+                     int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w,
                      int use_bulk) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
@@ -404,7 +408,9 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
   }
   __syncthreads();
   uint32_t parity = 0;
-  if (!ACC) zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins);
+  if (!ACC)
+    zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
+                              (long long)c_count * bins);
 
   // which of this lane's results are outputs: the first sample column of a bin, of an
   // existing bin row
@@ -413,15 +419,16 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
   for (int ch = 0; ch < NCH; ++ch) stores[ch] = (q & 1) == 0 && 8 * ch + (q >> 1) < pooled_w;
 
   long long u, u1;
-  cta_share((long long)channels * __ldg(img_start + num_images), u, u1);
+  cta_share((long long)c_count * __ldg(img_start + num_images), u, u1);
   int n = 0;
   unsigned epoch = 0;
   while (u < u1) {
-    const PlaneWork w = next_plane(img_start, channels, u, u1, n);
+    const PlaneWork w = next_plane(img_start, c_count, u, u1, n);
     __syncthreads();   // every warp is done reading the previous plane
 #ifndef MOBULA_EXP_NOLOAD
     load_padded_plane(plane, data + ((size_t)w.n * channels + w.c) * plane_elems,
-                      next_plane_ptr(data, img_start, channels, plane_elems, u, u1, n), height, width, pitch,
+                      next_plane_ptr(data, img_start, channels, c_count, plane_elems, u, u1, n), height, width,
+                      pitch,
                       &bar, parity, use_bulk);
 #endif
     ++epoch;
@@ -781,8 +788,8 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
                      const int* __restrict__ vcount, const uint2* __restrict__ rows_in,
                      const uint4* __restrict__ cols, const uint2* __restrict__ extra,
                      const int* __restrict__ img_start, int* __restrict__ counter, int num_images,
-                     int channels, int height, int width, int pitch2, int pooled_h, int pooled_w, int maxe,
-                     int maxc, int nbands, int band_rows) {
+                     int channels, int c_count, int height, int width, int pitch2, int pooled_h, int pooled_w,
+                     int maxe, int maxc, int nbands, int band_rows) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bins = pooled_h * pooled_w;
@@ -796,7 +803,7 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
   const unsigned slot_s = sbase + (unsigned)band_rows * rb;
   const unsigned eslot_s = slot_s + NT * 128u;
   const size_t plane_elems = (size_t)height * width;
-  const int cpairs = (channels + 1) >> 1;
+  const int cpairs = (c_count + 1) >> 1;
   const int units = num_images * cpairs * nbands;
   const int w4 = width >> 2;
 
@@ -812,7 +819,7 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     if (lane == 0) unit_next = atomicAdd(counter, 1);          // in flight while this unit runs
     const int p = unit / nbands, bnd = unit - p * nbands;
     const int n = p / cpairs, c = 2 * (p - n * cpairs);
-    const bool two = c + 1 < channels;
+    const bool two = c + 1 < c_count;
     const int tile_floats = two ? 2 * bins : bins;
     const int r0 = bnd * band_rows, r1 = min(height, r0 + band_rows);
     float* gplane = dx + ((size_t)n * channels + c) * plane_elems;
@@ -1111,7 +1118,8 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   int* order = (int*)(base + l.order);
   cudaError_t e = launch_roi_group(a, img_start, order, stream);
   if (e != cudaSuccess) return e;
-  const long long work = (long long)a.num_rois * a.channels;
+  const int cc = a.c_count > 0 ? a.c_count : a.channels;      // channels worked on (stride: a.channels)
+  const long long work = (long long)a.num_rois * cc;
   unsigned grid = 0;
   if (plan.fwd_two) {
     uint2* entries = (uint2*)(base + l.entries);
@@ -1126,7 +1134,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
                       work, &grid);                                                                  \
     if (e != cudaSuccess) return e;                                                                  \
     resident_fwd2_kernel<ITERS, NCH, ACC><<<grid, kFwd2Threads, plan.fwd_smem, stream>>>(            \
-        data, out, order, img_start, entries, a.num_images, a.channels, a.height, a.width,           \
+        data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,       \
         plan.pitch, a.pooled_h, a.pooled_w, plan.use_bulk);                                          \
   } while (0)
 #define MOBULA_FWD2_NCH(ITERS, NCH)                  \
@@ -1166,7 +1174,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     e = resident_grid(resident_fwd_kernel<G>, kFwdThreads, plan.fwd_smem, num_sms, work, &grid);    \
     if (e != cudaSuccess) return e;                                                                 \
     resident_fwd_kernel<G><<<grid, kFwdThreads, plan.fwd_smem, stream>>>(                           \
-        data, out, order, img_start, entries, a.num_images, a.channels, a.height, a.width,          \
+        data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,      \
         plan.pitch, a.pooled_h, a.pooled_w, accumulate, plan.use_bulk);                             \
   } while (0)
   switch (plan.grid) {
@@ -1211,7 +1219,8 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   resident_bwd2_visits_kernel<<<a.num_images * nbands, kVisitThreads, 0, stream>>>(
       order, img_start, bstart, a.num_images, a.num_rois, nbands, visits, vcount);
   count_launch();
-  const long long units = (long long)a.num_images * ((a.channels + 1) / 2) * nbands;
+  const int cc = a.c_count > 0 ? a.c_count : a.channels;      // channels worked on (stride: a.channels)
+  const long long units = (long long)a.num_images * ((cc + 1) / 2) * nbands;
   const long long cta_units = (units + kBwdWarps - 1) / kBwdWarps;
   unsigned grid = 0;
 #define MOBULA_BWD2(NT, NCK, NE, ACC)                                                                 \
@@ -1220,7 +1229,7 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
                       cta_units, &grid);                                                              \
     if (e != cudaSuccess) return e;                                                                   \
     resident_bwd2_kernel<NT, NCK, NE, ACC><<<grid, kBwdThreads, plan.bwd_smem, stream>>>(             \
-        dy, dx, visits, vcount, rows, cols, extra, img_start, counter, a.num_images, a.channels,      \
+        dy, dx, visits, vcount, rows, cols, extra, img_start, counter, a.num_images, a.channels, cc,  \
         a.height, a.width, plan.bwd_pitch2, a.pooled_h, a.pooled_w, plan.bwd_maxe, plan.bwd_maxc,     \
         nbands, plan.bwd_slab_rows);                                                                  \
   } while (0)

@@ -369,6 +369,43 @@ def test_numpy_operator_both_call_forms(api, oracle):
     assert not wide[..., 1::2].any()
 
 
+def test_host_buffer_path_is_pipelined_over_channel_chunks(api, native, oracle):
+    """Host tensors of 16 MiB and more are staged in channel chunks (copy-in, compute and
+    copy-out overlap); the result must not depend on that."""
+    from mobulaop_b200 import _native
+    wl = WL.Workload('host-chunks', 2, 50, 200, 272, 40, (7, 7), 0.25, 2)     # 21.8 MB of data
+    data, rois, dy = WL.make_inputs(wl, seed=5)
+    rois[3, 0] = 7                                  # a batch index outside [0, N)
+    good = np.array([r for r in range(len(rois)) if r != 3])
+    op = api.op.ROIAlign[np.ndarray](pooled_size=wl.pooled, spatial_scale=wl.scale,
+                                     sampling_ratio=wl.sampling_ratio)
+    y = op(data, rois)
+    y_ref = oracle.forward(data, rois[good], wl.pooled, wl.scale, wl.sampling_ratio, threads=0)
+    assert_bit_exact(y[good], y_ref)
+    assert not y[3].any()
+    dx, _ = op.backward(dy)
+    dyg = np.ascontiguousarray(dy[good])
+    dx_ref = oracle.backward(dyg, rois[good], data.shape, wl.scale, wl.sampling_ratio)
+    dx_abs = oracle.backward(np.abs(dyg), rois[good], data.shape, wl.scale, wl.sampling_ratio)
+    assert_scatter_close(dx, dx_ref, dx_abs, rtol=1e-5)
+    assert _native.last_algo(False) == 'resident' and _native.last_algo(True) == 'resident'
+    # accumulating variants (req = 'add') through the v2 entry points with host pointers
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    N, C, H, W = data.shape
+    R = len(rois)
+    flags = _native.make_flags(accumulate=True, host=True)
+    base = np.random.default_rng(6).standard_normal(y.shape).astype(np.float32)
+    acc = base.copy()
+    _native.check(native.mobula_roialign_forward_f32(0, None, p(data), p(rois), p(acc), R, N, C, H, W, 7, 7,
+                                                     wl.scale, 2, flags))
+    assert_bit_exact(acc, (base + y).astype(np.float32))
+    dbase = np.random.default_rng(7).standard_normal(data.shape).astype(np.float32)
+    dacc = dbase.copy()
+    _native.check(native.mobula_roialign_backward_f32(0, None, p(dy), p(rois), p(dacc), R, N, C, H, W, 7, 7,
+                                                      wl.scale, 2, _native.BWD_ATOMIC, flags))
+    np.testing.assert_allclose(dacc, dbase + dx, rtol=1e-5, atol=1e-5)
+
+
 def test_mixed_devices_rejected(api, torch):
     dev = torch.device('cuda', 0)
     data = torch.zeros((1, 1, 4, 4), device=dev)

@@ -209,3 +209,19 @@ def test_two_rank_gloo_driver(tmp_path):
         capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert 'SHARD-OK' in out.stdout
+
+
+def test_result_arrays_fall_back_to_pageable_memory_without_a_gpu():
+    """mobulaop_b200.glue.pinned: small results are plain NumPy arrays; large ones are
+    page-locked when cudaMallocHost works and plain arrays otherwise (this container)."""
+    from mobulaop_b200.glue import pinned
+    small = pinned.empty((3, 5), np.float32)
+    assert small.shape == (3, 5) and small.dtype == np.float32
+    big = pinned.empty((1 << 19,), np.float32)           # 2 MiB
+    assert big.shape == (1 << 19,) and big.dtype == np.float32
+    big[:] = 1.0
+    assert float(big.sum()) == float(1 << 19)
+    view = big[::2]
+    del big                                              # the buffer outlives its first owner
+    assert view[0] == 1.0
+    pinned.drain()

@@ -146,7 +146,7 @@ void mobula_host_free(void* ptr);
 /* Number of kernel launches issued by this library since load (all threads). */
 uint64_t mobula_roialign_launch_count(void);
 
-/* Name of the kernel family the last forward / backward call on this thread used
+/* Name of the kernel family the last forward / backward call of this process used
  * ("gather", "plane", "deterministic", ...). */
 const char* mobula_roialign_last_algo(int backward);
 

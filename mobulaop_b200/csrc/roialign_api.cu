@@ -25,7 +25,8 @@ static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static thread_local std::string t_error;
-static thread_local const char* t_algo[2] = {"none", "none"};
+// last kernel family used, process wide (autograd runs the backward on another thread)
+static std::atomic<const char*> t_algo[2] = {{"none"}, {"none"}};
 
 static int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -321,7 +322,7 @@ MOBULA_EXPORT uint64_t mobula_roialign_launch_count(void) {
   return g_launches.load(std::memory_order_relaxed);
 }
 
-MOBULA_EXPORT const char* mobula_roialign_last_algo(int backward) { return t_algo[backward ? 1 : 0]; }
+MOBULA_EXPORT const char* mobula_roialign_last_algo(int backward) { return t_algo[backward ? 1 : 0].load(); }
 
 // ---- host-buffer path, pipelined -------------------------------------------------------
 // The staged tensors are cut into channel chunks; chunk k+1 is copied in and chunk k-1 copied

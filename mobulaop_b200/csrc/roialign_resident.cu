@@ -373,14 +373,17 @@ struct Roi2Regs {
   int roi;
 };
 
+// Lanes without a sample column / bin row of their own re-read the last existing one: same
+// addresses as a working lane, i.e. broadcasts that add no bank conflicts.
 template <int ITERS, int NCH>
 __device__ __forceinline__ void load_roi2(Roi2Regs<ITERS, NCH>& r, const uint2* __restrict__ ent,
-                                          const int* __restrict__ order_j, int h, int q) {
+                                          const int* __restrict__ order_j, int h, int q, int last_row,
+                                          int last_col) {
   const uint4* ent_y = reinterpret_cast<const uint4*>(ent);
 #pragma unroll
-  for (int it = 0; it < ITERS; ++it) r.y[it] = __ldg(ent_y + 2 * it + h);
+  for (int it = 0; it < ITERS; ++it) r.y[it] = __ldg(ent_y + min(2 * it + h, last_row));
 #pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) r.x[ch] = __ldg(ent + 4 * ITERS + 16 * ch + q);
+  for (int ch = 0; ch < NCH; ++ch) r.x[ch] = __ldg(ent + 4 * ITERS + min(16 * ch + q, last_col));
   r.roi = __ldg(order_j);
 }
 
@@ -438,11 +441,14 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
 
     int jj = w.jj0 + warp;
     Roi2Regs<ITERS, NCH> nxt;
-    if (jj < w.jj1) load_roi2(nxt, entries + (size_t)(w.j0 + jj) * kPerRoi, order + w.j0 + jj, h, q);
+    if (jj < w.jj1)
+      load_roi2(nxt, entries + (size_t)(w.j0 + jj) * kPerRoi, order + w.j0 + jj, h, q, pooled_h - 1,
+                2 * pooled_w - 1);
     for (; jj < w.jj1; jj += kFwd2Warps) {
       const Roi2Regs<ITERS, NCH> cur = nxt;
       if (jj + kFwd2Warps < w.jj1)
-        load_roi2(nxt, entries + (size_t)(w.j0 + jj + kFwd2Warps) * kPerRoi, order + w.j0 + jj + kFwd2Warps, h, q);
+        load_roi2(nxt, entries + (size_t)(w.j0 + jj + kFwd2Warps) * kPerRoi, order + w.j0 + jj + kFwd2Warps, h, q,
+                  pooled_h - 1, 2 * pooled_w - 1);
 
       unsigned xa[NCH], xb[NCH];      // shared-memory address of the low column in row 0 / row 1
       float2 lx2[NCH], hx2[NCH];

@@ -251,15 +251,12 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
                   "%s needs num_images in [0, 4096] and a %dx%d fp32 plane within %d bytes of shared "
                   "memory", deterministic ? "deterministic backward" : "plane algorithm", a.height,
                   a.width, st.smem_optin);
-    // owner-computes plane kernels: canonical order for the deterministic mode (also the
-    // fall-back when the merged tables cannot be used), merged weights otherwise
-    const bool canonical = deterministic || !plan.fast_bwd || (flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES);
-    t_algo[1] = canonical ? "plane-canonical" : "plane";
+    // owner-computes plane kernel, contributions in the canonical (single-thread) order
+    t_algo[1] = "plane-canonical";
     RoiTables tables;
-    int rc = prepare_tables(st, a, canonical ? kNeedCells : (kNeedCells | kNeedFast), plan.bwd_pitch, flags,
-                            stream, &tables);
+    int rc = prepare_tables(st, a, kNeedCells, plan.bwd_pitch, flags, stream, &tables);
     if (rc) return rc;
-    CUDA_TRY(launch_bwd_plane(a, plan, tables, dy, dx, accumulate, canonical ? 1 : 0, st.num_sms, stream));
+    CUDA_TRY(launch_bwd_plane(a, plan, tables, dy, dx, accumulate, st.num_sms, stream));
     return release_tables(st, stream);
   }
   {

@@ -39,29 +39,13 @@ struct __align__(16) AxisEntry {
   float w_lo;       // weight of `lo` (1 - l)
 };
 
-// A feature-map row (or column) some sample of the ROI touches, the contiguous range of
-// sample indices k = p*grid + i that touch it (as lo or as hi), and the same information
-// merged per pooled index for the fast backward: hits[hit_first .. hit_first+nhits) hold
-// (p, sum of the weights with which samples of pooled index p touch this pixel).
+// A feature-map row (or column) some sample of the ROI touches and the contiguous range of
+// sample indices k = p*grid + i that touch it (as lo or as hi): the inverse map the canonical
+// (deterministic) backward walks.
 struct __align__(16) AxisCell {
-  // 16-byte chunk A (fast backward)
   int pix;          // row (premultiplied by the plane pitch) or column
-  int nhits;        // merged hits of this pixel
-  int h0p;          // first merged hit, inline
-  float h0w;
-  // chunk B
-  int h1p;          // second merged hit, inline (further ones only in hits[])
-  float h1w;
-  int hit_first;    // index of the first merged hit in hits[]
   int p_first;      // pooled index of sample k_first (k = p * grid + i)
-  // chunk C (canonical backward)
   int k_first, k_last;
-  int pad0, pad1;
-};
-
-struct __align__(8) AxisHit {
-  int p;            // pooled index (ph or pw)
-  float w;          // merged weight; rows carry the 1/count of ROIAlign.cpp:143-146 as well
 };
 
 struct __align__(16) RoiRec {
@@ -76,20 +60,9 @@ struct __align__(16) RoiRec {
   int x_first, x_last;
 };
 
-// (roi, band): `nrows` cells of the roi, starting at cells[ycell], lie in the row band.
-// Self-contained so that the fast backward needs no other record before its loads.
-struct __align__(16) BandPair {
-  int roi;          // row of the caller's roi table (addresses dy)
-  int nrows;
-  int ycell;        // absolute index of the first cell of the band
-  int xcell;        // absolute index of the roi's first column cell
-  int nxcell;
-  int pad0, pad1, pad2;
-};
+constexpr int kBands = 16;   // row bands per plane = warps of the canonical backward's CTAs
 
-constexpr int kBands = 16;   // row bands per plane = warps of the backward CTAs
-
-enum : unsigned { kNeedCells = 1u, kNeedFast = 2u };
+enum : unsigned { kNeedCells = 1u };
 
 struct RoiTables {
   int* img_start;    // [N+2]: grouped position of the first ROI of image n; segment N holds the
@@ -98,9 +71,6 @@ struct RoiTables {
   RoiRec* recs;      // [R]   indexed by grouped position
   AxisEntry* axis;   // [arena]
   AxisCell* cells;   // [2 * arena]
-  AxisHit* hits;     // [2 * arena]
-  BandPair* pairs;   // [R * kBands]: list (n, b) starts at kBands * img_start[n] + b * rois_of(n)
-  int* pair_count;   // [N * kBands]
   long long arena;   // capacity of `axis` in entries
   int pitch;         // shared-memory row pitch the y offsets are premultiplied with
   int regular;       // fixed sampling ratio and an exact arena: roi j owns entries
@@ -125,7 +95,6 @@ struct PlanePlan {
   int bwd_pitch;
   size_t bwd_plane_bytes;
   int gslot_floats;    // staging floats per warp; 0: does not fit, dy is read in place
-  int fast_bwd;        // the merged-weight backward can be used
   int use_bulk;        // rows can be moved with cp.async.bulk (16-byte alignment holds)
   int ctas_per_sm;     // resident CTAs per SM (forward footprint)
   int bwd_ctas_per_sm;
@@ -136,11 +105,10 @@ cudaError_t launch_fwd_plane(const RoiAlignArgs& a, const PlanePlan& plan, const
                              const float* data, float* out, int accumulate, int num_sms,
                              cudaStream_t stream);
 // Owner-computes backward: every dX element is produced by exactly one thread and written
-// once (zero-fill fused).  canonical = 1: contributions are added one by one in the order of
-// the single-thread reference (bit-exact); 0: contributions of a ROI to a pixel are summed
-// first (fewer operations, still reproducible run to run).
+// once (zero-fill fused); contributions are added one by one in the order of the single-thread
+// reference (bit-exact): the deterministic mode.
 cudaError_t launch_bwd_plane(const RoiAlignArgs& a, const PlanePlan& plan, const RoiTables& t,
-                             const float* dy, float* dx, int accumulate, int canonical, int num_sms,
+                             const float* dy, float* dx, int accumulate, int num_sms,
                              cudaStream_t stream);
 
 // ---- resident family (roialign_resident.cu): fixed sampling ratio, padded plane resident in

@@ -5,9 +5,10 @@
 // engine (cp.async.bulk + mbarrier transaction count), every tap of every ROI of that image
 // is then a shared-memory access, and HBM sees the algorithmic traffic only:
 //   forward : each plane read once, each output written once
-//   backward: each dy element read once, each dX element WRITTEN once (the zero-fill of
-//             ROIAlign.py:33-34 is fused: the plane is accumulated in shared memory, no
-//             global atomics, no read-modify-write of dX)
+//   backward: each dX element WRITTEN once (the zero-fill of ROIAlign.py:33-34 is fused: the
+//             plane is accumulated in shared memory, no global atomics, no read-modify-write of
+//             dX), contributions added in the reference's single-thread order (deterministic
+//             mode; the fast non-deterministic backward lives in roialign_resident.cu)
 // ROI decoding comes from the tables of roialign_tables.cu (shared by all C planes).
 //
 // Arithmetic and its order are the reference's (ROIAlign.cpp:56-74, 126-158 and
@@ -382,21 +383,12 @@ struct CellRegs {
 };
 
 __device__ __forceinline__ CellRegs load_cell(const AxisCell* __restrict__ c) {
-  const int4 b = __ldg(reinterpret_cast<const int4*>(c) + 1);   // h1p, h1w, hit_first, p_first
-  const int4 k = __ldg(reinterpret_cast<const int4*>(c) + 2);   // k_first, k_last
+  const int4 v = __ldg(reinterpret_cast<const int4*>(c));   // pix, p_first, k_first, k_last
   CellRegs r;
-  r.pix = __ldg(&c->pix);
-  r.k_first = k.x;
-  r.k_last = k.y;
-  r.p_first = b.w;
-  return r;
-}
-
-__device__ __forceinline__ AxisHit load_hit(const AxisHit* __restrict__ h) {
-  const int2 v = __ldg(reinterpret_cast<const int2*>(h));
-  AxisHit r;
-  r.p = v.x;
-  r.w = __int_as_float(v.y);
+  r.pix = v.x;
+  r.p_first = v.y;
+  r.k_first = v.z;
+  r.k_last = v.w;
   return r;
 }
 
@@ -585,179 +577,6 @@ roialign_bwd_plane_canonical_kernel(const float* __restrict__ dy, float* __restr
   if (use_bulk && tid < 32) ptx::bulk_wait_all();
 }
 
-// Everything a warp needs for one (roi, band) pair, held in registers so that the loads of
-// pair i+1 are in flight while pair i is computed.
-template <int GR>
-struct PairRegs {
-  int nrows, nxcell;
-  const AxisCell* xcells;
-  float g[GR > 0 ? GR : 1];   // lane's share of the dy tile
-  int4 ya, yb;                // row cell `lane` of the band: chunks A and B
-  int4 xa, xb;                // column cell `lane`: chunks A and B
-};
-
-template <int GR>
-__device__ __forceinline__ void issue_pair_loads(PairRegs<GR>& r, const int4 p0, const int4 p1,
-                                                 const float* __restrict__ dy, const AxisCell* __restrict__ cells,
-                                                 int channels, int c, int bins, int lane) {
-  // p0 = {roi, nrows, ycell, xcell}, p1 = {nxcell, -, -, -}
-  r.nrows = p0.y;
-  r.nxcell = p1.x;
-  r.xcells = cells + p0.w;
-  const float* dtop = dy + ((size_t)p0.x * channels + c) * bins;
-#pragma unroll
-  for (int i = 0; i < GR; ++i) r.g[i] = (lane + 32 * i < bins) ? __ldg(dtop + lane + 32 * i) : 0.0f;
-  const int yrow = lane < r.nrows ? lane : 0;
-  const int4* yc = reinterpret_cast<const int4*>(cells + p0.z + yrow);
-  r.ya = __ldg(yc);
-  r.yb = __ldg(yc + 1);
-  const int xcol = lane < r.nxcell ? lane : 0;
-  const int4* xc = reinterpret_cast<const int4*>(r.xcells + xcol);
-  r.xa = __ldg(xc);
-  r.xb = __ldg(xc + 1);
-}
-
-// One column cell (this lane) against the rows of the band (held one per lane in ya/yb).
-// `simple` is warp-uniform: no lane has more than two merged column hits.
-__device__ __forceinline__ void fast_rows(float* plane, const float* g, int pooled_w, int nrows, const int4 ya,
-                                          const int4 yb, const AxisHit* __restrict__ hits, bool simple,
-                                          bool active, int col, int nxh, int x0p, float x0w, int x1p,
-                                          float x1w, int xhit_first) {
-  for (int r = 0; r < nrows; ++r) {
-    const int rowpix = __shfl_sync(0xffffffffu, ya.x, r);
-    const int nyh = __shfl_sync(0xffffffffu, ya.y, r);
-    if (simple && nyh <= 2) {        // warp-uniform: the common shape, at most two hits per axis
-      const int y0p = __shfl_sync(0xffffffffu, ya.z, r);
-      const float y0w = __int_as_float(__shfl_sync(0xffffffffu, ya.w, r));
-      const float* g0 = g + y0p * pooled_w;
-      float acc = (y0w * x0w) * g0[x0p];
-      if (nxh > 1) acc = fmaf(y0w * x1w, g0[x1p], acc);
-      if (nyh > 1) {
-        const int y1p = __shfl_sync(0xffffffffu, yb.x, r);
-        const float y1w = __int_as_float(__shfl_sync(0xffffffffu, yb.y, r));
-        const float* g1 = g + y1p * pooled_w;
-        acc = fmaf(y1w * x0w, g1[x0p], acc);
-        if (nxh > 1) acc = fmaf(y1w * x1w, g1[x1p], acc);
-      }
-      if (active) plane[rowpix + col] += acc;
-    } else {
-      // many bins fold onto this pixel (tiny ROIs): walk the full hit lists
-      const int yhit_first = __shfl_sync(0xffffffffu, yb.z, r);
-      if (active) {
-        float acc = 0.0f;
-        for (int a = 0; a < nyh; ++a) {
-          const AxisHit hy = load_hit(hits + yhit_first + a);
-          const float* ga = g + hy.p * pooled_w;
-          for (int b = 0; b < nxh; ++b) {
-            const AxisHit hx = load_hit(hits + xhit_first + b);
-            acc = fmaf(hy.w * hx.w, ga[hx.p], acc);
-          }
-        }
-        plane[rowpix + col] += acc;
-      }
-    }
-  }
-}
-
-// Merged weights, FMA, loads of the next (roi, band) pair prefetched: the default backward.
-// Results are reproducible run to run (fixed ownership, fixed order) but the contributions
-// of a ROI to a pixel are summed before they are added, so they are not bit-identical to
-// the single-thread reference (use the canonical kernel for that).
-template <int GR>
-__global__ void __launch_bounds__(kBwdThreads, 1)
-roialign_bwd_plane_fast_kernel(const float* __restrict__ dy, float* __restrict__ dx,
-                               const AxisCell* __restrict__ cells, const AxisHit* __restrict__ hits,
-                               const BandPair* __restrict__ pairs, const int* __restrict__ pair_count,
-                               const int* __restrict__ img_start, int num_images, int channels, int height,
-                               int width, int pooled_h, int pooled_w, int accumulate, int use_bulk,
-                               int gslot_floats) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t bar;
-  float* plane = reinterpret_cast<float*>(smem_raw);
-  const int pitch = width;                      // dense rows: one row per warp instruction
-  const int plane_elems = height * width;
-  const int bins = pooled_h * pooled_w;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* gslot = plane + (size_t)height * pitch + (size_t)warp * gslot_floats;
-
-  if (tid == 0 && use_bulk) {
-    ptx::mbar_init(&bar, 1);
-    ptx::fence_mbar_init();
-  }
-  __syncthreads();
-  uint32_t parity = 0;
-
-  const int planes = num_images * channels;
-  for (int p = blockIdx.x; p < planes; p += gridDim.x) {
-    const int n = p / channels, c = p - n * channels;
-    const int j0 = __ldg(img_start + n), j1 = __ldg(img_start + n + 1);
-    float* gplane = dx + ((size_t)n * channels + c) * plane_elems;
-    if (j0 == j1) {
-      if (!accumulate)
-        for (int i = tid; i < plane_elems; i += blockDim.x) gplane[i] = 0.0f;
-      continue;
-    }
-    const int npairs = __ldg(pair_count + n * kBands + warp);
-    const int4* plist = reinterpret_cast<const int4*>(pairs + (size_t)kBands * j0 + (size_t)warp * (j1 - j0));
-    // the first pair's loads overlap the plane initialisation
-    PairRegs<GR> cur, nxt;
-    int4 q0 = make_int4(0, 0, 0, 0), q1 = q0;       // pair record after next
-    if (npairs > 0) issue_pair_loads<GR>(cur, __ldg(plist), __ldg(plist + 1), dy, cells, channels, c, bins, lane);
-    if (npairs > 1) {
-      q0 = __ldg(plist + 2);
-      q1 = __ldg(plist + 3);
-    }
-
-    __syncthreads();   // the previous plane has left shared memory
-    if (accumulate) {
-      load_plane(plane, gplane, height, width, pitch, &bar, parity, use_bulk);
-    } else {
-      float4* p4 = reinterpret_cast<float4*>(plane);
-      const int n4 = (height * pitch) >> 2;
-      for (int i = tid; i < n4; i += blockDim.x) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i = (n4 << 2) + tid; i < height * pitch; i += blockDim.x) plane[i] = 0.0f;
-      __syncthreads();
-    }
-
-    for (int i = 0; i < npairs; ++i) {
-      if (i + 1 < npairs) {
-        issue_pair_loads<GR>(nxt, q0, q1, dy, cells, channels, c, bins, lane);
-        if (i + 2 < npairs) {
-          q0 = __ldg(plist + 2 * (i + 2));
-          q1 = __ldg(plist + 2 * (i + 2) + 1);
-        }
-      }
-      // dy tile of the current pair -> this warp's slot
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < GR; ++k)
-        if (lane + 32 * k < bins) gslot[lane + 32 * k] = cur.g[k];
-      __syncwarp();
-
-      {
-        const bool active = lane < cur.nxcell;
-        const bool simple = __all_sync(0xffffffffu, !active || cur.xa.y <= 2);
-        fast_rows(plane, gslot, pooled_w, cur.nrows, cur.ya, cur.yb, hits, simple, active, cur.xa.x, cur.xa.y,
-                  cur.xa.z, __int_as_float(cur.xa.w), cur.xb.x, __int_as_float(cur.xb.y), cur.xb.z);
-      }
-      for (int xs = 32; xs < cur.nxcell; xs += 32) {      // more than 32 touched columns
-        const bool active = xs + lane < cur.nxcell;
-        const int4* xc = reinterpret_cast<const int4*>(cur.xcells + (active ? xs + lane : 0));
-        const int4 xa = __ldg(xc), xb = __ldg(xc + 1);
-        const bool simple = __all_sync(0xffffffffu, !active || xa.y <= 2);
-        fast_rows(plane, gslot, pooled_w, cur.nrows, cur.ya, cur.yb, hits, simple, active, xa.x, xa.y, xa.z,
-                  __int_as_float(xa.w), xb.x, __int_as_float(xb.y), xb.z);
-      }
-      __syncwarp();   // the next ROI may hand a pixel to another lane
-      cur = nxt;
-    }
-    if (use_bulk) ptx::fence_proxy_async();   // my shared-memory writes -> visible to the copy engine
-    __syncthreads();
-    store_plane(gplane, plane, height, width, pitch, use_bulk);
-  }
-  if (use_bulk && tid < 32) ptx::bulk_wait_all();
-}
-
 template <typename K>
 cudaError_t set_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -797,8 +616,6 @@ bool plane_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_opti
   const int bins = a.pooled_h * a.pooled_w;
   const size_t gslot = (size_t)((bins + 31) / 32 * 32);
   plan->gslot_floats = dense + gslot * sizeof(float) * kBands <= budget ? (int)gslot : 0;
-  // the fast kernel keeps the lane's share of a dy tile in at most 7 registers
-  plan->fast_bwd = (plan->gslot_floats > 0 && bins <= 7 * 32 && a.height <= 32 * kBands) ? 1 : 0;
   plan->use_bulk = (a.width % 4 == 0) && ((uintptr_t)plane_ptr % 16 == 0) ? 1 : 0;
   plan->ctas_per_sm = ctas_per_sm(plan->plane_bytes, kRegularThreads, smem_optin);
   plan->bwd_ctas_per_sm =
@@ -850,33 +667,19 @@ cudaError_t launch_fwd_plane(const RoiAlignArgs& a, const PlanePlan& plan, const
 }
 
 cudaError_t launch_bwd_plane(const RoiAlignArgs& a, const PlanePlan& plan, const RoiTables& t,
-                             const float* dy, float* dx, int accumulate, int canonical, int num_sms,
+                             const float* dy, float* dx, int accumulate, int num_sms,
                              cudaStream_t stream) {
   const long long planes = (long long)a.num_images * a.channels;
   if (planes == 0) return cudaSuccess;
   long long grid = (long long)num_sms * plan.bwd_ctas_per_sm;
   if (grid > planes) grid = planes;
   const size_t smem = plan.bwd_plane_bytes + (size_t)plan.gslot_floats * sizeof(float) * kBands;
-  if (canonical) {
-    cudaError_t e = set_smem(roialign_bwd_plane_canonical_kernel, smem);
-    if (e != cudaSuccess) return e;
-    roialign_bwd_plane_canonical_kernel<<<(unsigned)grid, kBwdThreads, smem, stream>>>(
-        dy, dx, a.rois, t.recs, t.axis, t.cells, t.img_start, a.num_images, a.channels, a.height, a.width,
-        plan.bwd_pitch, a.pooled_h, a.pooled_w, a.scale, a.sampling_ratio, accumulate, plan.use_bulk,
-        plan.gslot_floats);
-  } else {
-    const int bins = a.pooled_h * a.pooled_w;
-#define MOBULA_BWD_FAST(GR)                                                                         \
-  do {                                                                                              \
-    cudaError_t e = set_smem(roialign_bwd_plane_fast_kernel<GR>, smem);                             \
-    if (e != cudaSuccess) return e;                                                                 \
-    roialign_bwd_plane_fast_kernel<GR><<<(unsigned)grid, kBwdThreads, smem, stream>>>(              \
-        dy, dx, t.cells, t.hits, t.pairs, t.pair_count, t.img_start, a.num_images, a.channels,      \
-        a.height, a.width, a.pooled_h, a.pooled_w, accumulate, plan.use_bulk, plan.gslot_floats);   \
-  } while (0)
-    if (bins <= 64) MOBULA_BWD_FAST(2); else MOBULA_BWD_FAST(7);
-#undef MOBULA_BWD_FAST
-  }
+  cudaError_t e = set_smem(roialign_bwd_plane_canonical_kernel, smem);
+  if (e != cudaSuccess) return e;
+  roialign_bwd_plane_canonical_kernel<<<(unsigned)grid, kBwdThreads, smem, stream>>>(
+      dy, dx, a.rois, t.recs, t.axis, t.cells, t.img_start, a.num_images, a.channels, a.height, a.width,
+      plan.bwd_pitch, a.pooled_h, a.pooled_w, a.scale, a.sampling_ratio, accumulate, plan.use_bulk,
+      plan.gslot_floats);
   count_launch();
   return cudaGetLastError();
 }

@@ -6,10 +6,7 @@
 //                          image = the canonical accumulation order of the backward)
 //   2. roi_records_kernel  per-ROI geometry + arena offsets (exclusive scan)
 //   3. roi_fill_kernel     per-axis sample tables and, for the backward, the inverse map
-//                          row/column -> contiguous range of samples touching it (plus the
-//                          per-pooled-index merged weights of the fast backward)
-//   4. roi_pairs_kernel    (fast backward) per image and row band, the ordered list of ROIs
-//                          with touched rows in the band
+//                          row/column -> contiguous range of samples touching it
 // All arithmetic goes through roialign_common.cuh, i.e. rounds like the reference.
 #include "roialign_kernels.h"
 #include "roialign_common.cuh"
@@ -120,8 +117,7 @@ roi_records_kernel(const float* __restrict__ rois, int num_rois, int num_images,
 __global__ void __launch_bounds__(128)
 roi_fill_kernel(const float* __restrict__ rois, int num_rois, int height, int width, int pitch,
                 int pooled_h, int pooled_w, float scale, int sampling_ratio, RoiRec* __restrict__ recs,
-                AxisEntry* __restrict__ axis, AxisCell* __restrict__ cells, AxisHit* __restrict__ hits,
-                unsigned need) {
+                AxisEntry* __restrict__ axis, AxisCell* __restrict__ cells, unsigned need) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = t >> 1, ax = t & 1;        // ax 0: y (rows), 1: x (columns)
   if (j >= num_rois) return;
@@ -165,10 +161,6 @@ roi_fill_kernel(const float* __restrict__ rois, int num_rois, int height, int wi
           cell.pix = pix;
           cell.k_first = cell.k_last = k;
           cell.p_first = p;
-          cell.hit_first = cell.nhits = 0;
-          cell.h0p = cell.h1p = 0;
-          cell.h0w = cell.h1w = 0.0f;
-          cell.pad0 = cell.pad1 = 0;
           c[ncell++] = cell;
           pix_min = min(pix_min, pix);
           pix_max = max(pix_max, pix);
@@ -178,49 +170,6 @@ roi_fill_kernel(const float* __restrict__ rois, int num_rois, int height, int wi
     if (++i == grid) {
       i = 0;
       ++p;
-    }
-  }
-  if (need & kNeedFast) {
-    // merged weights: for every touched pixel, one hit per pooled index
-    const float inv_count = ax ? 1.0f : __fdiv_rn(1.0f, g.count);
-    int nh = cell_base;                      // hits of this axis start at the cell base
-    for (int q = 0; q < ncell; ++q) {
-      AxisCell cell = c[q];
-      cell.hit_first = nh;
-      int cur_p = -1;
-      float w = 0.0f;
-      for (int k = cell.k_first; k <= cell.k_last; ++k) {
-        const AxisEntry en = e[k];
-        float wk = 0.0f;
-        if (en.lo == cell.pix) wk += en.w_lo;
-        if (en.hi == cell.pix) wk += en.w_hi;
-        const int pk = k / grid;
-        if (pk != cur_p) {
-          if (cur_p >= 0 && w != 0.0f) {
-            hits[nh].p = cur_p;
-            hits[nh].w = w * inv_count;
-            ++nh;
-          }
-          cur_p = pk;
-          w = 0.0f;
-        }
-        w += wk;
-      }
-      if (cur_p >= 0 && w != 0.0f) {
-        hits[nh].p = cur_p;
-        hits[nh].w = w * inv_count;
-        ++nh;
-      }
-      cell.nhits = nh - cell.hit_first;
-      if (cell.nhits > 0) {
-        cell.h0p = hits[cell.hit_first].p;
-        cell.h0w = hits[cell.hit_first].w;
-      }
-      if (cell.nhits > 1) {
-        cell.h1p = hits[cell.hit_first + 1].p;
-        cell.h1w = hits[cell.hit_first + 1].w;
-      }
-      c[q] = cell;
     }
   }
   if (need) {
@@ -236,50 +185,6 @@ roi_fill_kernel(const float* __restrict__ rois, int num_rois, int height, int wi
       rec->y_last = last;
     }
   }
-}
-
-// One warp per (image, band): the ordered list of ROIs with cells in the band.
-__global__ void __launch_bounds__(128)
-roi_pairs_kernel(const RoiRec* __restrict__ recs, const AxisCell* __restrict__ cells,
-                 const int* __restrict__ img_start, int num_images, int height, int pitch,
-                 BandPair* __restrict__ pairs, int* __restrict__ pair_count) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= num_images * kBands) return;
-  const int n = w / kBands, b = w - n * kBands;
-  const int j0 = img_start[n], j1 = img_start[n + 1];
-  const int row0 = (int)(((long long)b * height) / kBands);
-  const int row1 = (int)(((long long)(b + 1) * height) / kBands);
-  const int pix0 = row0 * pitch, pix1 = row1 * pitch;
-  BandPair* out = pairs + (size_t)kBands * j0 + (size_t)b * (j1 - j0);
-  int count = 0;
-  for (int jb = j0; jb < j1; jb += 32) {
-    const int j = jb + lane;
-    BandPair pr;
-    pr.roi = 0;
-    pr.nrows = 0;
-    pr.ycell = pr.xcell = pr.nxcell = 0;
-    pr.pad0 = pr.pad1 = pr.pad2 = 0;
-    if (j < j1 && row1 > row0) {
-      const RoiRec r = recs[j];
-      if (r.yoff >= 0 && r.y_first < row1 && r.y_last >= row0 && r.nxcell > 0) {
-        const AxisCell* c = cells + r.ycell;
-        int a = 0;
-        while (a < r.nycell && c[a].pix < pix0) ++a;
-        int z = a;
-        while (z < r.nycell && c[z].pix < pix1) ++z;
-        pr.roi = r.roi;
-        pr.nrows = z - a;
-        pr.ycell = r.ycell + a;
-        pr.xcell = r.xcell;
-        pr.nxcell = r.nxcell;
-      }
-    }
-    const bool keep = pr.nrows > 0;
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (keep) out[count + __popc(m & ((1u << lane) - 1u))] = pr;
-    count += __popc(m);
-  }
-  if (lane == 0) pair_count[w] = count;
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -299,7 +204,7 @@ long long arena_entries(const RoiAlignArgs& a) {
 }
 
 struct Layout {
-  size_t img_start, order, recs, axis, cells, hits, pairs, pair_count, total;
+  size_t img_start, order, recs, axis, cells, total;
 };
 
 Layout layout_of(const RoiAlignArgs& a, unsigned need) {
@@ -312,9 +217,6 @@ Layout layout_of(const RoiAlignArgs& a, unsigned need) {
   l.recs = p;       p += align_up(R * sizeof(RoiRec), 256);
   l.axis = p;       p += align_up(arena * sizeof(AxisEntry), 256);
   l.cells = p;      p += need ? align_up(2 * arena * sizeof(AxisCell), 256) : 0;
-  l.hits = p;       p += (need & kNeedFast) ? align_up(2 * arena * sizeof(AxisHit), 256) : 0;
-  l.pairs = p;      p += (need & kNeedFast) ? align_up(R * kBands * sizeof(BandPair), 256) : 0;
-  l.pair_count = p; p += (need & kNeedFast) ? align_up(N * kBands * sizeof(int), 256) : 0;
   l.total = p;
   return l;
 }
@@ -334,9 +236,6 @@ RoiTables roi_tables_carve(const RoiAlignArgs& a, unsigned need, int pitch, void
   t.recs = (RoiRec*)(p + l.recs);
   t.axis = (AxisEntry*)(p + l.axis);
   t.cells = (AxisCell*)(p + l.cells);
-  t.hits = (AxisHit*)(p + l.hits);
-  t.pairs = (BandPair*)(p + l.pairs);
-  t.pair_count = (int*)(p + l.pair_count);
   t.arena = arena_entries(a);
   t.pitch = pitch;
   t.regular = (a.sampling_ratio > 0 && t_arena_override < 0) ? 1 : 0;
@@ -355,10 +254,7 @@ cudaError_t launch_roi_tables(const RoiAlignArgs& a, const RoiTables& t, unsigne
                               cudaStream_t stream) {
   if (a.num_rois == 0) {
     // every segment is empty
-    cudaError_t e = cudaMemsetAsync(t.img_start, 0, (size_t)(a.num_images + 2) * sizeof(int), stream);
-    if (e == cudaSuccess && (need & kNeedFast) && a.num_images > 0)
-      e = cudaMemsetAsync(t.pair_count, 0, (size_t)a.num_images * kBands * sizeof(int), stream);
-    return e;
+    return cudaMemsetAsync(t.img_start, 0, (size_t)(a.num_images + 2) * sizeof(int), stream);
   }
   roi_group_kernel<<<a.num_images + 1, kGroupThreads, 0, stream>>>(a.rois, a.num_rois, a.num_images,
                                                                    t.img_start, t.order);
@@ -370,14 +266,8 @@ cudaError_t launch_roi_tables(const RoiAlignArgs& a, const RoiTables& t, unsigne
   const int threads = 2 * a.num_rois;
   roi_fill_kernel<<<(threads + 127) / 128, 128, 0, stream>>>(
       a.rois, a.num_rois, a.height, a.width, t.pitch, a.pooled_h, a.pooled_w, a.scale,
-      a.sampling_ratio, t.recs, t.axis, t.cells, t.hits, need);
+      a.sampling_ratio, t.recs, t.axis, t.cells, need);
   count_launch();
-  if ((need & kNeedFast) && a.num_images > 0) {
-    const int warps = a.num_images * kBands;
-    roi_pairs_kernel<<<(warps * 32 + 127) / 128, 128, 0, stream>>>(
-        t.recs, t.cells, t.img_start, a.num_images, a.height, t.pitch, t.pairs, t.pair_count);
-    count_launch();
-  }
   return cudaGetLastError();
 }
 

@@ -121,6 +121,7 @@ struct ResidentPlan {
   int pitch;           // floats between rows of the padded plane in shared memory
   int per_roi;         // sample entries per ROI: (PH + PW) * grid
   int fwd_two;         // the sampling_ratio == 2 forward (lane = sample column) applies
+  int fwd_pair;        // ... on a channel pair (two padded planes fit shared memory)
   int ypairs, xslots;  // its table: row records (pairs) and column records per ROI
   size_t plane_bytes;  // (H + 1) * pitch * 4
   size_t fwd_smem;

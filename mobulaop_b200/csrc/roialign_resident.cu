@@ -91,8 +91,9 @@ resident_fwd_table_kernel(const float* __restrict__ rois, const int* __restrict_
 __global__ void __launch_bounds__(256)
 resident_fwd2_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
                            const int* __restrict__ img_start, int num_images, int height, int width,
-                           int pitch, int pooled_h, int pooled_w, float scale, int ypairs, int xslots,
-                           uint2* __restrict__ entries) {
+                           int pitch, int unit, int pooled_h, int pooled_w, float scale, int ypairs,
+                           int xslots, uint2* __restrict__ entries) {
+  // `unit` = bytes per pixel of the shared-memory plane: 4, or 8 for a channel pair
   const int per_roi = 2 * ypairs + xslots;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int valid = __ldg(img_start + num_images);
@@ -102,14 +103,14 @@ resident_fwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   const RoiGeom g = roi_decode(rois + (size_t)roi * 5, scale, pooled_h, pooled_w, 2);
   AxisSample s;
   if (k < 2 * ypairs) {
-    s.lo_off = (unsigned)((height + 1) * pitch * 4);
+    s.lo_off = (unsigned)((height + 1) * pitch * unit);
     s.l = 0.0f;
-    if (k < 2 * pooled_h) s = make_sample(g.start_h, k >> 1, g.bin_h, k & 1, 2, height, pitch * 4);
+    if (k < 2 * pooled_h) s = make_sample(g.start_h, k >> 1, g.bin_h, k & 1, 2, height, pitch * unit);
   } else {
     const int kk = k - 2 * ypairs;
-    s.lo_off = (unsigned)((width + 1) * 4);
+    s.lo_off = (unsigned)((width + 1) * unit);
     s.l = 0.0f;
-    if (kk < 2 * pooled_w) s = make_sample(g.start_w, kk >> 1, g.bin_w, kk & 1, 2, width, 4);
+    if (kk < 2 * pooled_w) s = make_sample(g.start_w, kk >> 1, g.bin_w, kk & 1, 2, width, unit);
   }
   entries[t] = make_uint2(s.lo_off, __float_as_uint(s.l));
 }
@@ -496,6 +497,167 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
             float* o = optr + (2 * it) * pooled_w + 8 * ch;
             if (ACC) *o = __fadd_rn(*o, y);
             else *o = y;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- the same forward over a channel PAIR (planes small enough that two padded planes fit) ----
+// The plane holds two channels interleaved (float2 per pixel): every tap is one 8-byte load that
+// serves both channels, a half-warp's load touches ONE feature-map row (8-byte accesses are
+// served per half-warp), and the weights, addresses and table look-ups are shared by the pair.
+__device__ __forceinline__ float2 lds2_at(unsigned addr, unsigned epoch) {
+  float2 v;
+  asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "r"(epoch));
+  return v;
+}
+__device__ __forceinline__ float2 lds2_at8(unsigned addr, unsigned epoch) {
+  float2 v;
+  asm("ld.shared.v2.f32 {%0, %1}, [%2+8];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "r"(epoch));
+  return v;
+}
+
+// two dense planes (the second may be absent) -> one padded float2 plane in shared memory
+__device__ __forceinline__ void load_padded_pair(float2* plane, const float* __restrict__ src0,
+                                                 const float* __restrict__ src1, int height, int width,
+                                                 int pitch) {
+  if ((width & 3) == 0 && (((uintptr_t)src0 | (uintptr_t)src1) & 15u) == 0) {
+    const int w4 = width >> 2, total = height * w4;
+    int r = threadIdx.x / w4, c4 = threadIdx.x - r * w4;
+    const int dr = blockDim.x / w4, dc = blockDim.x - dr * w4;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src0) + i);
+      const float4 b = src1 ? __ldg(reinterpret_cast<const float4*>(src1) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4* dst = reinterpret_cast<float4*>(plane + (size_t)r * pitch + 4 * c4);
+      dst[0] = make_float4(a.x, b.x, a.y, b.y);
+      dst[1] = make_float4(a.z, b.z, a.w, b.w);
+      r += dr;
+      c4 += dc;
+      if (c4 >= w4) {
+        c4 -= w4;
+        ++r;
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < height * width; i += blockDim.x) {
+      const int r = i / width;
+      plane[r * pitch + (i - r * width)] = make_float2(__ldg(src0 + i), src1 ? __ldg(src1 + i) : 0.0f);
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < height; r += blockDim.x) plane[r * pitch + width] = plane[r * pitch + width - 1];
+  __syncthreads();
+  for (int x = threadIdx.x; x <= width; x += blockDim.x)
+    plane[height * pitch + x] = plane[(height - 1) * pitch + x];
+  __syncthreads();
+}
+
+template <int ITERS, int NCH, bool ACC>
+__global__ void __launch_bounds__(kFwd2Threads, 1)
+resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
+                      const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
+                      int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* plane = reinterpret_cast<float2*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bins = pooled_h * pooled_w;
+  constexpr int kPerRoi = 4 * ITERS + 16 * NCH;       // uint2 records
+  const size_t plane_elems = (size_t)height * width;
+  const int h = lane >> 4, q = lane & 15;
+  const unsigned sbase = ptx::smem_addr(smem_raw);
+  const unsigned row_bytes = (unsigned)pitch * 8u;
+  const int cpairs = (c_count + 1) >> 1;
+
+  // the same padding as zero_padding(), on a plane of 2 * pitch floats per row
+  zero_padding(reinterpret_cast<float*>(smem_raw), height, 2 * width + 1, 2 * pitch);
+  __syncthreads();
+  if (!ACC)
+    zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
+                              (long long)c_count * bins);
+
+  bool stores[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) stores[ch] = (q & 1) == 0 && 8 * ch + (q >> 1) < pooled_w;
+
+  long long u, u1;
+  cta_share((long long)cpairs * __ldg(img_start + num_images), u, u1);
+  int n = 0;
+  unsigned epoch = 0;
+  while (u < u1) {
+    const PlaneWork w = next_plane(img_start, cpairs, u, u1, n);      // w.c: channel pair
+    const int c = 2 * w.c;
+    const bool two = c + 1 < c_count;
+    __syncthreads();   // every warp is done reading the previous plane
+    const float* src0 = data + ((size_t)w.n * channels + c) * plane_elems;
+    load_padded_pair(plane, src0, two ? src0 + plane_elems : nullptr, height, width, pitch);
+    ++epoch;
+
+    int jj = w.jj0 + warp;
+    Roi2Regs<ITERS, NCH> nxt;
+    if (jj < w.jj1)
+      load_roi2(nxt, entries + (size_t)(w.j0 + jj) * kPerRoi, order + w.j0 + jj, h, q, pooled_h - 1,
+                2 * pooled_w - 1);
+    for (; jj < w.jj1; jj += kFwd2Warps) {
+      const Roi2Regs<ITERS, NCH> cur = nxt;
+      if (jj + kFwd2Warps < w.jj1)
+        load_roi2(nxt, entries + (size_t)(w.j0 + jj + kFwd2Warps) * kPerRoi, order + w.j0 + jj + kFwd2Warps, h, q,
+                  pooled_h - 1, 2 * pooled_w - 1);
+
+      unsigned xa[NCH], xb[NCH];      // shared-memory address of the low column in row 0 / row 1
+      float lx[NCH], hx[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        xa[ch] = sbase + cur.x[ch].x;
+        xb[ch] = xa[ch] + row_bytes;
+        lx[ch] = __uint_as_float(cur.x[ch].y);
+        hx[ch] = __fsub_rn(1.0f, lx[ch]);
+      }
+      float* optr = out + ((size_t)cur.roi * channels + c) * bins + h * pooled_w + (q >> 1);
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const uint4 ey = cur.y[it];
+        const float ly0 = __uint_as_float(ey.y), ly1 = __uint_as_float(ey.w);
+        const float hy0 = __fsub_rn(1.0f, ly0), hy1 = __fsub_rn(1.0f, ly1);
+        const bool row_ok = 2 * it + h < pooled_h;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          // one bilinear sample of both channels (.x / .y); products packed over the pair, sums
+          // scalar (see resident_fwd2_kernel), order as in bilinear.h:50-56
+          auto sample = [&](unsigned row, float hy, float ly) {
+            const unsigned a = xa[ch] + row, b = xb[ch] + row;
+            const float2 v1 = lds2_at(a, epoch), v2 = lds2_at8(a, epoch);
+            const float2 v3 = lds2_at(b, epoch), v4 = lds2_at8(b, epoch);
+            const float w1 = __fmul_rn(hy, hx[ch]), w2 = __fmul_rn(hy, lx[ch]);
+            const float w3 = __fmul_rn(ly, hx[ch]), w4 = __fmul_rn(ly, lx[ch]);
+            const float2 p1 = __fmul2_rn(make_float2(w1, w1), v1), p2 = __fmul2_rn(make_float2(w2, w2), v2);
+            const float2 p3 = __fmul2_rn(make_float2(w3, w3), v3), p4 = __fmul2_rn(make_float2(w4, w4), v4);
+            float2 s;
+            s.x = __fadd_rn(__fadd_rn(__fadd_rn(p1.x, p2.x), p3.x), p4.x);
+            s.y = __fadd_rn(__fadd_rn(__fadd_rn(p1.y, p2.y), p3.y), p4.y);
+            return s;
+          };
+          const float2 s0 = sample(ey.x, hy0, ly0), s1 = sample(ey.z, hy1, ly1);
+          float2 t;
+          t.x = __fadd_rn(0.0f, s0.x);
+          t.y = __fadd_rn(0.0f, s0.y);
+          t.x = __fadd_rn(t.x, __shfl_down_sync(0xffffffffu, s0.x, 1));
+          t.y = __fadd_rn(t.y, __shfl_down_sync(0xffffffffu, s0.y, 1));
+          t.x = __fadd_rn(t.x, s1.x);
+          t.y = __fadd_rn(t.y, s1.y);
+          t.x = __fadd_rn(t.x, __shfl_down_sync(0xffffffffu, s1.x, 1));
+          t.y = __fadd_rn(t.y, __shfl_down_sync(0xffffffffu, s1.y, 1));
+          if (stores[ch] && row_ok) {
+            float* o = optr + (2 * it) * pooled_w + 8 * ch;
+            const float y0 = __fmul_rn(t.x, 0.25f), y1 = __fmul_rn(t.y, 0.25f);     // count = 4: exact
+            if (ACC) {
+              o[0] = __fadd_rn(o[0], y0);
+              if (two) o[bins] = __fadd_rn(o[bins], y1);
+            } else {
+              o[0] = y0;
+              if (two) o[bins] = y1;
+            }
           }
         }
       }
@@ -1069,10 +1231,12 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
   plan->pitch = pitch;
   plan->per_roi = per_roi;
   plan->fwd_two = two ? 1 : 0;
+  // channel-pair variant of the sampling_ratio == 2 forward: two padded planes must fit
+  plan->fwd_pair = (two && 2 * plane_bytes + 64 <= (size_t)smem_optin) ? 1 : 0;
   plan->ypairs = 2 * ((a.pooled_h + 1) / 2);
   plan->xslots = 16 * ((2 * a.pooled_w + 15) / 16);
   plan->plane_bytes = plane_bytes;
-  plan->fwd_smem = fwd_smem;
+  plan->fwd_smem = plan->fwd_pair ? 2 * plane_bytes : fwd_smem;
   plan->use_bulk = (a.width % 4 == 0) && ((uintptr_t)plane_ptr % 16 == 0) ? 1 : 0;
   // backward: sampling_ratio 2, the dy tile of a (roi, channel) in a 256-float slot; the plane
   // is cut into as few slabs of rows as let two CTAs share an SM
@@ -1131,11 +1295,20 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     uint2* entries = (uint2*)(base + l.entries);
     const long long threads = (long long)a.num_rois * (2 * plan.ypairs + plan.xslots);
     resident_fwd2_table_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
-        a.rois, order, img_start, a.num_images, a.height, a.width, plan.pitch, a.pooled_h, a.pooled_w,
-        a.scale, plan.ypairs, plan.xslots, entries);
+        a.rois, order, img_start, a.num_images, a.height, a.width, plan.pitch, plan.fwd_pair ? 8 : 4,
+        a.pooled_h, a.pooled_w, a.scale, plan.ypairs, plan.xslots, entries);
     count_launch();
 #define MOBULA_FWD2(ITERS, NCH, ACC)                                                                 \
   do {                                                                                               \
+    if (plan.fwd_pair) {                                                                             \
+      e = resident_grid(resident_fwd2p_kernel<ITERS, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms, \
+                        (work + 1) / 2, &grid);                                                      \
+      if (e != cudaSuccess) return e;                                                                \
+      resident_fwd2p_kernel<ITERS, NCH, ACC><<<grid, kFwd2Threads, plan.fwd_smem, stream>>>(         \
+          data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,     \
+          plan.pitch, a.pooled_h, a.pooled_w);                                                       \
+      break;                                                                                         \
+    }                                                                                                \
     e = resident_grid(resident_fwd2_kernel<ITERS, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms,   \
                       work, &grid);                                                                  \
     if (e != cudaSuccess) return e;                                                                  \

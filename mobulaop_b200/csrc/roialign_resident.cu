@@ -1258,7 +1258,7 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
     if (per_warp > slot + row_bytes && a.num_rois <= (1 << 20)) {
       int rows = (int)((per_warp - slot) / row_bytes);
       if (rows > a.height) rows = a.height;
-      plan->bwd_ok = 1;
+      plan->bwd_ok = (a.height + rows - 1) / rows <= 4096 ? 1 : 0;   // band index: 12 bits of the sort key
       plan->bwd_slabs = (a.height + rows - 1) / rows;
       plan->bwd_slab_rows = rows;
       plan->bwd_smem = (size_t)kBwdWarps * (rows * row_bytes + slot);

@@ -244,6 +244,25 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
   const bool deterministic = mode == MOBULA_ROIALIGN_BWD_DETERMINISTIC;
   if (deterministic && algo == MOBULA_ROIALIGN_ALGO_GATHER)
     return fail(MOBULA_ERR_UNSUPPORTED, "the gather backward uses global atomics: not deterministic");
+  {
+    // resident kernels: fast (merged weights) or deterministic (canonical order) variant
+    ResidentPlan rplan;
+    const bool resident_ok = !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && a.num_images >= 0 &&
+                             resident_supported(a, dx, st.smem_optin, &rplan) && rplan.bwd_ok;
+    if (algo == MOBULA_ROIALIGN_ALGO_RESIDENT && !resident_ok)
+      return fail(MOBULA_ERR_UNSUPPORTED,
+                  "resident backward needs num_images in [0, 4096], sampling_ratio 2, pooled_w <= 16 and "
+                  "a %dx%d fp32 plane slab within %d bytes of shared memory", a.height, a.width,
+                  st.smem_optin);
+    if (resident_ok && (algo == MOBULA_ROIALIGN_ALGO_RESIDENT || algo == MOBULA_ROIALIGN_ALGO_AUTO)) {
+      t_algo[1] = deterministic ? "resident-canonical" : "resident";
+      void* ws = nullptr;
+      int rc = prepare_workspace(st, resident_bwd_workspace(a, rplan, deterministic), stream, &ws);
+      if (rc) return rc;
+      CUDA_TRY(launch_bwd_resident(a, rplan, ws, dy, dx, accumulate, deterministic, st.num_sms, stream));
+      return release_tables(st, stream);
+    }
+  }
   if (deterministic || algo == MOBULA_ROIALIGN_ALGO_PLANE) {
     PlanePlan plan;
     if (!plane_supported(a, dx, st.smem_optin, &plan))
@@ -258,24 +277,6 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
     if (rc) return rc;
     CUDA_TRY(launch_bwd_plane(a, plan, tables, dy, dx, accumulate, st.num_sms, stream));
     return release_tables(st, stream);
-  }
-  {
-    ResidentPlan rplan;
-    const bool resident_ok = !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && a.num_images >= 0 &&
-                             resident_supported(a, dx, st.smem_optin, &rplan) && rplan.bwd_ok;
-    if (algo == MOBULA_ROIALIGN_ALGO_RESIDENT && !resident_ok)
-      return fail(MOBULA_ERR_UNSUPPORTED,
-                  "resident backward needs num_images in [0, 4096], sampling_ratio 2, pooled_w <= 16 and "
-                  "a %dx%d fp32 plane slab within %d bytes of shared memory", a.height, a.width,
-                  st.smem_optin);
-    if (resident_ok && (algo == MOBULA_ROIALIGN_ALGO_RESIDENT || algo == MOBULA_ROIALIGN_ALGO_AUTO)) {
-      t_algo[1] = "resident";
-      void* ws = nullptr;
-      int rc = prepare_workspace(st, resident_bwd_workspace(a, rplan), stream, &ws);
-      if (rc) return rc;
-      CUDA_TRY(launch_bwd_resident(a, rplan, ws, dy, dx, accumulate, st.num_sms, stream));
-      return release_tables(st, stream);
-    }
   }
   t_algo[1] = "gather";
   if (!accumulate) {
@@ -356,7 +357,8 @@ static bool resident_backward_applies(DeviceState& st, const RoiAlignArgs& a, co
                                       unsigned flags) {
   const unsigned algo = algo_of(flags);
   ResidentPlan plan;
-  return mode == MOBULA_ROIALIGN_BWD_ATOMIC && !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) &&
+  (void)mode;
+  return !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) &&
          (algo == MOBULA_ROIALIGN_ALGO_AUTO || algo == MOBULA_ROIALIGN_ALGO_RESIDENT) &&
          resident_supported(a, dx, st.smem_optin, &plan) && plan.bwd_ok;
 }

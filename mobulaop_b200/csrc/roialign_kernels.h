@@ -136,11 +136,12 @@ size_t resident_fwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan);
 cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan, void* workspace,
                                 const float* data, float* out, int accumulate, int num_sms,
                                 cudaStream_t stream);
-size_t resident_bwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan);
-// dX := scatter (accumulate = 0, zero-fill fused) or dX += scatter; not bit-identical to the
-// reference's single-thread order, reproducible run to run
+size_t resident_bwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan, int deterministic);
+// dX := scatter (accumulate = 0, zero-fill fused) or dX += scatter.  deterministic = 0: merged
+// weights, reproducible run to run, within 1e-5 of the reference; 1: every contribution added
+// separately in the reference's single-thread order, bit-identical dX.
 cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan, void* workspace,
-                                const float* dy, float* dx, int accumulate, int num_sms,
+                                const float* dy, float* dx, int accumulate, int deterministic, int num_sms,
                                 cudaStream_t stream);
 
 }  // namespace mobula_b200

@@ -875,6 +875,180 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   }
 }
 
+// Tables of the DETERMINISTIC backward: the same shape as above, but nothing is merged --
+// every record keeps the individual bilinear taps so that the kernel can add the contributions
+// to a pixel one by one, in the reference's single-thread order (roi, ph, pw, iy, ix, tap):
+//   rows[j][maxe]    uint4: x = row * row_bytes | ph, y = flags (bit iy: sample row iy of bin row
+//                    ph touches this row), z / w = its row weight for iy = 0 / 1
+//   colh[j][maxc]    uint4: x = col_off | nhits << 16, y = index of the third hit in extra[j][],
+//                    z = pwA | flagsA << 8 | pwB << 16 | flagsB << 24 (bit ix: sample column ix
+//                    of bin column pw touches this column)
+//   colw[j][maxc]    uint4: column weights of hit A for ix = 0 / 1, of hit B for ix = 0 / 1
+//   extra[j][maxc]   uint4: x = pw | flags << 8, z / w = weights for ix = 0 / 1
+// A clamped sample (low = high tap, bilinear.h:32-44) keeps only its low tap: the high one has
+// weight 0 and adding +-0 never changes a sum that started at +0.
+__global__ void __launch_bounds__(128)
+resident_bwd2d_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
+                            const int* __restrict__ img_start, int num_images, int num_rois, int height,
+                            int width, int row_bytes, int col_bytes, int pooled_h, int pooled_w, float scale,
+                            int maxe, int maxc, int band_rows, int nbands, uint4* __restrict__ rows_out,
+                            unsigned char* __restrict__ bstart, uint4* __restrict__ colh,
+                            uint4* __restrict__ colw, uint4* __restrict__ extra, int* __restrict__ counter) {
+  __shared__ unsigned s_key[4][64], s_srow[4][64], s_rfl[4][64];
+  __shared__ float s_w0[4][64], s_w1[4][64];
+  __shared__ int s_lo[4][32], s_hi[4][32];
+  __shared__ float s_fl[4][32];
+  // open columns A / B of the merge: per hit (pw, flags, weight ix=0, weight ix=1)
+  __shared__ int s_pw[4][2][kMaxHitsPerCol], s_cf[4][2][kMaxHitsPerCol];
+  __shared__ float s_c0[4][2][kMaxHitsPerCol], s_c1[4][2][kMaxHitsPerCol];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 4 + wib;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
+  const int valid = __ldg(img_start + num_images);
+  if (j >= valid) return;
+  const int roi = __ldg(order + j);
+  const RoiGeom g = roi_decode(rois + (size_t)roi * 5, scale, pooled_h, pooled_w, 2);
+
+  // ---- rows ----
+  int nrow = 0, rrow[4] = {0, 0, 0, 0};
+  unsigned rfl[4] = {0u, 0u, 0u, 0u};
+  float rw0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, rw1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (lane < pooled_h) {
+    auto add = [&](int row, int iy, float w) {
+      int k = 0;
+      while (k < nrow && rrow[k] != row) ++k;
+      if (k == nrow) {
+        rrow[k] = row;
+        ++nrow;
+      }
+      rfl[k] |= 1u << iy;
+      if (iy) rw1[k] = w;
+      else rw0[k] = w;
+    };
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const AxisTap t = axis_decode(sample_pos(g.start_h, lane, g.bin_h, i, 2), height);
+      if (t.valid) {
+        add(t.lo, i, t.wh);
+        if (t.hi != t.lo) add(t.hi, i, t.wl);
+      }
+    }
+  }
+  int incl = nrow;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  int ne = __shfl_sync(0xffffffffu, incl, 31);
+  const int base = incl - nrow;
+
+  // ---- columns ----
+  AxisTap mine;
+  mine.valid = false;
+  mine.lo = mine.hi = 0;
+  mine.wl = mine.wh = 0.0f;
+  if (lane < 2 * pooled_w) mine = axis_decode(sample_pos(g.start_w, lane >> 1, g.bin_w, lane & 1, 2), width);
+  uint4* hrow = colh + (size_t)j * maxc;
+  uint4* wrow = colw + (size_t)j * maxc;
+  uint4* erow = extra + (size_t)j * maxc;
+  int ncols = 0;
+  s_lo[wib][lane] = mine.valid ? mine.lo : -1;
+  s_hi[wib][lane] = mine.hi;
+  s_fl[wib][lane] = mine.wl;
+  __syncwarp();
+  if (lane == 0) {
+    int colA = -1, nA = 0, nB = 0, nextra = 0, A = 0;      // A: which of the two slots is column A
+    auto hit = [&](int slot, int& n, int pw, int ix, float w) {
+      if (n == 0 || s_pw[wib][slot][n - 1] != pw) {
+        s_pw[wib][slot][n] = pw;
+        s_cf[wib][slot][n] = 0;
+        s_c0[wib][slot][n] = s_c1[wib][slot][n] = 0.0f;
+        ++n;
+      }
+      s_cf[wib][slot][n - 1] |= 1 << ix;
+      if (ix) s_c1[wib][slot][n - 1] = w;
+      else s_c0[wib][slot][n - 1] = w;
+    };
+    auto flushA = [&]() {
+      if (nA > 0 && colA < width) {
+        const int* pw = s_pw[wib][A];
+        const int* cf = s_cf[wib][A];
+        const float* c0 = s_c0[wib][A];
+        const float* c1 = s_c1[wib][A];
+        hrow[ncols] = make_uint4((unsigned)(colA * col_bytes) | ((unsigned)nA << 16), (unsigned)nextra,
+                                 (unsigned)pw[0] | ((unsigned)cf[0] << 8) |
+                                     ((unsigned)(nA > 1 ? pw[1] : 0) << 16) | ((unsigned)(nA > 1 ? cf[1] : 0) << 24),
+                                 0u);
+        wrow[ncols] = make_uint4(__float_as_uint(c0[0]), __float_as_uint(c1[0]),
+                                 __float_as_uint(nA > 1 ? c0[1] : 0.0f), __float_as_uint(nA > 1 ? c1[1] : 0.0f));
+        for (int k = 2; k < nA; ++k)
+          erow[nextra++] = make_uint4((unsigned)pw[k] | ((unsigned)cf[k] << 8), 0u, __float_as_uint(c0[k]),
+                                      __float_as_uint(c1[k]));
+        ++ncols;
+      }
+      colA += 1;
+      A ^= 1;             // B becomes A
+      nA = nB;
+      nB = 0;
+    };
+    for (int s = 0; s < 2 * pooled_w; ++s) {
+      const int lo = s_lo[wib][s];
+      if (lo < 0) continue;
+      const int hi = s_hi[wib][s];
+      const float l = s_fl[wib][s], h = __fsub_rn(1.0f, l);
+      if (colA < 0) colA = lo;
+      while (colA < lo) {
+        if (nA == 0 && nB == 0) {
+          colA = lo;
+          break;
+        }
+        flushA();
+      }
+      hit(A, nA, s >> 1, s & 1, h);
+      if (hi != lo) hit(A ^ 1, nB, s >> 1, s & 1, l);
+    }
+    flushA();
+    flushA();
+  }
+  ncols = __shfl_sync(0xffffffffu, ncols, 0);
+  for (int k = ncols + lane; k < maxc; k += 32) hrow[k] = make_uint4(0u, 0u, 0u, 0u);   // unused slots
+  if (ncols == 0) {
+    ne = 0;
+    nrow = 0;
+  }
+
+  // ---- row entries sorted by (band, bin row, row) ----
+  for (int k = 0; k < nrow; ++k) {
+    s_key[wib][base + k] = (unsigned)((rrow[k] / band_rows) * 16 + lane) * 65536u + (unsigned)rrow[k];
+    s_rfl[wib][base + k] = rfl[k];
+    s_w0[wib][base + k] = rw0[k];
+    s_w1[wib][base + k] = rw1[k];
+  }
+  __syncwarp();
+  uint4* rout = rows_out + (size_t)j * maxe;
+  for (int e = lane; e < ne; e += 32) {
+    const unsigned key = s_key[wib][e];
+    int rank = 0;
+    for (int k = 0; k < ne; ++k) rank += s_key[wib][k] < key ? 1 : 0;
+    const unsigned row = key & 0xffffu, ph = (key >> 16) & 15u;
+    rout[rank] = make_uint4(row * (unsigned)row_bytes | ph, s_rfl[wib][e], __float_as_uint(s_w0[wib][e]),
+                            __float_as_uint(s_w1[wib][e]));
+    s_srow[wib][rank] = row;
+  }
+  __syncwarp();
+  for (int bnd = lane; bnd <= nbands; bnd += 32) {
+    const unsigned limit = (unsigned)(bnd * band_rows);
+    int lo = 0, hi = ne;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_srow[wib][mid] < limit) lo = mid + 1;
+      else hi = mid;
+    }
+    bstart[(size_t)bnd * num_rois + j] = (unsigned char)(bnd == nbands ? ne : lo);
+  }
+}
+
 // One block per (image, band): the visits of the band, in ROI order.  Thread t owns a
 // contiguous run of the image's ROIs; a block-wide prefix sum places its visits.
 // visit = x: grouped position | first entry << 20 | (entries - 1) << 26; y: roi row
@@ -932,6 +1106,14 @@ __device__ __forceinline__ float lds_vol(unsigned addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
 __device__ __forceinline__ uint2 lds64u(unsigned addr) {
   uint2 v;
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
@@ -940,21 +1122,34 @@ __device__ __forceinline__ uint2 lds64u(unsigned addr) {
 
 // Everything a warp needs for one visit, fetched while the previous visit is computed: NT floats
 // of the dy tile pair per lane, NE row entries of the band, NCK column records.
-template <int NT, int NCK, int NE>
+template <bool DET>
+struct RowEntry {
+  typedef uint2 type;       // merged: row | ph, weight
+};
+template <>
+struct RowEntry<true> {
+  typedef uint4 type;       // deterministic: row | ph, flags, weight iy = 0, weight iy = 1
+};
+
+template <int NT, int NCK, int NE, bool DET>
 struct VisitRegs {
   float g[NT];
-  uint2 e[NE];
+  typename RowEntry<DET>::type e[NE];
   uint4 col[NCK];
+  uint4 colw[DET ? NCK : 1];      // deterministic: the column weights
 };
 
 // Every warp is on its own: it takes (image, channel pair, band) units from a queue, keeps the
 // band -- `band_rows` rows x two channels, float2 per pixel -- in its private shared memory,
 // walks the band's visit list and stores the finished band to the two dX planes.
-template <int NT, int NCK, int NE, bool ACC>
+// DET: contributions are added one by one in the reference's single-thread order (bit-exact dX)
+// instead of merged per ROI.
+template <int NT, int NCK, int NE, bool ACC, bool DET>
 __global__ void __launch_bounds__(kBwdThreads, 2)
 resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const uint2* __restrict__ visits,
-                     const int* __restrict__ vcount, const uint2* __restrict__ rows_in,
-                     const uint4* __restrict__ cols, const uint2* __restrict__ extra,
+                     const int* __restrict__ vcount, const void* __restrict__ rows_v,
+                     const uint4* __restrict__ cols, const uint4* __restrict__ colw,
+                     const void* __restrict__ extra_v,
                      const int* __restrict__ img_start, int* __restrict__ counter, int num_images,
                      int channels, int c_count, int height, int width, int pitch2, int pooled_h, int pooled_w,
                      int maxe, int maxc, int nbands, int band_rows) {
@@ -964,7 +1159,10 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
   const unsigned rb = (unsigned)pitch2 * 8u;                 // bytes per band row
   // per warp: the band, then the dy tiles of the channel pair (NT * 32 floats) and the row
   // entries of the visit (NE * 32 * 8 bytes)
-  const unsigned slot_bytes = (unsigned)(NT * 32 + NE * 64 + 4) * 4u;     // + one spare entry
+  typedef typename RowEntry<DET>::type Entry;
+  const Entry* rows_in = static_cast<const Entry*>(rows_v);
+  constexpr unsigned kEntry = (unsigned)sizeof(Entry);
+  const unsigned slot_bytes = (unsigned)(NT * 32) * 4u + (NE * 32u + 2u) * kEntry;   // + spare entries
   const unsigned warp_bytes = (unsigned)band_rows * rb + slot_bytes;
   float2* band = reinterpret_cast<float2*>(smem_raw + (size_t)warp * warp_bytes);
   const unsigned sbase = ptx::smem_addr(band);
@@ -1025,27 +1223,84 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     const unsigned jv_ = vx_ & 0xfffffu, first_ = (vx_ >> 20) & 63u, cnt_ = (vx_ >> 26) + 1u;       \
     const float* tile_ = dy_c + (size_t)roi_ * cb;                                                \
     _Pragma("unroll") for (int i = 0; i < NT; ++i)(v).g[i] = __ldg(tile_ + tix[i]);               \
-    const uint2* er_ = rows_in + (jv_ * (unsigned)maxe + first_ + (unsigned)lane);                \
+    const Entry* er_ = rows_in + (jv_ * (unsigned)maxe + first_ + (unsigned)lane);                \
     _Pragma("unroll") for (int i = 0; i < NE; ++i)                                                \
-        (v).e[i] = (unsigned)lane + 32u * i < cnt_ ? __ldg(er_ + 32 * i) : make_uint2(0u, 0u);    \
+        if ((unsigned)lane + 32u * i < cnt_)(v).e[i] = __ldg(er_ + 32 * i);                       \
     const uint4* cr_ = cols + (jv_ * (unsigned)maxc + (unsigned)lane);                            \
     _Pragma("unroll") for (int i = 0; i < NCK; ++i)(v).col[i] = __ldg(cr_ + 32 * i);              \
+    if (DET) {                                                                                    \
+      const uint4* cw_ = colw + (jv_ * (unsigned)maxc + (unsigned)lane);                          \
+      _Pragma("unroll") for (int i = 0; i < NCK; ++i)(v).colw[i] = __ldg(cw_ + 32 * i);           \
+    }                                                                                             \
   } while (0)
 
     // one visit: the ROI's dy tiles and the band's row entries go to the warp's slot, then every
     // touched column (lane) adds its share to the band's rows
-    auto visit = [&](const VisitRegs<NT, NCK, NE>& cur, unsigned vx) {
+    auto visit = [&](const VisitRegs<NT, NCK, NE, DET>& cur, unsigned vx) {
       const unsigned jcur = vx & 0xfffffu, cnt = (vx >> 26) + 1u;
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < NT; ++i) sts_at(tile_s + 128u * i, cur.g[i]);
 #pragma unroll
       for (int i = 0; i < NE; ++i)
-        if ((unsigned)lane + 32u * i < cnt)
-          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(eslot_s + (lane + 32u * i) * 8u), "r"(cur.e[i].x),
-                       "r"(cur.e[i].y)
-                       : "memory");
+        if ((unsigned)lane + 32u * i < cnt) {
+          if constexpr (DET)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(eslot_s + (lane + 32u * i) * 16u),
+                         "r"(cur.e[i].x), "r"(cur.e[i].y), "r"(cur.e[i].z), "r"(cur.e[i].w)
+                         : "memory");
+          else
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(eslot_s + (lane + 32u * i) * 8u),
+                         "r"(cur.e[i].x), "r"(cur.e[i].y)
+                         : "memory");
+        }
       __syncwarp();
+      if constexpr (DET) {
+        const uint4* extra = static_cast<const uint4*>(extra_v);
+#pragma unroll
+        for (int ck = 0; ck < NCK; ++ck) {
+          const uint4 ch = cur.col[ck], cw = cur.colw[ck];
+          const int nh = (int)((ch.x >> 16) & 0xffu);
+          if (nh == 0) continue;                        // this lane has no column in this chunk
+          const unsigned caddr = col_base + (ch.x & 0xffffu);
+          for (unsigned e = 0; e < cnt; ++e) {
+            const uint4 re = lds128(eslot_s + e * 16u);           // broadcast
+            const unsigned ph = re.x & 15u, rfl = re.y;
+            const float wy0 = __uint_as_float(re.z), wy1 = __uint_as_float(re.w);
+            const unsigned a = caddr + (re.x & ~15u);
+            const unsigned grow = slot_s + ph * (unsigned)pooled_w * 4u;
+            float2 v = lds64(a);
+            // the reference's order at this pixel: pw, then iy, then ix (ROIAlign.cpp:126-157);
+            // g = (dtop * (wy * wx)) / count, count = 4
+            auto hit = [&](unsigned pw, unsigned cfl, float wx0, float wx1) {
+              const float d0 = lds_vol(grow + pw * 4u), d1 = lds_vol(grow + pw * 4u + ch1);
+              auto add = [&](float wy, float wx) {
+                const float w = __fmul_rn(wy, wx);
+                v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(d0, w), 0.25f));
+                v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(d1, w), 0.25f));
+              };
+              if (rfl & 1u) {
+                if (cfl & 1u) add(wy0, wx0);
+                if (cfl & 2u) add(wy0, wx1);
+              }
+              if (rfl & 2u) {
+                if (cfl & 1u) add(wy1, wx0);
+                if (cfl & 2u) add(wy1, wx1);
+              }
+            };
+            hit(ch.z & 0xffu, (ch.z >> 8) & 0xffu, __uint_as_float(cw.x), __uint_as_float(cw.y));
+            if (nh > 1) {
+              hit((ch.z >> 16) & 0xffu, ch.z >> 24, __uint_as_float(cw.z), __uint_as_float(cw.w));
+              for (int x = 2; x < nh; ++x) {
+                const uint4 hx = __ldg(extra + (size_t)jcur * maxc + ch.y + (x - 2));
+                hit(hx.x & 0xffu, (hx.x >> 8) & 0xffu, __uint_as_float(hx.z), __uint_as_float(hx.w));
+              }
+            }
+            sts64(a, v);
+          }
+        }
+        return;
+      }
+      const uint2* extra = static_cast<const uint2*>(extra_v);
 #pragma unroll
       for (int ck = 0; ck < NCK; ++ck) {
         const uint4 cr = cur.col[ck];
@@ -1112,9 +1367,9 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
       MOBULA_LOAD_VISIT(v, k);                                                                    \
     }                                                                                             \
   } while (0)
-    if constexpr (NT >= 8) {
-      // large tiles: two sets (three would not fit the register budget of two CTAs per SM)
-      VisitRegs<NT, NCK, NE> va, vb;
+    if constexpr (NT >= 8 || DET) {
+      // large tiles, wide records: two sets (three would not fit the register budget of two CTAs per SM)
+      VisitRegs<NT, NCK, NE, DET> va, vb;
       unsigned xa = 0u, xb = 0u;
       MOBULA_STAGE(va, xa, 0);
       for (int k = 0; k < nvis; k += 2) {
@@ -1125,7 +1380,7 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
         visit(vb, xb);
       }
     } else {
-      VisitRegs<NT, NCK, NE> va, vb, vc;
+      VisitRegs<NT, NCK, NE, DET> va, vb, vc;
       unsigned xa = 0u, xb = 0u, xc = 0u;
       MOBULA_STAGE(va, xa, 0);
       MOBULA_STAGE(vb, xb, 1);
@@ -1177,19 +1432,20 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
 }
 
 struct BwdLayout {
-  size_t img_start, order, rows, bstart, cols, extra, visits, vcount, counter, total;
+  size_t img_start, order, rows, bstart, cols, colw, extra, visits, vcount, counter, total;
 };
 
-BwdLayout bwd_layout(const RoiAlignArgs& a, int maxe, int maxc, int nbands) {
+BwdLayout bwd_layout(const RoiAlignArgs& a, int maxe, int maxc, int nbands, bool det) {
   BwdLayout l;
   size_t p = 0;
   const size_t R = (size_t)a.num_rois, N = (size_t)(a.num_images > 0 ? a.num_images : 0);
   l.img_start = p;  p += align_up((N + 2) * sizeof(int), 256);
   l.order = p;      p += align_up(R * sizeof(int), 256);
-  l.rows = p;       p += align_up(R * maxe * sizeof(uint2), 256);
+  l.rows = p;       p += align_up(R * maxe * (det ? sizeof(uint4) : sizeof(uint2)), 256);
   l.bstart = p;     p += align_up(R * (size_t)(nbands + 1), 256);
   l.cols = p;       p += align_up(R * maxc * sizeof(uint4), 256);
-  l.extra = p;      p += align_up(R * maxc * sizeof(uint2), 256);
+  l.colw = p;       p += det ? align_up(R * maxc * sizeof(uint4), 256) : 0;
+  l.extra = p;      p += align_up(R * maxc * (det ? sizeof(uint4) : sizeof(uint2)), 256);
   l.visits = p;     p += align_up(R * (size_t)nbands * sizeof(uint2), 256);
   l.vcount = p;     p += align_up(N * (size_t)nbands * sizeof(int), 256);
   l.counter = p;    p += 256;
@@ -1248,7 +1504,8 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
     const int maxc = (4 * a.pooled_w + 31) / 32 * 32, maxe = (4 * a.pooled_h + 31) / 32 * 32;
     const bool small = maxc == 32 && maxe == 32;
     // per warp: dy tiles of the channel pair + the row entries of a visit
-    const size_t slot = (size_t)(nt * 32 + (small ? 1 : 2) * 64 + 4) * sizeof(float);
+    // (sized for the 16-byte records of the deterministic variant)
+    const size_t slot = (size_t)(nt * 32) * sizeof(float) + ((small ? 1 : 2) * 32 + 2) * sizeof(uint4);
     // band rows hold two channels (float2 per pixel); a warp instruction touches one row, so
     // the pitch only has to keep rows 16-byte aligned
     const int pitch2 = (a.width + 1) & ~1;
@@ -1367,33 +1624,41 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   return cudaGetLastError();
 }
 
-size_t resident_bwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan) {
-  return bwd_layout(a, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slabs).total;
+size_t resident_bwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan, int deterministic) {
+  return bwd_layout(a, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slabs, deterministic != 0).total;
 }
 
 cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan, void* workspace,
-                                const float* dy, float* dx, int accumulate, int num_sms,
+                                const float* dy, float* dx, int accumulate, int deterministic, int num_sms,
                                 cudaStream_t stream) {
   if (a.num_images == 0 || a.channels == 0) return cudaSuccess;
   const int nbands = plan.bwd_slabs;
-  const BwdLayout l = bwd_layout(a, plan.bwd_maxe, plan.bwd_maxc, nbands);
+  const bool det = deterministic != 0;
+  const BwdLayout l = bwd_layout(a, plan.bwd_maxe, plan.bwd_maxc, nbands, det);
   char* base = (char*)workspace;
   int* img_start = (int*)(base + l.img_start);
   int* order = (int*)(base + l.order);
-  uint2* rows = (uint2*)(base + l.rows);
+  void* rows = base + l.rows;
   unsigned char* bstart = (unsigned char*)(base + l.bstart);
   uint4* cols = (uint4*)(base + l.cols);
-  uint2* extra = (uint2*)(base + l.extra);
+  uint4* colw = (uint4*)(base + l.colw);
+  void* extra = base + l.extra;
   uint2* visits = (uint2*)(base + l.visits);
   int* vcount = (int*)(base + l.vcount);
   int* counter = (int*)(base + l.counter);
   cudaError_t e = launch_roi_group(a, img_start, order, stream);
   if (e != cudaSuccess) return e;
   const int tb = a.num_rois > 0 ? (a.num_rois + 3) / 4 : 1;       // one warp per ROI
-  resident_bwd2_table_kernel<<<tb, 128, 0, stream>>>(
-      a.rois, order, img_start, a.num_images, a.num_rois, a.height, a.width, plan.bwd_pitch2 * 8, 8,
-      a.pooled_h, a.pooled_w, a.scale, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slab_rows, nbands, rows, bstart,
-      cols, extra, counter);
+  if (det)
+    resident_bwd2d_table_kernel<<<tb, 128, 0, stream>>>(
+        a.rois, order, img_start, a.num_images, a.num_rois, a.height, a.width, plan.bwd_pitch2 * 8, 8,
+        a.pooled_h, a.pooled_w, a.scale, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slab_rows, nbands, (uint4*)rows,
+        bstart, cols, colw, (uint4*)extra, counter);
+  else
+    resident_bwd2_table_kernel<<<tb, 128, 0, stream>>>(
+        a.rois, order, img_start, a.num_images, a.num_rois, a.height, a.width, plan.bwd_pitch2 * 8, 8,
+        a.pooled_h, a.pooled_w, a.scale, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slab_rows, nbands, (uint2*)rows,
+        bstart, cols, (uint2*)extra, counter);
   count_launch();
   resident_bwd2_visits_kernel<<<a.num_images * nbands, kVisitThreads, 0, stream>>>(
       order, img_start, bstart, a.num_images, a.num_rois, nbands, visits, vcount);
@@ -1402,20 +1667,25 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   const long long units = (long long)a.num_images * ((cc + 1) / 2) * nbands;
   const long long cta_units = (units + kBwdWarps - 1) / kBwdWarps;
   unsigned grid = 0;
-#define MOBULA_BWD2(NT, NCK, NE, ACC)                                                                 \
+#define MOBULA_BWD2(NT, NCK, NE, ACC, DET)                                                            \
   do {                                                                                                \
-    e = resident_grid(resident_bwd2_kernel<NT, NCK, NE, ACC>, kBwdThreads, plan.bwd_smem, num_sms,    \
-                      cta_units, &grid);                                                              \
+    e = resident_grid(resident_bwd2_kernel<NT, NCK, NE, ACC, DET>, kBwdThreads, plan.bwd_smem,        \
+                      num_sms, cta_units, &grid);                                                     \
     if (e != cudaSuccess) return e;                                                                   \
-    resident_bwd2_kernel<NT, NCK, NE, ACC><<<grid, kBwdThreads, plan.bwd_smem, stream>>>(             \
-        dy, dx, visits, vcount, rows, cols, extra, img_start, counter, a.num_images, a.channels, cc,  \
-        a.height, a.width, plan.bwd_pitch2, a.pooled_h, a.pooled_w, plan.bwd_maxe, plan.bwd_maxc,     \
-        nbands, plan.bwd_slab_rows);                                                                  \
+    resident_bwd2_kernel<NT, NCK, NE, ACC, DET><<<grid, kBwdThreads, plan.bwd_smem, stream>>>(        \
+        dy, dx, visits, vcount, rows, cols, colw, extra, img_start, counter, a.num_images,            \
+        a.channels, cc, a.height, a.width, plan.bwd_pitch2, a.pooled_h, a.pooled_w, plan.bwd_maxe,    \
+        plan.bwd_maxc, nbands, plan.bwd_slab_rows);                                                   \
   } while (0)
-#define MOBULA_BWD2_ACC(NT, NCK, NE)                    \
-  do {                                                  \
-    if (accumulate) MOBULA_BWD2(NT, NCK, NE, true);     \
-    else MOBULA_BWD2(NT, NCK, NE, false);               \
+#define MOBULA_BWD2_ACC(NT, NCK, NE)                                       \
+  do {                                                                     \
+    if (det) {                                                             \
+      if (accumulate) MOBULA_BWD2(NT, NCK, NE, true, true);                \
+      else MOBULA_BWD2(NT, NCK, NE, false, true);                          \
+    } else {                                                               \
+      if (accumulate) MOBULA_BWD2(NT, NCK, NE, true, false);               \
+      else MOBULA_BWD2(NT, NCK, NE, false, false);                         \
+    }                                                                      \
   } while (0)
 #define MOBULA_BWD2_NT(NT)                                                  \
   do {                                                                      \

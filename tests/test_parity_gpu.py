@@ -139,6 +139,15 @@ def test_backward_deterministic_golden_bit_exact(direct, name):
     assert_bit_exact(dx, g['dx'])
     again = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], mode='deterministic')
     assert_bit_exact(dx, again)
+    # sampling_ratio 2 takes the resident kernel's canonical-order variant, anything else the
+    # whole-plane canonical kernel; both must give the single-thread reference's bits
+    from mobulaop_b200 import _native
+    expect = 'resident-canonical' if g['sr'] == 2 and max(g['pooled']) <= 16 else 'plane-canonical'
+    assert _native.last_algo(True) == expect
+    plane = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], mode='deterministic',
+                            algo='plane')
+    assert _native.last_algo(True) == 'plane-canonical'
+    assert_bit_exact(plane, g['dx'])
 
 
 # ---- seeded workloads shaped like the BASELINE configs, oracle-sized -------------------

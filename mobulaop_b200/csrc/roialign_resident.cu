@@ -1159,6 +1159,9 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
   const unsigned rb = (unsigned)pitch2 * 8u;                 // bytes per band row
   // per warp: the band, then the dy tiles of the channel pair (NT * 32 floats) and the row
   // entries of the visit (NE * 32 * 8 bytes)
+  constexpr unsigned kMaxE = NE * 32u, kMaxC = NCK * 32u;      // = maxe, maxc of the tables
+  (void)maxe;
+  (void)maxc;
   typedef typename RowEntry<DET>::type Entry;
   const Entry* rows_in = static_cast<const Entry*>(rows_v);
   constexpr unsigned kEntry = (unsigned)sizeof(Entry);
@@ -1223,13 +1226,13 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     const unsigned jv_ = vx_ & 0xfffffu, first_ = (vx_ >> 20) & 63u, cnt_ = (vx_ >> 26) + 1u;       \
     const float* tile_ = dy_c + (size_t)roi_ * cb;                                                \
     _Pragma("unroll") for (int i = 0; i < NT; ++i)(v).g[i] = __ldg(tile_ + tix[i]);               \
-    const Entry* er_ = rows_in + (jv_ * (unsigned)maxe + first_ + (unsigned)lane);                \
+    const Entry* er_ = rows_in + (jv_ * kMaxE + first_ + (unsigned)lane);                \
     _Pragma("unroll") for (int i = 0; i < NE; ++i)                                                \
         if ((unsigned)lane + 32u * i < cnt_)(v).e[i] = __ldg(er_ + 32 * i);                       \
-    const uint4* cr_ = cols + (jv_ * (unsigned)maxc + (unsigned)lane);                            \
+    const uint4* cr_ = cols + (jv_ * kMaxC + (unsigned)lane);                            \
     _Pragma("unroll") for (int i = 0; i < NCK; ++i)(v).col[i] = __ldg(cr_ + 32 * i);              \
     if (DET) {                                                                                    \
-      const uint4* cw_ = colw + (jv_ * (unsigned)maxc + (unsigned)lane);                          \
+      const uint4* cw_ = colw + (jv_ * kMaxC + (unsigned)lane);                          \
       _Pragma("unroll") for (int i = 0; i < NCK; ++i)(v).colw[i] = __ldg(cw_ + 32 * i);           \
     }                                                                                             \
   } while (0)
@@ -1291,7 +1294,7 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
             if (nh > 1) {
               hit((ch.z >> 16) & 0xffu, ch.z >> 24, __uint_as_float(cw.z), __uint_as_float(cw.w));
               for (int x = 2; x < nh; ++x) {
-                const uint4 hx = __ldg(extra + (size_t)jcur * maxc + ch.y + (x - 2));
+                const uint4 hx = __ldg(extra + (size_t)jcur * kMaxC + ch.y + (x - 2));
                 hit(hx.x & 0xffu, (hx.x >> 8) & 0xffu, __uint_as_float(hx.z), __uint_as_float(hx.w));
               }
             }
@@ -1325,7 +1328,7 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
               t.x = fmaf(w1, lds_vol(g1 + grow), t.x);
               t.y = fmaf(w1, lds_vol(g1 + grow + ch1), t.y);
               for (int x = 2; x < nh; ++x) {
-                const uint2 hx = __ldg(extra + (size_t)jcur * maxc + cr.w + (x - 2));
+                const uint2 hx = __ldg(extra + (size_t)jcur * kMaxC + cr.w + (x - 2));
                 const unsigned ge = slot_s + hx.x * 4u + grow;
                 t.x = fmaf(__uint_as_float(hx.y), lds_vol(ge), t.x);
                 t.y = fmaf(__uint_as_float(hx.y), lds_vol(ge + ch1), t.y);
@@ -1501,8 +1504,9 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
       a.pooled_h * a.pooled_w <= kMaxSlotFloats && a.height < 65536 && a.width * 8 < 65536) {
     const int nt_raw = (2 * a.pooled_h * a.pooled_w + 31) / 32;
     const int nt = nt_raw <= 1 ? 1 : nt_raw <= 2 ? 2 : nt_raw <= 4 ? 4 : nt_raw <= 8 ? 8 : 16;
-    const int maxc = (4 * a.pooled_w + 31) / 32 * 32, maxe = (4 * a.pooled_h + 31) / 32 * 32;
+    int maxc = (4 * a.pooled_w + 31) / 32 * 32, maxe = (4 * a.pooled_h + 31) / 32 * 32;
     const bool small = maxc == 32 && maxe == 32;
+    if (!small) maxc = maxe = 64;      // the kernel is instantiated for 32 / 32 and 64 / 64
     // per warp: dy tiles of the channel pair + the row entries of a visit
     // (sized for the 16-byte records of the deterministic variant)
     const size_t slot = (size_t)(nt * 32) * sizeof(float) + ((small ? 1 : 2) * 32 + 2) * sizeof(uint4);

@@ -187,7 +187,7 @@ def run_reference_arm(args):
         e2e=dict(value=res['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         gpu_launches=0,
     )
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -207,8 +207,6 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     build.build()
     lib = _native.load()
@@ -352,7 +350,7 @@ def run_ours(args):
                     dtype='f32', data='synthetic', config=cfg, roofline=roofline,
                     cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks.summary(),
                     wall_s_timed_region=wall)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -414,8 +412,31 @@ def run_e2e(args, wl, shard, world, dev):
                     'inputs and results in page-locked host memory (NumPy arrays)')
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version banner,
+    for one), so file descriptor 1 is pointed at stderr for the rest of the run and the result
+    line goes to a private duplicate of the original stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == 'reference':
         return run_reference_arm(args)
     return run_ours(args)

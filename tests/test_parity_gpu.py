@@ -192,6 +192,42 @@ def test_untabled_rois_take_the_on_the_fly_path(direct, name):
     assert_bit_exact(dx, g['dx'])
 
 
+# ---- odd shapes: everything the kernels special-case ---------------------------------------------
+ODD_SHAPES = [
+    # N, C, H, W, rois/img, pooled, scale, sr
+    (3, 5, 21, 30, 17, (7, 7), 0.25, 2),       # odd C (half a channel pair), W % 4 != 0
+    (2, 3, 40, 52, 23, (16, 16), 0.125, 2),    # widest pooled shape of the sr = 2 kernels
+    (2, 4, 33, 36, 19, (1, 1), 0.5, 2),        # a single bin
+    (2, 2, 18, 20, 9, (9, 3), 0.5, 2),         # PH > 8, PW small: mixed table sizes
+    (1, 7, 150, 200, 40, (7, 7), 0.25, 2),     # tall plane: many row bands per plane
+    (2, 3, 24, 28, 11, (7, 7), 0.25, 1),       # generic resident forward, sr 1
+    (2, 3, 24, 28, 11, (5, 6), 0.25, 4),       # ... sr 4
+]
+
+
+@pytest.mark.parametrize('shape', ODD_SHAPES, ids=lambda s: 'x'.join(str(v) for v in s[:5]) + '-p%dx%d-sr%d' % (s[5] + (s[7],)))
+def test_odd_shapes_against_the_oracle(direct, oracle, shape):
+    N, C, H, W, k, pooled, scale, sr = shape
+    wl = WL.Workload('odd', N, C, H, W, k, pooled, scale, sr, min_box=2.0, max_box=4.0 * max(H, W) / scale)
+    data, rois, dy = WL.make_inputs(wl, seed=23)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(rois))                  # ROIs not grouped by image
+    rois = np.ascontiguousarray(rois[perm])
+    dy = np.ascontiguousarray(dy[perm])
+    rois[rois[:, 0] == N - 1, 0] = 0 if N > 1 else 0   # the last image has no ROI at all
+    y_ref = oracle.forward(data, rois, pooled, scale, sr, threads=0)
+    dx_ref = oracle.backward(dy, rois, data.shape, scale, sr)
+    dx_abs = oracle.backward(np.abs(dy), rois, data.shape, scale, sr)
+    for algo in ('auto', 'gather'):
+        assert_bit_exact(direct.forward(data, rois, pooled, scale, sr, algo=algo), y_ref)
+        assert_scatter_close(direct.backward(dy, rois, data.shape, scale, sr, algo=algo), dx_ref, dx_abs,
+                             rtol=1e-5)
+    assert_bit_exact(direct.backward(dy, rois, data.shape, scale, sr, mode='deterministic'), dx_ref)
+    base = rng.standard_normal(data.shape).astype(np.float32)
+    acc = direct.backward(dy, rois, data.shape, scale, sr, accumulate_into=base.copy())
+    np.testing.assert_allclose(acc, base + dx_ref, rtol=1e-5, atol=1e-5)
+
+
 # ---- ROI bookkeeping --------------------------------------------------------------------
 @pytest.mark.parametrize('name', ['edges_sr0', 'edges_sr2', 'ref_value_test', 'fpn_14x14_sr2'])
 def test_bookkeeping_bit_exact(native, torch, oracle, name):

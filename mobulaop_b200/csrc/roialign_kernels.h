@@ -128,7 +128,7 @@ struct ResidentPlan {
   int bwd_ok;          // the resident backward applies
   int bwd_slabs, bwd_slab_rows, bwd_maxc, bwd_maxe, bwd_pitch2;   // bands per plane, rows per band, ...
   size_t bwd_smem;
-  int use_bulk;        // rows can be moved with cp.async.bulk (16-byte alignment holds)
+  int vec16;           // plane rows are 16-byte aligned in global memory: cp.async 16-byte loads
 };
 
 bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_optin, ResidentPlan* plan);

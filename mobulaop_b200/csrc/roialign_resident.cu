@@ -126,15 +126,10 @@ __device__ __forceinline__ void zero_padding(float* plane, int height, int width
 
 // rows of `width` floats, dense in global memory, `pitch` floats apart in shared memory;
 // then the repeated column W and the repeated row H.  Ends with the plane visible to all.
-// `next` (may be null): the plane this CTA loads after this one -- the L2 is asked for it now,
-// so that its load finds it there.
-__device__ __forceinline__ void load_padded_plane(float* plane, const float* __restrict__ src,
-                                                  const float* __restrict__ next, int height, int width,
-                                                  int pitch, uint64_t* bar, uint32_t& parity, int use_bulk) {
-  (void)bar;
-  (void)parity;
-  (void)next;
-  if (use_bulk) {
+// `vec16`: every row starts 16-byte aligned in global memory (W % 4 == 0, aligned base).
+__device__ __forceinline__ void load_padded_plane(float* plane, const float* __restrict__ src, int height,
+                                                  int width, int pitch, int vec16) {
+  if (vec16) {
     // 16-byte asynchronous copies, every thread a strided share: thousands in flight per SM
     // (the per-row cp.async.bulk variant reached 3 TB/s over the chip, this one is HBM bound)
     const int w4 = width >> 2, total = height * w4;
@@ -213,18 +208,6 @@ __device__ __forceinline__ PlaneWork next_plane(const int* __restrict__ img_star
   return w;
 }
 
-// Plane of the work unit `u` (the one next_plane would return next), or null at the end.
-__device__ __forceinline__ const float* next_plane_ptr(const float* __restrict__ data,
-                                                       const int* __restrict__ img_start, int channels,
-                                                       int c_count, size_t plane_elems, long long u,
-                                                       long long u1, int n) {
-  if (u >= u1) return nullptr;
-  while ((long long)c_count * __ldg(img_start + n + 1) <= u) ++n;
-  const int j0 = __ldg(img_start + n), nroi = __ldg(img_start + n + 1) - j0;
-  const int c = (int)((u - (long long)c_count * j0) / nroi);
-  return data + ((size_t)n * channels + c) * plane_elems;
-}
-
 // ---- generic forward (sampling ratio 1, 3, 4 and wide pooled shapes): lane = pooled bin ----
 template <int G>
 __device__ __forceinline__ float pool_bin(const unsigned char* plane, const uint4* __restrict__ ye,
@@ -261,9 +244,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
 resident_fwd_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                     const int* __restrict__ img_start, const uint4* __restrict__ entries, int num_images,
                     int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w,
-                    int accumulate, int use_bulk) {
+                    int accumulate, int vec16) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t bar;
   float* plane = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bins = pooled_h * pooled_w;
@@ -274,12 +256,7 @@ resident_fwd_kernel(const float* __restrict__ data, float* __restrict__ out, con
   const CountDiv div(G * G);
 
   zero_padding(plane, height, width, pitch);
-  if (tid == 0 && use_bulk) {
-    ptx::mbar_init(&bar, 1);
-    ptx::fence_mbar_init();
-  }
   __syncthreads();
-  uint32_t parity = 0;
   if (!accumulate)
     zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
                               (long long)c_count * bins);
@@ -294,10 +271,8 @@ resident_fwd_kernel(const float* __restrict__ data, float* __restrict__ out, con
   while (u < u1) {
     const PlaneWork w = next_plane(img_start, c_count, u, u1, n);
     __syncthreads();   // every warp is done reading the previous plane
-    load_padded_plane(plane, data + ((size_t)w.n * channels + w.c) * plane_elems,
-                      next_plane_ptr(data, img_start, channels, c_count, plane_elems, u, u1, n), height, width,
-                      pitch,
-                      &bar, parity, use_bulk);
+    load_padded_plane(plane, data + ((size_t)w.n * channels + w.c) * plane_elems, height, width, pitch,
+                      vec16);
 
     int jj = w.jj0 + warp;
     uint4 e0 = make_uint4(0, 0, 0, 0), e1 = e0;
@@ -393,9 +368,8 @@ __global__ void __launch_bounds__(kFwd2Threads, 1)
 resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                      const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
                      int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w,
-                     int use_bulk) {
+                     int vec16) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t bar;
   float* plane = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bins = pooled_h * pooled_w;
@@ -406,12 +380,7 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
   const unsigned row_bytes = (unsigned)pitch * 4u;
 
   zero_padding(plane, height, width, pitch);
-  if (tid == 0 && use_bulk) {
-    ptx::mbar_init(&bar, 1);
-    ptx::fence_mbar_init();
-  }
   __syncthreads();
-  uint32_t parity = 0;
   if (!ACC)
     zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
                               (long long)c_count * bins);
@@ -429,16 +398,9 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
   while (u < u1) {
     const PlaneWork w = next_plane(img_start, c_count, u, u1, n);
     __syncthreads();   // every warp is done reading the previous plane
-#ifndef MOBULA_EXP_NOLOAD
-    load_padded_plane(plane, data + ((size_t)w.n * channels + w.c) * plane_elems,
-                      next_plane_ptr(data, img_start, channels, c_count, plane_elems, u, u1, n), height, width,
-                      pitch,
-                      &bar, parity, use_bulk);
-#endif
+    load_padded_plane(plane, data + ((size_t)w.n * channels + w.c) * plane_elems, height, width, pitch,
+                      vec16);
     ++epoch;
-#ifdef MOBULA_EXP_NOROI
-    continue;
-#endif
 
     int jj = w.jj0 + warp;
     Roi2Regs<ITERS, NCH> nxt;
@@ -1496,7 +1458,7 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
   plan->xslots = 16 * ((2 * a.pooled_w + 15) / 16);
   plan->plane_bytes = plane_bytes;
   plan->fwd_smem = plan->fwd_pair ? 2 * plane_bytes : fwd_smem;
-  plan->use_bulk = (a.width % 4 == 0) && ((uintptr_t)plane_ptr % 16 == 0) ? 1 : 0;
+  plan->vec16 = (a.width % 4 == 0) && ((uintptr_t)plane_ptr % 16 == 0) ? 1 : 0;
   // backward: sampling_ratio 2, the dy tile of a (roi, channel) in a 256-float slot; the plane
   // is cut into as few slabs of rows as let two CTAs share an SM
   plan->bwd_ok = 0;
@@ -1575,7 +1537,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     if (e != cudaSuccess) return e;                                                                  \
     resident_fwd2_kernel<ITERS, NCH, ACC><<<grid, kFwd2Threads, plan.fwd_smem, stream>>>(            \
         data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,       \
-        plan.pitch, a.pooled_h, a.pooled_w, plan.use_bulk);                                          \
+        plan.pitch, a.pooled_h, a.pooled_w, plan.vec16);                                          \
   } while (0)
 #define MOBULA_FWD2_NCH(ITERS, NCH)                  \
   do {                                               \
@@ -1615,7 +1577,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     if (e != cudaSuccess) return e;                                                                 \
     resident_fwd_kernel<G><<<grid, kFwdThreads, plan.fwd_smem, stream>>>(                           \
         data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,      \
-        plan.pitch, a.pooled_h, a.pooled_w, accumulate, plan.use_bulk);                             \
+        plan.pitch, a.pooled_h, a.pooled_w, accumulate, plan.vec16);                             \
   } while (0)
   switch (plan.grid) {
     case 1: MOBULA_RESIDENT_FWD(1); break;

@@ -111,7 +111,13 @@ const char* mobula_last_error(void);
 /* Forward bilinear pool.  `stream` is a cudaStream_t (NULL = legacy default
  * stream); the call is asynchronous unless MOBULA_ROIALIGN_HOST_BUFFERS is set.
  * `num_images` = N, or -1 if unknown (disables the batch-index range check and the
- * PLANE algorithm). */
+ * PLANE algorithm).
+ * Device-pointer calls may be captured into a CUDA graph: they do not synchronise,
+ * allocate or read back once the per-device workspace has its size, so run the same
+ * call once before the capture (a capture that would have to grow the workspace fails
+ * with MOBULA_ERR_UNSUPPORTED).  The workspace is shared by all streams of a device;
+ * eager calls order themselves on it, graph replays must be ordered against other
+ * users of the library on the same device by the caller. */
 int mobula_roialign_forward_f32(int device_id, void* stream, const float* bottom_data,
                                 const float* bottom_rois, float* top_data, int num_rois,
                                 int num_images, int channels, int height, int width,

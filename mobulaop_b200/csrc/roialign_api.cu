@@ -152,16 +152,45 @@ static unsigned algo_of(unsigned flags) {
 }
 
 // ---- device-pointer implementations --------------------------------------------------
+static bool is_capturing(cudaStream_t stream) {
+  cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &status) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return status == cudaStreamCaptureStatusActive;
+}
+
+// Hands the per-device workspace to a call on `stream`.  The workspace is shared by every
+// stream of the device: a call on another stream waits for the previous user to finish
+// with it.  While `stream` is being captured into a CUDA graph nothing may be allocated
+// and eager events may not be waited on: the workspace must already be large enough (run
+// the call once before capturing), and ordering the graph's replays against eager calls on
+// other streams is the caller's business.
+static int acquire_workspace(DeviceState& st, size_t bytes, cudaStream_t stream) {
+  if (is_capturing(stream)) {
+    if (bytes > st.workspace.bytes)
+      return fail(MOBULA_ERR_UNSUPPORTED,
+                  "stream capture: the %zu-byte workspace of this call does not exist yet; run the "
+                  "same call once outside the capture", bytes);
+    return MOBULA_OK;
+  }
+  if (st.ws_used && st.ws_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, st.ws_done, 0));
+  if (bytes > st.workspace.bytes && st.ws_used) CUDA_TRY(cudaEventSynchronize(st.ws_done));
+  CUDA_TRY(st.workspace.reserve(bytes, stream));
+  return MOBULA_OK;
+}
+
 // Builds the ROI tables for this call in the per-device workspace.
 static int prepare_tables(DeviceState& st, const RoiAlignArgs& a, unsigned need, int pitch,
                           unsigned flags, cudaStream_t stream, RoiTables* tables) {
-  // the workspace is shared by every stream of the device: a call on another stream waits
-  // for the previous user to finish with it
-  if (st.ws_used && st.ws_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, st.ws_done, 0));
   roi_tables_set_arena_override((flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) ? 0 : -1);
   const size_t bytes = roi_tables_bytes(a, need);
-  if (bytes > st.workspace.bytes && st.ws_used) CUDA_TRY(cudaEventSynchronize(st.ws_done));
-  CUDA_TRY(st.workspace.reserve(bytes, stream));
+  const int rc = acquire_workspace(st, bytes, stream);
+  if (rc) {
+    roi_tables_set_arena_override(-1);
+    return rc;
+  }
   *tables = roi_tables_carve(a, need, pitch, st.workspace.ptr);
   roi_tables_set_arena_override(-1);
   CUDA_TRY(launch_roi_tables(a, *tables, need, stream));
@@ -169,6 +198,7 @@ static int prepare_tables(DeviceState& st, const RoiAlignArgs& a, unsigned need,
 }
 
 static int release_tables(DeviceState& st, cudaStream_t stream) {
+  if (is_capturing(stream)) return MOBULA_OK;   // an event recorded here could not be waited on later
   if (!st.ws_done) CUDA_TRY(cudaEventCreateWithFlags(&st.ws_done, cudaEventDisableTiming));
   CUDA_TRY(cudaEventRecord(st.ws_done, stream));
   st.ws_stream = stream;
@@ -178,9 +208,8 @@ static int release_tables(DeviceState& st, cudaStream_t stream) {
 
 // Workspace of the resident kernels: same buffer, same hand-over rules as prepare_tables.
 static int prepare_workspace(DeviceState& st, size_t bytes, cudaStream_t stream, void** ws) {
-  if (st.ws_used && st.ws_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, st.ws_done, 0));
-  if (bytes > st.workspace.bytes && st.ws_used) CUDA_TRY(cudaEventSynchronize(st.ws_done));
-  CUDA_TRY(st.workspace.reserve(bytes, stream));
+  const int rc = acquire_workspace(st, bytes, stream);
+  if (rc) return rc;
   *ws = st.workspace.ptr;
   return MOBULA_OK;
 }

@@ -451,6 +451,54 @@ def test_host_buffer_path_is_pipelined_over_channel_chunks(api, native, oracle):
     np.testing.assert_allclose(dacc, dbase + dx, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize('deterministic', [False, True])
+def test_launches_can_be_captured_in_a_cuda_graph(api, torch, oracle, deterministic):
+    """Device-pointer calls are stream-ordered: no synchronise, no allocation and no host
+    read once the workspace exists, so forward + backward replay from a CUDA graph on new
+    contents of the same buffers."""
+    wl = _sample('C2', C=5, rois_per_image=64)
+    dev = torch.device('cuda', 0)
+    PH, PW = wl.pooled
+    first, second = WL.make_inputs(wl, seed=5), WL.make_inputs(wl, seed=6)
+    x = torch.from_numpy(first[0]).to(dev)
+    rois = torch.from_numpy(first[1]).to(dev)
+    dy = torch.from_numpy(first[2]).to(dev)
+    y = torch.empty(wl.out_shape, device=dev)
+    dx = torch.empty(wl.data_shape, device=dev)
+    nthreads = int(y.numel())
+    mode = 'deterministic' if deterministic else 'atomic'
+
+    def step():
+        api.func.roi_align_forward(nthreads, x, wl.scale, wl.C, wl.H, wl.W, PH, PW, wl.sampling_ratio,
+                                   rois, y)
+        api.func.roi_align_backward(nthreads, dy, wl.scale, wl.C, wl.H, wl.W, PH, PW, wl.sampling_ratio,
+                                    dx, rois, mode=mode, accumulate=False)
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        step()                      # sizes the workspace outside the capture
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    x.copy_(torch.from_numpy(second[0]))
+    rois.copy_(torch.from_numpy(second[1]))
+    dy.copy_(torch.from_numpy(second[2]))
+    y.fill_(float('nan'))
+    dx.fill_(float('nan'))
+    graph.replay()
+    torch.cuda.synchronize(dev)
+    data2, rois2, dy2 = second
+    assert_bit_exact(y.cpu().numpy(), oracle.forward(data2, rois2, wl.pooled, wl.scale, wl.sampling_ratio))
+    dx_ref = oracle.backward(dy2, rois2, data2.shape, wl.scale, wl.sampling_ratio)
+    if deterministic:
+        assert_bit_exact(dx.cpu().numpy(), dx_ref)
+    else:
+        dx_abs = oracle.backward(np.abs(dy2), rois2, data2.shape, wl.scale, wl.sampling_ratio)
+        assert_scatter_close(dx.cpu().numpy(), dx_ref, dx_abs, rtol=1e-5)
+
+
 def test_mixed_devices_rejected(api, torch):
     dev = torch.device('cuda', 0)
     data = torch.zeros((1, 1, 4, 4), device=dev)

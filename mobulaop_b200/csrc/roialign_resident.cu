@@ -1093,6 +1093,12 @@ struct RowEntry<true> {
   typedef uint4 type;       // deterministic: row | ph, flags, weight iy = 0, weight iy = 1
 };
 
+template <int NCK, bool DET>
+struct VisitCols {
+  uint4 col[NCK];
+  uint4 colw[DET ? NCK : 1];
+};
+
 template <int NT, int NCK, int NE, bool DET>
 struct VisitRegs {
   float g[NT];
@@ -1199,10 +1205,9 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     }                                                                                             \
   } while (0)
 
-    // one visit: the ROI's dy tiles and the band's row entries go to the warp's slot, then every
-    // touched column (lane) adds its share to the band's rows
-    auto visit = [&](const VisitRegs<NT, NCK, NE, DET>& cur, unsigned vx) {
-      const unsigned jcur = vx & 0xfffffu, cnt = (vx >> 26) + 1u;
+    // one visit, first half: the ROI's dy tiles and the band's row entries go to the warp's slot
+    auto publish = [&](const VisitRegs<NT, NCK, NE, DET>& cur, unsigned vx) {
+      const unsigned cnt = (vx >> 26) + 1u;
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < NT; ++i) sts_at(tile_s + 128u * i, cur.g[i]);
@@ -1219,6 +1224,10 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
                          : "memory");
         }
       __syncwarp();
+    };
+    // second half: every touched column (lane) adds its share to the band's rows
+    auto apply = [&](const VisitCols<NCK, DET>& cur, unsigned vx) {
+      const unsigned jcur = vx & 0xfffffu, cnt = (vx >> 26) + 1u;
       if constexpr (DET) {
         const uint4* extra = static_cast<const uint4*>(extra_v);
 #pragma unroll
@@ -1316,7 +1325,10 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
       }
     };
 
-    // register sets in turn: the loads of the next visits are in flight while visit k runs
+    // Two register sets in turn.  A visit first publishes its set, then starts the loads of the
+    // visit two ahead into the registers just freed, then computes: the scoreboard wait of the
+    // publishing stores (every global load of this kernel shares one scoreboard) therefore
+    // covers only loads that have been in flight for a whole visit, never the ones just issued.
     // (visit records come 32 at a time, the next chunk one chunk ahead)
     uint2 vnext = 32 + lane < nvis ? __ldg(vlist + 32 + lane) : make_uint2(0u, 0u);
     // STAGE(set, x, k): visit k (k < nvis) -> register set; its record comes from the current
@@ -1332,34 +1344,30 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
       MOBULA_LOAD_VISIT(v, k);                                                                    \
     }                                                                                             \
   } while (0)
-    if constexpr (NT >= 8 || DET) {
-      // large tiles, wide records: two sets (three would not fit the register budget of two CTAs per SM)
+#define MOBULA_VISIT(v, vx, knext)                                                                \
+  do {                                                                                            \
+    VisitCols<NCK, DET> cols_;                                                                    \
+    _Pragma("unroll") for (int i = 0; i < NCK; ++i) {                                             \
+      cols_.col[i] = (v).col[i];                                                                  \
+      if (DET) cols_.colw[i] = (v).colw[i];                                                       \
+    }                                                                                             \
+    const unsigned x_ = vx;                                                                       \
+    publish(v, x_);                                                                               \
+    MOBULA_STAGE(v, vx, knext);                                                                   \
+    apply(cols_, x_);                                                                             \
+  } while (0)
+    {
       VisitRegs<NT, NCK, NE, DET> va, vb;
       unsigned xa = 0u, xb = 0u;
       MOBULA_STAGE(va, xa, 0);
-      for (int k = 0; k < nvis; k += 2) {
-        MOBULA_STAGE(vb, xb, k + 1);
-        visit(va, xa);
-        if (k + 1 >= nvis) break;
-        MOBULA_STAGE(va, xa, k + 2);
-        visit(vb, xb);
-      }
-    } else {
-      VisitRegs<NT, NCK, NE, DET> va, vb, vc;
-      unsigned xa = 0u, xb = 0u, xc = 0u;
-      MOBULA_STAGE(va, xa, 0);
       MOBULA_STAGE(vb, xb, 1);
-      for (int k = 0; k < nvis; k += 3) {
-        MOBULA_STAGE(vc, xc, k + 2);
-        visit(va, xa);
+      for (int k = 0; k < nvis; k += 2) {
+        MOBULA_VISIT(va, xa, k + 2);
         if (k + 1 >= nvis) break;
-        MOBULA_STAGE(va, xa, k + 3);
-        visit(vb, xb);
-        if (k + 2 >= nvis) break;
-        MOBULA_STAGE(vb, xb, k + 4);
-        visit(vc, xc);
+        MOBULA_VISIT(vb, xb, k + 3);
       }
     }
+#undef MOBULA_VISIT
 #undef MOBULA_STAGE
 #undef MOBULA_LOAD_VISIT
 

@@ -696,7 +696,7 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   __shared__ float s_fl[4][32], s_wa[4][kMaxHitsPerCol], s_wb[4][kMaxHitsPerCol];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x * 4 + wib;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = counter[1] = 0;   // unit queue, visit blocks done
   const int valid = __ldg(img_start + num_images);
   if (j >= valid) return;
   const int roi = __ldg(order + j);
@@ -865,7 +865,7 @@ resident_bwd2d_table_kernel(const float* __restrict__ rois, const int* __restric
   __shared__ float s_c0[4][2][kMaxHitsPerCol], s_c1[4][2][kMaxHitsPerCol];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x * 4 + wib;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = counter[1] = 0;   // unit queue, visit blocks done
   const int valid = __ldg(img_start + num_images);
   if (j >= valid) return;
   const int roi = __ldg(order + j);
@@ -1014,12 +1014,19 @@ resident_bwd2d_table_kernel(const float* __restrict__ rois, const int* __restric
 // One block per (image, band): the visits of the band, in ROI order.  Thread t owns a
 // contiguous run of the image's ROIs; a block-wide prefix sum places its visits.
 // visit = x: grouped position | first entry << 20 | (entries - 1) << 26; y: roi row
+// The block that finishes last then orders the (image, band) pairs by work, heaviest first
+// (`uorder`): the main kernel's warps take units from a queue, and a unit is as long as its
+// band's visit list, so the long ones must start first for the warps to finish together.
 constexpr int kVisitThreads = 128;
+constexpr int kWorkBuckets = 64;
 __global__ void __launch_bounds__(kVisitThreads)
 resident_bwd2_visits_kernel(const int* __restrict__ order, const int* __restrict__ img_start,
                             const unsigned char* __restrict__ bstart, int num_images, int num_rois, int nbands,
-                            uint2* __restrict__ visits, int* __restrict__ vcount) {
+                            uint2* __restrict__ visits, int* __restrict__ vcount, int* __restrict__ uwork,
+                            int* __restrict__ uorder, int* __restrict__ counter) {
   __shared__ int s_warp[kVisitThreads / 32];
+  __shared__ int s_entries, s_last, s_max, s_hist[kWorkBuckets];
+  if (threadIdx.x == 0) s_entries = 0;
   const int w = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int n = w / nbands, bnd = w - n * nbands;
   const int j0 = __ldg(img_start + n), nroi = __ldg(img_start + n + 1) - j0;
@@ -1044,14 +1051,51 @@ resident_bwd2_visits_kernel(const int* __restrict__ order, const int* __restrict
     if (k < wid) before += v;
     total += v;
   }
+  int entries = 0;
   for (int jj = jb; jj < je; ++jj) {
     const int j = j0 + jj;
     const int first = s0[j], cnt = s1[j] - first;
-    if (cnt > 0)
+    if (cnt > 0) {
       list[before++] = make_uint2((unsigned)j | ((unsigned)first << 20) | ((unsigned)(cnt - 1) << 26),
                                   (unsigned)__ldg(order + j));
+      entries += cnt;
+    }
   }
-  if (t == 0) vcount[w] = total;
+  if (entries) atomicAdd(&s_entries, entries);
+  __syncthreads();
+  if (t == 0) {
+    vcount[w] = total;
+    uwork[w] = 3 * total + s_entries;        // a visit costs about three row entries
+    __threadfence();
+    s_last = atomicAdd(counter + 1, 1) == (int)gridDim.x - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // counting sort of the pairs by work, in kWorkBuckets classes, heaviest class first
+  const int pairs = (int)gridDim.x;
+  const volatile int* work = uwork;
+  if (t == 0) s_max = 1;
+  for (int k = t; k < kWorkBuckets; k += kVisitThreads) s_hist[k] = 0;
+  __syncthreads();
+  int mx = 0;
+  for (int k = t; k < pairs; k += kVisitThreads) mx = max(mx, work[k]);
+  atomicMax(&s_max, mx);
+  __syncthreads();
+  const long long top = s_max;
+  auto bucket = [&](int v) { return (kWorkBuckets - 1) - (int)((long long)v * (kWorkBuckets - 1) / top); };
+  for (int k = t; k < pairs; k += kVisitThreads) atomicAdd(&s_hist[bucket(work[k])], 1);
+  __syncthreads();
+  if (t == 0) {
+    int run = 0;
+    for (int k = 0; k < kWorkBuckets; ++k) {
+      const int c = s_hist[k];
+      s_hist[k] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  for (int k = t; k < pairs; k += kVisitThreads) uorder[atomicAdd(&s_hist[bucket(work[k])], 1)] = k;
 }
 
 // 8-byte shared-memory accesses on a 32-bit shared address; volatile: program order is kept
@@ -1115,7 +1159,8 @@ struct VisitRegs {
 template <int NT, int NCK, int NE, bool ACC, bool DET>
 __global__ void __launch_bounds__(kBwdThreads, 2)
 resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const uint2* __restrict__ visits,
-                     const int* __restrict__ vcount, const void* __restrict__ rows_v,
+                     const int* __restrict__ vcount, const int* __restrict__ uorder,
+                     const void* __restrict__ rows_v,
                      const uint4* __restrict__ cols, const uint4* __restrict__ colw,
                      const void* __restrict__ extra_v,
                      const int* __restrict__ img_start, int* __restrict__ counter, int num_images,
@@ -1154,8 +1199,9 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     const int unit = __shfl_sync(0xffffffffu, unit_next, 0);
     if (unit >= units) break;
     if (lane == 0) unit_next = atomicAdd(counter, 1);          // in flight while this unit runs
-    const int p = unit / nbands, bnd = unit - p * nbands;
-    const int n = p / cpairs, c = 2 * (p - n * cpairs);
+    // units in queue order: (image, band) pairs by decreasing work, then the channel pairs
+    const int rank = unit / cpairs, c = 2 * (unit - rank * cpairs);
+    const int pair = __ldg(uorder + rank), n = pair / nbands, bnd = pair - n * nbands;
     const bool two = c + 1 < c_count;
     const int tile_floats = two ? 2 * bins : bins;
     const int r0 = bnd * band_rows, r1 = min(height, r0 + band_rows);
@@ -1405,7 +1451,7 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
 }
 
 struct BwdLayout {
-  size_t img_start, order, rows, bstart, cols, colw, extra, visits, vcount, counter, total;
+  size_t img_start, order, rows, bstart, cols, colw, extra, visits, vcount, uwork, uorder, counter, total;
 };
 
 BwdLayout bwd_layout(const RoiAlignArgs& a, int maxe, int maxc, int nbands, bool det) {
@@ -1421,6 +1467,8 @@ BwdLayout bwd_layout(const RoiAlignArgs& a, int maxe, int maxc, int nbands, bool
   l.extra = p;      p += align_up(R * maxc * (det ? sizeof(uint4) : sizeof(uint2)), 256);
   l.visits = p;     p += align_up(R * (size_t)nbands * sizeof(uint2), 256);
   l.vcount = p;     p += align_up(N * (size_t)nbands * sizeof(int), 256);
+  l.uwork = p;      p += align_up(N * (size_t)nbands * sizeof(int), 256);
+  l.uorder = p;     p += align_up(N * (size_t)nbands * sizeof(int), 256);
   l.counter = p;    p += 256;
   l.total = p;
   return l;
@@ -1619,6 +1667,8 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   void* extra = base + l.extra;
   uint2* visits = (uint2*)(base + l.visits);
   int* vcount = (int*)(base + l.vcount);
+  int* uwork = (int*)(base + l.uwork);
+  int* uorder = (int*)(base + l.uorder);
   int* counter = (int*)(base + l.counter);
   cudaError_t e = launch_roi_group(a, img_start, order, stream);
   if (e != cudaSuccess) return e;
@@ -1635,7 +1685,7 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
         bstart, cols, (uint2*)extra, counter);
   count_launch();
   resident_bwd2_visits_kernel<<<a.num_images * nbands, kVisitThreads, 0, stream>>>(
-      order, img_start, bstart, a.num_images, a.num_rois, nbands, visits, vcount);
+      order, img_start, bstart, a.num_images, a.num_rois, nbands, visits, vcount, uwork, uorder, counter);
   count_launch();
   const int cc = a.c_count > 0 ? a.c_count : a.channels;      // channels worked on (stride: a.channels)
   const long long units = (long long)a.num_images * ((cc + 1) / 2) * nbands;
@@ -1647,7 +1697,7 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
                       num_sms, cta_units, &grid);                                                     \
     if (e != cudaSuccess) return e;                                                                   \
     resident_bwd2_kernel<NT, NCK, NE, ACC, DET><<<grid, kBwdThreads, plan.bwd_smem, stream>>>(        \
-        dy, dx, visits, vcount, rows, cols, colw, extra, img_start, counter, a.num_images,            \
+        dy, dx, visits, vcount, uorder, rows, cols, colw, extra, img_start, counter, a.num_images,    \
         a.channels, cc, a.height, a.width, plan.bwd_pitch2, a.pooled_h, a.pooled_w, plan.bwd_maxe,    \
         plan.bwd_maxc, nbands, plan.bwd_slab_rows);                                                   \
   } while (0)

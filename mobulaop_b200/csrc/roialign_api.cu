@@ -97,7 +97,7 @@ struct Buffer {
   }
 };
 
-constexpr int kHostChunks = 8;
+constexpr int kHostChunks = 32;   // at most; see host_chunks()
 
 struct DeviceState {
   std::mutex mu;
@@ -367,10 +367,26 @@ static int pipeline_setup(DeviceState& st) {
   return MOBULA_OK;
 }
 
+// Chunks of the host-buffer pipeline: enough for the copies to hide the kernels and for the
+// exposed first / last chunk to be short, few enough for every copy and kernel to stay large.
+// Measured on the C2 shapes (B200, PCIe 5 x16): the forward is best with 16 (its tail is one
+// kernel and one output chunk), the backward with 8 (its kernel needs >= 16 channel pairs to fill
+// the SMs, and its head is one kernel).  MOBULA_HOST_CHUNKS_FWD / _BWD override.
+static int host_chunks(bool backward) {
+  static const int chunks[2] = {
+      [] { const char* e = getenv("MOBULA_HOST_CHUNKS_FWD"); return e ? atoi(e) : 16; }(),
+      [] { const char* e = getenv("MOBULA_HOST_CHUNKS_BWD"); return e ? atoi(e) : 8; }()};
+  const int v = chunks[backward ? 1 : 0];
+  return v < 1 ? 1 : v > kHostChunks ? kHostChunks : v;
+}
+
 // channels per chunk (even, so that the backward's channel pairs stay whole); 0: do not chunk
-static int host_chunk(int channels, size_t tensor_bytes) {
-  if (channels < 2 * kHostChunks || tensor_bytes < (size_t(16) << 20)) return 0;
-  int cc = (channels + kHostChunks - 1) / kHostChunks;
+static int host_chunk(int channels, size_t tensor_bytes, bool backward) {
+  int chunks = host_chunks(backward);
+  if (tensor_bytes < (size_t(16) << 20)) return 0;
+  while (chunks > 1 && channels < 8 * chunks) chunks >>= 1;     // at least 8 channels per chunk
+  if (chunks < 2) return 0;
+  int cc = (channels + chunks - 1) / chunks;
   return (cc + 1) & ~1;
 }
 
@@ -432,11 +448,12 @@ MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, cons
   float* d_out = (float*)st.stage[2].ptr;
   RoiAlignArgs a = make_args(d_rois, num_rois, n_img, channels, height, width, pooled_height,
                              pooled_width, spatial_scale, sampling_ratio);
-  const int cc = resident_forward_applies(st, a, d_data, flags) ? host_chunk(channels, data_bytes) : 0;
+  const int cc = resident_forward_applies(st, a, d_data, flags) ? host_chunk(channels, data_bytes, false) : 0;
   if (cc > 0) {
     if ((rc = pipeline_setup(st))) return rc;
     const size_t hw = (size_t)height * width, bins = (size_t)pooled_height * pooled_width;
     const size_t row_pitch = (size_t)channels * bins * sizeof(float);
+    const size_t img_pitch = (size_t)channels * hw * sizeof(float);
     CUDA_TRY(cudaMemcpyAsync(d_rois, bottom_rois, rois_bytes, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaEventRecord(st.ev_start, stream));
     CUDA_TRY(cudaStreamWaitEvent(st.s_in, st.ev_start, 0));
@@ -444,11 +461,10 @@ MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, cons
     int k = 0;
     for (int c0 = 0; c0 < channels; c0 += cc, ++k) {
       const int cn = channels - c0 < cc ? channels - c0 : cc;
-      for (int n = 0; n < n_img; ++n) {
-        const size_t off = ((size_t)n * channels + c0) * hw;
-        CUDA_TRY(cudaMemcpyAsync(d_data + off, bottom_data + off, (size_t)cn * hw * sizeof(float),
-                                 cudaMemcpyHostToDevice, st.s_in));
-      }
+      // the chunk's channels of every image: n_img runs of cn planes, one image apart
+      if (n_img > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(d_data + c0 * hw, img_pitch, bottom_data + c0 * hw, img_pitch,
+                                   (size_t)cn * hw * sizeof(float), n_img, cudaMemcpyHostToDevice, st.s_in));
       if ((flags & MOBULA_ROIALIGN_ACCUMULATE) && num_rois > 0)
         CUDA_TRY(cudaMemcpy2DAsync(d_out + c0 * bins, row_pitch, top_data + c0 * bins, row_pitch,
                                    (size_t)cn * bins * sizeof(float), num_rois, cudaMemcpyHostToDevice, st.s_in));
@@ -519,11 +535,12 @@ MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream_, con
   float* d_dx = (float*)st.stage[2].ptr;
   RoiAlignArgs a = make_args(d_rois, num_rois, n_img, channels, height, width, pooled_height,
                              pooled_width, spatial_scale, sampling_ratio);
-  const int cc = resident_backward_applies(st, a, d_dx, mode, flags) ? host_chunk(channels, dx_bytes) : 0;
+  const int cc = resident_backward_applies(st, a, d_dx, mode, flags) ? host_chunk(channels, dx_bytes, true) : 0;
   if (cc > 0) {
     if ((rc = pipeline_setup(st))) return rc;
     const size_t hw = (size_t)height * width, bins = (size_t)pooled_height * pooled_width;
     const size_t row_pitch = (size_t)channels * bins * sizeof(float);
+    const size_t img_pitch = (size_t)channels * hw * sizeof(float);
     if (rois_bytes) CUDA_TRY(cudaMemcpyAsync(d_rois, bottom_rois, rois_bytes, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaEventRecord(st.ev_start, stream));
     CUDA_TRY(cudaStreamWaitEvent(st.s_in, st.ev_start, 0));
@@ -534,12 +551,9 @@ MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream_, con
       if (num_rois > 0)
         CUDA_TRY(cudaMemcpy2DAsync(d_dy + c0 * bins, row_pitch, top_diff + c0 * bins, row_pitch,
                                    (size_t)cn * bins * sizeof(float), num_rois, cudaMemcpyHostToDevice, st.s_in));
-      if (accumulate)
-        for (int n = 0; n < n_img; ++n) {
-          const size_t off = ((size_t)n * channels + c0) * hw;
-          CUDA_TRY(cudaMemcpyAsync(d_dx + off, bottom_diff + off, (size_t)cn * hw * sizeof(float),
-                                   cudaMemcpyHostToDevice, st.s_in));
-        }
+      if (accumulate && n_img > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(d_dx + c0 * hw, img_pitch, bottom_diff + c0 * hw, img_pitch,
+                                   (size_t)cn * hw * sizeof(float), n_img, cudaMemcpyHostToDevice, st.s_in));
       CUDA_TRY(cudaEventRecord(st.ev_in[k], st.s_in));
       CUDA_TRY(cudaStreamWaitEvent(stream, st.ev_in[k], 0));
       a.c_count = cn;
@@ -547,11 +561,9 @@ MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream_, con
         return rc;
       CUDA_TRY(cudaEventRecord(st.ev_done[k], stream));
       CUDA_TRY(cudaStreamWaitEvent(st.s_out, st.ev_done[k], 0));
-      for (int n = 0; n < n_img; ++n) {
-        const size_t off = ((size_t)n * channels + c0) * hw;
-        CUDA_TRY(cudaMemcpyAsync(bottom_diff + off, d_dx + off, (size_t)cn * hw * sizeof(float),
-                                 cudaMemcpyDeviceToHost, st.s_out));
-      }
+      if (n_img > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(bottom_diff + c0 * hw, img_pitch, d_dx + c0 * hw, img_pitch,
+                                   (size_t)cn * hw * sizeof(float), n_img, cudaMemcpyDeviceToHost, st.s_out));
     }
     CUDA_TRY(cudaStreamSynchronize(st.s_out));
     CUDA_TRY(cudaStreamSynchronize(stream));

@@ -15,7 +15,7 @@ namespace mobula_b200 {
 
 namespace {
 
-constexpr int kGroupThreads = 256;
+constexpr int kGroupThreads = 1024;
 constexpr int kRecThreads = 1024;
 
 __device__ __forceinline__ int segment_of(const float* __restrict__ rois, int r, int num_images) {

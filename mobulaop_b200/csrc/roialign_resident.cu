@@ -1228,9 +1228,10 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
 
     const unsigned col_base = sbase - (unsigned)r0 * rb;      // + row offset + column offset
     const float* dy_c = dy + (size_t)c * bins;
-    int tix[NT];              // tile floats past the pair's end re-read its last float (never used)
+    // float lane + 32 * i of the tile pair exists (one address per visit, constant offsets)
+    bool tile_ok[NT];
 #pragma unroll
-    for (int i = 0; i < NT; ++i) tix[i] = min(lane + 32 * i, tile_floats - 1);
+    for (int i = 0; i < NT; ++i) tile_ok[i] = lane + 32 * i < tile_floats;
 
     // visit k: record in lane k % 32 of `vrec` (chunk k / 32)
 #define MOBULA_LOAD_VISIT(v, k)                                                                   \
@@ -1238,8 +1239,9 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     const unsigned vx_ = __shfl_sync(0xffffffffu, vrec.x, (k) & 31);                              \
     const unsigned roi_ = __shfl_sync(0xffffffffu, vrec.y, (k) & 31);                             \
     const unsigned jv_ = vx_ & 0xfffffu, first_ = (vx_ >> 20) & 63u, cnt_ = (vx_ >> 26) + 1u;       \
-    const float* tile_ = dy_c + (size_t)roi_ * cb;                                                \
-    _Pragma("unroll") for (int i = 0; i < NT; ++i)(v).g[i] = __ldg(tile_ + tix[i]);               \
+    const float* tile_ = dy_c + ((size_t)roi_ * cb + (unsigned)lane);                             \
+    _Pragma("unroll") for (int i = 0; i < NT; ++i)                                                \
+        if (tile_ok[i])(v).g[i] = __ldg(tile_ + 32 * i);                                          \
     const Entry* er_ = rows_in + (jv_ * kMaxE + first_ + (unsigned)lane);                \
     _Pragma("unroll") for (int i = 0; i < NE; ++i)                                                \
         if ((unsigned)lane + 32u * i < cnt_)(v).e[i] = __ldg(er_ + 32 * i);                       \

@@ -127,6 +127,7 @@ struct ResidentPlan {
   size_t fwd_smem;
   int bwd_ok;          // the resident backward applies
   int bwd_slabs, bwd_slab_rows, bwd_maxc, bwd_maxe, bwd_pitch2;   // bands per plane, rows per band, ...
+  int bwd_ntx, bwd_tile_cols;   // column tiles per band, columns per tile
   size_t bwd_smem;
   int vec16;           // plane rows are 16-byte aligned in global memory: cp.async 16-byte loads
 };

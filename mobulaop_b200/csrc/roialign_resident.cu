@@ -689,7 +689,8 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
                            int width, int row_bytes, int col_bytes, int pooled_h, int pooled_w, float scale,
                            int maxe, int maxc, int band_rows, int nbands, uint2* __restrict__ rows_out,
                            unsigned char* __restrict__ bstart, uint4* __restrict__ cols,
-                           uint2* __restrict__ extra, int* __restrict__ counter) {
+                           uint2* __restrict__ extra, int2* __restrict__ crange,
+                           int* __restrict__ counter) {
   __shared__ unsigned s_key[4][64], s_srow[4][64];
   __shared__ float s_w[4][64];
   __shared__ int s_lo[4][32], s_hi[4][32], s_pa[4][kMaxHitsPerCol], s_pb[4][kMaxHitsPerCol];
@@ -742,6 +743,11 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   mine.lo = mine.hi = 0;
   mine.wl = mine.wh = 0.0f;
   if (lane < 2 * pooled_w) mine = axis_decode(sample_pos(g.start_w, lane >> 1, g.bin_w, lane & 1, 2), width);
+  {   // the columns this ROI touches: which column tiles have to visit it
+    const int cmin = __reduce_min_sync(0xffffffffu, mine.valid ? mine.lo : 0x7fffffff);
+    const int cmax = __reduce_max_sync(0xffffffffu, mine.valid ? mine.hi : -1);
+    if (lane == 0) crange[j] = make_int2(cmin, cmax);
+  }
   uint4* crow = cols + (size_t)j * maxc;
   uint2* erow = extra + (size_t)j * maxc;
   int ncols = 0;
@@ -855,7 +861,8 @@ resident_bwd2d_table_kernel(const float* __restrict__ rois, const int* __restric
                             int width, int row_bytes, int col_bytes, int pooled_h, int pooled_w, float scale,
                             int maxe, int maxc, int band_rows, int nbands, uint4* __restrict__ rows_out,
                             unsigned char* __restrict__ bstart, uint4* __restrict__ colh,
-                            uint4* __restrict__ colw, uint4* __restrict__ extra, int* __restrict__ counter) {
+                            uint4* __restrict__ colw, uint4* __restrict__ extra, int2* __restrict__ crange,
+                            int* __restrict__ counter) {
   __shared__ unsigned s_key[4][64], s_srow[4][64], s_rfl[4][64];
   __shared__ float s_w0[4][64], s_w1[4][64];
   __shared__ int s_lo[4][32], s_hi[4][32];
@@ -911,6 +918,11 @@ resident_bwd2d_table_kernel(const float* __restrict__ rois, const int* __restric
   mine.lo = mine.hi = 0;
   mine.wl = mine.wh = 0.0f;
   if (lane < 2 * pooled_w) mine = axis_decode(sample_pos(g.start_w, lane >> 1, g.bin_w, lane & 1, 2), width);
+  {   // the columns this ROI touches: which column tiles have to visit it
+    const int cmin = __reduce_min_sync(0xffffffffu, mine.valid ? mine.lo : 0x7fffffff);
+    const int cmax = __reduce_max_sync(0xffffffffu, mine.valid ? mine.hi : -1);
+    if (lane == 0) crange[j] = make_int2(cmin, cmax);
+  }
   uint4* hrow = colh + (size_t)j * maxc;
   uint4* wrow = colw + (size_t)j * maxc;
   uint4* erow = extra + (size_t)j * maxc;
@@ -1021,22 +1033,32 @@ constexpr int kVisitThreads = 128;
 constexpr int kWorkBuckets = 64;
 __global__ void __launch_bounds__(kVisitThreads)
 resident_bwd2_visits_kernel(const int* __restrict__ order, const int* __restrict__ img_start,
-                            const unsigned char* __restrict__ bstart, int num_images, int num_rois, int nbands,
+                            const unsigned char* __restrict__ bstart, const int2* __restrict__ crange,
+                            int num_images, int num_rois, int nbands, int ntx, int tile_cols,
                             uint2* __restrict__ visits, int* __restrict__ vcount, int* __restrict__ uwork,
                             int* __restrict__ uorder, int* __restrict__ counter) {
   __shared__ int s_warp[kVisitThreads / 32];
   __shared__ int s_entries, s_last, s_max, s_hist[kWorkBuckets];
   if (threadIdx.x == 0) s_entries = 0;
   const int w = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const int n = w / nbands, bnd = w - n * nbands;
+  // tile w = ((image, band), column tile): rows [bnd * band_rows, ...), columns [c0, c1)
+  const int tiles = nbands * ntx;
+  const int n = w / tiles, bt = w - n * tiles, bnd = bt / ntx, tx = bt - bnd * ntx;
+  const int c0 = tx * tile_cols, c1 = c0 + tile_cols;
   const int j0 = __ldg(img_start + n), nroi = __ldg(img_start + n + 1) - j0;
-  uint2* list = visits + ((size_t)j0 * nbands + (size_t)bnd * nroi);
+  uint2* list = visits + ((size_t)j0 * tiles + (size_t)bt * nroi);
   const unsigned char* s0 = bstart + (size_t)bnd * num_rois;
   const unsigned char* s1 = s0 + num_rois;
   const int per = (nroi + kVisitThreads - 1) / kVisitThreads;
   const int jb = min(nroi, t * per), je = min(nroi, jb + per);
+  auto meets = [&](int j) {
+    if (s1[j] <= s0[j]) return false;
+    if (ntx == 1) return true;
+    const int2 cr = crange[j];
+    return cr.y >= c0 && cr.x < c1;
+  };
   int mine = 0;
-  for (int jj = jb; jj < je; ++jj) mine += s1[j0 + jj] > s0[j0 + jj] ? 1 : 0;
+  for (int jj = jb; jj < je; ++jj) mine += meets(j0 + jj) ? 1 : 0;
   int incl = mine;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -1055,7 +1077,7 @@ resident_bwd2_visits_kernel(const int* __restrict__ order, const int* __restrict
   for (int jj = jb; jj < je; ++jj) {
     const int j = j0 + jj;
     const int first = s0[j], cnt = s1[j] - first;
-    if (cnt > 0) {
+    if (meets(j)) {
       list[before++] = make_uint2((unsigned)j | ((unsigned)first << 20) | ((unsigned)(cnt - 1) << 26),
                                   (unsigned)__ldg(order + j));
       entries += cnt;
@@ -1165,7 +1187,7 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
                      const void* __restrict__ extra_v,
                      const int* __restrict__ img_start, int* __restrict__ counter, int num_images,
                      int channels, int c_count, int height, int width, int pitch2, int pooled_h, int pooled_w,
-                     int maxe, int maxc, int nbands, int band_rows) {
+                     int maxe, int maxc, int nbands, int band_rows, int ntx, int tile_cols) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bins = pooled_h * pooled_w;
@@ -1186,7 +1208,8 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
   const unsigned eslot_s = slot_s + NT * 128u;
   const size_t plane_elems = (size_t)height * width;
   const int cpairs = (c_count + 1) >> 1;
-  const int units = num_images * cpairs * nbands;
+  const int tiles = nbands * ntx;                       // per plane: row bands x column tiles
+  const int units = num_images * cpairs * tiles;
   const int w4 = width >> 2;
 
   const unsigned tile_s = slot_s + (unsigned)lane * 4u;       // this lane's first tile float
@@ -1199,24 +1222,26 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     const int unit = __shfl_sync(0xffffffffu, unit_next, 0);
     if (unit >= units) break;
     if (lane == 0) unit_next = atomicAdd(counter, 1);          // in flight while this unit runs
-    // units in queue order: (image, band) pairs by decreasing work, then the channel pairs
+    // units in queue order: (image, tile) pairs by decreasing work, then the channel pairs
     const int rank = unit / cpairs, c = 2 * (unit - rank * cpairs);
-    const int pair = __ldg(uorder + rank), n = pair / nbands, bnd = pair - n * nbands;
+    const int pair = __ldg(uorder + rank), n = pair / tiles, bt = pair - n * tiles;
+    const int bnd = bt / ntx, tx = bt - bnd * ntx;
+    const int c0 = tx * tile_cols, cw = min(width, c0 + tile_cols) - c0;     // the tile's columns
     const bool two = c + 1 < c_count;
     const int tile_floats = two ? 2 * bins : bins;
     const int r0 = bnd * band_rows, r1 = min(height, r0 + band_rows);
     float* gplane = dx + ((size_t)n * channels + c) * plane_elems;
     const int j0 = __ldg(img_start + n), nroi = __ldg(img_start + n + 1) - j0;
-    const int nvis = __ldg(vcount + n * nbands + bnd);
-    const uint2* vlist = visits + ((size_t)j0 * nbands + (size_t)bnd * nroi);
+    const int nvis = __ldg(vcount + pair);
+    const uint2* vlist = visits + ((size_t)j0 * tiles + (size_t)bt * nroi);
     uint2 vrec = lane < nvis ? __ldg(vlist + lane) : make_uint2(0u, 0u);    // first 32 visits
 
     // ---- band := 0 (or the current dX rows when accumulating) ----
     __syncwarp();
     if (ACC) {
-      for (int i = lane; i < (r1 - r0) * width; i += 32) {
-        const int r = i / width, x = i - r * width;
-        const size_t gi = (size_t)(r0 + r) * width + x;
+      for (int i = lane; i < (r1 - r0) * cw; i += 32) {
+        const int r = i / cw, x = i - r * cw;
+        const size_t gi = (size_t)(r0 + r) * width + c0 + x;
         band[r * pitch2 + x] = make_float2(gplane[gi], two ? gplane[plane_elems + gi] : 0.0f);
       }
     } else {
@@ -1226,7 +1251,8 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     }
     __syncwarp();
 
-    const unsigned col_base = sbase - (unsigned)r0 * rb;      // + row offset + column offset
+    const unsigned col_base = sbase - (unsigned)r0 * rb - (unsigned)c0 * 8u;   // + row offset + column offset
+    const unsigned tile_lo = (unsigned)c0 * 8u, tile_span = (unsigned)cw * 8u;   // column offsets of the tile
     const float* dy_c = dy + (size_t)c * bins;
     // float lane + 32 * i of the tile pair exists (one address per visit, constant offsets)
     bool tile_ok[NT];
@@ -1282,7 +1308,8 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
         for (int ck = 0; ck < NCK; ++ck) {
           const uint4 ch = cur.col[ck], cw = cur.colw[ck];
           const int nh = (int)((ch.x >> 16) & 0xffu);
-          if (nh == 0) continue;                        // this lane has no column in this chunk
+          // this lane has no column in this chunk, or its column belongs to another tile
+          if (nh == 0 || (ch.x & 0xffffu) - tile_lo >= tile_span) continue;
           const unsigned caddr = col_base + (ch.x & 0xffffu);
           for (unsigned e = 0; e < cnt; ++e) {
             const uint4 re = lds128(eslot_s + e * 16u);           // broadcast
@@ -1327,7 +1354,8 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
       for (int ck = 0; ck < NCK; ++ck) {
         const uint4 cr = cur.col[ck];
         const int nh = (int)((cr.x >> 16) & 0xffu);
-        if (nh == 0) continue;                        // this lane has no column in this chunk
+        // this lane has no column in this chunk, or its column belongs to another tile
+        if (nh == 0 || (cr.x & 0xffffu) - tile_lo >= tile_span) continue;
         const unsigned caddr = col_base + (cr.x & 0xffffu);
         const unsigned g0 = slot_s + ((cr.x >> 24) & 0xfu) * 4u, g1 = slot_s + (cr.x >> 28) * 4u;
         const float w0 = __uint_as_float(cr.y), w1 = __uint_as_float(cr.z);
@@ -1422,29 +1450,30 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     __syncwarp();
     // ---- the finished band -> the two planes of dX, each element written once ----
     float* gplane1 = gplane + plane_elems;
-    if ((width & 3) == 0 && ((uintptr_t)dx & 15u) == 0) {
-      const int total = (r1 - r0) * w4;
-      int r = lane / w4, c4 = lane - r * w4;
-      const int dr = 32 / w4, dc = 32 - dr * w4;
-      float4* ga = reinterpret_cast<float4*>(gplane + (size_t)r0 * width);
-      float4* gb = reinterpret_cast<float4*>(gplane1 + (size_t)r0 * width);
+    if (((width | c0 | cw) & 3) == 0 && ((uintptr_t)dx & 15u) == 0) {
+      const int t4 = cw >> 2, total = (r1 - r0) * t4;          // the tile's row segments, 16 bytes at a time
+      int r = lane / t4, c4 = lane - r * t4;
+      const int dr = 32 / t4, dc = 32 - dr * t4;
+      float4* ga = reinterpret_cast<float4*>(gplane + (size_t)r0 * width + c0);
+      float4* gb = reinterpret_cast<float4*>(gplane1 + (size_t)r0 * width + c0);
       for (int i = lane; i < total; i += 32) {
         const float4* src = reinterpret_cast<const float4*>(band + (size_t)r * pitch2 + 4 * c4);
         const float4 lo = src[0], hi = src[1];       // (a0 b0 a1 b1) (a2 b2 a3 b3)
-        ga[i] = make_float4(lo.x, lo.z, hi.x, hi.z);
-        if (two) gb[i] = make_float4(lo.y, lo.w, hi.y, hi.w);
+        const size_t gi = (size_t)r * w4 + c4;
+        ga[gi] = make_float4(lo.x, lo.z, hi.x, hi.z);
+        if (two) gb[gi] = make_float4(lo.y, lo.w, hi.y, hi.w);
         r += dr;
         c4 += dc;
-        if (c4 >= w4) {
-          c4 -= w4;
+        if (c4 >= t4) {
+          c4 -= t4;
           ++r;
         }
       }
     } else {
-      for (int i = lane; i < (r1 - r0) * width; i += 32) {
-        const int r = i / width, x = i - r * width;
+      for (int i = lane; i < (r1 - r0) * cw; i += 32) {
+        const int r = i / cw, x = i - r * cw;
         const float2 v = band[r * pitch2 + x];
-        const size_t gi = (size_t)(r0 + r) * width + x;
+        const size_t gi = (size_t)(r0 + r) * width + c0 + x;
         gplane[gi] = v.x;
         if (two) gplane1[gi] = v.y;
       }
@@ -1453,10 +1482,10 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
 }
 
 struct BwdLayout {
-  size_t img_start, order, rows, bstart, cols, colw, extra, visits, vcount, uwork, uorder, counter, total;
+  size_t img_start, order, rows, bstart, cols, colw, extra, crange, visits, vcount, uwork, uorder, counter, total;
 };
 
-BwdLayout bwd_layout(const RoiAlignArgs& a, int maxe, int maxc, int nbands, bool det) {
+BwdLayout bwd_layout(const RoiAlignArgs& a, int maxe, int maxc, int nbands, int ntx, bool det) {
   BwdLayout l;
   size_t p = 0;
   const size_t R = (size_t)a.num_rois, N = (size_t)(a.num_images > 0 ? a.num_images : 0);
@@ -1467,10 +1496,12 @@ BwdLayout bwd_layout(const RoiAlignArgs& a, int maxe, int maxc, int nbands, bool
   l.cols = p;       p += align_up(R * maxc * sizeof(uint4), 256);
   l.colw = p;       p += det ? align_up(R * maxc * sizeof(uint4), 256) : 0;
   l.extra = p;      p += align_up(R * maxc * (det ? sizeof(uint4) : sizeof(uint2)), 256);
-  l.visits = p;     p += align_up(R * (size_t)nbands * sizeof(uint2), 256);
-  l.vcount = p;     p += align_up(N * (size_t)nbands * sizeof(int), 256);
-  l.uwork = p;      p += align_up(N * (size_t)nbands * sizeof(int), 256);
-  l.uorder = p;     p += align_up(N * (size_t)nbands * sizeof(int), 256);
+  const size_t tiles = (size_t)nbands * ntx;
+  l.crange = p;     p += align_up(R * sizeof(int2), 256);
+  l.visits = p;     p += align_up(R * tiles * sizeof(uint2), 256);
+  l.vcount = p;     p += align_up(N * tiles * sizeof(int), 256);
+  l.uwork = p;      p += align_up(N * tiles * sizeof(int), 256);
+  l.uorder = p;     p += align_up(N * tiles * sizeof(int), 256);
   l.counter = p;    p += 256;
   l.total = p;
   return l;
@@ -1532,9 +1563,19 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
     const size_t slot = (size_t)(nt * 32) * sizeof(float) + ((small ? 1 : 2) * 32 + 2) * sizeof(uint4);
     // band rows hold two channels (float2 per pixel); a warp instruction touches one row, so
     // the pitch only has to keep rows 16-byte aligned
-    const int pitch2 = (a.width + 1) & ~1;
-    // every warp owns a private band of rows; two CTAs of kBwdWarps warps share an SM
+    // every warp owns a private tile of the plane; two CTAs of kBwdWarps warps share an SM
     const size_t per_warp = (((size_t)smem_optin + 1024) / 2 - 1024 - 64) / kBwdWarps / 16 * 16;
+    // A visit has a fixed cost (~45 % of the kernel's instructions at C2), and a ROI is visited
+    // by every tile it meets: full-width bands of a wide plane are only a few rows high and a
+    // typical ROI meets many of them.  Two column tiles of twice the height meet it less often
+    // (C2: 5.9 -> 3.8 visits per ROI); with bands of 8 rows and more the row work dominates
+    // and splitting the columns (= the lanes) only costs.
+    int ntx = 1, tile_cols = (a.width + 3) & ~3;
+    if (per_warp > slot && (per_warp - slot) / ((size_t)tile_cols * sizeof(float2)) < 8 && a.width >= 64) {
+      ntx = 2;
+      tile_cols = ((a.width + 1) / 2 + 3) & ~3;
+    }
+    const int pitch2 = tile_cols;
     const size_t row_bytes = (size_t)pitch2 * sizeof(float2);
     if (per_warp > slot + row_bytes && a.num_rois <= (1 << 20)) {
       int rows = (int)((per_warp - slot) / row_bytes);
@@ -1544,6 +1585,8 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
       plan->bwd_slab_rows = rows;
       plan->bwd_smem = (size_t)kBwdWarps * (rows * row_bytes + slot);
       plan->bwd_pitch2 = pitch2;
+      plan->bwd_ntx = ntx;
+      plan->bwd_tile_cols = tile_cols;
       plan->bwd_maxc = maxc;
       plan->bwd_maxe = maxe;
     }
@@ -1649,7 +1692,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
 }
 
 size_t resident_bwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan, int deterministic) {
-  return bwd_layout(a, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slabs, deterministic != 0).total;
+  return bwd_layout(a, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slabs, plan.bwd_ntx, deterministic != 0).total;
 }
 
 cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan, void* workspace,
@@ -1658,7 +1701,8 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   if (a.num_images == 0 || a.channels == 0) return cudaSuccess;
   const int nbands = plan.bwd_slabs;
   const bool det = deterministic != 0;
-  const BwdLayout l = bwd_layout(a, plan.bwd_maxe, plan.bwd_maxc, nbands, det);
+  const int ntx = plan.bwd_ntx;
+  const BwdLayout l = bwd_layout(a, plan.bwd_maxe, plan.bwd_maxc, nbands, ntx, det);
   char* base = (char*)workspace;
   int* img_start = (int*)(base + l.img_start);
   int* order = (int*)(base + l.order);
@@ -1667,6 +1711,7 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   uint4* cols = (uint4*)(base + l.cols);
   uint4* colw = (uint4*)(base + l.colw);
   void* extra = base + l.extra;
+  int2* crange = (int2*)(base + l.crange);
   uint2* visits = (uint2*)(base + l.visits);
   int* vcount = (int*)(base + l.vcount);
   int* uwork = (int*)(base + l.uwork);
@@ -1679,18 +1724,19 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     resident_bwd2d_table_kernel<<<tb, 128, 0, stream>>>(
         a.rois, order, img_start, a.num_images, a.num_rois, a.height, a.width, plan.bwd_pitch2 * 8, 8,
         a.pooled_h, a.pooled_w, a.scale, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slab_rows, nbands, (uint4*)rows,
-        bstart, cols, colw, (uint4*)extra, counter);
+        bstart, cols, colw, (uint4*)extra, crange, counter);
   else
     resident_bwd2_table_kernel<<<tb, 128, 0, stream>>>(
         a.rois, order, img_start, a.num_images, a.num_rois, a.height, a.width, plan.bwd_pitch2 * 8, 8,
         a.pooled_h, a.pooled_w, a.scale, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slab_rows, nbands, (uint2*)rows,
-        bstart, cols, (uint2*)extra, counter);
+        bstart, cols, (uint2*)extra, crange, counter);
   count_launch();
-  resident_bwd2_visits_kernel<<<a.num_images * nbands, kVisitThreads, 0, stream>>>(
-      order, img_start, bstart, a.num_images, a.num_rois, nbands, visits, vcount, uwork, uorder, counter);
+  resident_bwd2_visits_kernel<<<a.num_images * nbands * ntx, kVisitThreads, 0, stream>>>(
+      order, img_start, bstart, crange, a.num_images, a.num_rois, nbands, ntx, plan.bwd_tile_cols, visits, vcount,
+      uwork, uorder, counter);
   count_launch();
   const int cc = a.c_count > 0 ? a.c_count : a.channels;      // channels worked on (stride: a.channels)
-  const long long units = (long long)a.num_images * ((cc + 1) / 2) * nbands;
+  const long long units = (long long)a.num_images * ((cc + 1) / 2) * nbands * ntx;
   const long long cta_units = (units + kBwdWarps - 1) / kBwdWarps;
   unsigned grid = 0;
 #define MOBULA_BWD2(NT, NCK, NE, ACC, DET)                                                            \
@@ -1701,7 +1747,7 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     resident_bwd2_kernel<NT, NCK, NE, ACC, DET><<<grid, kBwdThreads, plan.bwd_smem, stream>>>(        \
         dy, dx, visits, vcount, uorder, rows, cols, colw, extra, img_start, counter, a.num_images,    \
         a.channels, cc, a.height, a.width, plan.bwd_pitch2, a.pooled_h, a.pooled_w, plan.bwd_maxe,    \
-        plan.bwd_maxc, nbands, plan.bwd_slab_rows);                                                   \
+        plan.bwd_maxc, nbands, plan.bwd_slab_rows, ntx, plan.bwd_tile_cols);                          \
   } while (0)
 #define MOBULA_BWD2_ACC(NT, NCK, NE)                                       \
   do {                                                                     \

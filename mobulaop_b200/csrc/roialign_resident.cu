@@ -677,22 +677,24 @@ constexpr int kMaxHitsPerCol = 16;    // = max pooled_w
 //   cols[j][maxc]   column records, one per touched column: x = col_off | nhits << 16 |
 //                   pw0 << 24 | pw1 << 28 (nhits = 0: unused slot), y = w0, z = w1, w = index of
 //                   the third hit in extra[j][]
-//   rows[j][maxe]   row entries sorted by feature-map row: x = row * row_bytes | ph (row_bytes is
-//                   a multiple of 16), y = merged row weight of bin row ph on that row
-//   bstart[b][j]    index of the first row entry in band b (rows [b * band_rows, ...)), for
-//                   b = 0 .. nbands; bstart[nbands][j] = number of entries
+//   rows[j][maxe]   bin-row records, 32 bytes each, sorted by (band, bin row): the <= 4 rows
+//                   of bin row ph that lie in one band.  First uint4: x = ph | rows << 4,
+//                   y = off0 | off1 << 16, z = off2 | off3 << 16 (byte offsets of the rows from
+//                   the band's first row); second uint4: the merged row weights
+//   bstart[b][j]    index of the first record of band b (rows [b * band_rows, ...)), for
+//                   b = 0 .. nbands; bstart[nbands][j] = number of records
 // and per (image, band) the ordered list of visits (roialign_bwd2_visits_kernel).
 // One warp per ROI: lanes decode the samples in parallel, lane 0 merges the column taps.
 __global__ void __launch_bounds__(128)
 resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
                            const int* __restrict__ img_start, int num_images, int num_rois, int height,
                            int width, int row_bytes, int col_bytes, int pooled_h, int pooled_w, float scale,
-                           int maxe, int maxc, int band_rows, int nbands, uint2* __restrict__ rows_out,
+                           int maxe, int maxc, int band_rows, int nbands, uint4* __restrict__ rows_out,
                            unsigned char* __restrict__ bstart, uint4* __restrict__ cols,
                            uint2* __restrict__ extra, int2* __restrict__ crange,
                            int* __restrict__ counter) {
-  __shared__ unsigned s_key[4][64], s_srow[4][64];
-  __shared__ float s_w[4][64];
+  __shared__ unsigned s_key[4][64], s_sband[4][64];
+  __shared__ uint4 s_ra[4][64], s_rb[4][64];
   __shared__ int s_lo[4][32], s_hi[4][32], s_pa[4][kMaxHitsPerCol], s_pb[4][kMaxHitsPerCol];
   __shared__ float s_fl[4][32], s_wa[4][kMaxHitsPerCol], s_wb[4][kMaxHitsPerCol];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -726,15 +728,26 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
       }
     }
   }
-  // exclusive prefix over the lanes -> position of this bin row's entries in the ROI's list
-  int incl = nrow;
+  // records of this bin row: runs of its (ascending) rows inside one band
+  int nrec = 0, rec_first[4] = {0, 0, 0, 0}, rec_n[4] = {0, 0, 0, 0};
+  for (int k = 0; k < nrow; ++k) {
+    if (nrec == 0 || rrow[k] / band_rows != rrow[rec_first[nrec - 1]] / band_rows) {
+      rec_first[nrec] = k;
+      rec_n[nrec] = 1;
+      ++nrec;
+    } else {
+      ++rec_n[nrec - 1];
+    }
+  }
+  // exclusive prefix over the lanes -> position of this bin row's records in the ROI's list
+  int incl = nrec;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const int v = __shfl_up_sync(0xffffffffu, incl, d);
     if (lane >= d) incl += v;
   }
   int ne = __shfl_sync(0xffffffffu, incl, 31);
-  const int base = incl - nrow;
+  const int base = incl - nrec;
 
   // ---- columns: sample column s = lane (pooled_w <= 16); lane 0 then walks them in order
   // with two open columns A (colA) and B (colA + 1) ----
@@ -810,33 +823,41 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   for (int k = ncols + lane; k < maxc; k += 32) crow[k] = make_uint4(0u, 0u, 0u, 0u);   // unused slots
   if (ncols == 0) {
     ne = 0;      // no column inside the plane: the ROI contributes nothing
-    nrow = 0;
+    nrec = 0;
   }
 
-  // ---- row entries, sorted by (band, bin row, row) so that the entries of a band are
-  // contiguous and a bin row's entries follow each other ----
-  for (int k = 0; k < nrow; ++k) {
-    s_key[wib][base + k] = (unsigned)((rrow[k] / band_rows) * 16 + lane) * 65536u + (unsigned)rrow[k];
-    s_w[wib][base + k] = rw[k];
+  // ---- bin-row records, sorted by (band, bin row) so that the records of a band are contiguous ----
+  for (int q = 0; q < nrec; ++q) {
+    const int k0 = rec_first[q], band = rrow[k0] / band_rows, r0 = band * band_rows;
+    unsigned off[4] = {0u, 0u, 0u, 0u};
+    float w[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int i = 0; i < rec_n[q]; ++i) {
+      off[i] = (unsigned)((rrow[k0 + i] - r0) * row_bytes);
+      w[i] = rw[k0 + i];
+    }
+    s_key[wib][base + q] = (unsigned)(band * 16 + lane);
+    s_ra[wib][base + q] = make_uint4((unsigned)lane | ((unsigned)rec_n[q] << 4), off[0] | (off[1] << 16),
+                                     off[2] | (off[3] << 16), 0u);
+    s_rb[wib][base + q] = make_uint4(__float_as_uint(w[0]), __float_as_uint(w[1]), __float_as_uint(w[2]),
+                                     __float_as_uint(w[3]));
   }
   __syncwarp();
-  uint2* rout = rows_out + (size_t)j * maxe;
+  uint4* rout = rows_out + (size_t)j * maxe * 2;
   for (int e = lane; e < ne; e += 32) {
     const unsigned key = s_key[wib][e];
     int rank = 0;
     for (int k = 0; k < ne; ++k) rank += s_key[wib][k] < key ? 1 : 0;
-    const unsigned row = key & 0xffffu, ph = (key >> 16) & 15u;
-    rout[rank] = make_uint2(row * (unsigned)row_bytes | ph, __float_as_uint(s_w[wib][e]));
-    s_srow[wib][rank] = row;
+    rout[2 * rank] = s_ra[wib][e];
+    rout[2 * rank + 1] = s_rb[wib][e];
+    s_sband[wib][rank] = key >> 4;
   }
   __syncwarp();
-  // first entry of every band: entries with row < b * band_rows (rows ascend with the rank)
+  // first record of every band (bands ascend with the rank)
   for (int bnd = lane; bnd <= nbands; bnd += 32) {
-    const unsigned limit = (unsigned)(bnd * band_rows);
     int lo = 0, hi = ne;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if (s_srow[wib][mid] < limit) lo = mid + 1;
+      if (s_sband[wib][mid] < (unsigned)bnd) lo = mid + 1;
       else hi = mid;
     }
     bstart[(size_t)bnd * num_rois + j] = (unsigned char)(bnd == nbands ? ne : lo);
@@ -1142,6 +1163,10 @@ __device__ __forceinline__ uint4 lds128(unsigned addr) {
                : "memory");
   return v;
 }
+__device__ __forceinline__ void sts128(unsigned addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ uint2 lds64u(unsigned addr) {
   uint2 v;
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
@@ -1149,16 +1174,9 @@ __device__ __forceinline__ uint2 lds64u(unsigned addr) {
 }
 
 // Everything a warp needs for one visit, fetched while the previous visit is computed: NT floats
-// of the dy tile pair per lane, NE row entries of the band, NCK column records.
-template <bool DET>
-struct RowEntry {
-  typedef uint2 type;       // merged: row | ph, weight
-};
-template <>
-struct RowEntry<true> {
-  typedef uint4 type;       // deterministic: row | ph, flags, weight iy = 0, weight iy = 1
-};
-
+// of the dy tile pair per lane, the band's records of the ROI (merged mode: one 32-byte bin-row
+// record per lane, at most 16; deterministic mode: NE 16-byte row entries), NCK column records.
+constexpr int kMaxVisitRecords = 16;     // = max pooled_h: a bin row has one record per band
 template <int NCK, bool DET>
 struct VisitCols {
   uint4 col[NCK];
@@ -1168,7 +1186,7 @@ struct VisitCols {
 template <int NT, int NCK, int NE, bool DET>
 struct VisitRegs {
   float g[NT];
-  typename RowEntry<DET>::type e[NE];
+  uint4 e[DET ? NE : 2];
   uint4 col[NCK];
   uint4 colw[DET ? NCK : 1];      // deterministic: the column weights
 };
@@ -1197,10 +1215,9 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
   constexpr unsigned kMaxE = NE * 32u, kMaxC = NCK * 32u;      // = maxe, maxc of the tables
   (void)maxe;
   (void)maxc;
-  typedef typename RowEntry<DET>::type Entry;
-  const Entry* rows_in = static_cast<const Entry*>(rows_v);
-  constexpr unsigned kEntry = (unsigned)sizeof(Entry);
-  const unsigned slot_bytes = (unsigned)(NT * 32) * 4u + (NE * 32u + 2u) * kEntry;   // + spare entries
+  const uint4* rows_in = static_cast<const uint4*>(rows_v);
+  const unsigned slot_bytes =
+      (unsigned)(NT * 32) * 4u + (DET ? (NE * 32u + 2u) * 16u : (unsigned)kMaxVisitRecords * 32u);
   const unsigned warp_bytes = (unsigned)band_rows * rb + slot_bytes;
   float2* band = reinterpret_cast<float2*>(smem_raw + (size_t)warp * warp_bytes);
   const unsigned sbase = ptx::smem_addr(band);
@@ -1268,9 +1285,15 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     const float* tile_ = dy_c + ((size_t)roi_ * cb + (unsigned)lane);                             \
     _Pragma("unroll") for (int i = 0; i < NT; ++i)                                                \
         if (tile_ok[i])(v).g[i] = __ldg(tile_ + 32 * i);                                          \
-    const Entry* er_ = rows_in + (jv_ * kMaxE + first_ + (unsigned)lane);                \
-    _Pragma("unroll") for (int i = 0; i < NE; ++i)                                                \
-        if ((unsigned)lane + 32u * i < cnt_)(v).e[i] = __ldg(er_ + 32 * i);                       \
+    if (DET) {                                                                                    \
+      const uint4* er_ = rows_in + (jv_ * kMaxE + first_ + (unsigned)lane);                       \
+      _Pragma("unroll") for (int i = 0; i < (DET ? NE : 0); ++i)                                  \
+          if ((unsigned)lane + 32u * i < cnt_)(v).e[i] = __ldg(er_ + 32 * i);                     \
+    } else if ((unsigned)lane < cnt_) {                                                           \
+      const uint4* er_ = rows_in + (size_t)(jv_ * kMaxE + first_ + (unsigned)lane) * 2;           \
+      (v).e[0] = __ldg(er_);                                                                      \
+      (v).e[1] = __ldg(er_ + 1);                                                                  \
+    }                                                                                             \
     const uint4* cr_ = cols + (jv_ * kMaxC + (unsigned)lane);                            \
     _Pragma("unroll") for (int i = 0; i < NCK; ++i)(v).col[i] = __ldg(cr_ + 32 * i);              \
     if (DET) {                                                                                    \
@@ -1285,18 +1308,14 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < NT; ++i) sts_at(tile_s + 128u * i, cur.g[i]);
+      if constexpr (DET) {
 #pragma unroll
-      for (int i = 0; i < NE; ++i)
-        if ((unsigned)lane + 32u * i < cnt) {
-          if constexpr (DET)
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(eslot_s + (lane + 32u * i) * 16u),
-                         "r"(cur.e[i].x), "r"(cur.e[i].y), "r"(cur.e[i].z), "r"(cur.e[i].w)
-                         : "memory");
-          else
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(eslot_s + (lane + 32u * i) * 8u),
-                         "r"(cur.e[i].x), "r"(cur.e[i].y)
-                         : "memory");
-        }
+        for (int i = 0; i < NE; ++i)
+          if ((unsigned)lane + 32u * i < cnt) sts128(eslot_s + (lane + 32u * i) * 16u, cur.e[i]);
+      } else if ((unsigned)lane < cnt) {
+        sts128(eslot_s + lane * 32u, cur.e[0]);
+        sts128(eslot_s + lane * 32u + 16u, cur.e[1]);
+      }
       __syncwarp();
     };
     // second half: every touched column (lane) adds its share to the band's rows
@@ -1356,46 +1375,45 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
         const int nh = (int)((cr.x >> 16) & 0xffu);
         // this lane has no column in this chunk, or its column belongs to another tile
         if (nh == 0 || (cr.x & 0xffffu) - tile_lo >= tile_span) continue;
-        const unsigned caddr = col_base + (cr.x & 0xffffu);
+        const unsigned caddr = sbase + ((cr.x & 0xffffu) - tile_lo);     // + row offset inside the band
         const unsigned g0 = slot_s + ((cr.x >> 24) & 0xfu) * 4u, g1 = slot_s + (cr.x >> 28) * 4u;
         const float w0 = __uint_as_float(cr.y), w1 = __uint_as_float(cr.z);
-        unsigned cur_ph = 0xffffffffu;
-        float2 t = make_float2(0.0f, 0.0f);
-        unsigned e = 0;
-        while (e < cnt) {
-          const uint2 re = lds64u(eslot_s + e * 8u);            // broadcast
-          const uint2 rn = lds64u(eslot_s + e * 8u + 8u);       // next entry (slot has room)
-          const unsigned ph = re.x & 15u;
-          if (ph != cur_ph) {                                   // warp-uniform
-            cur_ph = ph;
-            const unsigned grow = ph * (unsigned)pooled_w * 4u;
-            t.x = w0 * lds_vol(g0 + grow);
-            t.y = w0 * lds_vol(g0 + grow + ch1);
-            if (nh > 1) {
-              t.x = fmaf(w1, lds_vol(g1 + grow), t.x);
-              t.y = fmaf(w1, lds_vol(g1 + grow + ch1), t.y);
-              for (int x = 2; x < nh; ++x) {
-                const uint2 hx = __ldg(extra + (size_t)jcur * kMaxC + cr.w + (x - 2));
-                const unsigned ge = slot_s + hx.x * 4u + grow;
-                t.x = fmaf(__uint_as_float(hx.y), lds_vol(ge), t.x);
-                t.y = fmaf(__uint_as_float(hx.y), lds_vol(ge + ch1), t.y);
-              }
+        // one bin row at a time: T = sum_pw Wx[col][pw] * dy[ph][pw] for the channel pair, then
+        // its <= 4 rows in this band, all distinct: the read-modify-writes overlap
+        for (unsigned e = 0; e < cnt; ++e) {
+          const uint4 ra = lds128(eslot_s + e * 32u), rw = lds128(eslot_s + e * 32u + 16u);   // broadcasts
+          const unsigned grow = (ra.x & 15u) * (unsigned)pooled_w * 4u, nr = ra.x >> 4;
+          float2 t;
+          t.x = w0 * lds_vol(g0 + grow);
+          t.y = w0 * lds_vol(g0 + grow + ch1);
+          if (nh > 1) {
+            t.x = fmaf(w1, lds_vol(g1 + grow), t.x);
+            t.y = fmaf(w1, lds_vol(g1 + grow + ch1), t.y);
+            for (int x = 2; x < nh; ++x) {
+              const uint2 hx = __ldg(extra + (size_t)jcur * kMaxC + cr.w + (x - 2));
+              const unsigned ge = slot_s + hx.x * 4u + grow;
+              t.x = fmaf(__uint_as_float(hx.y), lds_vol(ge), t.x);
+              t.y = fmaf(__uint_as_float(hx.y), lds_vol(ge + ch1), t.y);
             }
           }
-          const unsigned a = caddr + (re.x & ~15u);
-          const float wy = __uint_as_float(re.y);
-          if (e + 1 < cnt && (rn.x & 15u) == ph) {
-            // two rows of one bin row: distinct addresses, the read-modify-writes overlap
-            const unsigned a2 = caddr + (rn.x & ~15u);
-            const float wy2 = __uint_as_float(rn.y);
-            const float2 v = lds64(a), v2 = lds64(a2);
-            sts64(a, make_float2(fmaf(wy, t.x, v.x), fmaf(wy, t.y, v.y)));
-            sts64(a2, make_float2(fmaf(wy2, t.x, v2.x), fmaf(wy2, t.y, v2.y)));
-            e += 2;
+          const unsigned a0 = caddr + (ra.y & 0xffffu), a1 = caddr + (ra.y >> 16);
+          const unsigned a2 = caddr + (ra.z & 0xffffu), a3 = caddr + (ra.z >> 16);
+          const float y0 = __uint_as_float(rw.x), y1 = __uint_as_float(rw.y);
+          const float y2 = __uint_as_float(rw.z), y3 = __uint_as_float(rw.w);
+          if (nr <= 2u) {                                   // warp-uniform
+            const float2 v0 = lds64(a0);
+            float2 v1 = make_float2(0.0f, 0.0f);
+            if (nr == 2u) v1 = lds64(a1);
+            sts64(a0, make_float2(fmaf(y0, t.x, v0.x), fmaf(y0, t.y, v0.y)));
+            if (nr == 2u) sts64(a1, make_float2(fmaf(y1, t.x, v1.x), fmaf(y1, t.y, v1.y)));
           } else {
-            const float2 v = lds64(a);
-            sts64(a, make_float2(fmaf(wy, t.x, v.x), fmaf(wy, t.y, v.y)));
-            e += 1;
+            const float2 v0 = lds64(a0), v1 = lds64(a1), v2 = lds64(a2);
+            float2 v3 = make_float2(0.0f, 0.0f);
+            if (nr == 4u) v3 = lds64(a3);
+            sts64(a0, make_float2(fmaf(y0, t.x, v0.x), fmaf(y0, t.y, v0.y)));
+            sts64(a1, make_float2(fmaf(y1, t.x, v1.x), fmaf(y1, t.y, v1.y)));
+            sts64(a2, make_float2(fmaf(y2, t.x, v2.x), fmaf(y2, t.y, v2.y)));
+            if (nr == 4u) sts64(a3, make_float2(fmaf(y3, t.x, v3.x), fmaf(y3, t.y, v3.y)));
           }
         }
       }
@@ -1491,7 +1509,7 @@ BwdLayout bwd_layout(const RoiAlignArgs& a, int maxe, int maxc, int nbands, int 
   const size_t R = (size_t)a.num_rois, N = (size_t)(a.num_images > 0 ? a.num_images : 0);
   l.img_start = p;  p += align_up((N + 2) * sizeof(int), 256);
   l.order = p;      p += align_up(R * sizeof(int), 256);
-  l.rows = p;       p += align_up(R * maxe * (det ? sizeof(uint4) : sizeof(uint2)), 256);
+  l.rows = p;       p += align_up(R * maxe * (det ? sizeof(uint4) : 2 * sizeof(uint4)), 256);   // merged: 32-byte records
   l.bstart = p;     p += align_up(R * (size_t)(nbands + 1), 256);
   l.cols = p;       p += align_up(R * maxc * sizeof(uint4), 256);
   l.colw = p;       p += det ? align_up(R * maxc * sizeof(uint4), 256) : 0;
@@ -1728,7 +1746,7 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   else
     resident_bwd2_table_kernel<<<tb, 128, 0, stream>>>(
         a.rois, order, img_start, a.num_images, a.num_rois, a.height, a.width, plan.bwd_pitch2 * 8, 8,
-        a.pooled_h, a.pooled_w, a.scale, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slab_rows, nbands, (uint2*)rows,
+        a.pooled_h, a.pooled_w, a.scale, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slab_rows, nbands, (uint4*)rows,
         bstart, cols, (uint2*)extra, crange, counter);
   count_launch();
   resident_bwd2_visits_kernel<<<a.num_images * nbands * ntx, kVisitThreads, 0, stream>>>(

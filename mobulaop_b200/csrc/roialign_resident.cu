@@ -1050,7 +1050,7 @@ resident_bwd2d_table_kernel(const float* __restrict__ rois, const int* __restric
 // The block that finishes last then orders the (image, band) pairs by work, heaviest first
 // (`uorder`): the main kernel's warps take units from a queue, and a unit is as long as its
 // band's visit list, so the long ones must start first for the warps to finish together.
-constexpr int kVisitThreads = 128;
+constexpr int kVisitThreads = 512;
 constexpr int kWorkBuckets = 64;
 __global__ void __launch_bounds__(kVisitThreads)
 resident_bwd2_visits_kernel(const int* __restrict__ order, const int* __restrict__ img_start,

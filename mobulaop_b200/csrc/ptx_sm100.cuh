@@ -82,5 +82,32 @@ __device__ __forceinline__ void bulk_wait_read() {
 // waits until every committed bulk store of this thread has completed
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- programmatic dependent launch: the kernels of one call are chained -------------------
+// A kernel launched with chained_launch() may be SCHEDULED while its predecessor in the stream
+// still runs (hiding the launch latency between the small table kernels and the main kernel);
+// chain_enter() at its very top holds it until the predecessor has completed and its writes
+// are visible, then lets the successor be scheduled in turn.  Launched the ordinary way both
+// instructions do nothing.
+__device__ __forceinline__ void chain_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 }  // namespace ptx
+
+template <typename... Params, typename... Args>
+inline cudaError_t chained_launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
 }  // namespace mobula_b200

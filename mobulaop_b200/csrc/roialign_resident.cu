@@ -62,6 +62,7 @@ resident_fwd_table_kernel(const float* __restrict__ rois, const int* __restrict_
                           const int* __restrict__ img_start, int num_images, int height, int width,
                           int pitch, int pooled_h, int pooled_w, float scale, int grid,
                           uint4* __restrict__ entries) {
+  ptx::chain_enter();
   const int per_roi = (pooled_h + pooled_w) * grid;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int valid = __ldg(img_start + num_images);
@@ -93,6 +94,7 @@ resident_fwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
                            const int* __restrict__ img_start, int num_images, int height, int width,
                            int pitch, int unit, int pooled_h, int pooled_w, float scale, int ypairs,
                            int xslots, uint2* __restrict__ entries) {
+  ptx::chain_enter();
   // `unit` = bytes per pixel of the shared-memory plane: 4, or 8 for a channel pair
   const int per_roi = 2 * ypairs + xslots;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,6 +247,7 @@ resident_fwd_kernel(const float* __restrict__ data, float* __restrict__ out, con
                     const int* __restrict__ img_start, const uint4* __restrict__ entries, int num_images,
                     int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w,
                     int accumulate, int vec16) {
+  ptx::chain_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* plane = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -369,6 +372,7 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
                      const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
                      int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w,
                      int vec16) {
+  ptx::chain_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* plane = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -521,6 +525,7 @@ __global__ void __launch_bounds__(kFwd2Threads, 1)
 resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                       const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
                       int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w) {
+  ptx::chain_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* plane = reinterpret_cast<float2*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -693,6 +698,7 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
                            unsigned char* __restrict__ bstart, uint4* __restrict__ cols,
                            uint2* __restrict__ extra, int2* __restrict__ crange,
                            int* __restrict__ counter) {
+  ptx::chain_enter();
   __shared__ unsigned s_key[4][64], s_sband[4][64];
   __shared__ uint4 s_ra[4][64], s_rb[4][64];
   __shared__ int s_lo[4][32], s_hi[4][32], s_pa[4][kMaxHitsPerCol], s_pb[4][kMaxHitsPerCol];
@@ -884,6 +890,7 @@ resident_bwd2d_table_kernel(const float* __restrict__ rois, const int* __restric
                             unsigned char* __restrict__ bstart, uint4* __restrict__ colh,
                             uint4* __restrict__ colw, uint4* __restrict__ extra, int2* __restrict__ crange,
                             int* __restrict__ counter) {
+  ptx::chain_enter();
   __shared__ unsigned s_key[4][64], s_srow[4][64], s_rfl[4][64];
   __shared__ float s_w0[4][64], s_w1[4][64];
   __shared__ int s_lo[4][32], s_hi[4][32];
@@ -1058,6 +1065,7 @@ resident_bwd2_visits_kernel(const int* __restrict__ order, const int* __restrict
                             int num_images, int num_rois, int nbands, int ntx, int tile_cols,
                             uint2* __restrict__ visits, int* __restrict__ vcount, int* __restrict__ uwork,
                             int* __restrict__ uorder, int* __restrict__ counter) {
+  ptx::chain_enter();
   __shared__ int s_warp[kVisitThreads / 32];
   __shared__ int s_entries, s_last, s_max, s_hist[kWorkBuckets];
   if (threadIdx.x == 0) s_entries = 0;
@@ -1206,6 +1214,7 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
                      const int* __restrict__ img_start, int* __restrict__ counter, int num_images,
                      int channels, int c_count, int height, int width, int pitch2, int pooled_h, int pooled_w,
                      int maxe, int maxc, int nbands, int band_rows, int ntx, int tile_cols) {
+  ptx::chain_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bins = pooled_h * pooled_w;
@@ -1636,7 +1645,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   if (plan.fwd_two) {
     uint2* entries = (uint2*)(base + l.entries);
     const long long threads = (long long)a.num_rois * (2 * plan.ypairs + plan.xslots);
-    resident_fwd2_table_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+    chained_launch(resident_fwd2_table_kernel, (unsigned)((threads + 255) / 256), 256, 0, stream, 
         a.rois, order, img_start, a.num_images, a.height, a.width, plan.pitch, plan.fwd_pair ? 8 : 4,
         a.pooled_h, a.pooled_w, a.scale, plan.ypairs, plan.xslots, entries);
     count_launch();
@@ -1646,7 +1655,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
       e = resident_grid(resident_fwd2p_kernel<ITERS, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms, \
                         (work + 1) / 2, &grid);                                                      \
       if (e != cudaSuccess) return e;                                                                \
-      resident_fwd2p_kernel<ITERS, NCH, ACC><<<grid, kFwd2Threads, plan.fwd_smem, stream>>>(         \
+      chained_launch(resident_fwd2p_kernel<ITERS, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream,          \
           data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,     \
           plan.pitch, a.pooled_h, a.pooled_w);                                                       \
       break;                                                                                         \
@@ -1654,7 +1663,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     e = resident_grid(resident_fwd2_kernel<ITERS, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms,   \
                       work, &grid);                                                                  \
     if (e != cudaSuccess) return e;                                                                  \
-    resident_fwd2_kernel<ITERS, NCH, ACC><<<grid, kFwd2Threads, plan.fwd_smem, stream>>>(            \
+    chained_launch(resident_fwd2_kernel<ITERS, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream,             \
         data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,       \
         plan.pitch, a.pooled_h, a.pooled_w, plan.vec16);                                          \
   } while (0)
@@ -1686,7 +1695,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   }
   uint4* entries = (uint4*)(base + l.entries);
   const long long threads = (long long)a.num_rois * plan.per_roi;
-  resident_fwd_table_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+  chained_launch(resident_fwd_table_kernel, (unsigned)((threads + 255) / 256), 256, 0, stream, 
       a.rois, order, img_start, a.num_images, a.height, a.width, plan.pitch, a.pooled_h, a.pooled_w,
       a.scale, plan.grid, entries);
   count_launch();
@@ -1694,7 +1703,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   do {                                                                                              \
     e = resident_grid(resident_fwd_kernel<G>, kFwdThreads, plan.fwd_smem, num_sms, work, &grid);    \
     if (e != cudaSuccess) return e;                                                                 \
-    resident_fwd_kernel<G><<<grid, kFwdThreads, plan.fwd_smem, stream>>>(                           \
+    chained_launch(resident_fwd_kernel<G>, grid, kFwdThreads, plan.fwd_smem, stream,                            \
         data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,      \
         plan.pitch, a.pooled_h, a.pooled_w, accumulate, plan.vec16);                             \
   } while (0)
@@ -1739,17 +1748,17 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   if (e != cudaSuccess) return e;
   const int tb = a.num_rois > 0 ? (a.num_rois + 3) / 4 : 1;       // one warp per ROI
   if (det)
-    resident_bwd2d_table_kernel<<<tb, 128, 0, stream>>>(
+    chained_launch(resident_bwd2d_table_kernel, tb, 128, 0, stream, 
         a.rois, order, img_start, a.num_images, a.num_rois, a.height, a.width, plan.bwd_pitch2 * 8, 8,
         a.pooled_h, a.pooled_w, a.scale, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slab_rows, nbands, (uint4*)rows,
         bstart, cols, colw, (uint4*)extra, crange, counter);
   else
-    resident_bwd2_table_kernel<<<tb, 128, 0, stream>>>(
+    chained_launch(resident_bwd2_table_kernel, tb, 128, 0, stream, 
         a.rois, order, img_start, a.num_images, a.num_rois, a.height, a.width, plan.bwd_pitch2 * 8, 8,
         a.pooled_h, a.pooled_w, a.scale, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slab_rows, nbands, (uint4*)rows,
         bstart, cols, (uint2*)extra, crange, counter);
   count_launch();
-  resident_bwd2_visits_kernel<<<a.num_images * nbands * ntx, kVisitThreads, 0, stream>>>(
+  chained_launch(resident_bwd2_visits_kernel, a.num_images * nbands * ntx, kVisitThreads, 0, stream, 
       order, img_start, bstart, crange, a.num_images, a.num_rois, nbands, ntx, plan.bwd_tile_cols, visits, vcount,
       uwork, uorder, counter);
   count_launch();
@@ -1762,7 +1771,7 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     e = resident_grid(resident_bwd2_kernel<NT, NCK, NE, ACC, DET>, kBwdThreads, plan.bwd_smem,        \
                       num_sms, cta_units, &grid);                                                     \
     if (e != cudaSuccess) return e;                                                                   \
-    resident_bwd2_kernel<NT, NCK, NE, ACC, DET><<<grid, kBwdThreads, plan.bwd_smem, stream>>>(        \
+    chained_launch(resident_bwd2_kernel<NT, NCK, NE, ACC, DET>, grid, kBwdThreads, plan.bwd_smem, stream,         \
         dy, dx, visits, vcount, uorder, rows, cols, colw, extra, img_start, counter, a.num_images,    \
         a.channels, cc, a.height, a.width, plan.bwd_pitch2, a.pooled_h, a.pooled_w, plan.bwd_maxe,    \
         plan.bwd_maxc, nbands, plan.bwd_slab_rows, ntx, plan.bwd_tile_cols);                          \

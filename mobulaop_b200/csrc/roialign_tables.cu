@@ -10,6 +10,7 @@
 // All arithmetic goes through roialign_common.cuh, i.e. rounds like the reference.
 #include "roialign_kernels.h"
 #include "roialign_common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace mobula_b200 {
 
@@ -49,6 +50,7 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T* total, T* warp_sums /*
 __global__ void __launch_bounds__(kGroupThreads)
 roi_group_kernel(const float* __restrict__ rois, int num_rois, int num_images,
                  int* __restrict__ img_start, int* __restrict__ order) {
+  ptx::chain_enter();
   __shared__ int warp_sums[kGroupThreads / 32];
   const int seg = blockIdx.x;
   int before = 0;
@@ -244,7 +246,7 @@ RoiTables roi_tables_carve(const RoiAlignArgs& a, unsigned need, int pitch, void
 
 cudaError_t launch_roi_group(const RoiAlignArgs& a, int* img_start, int* order, cudaStream_t stream) {
   if (a.num_rois == 0) return cudaMemsetAsync(img_start, 0, (size_t)(a.num_images + 2) * sizeof(int), stream);
-  roi_group_kernel<<<a.num_images + 1, kGroupThreads, 0, stream>>>(a.rois, a.num_rois, a.num_images,
+  chained_launch(roi_group_kernel, a.num_images + 1, kGroupThreads, 0, stream, a.rois, a.num_rois, a.num_images,
                                                                    img_start, order);
   count_launch();
   return cudaGetLastError();

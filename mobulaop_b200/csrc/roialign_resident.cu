@@ -701,8 +701,8 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   ptx::chain_enter();
   __shared__ unsigned s_key[4][64], s_sband[4][64];
   __shared__ uint4 s_ra[4][64], s_rb[4][64];
-  __shared__ int s_lo[4][32], s_hi[4][32], s_pa[4][kMaxHitsPerCol], s_pb[4][kMaxHitsPerCol];
-  __shared__ float s_fl[4][32], s_wa[4][kMaxHitsPerCol], s_wb[4][kMaxHitsPerCol];
+  __shared__ unsigned s_tkey[4][64], s_ckey[4][64];
+  __shared__ float s_tw[4][64], s_cw[4][64];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x * 4 + wib;
   if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = counter[1] = 0;   // unit queue, visit blocks done
@@ -755,8 +755,10 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   int ne = __shfl_sync(0xffffffffu, incl, 31);
   const int base = incl - nrec;
 
-  // ---- columns: sample column s = lane (pooled_w <= 16); lane 0 then walks them in order
-  // with two open columns A (colA) and B (colA + 1) ----
+  // ---- columns: sample column s = lane (pooled_w <= 16).  The even lane of a bin column
+  // merges the <= 4 taps of its two samples per touched column, the (column, bin column,
+  // weight) triples of the ROI are sorted, and a run of one column becomes a column record
+  // (two hits inline, the rest in the overflow list) -- every step across the lanes ----
   AxisTap mine;
   mine.valid = false;
   mine.lo = mine.hi = 0;
@@ -769,63 +771,104 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   }
   uint4* crow = cols + (size_t)j * maxc;
   uint2* erow = extra + (size_t)j * maxc;
-  int ncols = 0;
-  s_lo[wib][lane] = mine.valid ? mine.lo : -1;
-  s_hi[wib][lane] = mine.hi;
-  s_fl[wib][lane] = mine.wl;
-  __syncwarp();
-  if (lane == 0) {
-    int colA = -1, nA = 0, nB = 0, nextra = 0;
-    int* pA = s_pa[wib];
-    int* pB = s_pb[wib];
-    float* wA = s_wa[wib];
-    float* wB = s_wb[wib];
-    auto flushA = [&]() {
-      if (nA > 0 && colA < width) {
-        uint4 r;
-        r.x = (unsigned)(colA * col_bytes) | ((unsigned)nA << 16) | ((unsigned)pA[0] << 24) |
-              ((unsigned)(nA > 1 ? pA[1] : 0) << 28);
-        r.y = __float_as_uint(wA[0]);
-        r.z = __float_as_uint(nA > 1 ? wA[1] : 0.0f);
-        r.w = (unsigned)nextra;
-        for (int k = 2; k < nA; ++k) erow[nextra++] = make_uint2((unsigned)pA[k], __float_as_uint(wA[k]));
-        crow[ncols++] = r;
-      }
-      colA += 1;
-      nA = nB;
-      for (int k = 0; k < nB; ++k) {
-        pA[k] = pB[k];
-        wA[k] = wB[k];
-      }
-      nB = 0;
-    };
-    for (int s = 0; s < 2 * pooled_w; ++s) {
-      const int lo = s_lo[wib][s];
-      if (lo < 0) continue;
-      const int hi = s_hi[wib][s];
-      const float l = s_fl[wib][s], h = __fsub_rn(1.0f, l);
-      const int pw = s >> 1;
-      if (colA < 0) colA = lo;
-      while (colA < lo) {
-        if (nA == 0 && nB == 0) {
-          colA = lo;             // nothing open: jump
-          break;
-        }
-        flushA();
-      }
+  (void)col_bytes;
+  int tcol[4] = {0, 0, 0, 0}, ntap = 0;
+  float tw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  {
+    // the odd sample of the bin column comes over from the next lane
+    const int o_valid = __shfl_down_sync(0xffffffffu, mine.valid ? 1 : 0, 1);
+    const int o_lo = __shfl_down_sync(0xffffffffu, mine.lo, 1), o_hi = __shfl_down_sync(0xffffffffu, mine.hi, 1);
+    const float o_l = __shfl_down_sync(0xffffffffu, mine.wl, 1);
+    if ((lane & 1) == 0 && lane < 2 * pooled_w) {
+      auto add = [&](int col, float w) {
+        for (int k = 0; k < ntap; ++k)
+          if (tcol[k] == col) {
+            tw[k] += w;
+            return;
+          }
+        tcol[ntap] = col;
+        tw[ntap] = w;
+        ++ntap;
+      };
       // 1/count folded into the column weights: count = 4, an exact scaling
-      const float wlo = __fmul_rn(h, 0.25f), whi = __fmul_rn(l, 0.25f);
-      if (nA > 0 && pA[nA - 1] == pw) wA[nA - 1] += wlo;
-      else { pA[nA] = pw; wA[nA] = wlo; ++nA; }
-      if (hi != lo) {            // the clamped sample has no second column (its weight is 0)
-        if (nB > 0 && pB[nB - 1] == pw) wB[nB - 1] += whi;
-        else { pB[nB] = pw; wB[nB] = whi; ++nB; }
+      auto sample = [&](int lo, int hi, float l) {
+        add(lo, __fmul_rn(__fsub_rn(1.0f, l), 0.25f));
+        if (hi != lo) add(hi, __fmul_rn(l, 0.25f));      // the clamped sample has no second column
+      };
+      if (mine.valid) sample(mine.lo, mine.hi, mine.wl);
+      if (o_valid) sample(o_lo, o_hi, o_l);
+    }
+  }
+  int tincl = ntap;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, tincl, d);
+    if (lane >= d) tincl += v;
+  }
+  const int nt = __shfl_sync(0xffffffffu, tincl, 31);      // <= 4 * pooled_w <= 64 triples
+  for (int k = 0; k < ntap; ++k) {
+    s_tkey[wib][tincl - ntap + k] = (unsigned)tcol[k] * 16u + (unsigned)(lane >> 1);
+    s_tw[wib][tincl - ntap + k] = tw[k];
+  }
+  __syncwarp();
+  for (int e = lane; e < nt; e += 32) {                     // rank sort by (column, bin column): keys are unique
+    const unsigned key = s_tkey[wib][e];
+    int rank = 0;
+    for (int k = 0; k < nt; ++k) rank += s_tkey[wib][k] < key ? 1 : 0;
+    s_ckey[wib][rank] = key;
+    s_cw[wib][rank] = s_tw[wib][e];
+  }
+  __syncwarp();
+  int ncols = 0;
+  {
+    // triple i = lane (+ 32): head of its column's run?  position in the run?  overflow hits before it?
+    unsigned heads[2], more[2];
+    int run_pos[2];
+#pragma unroll
+    for (int hset = 0; hset < 2; ++hset) {
+      const int i = lane + 32 * hset;
+      const bool in = i < nt;
+      const bool head = in && (i == 0 || (s_ckey[wib][i - 1] >> 4) != (s_ckey[wib][i] >> 4));
+      heads[hset] = __ballot_sync(0xffffffffu, head);
+    }
+    const unsigned le = 0xffffffffu >> (31 - lane);          // lanes <= this one
+#pragma unroll
+    for (int hset = 0; hset < 2; ++hset) {
+      const int i = lane + 32 * hset;
+      int h;                                                  // index of the run's head
+      if (hset == 1 && (heads[1] & le)) h = 32 + 31 - __clz(heads[1] & le);
+      else h = 31 - __clz(hset == 1 ? heads[0] : (heads[0] & le));
+      run_pos[hset] = i - h;
+      more[hset] = __ballot_sync(0xffffffffu, i < nt && run_pos[hset] >= 2);
+    }
+    ncols = __popc(heads[0]) + __popc(heads[1]);
+    const unsigned lt = le >> 1;                              // lanes < this one
+#pragma unroll
+    for (int hset = 0; hset < 2; ++hset) {
+      const int i = lane + 32 * hset;
+      if (i >= nt) continue;
+      const unsigned key = s_ckey[wib][i];
+      const int before = hset == 0 ? __popc(more[0] & lt) : __popc(more[0]) + __popc(more[1] & lt);
+      if (run_pos[hset] >= 2) {
+        erow[before] = make_uint2(key & 15u, __float_as_uint(s_cw[wib][i]));
+      } else if (run_pos[hset] == 0) {
+        // length of the run: up to the next head
+        unsigned above = hset == 0 ? (heads[0] & ~le) : 0u, above1 = hset == 0 ? heads[1] : (heads[1] & ~le);
+        int next = nt;
+        if (above) next = __ffs(above) - 1;
+        else if (above1) next = 32 + __ffs(above1) - 1;
+        const int nh = next - i;
+        const int slot = hset == 0 ? __popc(heads[0] & lt) : __popc(heads[0]) + __popc(heads[1] & lt);
+        uint4 r;
+        r.x = (key >> 4) * 8u | ((unsigned)nh << 16) | ((key & 15u) << 24) |
+              ((nh > 1 ? s_ckey[wib][i + 1] & 15u : 0u) << 28);
+        r.y = __float_as_uint(s_cw[wib][i]);
+        r.z = __float_as_uint(nh > 1 ? s_cw[wib][i + 1] : 0.0f);
+        r.w = (unsigned)before;                               // its overflow hits start here
+        crow[slot] = r;
       }
     }
-    flushA();
-    flushA();
   }
-  ncols = __shfl_sync(0xffffffffu, ncols, 0);
   for (int k = ncols + lane; k < maxc; k += 32) crow[k] = make_uint4(0u, 0u, 0u, 0u);   // unused slots
   if (ncols == 0) {
     ne = 0;      // no column inside the plane: the ROI contributes nothing

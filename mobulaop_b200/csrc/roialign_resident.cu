@@ -678,92 +678,14 @@ constexpr int kBwdThreads = kBwdWarps * 32;
 constexpr int kMaxSlotFloats = 256;   // dy tile of one (roi, channel): PH * PW <= 256 floats
 constexpr int kMaxHitsPerCol = 16;    // = max pooled_w
 
-// Tables of the backward, per ROI at grouped position j (channel independent):
-//   cols[j][maxc]   column records, one per touched column: x = col_off | nhits << 16 |
-//                   pw0 << 24 | pw1 << 28 (nhits = 0: unused slot), y = w0, z = w1, w = index of
-//                   the third hit in extra[j][]
-//   rows[j][maxe]   bin-row records, 32 bytes each, sorted by (band, bin row): the <= 4 rows
-//                   of bin row ph that lie in one band.  First uint4: x = ph | rows << 4,
-//                   y = off0 | off1 << 16, z = off2 | off3 << 16 (byte offsets of the rows from
-//                   the band's first row); second uint4: the merged row weights
-//   bstart[b][j]    index of the first record of band b (rows [b * band_rows, ...)), for
-//                   b = 0 .. nbands; bstart[nbands][j] = number of records
-// and per (image, band) the ordered list of visits (roialign_bwd2_visits_kernel).
-// One warp per ROI: lanes decode the samples in parallel, lane 0 merges the column taps.
-__global__ void __launch_bounds__(128)
-resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
-                           const int* __restrict__ img_start, int num_images, int num_rois, int height,
-                           int width, int row_bytes, int col_bytes, int pooled_h, int pooled_w, float scale,
-                           int maxe, int maxc, int band_rows, int nbands, uint4* __restrict__ rows_out,
-                           unsigned char* __restrict__ bstart, uint4* __restrict__ cols,
-                           uint2* __restrict__ extra, int2* __restrict__ crange,
-                           int* __restrict__ counter) {
-  ptx::chain_enter();
-  __shared__ unsigned s_key[4][64], s_sband[4][64];
-  __shared__ uint4 s_ra[4][64], s_rb[4][64];
-  __shared__ unsigned s_tkey[4][64], s_ckey[4][64];
-  __shared__ float s_tw[4][64], s_cw[4][64];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 4 + wib;
-  if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = counter[1] = 0;   // unit queue, visit blocks done
-  const int valid = __ldg(img_start + num_images);
-  if (j >= valid) return;
-  const int roi = __ldg(order + j);
-  const RoiGeom g = roi_decode(rois + (size_t)roi * 5, scale, pooled_h, pooled_w, 2);
-
-  // ---- rows: bin row `lane` touches <= 4 distinct rows (ascending), weights merged ----
-  int nrow = 0, rrow[4] = {0, 0, 0, 0};
-  float rw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  if (lane < pooled_h) {
-    auto add = [&](int row, float w) {
-      for (int k = 0; k < nrow; ++k)
-        if (rrow[k] == row) {
-          rw[k] += w;
-          return;
-        }
-      rrow[nrow] = row;
-      rw[nrow] = w;
-      ++nrow;
-    };
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const AxisTap t = axis_decode(sample_pos(g.start_h, lane, g.bin_h, i, 2), height);
-      if (t.valid) {
-        add(t.lo, t.wh);
-        if (t.hi != t.lo) add(t.hi, t.wl);     // the clamped sample has no second row
-      }
-    }
-  }
-  // records of this bin row: runs of its (ascending) rows inside one band
-  int nrec = 0, rec_first[4] = {0, 0, 0, 0}, rec_n[4] = {0, 0, 0, 0};
-  for (int k = 0; k < nrow; ++k) {
-    if (nrec == 0 || rrow[k] / band_rows != rrow[rec_first[nrec - 1]] / band_rows) {
-      rec_first[nrec] = k;
-      rec_n[nrec] = 1;
-      ++nrec;
-    } else {
-      ++rec_n[nrec - 1];
-    }
-  }
-  // exclusive prefix over the lanes -> position of this bin row's records in the ROI's list
-  int incl = nrec;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  int ne = __shfl_sync(0xffffffffu, incl, 31);
-  const int base = incl - nrec;
-
-  // ---- columns: sample column s = lane (pooled_w <= 16).  The even lane of a bin column
-  // merges the <= 4 taps of its two samples per touched column, the (column, bin column,
-  // weight) triples of the ROI are sorted, and a run of one column becomes a column record
-  // (two hits inline, the rest in the overflow list) -- every step across the lanes ----
-  AxisTap mine;
-  mine.valid = false;
-  mine.lo = mine.hi = 0;
-  mine.wl = mine.wh = 0.0f;
-  if (lane < 2 * pooled_w) mine = axis_decode(sample_pos(g.start_w, lane >> 1, g.bin_w, lane & 1, 2), width);
+// Column records of one ROI (see the table kernel below): `mine` = the sample column of this
+// lane.  The even lane of a bin column merges the <= 4 taps of its two samples per touched
+// column, the (column, bin column, weight) triples of the ROI are sorted, and a run of one
+// column becomes a column record (two hits inline, the rest in the overflow list).
+__device__ __forceinline__ void bwd2_column_records(const AxisTap& mine, int lane, int wib, int j, int pooled_w,
+                                                    int maxc, uint4* __restrict__ cols, uint2* __restrict__ extra,
+                                                    int2* __restrict__ crange, unsigned (*s_tkey)[64],
+                                                    unsigned (*s_ckey)[64], float (*s_tw)[64], float (*s_cw)[64]) {
   {   // the columns this ROI touches: which column tiles have to visit it
     const int cmin = __reduce_min_sync(0xffffffffu, mine.valid ? mine.lo : 0x7fffffff);
     const int cmax = __reduce_max_sync(0xffffffffu, mine.valid ? mine.hi : -1);
@@ -771,7 +693,6 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   }
   uint4* crow = cols + (size_t)j * maxc;
   uint2* erow = extra + (size_t)j * maxc;
-  (void)col_bytes;
   int tcol[4] = {0, 0, 0, 0}, ntap = 0;
   float tw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   {
@@ -870,8 +791,100 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
     }
   }
   for (int k = ncols + lane; k < maxc; k += 32) crow[k] = make_uint4(0u, 0u, 0u, 0u);   // unused slots
-  if (ncols == 0) {
-    ne = 0;      // no column inside the plane: the ROI contributes nothing
+}
+
+// Tables of the backward, per ROI at grouped position j (channel independent):
+//   cols[j][maxc]   column records, one per touched column: x = col_off | nhits << 16 |
+//                   pw0 << 24 | pw1 << 28 (nhits = 0: unused slot), y = w0, z = w1, w = index of
+//                   the third hit in extra[j][]
+//   rows[j][maxe]   bin-row records, 32 bytes each, sorted by (band, bin row): the <= 4 rows
+//                   of bin row ph that lie in one band.  First uint4: x = ph | rows << 4,
+//                   y = off0 | off1 << 16, z = off2 | off3 << 16 (byte offsets of the rows from
+//                   the band's first row); second uint4: the merged row weights
+//   bstart[b][j]    index of the first record of band b (rows [b * band_rows, ...)), for
+//                   b = 0 .. nbands; bstart[nbands][j] = number of records
+// and per (image, band) the ordered list of visits (roialign_bwd2_visits_kernel).
+// Two warps per ROI, every step across the lanes: one warp builds the bin-row records, the other
+// one the column records.
+__global__ void __launch_bounds__(256)
+resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
+                           const int* __restrict__ img_start, int num_images, int num_rois, int height,
+                           int width, int row_bytes, int col_bytes, int pooled_h, int pooled_w, float scale,
+                           int maxe, int maxc, int band_rows, int nbands, uint4* __restrict__ rows_out,
+                           unsigned char* __restrict__ bstart, uint4* __restrict__ cols,
+                           uint2* __restrict__ extra, int2* __restrict__ crange,
+                           int* __restrict__ counter) {
+  ptx::chain_enter();
+  __shared__ unsigned s_key[4][64], s_sband[4][64];
+  __shared__ uint4 s_ra[4][64], s_rb[4][64];
+  __shared__ unsigned s_tkey[4][64], s_ckey[4][64];
+  __shared__ float s_tw[4][64], s_cw[4][64];
+  const int wib = threadIdx.x >> 6, lane = threadIdx.x & 31;
+  const bool column_warp = (threadIdx.x >> 5) & 1;
+  const int j = blockIdx.x * 4 + wib;
+  if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = counter[1] = 0;   // unit queue, visit blocks done
+  const int valid = __ldg(img_start + num_images);
+  if (j >= valid) return;
+  const int roi = __ldg(order + j);
+  const RoiGeom g = roi_decode(rois + (size_t)roi * 5, scale, pooled_h, pooled_w, 2);
+  AxisTap mine;
+  mine.valid = false;
+  mine.lo = mine.hi = 0;
+  mine.wl = mine.wh = 0.0f;
+  if (lane < 2 * pooled_w) mine = axis_decode(sample_pos(g.start_w, lane >> 1, g.bin_w, lane & 1, 2), width);
+  if (column_warp) {
+    bwd2_column_records(mine, lane, wib, j, pooled_w, maxc, cols, extra, crange, s_tkey, s_ckey, s_tw, s_cw);
+    return;
+  }
+  // no column inside the plane: the ROI contributes nothing
+  const bool has_columns = __any_sync(0xffffffffu, mine.valid);
+
+  // ---- rows: bin row `lane` touches <= 4 distinct rows (ascending), weights merged ----
+  int nrow = 0, rrow[4] = {0, 0, 0, 0};
+  float rw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (lane < pooled_h) {
+    auto add = [&](int row, float w) {
+      for (int k = 0; k < nrow; ++k)
+        if (rrow[k] == row) {
+          rw[k] += w;
+          return;
+        }
+      rrow[nrow] = row;
+      rw[nrow] = w;
+      ++nrow;
+    };
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const AxisTap t = axis_decode(sample_pos(g.start_h, lane, g.bin_h, i, 2), height);
+      if (t.valid) {
+        add(t.lo, t.wh);
+        if (t.hi != t.lo) add(t.hi, t.wl);     // the clamped sample has no second row
+      }
+    }
+  }
+  // records of this bin row: runs of its (ascending) rows inside one band
+  int nrec = 0, rec_first[4] = {0, 0, 0, 0}, rec_n[4] = {0, 0, 0, 0};
+  for (int k = 0; k < nrow; ++k) {
+    if (nrec == 0 || rrow[k] / band_rows != rrow[rec_first[nrec - 1]] / band_rows) {
+      rec_first[nrec] = k;
+      rec_n[nrec] = 1;
+      ++nrec;
+    } else {
+      ++rec_n[nrec - 1];
+    }
+  }
+  // exclusive prefix over the lanes -> position of this bin row's records in the ROI's list
+  int incl = nrec;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  int ne = __shfl_sync(0xffffffffu, incl, 31);
+  const int base = incl - nrec;
+
+  if (!has_columns) {
+    ne = 0;
     nrec = 0;
   }
 
@@ -1796,7 +1809,7 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
         a.pooled_h, a.pooled_w, a.scale, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slab_rows, nbands, (uint4*)rows,
         bstart, cols, colw, (uint4*)extra, crange, counter);
   else
-    chained_launch(resident_bwd2_table_kernel, tb, 128, 0, stream, 
+    chained_launch(resident_bwd2_table_kernel, tb, 256, 0, stream, 
         a.rois, order, img_start, a.num_images, a.num_rois, a.height, a.width, plan.bwd_pitch2 * 8, 8,
         a.pooled_h, a.pooled_w, a.scale, plan.bwd_maxe, plan.bwd_maxc, plan.bwd_slab_rows, nbands, (uint4*)rows,
         bstart, cols, (uint2*)extra, crange, counter);

@@ -200,6 +200,8 @@ ODD_SHAPES = [
     (2, 4, 33, 36, 19, (1, 1), 0.5, 2),        # a single bin
     (2, 2, 18, 20, 9, (9, 3), 0.5, 2),         # PH > 8, PW small: mixed table sizes
     (1, 7, 150, 200, 40, (7, 7), 0.25, 2),     # tall plane: many row bands per plane
+    (1, 3, 37, 271, 30, (7, 7), 0.25, 2),      # wide plane, odd width: two column tiles, the second ragged
+    (1, 2, 30, 300, 25, (14, 14), 0.25, 2),    # two column tiles with two chunks of column records
     (2, 3, 24, 28, 11, (7, 7), 0.25, 1),       # generic resident forward, sr 1
     (2, 3, 24, 28, 11, (5, 6), 0.25, 4),       # ... sr 4
 ]

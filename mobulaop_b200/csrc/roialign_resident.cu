@@ -793,7 +793,7 @@ __device__ __forceinline__ void bwd2_column_records(const AxisTap& mine, int lan
   for (int k = ncols + lane; k < maxc; k += 32) crow[k] = make_uint4(0u, 0u, 0u, 0u);   // unused slots
 }
 
-// Tables of the backward, per ROI at grouped position j (channel independent):
+// Tables of the backward, per ROI row j (channel independent):
 //   cols[j][maxc]   column records, one per touched column: x = col_off | nhits << 16 |
 //                   pw0 << 24 | pw1 << 28 (nhits = 0: unused slot), y = w0, z = w1, w = index of
 //                   the third hit in extra[j][]
@@ -807,8 +807,8 @@ __device__ __forceinline__ void bwd2_column_records(const AxisTap& mine, int lan
 // Two warps per ROI, every step across the lanes: one warp builds the bin-row records, the other
 // one the column records.
 __global__ void __launch_bounds__(256)
-resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
-                           const int* __restrict__ img_start, int num_images, int num_rois, int height,
+resident_bwd2_table_kernel(const float* __restrict__ rois, int* __restrict__ order,
+                           int* __restrict__ img_start, int num_images, int num_rois, int height,
                            int width, int row_bytes, int col_bytes, int pooled_h, int pooled_w, float scale,
                            int maxe, int maxc, int band_rows, int nbands, uint4* __restrict__ rows_out,
                            unsigned char* __restrict__ bstart, uint4* __restrict__ cols,
@@ -819,13 +819,19 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   __shared__ uint4 s_ra[4][64], s_rb[4][64];
   __shared__ unsigned s_tkey[4][64], s_ckey[4][64];
   __shared__ float s_tw[4][64], s_cw[4][64];
+  if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = counter[1] = 0;   // unit queue, visit blocks done
+  // the first num_images + 1 blocks group the ROI rows by image (nobody in this launch reads
+  // the result), the others build the tables, indexed by ROI ROW
+  if ((int)blockIdx.x <= num_images) {
+    __shared__ int s_sums[8];
+    roi_group_block<256>(rois, num_rois, num_images, blockIdx.x, img_start, order, s_sums);
+    return;
+  }
   const int wib = threadIdx.x >> 6, lane = threadIdx.x & 31;
   const bool column_warp = (threadIdx.x >> 5) & 1;
-  const int j = blockIdx.x * 4 + wib;
-  if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = counter[1] = 0;   // unit queue, visit blocks done
-  const int valid = __ldg(img_start + num_images);
-  if (j >= valid) return;
-  const int roi = __ldg(order + j);
+  const int j = ((int)blockIdx.x - num_images - 1) * 4 + wib;          // the ROI row
+  if (j >= num_rois || segment_of(rois, j, num_images) == num_images) return;
+  const int roi = j;
   const RoiGeom g = roi_decode(rois + (size_t)roi * 5, scale, pooled_h, pooled_w, 2);
   AxisTap mine;
   mine.valid = false;
@@ -939,8 +945,8 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
 // A clamped sample (low = high tap, bilinear.h:32-44) keeps only its low tap: the high one has
 // weight 0 and adding +-0 never changes a sum that started at +0.
 __global__ void __launch_bounds__(128)
-resident_bwd2d_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
-                            const int* __restrict__ img_start, int num_images, int num_rois, int height,
+resident_bwd2d_table_kernel(const float* __restrict__ rois, int* __restrict__ order,
+                            int* __restrict__ img_start, int num_images, int num_rois, int height,
                             int width, int row_bytes, int col_bytes, int pooled_h, int pooled_w, float scale,
                             int maxe, int maxc, int band_rows, int nbands, uint4* __restrict__ rows_out,
                             unsigned char* __restrict__ bstart, uint4* __restrict__ colh,
@@ -954,12 +960,16 @@ resident_bwd2d_table_kernel(const float* __restrict__ rois, const int* __restric
   // open columns A / B of the merge: per hit (pw, flags, weight ix=0, weight ix=1)
   __shared__ int s_pw[4][2][kMaxHitsPerCol], s_cf[4][2][kMaxHitsPerCol];
   __shared__ float s_c0[4][2][kMaxHitsPerCol], s_c1[4][2][kMaxHitsPerCol];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 4 + wib;
   if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = counter[1] = 0;   // unit queue, visit blocks done
-  const int valid = __ldg(img_start + num_images);
-  if (j >= valid) return;
-  const int roi = __ldg(order + j);
+  if ((int)blockIdx.x <= num_images) {       // grouping blocks, see resident_bwd2_table_kernel
+    __shared__ int s_sums[4];
+    roi_group_block<128>(rois, num_rois, num_images, blockIdx.x, img_start, order, s_sums);
+    return;
+  }
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = ((int)blockIdx.x - num_images - 1) * 4 + wib;          // the ROI row
+  if (j >= num_rois || segment_of(rois, j, num_images) == num_images) return;
+  const int roi = j;
   const RoiGeom g = roi_decode(rois + (size_t)roi * 5, scale, pooled_h, pooled_w, 2);
 
   // ---- rows ----
@@ -1109,7 +1119,7 @@ resident_bwd2d_table_kernel(const float* __restrict__ rois, const int* __restric
 
 // One block per (image, band): the visits of the band, in ROI order.  Thread t owns a
 // contiguous run of the image's ROIs; a block-wide prefix sum places its visits.
-// visit = x: grouped position | first entry << 20 | (entries - 1) << 26; y: roi row
+// visit = x: roi row | first entry << 20 | (entries - 1) << 26; y: roi row
 // The block that finishes last then orders the (image, band) pairs by work, heaviest first
 // (`uorder`): the main kernel's warps take units from a queue, and a unit is as long as its
 // band's visit list, so the long ones must start first for the warps to finish together.
@@ -1136,14 +1146,15 @@ resident_bwd2_visits_kernel(const int* __restrict__ order, const int* __restrict
   const unsigned char* s1 = s0 + num_rois;
   const int per = (nroi + kVisitThreads - 1) / kVisitThreads;
   const int jb = min(nroi, t * per), je = min(nroi, jb + per);
-  auto meets = [&](int j) {
-    if (s1[j] <= s0[j]) return false;
+  // (the tables are indexed by ROI row r = order[j])
+  auto meets = [&](int r) {
+    if (s1[r] <= s0[r]) return false;
     if (ntx == 1) return true;
-    const int2 cr = crange[j];
+    const int2 cr = crange[r];
     return cr.y >= c0 && cr.x < c1;
   };
   int mine = 0;
-  for (int jj = jb; jj < je; ++jj) mine += meets(j0 + jj) ? 1 : 0;
+  for (int jj = jb; jj < je; ++jj) mine += meets(__ldg(order + j0 + jj)) ? 1 : 0;
   int incl = mine;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -1160,11 +1171,11 @@ resident_bwd2_visits_kernel(const int* __restrict__ order, const int* __restrict
   }
   int entries = 0;
   for (int jj = jb; jj < je; ++jj) {
-    const int j = j0 + jj;
-    const int first = s0[j], cnt = s1[j] - first;
-    if (meets(j)) {
-      list[before++] = make_uint2((unsigned)j | ((unsigned)first << 20) | ((unsigned)(cnt - 1) << 26),
-                                  (unsigned)__ldg(order + j));
+    const int r = __ldg(order + j0 + jj);
+    const int first = s0[r], cnt = s1[r] - first;
+    if (meets(r)) {
+      list[before++] = make_uint2((unsigned)r | ((unsigned)first << 20) | ((unsigned)(cnt - 1) << 26),
+                                  (unsigned)r);
       entries += cnt;
     }
   }
@@ -1800,9 +1811,9 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   int* uwork = (int*)(base + l.uwork);
   int* uorder = (int*)(base + l.uorder);
   int* counter = (int*)(base + l.counter);
-  cudaError_t e = launch_roi_group(a, img_start, order, stream);
-  if (e != cudaSuccess) return e;
-  const int tb = a.num_rois > 0 ? (a.num_rois + 3) / 4 : 1;       // one warp per ROI
+  cudaError_t e = cudaSuccess;
+  // grouping blocks (one per image + one for the rows with an invalid batch index), then four ROIs per block
+  const int tb = a.num_images + 1 + (a.num_rois + 3) / 4;
   if (det)
     chained_launch(resident_bwd2d_table_kernel, tb, 128, 0, stream, 
         a.rois, order, img_start, a.num_images, a.num_rois, a.height, a.width, plan.bwd_pitch2 * 8, 8,

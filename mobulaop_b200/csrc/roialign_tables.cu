@@ -19,58 +19,12 @@ namespace {
 constexpr int kGroupThreads = 1024;
 constexpr int kRecThreads = 1024;
 
-__device__ __forceinline__ int segment_of(const float* __restrict__ rois, int r, int num_images) {
-  const int b = __float2int_rz(__ldg(rois + (size_t)r * 5));
-  return (b >= 0 && b < num_images) ? b : num_images;
-}
-
-// block-wide exclusive prefix sum of one value per thread; returns the block total too
-template <int THREADS, typename T>
-__device__ __forceinline__ T block_exclusive_scan(T v, T* total, T* warp_sums /* [THREADS/32] */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T incl = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const T n = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += n;
-  }
-  if (lane == 31) warp_sums[warp] = incl;
-  __syncthreads();
-  T warp_prefix = 0, all = 0;
-  for (int w = 0; w < THREADS / 32; ++w) {
-    const T s = warp_sums[w];
-    if (w < warp) warp_prefix += s;
-    all += s;
-  }
-  __syncthreads();
-  *total = all;
-  return warp_prefix + incl - v;
-}
-
 __global__ void __launch_bounds__(kGroupThreads)
 roi_group_kernel(const float* __restrict__ rois, int num_rois, int num_images,
                  int* __restrict__ img_start, int* __restrict__ order) {
   ptx::chain_enter();
   __shared__ int warp_sums[kGroupThreads / 32];
-  const int seg = blockIdx.x;
-  int before = 0;
-  for (int r = threadIdx.x; r < num_rois; r += kGroupThreads)
-    before += segment_of(rois, r, num_images) < seg ? 1 : 0;
-  int start;
-  block_exclusive_scan<kGroupThreads>(before, &start, warp_sums);
-  int running = start;
-  for (int base = 0; base < num_rois; base += kGroupThreads) {
-    const int r = base + threadIdx.x;
-    const int mine = (r < num_rois && segment_of(rois, r, num_images) == seg) ? 1 : 0;
-    int total;
-    const int pos = block_exclusive_scan<kGroupThreads>(mine, &total, warp_sums);
-    if (mine) order[running + pos] = r;
-    running += total;
-  }
-  if (threadIdx.x == 0) {
-    img_start[seg] = start;
-    if (seg == num_images) img_start[seg + 1] = num_rois;
-  }
+  roi_group_block<kGroupThreads>(rois, num_rois, num_images, blockIdx.x, img_start, order, warp_sums);
 }
 
 __global__ void __launch_bounds__(kRecThreads)

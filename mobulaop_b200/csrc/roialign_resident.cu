@@ -819,7 +819,7 @@ resident_bwd2_table_kernel(const float* __restrict__ rois, int* __restrict__ ord
   __shared__ uint4 s_ra[4][64], s_rb[4][64];
   __shared__ unsigned s_tkey[4][64], s_ckey[4][64];
   __shared__ float s_tw[4][64], s_cw[4][64];
-  if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = counter[1] = 0;   // unit queue, visit blocks done
+  if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = counter[1] = counter[2] = 0;   // unit queue, visit blocks done, heaviest pair
   // the first num_images + 1 blocks group the ROI rows by image (nobody in this launch reads
   // the result), the others build the tables, indexed by ROI ROW
   if ((int)blockIdx.x <= num_images) {
@@ -960,7 +960,7 @@ resident_bwd2d_table_kernel(const float* __restrict__ rois, int* __restrict__ or
   // open columns A / B of the merge: per hit (pw, flags, weight ix=0, weight ix=1)
   __shared__ int s_pw[4][2][kMaxHitsPerCol], s_cf[4][2][kMaxHitsPerCol];
   __shared__ float s_c0[4][2][kMaxHitsPerCol], s_c1[4][2][kMaxHitsPerCol];
-  if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = counter[1] = 0;   // unit queue, visit blocks done
+  if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = counter[1] = counter[2] = 0;   // unit queue, visit blocks done, heaviest pair
   if ((int)blockIdx.x <= num_images) {       // grouping blocks, see resident_bwd2_table_kernel
     __shared__ int s_sums[4];
     roi_group_block<128>(rois, num_rois, num_images, blockIdx.x, img_start, order, s_sums);
@@ -1133,7 +1133,7 @@ resident_bwd2_visits_kernel(const int* __restrict__ order, const int* __restrict
                             int* __restrict__ uorder, int* __restrict__ counter) {
   ptx::chain_enter();
   __shared__ int s_warp[kVisitThreads / 32];
-  __shared__ int s_entries, s_last, s_max, s_hist[kWorkBuckets];
+  __shared__ int s_entries, s_last, s_hist[kWorkBuckets];
   if (threadIdx.x == 0) s_entries = 0;
   const int w = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
   // tile w = ((image, band), column tile): rows [bnd * band_rows, ...), columns [c0, c1)
@@ -1183,34 +1183,34 @@ resident_bwd2_visits_kernel(const int* __restrict__ order, const int* __restrict
   __syncthreads();
   if (t == 0) {
     vcount[w] = total;
-    uwork[w] = 3 * total + s_entries;        // a visit costs about three row entries
+    const int mywork = 3 * total + s_entries;      // a visit costs about three row entries
+    uwork[w] = mywork;
+    atomicMax(counter + 2, mywork);                // the heaviest pair, for the classes below
     __threadfence();
     s_last = atomicAdd(counter + 1, 1) == (int)gridDim.x - 1 ? 1 : 0;
   }
+  for (int k = t; k < kWorkBuckets; k += kVisitThreads) s_hist[k] = 0;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   // counting sort of the pairs by work, in kWorkBuckets classes, heaviest class first
   const int pairs = (int)gridDim.x;
   const volatile int* work = uwork;
-  if (t == 0) s_max = 1;
-  for (int k = t; k < kWorkBuckets; k += kVisitThreads) s_hist[k] = 0;
-  __syncthreads();
-  int mx = 0;
-  for (int k = t; k < pairs; k += kVisitThreads) mx = max(mx, work[k]);
-  atomicMax(&s_max, mx);
-  __syncthreads();
-  const long long top = s_max;
+  const long long top = max(1, *(const volatile int*)(counter + 2));
   auto bucket = [&](int v) { return (kWorkBuckets - 1) - (int)((long long)v * (kWorkBuckets - 1) / top); };
   for (int k = t; k < pairs; k += kVisitThreads) atomicAdd(&s_hist[bucket(work[k])], 1);
   __syncthreads();
-  if (t == 0) {
-    int run = 0;
-    for (int k = 0; k < kWorkBuckets; ++k) {
-      const int c = s_hist[k];
-      s_hist[k] = run;
-      run += c;
+  if (t < 32) {                                   // exclusive prefix over the classes, one warp
+    static_assert(kWorkBuckets == 64, "two classes per lane");
+    const int a = s_hist[2 * t], b = s_hist[2 * t + 1];
+    int incl = a + b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (t >= d) incl += v;
     }
+    s_hist[2 * t] = incl - a - b;
+    s_hist[2 * t + 1] = incl - b;
   }
   __syncthreads();
   for (int k = t; k < pairs; k += kVisitThreads) uorder[atomicAdd(&s_hist[bucket(work[k])], 1)] = k;

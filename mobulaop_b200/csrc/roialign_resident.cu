@@ -1327,7 +1327,9 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     const int j0 = __ldg(img_start + n), nroi = __ldg(img_start + n + 1) - j0;
     const int nvis = __ldg(vcount + pair);
     const uint2* vlist = visits + ((size_t)j0 * tiles + (size_t)bt * nroi);
-    uint2 vrec = lane < nvis ? __ldg(vlist + lane) : make_uint2(0u, 0u);    // first 32 visits
+    // visit records: every lane reads the same 8 bytes, two visits before they are staged
+    uint2 rec0 = nvis > 0 ? __ldg(vlist) : make_uint2(0u, 0u);
+    uint2 rec1 = nvis > 1 ? __ldg(vlist + 1) : make_uint2(0u, 0u);
 
     // ---- band := 0 (or the current dX rows when accumulating) ----
     __syncwarp();
@@ -1352,11 +1354,10 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
 #pragma unroll
     for (int i = 0; i < NT; ++i) tile_ok[i] = lane + 32 * i < tile_floats;
 
-    // visit k: record in lane k % 32 of `vrec` (chunk k / 32)
-#define MOBULA_LOAD_VISIT(v, k)                                                                   \
+    // visit k with its record `rec`
+#define MOBULA_LOAD_VISIT(v, rec)                                                                  \
   do {                                                                                            \
-    const unsigned vx_ = __shfl_sync(0xffffffffu, vrec.x, (k) & 31);                              \
-    const unsigned roi_ = __shfl_sync(0xffffffffu, vrec.y, (k) & 31);                             \
+    const unsigned vx_ = (rec).x, roi_ = (rec).y;                                                 \
     const unsigned jv_ = vx_ & 0xfffffu, first_ = (vx_ >> 20) & 63u, cnt_ = (vx_ >> 26) + 1u;       \
     const float* tile_ = dy_c + ((size_t)roi_ * cb + (unsigned)lane);                             \
     _Pragma("unroll") for (int i = 0; i < NT; ++i)                                                \
@@ -1499,19 +1500,15 @@ resident_bwd2_kernel(const float* __restrict__ dy, float* __restrict__ dx, const
     // visit two ahead into the registers just freed, then computes: the scoreboard wait of the
     // publishing stores (every global load of this kernel shares one scoreboard) therefore
     // covers only loads that have been in flight for a whole visit, never the ones just issued.
-    // (visit records come 32 at a time, the next chunk one chunk ahead)
-    uint2 vnext = 32 + lane < nvis ? __ldg(vlist + 32 + lane) : make_uint2(0u, 0u);
-    // STAGE(set, x, k): visit k (k < nvis) -> register set; its record comes from the current
-    // chunk, or from the next one when k has crossed into it
+    // STAGE(set, x, k): visit k (k < nvis) -> register set; the record of visit k + 2 is requested
 #define MOBULA_STAGE(v, vx, k)                                                                    \
   do {                                                                                            \
     if ((k) < nvis) {                                                                             \
-      if (((k) & 31) == 0 && (k) > 0) {                                                           \
-        vrec = vnext;                                                                             \
-        vnext = (k) + 32 + lane < nvis ? __ldg(vlist + (k) + 32 + lane) : make_uint2(0u, 0u);     \
-      }                                                                                           \
-      vx = __shfl_sync(0xffffffffu, vrec.x, (k) & 31);                                            \
-      MOBULA_LOAD_VISIT(v, k);                                                                    \
+      const uint2 rec_ = rec0;                                                                    \
+      rec0 = rec1;                                                                                \
+      if ((k) + 2 < nvis) rec1 = __ldg(vlist + (k) + 2);                                          \
+      vx = rec_.x;                                                                                \
+      MOBULA_LOAD_VISIT(v, rec_);                                                                 \
     }                                                                                             \
   } while (0)
 #define MOBULA_VISIT(v, vx, knext)                                                                \

@@ -470,6 +470,147 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
   }
 }
 
+// ---- the same forward for an ODD number of bin rows (7 x 7: every BASELINE box head) -----------
+// With two bin rows per warp step the last step of an odd pooled height is half empty (1 / 8 of
+// the tap loads at 7 x 7).  Here a warp works on TWO ROIs at once -- half-warp h on its own ROI,
+// one bin row per step -- so PH steps serve two ROIs instead of PH + 1.  Everything else is the
+// kernel above: same records, same arithmetic, same order of sums.  The first kRowsAhead row
+// records of the next ROI pair are fetched a pair ahead, the others at the start of the pair
+// (they are needed kRowsAhead steps later): registers.
+constexpr int kRowsAhead = 4;
+
+template <int PH, int NCH>
+struct RoiHead {
+  uint4 y[PH < kRowsAhead ? PH : kRowsAhead];
+  uint2 x[NCH];
+  int roi;
+};
+
+template <int PH, int NCH>
+__device__ __forceinline__ void load_roi_head(RoiHead<PH, NCH>& r, const uint2* __restrict__ ent,
+                                              const int* __restrict__ order_j, int q, int last_col) {
+  constexpr int kIters = (PH + 1) / 2;
+  const uint4* ent_y = reinterpret_cast<const uint4*>(ent);
+#pragma unroll
+  for (int it = 0; it < (PH < kRowsAhead ? PH : kRowsAhead); ++it) r.y[it] = __ldg(ent_y + it);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) r.x[ch] = __ldg(ent + 4 * kIters + min(16 * ch + q, last_col));
+  r.roi = __ldg(order_j);
+}
+
+template <int PH, int NCH, bool ACC>
+__global__ void __launch_bounds__(kFwd2Threads, 1)
+resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
+                      const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
+                      int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w,
+                      int vec16) {
+  ptx::chain_enter();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* plane = reinterpret_cast<float*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bins = pooled_h * pooled_w;
+  constexpr int kIters = (PH + 1) / 2;
+  constexpr int kPerRoi = 4 * kIters + 16 * NCH;      // uint2 records, as the table kernel lays them out
+  constexpr int kHead = PH < kRowsAhead ? PH : kRowsAhead;
+  const size_t plane_elems = (size_t)height * width;
+  const int h = lane >> 4, q = lane & 15;
+  const unsigned sbase = ptx::smem_addr(smem_raw);
+  const unsigned row_bytes = (unsigned)pitch * 4u;
+
+  zero_padding(plane, height, width, pitch);
+  __syncthreads();
+  if (!ACC)
+    zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
+                              (long long)c_count * bins);
+
+  bool stores[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) stores[ch] = (q & 1) == 0 && 8 * ch + (q >> 1) < pooled_w;
+
+  long long u, u1;
+  cta_share((long long)c_count * __ldg(img_start + num_images), u, u1);
+  int n = 0;
+  unsigned epoch = 0;
+  while (u < u1) {
+    const PlaneWork w = next_plane(img_start, c_count, u, u1, n);
+    __syncthreads();   // every warp is done reading the previous plane
+    load_padded_plane(plane, data + ((size_t)w.n * channels + w.c) * plane_elems, height, width, pitch,
+                      vec16);
+    ++epoch;
+
+    // pair p of this warp: ROIs jj and jj + 1; a half-warp without a ROI of its own repeats the
+    // other one's loads (same addresses: broadcasts) and stores nothing
+    auto mine = [&](int pair_jj) { return w.j0 + min(pair_jj + h, w.jj1 - 1); };
+    int jj = w.jj0 + 2 * warp;
+    RoiHead<PH, NCH> nxt;
+    if (jj < w.jj1) load_roi_head(nxt, entries + (size_t)mine(jj) * kPerRoi, order + mine(jj), q, 2 * pooled_w - 1);
+    for (; jj < w.jj1; jj += 2 * kFwd2Warps) {
+      const bool have = jj + h < w.jj1;
+      const uint4* ent_y = reinterpret_cast<const uint4*>(entries + (size_t)mine(jj) * kPerRoi);
+      uint4 ys[PH];
+#pragma unroll
+      for (int it = 0; it < kHead; ++it) ys[it] = nxt.y[it];
+#pragma unroll
+      for (int it = kHead; it < PH; ++it) ys[it] = __ldg(ent_y + it);
+      uint2 xs[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) xs[ch] = nxt.x[ch];
+      const int roi = nxt.roi;
+      if (jj + 2 * kFwd2Warps < w.jj1)
+        load_roi_head(nxt, entries + (size_t)mine(jj + 2 * kFwd2Warps) * kPerRoi, order + mine(jj + 2 * kFwd2Warps), q,
+                      2 * pooled_w - 1);
+
+      unsigned xa[NCH], xb[NCH];      // shared-memory address of the low column in row 0 / row 1
+      float2 lx2[NCH], hx2[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        xa[ch] = sbase + xs[ch].x;
+        xb[ch] = xa[ch] + row_bytes;
+        const float lx = __uint_as_float(xs[ch].y), hx = __fsub_rn(1.0f, lx);
+        lx2[ch] = make_float2(lx, lx);
+        hx2[ch] = make_float2(hx, hx);
+      }
+      // this lane's first output: bin (0, q / 2) of chunk 0 of its half-warp's ROI
+      float* optr = out + ((size_t)roi * channels + w.c) * bins + (q >> 1);
+#pragma unroll
+      for (int it = 0; it < PH; ++it) {
+        const uint4 ey = ys[it];
+        const float2 ly2 = make_float2(__uint_as_float(ey.y), __uint_as_float(ey.w));
+        const float2 hy2 = make_float2(__fsub_rn(1.0f, ly2.x), __fsub_rn(1.0f, ly2.y));
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          // taps of sample iy = 0 in .x, of iy = 1 in .y: v1 v2 / v3 v4 as in bilinear.h:50-53
+          const unsigned a0 = xa[ch] + ey.x, b0 = xb[ch] + ey.x, a1 = xa[ch] + ey.z, b1 = xb[ch] + ey.z;
+          const float2 v1 = make_float2(lds_at(a0, epoch), lds_at(a1, epoch));
+          const float2 v2 = make_float2(lds_at4(a0, epoch), lds_at4(a1, epoch));
+          const float2 v3 = make_float2(lds_at(b0, epoch), lds_at(b1, epoch));
+          const float2 v4 = make_float2(lds_at4(b0, epoch), lds_at4(b1, epoch));
+          const float2 w1 = __fmul2_rn(hy2, hx2[ch]), w2 = __fmul2_rn(hy2, lx2[ch]);
+          const float2 w3 = __fmul2_rn(ly2, hx2[ch]), w4 = __fmul2_rn(ly2, lx2[ch]);
+          // scalar sums: see resident_fwd2_kernel
+          const float2 p1 = __fmul2_rn(w1, v1), p2 = __fmul2_rn(w2, v2);
+          const float2 p3 = __fmul2_rn(w3, v3), p4 = __fmul2_rn(w4, v4);
+          float2 sm;
+          sm.x = __fadd_rn(__fadd_rn(__fadd_rn(p1.x, p2.x), p3.x), p4.x);
+          sm.y = __fadd_rn(__fadd_rn(__fadd_rn(p1.y, p2.y), p3.y), p4.y);
+          const float s0n = __shfl_down_sync(0xffffffffu, sm.x, 1);
+          const float s1n = __shfl_down_sync(0xffffffffu, sm.y, 1);
+          float t = __fadd_rn(0.0f, sm.x);
+          t = __fadd_rn(t, s0n);
+          t = __fadd_rn(t, sm.y);
+          t = __fadd_rn(t, s1n);
+          const float y = __fmul_rn(t, 0.25f);     // count = 4: an exact scaling
+          if (stores[ch] && have) {
+            float* o = optr + it * pooled_w + 8 * ch;
+            if (ACC) *o = __fadd_rn(*o, y);
+            else *o = y;
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---- the same forward over a channel PAIR (planes small enough that two padded planes fit) ----
 // The plane holds two channels interleaved (float2 per pixel): every tap is one 8-byte load that
 // serves both channels, a half-warp's load touches ONE feature-map row (8-byte accesses are
@@ -1741,6 +1882,33 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     if (plan.xslots == 16) MOBULA_FWD2_NCH(ITERS, 1);        \
     else MOBULA_FWD2_NCH(ITERS, 2);                          \
   } while (0)
+    const bool pairs_of_rois = !plan.fwd_pair && (a.pooled_h & 1) && a.pooled_h <= 7;
+#define MOBULA_FWD2R(PH, NCH, ACC)                                                                    \
+  do {                                                                                               \
+    e = resident_grid(resident_fwd2r_kernel<PH, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms, work, &grid); \
+    if (e != cudaSuccess) return e;                                                                  \
+    chained_launch(resident_fwd2r_kernel<PH, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream,   \
+        data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,       \
+        plan.pitch, a.pooled_h, a.pooled_w, plan.vec16);                                             \
+  } while (0)
+#define MOBULA_FWD2R_PH(PH)                                          \
+  do {                                                               \
+    if (plan.xslots == 16) {                                         \
+      if (accumulate) MOBULA_FWD2R(PH, 1, true);                     \
+      else MOBULA_FWD2R(PH, 1, false);                               \
+    } else {                                                         \
+      if (accumulate) MOBULA_FWD2R(PH, 2, true);                     \
+      else MOBULA_FWD2R(PH, 2, false);                               \
+    }                                                                \
+  } while (0)
+    if (pairs_of_rois) {
+      switch (a.pooled_h) {
+        case 1: MOBULA_FWD2R_PH(1); break;
+        case 3: MOBULA_FWD2R_PH(3); break;
+        case 5: MOBULA_FWD2R_PH(5); break;
+        default: MOBULA_FWD2R_PH(7); break;
+      }
+    } else
     switch (plan.ypairs / 2) {
       case 1: MOBULA_FWD2_ITERS(1); break;
       case 2: MOBULA_FWD2_ITERS(2); break;
@@ -1751,6 +1919,8 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
       case 7: MOBULA_FWD2_ITERS(7); break;
       default: MOBULA_FWD2_ITERS(8); break;
     }
+#undef MOBULA_FWD2R_PH
+#undef MOBULA_FWD2R
 #undef MOBULA_FWD2_ITERS
 #undef MOBULA_FWD2_NCH
 #undef MOBULA_FWD2

@@ -202,6 +202,9 @@ ODD_SHAPES = [
     (1, 7, 150, 200, 40, (7, 7), 0.25, 2),     # tall plane: many row bands per plane
     (1, 3, 37, 271, 30, (7, 7), 0.25, 2),      # wide plane, odd width: two column tiles, the second ragged
     (1, 2, 30, 300, 25, (14, 14), 0.25, 2),    # two column tiles with two chunks of column records
+    (1, 2, 150, 200, 30, (5, 12), 0.25, 2),    # odd pooled height on a single-plane kernel: two ROIs per warp,
+    (1, 2, 150, 200, 30, (3, 16), 0.25, 2),    # ... two chunks of sample columns
+    (1, 3, 150, 200, 30, (1, 3), 0.25, 2),     # ... one bin row
     (2, 3, 24, 28, 11, (7, 7), 0.25, 1),       # generic resident forward, sr 1
     (2, 3, 24, 28, 11, (5, 6), 0.25, 4),       # ... sr 4
 ]

@@ -18,7 +18,7 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 $CMD > gpurun_out/plain_launches.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/${TAG}_launches_C2.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/plain_full.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'resident_(fwd2|bwd2)_kernel' -s 6 -c 2 -f -o gpurun_out/prof_${TAG}_final $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'resident_(fwd2r?|bwd2)_kernel' -s 6 -c 2 -f -o gpurun_out/prof_${TAG}_final $CMD > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 for f in gpurun_out/${TAG}_bench_*.json; do python - "$f" <<'PY'
 import json, sys

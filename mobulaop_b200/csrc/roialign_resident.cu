@@ -773,6 +773,133 @@ resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, c
   }
 }
 
+// The channel-pair forward for odd pooled heights: two ROIs per warp, as resident_fwd2r_kernel.
+template <int PH, int NCH, bool ACC>
+__global__ void __launch_bounds__(kFwd2Threads, 1)
+resident_fwd2pr_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
+                      const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
+                      int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w) {
+  ptx::chain_enter();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* plane = reinterpret_cast<float2*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bins = pooled_h * pooled_w;
+  constexpr int kIters = (PH + 1) / 2;
+  constexpr int kPerRoi = 4 * kIters + 16 * NCH;      // uint2 records, as the table kernel lays them out
+  constexpr int kHead = PH < kRowsAhead ? PH : kRowsAhead;
+  const size_t plane_elems = (size_t)height * width;
+  const int h = lane >> 4, q = lane & 15;
+  const unsigned sbase = ptx::smem_addr(smem_raw);
+  const unsigned row_bytes = (unsigned)pitch * 8u;
+  const int cpairs = (c_count + 1) >> 1;
+
+  // the same padding as zero_padding(), on a plane of 2 * pitch floats per row
+  zero_padding(reinterpret_cast<float*>(smem_raw), height, 2 * width + 1, 2 * pitch);
+  __syncthreads();
+  if (!ACC)
+    zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
+                              (long long)c_count * bins);
+
+  bool stores[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) stores[ch] = (q & 1) == 0 && 8 * ch + (q >> 1) < pooled_w;
+
+  long long u, u1;
+  cta_share((long long)cpairs * __ldg(img_start + num_images), u, u1);
+  int n = 0;
+  unsigned epoch = 0;
+  while (u < u1) {
+    const PlaneWork w = next_plane(img_start, cpairs, u, u1, n);      // w.c: channel pair
+    const int c = 2 * w.c;
+    const bool two = c + 1 < c_count;
+    __syncthreads();   // every warp is done reading the previous plane
+    const float* src0 = data + ((size_t)w.n * channels + c) * plane_elems;
+    load_padded_pair(plane, src0, two ? src0 + plane_elems : nullptr, height, width, pitch);
+    ++epoch;
+
+    // two ROIs per warp, half-warp h on its own ROI (see resident_fwd2r_kernel)
+    auto mine = [&](int pair_jj) { return w.j0 + min(pair_jj + h, w.jj1 - 1); };
+    int jj = w.jj0 + 2 * warp;
+    RoiHead<PH, NCH> nxt;
+    if (jj < w.jj1) load_roi_head(nxt, entries + (size_t)mine(jj) * kPerRoi, order + mine(jj), q, 2 * pooled_w - 1);
+    for (; jj < w.jj1; jj += 2 * kFwd2Warps) {
+      const bool have = jj + h < w.jj1;
+      const uint4* ent_y = reinterpret_cast<const uint4*>(entries + (size_t)mine(jj) * kPerRoi);
+      struct {
+        uint4 y[PH];
+        uint2 x[NCH];
+        int roi;
+      } cur;
+#pragma unroll
+      for (int it = 0; it < kHead; ++it) cur.y[it] = nxt.y[it];
+#pragma unroll
+      for (int it = kHead; it < PH; ++it) cur.y[it] = __ldg(ent_y + it);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) cur.x[ch] = nxt.x[ch];
+      cur.roi = nxt.roi;
+      if (jj + 2 * kFwd2Warps < w.jj1)
+        load_roi_head(nxt, entries + (size_t)mine(jj + 2 * kFwd2Warps) * kPerRoi, order + mine(jj + 2 * kFwd2Warps), q,
+                      2 * pooled_w - 1);
+
+      unsigned xa[NCH], xb[NCH];      // shared-memory address of the low column in row 0 / row 1
+      float lx[NCH], hx[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        xa[ch] = sbase + cur.x[ch].x;
+        xb[ch] = xa[ch] + row_bytes;
+        lx[ch] = __uint_as_float(cur.x[ch].y);
+        hx[ch] = __fsub_rn(1.0f, lx[ch]);
+      }
+      float* optr = out + ((size_t)cur.roi * channels + c) * bins + (q >> 1);
+#pragma unroll
+      for (int it = 0; it < PH; ++it) {
+        const uint4 ey = cur.y[it];
+        const float ly0 = __uint_as_float(ey.y), ly1 = __uint_as_float(ey.w);
+        const float hy0 = __fsub_rn(1.0f, ly0), hy1 = __fsub_rn(1.0f, ly1);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          // one bilinear sample of both channels (.x / .y); products packed over the pair, sums
+          // scalar (see resident_fwd2_kernel), order as in bilinear.h:50-56
+          auto sample = [&](unsigned row, float hy, float ly) {
+            const unsigned a = xa[ch] + row, b = xb[ch] + row;
+            const float2 v1 = lds2_at(a, epoch), v2 = lds2_at8(a, epoch);
+            const float2 v3 = lds2_at(b, epoch), v4 = lds2_at8(b, epoch);
+            const float w1 = __fmul_rn(hy, hx[ch]), w2 = __fmul_rn(hy, lx[ch]);
+            const float w3 = __fmul_rn(ly, hx[ch]), w4 = __fmul_rn(ly, lx[ch]);
+            const float2 p1 = __fmul2_rn(make_float2(w1, w1), v1), p2 = __fmul2_rn(make_float2(w2, w2), v2);
+            const float2 p3 = __fmul2_rn(make_float2(w3, w3), v3), p4 = __fmul2_rn(make_float2(w4, w4), v4);
+            float2 s;
+            s.x = __fadd_rn(__fadd_rn(__fadd_rn(p1.x, p2.x), p3.x), p4.x);
+            s.y = __fadd_rn(__fadd_rn(__fadd_rn(p1.y, p2.y), p3.y), p4.y);
+            return s;
+          };
+          const float2 s0 = sample(ey.x, hy0, ly0), s1 = sample(ey.z, hy1, ly1);
+          float2 t;
+          t.x = __fadd_rn(0.0f, s0.x);
+          t.y = __fadd_rn(0.0f, s0.y);
+          t.x = __fadd_rn(t.x, __shfl_down_sync(0xffffffffu, s0.x, 1));
+          t.y = __fadd_rn(t.y, __shfl_down_sync(0xffffffffu, s0.y, 1));
+          t.x = __fadd_rn(t.x, s1.x);
+          t.y = __fadd_rn(t.y, s1.y);
+          t.x = __fadd_rn(t.x, __shfl_down_sync(0xffffffffu, s1.x, 1));
+          t.y = __fadd_rn(t.y, __shfl_down_sync(0xffffffffu, s1.y, 1));
+          if (stores[ch] && have) {
+            float* o = optr + it * pooled_w + 8 * ch;
+            const float y0 = __fmul_rn(t.x, 0.25f), y1 = __fmul_rn(t.y, 0.25f);     // count = 4: exact
+            if (ACC) {
+              o[0] = __fadd_rn(o[0], y0);
+              if (two) o[bins] = __fadd_rn(o[bins], y1);
+            } else {
+              o[0] = y0;
+              if (two) o[bins] = y1;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 template <typename K>
 cudaError_t set_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -1882,9 +2009,18 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     if (plan.xslots == 16) MOBULA_FWD2_NCH(ITERS, 1);        \
     else MOBULA_FWD2_NCH(ITERS, 2);                          \
   } while (0)
-    const bool pairs_of_rois = !plan.fwd_pair && (a.pooled_h & 1) && a.pooled_h <= 7;
+    const bool pairs_of_rois = (a.pooled_h & 1) && a.pooled_h <= 7;
 #define MOBULA_FWD2R(PH, NCH, ACC)                                                                    \
   do {                                                                                               \
+    if (plan.fwd_pair) {                                                                             \
+      e = resident_grid(resident_fwd2pr_kernel<PH, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms,  \
+                        (work + 1) / 2, &grid);                                                      \
+      if (e != cudaSuccess) return e;                                                                \
+      chained_launch(resident_fwd2pr_kernel<PH, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream, \
+          data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,     \
+          plan.pitch, a.pooled_h, a.pooled_w);                                                       \
+      break;                                                                                         \
+    }                                                                                                \
     e = resident_grid(resident_fwd2r_kernel<PH, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms, work, &grid); \
     if (e != cudaSuccess) return e;                                                                  \
     chained_launch(resident_fwd2r_kernel<PH, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream,   \

@@ -5,13 +5,17 @@
 
 A "step" is one forward bilinear pool plus one backward gradient scatter (dX produced from
 scratch, zero-fill included) over one batch of synthetic inputs already resident in HBM.
-N=1 runs BASELINE.json configs[1] (C2, the Faster R-CNN box head); N>1 runs the same
-per-GPU work on every rank (weak scaling): the global problem has 2*N images, it is split
-with mobulaop_b200.sharding (per-image ROI ownership, no data-path collective).
+The default workload is BASELINE.json configs[3] (C4: 64 images of the Faster R-CNN box-head
+shape, 32768 ROIs) for EVERY N: the 64 images are split over the N ranks with
+mobulaop_b200.sharding (per-image ROI ownership, no data-path collective) = strong scaling;
+N=1 runs all of it on one GPU (it fits: 3.6 GB of feature maps).  The C2 box head (configs[1],
+what round 1 was quoted on) is timed per rank as the `secondary` record.  `--scaling weak
+--workload C2` is the round-1 protocol (every rank owns 2 images).
 
 value      ROIs/s over all ranks, device time (CUDA events on the launching stream), max over ranks
 e2e        the same metric through mobula.op.ROIAlign[np.ndarray] with pinned HOST buffers:
            host->device and device->host copies inside the timed region
+e2e_torch  the same metric through mobula.op.ROIAlign on CUDA tensors (torch autograd), wall clock
 roofline   dominant kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
 cpu_baseline  the reference's own C++ (oracle/_ref, OpenMP, all host cores) on rank 0, N=1
 
@@ -42,7 +46,10 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='C2', choices=sorted(WL.CONFIGS))
+    ap.add_argument('--workload', default='C4', choices=sorted(WL.CONFIGS))
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
+    ap.add_argument('--no-secondary', action='store_true')
+    ap.add_argument('--e2e-torch-steps', type=int, default=200)
     ap.add_argument('--mode', default='atomic', choices=['atomic', 'deterministic'])
     ap.add_argument('--algo', default='auto', choices=['auto', 'gather', 'plane', 'resident'])
     ap.add_argument('--no-e2e', action='store_true')
@@ -180,7 +187,7 @@ def run_reference_arm(args):
     line = dict(
         impl='reference', metric=METRIC, value=res['value'], unit=UNIT, n_gpus=args.gpus,
         steps=steps, warmup=warmup, ms_per_step=res['step_s'] * 1e3, higher_is_better=True,
-        scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+        scaling=args.scaling, vs_baseline=None, dtype='f32', data='synthetic',
         config=wl.describe(),
         cpu_baseline=dict(value=res['value'], unit=UNIT, cores=res['cores'], kind=res['kind'],
                           sample=res['sample']),
@@ -194,6 +201,125 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
+class DeviceRun(object):
+    """One rank's share of a workload, resident in HBM, launched through the C-ABI."""
+
+    def __init__(self, lib, torch, dev, local_rank, wl, rois_np, mode, algo, seed):
+        import ctypes
+        from mobulaop_b200 import _native
+        self.lib, self.torch, self.dev, self.wl = lib, torch, dev, wl
+        self._native = _native
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        if wl.literal:      # benchmark_roi_align.py:15: data = arange
+            self.data = torch.arange(int(np.prod(wl.data_shape)), dtype=torch.float32,
+                                     device=dev).reshape(wl.data_shape)
+        else:
+            self.data = torch.randn(wl.data_shape, dtype=torch.float32, device=dev, generator=gen)
+        self.dy = torch.randn(wl.out_shape, dtype=torch.float32, device=dev, generator=gen)
+        self.rois = torch.from_numpy(rois_np).to(dev)
+        self.out = torch.empty(wl.out_shape, dtype=torch.float32, device=dev)
+        self.dx = torch.empty(wl.data_shape, dtype=torch.float32, device=dev)
+        self.stream = torch.cuda.current_stream(dev)
+        self.sp = ctypes.c_void_p(self.stream.cuda_stream)
+        self.mode = _native.BWD_DETERMINISTIC if mode == 'deterministic' else _native.BWD_ATOMIC
+        self.flags = _native.make_flags(algo=algo)
+        self.local_rank = local_rank
+        self._vp = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def fwd(self):
+        wl, vp = self.wl, self._vp
+        self._native.check(self.lib.mobula_roialign_forward_f32(
+            self.local_rank, self.sp, vp(self.data), vp(self.rois), vp(self.out), wl.R, wl.N, wl.C,
+            wl.H, wl.W, wl.pooled[0], wl.pooled[1], wl.scale, wl.sampling_ratio, self.flags))
+
+    def bwd(self):
+        wl, vp = self.wl, self._vp
+        self._native.check(self.lib.mobula_roialign_backward_f32(
+            self.local_rank, self.sp, vp(self.dy), vp(self.rois), vp(self.dx), wl.R, wl.N, wl.C,
+            wl.H, wl.W, wl.pooled[0], wl.pooled[1], wl.scale, wl.sampling_ratio, self.mode, self.flags))
+
+    def free(self):
+        self.data = self.dy = self.out = self.dx = self.rois = None
+        self.torch.cuda.empty_cache()
+
+
+def timed_steps(run, flush_l2, barrier, steps, warmup, clocks_index=None):
+    """W untimed + K timed fwd+bwd steps; CUDA events on the launching stream, L2 flushed between
+    steps outside the events.  Returns per-rank means in ms and the launch count."""
+    torch, native = run.torch, run._native
+    for _ in range(warmup):
+        flush_l2()
+        run.fwd()
+        run.bwd()
+    barrier()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    launches0 = native.launch_count()
+    sampler = ClockSampler(clocks_index) if clocks_index is not None else None
+    if sampler:
+        sampler.__enter__()
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(steps):
+        flush_l2()                          # evict L2 between steps (outside the events)
+        ev[k][0].record(run.stream)
+        run.fwd()
+        ev[k][1].record(run.stream)
+        run.bwd()
+        ev[k][2].record(run.stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    if sampler:
+        sampler.__exit__()
+    fwd_ms = np.array([ev[k][0].elapsed_time(ev[k][1]) for k in range(steps)])
+    bwd_ms = np.array([ev[k][1].elapsed_time(ev[k][2]) for k in range(steps)])
+    return dict(step_ms=float((fwd_ms + bwd_ms).mean()), fwd_ms=float(fwd_ms.mean()),
+                bwd_ms=float(bwd_ms.mean()), launches=native.launch_count() - launches0, wall=wall,
+                clocks=sampler.summary() if sampler else None,
+                algo_fwd=native.last_algo(False), algo_bwd=native.last_algo(True))
+
+
+def rank_stats(torch, dist, dev, world, local):
+    """max / mean / per-rank of a few per-rank floats."""
+    t = torch.tensor(local, dtype=torch.float64, device=dev)
+    if world > 1:
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        allr = torch.stack(parts).cpu().numpy()
+    else:
+        allr = t.cpu().numpy()[None]
+    return allr
+
+
+def roofline_record(wl, res, peak, peak_src, traffic):
+    b_fwd, b_bwd = wl.bytes_forward(), wl.bytes_backward()
+    fwd_ms, bwd_ms, step_ms = res['fwd_ms'], res['bwd_ms'], res['step_ms']
+    if bwd_ms >= fwd_ms:
+        kname, kbytes, kms = 'backward (%s)' % res['algo_bwd'], b_bwd, bwd_ms
+    else:
+        kname, kbytes, kms = 'forward (%s)' % res['algo_fwd'], b_fwd, fwd_ms
+    achieved = kbytes / (kms * 1e-3) / 1e9
+    tr = (traffic or {}).get(wl.name, {}).get(kname, {}).get('bytes')
+    return dict(bound='hbm', kernel=kname, achieved=achieved, peak=peak, unit='GB/s',
+                frac=achieved / peak, traffic=tr, peak_source=peak_src, algorithmic_bytes=kbytes,
+                fwd=dict(ms=fwd_ms, bytes=b_fwd, gbs=b_fwd / (fwd_ms * 1e-3) / 1e9,
+                         frac=b_fwd / (fwd_ms * 1e-3) / 1e9 / peak, algo=res['algo_fwd']),
+                bwd=dict(ms=bwd_ms, bytes=b_bwd, gbs=b_bwd / (bwd_ms * 1e-3) / 1e9,
+                         frac=b_bwd / (bwd_ms * 1e-3) / 1e9 / peak, algo=res['algo_bwd']),
+                step=dict(bytes=b_fwd + b_bwd, gbs=(b_fwd + b_bwd) / (step_ms * 1e-3) / 1e9,
+                          frac=(b_fwd + b_bwd) / (step_ms * 1e-3) / 1e9 / peak))
+
+
+def load_traffic():
+    """DRAM bytes per launch of the hot kernels, written by scripts/ncu_traffic.py from the
+    `ncu --set full` capture of the same round (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -212,18 +338,20 @@ def run_ours(args):
     lib = _native.load()
 
     base = WL.CONFIGS[args.workload]
-    # weak scaling: every rank owns base.N images and their ROIs
-    glob = base.scaled(N=base.N * world, name=base.name)
+    if args.scaling == 'strong':
+        # the workload is fixed (C4: 64 images, 32768 ROIs); rank g owns images
+        # [g*N/G, (g+1)*N/G) and every ROI that points into them (per-image ROI ownership)
+        if base.N < world:
+            raise SystemExit('%s has %d images: cannot split over %d ranks' % (base.name, base.N, world))
+        glob = base
+    else:
+        # weak scaling: every rank owns base.N images and their ROIs
+        glob = base.scaled(N=base.N * world, name=base.name)
     rois_global = WL.make_rois(glob, seed=0)
     shard = sharding.make_shard(rois_global, glob.N, rank, world)
-    assert shard.num_images == base.N and shard.num_rois == base.R
-    wl = base
-    rng = np.random.default_rng(1234 + rank)
-    data = torch.from_numpy(rng.standard_normal(wl.data_shape, dtype=np.float32)).to(dev)
-    dy = torch.from_numpy(rng.standard_normal(wl.out_shape, dtype=np.float32)).to(dev)
-    rois = torch.from_numpy(shard.rois).to(dev)
-    out = torch.empty(wl.out_shape, dtype=torch.float32, device=dev)
-    dx = torch.empty(wl.data_shape, dtype=torch.float32, device=dev)
+    wl = base.scaled(N=shard.num_images, name=base.name)
+    assert shard.num_rois == wl.R, (shard.num_rois, wl.R)
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device=dev)   # 256 MB, only ever read
 
@@ -234,122 +362,75 @@ def run_ours(args):
         flush.zero_()
         flush_rd.sum()
 
-    import ctypes
-    stream = torch.cuda.current_stream(dev)
-    sp = ctypes.c_void_p(stream.cuda_stream)
-    mode = _native.BWD_DETERMINISTIC if args.mode == 'deterministic' else _native.BWD_ATOMIC
-    flags = _native.make_flags(algo=args.algo)
-    PH, PW = wl.pooled
-
-    def vp(t):
-        return ctypes.c_void_p(t.data_ptr())
-
-    def fwd():
-        _native.check(lib.mobula_roialign_forward_f32(
-            local_rank, sp, vp(data), vp(rois), vp(out), wl.R, wl.N, wl.C, wl.H, wl.W, PH, PW,
-            wl.scale, wl.sampling_ratio, flags))
-
-    def bwd():
-        _native.check(lib.mobula_roialign_backward_f32(
-            local_rank, sp, vp(dy), vp(rois), vp(dx), wl.R, wl.N, wl.C, wl.H, wl.W, PH, PW,
-            wl.scale, wl.sampling_ratio, mode, flags))
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        flush_l2()
-        fwd()
-        bwd()
-    barrier()
-
-    K = max(args.steps, 1)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    launches0 = _native.launch_count()
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        wall0 = time.perf_counter()
-        for k in range(K):
-            flush_l2()                          # evict L2 between steps (outside the events)
-            ev[k][0].record(stream)
-            fwd()
-            ev[k][1].record(stream)
-            bwd()
-            ev[k][2].record(stream)
-        barrier()
-        wall = time.perf_counter() - wall0
-    launches = _native.launch_count() - launches0
-    fwd_ms = np.array([ev[k][0].elapsed_time(ev[k][1]) for k in range(K)])
-    bwd_ms = np.array([ev[k][1].elapsed_time(ev[k][2]) for k in range(K)])
-    step_ms_local = float((fwd_ms + bwd_ms).sum() / K)
-
-    stats = torch.tensor([step_ms_local, float(fwd_ms.mean()), float(bwd_ms.mean()), float(launches)],
-                         dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = stats.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        step_ms, fwd_mean, bwd_mean, launches = mx[0].item(), mx[1].item(), mx[2].item(), int(sm[3].item())
-    else:
-        step_ms, fwd_mean, bwd_mean = step_ms_local, float(fwd_ms.mean()), float(bwd_ms.mean())
-    total_rois = wl.R * world
+    K, W = max(args.steps, 1), max(args.warmup, 3)
+    run = DeviceRun(lib, torch, dev, local_rank, wl, shard.rois, args.mode, args.algo, 1234 + rank)
+    res = timed_steps(run, flush_l2, barrier, K, W, clocks_index=local_rank)
+    allr = rank_stats(torch, dist, dev, world, [res['step_ms'], res['fwd_ms'], res['bwd_ms'],
+                                                float(res['launches'])])
+    step_ms, fwd_max, bwd_max = float(allr[:, 0].max()), float(allr[:, 1].max()), float(allr[:, 2].max())
+    launches = int(allr[:, 3].sum())
+    total_rois = glob.R
     value = total_rois / (step_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (per launch, this rank) ------------------------
     peak, peak_src = measured_peaks()
-    b_fwd, b_bwd = wl.bytes_forward(), wl.bytes_backward()
-    if bwd_mean >= fwd_mean:
-        kname, kbytes, kms = 'backward (%s)' % _native.last_algo(True), b_bwd, bwd_mean
-    else:
-        kname, kbytes, kms = 'forward (%s)' % _native.last_algo(False), b_fwd, fwd_mean
-    achieved = kbytes / (kms * 1e-3) / 1e9
-    traffic = None          # DRAM bytes of that kernel from the committed ncu --set full capture
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-            traffic = json.load(f).get(wl.name, {}).get(kname, {}).get('bytes')
-    except (OSError, ValueError):
-        pass
-    roofline = dict(bound='hbm', kernel=kname, achieved=achieved, peak=peak, unit='GB/s',
-                    frac=achieved / peak, traffic=traffic, peak_source=peak_src,
-                    algorithmic_bytes=kbytes,
-                    fwd=dict(ms=fwd_mean, bytes=b_fwd, gbs=b_fwd / (fwd_mean * 1e-3) / 1e9,
-                             frac=b_fwd / (fwd_mean * 1e-3) / 1e9 / peak,
-                             algo=_native.last_algo(False)),
-                    bwd=dict(ms=bwd_mean, bytes=b_bwd, gbs=b_bwd / (bwd_mean * 1e-3) / 1e9,
-                             frac=b_bwd / (bwd_mean * 1e-3) / 1e9 / peak,
-                             algo=_native.last_algo(True)),
-                    step=dict(bytes=b_fwd + b_bwd, gbs=(b_fwd + b_bwd) / (step_ms_local * 1e-3) / 1e9,
-                              frac=(b_fwd + b_bwd) / (step_ms_local * 1e-3) / 1e9 / peak))
+    traffic = load_traffic()
+    roofline = roofline_record(wl, res, peak, peak_src, traffic)      # this rank's launches
 
-    # ---- end to end through the public API with pinned host buffers ----------------------
-    e2e = None
+    # ---- end to end through the public API --------------------------------------------------
+    e2e = e2e_torch = None
     if not args.no_e2e:
-        e2e = run_e2e(args, wl, shard, world, dev)
+        e2e_torch = run_e2e_torch(args, wl, run, world, dev, glob.R)
+    run.free()
+    if not args.no_e2e:
+        e2e = run_e2e(args, wl, shard, world, dev, glob.R)
+
+    # ---- secondary record: the C2 box head per rank (the shape round 1 was quoted on) ---------
+    secondary = None
+    if args.workload != 'C2' and not args.no_secondary:
+        c2 = WL.CONFIGS['C2']
+        c2_rois = WL.make_rois(c2, seed=0)
+        run2 = DeviceRun(lib, torch, dev, local_rank, c2, c2_rois, args.mode, args.algo, 99 + rank)
+        res2 = timed_steps(run2, flush_l2, barrier, max(10, min(K, 50)), W)
+        all2 = rank_stats(torch, dist, dev, world, [res2['step_ms'], res2['fwd_ms'], res2['bwd_ms']])
+        run2.free()
+        s_ms = float(all2[:, 0].max())
+        secondary = dict(workload=c2.name, config=c2.describe(), scaling='weak (every rank runs C2)',
+                         value=c2.R * world / (s_ms * 1e-3), unit=UNIT, ms_per_step=s_ms,
+                         fwd_ms=float(all2[:, 1].max()), bwd_ms=float(all2[:, 2].max()),
+                         roofline=roofline_record(c2, res2, peak, peak_src, traffic))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            res = time_cpu(wl, steps=3, warmup=1, budget_s=4.0)
-            cpu = dict(value=res['value'], unit=UNIT, cores=res['cores'], kind=res['kind'],
-                       sample=res['sample'])
+            r = time_cpu(base, steps=3, warmup=1, budget_s=4.0)
+            cpu = dict(value=r['value'], unit=UNIT, cores=r['cores'], kind=r['kind'], sample=r['sample'])
         except Exception as err:          # the checker is optional for the product arm
             cpu = dict(value=None, unit=UNIT, cores=0, kind='unavailable', sample=str(err))
 
     if rank == 0:
-        cfg = wl.describe()
-        cfg.update(images_total=wl.N * world, rois_total=total_rois, parallelism='roi-shard-by-image x%d' % world,
-                   backward_mode=args.mode, algo=args.algo,
-                   l2='256 MB buffer written, then another 256 MB read, between timed steps (outside the CUDA '
-                      'events): cold L2 without dirty flush lines; '
-                      'step inputs+outputs are %.0f MB > 126 MB L2' % ((b_fwd + b_bwd) / 1e6))
-        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=max(args.warmup, 3),
-                    ms_per_step=step_ms, higher_is_better=True, scaling='weak', vs_baseline=None,
-                    dtype='f32', data='synthetic', config=cfg, roofline=roofline,
-                    cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks.summary(),
-                    wall_s_timed_region=wall)
+        b_step = wl.bytes_forward() + wl.bytes_backward()
+        details = dict(
+            images_total=glob.N, rois_total=total_rois, images_per_rank=wl.N, rois_per_rank=wl.R,
+            parallelism='roi-shard-by-image x%d (%s scaling)' % (world, args.scaling),
+            backward_mode=args.mode, algo=args.algo,
+            shard_ms=dict(max=step_ms, mean=float(allr[:, 0].mean()), per_rank=[float(v) for v in allr[:, 0]]),
+            fwd_ms_max=fwd_max, bwd_ms_max=bwd_max,
+            l2='256 MB buffer written, then another 256 MB read, between timed steps (outside the CUDA '
+               'events): cold L2 without dirty flush lines; a rank\'s step moves %.0f MB > 126 MB L2' % (b_step / 1e6),
+            compare_with='profiles/r1_bench_C4.json (round 1, C4 on one GPU: 3.47 M ROIs/s, 16.8 %% of '
+                         'roofline); BENCH_r01.json was the C2 line -- see `secondary`'
+            if args.workload == 'C4' else None)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W,
+                    ms_per_step=step_ms, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
+                    dtype='f32', data='synthetic', config=base.describe(), details=details,
+                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, e2e_torch=e2e_torch,
+                    secondary=secondary, gpu_launches=launches, clocks=res['clocks'],
+                    wall_s_timed_region=res['wall'])
         emit(line)
     if world > 1:
         dist.barrier()
@@ -357,7 +438,48 @@ def run_ours(args):
     return 0
 
 
-def run_e2e(args, wl, shard, world, dev):
+def run_e2e_torch(args, wl, run, world, dev, total_rois):
+    """fwd+bwd through mobula.op.ROIAlign on DEVICE tensors (torch autograd), wall clock over
+    many steps: what a training loop pays, dispatch included (no L2 flush, no copies)."""
+    import torch
+    import torch.distributed as dist
+    import mobula
+    mobula.op.load('ROIAlign')
+    x = run.data.requires_grad_(True)
+    deterministic = args.mode == 'deterministic'
+
+    def step():
+        x.grad = None
+        y = mobula.op.ROIAlign(x, run.rois, pooled_size=wl.pooled, spatial_scale=wl.scale,
+                               sampling_ratio=wl.sampling_ratio, deterministic=deterministic)
+        y.backward(run.dy)
+
+    with mobula.config.TempConfig(ROIALIGN_ALGO=args.algo):
+        for _ in range(3):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        n = max(args.e2e_torch_steps, 1)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step()
+        host_s = (time.perf_counter() - t0) / n          # time to ISSUE a step
+        torch.cuda.synchronize(dev)
+        step_s = (time.perf_counter() - t0) / n
+    run.data.requires_grad_(False)
+    x.grad = None
+    t = torch.tensor([step_s, host_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_s, host_s = t[0].item(), t[1].item()
+    return dict(value=total_rois / step_s, unit=UNIT, ms_per_step=step_s * 1e3,
+                host_issue_us_per_step=host_s * 1e6, steps=n,
+                api='mobula.op.ROIAlign(x, rois, ...) + y.backward(dy) on CUDA tensors (torch autograd), '
+                    'wall clock, warm L2, no copies')
+
+
+def run_e2e(args, wl, shard, world, dev, total_rois):
     """fwd+bwd through mobula.op.ROIAlign on NumPy views of pinned host memory."""
     import ctypes
     import torch
@@ -375,11 +497,14 @@ def run_e2e(args, wl, shard, world, dev):
         buf = (ctypes.c_float * n).from_address(ptr)
         return np.frombuffer(buf, dtype=np.float32).reshape(shape), ptr
 
-    rng = np.random.default_rng(99)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)
     data, p0 = pinned(wl.data_shape)
     dy, p1 = pinned(wl.out_shape)
-    data[...] = rng.standard_normal(wl.data_shape, dtype=np.float32)
-    dy[...] = rng.standard_normal(wl.out_shape, dtype=np.float32)
+    # synthetic N(0,1) inputs, generated on the device and copied into the pinned host arrays
+    torch.from_numpy(data).copy_(torch.randn(wl.data_shape, dtype=torch.float32, device=dev, generator=gen))
+    torch.from_numpy(dy).copy_(torch.randn(wl.out_shape, dtype=torch.float32, device=dev, generator=gen))
+    torch.cuda.empty_cache()
     rois = shard.rois
     op = mobula.op.ROIAlign[np.ndarray](pooled_size=wl.pooled, spatial_scale=wl.scale,
                                         sampling_ratio=wl.sampling_ratio,
@@ -404,12 +529,13 @@ def run_e2e(args, wl, shard, world, dev):
     step_s = t.item()
     h2d = data.nbytes + dy.nbytes + 2 * rois.nbytes
     d2h = y.nbytes + dxh.nbytes
+    del y, dxh
     lib.mobula_host_free(ctypes.c_void_p(p0))
     lib.mobula_host_free(ctypes.c_void_p(p1))
-    return dict(value=wl.R * world / step_s, unit=UNIT, h2d_bytes_per_step=int(h2d),
+    return dict(value=total_rois / step_s, unit=UNIT, h2d_bytes_per_step=int(h2d),
                 d2h_bytes_per_step=int(d2h), ms_per_step=step_s * 1e3, steps=n,
                 api='mobula.op.ROIAlign[np.ndarray] (C-ABI, MOBULA_ROIALIGN_HOST_BUFFERS), '
-                    'inputs and results in page-locked host memory (NumPy arrays)')
+                    'inputs and results in page-locked host memory (NumPy arrays); bytes are per rank')
 
 
 _RESULT_FD = None

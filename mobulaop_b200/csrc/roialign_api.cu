@@ -104,7 +104,12 @@ struct DeviceState {
   bool probed = false;
   int num_sms = 0;
   int smem_optin = 0;
-  Buffer workspace;            // ROI tables of the plane kernels (one call at a time)
+  Buffer workspace;            // ROI tables of eager calls (one call at a time)
+  // Workspaces donated to CUDA graphs: a capture bakes the workspace address into the graph, so
+  // the buffer a capture used is never freed, grown or handed to an eager call again (it lives
+  // until mobula_roialign_release); the eager path allocates a fresh one on its next call.
+  Buffer graph_ws[8];
+  int graph_ws_count = 0;
   cudaEvent_t ws_done = nullptr;   // recorded after the last kernel that reads the workspace
   cudaStream_t ws_stream = nullptr;
   bool ws_used = false;
@@ -161,23 +166,33 @@ static bool is_capturing(cudaStream_t stream) {
   return status == cudaStreamCaptureStatusActive;
 }
 
-// Hands the per-device workspace to a call on `stream`.  The workspace is shared by every
-// stream of the device: a call on another stream waits for the previous user to finish
-// with it.  While `stream` is being captured into a CUDA graph nothing may be allocated
-// and eager events may not be waited on: the workspace must already be large enough (run
-// the call once before capturing), and ordering the graph's replays against eager calls on
-// other streams is the caller's business.
-static int acquire_workspace(DeviceState& st, size_t bytes, cudaStream_t stream) {
+// Hands a workspace to a call on `stream`.  Eager calls share one per-device buffer: a call on
+// another stream waits for the previous user to finish with it, and it grows on demand.  While
+// `stream` is being captured into a CUDA graph nothing may be allocated and eager events may
+// not be waited on: the capture takes over ("is donated") the current eager buffer, which must
+// already be large enough (run the same call once before capturing).  A donated buffer is never
+// freed, grown or used by an eager call again, so replays cannot read freed or overwritten
+// tables; ordering replays of DIFFERENT graphs against each other is the caller's business.
+static int acquire_workspace(DeviceState& st, size_t bytes, cudaStream_t stream, void** out) {
   if (is_capturing(stream)) {
-    if (bytes > st.workspace.bytes)
-      return fail(MOBULA_ERR_UNSUPPORTED,
-                  "stream capture: the %zu-byte workspace of this call does not exist yet; run the "
-                  "same call once outside the capture", bytes);
+    Buffer* donated = st.graph_ws_count ? &st.graph_ws[st.graph_ws_count - 1] : nullptr;
+    if (!donated || donated->bytes < bytes) {
+      if (st.workspace.bytes < bytes || st.graph_ws_count >= 8)
+        return fail(MOBULA_ERR_UNSUPPORTED,
+                    "stream capture: the %zu-byte workspace of this call does not exist yet; run the "
+                    "same call once outside the capture", bytes);
+      st.graph_ws[st.graph_ws_count] = st.workspace;     // donate; eager calls get a new buffer
+      donated = &st.graph_ws[st.graph_ws_count++];
+      st.workspace = Buffer();
+      st.ws_used = false;
+    }
+    *out = donated->ptr;
     return MOBULA_OK;
   }
   if (st.ws_used && st.ws_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, st.ws_done, 0));
   if (bytes > st.workspace.bytes && st.ws_used) CUDA_TRY(cudaEventSynchronize(st.ws_done));
   CUDA_TRY(st.workspace.reserve(bytes, stream));
+  *out = st.workspace.ptr;
   return MOBULA_OK;
 }
 
@@ -186,12 +201,13 @@ static int prepare_tables(DeviceState& st, const RoiAlignArgs& a, unsigned need,
                           unsigned flags, cudaStream_t stream, RoiTables* tables) {
   roi_tables_set_arena_override((flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) ? 0 : -1);
   const size_t bytes = roi_tables_bytes(a, need);
-  const int rc = acquire_workspace(st, bytes, stream);
+  void* ws = nullptr;
+  const int rc = acquire_workspace(st, bytes, stream, &ws);
   if (rc) {
     roi_tables_set_arena_override(-1);
     return rc;
   }
-  *tables = roi_tables_carve(a, need, pitch, st.workspace.ptr);
+  *tables = roi_tables_carve(a, need, pitch, ws);
   roi_tables_set_arena_override(-1);
   CUDA_TRY(launch_roi_tables(a, *tables, need, stream));
   return MOBULA_OK;
@@ -208,10 +224,7 @@ static int release_tables(DeviceState& st, cudaStream_t stream) {
 
 // Workspace of the resident kernels: same buffer, same hand-over rules as prepare_tables.
 static int prepare_workspace(DeviceState& st, size_t bytes, cudaStream_t stream, void** ws) {
-  const int rc = acquire_workspace(st, bytes, stream);
-  if (rc) return rc;
-  *ws = st.workspace.ptr;
-  return MOBULA_OK;
+  return acquire_workspace(st, bytes, stream, ws);
 }
 
 static int forward_device(DeviceState& st, int device, cudaStream_t stream, const float* data,
@@ -624,12 +637,14 @@ MOBULA_EXPORT void mobula_roialign_release(void) {
   for (int d = 0; d < count && d < kMaxDevices; ++d) {
     DeviceState& st = g_dev[d];
     std::lock_guard<std::mutex> lock(st.mu);
-    if (!st.workspace.ptr && !st.stage[0].ptr && !st.stage[1].ptr && !st.stage[2].ptr &&
-        !st.stage[3].ptr)
+    if (!st.workspace.ptr && !st.graph_ws_count && !st.stage[0].ptr && !st.stage[1].ptr &&
+        !st.stage[2].ptr && !st.stage[3].ptr)
       continue;
     cudaSetDevice(d);
     cudaDeviceSynchronize();
     st.workspace.release();
+    for (int k = 0; k < st.graph_ws_count; ++k) st.graph_ws[k].release();
+    st.graph_ws_count = 0;
     if (st.ws_done) cudaEventDestroy(st.ws_done);
     st.ws_done = nullptr;
     st.ws_used = false;

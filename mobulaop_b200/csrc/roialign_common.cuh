@@ -14,6 +14,8 @@
 
 namespace mobula_b200 {
 
+constexpr float kMaxAdaptiveGrid = 1024.0f;
+
 struct RoiGeom {
   int batch;            // ROIAlign.cpp:25
   float start_w, start_h;
@@ -36,12 +38,24 @@ __device__ __forceinline__ RoiGeom roi_decode(const float* __restrict__ roi, flo
   const float roi_h = fmaxf(__fsub_rn(end_h, g.start_h), 1.0f);
   g.bin_h = __fdiv_rn(roi_h, (float)pooled_h);
   g.bin_w = __fdiv_rn(roi_w, (float)pooled_w);
-  if (sampling_ratio > 0) {
-    g.grid_h = g.grid_w = sampling_ratio;
-  } else {
-    g.grid_h = __float2int_rz(ceilf(g.bin_h));
-    g.grid_w = __float2int_rz(ceilf(g.bin_w));
+  float gh = (float)sampling_ratio, gw = (float)sampling_ratio;
+  if (sampling_ratio <= 0) {
+    gh = ceilf(g.bin_h);
+    gw = ceilf(g.bin_w);
   }
+  // A ROI with a non-finite coordinate, or an adaptive grid beyond kMaxAdaptiveGrid samples per
+  // bin axis (a box thousands of pixels outside the map), would overflow the int grid sizes and
+  // keep a thread looping for minutes; the reference itself is undefined there ((int)inf,
+  // ROIAlign.cpp:47-51).  Such a ROI is moved outside the plane: every sample is rejected
+  // (bilinear.h:15-18), its output rows are zero and it scatters nothing.
+  const float probe = (g.start_w + g.start_h) + (g.bin_w + g.bin_h);
+  if (!(gh <= kMaxAdaptiveGrid && gw <= kMaxAdaptiveGrid) || !(fabsf(probe) <= 3.0e38f)) {
+    g.start_w = g.start_h = -1.0e30f;
+    g.bin_w = g.bin_h = 0.0f;
+    gh = gw = 1.0f;
+  }
+  g.grid_h = __float2int_rz(gh);
+  g.grid_w = __float2int_rz(gw);
   g.count = (float)(g.grid_h * g.grid_w);
   return g;
 }

@@ -74,7 +74,6 @@ def _make_classes(op, name):
     class _Function(torch.autograd.Function):
         @staticmethod
         def forward(ctx, record, *inputs):
-            ctx.record = record
             record.in_data = inputs
             record.req = ['write'] * len(inputs)
             first = inputs[0] if inputs else None
@@ -87,18 +86,24 @@ def _make_classes(op, name):
                 result = result if isinstance(result, (list, tuple)) else [result]
                 for dst, value in zip(record.out_data, result):
                     record.assign(dst, 'write', value)
-            if len(record.out_data) == 1:
-                return record.out_data[0]
-            return tuple(record.out_data)
+            outs = record.out_data
+            # the inputs go through autograd's own storage (version-counter check, no
+            # output -> grad_fn -> record -> output cycle); the record keeps scalars only
+            ctx.save_for_backward(*inputs)
+            ctx.record = record
+            record.in_data = record.out_data = None
+            return outs[0] if len(outs) == 1 else tuple(outs)
 
         @staticmethod
         @once_differentiable
         def backward(ctx, *out_grads):
             record = ctx.record
+            inputs = ctx.saved_tensors
             needs = ctx.needs_input_grad[1:]
+            record.in_data = inputs
             record.req = ['write' if n else 'null' for n in needs]
             record.in_grad = [torch.empty_like(d) if n else None
-                              for d, n in zip(record.in_data, needs)]
+                              for d, n in zip(inputs, needs)]
             record.out_grad = [g.contiguous() if g is not None else None for g in out_grads]
             result = record._backward(*record.out_grad)
             if result is not None:
@@ -106,7 +111,9 @@ def _make_classes(op, name):
                 for i in range(n_inputs):
                     if record.in_grad[i] is not None:
                         record.assign(record.in_grad[i], record.req[i], result[i])
-            return (None,) + tuple(record.in_grad)
+            grads = tuple(record.in_grad)
+            record.in_data = record.in_grad = record.out_grad = None
+            return (None,) + grads
 
     _Function.__name__ = '_%s_TORCH_FUNC' % name
 

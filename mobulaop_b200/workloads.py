@@ -8,7 +8,7 @@ import numpy as np
 
 class Workload(object):
     def __init__(self, name, N, C, H, W, rois_per_image, pooled, scale, sampling_ratio,
-                 min_box=16.0, max_box=512.0, stress=False):
+                 min_box=16.0, max_box=512.0, stress=False, literal=False):
         self.name = name
         self.N, self.C, self.H, self.W = N, C, H, W
         self.rois_per_image = rois_per_image
@@ -17,6 +17,9 @@ class Workload(object):
         self.sampling_ratio = int(sampling_ratio)
         self.min_box, self.max_box = float(min_box), float(max_box)
         self.stress = stress
+        # literal: the inputs of the reference's own benchmark script instead of random FPN boxes
+        # (benchmark/benchmark_roi_align.py:15-21: data = arange, rois[i] = [i % N, 0, 0, i % H, i % W])
+        self.literal = literal
 
     @property
     def R(self):
@@ -34,7 +37,7 @@ class Workload(object):
         """Same geometry with fewer images / channels / ROIs (oracle-sized samples)."""
         return Workload(name or self.name + '-sample', N or self.N, C or self.C, self.H, self.W,
                         rois_per_image or self.rois_per_image, self.pooled, self.scale,
-                        self.sampling_ratio, self.min_box, self.max_box, self.stress)
+                        self.sampling_ratio, self.min_box, self.max_box, self.stress, self.literal)
 
     def describe(self):
         return dict(workload=self.name, N=self.N, C=self.C, H=self.H, W=self.W, R=self.R,
@@ -52,7 +55,9 @@ class Workload(object):
 
 
 def make_rois(wl, seed=0):
-    """[R, 5] float32, grouped by image, `rois_per_image` each."""
+    """[R, 5] float32, `rois_per_image` per image (grouped by image unless `wl.literal`)."""
+    if wl.literal:
+        return literal_benchmark_inputs(wl.N, 1, wl.H, wl.W, wl.R)[1]
     rng = np.random.default_rng(seed + 1000003)
     img_w, img_h = wl.W / wl.scale, wl.H / wl.scale
     out = np.empty((wl.R, 5), np.float32)
@@ -86,7 +91,10 @@ def make_rois(wl, seed=0):
 
 def make_inputs(wl, seed=0, with_dy=True):
     rng = np.random.default_rng(seed)
-    data = rng.standard_normal(wl.data_shape, dtype=np.float32)
+    if wl.literal:
+        data = np.arange(int(np.prod(wl.data_shape)), dtype=np.float32).reshape(wl.data_shape)
+    else:
+        data = rng.standard_normal(wl.data_shape, dtype=np.float32)
     rois = make_rois(wl, seed)
     dy = rng.standard_normal(wl.out_shape, dtype=np.float32) if with_dy else None
     return data, rois, dy
@@ -101,8 +109,9 @@ def literal_benchmark_inputs(N=2, C=1024, H=14, W=14, R=512):
 
 CONFIGS = {
     # BASELINE.json configs[0]: the reference's own CPU-runnable benchmark shape
-    'C1': Workload('C1-bench-7x7-sr2', 2, 1024, 14, 14, 256, (7, 7), 1.0, 2),
-    'C1-literal': Workload('C1-bench-literal-2x2-sr1', 2, 1024, 14, 14, 256, (2, 2), 1.0, 1),
+    # (the script's literal inputs; BASELINE.json quotes it at 7x7 / sr 2, the script itself runs 2x2 / sr 1)
+    'C1': Workload('C1-bench-7x7-sr2', 2, 1024, 14, 14, 256, (7, 7), 1.0, 2, literal=True),
+    'C1-literal': Workload('C1-bench-literal-2x2-sr1', 2, 1024, 14, 14, 256, (2, 2), 1.0, 1, literal=True),
     # configs[1]: the configuration the metric is quoted on
     'C2': Workload('C2-box-head', 2, 256, 200, 272, 512, (7, 7), 0.25, 2),
     'C3': Workload('C3-mask-head', 8, 256, 128, 128, 1000, (14, 14), 0.25, 2),

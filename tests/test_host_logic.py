@@ -225,3 +225,57 @@ def test_result_arrays_fall_back_to_pageable_memory_without_a_gpu():
     del big                                              # the buffer outlives its first owner
     assert view[0] == 1.0
     pinned.drain()
+
+
+def test_cupy_adapter_attribute_mapping(mobula):
+    """CuPy is absent from the image: the adapter is exercised against a stub
+    module exposing .data.ptr / .device.id / .dtype / .flags (tests/cupy_stub.py).  No launch
+    here -- the GPU leg is tests/test_parity_gpu.py::test_cupy_operator_through_stub."""
+    import ctypes
+    try:
+        import cupy
+    except ImportError:
+        import cupy_stub
+        cupy = cupy_stub.install()
+    if not getattr(cupy, '__stub__', False):
+        pytest.skip('a real CuPy is installed; the stub test does not apply')
+    be = mobula.glue.backend
+    a = cupy.zeros((2, 3, 4, 5), np.float32)
+    glue_mod = be.get_var_glue(a)
+    assert glue_mod is not None and glue_mod.__name__.endswith('cupy_glue')
+    assert be.get_var_type_glue(cupy.ndarray) is glue_mod
+    view = glue_mod.Tensor(a)
+    assert view.ctype is ctypes.c_float
+    assert view.dev_id == a.device.id
+    assert view.shape == (2, 3, 4, 5)
+    ptr = view.data_ptr
+    assert isinstance(ptr, ctypes.c_void_p) and ptr.value == a.data.ptr
+    strided = a[:, :, ::2]
+    assert not strided.flags.c_contiguous
+    ptr2, keep = glue_mod.Tensor(strided).data_ptr        # copy made, kept alive for the call
+    assert keep.flags.c_contiguous and ptr2.value == keep.data.ptr
+    assert isinstance(view.stream, int)
+    # the operator class is generated for the CuPy array module
+    op = mobula.op.ROIAlign[cupy.ndarray](pooled_size=(2, 2), spatial_scale=1.0, sampling_ratio=1)
+    assert op.F is cupy
+    assert op.infer_shape([(1, 3, 8, 8), (4, 5)])[1] == [[4, 3, 2, 2]]
+    with pytest.raises(TypeError):
+        be.get_args_glue(np.zeros(1), a)
+
+
+def test_pinned_pool_is_bounded():
+    """The result cache of the NumPy adapter keeps at most `_MAX_POOL_BYTES` of page-locked
+    memory, whatever sizes come and go (detection workloads change R every step)."""
+    from mobulaop_b200.glue import pinned
+    pinned.drain()
+    freed = []
+    pinned._pool_put(100, 0xA0, free=freed.append, cap=250)
+    pinned._pool_put(100, 0xB0, free=freed.append, cap=250)
+    assert pinned.pooled_bytes() == 200 and not freed
+    pinned._pool_put(100, 0xC0, free=freed.append, cap=250)     # evicts the oldest
+    assert freed == [0xA0] and pinned.pooled_bytes() == 200
+    pinned._pool_put(300, 0xD0, free=freed.append, cap=250)     # larger than the cap: not kept
+    assert freed == [0xA0, 0xD0] and pinned.pooled_bytes() == 200
+    assert pinned._pool_take(100) == 0xC0                        # most recently released first
+    assert pinned._pool_take(100) == 0xB0
+    assert pinned._pool_take(100) is None and pinned.pooled_bytes() == 0

@@ -526,32 +526,200 @@ def test_same_result_on_every_gpu(direct, native, torch):
 
 
 # ---- full BASELINE sizes: size-independent properties ----------------------------------------
-@pytest.mark.parametrize('key', ['C2', 'C3'])
-def test_full_size_properties(direct, oracle, torch, key):
+def _bits_equal(torch, a, b):
+    return bool(torch.equal(a.view(torch.int32), b.view(torch.int32)))
+
+
+@pytest.mark.parametrize('key', ['C2', 'C3', 'C4', 'C5'])
+def test_full_size_properties(native, oracle, torch, key):
+    """Every BASELINE configuration at its FULL size.  The tensors stay on the device (C4 is
+    3.6 GB of feature maps); only channel slices travel to the host for the oracle."""
+    from mobulaop_b200 import _native
     wl = WL.CONFIGS[key]
-    data, rois, dy = WL.make_inputs(wl, seed=0)
-    y = direct.forward(data, rois, wl.pooled, wl.scale, wl.sampling_ratio)
-    dx = direct.backward(dy, rois, data.shape, wl.scale, wl.sampling_ratio)
+    dev = torch.device('cuda', 0)
+    data_h, rois_h, dy_h = WL.make_inputs(wl, seed=0)
+    if key == 'C5':
+        # the stress set must contain what it is for: grids of 16+ samples per bin axis,
+        # degenerate and fully-outside boxes
+        gi = oracle.bookkeeping(rois_h, (wl.H, wl.W), wl.pooled, wl.scale, wl.sampling_ratio, 1)[0]
+        assert gi[:, 1].max() >= 16 and gi[:, 2].max() >= 16 and gi[:, 1].min() == 1
+    data = torch.from_numpy(data_h).to(dev)
+    rois = torch.from_numpy(rois_h).to(dev)
+    dy = torch.from_numpy(dy_h).to(dev)
+    PH, PW = wl.pooled
+    sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def forward():
+        out = torch.full(wl.out_shape, float('nan'), device=dev)
+        _native.check(native.mobula_roialign_forward_f32(
+            0, sp, p(data), p(rois), p(out), wl.R, wl.N, wl.C, wl.H, wl.W, PH, PW, wl.scale,
+            wl.sampling_ratio, _native.make_flags()))
+        return out
+
+    def backward(g, mode):
+        dx = torch.full(wl.data_shape, float('nan'), device=dev)
+        _native.check(native.mobula_roialign_backward_f32(
+            0, sp, p(g), p(rois), p(dx), wl.R, wl.N, wl.C, wl.H, wl.W, PH, PW, wl.scale,
+            wl.sampling_ratio, mode, _native.make_flags()))
+        return dx
+
+    y = forward()
+    dx = backward(dy, _native.BWD_ATOMIC)
+    torch.cuda.synchronize(dev)
     # (1) a channel slice of the full-size result equals the oracle on that slice, all ROIs
     cs = [0, wl.C // 2, wl.C - 1]
-    sub = np.ascontiguousarray(data[:, cs])
-    assert_bit_exact(np.ascontiguousarray(y[:, cs]),
-                     oracle.forward(sub, rois, wl.pooled, wl.scale, wl.sampling_ratio, threads=0))
-    dys = np.ascontiguousarray(dy[:, cs])
-    ref = oracle.backward(dys, rois, sub.shape, wl.scale, wl.sampling_ratio)
-    ref_abs = oracle.backward(np.abs(dys), rois, sub.shape, wl.scale, wl.sampling_ratio)
-    assert_scatter_close(np.ascontiguousarray(dx[:, cs]), ref, ref_abs, rtol=1e-5)
+    sub = np.ascontiguousarray(data_h[:, cs])
+    assert_bit_exact(y[:, cs].contiguous().cpu().numpy(),
+                     oracle.forward(sub, rois_h, wl.pooled, wl.scale, wl.sampling_ratio, threads=0))
+    dys = np.ascontiguousarray(dy_h[:, cs])
+    ref = oracle.backward(dys, rois_h, sub.shape, wl.scale, wl.sampling_ratio)
+    ref_abs = oracle.backward(np.abs(dys), rois_h, sub.shape, wl.scale, wl.sampling_ratio)
+    assert_scatter_close(dx[:, cs].contiguous().cpu().numpy(), ref, ref_abs, rtol=1e-5)
     # (2) adjoint identity <fwd(x), dy> == <x, bwd(dy)> ties the two kernels together
-    lhs = float(np.vdot(y.astype(np.float64), dy.astype(np.float64)))
-    rhs = float(np.vdot(data.astype(np.float64), dx.astype(np.float64)))
-    scale = float(np.linalg.norm(y.astype(np.float64)) * np.linalg.norm(dy.astype(np.float64)))
+    lhs = float(torch.dot(y.double().reshape(-1), dy.double().reshape(-1)))
+    rhs = float(torch.dot(data.double().reshape(-1), dx.double().reshape(-1)))
+    scale = float(torch.linalg.vector_norm(y.double()) * torch.linalg.vector_norm(dy.double()))
     assert abs(lhs - rhs) <= 1e-5 * scale, (lhs, rhs, scale)
+    del y, dx
     # (3) deterministic mode: bit-reproducible and equal to the canonical order
-    d1 = direct.backward(dy, rois, data.shape, wl.scale, wl.sampling_ratio, mode='deterministic')
-    d2 = direct.backward(dy, rois, data.shape, wl.scale, wl.sampling_ratio, mode='deterministic')
-    assert_bit_exact(d1, d2)
-    assert_bit_exact(np.ascontiguousarray(d1[:, cs]), ref)
+    d1 = backward(dy, _native.BWD_DETERMINISTIC)
+    d2 = backward(dy, _native.BWD_DETERMINISTIC)
+    assert _bits_equal(torch, d1, d2)
+    assert_bit_exact(d1[:, cs].contiguous().cpu().numpy(), ref)
+    del d2
     # (4) linearity of the scatter in dy (exact for power-of-two factors)
-    d4 = direct.backward(dy * np.float32(4), rois, data.shape, wl.scale, wl.sampling_ratio,
-                         mode='deterministic')
-    assert_bit_exact(d4, d1 * np.float32(4))
+    d4 = backward(dy * 4.0, _native.BWD_DETERMINISTIC)
+    assert _bits_equal(torch, d4, d1 * 4.0)
+
+
+# ---- the sharded path on the devices (SURVEY.md 8e, BASELINE config 4) ---------------------------
+def test_sharded_cuda_path_matches_single_device(native, torch, oracle):
+    """A C4-shaped mini problem split by image with sharding.make_shard, every shard run through
+    the CUDA path on its own device (all visible GPUs; four shards in turn on one GPU when only
+    one is there), reassembled, and compared bit for bit with the single-device result and the
+    oracle: forward and deterministic backward; the atomic backward within its tolerance."""
+    from mobulaop_b200 import sharding as S
+    G = torch.cuda.device_count()
+    world = G if G >= 2 else 4
+    wl = WL.CONFIGS['C4'].scaled(N=2 * world + 1, C=4, rois_per_image=48)     # uneven image split
+    data, rois, dy = WL.make_inputs(wl, seed=29)
+    perm = np.random.default_rng(3).permutation(len(rois))                    # rows not grouped by image
+    rois, dy = np.ascontiguousarray(rois[perm]), np.ascontiguousarray(dy[perm])
+    rois[5, 0] = wl.N + 3                                                     # owned by nobody
+    rois[9, 0] = -2
+    shards = S.make_shards(rois, wl.N, world)
+    ys, dxs, dxa = [], [], []
+    for s in shards:
+        d = Direct(native, torch, device=s.rank % G)
+        local = np.ascontiguousarray(data[s.image_begin:s.image_end])
+        ys.append(d.forward(local, s.rois, wl.pooled, wl.scale, wl.sampling_ratio))
+        g = S.scatter_rows(s, dy)
+        dxs.append(d.backward(g, s.rois, local.shape, wl.scale, wl.sampling_ratio, mode='deterministic'))
+        dxa.append(d.backward(g, s.rois, local.shape, wl.scale, wl.sampling_ratio))
+    y = S.assemble_rows(shards, ys, wl.R)
+    dx = S.assemble_images(shards, dxs)
+    single = Direct(native, torch, device=0)
+    assert_bit_exact(y, single.forward(data, rois, wl.pooled, wl.scale, wl.sampling_ratio))
+    assert_bit_exact(dx, single.backward(dy, rois, data.shape, wl.scale, wl.sampling_ratio,
+                                         mode='deterministic'))
+    good = np.array([r for r in range(wl.R) if r not in (5, 9)])
+    assert not y[[5, 9]].any()
+    assert_bit_exact(y[good], oracle.forward(data, rois[good], wl.pooled, wl.scale, wl.sampling_ratio, threads=0))
+    dyg = np.ascontiguousarray(dy[good])
+    ref = oracle.backward(dyg, rois[good], data.shape, wl.scale, wl.sampling_ratio)
+    assert_bit_exact(dx, ref)
+    ref_abs = oracle.backward(np.abs(dyg), rois[good], data.shape, wl.scale, wl.sampling_ratio)
+    assert_scatter_close(S.assemble_images(shards, dxa), ref, ref_abs, rtol=1e-5)
+
+
+# ---- CuPy adapter (through a stub module: CuPy is not in the image) ---------------------------
+def test_cupy_operator_through_stub(api, oracle):
+    try:
+        import cupy
+    except ImportError:
+        import cupy_stub
+        cupy = cupy_stub.install()
+    g = load_golden('fpn_14x14_sr2')
+    data, rois, dy = cupy.asarray(g['data']), cupy.asarray(g['rois']), cupy.asarray(g['dy'])
+    op = api.op.ROIAlign[cupy.ndarray](pooled_size=g['pooled'], spatial_scale=g['scale'],
+                                       sampling_ratio=g['sr'], deterministic=True)
+    y = op(data, rois)
+    assert isinstance(y, cupy.ndarray)
+    assert_bit_exact(y.get(), g['y'])
+    dx, drois = op.backward(dy)
+    assert_bit_exact(dx.get(), g['dx'])
+    assert not drois.get().any()
+    # plain call form picks the adapter from the argument types
+    y2 = api.op.ROIAlign(data, rois, pooled_size=g['pooled'], spatial_scale=g['scale'],
+                         sampling_ratio=g['sr'])
+    assert_bit_exact(y2.get(), g['y'])
+    # a non-contiguous view is copied for the call
+    wide = cupy.asarray(np.repeat(g['data'], 2, axis=3))
+    y3 = op(wide[:, :, :, ::2], rois)
+    assert_bit_exact(y3.get(), g['y'])
+
+
+# ---- hostile ROIs -------------------------------------------------------------------------------
+@pytest.mark.parametrize('sr', [0, 2])
+def test_nonfinite_and_gigantic_rois_do_not_hang(direct, oracle, sr):
+    """A non-finite coordinate, or an adaptive grid of more than 1024 samples per bin axis, would
+    overflow the reference's int grid sizes ((int)inf, ROIAlign.cpp:47-51) and spin a GPU thread
+    for minutes: such ROIs produce zero rows and no gradient; their neighbours are untouched."""
+    rng = np.random.default_rng(4)
+    data = rng.standard_normal((1, 3, 20, 24)).astype(np.float32)
+    rois = np.array([[0, 2, 2, 30, 40],
+                     [0, 1, 1, np.inf, 9],
+                     [0, np.nan, 1, 5, 9],
+                     [0, 0, 0, 3.0e7, 3.0e7],
+                     [0, 5, 6, 60, 70]], np.float32)
+    dy = rng.standard_normal((5, 3, 3, 3)).astype(np.float32)
+    bad = [1, 2] + ([3] if sr == 0 else [])
+    good = [r for r in range(5) if r not in bad]
+    y_ref = oracle.forward(data, rois[good], (3, 3), 0.5, sr, threads=0)
+    dyg = np.ascontiguousarray(dy[good])
+    dx_ref = oracle.backward(dyg, rois[good], data.shape, 0.5, sr)
+    dx_abs = oracle.backward(np.abs(dyg), rois[good], data.shape, 0.5, sr)
+    for algo in ('auto', 'gather'):
+        y = direct.forward(data, rois, (3, 3), 0.5, sr, algo=algo)
+        assert_bit_exact(y[good], y_ref)
+        assert not y[bad].any()
+        dx = direct.backward(dy, rois, data.shape, 0.5, sr, algo=algo)
+        assert_scatter_close(dx, dx_ref, dx_abs, rtol=1e-5)
+    assert_bit_exact(direct.backward(dy, rois, data.shape, 0.5, sr, mode='deterministic'), dx_ref)
+
+
+def test_graph_replay_survives_workspace_growth(api, torch, oracle):
+    """A captured graph keeps the workspace it was captured with: a later, larger eager call
+    allocates its own and must not free or overwrite the tables the replays read."""
+    wl = _sample('C2', C=3, rois_per_image=40)
+    big = _sample('C2', C=3, rois_per_image=900)
+    dev = torch.device('cuda', 0)
+    PH, PW = wl.pooled
+    data, rois_h, _ = WL.make_inputs(wl, seed=8)
+    x = torch.from_numpy(data).to(dev)
+    rois = torch.from_numpy(rois_h).to(dev)
+    y = torch.empty(wl.out_shape, device=dev)
+
+    def step():
+        api.func.roi_align_forward(int(y.numel()), x, wl.scale, wl.C, wl.H, wl.W, PH, PW,
+                                   wl.sampling_ratio, rois, y)
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    # an eager call with 22x the ROIs: needs a larger workspace than the captured one
+    bdata, brois, _ = WL.make_inputs(big, seed=9)
+    by = torch.empty(big.out_shape, device=dev)
+    api.func.roi_align_forward(int(by.numel()), torch.from_numpy(bdata).to(dev), big.scale, big.C, big.H,
+                               big.W, PH, PW, big.sampling_ratio, torch.from_numpy(brois).to(dev), by)
+    y.fill_(float('nan'))
+    graph.replay()
+    torch.cuda.synchronize(dev)
+    assert_bit_exact(y.cpu().numpy(), oracle.forward(data, rois_h, wl.pooled, wl.scale, wl.sampling_ratio))
+    assert_bit_exact(by.cpu().numpy(), oracle.forward(bdata, brois, big.pooled, big.scale, big.sampling_ratio))

@@ -20,8 +20,9 @@ BWD_DETERMINISTIC = 1
 FLAG_ACCUMULATE = 1
 FLAG_HOST_BUFFERS = 2
 ALGO_SHIFT = 8
-ALGO_AUTO, ALGO_GATHER, ALGO_PLANE, ALGO_RESIDENT = 0, 1, 2, 3
-ALGOS = {'auto': ALGO_AUTO, 'gather': ALGO_GATHER, 'plane': ALGO_PLANE, 'resident': ALGO_RESIDENT}
+ALGO_AUTO, ALGO_GATHER, ALGO_PLANE, ALGO_RESIDENT, ALGO_SWEEP = 0, 1, 2, 3, 4
+ALGOS = {'auto': ALGO_AUTO, 'gather': ALGO_GATHER, 'plane': ALGO_PLANE, 'resident': ALGO_RESIDENT,
+         'sweep': ALGO_SWEEP}
 
 # every symbol include/mobula_roialign.h declares
 EXPORTED_SYMBOLS = (

@@ -16,7 +16,8 @@ LIB_DIR = os.path.join(PKG_DIR, 'lib')
 LIB_NAME = 'libmobula_roialign_sm100.so'
 LIB_PATH = os.path.join(LIB_DIR, LIB_NAME)
 
-SOURCES = ['roialign_api.cu', 'roialign_gather.cu', 'roialign_tables.cu', 'roialign_plane.cu', 'roialign_resident.cu']
+SOURCES = ['roialign_api.cu', 'roialign_gather.cu', 'roialign_tables.cu', 'roialign_plane.cu', 'roialign_resident.cu',
+           'roialign_sweep.cu']
 HEADERS = ['roialign_kernels.h', 'roialign_common.cuh', 'ptx_sm100.cuh',
            os.path.join('..', '..', 'include', 'mobula_roialign.h')]
 
@@ -48,25 +49,56 @@ def is_stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > built for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile the library in-tree; returns its path."""
-    if not force and not is_stale():
-        return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [find_nvcc()] + NVCC_FLAGS + os.environ.get('MOBULA_NVCC_EXTRA', '').split()
+def _object_path(src):
+    return os.path.join(LIB_DIR, 'obj', os.path.basename(src)[:-3] + '.o')
+
+
+def _compile(nvcc, src, obj, verbose):
+    cmd = [nvcc] + [f for f in NVCC_FLAGS if f != '-shared'] + os.environ.get('MOBULA_NVCC_EXTRA', '').split()
     if os.path.exists('/usr/bin/g++'):
         cmd += ['-ccbin', '/usr/bin/g++']     # the image's $CC wrapper lacks libgomp specs
     if verbose:
         cmd += ['-Xptxas', '-v']
-    tmp = LIB_PATH + '.tmp.%d' % os.getpid()
-    cmd += ['-o', tmp] + sources()
+    tmp = obj + '.tmp.%d' % os.getpid()
+    cmd += ['-c', src, '-o', tmp]
     out = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or out.returncode != 0:
         sys.stderr.write(' '.join(cmd) + '\n' + out.stdout + out.stderr)
     if out.returncode != 0:
         if os.path.exists(tmp):
             os.remove(tmp)
-        raise RuntimeError('nvcc failed building %s' % LIB_NAME)
+        raise RuntimeError('nvcc failed compiling %s' % src)
+    os.replace(tmp, obj)
+
+
+def build(force=False, verbose=False):
+    """Compile the library in-tree (one object per source, in parallel); returns its path."""
+    if not force and not is_stale():
+        return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(os.path.join(LIB_DIR, 'obj'), exist_ok=True)
+    nvcc = find_nvcc()
+    headers = [os.path.normpath(os.path.join(CSRC_DIR, h)) for h in HEADERS]
+    newest_header = max(os.path.getmtime(h) for h in headers if os.path.exists(h))
+    todo = []
+    for src in sources():
+        obj = _object_path(src)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header):
+            todo.append((src, obj))
+    with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as pool:
+        for fut in [pool.submit(_compile, nvcc, src, obj, verbose) for src, obj in todo]:
+            fut.result()
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a']
+    if os.path.exists('/usr/bin/g++'):
+        cmd += ['-ccbin', '/usr/bin/g++']
+    tmp = LIB_PATH + '.tmp.%d' % os.getpid()
+    cmd += ['-o', tmp] + [_object_path(src) for src in sources()]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if out.returncode != 0:
+        sys.stderr.write(' '.join(cmd) + '\n' + out.stdout + out.stderr)
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        raise RuntimeError('nvcc failed linking %s' % LIB_NAME)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

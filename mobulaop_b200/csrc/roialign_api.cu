@@ -152,6 +152,12 @@ static int images_from_host_rois(const float* rois, int num_rois) {
   return n;
 }
 
+// MOBULA_ROIALIGN_PREFER_SWEEP=0 keeps the automatic choice on the resident kernels
+static bool prefer_sweep() {
+  static const bool v = [] { const char* e = getenv("MOBULA_ROIALIGN_PREFER_SWEEP"); return e ? atoi(e) != 0 : false; }();
+  return v;
+}
+
 static unsigned algo_of(unsigned flags) {
   return (flags & MOBULA_ROIALIGN_ALGO_MASK) >> MOBULA_ROIALIGN_ALGO_SHIFT;
 }
@@ -233,9 +239,27 @@ static int forward_device(DeviceState& st, int device, cudaStream_t stream, cons
   (void)rois;
   const int accumulate = (flags & MOBULA_ROIALIGN_ACCUMULATE) ? 1 : 0;
   const unsigned algo = algo_of(flags);
-  if (algo > MOBULA_ROIALIGN_ALGO_RESIDENT)
+  if (algo > MOBULA_ROIALIGN_ALGO_SWEEP)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown forward algorithm %u", algo);
   const bool no_tables = (flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) != 0;
+  {
+    SweepPlan splan;
+    const bool want = algo == MOBULA_ROIALIGN_ALGO_SWEEP || (algo == MOBULA_ROIALIGN_ALGO_AUTO && prefer_sweep());
+    const bool sweep_ok = want && !no_tables && sweep_supported(a, data, st.smem_optin, st.num_sms, &splan);
+    if (algo == MOBULA_ROIALIGN_ALGO_SWEEP && !sweep_ok)
+      return fail(MOBULA_ERR_UNSUPPORTED,
+                  "sweep algorithm needs num_images in [1, 4096], width %% 4 == 0, 16-byte aligned data, "
+                  "pooled_w <= 16 and at least four %d-pixel rows of 32 channels within %d bytes of shared "
+                  "memory", a.width, st.smem_optin);
+    if (sweep_ok) {
+      t_algo[0] = "sweep";
+      void* ws = nullptr;
+      int rc = prepare_workspace(st, sweep_fwd_workspace(a, splan), stream, &ws);
+      if (rc) return rc;
+      CUDA_TRY(launch_fwd_sweep(a, splan, ws, data, out, accumulate, st.num_sms, stream));
+      return release_tables(st, stream);
+    }
+  }
   ResidentPlan rplan;
   const bool resident_ok = !no_tables && resident_supported(a, data, st.smem_optin, &rplan);
   if (algo == MOBULA_ROIALIGN_ALGO_RESIDENT && !resident_ok)
@@ -275,11 +299,12 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
   (void)device;
   (void)rois;
   const int accumulate = (flags & MOBULA_ROIALIGN_ACCUMULATE) ? 1 : 0;
-  const unsigned algo = algo_of(flags);
+  unsigned algo = algo_of(flags);
   if (mode != MOBULA_ROIALIGN_BWD_ATOMIC && mode != MOBULA_ROIALIGN_BWD_DETERMINISTIC)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward mode %d", mode);
-  if (algo > MOBULA_ROIALIGN_ALGO_RESIDENT)
+  if (algo > MOBULA_ROIALIGN_ALGO_SWEEP)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward algorithm %u", algo);
+  if (algo == MOBULA_ROIALIGN_ALGO_SWEEP) algo = MOBULA_ROIALIGN_ALGO_AUTO;   // no sweep backward yet
   if (!accumulate && a.num_images < 0)
     return fail(MOBULA_ERR_INVALID_ARGUMENT,
                 "backward without MOBULA_ROIALIGN_ACCUMULATE needs num_images >= 0");

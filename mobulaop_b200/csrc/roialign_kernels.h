@@ -145,4 +145,20 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
                                 const float* dy, float* dx, int accumulate, int deterministic, int num_sms,
                                 cudaStream_t stream);
 
+// ---- sweep family (roialign_sweep.cu): lane = channel, TMA-fed ring of full-width rows of 32
+// channels, items sorted by row; any sampling grid, any pooled height, pooled width <= 16 ------
+struct SweepPlan {
+  int wbox, nbox, xb, rowf;   // TMA box width, boxes per 8-channel group row, first pixel of box 1, floats per ring row
+  int ring, span;             // ring rows; rows one item's taps may span
+  int pwp;                    // staging pitch
+  int segs;                   // row segments per image
+  int colcap;                 // column records per ROI
+  size_t smem;
+};
+
+bool sweep_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_optin, int num_sms, SweepPlan* plan);
+size_t sweep_fwd_workspace(const RoiAlignArgs& a, const SweepPlan& plan);
+cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void* workspace, const float* data,
+                             float* out, int accumulate, int num_sms, cudaStream_t stream);
+
 }  // namespace mobula_b200

@@ -1,0 +1,745 @@
+// "sweep" kernels: lane = channel.
+//
+// The resident kernels keep ONE channel plane in shared memory and map lanes to samples, so
+// every bilinear tap is a 4-byte gather with whatever bank conflicts the ROI geometry produces
+// (measured 1.8 wavefronts per load, 47 % of all shared-memory wavefronts are replays).  Here a
+// CTA holds a few full-width ROWS of 32 channels of one image and the 32 lanes of a warp are
+// those 32 channels: a warp works on one sample at a time, the tap address is warp-uniform up
+// to the lane's channel offset, and the channel offsets are laid out so that the 32 lanes hit
+// the 32 banks -- one wavefront per tap load whatever the ROI looks like.  Geometry being
+// warp-uniform also means no divergence: adaptive grids (sampling_ratio <= 0), any pooled
+// shape, clamped and rejected samples are uniform branches.
+//
+// Data movement: a ring of rows in shared memory filled by TMA (cp.async.bulk.tensor, SASS
+// UTMALDG) from a 4-D tensor map over the caller's NCHW tensor: per ring row and per group of 8
+// channels one box {Wbox, 1 row, 8 channels}.  The box of channel group g starts g pixels left
+// of the plane (out-of-bounds elements are zero-filled), and Wbox / 4 is odd, so channel
+// (g, cl) of pixel x sits at word  cl * Wbox + x + g  of its group block: banks
+// 4 * (cl * odd mod 8) + g -- all 32 distinct.  Planes wider than 253 pixels take two boxes per
+// group.  The CTA sweeps its rows top to bottom; every feature-map row is read once per sweep.
+//
+// Work: (image, 32-channel group, row segment) units from a queue; inside a unit the "items"
+// -- runs of sample rows of one bin row of one ROI whose taps span at most kSpan rows -- sorted
+// by first row and handed to the 16 consumer warps in that order.  A bin row whose sample rows
+// are too far apart for one item is a chain of items: the running sums travel through a
+// scratch buffer (L2) and a "done" bit per item, so the reference's summation order (sample
+// rows outer, sample columns inner, ROIAlign.cpp:56-74) is kept and the result is bit-identical.
+// A bin row belongs to the segment that holds its LAST sample row; a segment's sweep starts as
+// far above its first row as its bin rows reach, so no partial sum crosses CTAs.
+//
+// Reference arithmetic: /root/reference/opzoo/ROIAlign/ROIAlign.cpp:9-76, bilinear.h:10-59.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "roialign_kernels.h"
+#include "roialign_common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace mobula_b200 {
+
+namespace {
+
+constexpr int kConsumers = 16;                        // warps that compute
+constexpr int kSweepThreads = (kConsumers + 1) * 32;  // + one producer warp (TMA)
+constexpr int kMaxRing = 16;
+constexpr int kMinRing = 4;
+constexpr int kMaxPooledW = 16;
+constexpr int kMaxPlaneH = 4095;                      // item records keep rows in 12 bits
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- table records ----------------------------------------------------------------------
+// One ROI, channel independent (64 bytes).
+struct __align__(16) SweepHdr {
+  int roi;               // row of the caller's roi table = output row
+  int batch;             // image, -1: batch index outside [0, N)
+  int grid;              // grid_h | grid_w << 16
+  float count;           // (float)(grid_h * grid_w)
+  float start_h, bin_h;
+  unsigned col_base;     // first column record of this ROI
+  int ncols;             // compacted tables: number of (valid) column records
+  unsigned short cstart[16];   // compacted tables: first record of bin column pw (end = next / ncols)
+};
+
+// A sample column: word offsets of the low / high tap inside a ring row's group block
+// (lo | hi << 16; 0xffffffff: the sample is outside the plane, bilinear.h:15-18) and the
+// fraction lx = weight of the high tap.
+typedef uint2 ColRec;
+constexpr unsigned kColInvalid = 0xffffffffu;
+
+// An item: sample rows [sy, sy + n) of bin row ph of ROI `roi`; taps in rows [key, key + dy].
+//   w0 roi   w1 sy | n << 16   w2 key | dy << 12 | ph << 16 | flags << 30   w3 predecessor item
+// flags: 1 = first item of its bin row (sums start at 0), 2 = last (divide and write the output)
+typedef uint4 ItemRec;
+constexpr unsigned kNoDep = 0xffffffffu;
+
+struct SweepParams {
+  const float* rois;
+  float* out;
+  int num_rois, num_images;
+  int channels;          // channel stride of data / out
+  int c_work;            // channels this call works on
+  int ncg;               // ceil(c_work / 32)
+  int height, width, pooled_h, pooled_w;
+  float scale;
+  int sampling_ratio;
+  int accumulate;
+  // shared-memory geometry
+  int wbox, nbox, xb;    // box width (floats), boxes per group row, first pixel of box 1
+  int rowf;              // floats per ring row = 4 * nbox * 8 * wbox
+  int ring, span;        // ring rows, max rows an item's taps may span
+  unsigned ring_magic;   // floor(2^32 / ring) + 1: q / ring == umulhi(q, magic)
+  int pwp;               // staging pitch per channel (pooled_w | 1)
+  int segs;              // row segments per image
+  int colcap;            // column records per ROI
+  int compact;           // column records hold only the samples inside the plane, per-bin ranges
+                         // in the header (every sampling ratio but 2)
+  // tables
+  int* cnt;              // [N * segs * H] items per (image, segment, first row); cursor in pass 2
+  int* start;            // [N * segs * H + 1] exclusive scan of cnt
+  int* unit_rows;        // [N * segs] 1 + last row any item of the unit touches
+  int* unit_counter;     // persistent-CTA queue
+  unsigned* done;        // one bit per item
+  SweepHdr* hdr;         // [R]
+  ColRec* cols;          // [R * colcap]
+  ItemRec* items;
+  float* scratch;        // running sums of chained items: [(roi * PH + ph) * ncg + cg][PW][32]
+};
+
+__host__ __device__ inline int seg_of_row(int y, int segs, int height) { return (int)(((long long)y * segs) / height); }
+
+// ---- pass 1 / pass 2 over the ROIs: one warp per ROI ---------------------------------------
+// PASS 1: header, column records, item counts.  PASS 2: item records at their sorted position.
+template <int PASS>
+__global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
+  ptx::chain_enter();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= p.num_rois) return;
+  const RoiGeom g = roi_decode(p.rois + (size_t)r * 5, p.scale, p.pooled_h, p.pooled_w, p.sampling_ratio);
+  const int n = (g.batch >= 0 && g.batch < p.num_images) ? g.batch : -1;
+  const int PH = p.pooled_h, PW = p.pooled_w, H = p.height, W = p.width;
+  if (PASS == 1) {
+    SweepHdr* h = p.hdr + r;
+    const unsigned col_base = (unsigned)r * (unsigned)p.colcap;
+    if (lane == 0) {
+      h->roi = r;
+      h->batch = n;
+      h->grid = g.grid_h | (g.grid_w << 16);
+      h->count = g.count;
+      h->start_h = g.start_h;
+      h->bin_h = g.bin_h;
+      h->col_base = col_base;
+    }
+    if (n < 0) {
+      // a ROI that points at no image reads nothing: its output rows are zero
+      if (!p.accumulate) {
+        const size_t per = (size_t)p.c_work * PH * PW;
+        float* o = p.out + (size_t)r * p.channels * PH * PW;
+        for (size_t i = lane; i < per; i += 32) o[i] = 0.0f;
+      }
+      if (lane == 0) h->ncols = 0;
+      return;
+    }
+    // column records: word offset of pixel x in a group block = box * 8 * wbox + (x - box * xb)
+    ColRec* cols = p.cols + col_base;
+    if (!p.compact) {
+      const int gw = g.grid_w, total = PW * gw;
+      for (int k = lane; k < total; k += 32) {
+        const int pw = k / gw, ix = k - pw * gw;
+        const AxisTap t = axis_decode(sample_pos(g.start_w, pw, g.bin_w, ix, gw), W);
+        ColRec c = make_uint2(kColInvalid, 0u);
+        if (t.valid) {
+          const int blo = (p.nbox > 1 && t.lo >= p.xb) ? 1 : 0, bhi = (p.nbox > 1 && t.hi >= p.xb) ? 1 : 0;
+          const unsigned lo = (unsigned)(blo * 8 * p.wbox + t.lo - blo * p.xb);
+          const unsigned hi = (unsigned)(bhi * 8 * p.wbox + t.hi - bhi * p.xb);
+          c = make_uint2(lo | (hi << 16), __float_as_uint(t.wl));
+        }
+        cols[k] = c;
+      }
+      if (lane == 0) h->ncols = total;
+    } else {
+      // only the samples inside the plane are kept, bin column by bin column (adaptive grids:
+      // at most 2W + 3 of them, the sample spacing bin / ceil(bin) is at least half a pixel)
+      int base = 0;
+      for (int pw = 0; pw < PW; ++pw) {
+        if (lane == 0 && pw < 16) h->cstart[pw] = (unsigned short)base;
+        for (int i0 = 0; i0 < g.grid_w; i0 += 32) {
+          const int ix = i0 + lane;
+          bool valid = false;
+          ColRec c = make_uint2(kColInvalid, 0u);
+          if (ix < g.grid_w) {
+            const AxisTap t = axis_decode(sample_pos(g.start_w, pw, g.bin_w, ix, g.grid_w), W);
+            valid = t.valid;
+            if (valid) {
+              const int blo = (p.nbox > 1 && t.lo >= p.xb) ? 1 : 0, bhi = (p.nbox > 1 && t.hi >= p.xb) ? 1 : 0;
+              const unsigned lo = (unsigned)(blo * 8 * p.wbox + t.lo - blo * p.xb);
+              const unsigned hi = (unsigned)(bhi * 8 * p.wbox + t.hi - bhi * p.xb);
+              c = make_uint2(lo | (hi << 16), __float_as_uint(t.wl));
+            }
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, valid);
+          if (valid) {
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < p.colcap) cols[pos] = c;
+          }
+          base += __popc(m);
+        }
+      }
+      if (base > p.colcap) base = p.colcap;     // cannot happen (see the bound above)
+      if (lane == 0) {
+        for (int pw = PW; pw < 16; ++pw) h->cstart[pw] = (unsigned short)base;
+        h->ncols = base;
+      }
+    }
+  }
+  if (n < 0) return;
+  // ---- items: lane = bin row --------------------------------------------------------------
+  for (int ph = lane; ph < PH; ph += 32) {
+    // pass A: the last sample row inside the plane decides the segment of the bin row
+    int last_lo = -1;
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const AxisTap t = axis_decode(sample_pos(g.start_h, ph, g.bin_h, iy, g.grid_h), H);
+      if (t.valid) last_lo = t.lo;
+    }
+    const int seg = last_lo < 0 ? 0 : seg_of_row(last_lo, p.segs, H);
+    const int unit = n * p.segs + seg;
+    int* cnt = p.cnt + (size_t)unit * H;
+    const int* start = p.start + (size_t)unit * H;
+    unsigned dep = kNoDep;
+    int open_key = -1, open_hi = 0, open_sy = 0, open_n = 0;
+    bool first = true;
+    auto emit = [&](bool last) {
+      const int key = open_key < 0 ? 0 : open_key;
+      if (PASS == 1) {
+        atomicAdd(cnt + key, 1);
+        atomicMax(p.unit_rows + unit, open_hi + 1);
+      } else {
+        const unsigned pos = (unsigned)(__ldg(start + key) + atomicAdd(cnt + key, 1));
+        const unsigned flags = (first ? 1u : 0u) | (last ? 2u : 0u);
+        p.items[pos] = make_uint4((unsigned)r, (unsigned)open_sy | ((unsigned)open_n << 16),
+                                  (unsigned)key | ((unsigned)(open_hi - key) << 12) | ((unsigned)ph << 16) |
+                                      (flags << 30),
+                                  dep);
+        dep = pos;
+      }
+      first = false;
+    };
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const AxisTap t = axis_decode(sample_pos(g.start_h, ph, g.bin_h, iy, g.grid_h), H);
+      if (!t.valid) continue;
+      if (open_key >= 0 && t.hi - open_key + 1 > p.span) {
+        emit(false);
+        open_key = -1;
+      }
+      if (open_key < 0) {
+        open_key = t.lo;
+        open_sy = ph * g.grid_h + iy;
+        open_n = 0;
+      }
+      open_hi = t.hi;
+      ++open_n;
+    }
+    if (open_key < 0) {       // no sample row inside the plane: the bin row is all zeros
+      open_sy = ph * g.grid_h;
+      open_n = 0;
+      open_hi = 0;
+    }
+    emit(true);
+  }
+}
+
+// exclusive scan of cnt[0, m) into start[0, m]; cnt is cleared (pass 2 uses it as cursors)
+__global__ void __launch_bounds__(1024) sweep_scan_kernel(int* __restrict__ cnt, int* __restrict__ start, int m) {
+  ptx::chain_enter();
+  __shared__ int warp_sums[32];
+  const int per = (m + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(m, lo + per);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += cnt[i];
+  int total;
+  int run = block_exclusive_scan<1024>(sum, &total, warp_sums);
+  for (int i = lo; i < hi; ++i) {
+    const int c = cnt[i];
+    start[i] = run;
+    cnt[i] = 0;
+    run += c;
+  }
+  if (threadIdx.x == 0) start[m] = total;
+}
+
+// ---- TMA ---------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(ptx::smem_addr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(ptx::smem_addr(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_addr(bar)) : "memory");
+}
+
+// A consumer warp is done with ring rows [from, to) of the current unit.  A warp can run far
+// ahead of the others (a gap in the item list), so before it arrives for a row it makes sure the
+// previous user of that slot has been released by EVERY warp: two arrivals of one warp in one
+// phase of empty[slot] would open the slot while another warp still reads it.
+__device__ __forceinline__ void release_rows(uint64_t* empty, unsigned seq0, int from, int to, int ring,
+                                             unsigned magic) {
+  for (int q = from; q < to; ++q) {
+    const unsigned s = seq0 + (unsigned)q;
+    const unsigned round = __umulhi(s, magic), slot = s - round * (unsigned)ring;
+    if (round > 0) ptx::mbar_wait(empty + slot, (round & 1u) ^ 1u);
+    mbar_arrive(empty + slot);
+  }
+}
+
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+__device__ __forceinline__ float ld_cg(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_cg(float* p, float v) { asm volatile("st.global.cg.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
+// ---- the forward sweep ---------------------------------------------------------------------
+// PWT: pooled width.  GWT > 0: fixed sampling ratio, column records at k = pw * GWT + ix;
+// GWT == 0: compacted column records with per-bin ranges (adaptive grids).
+template <int PWT, int GWT>
+__global__ void __launch_bounds__(kSweepThreads, 1)
+sweep_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SweepParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);
+  float* stage_all = ring + (size_t)p.ring * p.rowf;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_all + kConsumers * 32 * p.pwp);
+  uint64_t* empty = full + kMaxRing;
+  int* ctl = reinterpret_cast<int*>(empty + kMaxRing);     // [0] unit, [1] item cursor
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.ring; ++i) {
+      ptx::mbar_init(full + i, 1);
+      ptx::mbar_init(empty + i, kConsumers);
+    }
+    ptx::fence_mbar_init();
+  }
+  ptx::chain_enter();
+  const int H = p.height, PH = p.pooled_h;
+  const int bins = PH * PWT;
+  const unsigned ring_base = ptx::smem_addr(ring);
+  const int lg = lane >> 3, lc = lane & 7;
+  const unsigned lane_off = (unsigned)((lg * p.nbox * 8 * p.wbox + lc * p.wbox + lg) * 4);
+  const unsigned row_bytes = (unsigned)p.rowf * 4u;
+  float* stage = stage_all + (warp < kConsumers ? warp : 0) * 32 * p.pwp;
+  const int units = p.num_images * p.segs * p.ncg;
+  unsigned seq0 = 0;      // ring rows loaded before this unit (same in every thread)
+
+  for (;;) {
+    __syncthreads();      // every warp is done with the previous unit (and its ctl words)
+    if (threadIdx.x == 0) {
+      ctl[0] = atomicAdd(p.unit_counter, 1);
+      ctl[1] = 0;
+    }
+    __syncthreads();
+    const int u = ctl[0];
+    if (u >= units) break;
+    const int cg = u % p.ncg, us = u / p.ncg;              // us = image * segs + segment
+    const int n = us / p.segs;
+    const int item_lo = __ldg(p.start + (size_t)us * H), item_hi = __ldg(p.start + (size_t)(us + 1) * H);
+    if (item_lo >= item_hi) continue;
+    const int ya = (int)(__ldg(&p.items[item_lo].z) & 0xfffu);    // items are sorted by first row
+    const int nrows = __ldg(p.unit_rows + us) - ya;         // rows [ya, ya + nrows) are swept
+    const int c0 = cg * 32;
+
+    if (warp == kConsumers) {
+      // ---- producer: one ring row per step, 4 * nbox boxes, completion on full[slot] ----
+      for (int q = 0; q < nrows; ++q) {
+        const unsigned s = seq0 + (unsigned)q;
+        const unsigned round = __umulhi(s, p.ring_magic), slot = s - round * (unsigned)p.ring;
+        if (round > 0) {
+          ptx::mbar_wait(empty + slot, (round & 1u) ^ 1u);   // every consumer has left the old row
+          ptx::mbar_wait(full + slot, (round & 1u) ^ 1u);    // ... and its load has landed
+        }
+        if (lane == 0) ptx::mbar_arrive_expect_tx(full + slot, row_bytes);
+        __syncwarp();
+        if (lane < 4 * p.nbox) {
+          const int gg = lane / p.nbox, b = lane - gg * p.nbox;
+          float* dst = ring + (size_t)slot * p.rowf + (size_t)(gg * p.nbox + b) * 8 * p.wbox;
+          tma_load_4d(dst, &tmap, b * p.xb - gg, ya + q, c0 + gg * 8, n, full + slot);
+        }
+      }
+    } else {
+      // ---- consumers ------------------------------------------------------------------
+      int my_q = 0;       // rows [0, my_q) have been released by this warp
+      for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(&ctl[1], 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0) + item_lo;
+        if (idx >= item_hi) break;
+        const ItemRec it = __ldg(p.items + idx);
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(p.hdr + it.x));
+        const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(p.hdr + it.x) + 1);
+        const int roi = (int)h0.x;
+        const int gh = (int)(h0.z & 0xffffu), gw = (int)(h0.z >> 16);
+        const float count = __uint_as_float(h0.w);
+        const float start_h = __uint_as_float(h1.x), bin_h = __uint_as_float(h1.y);
+        const ColRec* cols = p.cols + h1.z;
+        const int sy0 = (int)(it.y & 0xffffu), nsy = (int)(it.y >> 16);
+        const int key = (int)(it.z & 0xfffu), dy = (int)((it.z >> 12) & 0xfu);
+        const int ph = (int)((it.z >> 16) & 0x3fffu);
+        const unsigned flags = it.z >> 30;
+        // ring: release the rows above this item, wait for the rows it reads
+        const int q0 = key - ya;
+        if (lane == 0) release_rows(empty, seq0, my_q, q0, p.ring, p.ring_magic);
+        if (q0 > my_q) my_q = q0;
+        if (nsy > 0)
+          for (int q = q0; q <= q0 + dy; ++q) {
+            const unsigned s = seq0 + (unsigned)q;
+            const unsigned round = __umulhi(s, p.ring_magic);
+            ptx::mbar_wait(full + (s - round * (unsigned)p.ring), round & 1u);
+          }
+        // running sums: zero, or what the predecessor item left
+        float acc[PWT];
+        float* scr = p.scratch + (((size_t)roi * PH + ph) * p.ncg + cg) * (PWT * 32) + lane;
+        if (flags & 1u) {
+#pragma unroll
+          for (int pw = 0; pw < PWT; ++pw) acc[pw] = 0.0f;
+        } else {
+          const unsigned dep = it.w;
+          if (lane == 0) {
+            const volatile unsigned* word = p.done + (dep >> 5);
+            while (!((*word >> (dep & 31u)) & 1u)) {
+            }
+          }
+          __syncwarp();
+          __threadfence();
+#pragma unroll
+          for (int pw = 0; pw < PWT; ++pw) acc[pw] = ld_cg(scr + pw * 32);
+        }
+        uint4 cs0 = make_uint4(0, 0, 0, 0), cs1 = cs0;
+        int ncols = 0;
+        if (GWT == 0) {
+          cs0 = __ldg(reinterpret_cast<const uint4*>(p.hdr + it.x) + 2);
+          cs1 = __ldg(reinterpret_cast<const uint4*>(p.hdr + it.x) + 3);
+          ncols = (int)h1.w;
+        }
+        for (int sy = sy0; sy < sy0 + nsy; ++sy) {
+          const int iy = sy - ph * gh;
+          const AxisTap t = axis_decode(sample_pos(start_h, ph, bin_h, iy, gh), H);
+          const unsigned slo = seq0 + (unsigned)(t.lo - ya), shi = seq0 + (unsigned)(t.hi - ya);
+          const unsigned row_lo = ring_base + lane_off + (slo - __umulhi(slo, p.ring_magic) * (unsigned)p.ring) * row_bytes;
+          const unsigned row_hi = ring_base + lane_off + (shi - __umulhi(shi, p.ring_magic) * (unsigned)p.ring) * row_bytes;
+          const float ly = t.wl, hy = t.wh;
+          if (GWT > 0) {
+#pragma unroll
+            for (int pw = 0; pw < PWT; ++pw) {
+#pragma unroll
+              for (int ix = 0; ix < GWT; ++ix) {
+                const ColRec c = __ldg(cols + pw * GWT + ix);
+                if (c.x != kColInvalid) {
+                  const unsigned olo = (c.x & 0xffffu) << 2, ohi = (c.x >> 16) << 2;
+                  const float lx = __uint_as_float(c.y), hx = __fsub_rn(1.0f, lx);
+                  const float v1 = lds_f32(row_lo + olo), v2 = lds_f32(row_lo + ohi);
+                  const float v3 = lds_f32(row_hi + olo), v4 = lds_f32(row_hi + ohi);
+                  const float s = tap_sum(__fmul_rn(hy, hx), v1, __fmul_rn(hy, lx), v2, __fmul_rn(ly, hx), v3,
+                                          __fmul_rn(ly, lx), v4);
+                  acc[pw] = __fadd_rn(acc[pw], s);
+                }
+              }
+            }
+          } else {
+            unsigned prev = kColInvalid;
+            float v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
+#pragma unroll
+            for (int pw = 0; pw < PWT; ++pw) {
+              const unsigned w = pw < 8 ? (pw < 4 ? (pw < 2 ? cs0.x : cs0.y) : (pw < 6 ? cs0.z : cs0.w))
+                                        : (pw < 12 ? (pw < 10 ? cs1.x : cs1.y) : (pw < 14 ? cs1.z : cs1.w));
+              const int k0 = (int)((pw & 1) ? (w >> 16) : (w & 0xffffu));
+              int k1 = ncols;
+              if (pw + 1 < 16) {
+                const int q = pw + 1;
+                const unsigned w1 = q < 8 ? (q < 4 ? (q < 2 ? cs0.x : cs0.y) : (q < 6 ? cs0.z : cs0.w))
+                                          : (q < 12 ? (q < 10 ? cs1.x : cs1.y) : (q < 14 ? cs1.z : cs1.w));
+                k1 = (int)((q & 1) ? (w1 >> 16) : (w1 & 0xffffu));
+              }
+              for (int k = k0; k < k1; ++k) {
+                const ColRec c = __ldg(cols + k);
+                if (c.x != prev) {      // neighbouring samples of a dense grid share their taps
+                  const unsigned olo = (c.x & 0xffffu) << 2, ohi = (c.x >> 16) << 2;
+                  v1 = lds_f32(row_lo + olo);
+                  v2 = lds_f32(row_lo + ohi);
+                  v3 = lds_f32(row_hi + olo);
+                  v4 = lds_f32(row_hi + ohi);
+                  prev = c.x;
+                }
+                const float lx = __uint_as_float(c.y), hx = __fsub_rn(1.0f, lx);
+                const float s = tap_sum(__fmul_rn(hy, hx), v1, __fmul_rn(hy, lx), v2, __fmul_rn(ly, hx), v3,
+                                        __fmul_rn(ly, lx), v4);
+                acc[pw] = __fadd_rn(acc[pw], s);
+              }
+            }
+          }
+        }
+        if (flags & 2u) {
+          // ---- the bin row is complete: divide, transpose through shared memory, store ----
+          const int cnt_i = gh * gw;
+          const bool pow2 = (cnt_i & (cnt_i - 1)) == 0;
+          const float inv = __fdiv_rn(1.0f, count);
+          __syncwarp();
+#pragma unroll
+          for (int pw = 0; pw < PWT; ++pw)
+            stage[lane * p.pwp + pw] = pow2 ? __fmul_rn(acc[pw], inv) : __fdiv_rn(acc[pw], count);
+          __syncwarp();
+          float* o = p.out + ((size_t)roi * p.channels + c0) * bins + ph * PWT;
+          const int cvalid = min(32, p.c_work - c0);
+#pragma unroll
+          for (int k = 0; k < PWT; ++k) {
+            const int f = k * 32 + lane;
+            const int c = f / PWT, pw = f - c * PWT;
+            if (c < cvalid) {
+              const float v = stage[c * p.pwp + pw];
+              float* dst = o + (size_t)c * bins + pw;
+              *dst = p.accumulate ? __fadd_rn(*dst, v) : v;
+            }
+          }
+        } else {
+          // ---- hand the running sums to the successor item ------------------------------
+#pragma unroll
+          for (int pw = 0; pw < PWT; ++pw) st_cg(scr + pw * 32, acc[pw]);
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) atomicOr(p.done + ((unsigned)idx >> 5), 1u << ((unsigned)idx & 31u));
+        }
+      }
+      // release the remaining rows of the unit
+      if (lane == 0) release_rows(empty, seq0, my_q, nrows, p.ring, p.ring_magic);
+    }
+    seq0 += (unsigned)nrows;
+  }
+  // the producer may not leave while a load is in flight: wait for the last fill of every slot
+  if (warp == kConsumers && seq0 > 0) {
+    const unsigned first = seq0 > (unsigned)p.ring ? seq0 - (unsigned)p.ring : 0u;
+    for (unsigned s = first; s < seq0; ++s) {
+      const unsigned round = __umulhi(s, p.ring_magic);
+      ptx::mbar_wait(full + (s - round * (unsigned)p.ring), round & 1u);
+    }
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+struct SweepLayout {
+  size_t zero_bytes;     // leading part of the workspace that is cleared per call
+  size_t cnt, start, unit_rows, unit_counter, done, hdr, cols, items, scratch, total;
+  long long item_cap;
+  int m;                 // N * segs * H
+};
+
+SweepLayout sweep_layout(const RoiAlignArgs& a, const SweepPlan& plan) {
+  SweepLayout L;
+  const int c_work = a.c_count > 0 ? a.c_count : a.channels;
+  const int ncg = (c_work + 31) / 32;
+  L.m = a.num_images * plan.segs * a.height;
+  const long long per_roi = a.sampling_ratio > 0 ? (long long)a.pooled_h * a.sampling_ratio
+                                                 : (long long)a.pooled_h + a.height + 2;
+  L.item_cap = (long long)a.num_rois * per_roi;
+  size_t off = 0;
+  L.cnt = off;          off = align_up(off + (size_t)L.m * 4, 16);
+  L.unit_rows = off;    off = align_up(off + (size_t)a.num_images * plan.segs * 4, 16);
+  L.unit_counter = off; off = align_up(off + 16, 16);
+  L.done = off;         off = align_up(off + (size_t)((L.item_cap + 31) / 32) * 4, 256);
+  L.zero_bytes = off;
+  L.start = off;        off = align_up(off + (size_t)(L.m + 1) * 4, 256);
+  L.hdr = off;          off = align_up(off + (size_t)a.num_rois * sizeof(SweepHdr), 256);
+  L.cols = off;         off = align_up(off + (size_t)a.num_rois * plan.colcap * sizeof(ColRec), 256);
+  L.items = off;        off = align_up(off + (size_t)L.item_cap * sizeof(ItemRec), 256);
+  L.scratch = off;
+  off = align_up(off + (size_t)a.num_rois * a.pooled_h * ncg * a.pooled_w * 32 * sizeof(float), 256);
+  L.total = off;
+  return L;
+}
+
+template <int PWT>
+cudaError_t launch_main(int gwt, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& map,
+                        const SweepParams& p) {
+  auto go = [&](auto kernel) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    count_launch();
+    return chained_launch(kernel, grid, dim3(kSweepThreads), smem, stream, map, p);
+  };
+  return gwt == 2 ? go(sweep_fwd_kernel<PWT, 2>) : go(sweep_fwd_kernel<PWT, 0>);
+}
+
+}  // namespace
+
+bool sweep_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_optin, int num_sms, SweepPlan* plan) {
+  if (a.num_images <= 0 || a.num_images > 4096 || a.num_rois <= 0) return false;
+  if (a.width % 4 != 0 || (reinterpret_cast<uintptr_t>(plane_ptr) & 15u)) return false;   // TMA strides
+  if (a.height > kMaxPlaneH || a.pooled_w > kMaxPooledW || a.pooled_h > 16383) return false;
+  if ((long long)a.pooled_h * (a.sampling_ratio > 0 ? a.sampling_ratio : 1024) > 65535) return false;
+  if (!encode_tiled_fn()) return false;
+  // boxes: wbox % 4 == 0, (wbox / 4) odd, every group (shift 0..3) covers its pixels
+  int nbox = 1, wbox = 0;
+  for (;; ++nbox) {
+    const int need = (a.width + nbox - 1) / nbox + 3;
+    wbox = (need + 3) / 4 * 4;
+    if ((wbox / 4) % 2 == 0) wbox += 4;
+    if (wbox <= 256) break;
+    if (nbox >= 2) return false;
+  }
+  plan->nbox = nbox;
+  plan->wbox = wbox;
+  plan->xb = wbox - 3;
+  plan->rowf = 4 * nbox * 8 * wbox;
+  plan->pwp = a.pooled_w | 1;
+  const size_t fixed = (size_t)kConsumers * 32 * plan->pwp * 4 + 2 * kMaxRing * 8 + 64;
+  const size_t row_bytes = (size_t)plan->rowf * 4;
+  if ((size_t)smem_optin < fixed + kMinRing * row_bytes) return false;
+  int ring = (int)(((size_t)smem_optin - fixed) / row_bytes);
+  if (ring > kMaxRing) ring = kMaxRing;
+  plan->ring = ring;
+  plan->span = ring >= 8 ? 4 : (ring >= 6 ? 4 : 3);
+  if (plan->span > ring - 2) plan->span = ring - 2;
+  plan->smem = fixed + (size_t)ring * row_bytes;
+  // row segments per image: fill the SMs without paying too much for the lead-in rows
+  const int c_work = a.c_count > 0 ? a.c_count : a.channels;
+  const int ncg = (c_work + 31) / 32;
+  const long long base_units = (long long)a.num_images * ncg;
+  int best = 1;
+  double best_score = -1.0;
+  for (int s = 1; s <= 32 && s * 8 <= a.height; ++s) {
+    const long long units = base_units * s;
+    const long long rounds = (units + num_sms - 1) / num_sms;
+    const double fill = (double)units / (double)(rounds * num_sms);
+    const double lead = 1.0 / (1.0 + 6.0 * (s - 1) / (double)a.height);
+    const double score = fill * lead;
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best = s;
+    }
+  }
+  plan->segs = best;
+  plan->colcap = a.sampling_ratio > 0 ? ((a.pooled_w * a.sampling_ratio + 1) & ~1)
+                                      : ((max(a.pooled_w, 2 * a.width + 3) + 2) & ~1);
+  return true;
+}
+
+size_t sweep_fwd_workspace(const RoiAlignArgs& a, const SweepPlan& plan) { return sweep_layout(a, plan).total; }
+
+cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void* workspace, const float* data,
+                             float* out, int accumulate, int num_sms, cudaStream_t stream) {
+  const SweepLayout L = sweep_layout(a, plan);
+  char* ws = static_cast<char*>(workspace);
+  const int c_work = a.c_count > 0 ? a.c_count : a.channels;
+  SweepParams p;
+  p.rois = a.rois;
+  p.out = out;
+  p.num_rois = a.num_rois;
+  p.num_images = a.num_images;
+  p.channels = a.channels;
+  p.c_work = c_work;
+  p.ncg = (c_work + 31) / 32;
+  p.height = a.height;
+  p.width = a.width;
+  p.pooled_h = a.pooled_h;
+  p.pooled_w = a.pooled_w;
+  p.scale = a.scale;
+  p.sampling_ratio = a.sampling_ratio;
+  p.accumulate = accumulate;
+  p.wbox = plan.wbox;
+  p.nbox = plan.nbox;
+  p.xb = plan.xb;
+  p.rowf = plan.rowf;
+  p.ring = plan.ring;
+  p.span = plan.span;
+  p.ring_magic = (unsigned)(0x100000000ull / (unsigned)plan.ring) + 1u;
+  p.pwp = plan.pwp;
+  p.segs = plan.segs;
+  p.colcap = plan.colcap;
+  p.compact = a.sampling_ratio == 2 ? 0 : 1;
+  p.cnt = reinterpret_cast<int*>(ws + L.cnt);
+  p.start = reinterpret_cast<int*>(ws + L.start);
+  p.unit_rows = reinterpret_cast<int*>(ws + L.unit_rows);
+  p.unit_counter = reinterpret_cast<int*>(ws + L.unit_counter);
+  p.done = reinterpret_cast<unsigned*>(ws + L.done);
+  p.hdr = reinterpret_cast<SweepHdr*>(ws + L.hdr);
+  p.cols = reinterpret_cast<ColRec*>(ws + L.cols);
+  p.items = reinterpret_cast<ItemRec*>(ws + L.items);
+  p.scratch = reinterpret_cast<float*>(ws + L.scratch);
+
+  // tensor map over the caller's tensor: {W, H, channels of this call, N}
+  CUtensorMap map;
+  const cuuint64_t dims[4] = {(cuuint64_t)a.width, (cuuint64_t)a.height, (cuuint64_t)c_work,
+                              (cuuint64_t)a.num_images};
+  const cuuint64_t strides[3] = {(cuuint64_t)a.width * 4, (cuuint64_t)a.width * a.height * 4,
+                                 (cuuint64_t)a.width * a.height * 4 * (cuuint64_t)a.channels};
+  const cuuint32_t box[4] = {(cuuint32_t)plan.wbox, 1, 8, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult cr = encode_tiled_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(data), dims,
+                                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
+
+  cudaError_t e = cudaMemsetAsync(ws, 0, L.zero_bytes, stream);
+  if (e != cudaSuccess) return e;
+  const dim3 rgrid((a.num_rois + 7) / 8), rblock(256);
+  count_launch();
+  e = chained_launch(sweep_roi_kernel<1>, rgrid, rblock, 0, stream, p);
+  if (e != cudaSuccess) return e;
+  count_launch();
+  e = chained_launch(sweep_scan_kernel, dim3(1), dim3(1024), 0, stream, p.cnt, p.start, L.m);
+  if (e != cudaSuccess) return e;
+  count_launch();
+  e = chained_launch(sweep_roi_kernel<2>, rgrid, rblock, 0, stream, p);
+  if (e != cudaSuccess) return e;
+  const long long units = (long long)a.num_images * plan.segs * p.ncg;
+  const dim3 grid((unsigned)(units < num_sms ? units : num_sms));
+  const int gwt = a.sampling_ratio == 2 ? 2 : 0;
+  switch (a.pooled_w) {
+    case 1: return launch_main<1>(gwt, grid, plan.smem, stream, map, p);
+    case 2: return launch_main<2>(gwt, grid, plan.smem, stream, map, p);
+    case 3: return launch_main<3>(gwt, grid, plan.smem, stream, map, p);
+    case 4: return launch_main<4>(gwt, grid, plan.smem, stream, map, p);
+    case 5: return launch_main<5>(gwt, grid, plan.smem, stream, map, p);
+    case 6: return launch_main<6>(gwt, grid, plan.smem, stream, map, p);
+    case 7: return launch_main<7>(gwt, grid, plan.smem, stream, map, p);
+    case 8: return launch_main<8>(gwt, grid, plan.smem, stream, map, p);
+    case 9: return launch_main<9>(gwt, grid, plan.smem, stream, map, p);
+    case 10: return launch_main<10>(gwt, grid, plan.smem, stream, map, p);
+    case 11: return launch_main<11>(gwt, grid, plan.smem, stream, map, p);
+    case 12: return launch_main<12>(gwt, grid, plan.smem, stream, map, p);
+    case 13: return launch_main<13>(gwt, grid, plan.smem, stream, map, p);
+    case 14: return launch_main<14>(gwt, grid, plan.smem, stream, map, p);
+    case 15: return launch_main<15>(gwt, grid, plan.smem, stream, map, p);
+    default: return launch_main<16>(gwt, grid, plan.smem, stream, map, p);
+  }
+}
+
+}  // namespace mobula_b200

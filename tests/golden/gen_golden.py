@@ -5,7 +5,7 @@ Runs ONLY in the build container: it imports the UNMODIFIED reference package fr
 /root/reference (NumPy adapter -> JIT-built CPU library) and records its outputs on
 seeded inputs.  The GPU box has no /root/reference, so the vectors are committed.
 
-    python tests/golden/gen_golden.py          # rewrites tests/golden/*.npz
+    python tests/golden/gen_golden.py [--only-new]     # rewrites tests/golden/*.npz
 
 Reference entry points exercised: mobula.op.load('ROIAlign')
 (/root/reference/mobula/op/loader.py:623-659) and the NumPy adapter
@@ -105,13 +105,54 @@ def cases():
                           axis=1).astype(np.float32)
     out['fpn_14x14_sr2'] = dict(data=data, rois=rois, pooled=(14, 14), scale=0.25, sr=2,
                                 dy=rng.standard_normal((R, C, 14, 14)).astype(np.float32))
+
+    # 6. (round 2) the same edge cases on planes whose width is a multiple of 4 -- what the
+    #    TMA-fed "sweep" kernels accept -- with their own generator so the vectors above stay put
+    rng = np.random.default_rng(20261020)
+    N, C, H, W = 2, 35, 13, 20                # 35 channels: one full 32-channel group + a ragged one
+    data = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    rois = np.array([
+        [0, -20.0, -12.0, 30.0, 22.0],
+        [1, 40.0, 30.0, 100.0, 70.0],
+        [0, 30.0, 30.0, 10.0, 10.0],
+        [1, 12.0, 12.0, 12.0, 12.0],
+        [0, 400.0, 400.0, 500.0, 500.0],
+        [1, -300.0, -300.0, -100.0, -100.0],
+        [0, 0.0, 0.0, 80.0, 52.0],            # exactly the plane
+        [1, 3.3, 7.7, 41.9, 29.1],
+        [0, 75.9, 47.9, 80.1, 52.1],          # tiny box on the far corner
+        [1, -4.0, 10.0, 84.0, 20.0],          # wider than the plane
+        [0, 10.0, -40.0, 30.0, 90.0],         # taller than the plane
+        [1, 76.0, 0.0, 79.9, 52.0],           # last column only (x >= W-1 clamp)
+    ], np.float32)
+    out['edges_w20_sr2'] = dict(data=data, rois=rois, pooled=(7, 7), scale=0.25, sr=2,
+                                dy=rng.standard_normal((len(rois), C, 7, 7)).astype(np.float32))
+    out['edges_w20_sr0'] = dict(data=data, rois=rois, pooled=(7, 7), scale=0.25, sr=0,
+                                dy=rng.standard_normal((len(rois), C, 7, 7)).astype(np.float32))
+    out['edges_w20_sr3_p5x3'] = dict(data=data, rois=rois, pooled=(5, 3), scale=0.25, sr=3,
+                                     dy=rng.standard_normal((len(rois), C, 5, 3)).astype(np.float32))
+    # a plane wider than one TMA box (two boxes per 8-channel group), ROIs across the seam
+    N, C, H, W, R = 2, 3, 11, 280, 40
+    data = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    size = np.exp(rng.uniform(np.log(8), np.log(900), (R, 2)))
+    ctr = rng.uniform(0, 1, (R, 2)) * np.array([W / 0.25, H / 0.25])
+    ctr[:12, 0] = rng.uniform(130, 150, 12) / 0.25            # around pixel column 140
+    rois = np.concatenate([rng.integers(0, N, (R, 1)), ctr - size / 2, ctr + size / 2],
+                          axis=1).astype(np.float32)
+    out['wide_w280_sr2'] = dict(data=data, rois=rois, pooled=(7, 7), scale=0.25, sr=2,
+                                dy=rng.standard_normal((R, C, 7, 7)).astype(np.float32))
+    out['wide_w280_sr0'] = dict(data=data, rois=rois, pooled=(4, 6), scale=0.25, sr=0,
+                                dy=rng.standard_normal((R, C, 4, 6)).astype(np.float32))
     return out
 
 
 def main():
     with tempfile.TemporaryDirectory() as tmp:
         mobula = import_reference(tmp)
+        only_new = '--only-new' in sys.argv
         for name, c in cases().items():
+            if only_new and os.path.exists(os.path.join(HERE, name + '.npz')):
+                continue
             op = mobula.op.ROIAlign[np.ndarray](pooled_size=c['pooled'],
                                                 spatial_scale=float(c['scale']),
                                                 sampling_ratio=int(c['sr']))

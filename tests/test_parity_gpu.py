@@ -20,12 +20,18 @@ from mobulaop_b200.testing import (assert_bit_exact, assert_scatter_close,
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not has_cuda(), reason='needs a CUDA device')]
 
-ALGOS = ['gather', 'plane', 'resident', 'auto']
+ALGOS = ['gather', 'plane', 'resident', 'sweep', 'auto']
 
 
-def _skip_unless_supported(algo, pooled, sr, backward=False):
+def _skip_unless_supported(algo, pooled, sr, backward=False, width=None):
     """The resident kernels exist for a fixed sampling ratio (forward 1..4, backward 2) and
-    bounded pooled shapes; asking for them explicitly elsewhere is an error by design."""
+    bounded pooled shapes, the sweep kernels for planes whose width is a multiple of 4 (TMA
+    strides) and pooled widths up to 16; asking for them explicitly elsewhere is an error by
+    design."""
+    if algo == 'sweep':
+        if width is None or width % 4 != 0 or pooled[1] > 16:
+            pytest.skip('sweep kernels: width % 4 == 0 and pooled width <= 16 only')
+        return
     if algo != 'resident':
         return
     if backward:
@@ -117,7 +123,7 @@ def _abs_sum(oracle, g):
 @pytest.mark.parametrize('name', golden_names())
 def test_forward_golden(direct, name, algo):
     g = load_golden(name)
-    _skip_unless_supported(algo, g['pooled'], g['sr'])
+    _skip_unless_supported(algo, g['pooled'], g['sr'], width=g['data'].shape[3])
     y = direct.forward(g['data'], g['rois'], g['pooled'], g['scale'], g['sr'], algo=algo)
     assert_within_ulp_or_rel(y, g['y'], ulp=2, rtol=1e-6)
     assert_bit_exact(y, g['y'])         # same operations in the same order as the reference
@@ -127,7 +133,7 @@ def test_forward_golden(direct, name, algo):
 @pytest.mark.parametrize('name', golden_names())
 def test_backward_atomic_golden(direct, oracle, name, algo):
     g = load_golden(name)
-    _skip_unless_supported(algo, g['pooled'], g['sr'], backward=True)
+    _skip_unless_supported(algo, g['pooled'], g['sr'], backward=True, width=g['data'].shape[3])
     dx = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], algo=algo)
     assert_scatter_close(dx, g['dx'], _abs_sum(oracle, g), rtol=1e-5)
 
@@ -167,7 +173,7 @@ SAMPLES = {
 @pytest.mark.parametrize('key', sorted(SAMPLES))
 def test_seeded_workload_parity(direct, oracle, key, algo):
     wl = SAMPLES[key]()
-    _skip_unless_supported(algo, wl.pooled, wl.sampling_ratio)
+    _skip_unless_supported(algo, wl.pooled, wl.sampling_ratio, width=wl.W)
     data, rois, dy = WL.make_inputs(wl, seed=17)
     y_ref = oracle.forward(data, rois, wl.pooled, wl.scale, wl.sampling_ratio, threads=0)
     y = direct.forward(data, rois, wl.pooled, wl.scale, wl.sampling_ratio, algo=algo)
@@ -233,6 +239,60 @@ def test_odd_shapes_against_the_oracle(direct, oracle, shape):
     np.testing.assert_allclose(acc, base + dx_ref, rtol=1e-5, atol=1e-5)
 
 
+# ---- sweep kernels (lane = channel, TMA row ring): shapes that exercise their special cases --------
+SWEEP_SHAPES = [
+    # N, C, H, W, rois/img, pooled, scale, sr
+    (3, 5, 21, 32, 17, (7, 7), 0.25, 2),        # one ragged channel group
+    (2, 40, 40, 52, 23, (16, 16), 0.125, 2),    # two channel groups (32 + 8), widest pooled shape
+    (2, 4, 33, 36, 19, (1, 1), 0.5, 2),         # a single bin
+    (2, 2, 18, 20, 9, (9, 3), 0.5, 2),          # PH > PW
+    (1, 7, 150, 200, 40, (7, 7), 0.25, 2),      # tall plane: several row segments per image, ring wraps often
+    (1, 3, 37, 272, 30, (7, 7), 0.25, 2),       # wider than one TMA box: two boxes per channel group
+    (1, 2, 30, 300, 25, (14, 14), 0.25, 2),     # ... with the mask-head pooling
+    (1, 33, 150, 200, 30, (5, 12), 0.25, 0),    # adaptive grid, compacted column records, two channel groups
+    (2, 3, 24, 28, 11, (7, 7), 0.25, 1),        # sampling ratio 1 / 4 / 3: compacted records, fixed grid
+    (2, 3, 24, 28, 11, (5, 6), 0.25, 4),
+    (2, 3, 64, 48, 31, (6, 5), 0.25, 3),
+    (2, 64, 200, 272, 48, (7, 7), 0.25, 2),     # the box-head plane: six-row ring, chained items
+    (1, 3, 60, 400, 30, (7, 7), 0.25, 0),       # 400 wide: four-row ring
+    (2, 3, 50, 68, 600, (7, 7), 0.25, 0),       # many ROIs per image, adaptive
+]
+
+
+@pytest.mark.parametrize('shape', SWEEP_SHAPES, ids=lambda s: 'x'.join(str(v) for v in s[:5]) + '-p%dx%d-sr%d' % (s[5] + (s[7],)))
+def test_sweep_forward_against_the_oracle(direct, oracle, shape):
+    from mobulaop_b200 import _native
+    N, C, H, W, k, pooled, scale, sr = shape
+    wl = WL.Workload('sweep', N, C, H, W, k, pooled, scale, sr, min_box=2.0, max_box=4.0 * max(H, W) / scale,
+                     stress=sr == 0)
+    data, rois, _ = WL.make_inputs(wl, seed=31, with_dy=False)
+    rng = np.random.default_rng(6)
+    perm = rng.permutation(len(rois))                  # ROIs not grouped by image
+    rois = np.ascontiguousarray(rois[perm])
+    if N > 2:
+        rois[rois[:, 0] == N - 1, 0] = 0               # the last image has no ROI at all
+    rois[1, 0] = N + 2                                 # points at no image: zero rows
+    y_ref = oracle.forward(data, np.delete(rois, 1, axis=0), pooled, scale, sr, threads=0)
+    y = direct.forward(data, rois, pooled, scale, sr, algo='sweep')
+    assert _native.last_algo(False) == 'sweep'
+    assert not y[1].any()
+    assert_bit_exact(np.delete(y, 1, axis=0), y_ref)
+    base = rng.standard_normal(y.shape).astype(np.float32)
+    acc = direct.forward(data, rois, pooled, scale, sr, algo='sweep', accumulate_into=base.copy())
+    expect = base.copy()
+    expect[np.arange(len(rois)) != 1] += y_ref
+    assert_bit_exact(acc, expect)
+
+
+def test_sweep_rejects_what_it_cannot_do(direct):
+    data = np.zeros((1, 2, 8, 18), np.float32)          # width % 4 != 0: no TMA tensor map
+    rois = np.array([[0, 1, 1, 9, 9]], np.float32)
+    with pytest.raises(NotImplementedError):
+        direct.forward(data, rois, (2, 2), 1.0, 2, algo='sweep')
+    with pytest.raises(NotImplementedError):            # pooled width beyond the register tile
+        direct.forward(np.zeros((1, 2, 8, 20), np.float32), rois, (2, 17), 1.0, 2, algo='sweep')
+
+
 # ---- ROI bookkeeping --------------------------------------------------------------------
 @pytest.mark.parametrize('name', ['edges_sr0', 'edges_sr2', 'ref_value_test', 'fpn_14x14_sr2'])
 def test_bookkeeping_bit_exact(native, torch, oracle, name):
@@ -261,7 +321,7 @@ def test_bookkeeping_bit_exact(native, torch, oracle, name):
 
 # ---- edge cases ---------------------------------------------------------------------------
 def test_empty_and_tiny_inputs(direct, oracle):
-    data = np.random.default_rng(0).standard_normal((2, 3, 9, 11)).astype(np.float32)
+    data = np.random.default_rng(0).standard_normal((2, 3, 9, 12)).astype(np.float32)
     none = np.zeros((0, 5), np.float32)
     assert direct.forward(data, none, (7, 7), 0.5, 2).shape == (0, 3, 7, 7)
     dx = direct.backward(np.zeros((0, 3, 7, 7), np.float32), none, data.shape, 0.5, 2)
@@ -280,7 +340,7 @@ def test_batch_index_out_of_range_is_ignored(direct, oracle, algo):
     """With N known, ROIs pointing outside [0, N) read nothing and scatter nothing
     (the reference would read out of bounds, ROIAlign.cpp:43-44)."""
     rng = np.random.default_rng(1)
-    data = rng.standard_normal((2, 2, 10, 10)).astype(np.float32)
+    data = rng.standard_normal((2, 2, 10, 12)).astype(np.float32)
     rois = np.array([[0, 1, 1, 8, 8], [2, 1, 1, 8, 8], [-1, 0, 0, 5, 5], [1, 0, 0, 9, 9]], np.float32)
     dy = rng.standard_normal((4, 2, 2, 2)).astype(np.float32)
     y = direct.forward(data, rois, (2, 2), 1.0, 2, algo=algo)
@@ -297,7 +357,7 @@ def test_batch_index_out_of_range_is_ignored(direct, oracle, algo):
 
 @pytest.mark.parametrize('algo', ALGOS)
 def test_accumulate_flags(direct, oracle, algo):
-    g = load_golden('edges_sr2')
+    g = load_golden('edges_w20_sr2' if algo == 'sweep' else 'edges_sr2')
     base = np.random.default_rng(2).standard_normal(g['y'].shape).astype(np.float32)
     y = direct.forward(g['data'], g['rois'], g['pooled'], g['scale'], g['sr'], algo=algo,
                        accumulate_into=base)

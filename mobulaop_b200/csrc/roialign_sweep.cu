@@ -30,6 +30,8 @@
 // Reference arithmetic: /root/reference/opzoo/ROIAlign/ROIAlign.cpp:9-76, bilinear.h:10-59.
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "roialign_kernels.h"
@@ -706,19 +708,43 @@ cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void*
                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  // Drivers up to 13.1 set a descriptor bit that makes the TMA unit raise "illegal instruction" on
+  // tensors under 128 KiB (seen here on 580.159 with tools/tma_probe.cu); CUTLASS clears it the
+  // same way (cute/atom/copy_traits_sm90_tma.hpp, make_tma_copy_desc).
+  {
+    int driver = 0;
+    const size_t extent = ((size_t)(a.num_images - 1) * a.channels + c_work) * a.height * a.width * sizeof(float);
+    if (cudaDriverGetVersion(&driver) == cudaSuccess && driver <= 13010 && extent < 131072)
+      reinterpret_cast<uint64_t*>(&map)[1] &= ~(1ull << 21);
+  }
 
+  static const bool debug = getenv("MOBULA_SWEEP_DEBUG") != nullptr;
+  auto checkpoint = [&](const char* what) -> cudaError_t {
+    if (!debug) return cudaSuccess;
+    const cudaError_t s = cudaStreamSynchronize(stream);
+    fprintf(stderr, "[sweep] %s: %s\n", what, cudaGetErrorString(s));
+    return s;
+  };
   cudaError_t e = cudaMemsetAsync(ws, 0, L.zero_bytes, stream);
   if (e != cudaSuccess) return e;
+  if ((e = checkpoint("memset")) != cudaSuccess) return e;
   const dim3 rgrid((a.num_rois + 7) / 8), rblock(256);
   count_launch();
   e = chained_launch(sweep_roi_kernel<1>, rgrid, rblock, 0, stream, p);
   if (e != cudaSuccess) return e;
+  if ((e = checkpoint("pass 1")) != cudaSuccess) return e;
   count_launch();
   e = chained_launch(sweep_scan_kernel, dim3(1), dim3(1024), 0, stream, p.cnt, p.start, L.m);
   if (e != cudaSuccess) return e;
+  if ((e = checkpoint("scan")) != cudaSuccess) return e;
   count_launch();
   e = chained_launch(sweep_roi_kernel<2>, rgrid, rblock, 0, stream, p);
   if (e != cudaSuccess) return e;
+  if ((e = checkpoint("pass 2")) != cudaSuccess) return e;
+  if (debug)
+    fprintf(stderr, "[sweep] wbox %d nbox %d xb %d rowf %d ring %d span %d segs %d colcap %d smem %zu units %lld\n",
+            plan.wbox, plan.nbox, plan.xb, plan.rowf, plan.ring, plan.span, plan.segs, plan.colcap, plan.smem,
+            (long long)a.num_images * plan.segs * p.ncg);
   const long long units = (long long)a.num_images * plan.segs * p.ncg;
   const dim3 grid((unsigned)(units < num_sms ? units : num_sms));
   const int gwt = a.sampling_ratio == 2 ? 2 : 0;

@@ -67,10 +67,10 @@ extern "C" {
 #define MOBULA_ROIALIGN_ALGO_RESIDENT 3u /* fixed sampling ratio: padded plane resident in
                                           shared memory, lean per-call ROI tables, work split
                                           evenly over the SMs                               */
-#define MOBULA_ROIALIGN_ALGO_SWEEP 4u  /* lane = channel: TMA-fed ring of full-width rows of 32
-                                          channels in shared memory, bank-conflict-free taps,
-                                          any sampling grid; needs width % 4 == 0, pooled width
-                                          <= 16 and a known num_images                      */
+#define MOBULA_ROIALIGN_ALGO_SWEEP 4u  /* lane = channel: ring of full-width rows of 32 channels
+                                          in shared memory, bank-conflict-free taps, any
+                                          sampling grid; needs pooled width <= 16 and a known
+                                          num_images                                        */
 
 /* ------------------------------------------------------------------------- *
  * 1. Drop-in symbols (reference ABI)                                         *

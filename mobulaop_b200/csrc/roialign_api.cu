@@ -248,9 +248,8 @@ static int forward_device(DeviceState& st, int device, cudaStream_t stream, cons
     const bool sweep_ok = want && !no_tables && sweep_supported(a, data, st.smem_optin, st.num_sms, &splan);
     if (algo == MOBULA_ROIALIGN_ALGO_SWEEP && !sweep_ok)
       return fail(MOBULA_ERR_UNSUPPORTED,
-                  "sweep algorithm needs num_images in [1, 4096], width %% 4 == 0, 16-byte aligned data, "
-                  "pooled_w <= 16 and at least four %d-pixel rows of 32 channels within %d bytes of shared "
-                  "memory", a.width, st.smem_optin);
+                  "sweep algorithm needs num_images in [1, 4096], pooled_w <= 16 and at least four "
+                  "%d-pixel rows of 32 channels within %d bytes of shared memory", a.width, st.smem_optin);
     if (sweep_ok) {
       t_algo[0] = "sweep";
       void* ws = nullptr;

@@ -145,10 +145,11 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
                                 const float* dy, float* dx, int accumulate, int deterministic, int num_sms,
                                 cudaStream_t stream);
 
-// ---- sweep family (roialign_sweep.cu): lane = channel, TMA-fed ring of full-width rows of 32
-// channels, items sorted by row; any sampling grid, any pooled height, pooled width <= 16 ------
+// ---- sweep family (roialign_sweep.cu): lane = channel, ring of full-width rows of 32 channels
+// (odd channel pitch: bank-conflict-free taps), items sorted by row; any sampling grid, any
+// pooled height, pooled width <= 16 ---------------------------------------------------------
 struct SweepPlan {
-  int wbox, nbox, xb, rowf;   // TMA box width, boxes per 8-channel group row, first pixel of box 1, floats per ring row
+  int pitch, rowf, vec4;      // floats between channels of a ring row (odd), floats per ring row, LDG.128 fill
   int ring, span;             // ring rows; rows one item's taps may span
   int pwp;                    // staging pitch
   int segs;                   // row segments per image

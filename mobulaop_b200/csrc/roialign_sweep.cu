@@ -10,13 +10,16 @@
 // warp-uniform also means no divergence: adaptive grids (sampling_ratio <= 0), any pooled
 // shape, clamped and rejected samples are uniform branches.
 //
-// Data movement: a ring of rows in shared memory filled by TMA (cp.async.bulk.tensor, SASS
-// UTMALDG) from a 4-D tensor map over the caller's NCHW tensor: per ring row and per group of 8
-// channels one box {Wbox, 1 row, 8 channels}.  The box of channel group g starts g pixels left
-// of the plane (out-of-bounds elements are zero-filled), and Wbox / 4 is odd, so channel
-// (g, cl) of pixel x sits at word  cl * Wbox + x + g  of its group block: banks
-// 4 * (cl * odd mod 8) + g -- all 32 distinct.  Planes wider than 253 pixels take two boxes per
-// group.  The CTA sweeps its rows top to bottom; every feature-map row is read once per sweep.
+// Data movement: a ring of full-width rows in shared memory, [row slot][32 channels][pitch] with an
+// ODD pitch, so channel c of pixel x sits at word c * pitch + x and the 32 channels of one pixel
+// occupy the 32 banks.  That skew needs 4-byte placement: every copy engine that moves 16-byte
+// granules (TMA tensor / bulk copies, 16-byte cp.async) keeps pixel x at a word == x (mod 4) and
+// would leave the 32 lanes on 8 banks (tools/tma_probe.cu, profiles/r2_tma_probe.txt: a tiled TMA
+// load with a start coordinate that is not a multiple of 16 bytes raises an illegal instruction).
+// The ring is therefore filled by four producer warps with coalesced LDG.128 (8 lanes = 32 pixels
+// of one channel, 4 channels per instruction) and 4 x STS.32, conflict-free on both sides; 16
+// consumer warps compute.  The CTA sweeps its rows top to bottom; every feature-map row is read
+// once per sweep.
 //
 // Work: (image, 32-channel group, row segment) units from a queue; inside a unit the "items"
 // -- runs of sample rows of one bin row of one ROI whose taps span at most kSpan rows -- sorted
@@ -28,8 +31,6 @@
 // far above its first row as its bin rows reach, so no partial sum crosses CTAs.
 //
 // Reference arithmetic: /root/reference/opzoo/ROIAlign/ROIAlign.cpp:9-76, bilinear.h:10-59.
-#include <cuda.h>
-
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -43,7 +44,9 @@ namespace mobula_b200 {
 namespace {
 
 constexpr int kConsumers = 16;                        // warps that compute
-constexpr int kSweepThreads = (kConsumers + 1) * 32;  // + one producer warp (TMA)
+constexpr int kProducers = 4;                         // warps that fill the row ring
+constexpr int kSweepThreads = (kConsumers + kProducers) * 32;
+constexpr int kFillBatch = 8;                         // 16-byte loads in flight per producer lane
 constexpr int kMaxRing = 16;
 constexpr int kMinRing = 4;
 constexpr int kMaxPooledW = 16;
@@ -64,9 +67,8 @@ struct __align__(16) SweepHdr {
   unsigned short cstart[16];   // compacted tables: first record of bin column pw (end = next / ncols)
 };
 
-// A sample column: word offsets of the low / high tap inside a ring row's group block
-// (lo | hi << 16; 0xffffffff: the sample is outside the plane, bilinear.h:15-18) and the
-// fraction lx = weight of the high tap.
+// A sample column: pixel columns of the low / high tap (lo | hi << 16; 0xffffffff: the sample is
+// outside the plane, bilinear.h:15-18) and the fraction lx = weight of the high tap.
 typedef uint2 ColRec;
 constexpr unsigned kColInvalid = 0xffffffffu;
 
@@ -87,9 +89,11 @@ struct SweepParams {
   float scale;
   int sampling_ratio;
   int accumulate;
+  const float* data;
   // shared-memory geometry
-  int wbox, nbox, xb;    // box width (floats), boxes per group row, first pixel of box 1
-  int rowf;              // floats per ring row = 4 * nbox * 8 * wbox
+  int pitch;             // floats between channels of a ring row (odd, >= width)
+  int rowf;              // floats per ring row = 32 * pitch
+  int vec4;              // rows are 16-byte aligned in global memory: LDG.128 fill
   int ring, span;        // ring rows, max rows an item's taps may span
   unsigned ring_magic;   // floor(2^32 / ring) + 1: q / ring == umulhi(q, magic)
   int pwp;               // staging pitch per channel (pooled_w | 1)
@@ -144,7 +148,6 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
       if (lane == 0) h->ncols = 0;
       return;
     }
-    // column records: word offset of pixel x in a group block = box * 8 * wbox + (x - box * xb)
     ColRec* cols = p.cols + col_base;
     if (!p.compact) {
       const int gw = g.grid_w, total = PW * gw;
@@ -152,12 +155,7 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
         const int pw = k / gw, ix = k - pw * gw;
         const AxisTap t = axis_decode(sample_pos(g.start_w, pw, g.bin_w, ix, gw), W);
         ColRec c = make_uint2(kColInvalid, 0u);
-        if (t.valid) {
-          const int blo = (p.nbox > 1 && t.lo >= p.xb) ? 1 : 0, bhi = (p.nbox > 1 && t.hi >= p.xb) ? 1 : 0;
-          const unsigned lo = (unsigned)(blo * 8 * p.wbox + t.lo - blo * p.xb);
-          const unsigned hi = (unsigned)(bhi * 8 * p.wbox + t.hi - bhi * p.xb);
-          c = make_uint2(lo | (hi << 16), __float_as_uint(t.wl));
-        }
+        if (t.valid) c = make_uint2((unsigned)t.lo | ((unsigned)t.hi << 16), __float_as_uint(t.wl));
         cols[k] = c;
       }
       if (lane == 0) h->ncols = total;
@@ -174,12 +172,7 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
           if (ix < g.grid_w) {
             const AxisTap t = axis_decode(sample_pos(g.start_w, pw, g.bin_w, ix, g.grid_w), W);
             valid = t.valid;
-            if (valid) {
-              const int blo = (p.nbox > 1 && t.lo >= p.xb) ? 1 : 0, bhi = (p.nbox > 1 && t.hi >= p.xb) ? 1 : 0;
-              const unsigned lo = (unsigned)(blo * 8 * p.wbox + t.lo - blo * p.xb);
-              const unsigned hi = (unsigned)(bhi * 8 * p.wbox + t.hi - bhi * p.xb);
-              c = make_uint2(lo | (hi << 16), __float_as_uint(t.wl));
-            }
+            if (valid) c = make_uint2((unsigned)t.lo | ((unsigned)t.hi << 16), __float_as_uint(t.wl));
           }
           const unsigned m = __ballot_sync(0xffffffffu, valid);
           if (valid) {
@@ -271,15 +264,7 @@ __global__ void __launch_bounds__(1024) sweep_scan_kernel(int* __restrict__ cnt,
   if (threadIdx.x == 0) start[m] = total;
 }
 
-// ---- TMA ---------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-      ::"r"(ptx::smem_addr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(ptx::smem_addr(bar))
-      : "memory");
-}
-
+// ---- ring barriers ------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_addr(bar)) : "memory");
 }
@@ -316,7 +301,7 @@ __device__ __forceinline__ void st_cg(float* p, float v) { asm volatile("st.glob
 // GWT == 0: compacted column records with per-bin ranges (adaptive grids).
 template <int PWT, int GWT>
 __global__ void __launch_bounds__(kSweepThreads, 1)
-sweep_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SweepParams p) {
+sweep_fwd_kernel(const SweepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ring = reinterpret_cast<float*>(smem_raw);
   float* stage_all = ring + (size_t)p.ring * p.rowf;
@@ -327,7 +312,7 @@ sweep_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SweepParams p) 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.ring; ++i) {
-      ptx::mbar_init(full + i, 1);
+      ptx::mbar_init(full + i, kProducers * 32);
       ptx::mbar_init(empty + i, kConsumers);
     }
     ptx::fence_mbar_init();
@@ -336,8 +321,7 @@ sweep_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SweepParams p) 
   const int H = p.height, PH = p.pooled_h;
   const int bins = PH * PWT;
   const unsigned ring_base = ptx::smem_addr(ring);
-  const int lg = lane >> 3, lc = lane & 7;
-  const unsigned lane_off = (unsigned)((lg * p.nbox * 8 * p.wbox + lc * p.wbox + lg) * 4);
+  const unsigned lane_off = (unsigned)(lane * p.pitch * 4);
   const unsigned row_bytes = (unsigned)p.rowf * 4u;
   float* stage = stage_all + (warp < kConsumers ? warp : 0) * 32 * p.pwp;
   const int units = p.num_images * p.segs * p.ncg;
@@ -360,22 +344,68 @@ sweep_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SweepParams p) 
     const int nrows = __ldg(p.unit_rows + us) - ya;         // rows [ya, ya + nrows) are swept
     const int c0 = cg * 32;
 
-    if (warp == kConsumers) {
-      // ---- producer: one ring row per step, 4 * nbox boxes, completion on full[slot] ----
+    if (warp >= kConsumers) {
+      // ---- producers: warp pw fills channels [8 pw, 8 pw + 8) of every ring row ------------
+      const int pw8 = (warp - kConsumers) * 8;
+      const int W = p.width;
+      const int cvalid = min(32, p.c_work - c0);
+      const size_t plane = (size_t)H * W;
+      const float* src0 = p.data + ((size_t)n * p.channels + c0) * plane + (size_t)ya * W;
       for (int q = 0; q < nrows; ++q) {
         const unsigned s = seq0 + (unsigned)q;
         const unsigned round = __umulhi(s, p.ring_magic), slot = s - round * (unsigned)p.ring;
-        if (round > 0) {
-          ptx::mbar_wait(empty + slot, (round & 1u) ^ 1u);   // every consumer has left the old row
-          ptx::mbar_wait(full + slot, (round & 1u) ^ 1u);    // ... and its load has landed
+        if (round > 0) ptx::mbar_wait(empty + slot, (round & 1u) ^ 1u);   // every consumer has left the old row
+        float* row = ring + (size_t)slot * p.rowf;
+        const float* src = src0 + (size_t)q * W;
+        if (p.vec4) {
+          // lane = (channel ci of 4, quad j of 8): 4 channels x 32 pixels per load instruction;
+          // the four stores of a quad hit banks (ci * pitch + 4 j + k) mod 32, all distinct
+          const int j = lane & 7, ci = lane >> 3;
+          const int nxc = (W + 31) >> 5, tasks = 2 * nxc;        // (channel half, 32-pixel chunk)
+          for (int t0 = 0; t0 < tasks; t0 += kFillBatch) {
+            float4 v[kFillBatch];
+#pragma unroll
+            for (int u = 0; u < kFillBatch; ++u) {
+              const int t = t0 + u, half = t >= nxc ? 1 : 0, xc = t - half * nxc;
+              const int c = pw8 + half * 4 + ci, x = xc * 32 + 4 * j;
+              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (t < tasks && x < W && c < cvalid)
+                v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * plane + x));
+            }
+#pragma unroll
+            for (int u = 0; u < kFillBatch; ++u) {
+              const int t = t0 + u, half = t >= nxc ? 1 : 0, xc = t - half * nxc;
+              const int c = pw8 + half * 4 + ci, x = xc * 32 + 4 * j;
+              if (t < tasks && x < W) {
+                float* d = row + c * p.pitch + x;
+                d[0] = v[u].x;
+                d[1] = v[u].y;
+                d[2] = v[u].z;
+                d[3] = v[u].w;
+              }
+            }
+          }
+        } else {
+          // rows not 16-byte aligned: lane = pixel, one channel per instruction
+          const int nxc = (W + 31) >> 5, tasks = 8 * nxc;
+          for (int t0 = 0; t0 < tasks; t0 += kFillBatch) {
+            float v[kFillBatch];
+#pragma unroll
+            for (int u = 0; u < kFillBatch; ++u) {
+              const int t = t0 + u, cc = t / nxc, xc = t - cc * nxc;
+              const int c = pw8 + cc, x = xc * 32 + lane;
+              v[u] = 0.f;
+              if (t < tasks && x < W && c < cvalid) v[u] = __ldg(src + (size_t)c * plane + x);
+            }
+#pragma unroll
+            for (int u = 0; u < kFillBatch; ++u) {
+              const int t = t0 + u, cc = t / nxc, xc = t - cc * nxc;
+              const int c = pw8 + cc, x = xc * 32 + lane;
+              if (t < tasks && x < W) row[c * p.pitch + x] = v[u];
+            }
+          }
         }
-        if (lane == 0) ptx::mbar_arrive_expect_tx(full + slot, row_bytes);
-        __syncwarp();
-        if (lane < 4 * p.nbox) {
-          const int gg = lane / p.nbox, b = lane - gg * p.nbox;
-          float* dst = ring + (size_t)slot * p.rowf + (size_t)(gg * p.nbox + b) * 8 * p.wbox;
-          tma_load_4d(dst, &tmap, b * p.xb - gg, ya + q, c0 + gg * 8, n, full + slot);
-        }
+        mbar_arrive(full + slot);       // release: this lane's stores are visible to who waits
       }
     } else {
       // ---- consumers ------------------------------------------------------------------
@@ -525,36 +555,9 @@ sweep_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SweepParams p) 
     }
     seq0 += (unsigned)nrows;
   }
-  // the producer may not leave while a load is in flight: wait for the last fill of every slot
-  if (warp == kConsumers && seq0 > 0) {
-    const unsigned first = seq0 > (unsigned)p.ring ? seq0 - (unsigned)p.ring : 0u;
-    for (unsigned s = first; s < seq0; ++s) {
-      const unsigned round = __umulhi(s, p.ring_magic);
-      ptx::mbar_wait(full + (s - round * (unsigned)p.ring), round & 1u);
-    }
-  }
 }
 
 // ---- host side ------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-    else
-      cudaGetLastError();
-  });
-  return fn;
-}
-
 struct SweepLayout {
   size_t zero_bytes;     // leading part of the workspace that is cleared per call
   size_t cnt, start, unit_rows, unit_counter, done, hdr, cols, items, scratch, total;
@@ -587,13 +590,12 @@ SweepLayout sweep_layout(const RoiAlignArgs& a, const SweepPlan& plan) {
 }
 
 template <int PWT>
-cudaError_t launch_main(int gwt, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& map,
-                        const SweepParams& p) {
+cudaError_t launch_main(int gwt, dim3 grid, size_t smem, cudaStream_t stream, const SweepParams& p) {
   auto go = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     count_launch();
-    return chained_launch(kernel, grid, dim3(kSweepThreads), smem, stream, map, p);
+    return chained_launch(kernel, grid, dim3(kSweepThreads), smem, stream, p);
   };
   return gwt == 2 ? go(sweep_fwd_kernel<PWT, 2>) : go(sweep_fwd_kernel<PWT, 0>);
 }
@@ -602,23 +604,11 @@ cudaError_t launch_main(int gwt, dim3 grid, size_t smem, cudaStream_t stream, co
 
 bool sweep_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_optin, int num_sms, SweepPlan* plan) {
   if (a.num_images <= 0 || a.num_images > 4096 || a.num_rois <= 0) return false;
-  if (a.width % 4 != 0 || (reinterpret_cast<uintptr_t>(plane_ptr) & 15u)) return false;   // TMA strides
-  if (a.height > kMaxPlaneH || a.pooled_w > kMaxPooledW || a.pooled_h > 16383) return false;
+  if (a.width > 65535 || a.height > kMaxPlaneH || a.pooled_w > kMaxPooledW || a.pooled_h > 16383) return false;
   if ((long long)a.pooled_h * (a.sampling_ratio > 0 ? a.sampling_ratio : 1024) > 65535) return false;
-  if (!encode_tiled_fn()) return false;
-  // boxes: wbox % 4 == 0, (wbox / 4) odd, every group (shift 0..3) covers its pixels
-  int nbox = 1, wbox = 0;
-  for (;; ++nbox) {
-    const int need = (a.width + nbox - 1) / nbox + 3;
-    wbox = (need + 3) / 4 * 4;
-    if ((wbox / 4) % 2 == 0) wbox += 4;
-    if (wbox <= 256) break;
-    if (nbox >= 2) return false;
-  }
-  plan->nbox = nbox;
-  plan->wbox = wbox;
-  plan->xb = wbox - 3;
-  plan->rowf = 4 * nbox * 8 * wbox;
+  plan->vec4 = (a.width % 4 == 0 && (reinterpret_cast<uintptr_t>(plane_ptr) & 15u) == 0) ? 1 : 0;
+  plan->pitch = a.width | 1;             // odd: the 32 channels of a pixel hit the 32 banks
+  plan->rowf = 32 * plan->pitch;
   plan->pwp = a.pooled_w | 1;
   const size_t fixed = (size_t)kConsumers * 32 * plan->pwp * 4 + 2 * kMaxRing * 8 + 64;
   const size_t row_bytes = (size_t)plan->rowf * 4;
@@ -674,9 +664,9 @@ cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void*
   p.scale = a.scale;
   p.sampling_ratio = a.sampling_ratio;
   p.accumulate = accumulate;
-  p.wbox = plan.wbox;
-  p.nbox = plan.nbox;
-  p.xb = plan.xb;
+  p.data = data;
+  p.pitch = plan.pitch;
+  p.vec4 = plan.vec4;
   p.rowf = plan.rowf;
   p.ring = plan.ring;
   p.span = plan.span;
@@ -694,29 +684,6 @@ cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void*
   p.cols = reinterpret_cast<ColRec*>(ws + L.cols);
   p.items = reinterpret_cast<ItemRec*>(ws + L.items);
   p.scratch = reinterpret_cast<float*>(ws + L.scratch);
-
-  // tensor map over the caller's tensor: {W, H, channels of this call, N}
-  CUtensorMap map;
-  const cuuint64_t dims[4] = {(cuuint64_t)a.width, (cuuint64_t)a.height, (cuuint64_t)c_work,
-                              (cuuint64_t)a.num_images};
-  const cuuint64_t strides[3] = {(cuuint64_t)a.width * 4, (cuuint64_t)a.width * a.height * 4,
-                                 (cuuint64_t)a.width * a.height * 4 * (cuuint64_t)a.channels};
-  const cuuint32_t box[4] = {(cuuint32_t)plan.wbox, 1, 8, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult cr = encode_tiled_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(data), dims,
-                                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
-  // Drivers up to 13.1 set a descriptor bit that makes the TMA unit raise "illegal instruction" on
-  // tensors under 128 KiB (seen here on 580.159 with tools/tma_probe.cu); CUTLASS clears it the
-  // same way (cute/atom/copy_traits_sm90_tma.hpp, make_tma_copy_desc).
-  {
-    int driver = 0;
-    const size_t extent = ((size_t)(a.num_images - 1) * a.channels + c_work) * a.height * a.width * sizeof(float);
-    if (cudaDriverGetVersion(&driver) == cudaSuccess && driver <= 13010 && extent < 131072)
-      reinterpret_cast<uint64_t*>(&map)[1] &= ~(1ull << 21);
-  }
 
   static const bool debug = getenv("MOBULA_SWEEP_DEBUG") != nullptr;
   auto checkpoint = [&](const char* what) -> cudaError_t {
@@ -742,29 +709,29 @@ cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void*
   if (e != cudaSuccess) return e;
   if ((e = checkpoint("pass 2")) != cudaSuccess) return e;
   if (debug)
-    fprintf(stderr, "[sweep] wbox %d nbox %d xb %d rowf %d ring %d span %d segs %d colcap %d smem %zu units %lld\n",
-            plan.wbox, plan.nbox, plan.xb, plan.rowf, plan.ring, plan.span, plan.segs, plan.colcap, plan.smem,
+    fprintf(stderr, "[sweep] pitch %d vec4 %d rowf %d ring %d span %d segs %d colcap %d smem %zu units %lld\n",
+            plan.pitch, plan.vec4, plan.rowf, plan.ring, plan.span, plan.segs, plan.colcap, plan.smem,
             (long long)a.num_images * plan.segs * p.ncg);
   const long long units = (long long)a.num_images * plan.segs * p.ncg;
   const dim3 grid((unsigned)(units < num_sms ? units : num_sms));
   const int gwt = a.sampling_ratio == 2 ? 2 : 0;
   switch (a.pooled_w) {
-    case 1: return launch_main<1>(gwt, grid, plan.smem, stream, map, p);
-    case 2: return launch_main<2>(gwt, grid, plan.smem, stream, map, p);
-    case 3: return launch_main<3>(gwt, grid, plan.smem, stream, map, p);
-    case 4: return launch_main<4>(gwt, grid, plan.smem, stream, map, p);
-    case 5: return launch_main<5>(gwt, grid, plan.smem, stream, map, p);
-    case 6: return launch_main<6>(gwt, grid, plan.smem, stream, map, p);
-    case 7: return launch_main<7>(gwt, grid, plan.smem, stream, map, p);
-    case 8: return launch_main<8>(gwt, grid, plan.smem, stream, map, p);
-    case 9: return launch_main<9>(gwt, grid, plan.smem, stream, map, p);
-    case 10: return launch_main<10>(gwt, grid, plan.smem, stream, map, p);
-    case 11: return launch_main<11>(gwt, grid, plan.smem, stream, map, p);
-    case 12: return launch_main<12>(gwt, grid, plan.smem, stream, map, p);
-    case 13: return launch_main<13>(gwt, grid, plan.smem, stream, map, p);
-    case 14: return launch_main<14>(gwt, grid, plan.smem, stream, map, p);
-    case 15: return launch_main<15>(gwt, grid, plan.smem, stream, map, p);
-    default: return launch_main<16>(gwt, grid, plan.smem, stream, map, p);
+    case 1: return launch_main<1>(gwt, grid, plan.smem, stream, p);
+    case 2: return launch_main<2>(gwt, grid, plan.smem, stream, p);
+    case 3: return launch_main<3>(gwt, grid, plan.smem, stream, p);
+    case 4: return launch_main<4>(gwt, grid, plan.smem, stream, p);
+    case 5: return launch_main<5>(gwt, grid, plan.smem, stream, p);
+    case 6: return launch_main<6>(gwt, grid, plan.smem, stream, p);
+    case 7: return launch_main<7>(gwt, grid, plan.smem, stream, p);
+    case 8: return launch_main<8>(gwt, grid, plan.smem, stream, p);
+    case 9: return launch_main<9>(gwt, grid, plan.smem, stream, p);
+    case 10: return launch_main<10>(gwt, grid, plan.smem, stream, p);
+    case 11: return launch_main<11>(gwt, grid, plan.smem, stream, p);
+    case 12: return launch_main<12>(gwt, grid, plan.smem, stream, p);
+    case 13: return launch_main<13>(gwt, grid, plan.smem, stream, p);
+    case 14: return launch_main<14>(gwt, grid, plan.smem, stream, p);
+    case 15: return launch_main<15>(gwt, grid, plan.smem, stream, p);
+    default: return launch_main<16>(gwt, grid, plan.smem, stream, p);
   }
 }
 

@@ -25,12 +25,11 @@ ALGOS = ['gather', 'plane', 'resident', 'sweep', 'auto']
 
 def _skip_unless_supported(algo, pooled, sr, backward=False, width=None):
     """The resident kernels exist for a fixed sampling ratio (forward 1..4, backward 2) and
-    bounded pooled shapes, the sweep kernels for planes whose width is a multiple of 4 (TMA
-    strides) and pooled widths up to 16; asking for them explicitly elsewhere is an error by
-    design."""
+    bounded pooled shapes, the sweep kernels for pooled widths up to 16; asking for them
+    explicitly elsewhere is an error by design."""
     if algo == 'sweep':
-        if width is None or width % 4 != 0 or pooled[1] > 16:
-            pytest.skip('sweep kernels: width % 4 == 0 and pooled width <= 16 only')
+        if pooled[1] > 16:
+            pytest.skip('sweep kernels: pooled width <= 16 only')
         return
     if algo != 'resident':
         return
@@ -256,6 +255,9 @@ SWEEP_SHAPES = [
     (2, 64, 200, 272, 48, (7, 7), 0.25, 2),     # the box-head plane: six-row ring, chained items
     (1, 3, 60, 400, 30, (7, 7), 0.25, 0),       # 400 wide: four-row ring
     (2, 3, 50, 68, 600, (7, 7), 0.25, 0),       # many ROIs per image, adaptive
+    (3, 5, 21, 30, 17, (7, 7), 0.25, 2),        # width % 4 != 0: rows not 16-byte aligned, 4-byte fill
+    (1, 3, 37, 271, 30, (7, 7), 0.25, 0),       # ... odd width, adaptive
+    (2, 8, 14, 14, 64, (7, 7), 1.0, 2),         # the reference benchmark's plane
 ]
 
 
@@ -285,10 +287,7 @@ def test_sweep_forward_against_the_oracle(direct, oracle, shape):
 
 
 def test_sweep_rejects_what_it_cannot_do(direct):
-    data = np.zeros((1, 2, 8, 18), np.float32)          # width % 4 != 0: no TMA tensor map
     rois = np.array([[0, 1, 1, 9, 9]], np.float32)
-    with pytest.raises(NotImplementedError):
-        direct.forward(data, rois, (2, 2), 1.0, 2, algo='sweep')
     with pytest.raises(NotImplementedError):            # pooled width beyond the register tile
         direct.forward(np.zeros((1, 2, 8, 20), np.float32), rois, (2, 17), 1.0, 2, algo='sweep')
 

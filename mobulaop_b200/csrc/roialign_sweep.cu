@@ -106,7 +106,7 @@ struct SweepParams {
   int* start;            // [N * segs * H + 1] exclusive scan of cnt
   int* unit_rows;        // [N * segs] 1 + last row any item of the unit touches
   int* unit_counter;     // persistent-CTA queue
-  unsigned* done;        // one bit per item
+  unsigned* done;        // one bit per (item, channel group)
   SweepHdr* hdr;         // [R]
   ColRec* cols;          // [R * colcap]
   ItemRec* items;
@@ -269,17 +269,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_addr(bar)) : "memory");
 }
 
-// A consumer warp is done with ring rows [from, to) of the current unit.  A warp can run far
-// ahead of the others (a gap in the item list), so before it arrives for a row it makes sure the
-// previous user of that slot has been released by EVERY warp: two arrivals of one warp in one
-// phase of empty[slot] would open the slot while another warp still reads it.
-__device__ __forceinline__ void release_rows(uint64_t* empty, unsigned seq0, int from, int to, int ring,
-                                             unsigned magic) {
+// A consumer warp is done with ring rows [from, to) of the current unit.  Barrier phases are told
+// apart by ONE parity bit, so a thread may only wait for fill r of a slot after it has seen fill
+// r - 1 complete (otherwise "fill r - 1 still pending" reads as "fill r done"), and nobody may
+// get two phases ahead of anybody.  Hence every lane waits for every row of the unit in order,
+// needed or not, and a row is released only after it has been loaded -- which also implies that
+// every warp had released the previous user of its slot.
+__device__ __forceinline__ void release_rows(uint64_t* full, uint64_t* empty, unsigned seq0, int from, int to,
+                                             int ring, unsigned magic, int lane) {
   for (int q = from; q < to; ++q) {
     const unsigned s = seq0 + (unsigned)q;
     const unsigned round = __umulhi(s, magic), slot = s - round * (unsigned)ring;
-    if (round > 0) ptx::mbar_wait(empty + slot, (round & 1u) ^ 1u);
-    mbar_arrive(empty + slot);
+    ptx::mbar_wait(full + slot, round & 1u);
+    if (lane == 0) mbar_arrive(empty + slot);
   }
 }
 
@@ -429,7 +431,7 @@ sweep_fwd_kernel(const SweepParams p) {
         const unsigned flags = it.z >> 30;
         // ring: release the rows above this item, wait for the rows it reads
         const int q0 = key - ya;
-        if (lane == 0) release_rows(empty, seq0, my_q, q0, p.ring, p.ring_magic);
+        release_rows(full, empty, seq0, my_q, q0, p.ring, p.ring_magic, lane);
         if (q0 > my_q) my_q = q0;
         if (nsy > 0)
           for (int q = q0; q <= q0 + dy; ++q) {
@@ -444,10 +446,11 @@ sweep_fwd_kernel(const SweepParams p) {
 #pragma unroll
           for (int pw = 0; pw < PWT; ++pw) acc[pw] = 0.0f;
         } else {
-          const unsigned dep = it.w;
+          // one "done" bit per (item, channel group): the same item list serves every group
+          const unsigned long long dep = (unsigned long long)it.w * (unsigned)p.ncg + (unsigned)cg;
           if (lane == 0) {
             const volatile unsigned* word = p.done + (dep >> 5);
-            while (!((*word >> (dep & 31u)) & 1u)) {
+            while (!((*word >> (unsigned)(dep & 31u)) & 1u)) {
             }
           }
           __syncwarp();
@@ -547,11 +550,14 @@ sweep_fwd_kernel(const SweepParams p) {
           for (int pw = 0; pw < PWT; ++pw) st_cg(scr + pw * 32, acc[pw]);
           __threadfence();
           __syncwarp();
-          if (lane == 0) atomicOr(p.done + ((unsigned)idx >> 5), 1u << ((unsigned)idx & 31u));
+          if (lane == 0) {
+            const unsigned long long bit = (unsigned long long)idx * (unsigned)p.ncg + (unsigned)cg;
+            atomicOr(p.done + (bit >> 5), 1u << (unsigned)(bit & 31u));
+          }
         }
       }
       // release the remaining rows of the unit
-      if (lane == 0) release_rows(empty, seq0, my_q, nrows, p.ring, p.ring_magic);
+      release_rows(full, empty, seq0, my_q, nrows, p.ring, p.ring_magic, lane);
     }
     seq0 += (unsigned)nrows;
   }
@@ -577,7 +583,7 @@ SweepLayout sweep_layout(const RoiAlignArgs& a, const SweepPlan& plan) {
   L.cnt = off;          off = align_up(off + (size_t)L.m * 4, 16);
   L.unit_rows = off;    off = align_up(off + (size_t)a.num_images * plan.segs * 4, 16);
   L.unit_counter = off; off = align_up(off + 16, 16);
-  L.done = off;         off = align_up(off + (size_t)((L.item_cap + 31) / 32) * 4, 256);
+  L.done = off;         off = align_up(off + (size_t)((L.item_cap * ncg + 31) / 32) * 4, 256);
   L.zero_bytes = off;
   L.start = off;        off = align_up(off + (size_t)(L.m + 1) * 4, 256);
   L.hdr = off;          off = align_up(off + (size_t)a.num_rois * sizeof(SweepHdr), 256);
@@ -615,9 +621,11 @@ bool sweep_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_opti
   if ((size_t)smem_optin < fixed + kMinRing * row_bytes) return false;
   int ring = (int)(((size_t)smem_optin - fixed) / row_bytes);
   if (ring > kMaxRing) ring = kMaxRing;
+  if (const char* e = getenv("MOBULA_SWEEP_RING")) ring = max(kMinRing, min(atoi(e), ring));   // experiments
   plan->ring = ring;
   plan->span = ring >= 8 ? 4 : (ring >= 6 ? 4 : 3);
   if (plan->span > ring - 2) plan->span = ring - 2;
+  if (const char* e = getenv("MOBULA_SWEEP_SPAN")) plan->span = max(2, min(atoi(e), ring - 2));   // experiments
   plan->smem = fixed + (size_t)ring * row_bytes;
   // row segments per image: fill the SMs without paying too much for the lead-in rows
   const int c_work = a.c_count > 0 ? a.c_count : a.channels;
@@ -637,6 +645,7 @@ bool sweep_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_opti
     }
   }
   plan->segs = best;
+  if (const char* e = getenv("MOBULA_SWEEP_SEGS")) plan->segs = max(1, min(atoi(e), a.height));   // experiments
   plan->colcap = a.sampling_ratio > 0 ? ((a.pooled_w * a.sampling_ratio + 1) & ~1)
                                       : ((max(a.pooled_w, 2 * a.width + 3) + 2) & ~1);
   return true;

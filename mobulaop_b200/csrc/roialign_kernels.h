@@ -149,11 +149,11 @@ cudaError_t launch_bwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
 // (odd channel pitch: bank-conflict-free taps), items sorted by row; any sampling grid, any
 // pooled height, pooled width <= 16 ---------------------------------------------------------
 struct SweepPlan {
-  int pitch, rowf, vec4;      // floats between channels of a ring row (odd), floats per ring row, LDG.128 fill
+  int pitch, rowf;            // floats between channels of a ring row (odd), floats per ring row
   int ring, span;             // ring rows; rows one item's taps may span
   int pwp;                    // staging pitch
   int segs;                   // row segments per image
-  int colcap;                 // column records per ROI
+  int colcap, rowcap;         // column / row records per ROI
   size_t smem;
 };
 

@@ -45,8 +45,8 @@ namespace {
 
 constexpr int kConsumers = 16;                        // warps that compute
 constexpr int kProducers = 4;                         // warps that fill the row ring
-constexpr int kSweepThreads = (kConsumers + kProducers) * 32;
 constexpr int kFillBatch = 8;                         // 16-byte loads in flight per producer lane
+constexpr int kSweepThreads = (kConsumers + kProducers) * 32;
 constexpr int kMaxRing = 16;
 constexpr int kMinRing = 4;
 constexpr int kMaxPooledW = 16;
@@ -71,9 +71,17 @@ struct __align__(16) SweepHdr {
 // outside the plane, bilinear.h:15-18) and the fraction lx = weight of the high tap.
 typedef uint2 ColRec;
 constexpr unsigned kColInvalid = 0xffffffffu;
+// The sampling_ratio == 2 kernel takes its sample columns ready to use (16 bytes): byte offsets
+// of the two taps inside a channel row, lx, hx = 1 - lx.  A sample outside the plane points both
+// taps at the zero pad column behind the row with lx = hx = 0: it contributes exactly +0, no branch.
+typedef uint4 ColRec4;
+// A sample row inside the plane: lo | hi << 16 (plane rows of the two taps), ly.  Indexed by the
+// ordinal of the row among the ROI's sample rows inside the plane.
+typedef uint2 RowRec;
 
-// An item: sample rows [sy, sy + n) of bin row ph of ROI `roi`; taps in rows [key, key + dy].
-//   w0 roi   w1 sy | n << 16   w2 key | dy << 12 | ph << 16 | flags << 30   w3 predecessor item
+// An item: n sample rows (row records [ord, ord + n)) of bin row ph of ROI `roi`; taps in plane
+// rows [key, key + dy].
+//   w0 roi   w1 ord | n << 16   w2 key | dy << 12 | ph << 16 | flags << 30   w3 predecessor item
 // flags: 1 = first item of its bin row (sums start at 0), 2 = last (divide and write the output)
 typedef uint4 ItemRec;
 constexpr unsigned kNoDep = 0xffffffffu;
@@ -92,13 +100,14 @@ struct SweepParams {
   const float* data;
   // shared-memory geometry
   int pitch;             // floats between channels of a ring row (odd, >= width)
+  int fill_mode;         // 0: LDG.128 + STS.32 (needs 16-byte aligned rows), 1: 4-byte cp.async
   int rowf;              // floats per ring row = 32 * pitch
-  int vec4;              // rows are 16-byte aligned in global memory: LDG.128 fill
   int ring, span;        // ring rows, max rows an item's taps may span
   unsigned ring_magic;   // floor(2^32 / ring) + 1: q / ring == umulhi(q, magic)
   int pwp;               // staging pitch per channel (pooled_w | 1)
   int segs;              // row segments per image
   int colcap;            // column records per ROI
+  int rowcap;            // row records per ROI
   int compact;           // column records hold only the samples inside the plane, per-bin ranges
                          // in the header (every sampling ratio but 2)
   // tables
@@ -108,7 +117,8 @@ struct SweepParams {
   int* unit_counter;     // persistent-CTA queue
   unsigned* done;        // one bit per (item, channel group)
   SweepHdr* hdr;         // [R]
-  ColRec* cols;          // [R * colcap]
+  ColRec* cols;          // [R * colcap] (ColRec4 when !compact)
+  RowRec* rows;          // [R * rowcap]
   ItemRec* items;
   float* scratch;        // running sums of chained items: [(roi * PH + ph) * ncg + cg][PW][32]
 };
@@ -150,13 +160,15 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
     }
     ColRec* cols = p.cols + col_base;
     if (!p.compact) {
+      ColRec4* cols4 = reinterpret_cast<ColRec4*>(p.cols) + col_base;
       const int gw = g.grid_w, total = PW * gw;
       for (int k = lane; k < total; k += 32) {
         const int pw = k / gw, ix = k - pw * gw;
         const AxisTap t = axis_decode(sample_pos(g.start_w, pw, g.bin_w, ix, gw), W);
-        ColRec c = make_uint2(kColInvalid, 0u);
-        if (t.valid) c = make_uint2((unsigned)t.lo | ((unsigned)t.hi << 16), __float_as_uint(t.wl));
-        cols[k] = c;
+        ColRec4 c = make_uint4((unsigned)W * 4u, (unsigned)W * 4u, 0u, 0u);      // the zero pad column
+        if (t.valid)
+          c = make_uint4((unsigned)t.lo * 4u, (unsigned)t.hi * 4u, __float_as_uint(t.wl), __float_as_uint(t.wh));
+        cols4[k] = c;
       }
       if (lane == 0) h->ncols = total;
     } else {
@@ -191,19 +203,36 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
   }
   if (n < 0) return;
   // ---- items: lane = bin row --------------------------------------------------------------
-  for (int ph = lane; ph < PH; ph += 32) {
-    // pass A: the last sample row inside the plane decides the segment of the bin row
-    int last_lo = -1;
-    for (int iy = 0; iy < g.grid_h; ++iy) {
-      const AxisTap t = axis_decode(sample_pos(g.start_h, ph, g.bin_h, iy, g.grid_h), H);
-      if (t.valid) last_lo = t.lo;
+  RowRec* rows = p.rows + (size_t)r * p.rowcap;
+  int ord_base = 0;       // sample rows inside the plane in the bin rows before this chunk of 32
+  for (int ph0 = 0; ph0 < PH; ph0 += 32) {
+    const int ph = ph0 + lane;
+    // pass A: the last sample row inside the plane decides the segment of the bin row; the
+    // number of rows inside the plane gives the ordinal of its first row record
+    int last_lo = -1, inside = 0;
+    if (ph < PH)
+      for (int iy = 0; iy < g.grid_h; ++iy) {
+        const AxisTap t = axis_decode(sample_pos(g.start_h, ph, g.bin_h, iy, g.grid_h), H);
+        if (t.valid) {
+          last_lo = t.lo;
+          ++inside;
+        }
+      }
+    int incl = inside;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
     }
+    int ord = ord_base + incl - inside;
+    ord_base += __shfl_sync(0xffffffffu, incl, 31);
+    if (ph >= PH) continue;
     const int seg = last_lo < 0 ? 0 : seg_of_row(last_lo, p.segs, H);
     const int unit = n * p.segs + seg;
     int* cnt = p.cnt + (size_t)unit * H;
     const int* start = p.start + (size_t)unit * H;
     unsigned dep = kNoDep;
-    int open_key = -1, open_hi = 0, open_sy = 0, open_n = 0;
+    int open_key = -1, open_hi = 0, open_ord = 0, open_n = 0;
     bool first = true;
     auto emit = [&](bool last) {
       const int key = open_key < 0 ? 0 : open_key;
@@ -213,7 +242,7 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
       } else {
         const unsigned pos = (unsigned)(__ldg(start + key) + atomicAdd(cnt + key, 1));
         const unsigned flags = (first ? 1u : 0u) | (last ? 2u : 0u);
-        p.items[pos] = make_uint4((unsigned)r, (unsigned)open_sy | ((unsigned)open_n << 16),
+        p.items[pos] = make_uint4((unsigned)r, (unsigned)open_ord | ((unsigned)open_n << 16),
                                   (unsigned)key | ((unsigned)(open_hi - key) << 12) | ((unsigned)ph << 16) |
                                       (flags << 30),
                                   dep);
@@ -224,20 +253,23 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
     for (int iy = 0; iy < g.grid_h; ++iy) {
       const AxisTap t = axis_decode(sample_pos(g.start_h, ph, g.bin_h, iy, g.grid_h), H);
       if (!t.valid) continue;
+      if (PASS == 1 && ord < p.rowcap)
+        rows[ord] = make_uint2((unsigned)t.lo | ((unsigned)t.hi << 16), __float_as_uint(t.wl));
       if (open_key >= 0 && t.hi - open_key + 1 > p.span) {
         emit(false);
         open_key = -1;
       }
       if (open_key < 0) {
         open_key = t.lo;
-        open_sy = ph * g.grid_h + iy;
+        open_ord = ord;
         open_n = 0;
       }
       open_hi = t.hi;
       ++open_n;
+      ++ord;
     }
     if (open_key < 0) {       // no sample row inside the plane: the bin row is all zeros
-      open_sy = ph * g.grid_h;
+      open_ord = 0;
       open_n = 0;
       open_hi = 0;
     }
@@ -285,6 +317,16 @@ __device__ __forceinline__ void release_rows(uint64_t* full, uint64_t* empty, un
   }
 }
 
+// 4-byte asynchronous copy global -> shared (LDGSTS.32)
+__device__ __forceinline__ void cp_async4(unsigned dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+// arrival on `bar` once every cp.async this thread issued so far has completed (the barrier's
+// expected count already includes it)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_addr(bar)) : "memory");
+}
+
 __device__ __forceinline__ float lds_f32(unsigned addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -296,6 +338,9 @@ __device__ __forceinline__ float ld_cg(const float* p) {
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+// orders this thread's earlier and later global accesses at GPU scope (no L1 invalidation: the
+// running sums go through st.cg / ld.cg)
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_cg(float* p, float v) { asm volatile("st.global.cg.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
 // ---- the forward sweep ---------------------------------------------------------------------
@@ -322,6 +367,8 @@ sweep_fwd_kernel(const SweepParams p) {
   ptx::chain_enter();
   const int H = p.height, PH = p.pooled_h;
   const int bins = PH * PWT;
+  // the zero pad column behind every channel row (samples outside the plane read it)
+  for (int i = threadIdx.x; i < p.ring * 32; i += kSweepThreads) ring[(size_t)i * p.pitch + p.width] = 0.0f;
   const unsigned ring_base = ptx::smem_addr(ring);
   const unsigned lane_off = (unsigned)(lane * p.pitch * 4);
   const unsigned row_bytes = (unsigned)p.rowf * 4u;
@@ -347,23 +394,37 @@ sweep_fwd_kernel(const SweepParams p) {
     const int c0 = cg * 32;
 
     if (warp >= kConsumers) {
-      // ---- producers: warp pw fills channels [8 pw, 8 pw + 8) of every ring row ------------
+      // ---- producers: warp pw fills channels [8 pw, 8 pw + 8) of every ring row with 4-byte
+      // cp.async (LDGSTS): lane = pixel, 128 coalesced bytes per instruction land on 32 consecutive
+      // banks; nothing is staged in registers, so a producer runs as many rows ahead as the ring
+      // has free slots.  Each lane's arrival on full[slot] fires when its own copies have landed.
       const int pw8 = (warp - kConsumers) * 8;
       const int W = p.width;
-      const int cvalid = min(32, p.c_work - c0);
+      const int cend = min(pw8 + 8, min(32, p.c_work - c0));
       const size_t plane = (size_t)H * W;
-      const float* src0 = p.data + ((size_t)n * p.channels + c0) * plane + (size_t)ya * W;
+      const float* src0 = p.data + ((size_t)n * p.channels + c0) * plane + (size_t)ya * W + lane;
       for (int q = 0; q < nrows; ++q) {
         const unsigned s = seq0 + (unsigned)q;
         const unsigned round = __umulhi(s, p.ring_magic), slot = s - round * (unsigned)p.ring;
         if (round > 0) ptx::mbar_wait(empty + slot, (round & 1u) ^ 1u);   // every consumer has left the old row
-        float* row = ring + (size_t)slot * p.rowf;
-        const float* src = src0 + (size_t)q * W;
-        if (p.vec4) {
-          // lane = (channel ci of 4, quad j of 8): 4 channels x 32 pixels per load instruction;
-          // the four stores of a quad hit banks (ci * pitch + 4 j + k) mod 32, all distinct
+        const float* src_row = src0 + (size_t)q * W;
+        if (p.fill_mode == 1) {
+          const unsigned dst_row = ring_base + slot * row_bytes + (unsigned)lane * 4u;
+          for (int c = pw8; c < cend; ++c) {
+            const float* src = src_row + (size_t)c * plane;
+            const unsigned dst = dst_row + (unsigned)(c * p.pitch) * 4u;
+#pragma unroll 3
+            for (int x = 0; x < W - lane; x += 32) cp_async4(dst + (unsigned)x * 4u, src + x);
+          }
+          cp_async_arrive(full + slot);
+        } else {
+          // LDG.128 + 4 x STS.32: lane = (channel ci of 4, quad j of 8): 4 channels x 32 pixels per
+          // load instruction; the four stores of a quad hit banks (ci * pitch + 4 j + k) mod 32, all
+          // distinct.  Eight loads are in flight per lane.
           const int j = lane & 7, ci = lane >> 3;
-          const int nxc = (W + 31) >> 5, tasks = 2 * nxc;        // (channel half, 32-pixel chunk)
+          const float* src = src_row - lane;                    // src0 carries + lane
+          float* row = ring + (size_t)slot * p.rowf;
+          const int nxc = (W + 31) >> 5, tasks = 2 * nxc;       // (channel half, 32-pixel chunk)
           for (int t0 = 0; t0 < tasks; t0 += kFillBatch) {
             float4 v[kFillBatch];
 #pragma unroll
@@ -371,7 +432,7 @@ sweep_fwd_kernel(const SweepParams p) {
               const int t = t0 + u, half = t >= nxc ? 1 : 0, xc = t - half * nxc;
               const int c = pw8 + half * 4 + ci, x = xc * 32 + 4 * j;
               v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (t < tasks && x < W && c < cvalid)
+              if (t < tasks && x < W && c < cend)
                 v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * plane + x));
             }
 #pragma unroll
@@ -387,27 +448,8 @@ sweep_fwd_kernel(const SweepParams p) {
               }
             }
           }
-        } else {
-          // rows not 16-byte aligned: lane = pixel, one channel per instruction
-          const int nxc = (W + 31) >> 5, tasks = 8 * nxc;
-          for (int t0 = 0; t0 < tasks; t0 += kFillBatch) {
-            float v[kFillBatch];
-#pragma unroll
-            for (int u = 0; u < kFillBatch; ++u) {
-              const int t = t0 + u, cc = t / nxc, xc = t - cc * nxc;
-              const int c = pw8 + cc, x = xc * 32 + lane;
-              v[u] = 0.f;
-              if (t < tasks && x < W && c < cvalid) v[u] = __ldg(src + (size_t)c * plane + x);
-            }
-#pragma unroll
-            for (int u = 0; u < kFillBatch; ++u) {
-              const int t = t0 + u, cc = t / nxc, xc = t - cc * nxc;
-              const int c = pw8 + cc, x = xc * 32 + lane;
-              if (t < tasks && x < W) row[c * p.pitch + x] = v[u];
-            }
-          }
+          mbar_arrive(full + slot);
         }
-        mbar_arrive(full + slot);       // release: this lane's stores are visible to who waits
       }
     } else {
       // ---- consumers ------------------------------------------------------------------
@@ -418,14 +460,14 @@ sweep_fwd_kernel(const SweepParams p) {
         idx = __shfl_sync(0xffffffffu, idx, 0) + item_lo;
         if (idx >= item_hi) break;
         const ItemRec it = __ldg(p.items + idx);
-        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(p.hdr + it.x));
-        const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(p.hdr + it.x) + 1);
-        const int roi = (int)h0.x;
-        const int gh = (int)(h0.z & 0xffffu), gw = (int)(h0.z >> 16);
-        const float count = __uint_as_float(h0.w);
-        const float start_h = __uint_as_float(h1.x), bin_h = __uint_as_float(h1.y);
-        const ColRec* cols = p.cols + h1.z;
-        const int sy0 = (int)(it.y & 0xffffu), nsy = (int)(it.y >> 16);
+        const int roi = (int)it.x;
+        const SweepHdr* hdr = p.hdr + roi;
+        const uint2 gc = __ldg(reinterpret_cast<const uint2*>(hdr) + 1);   // grid sizes, count: used at the end
+        const size_t col_base = (size_t)roi * p.colcap;
+        const ColRec* cols = p.cols + col_base;
+        const ColRec4* cols4 = reinterpret_cast<const ColRec4*>(p.cols) + col_base;
+        const int nsy = (int)(it.y >> 16);
+        const RowRec* rows = p.rows + (size_t)roi * p.rowcap + (it.y & 0xffffu);
         const int key = (int)(it.z & 0xfffu), dy = (int)((it.z >> 12) & 0xfu);
         const int ph = (int)((it.z >> 16) & 0x3fffu);
         const unsigned flags = it.z >> 30;
@@ -454,39 +496,35 @@ sweep_fwd_kernel(const SweepParams p) {
             }
           }
           __syncwarp();
-          __threadfence();
+          fence_gpu();
 #pragma unroll
           for (int pw = 0; pw < PWT; ++pw) acc[pw] = ld_cg(scr + pw * 32);
         }
         uint4 cs0 = make_uint4(0, 0, 0, 0), cs1 = cs0;
         int ncols = 0;
         if (GWT == 0) {
-          cs0 = __ldg(reinterpret_cast<const uint4*>(p.hdr + it.x) + 2);
-          cs1 = __ldg(reinterpret_cast<const uint4*>(p.hdr + it.x) + 3);
-          ncols = (int)h1.w;
+          cs0 = __ldg(reinterpret_cast<const uint4*>(hdr) + 2);
+          cs1 = __ldg(reinterpret_cast<const uint4*>(hdr) + 3);
+          ncols = __ldg(&hdr->ncols);
         }
-        for (int sy = sy0; sy < sy0 + nsy; ++sy) {
-          const int iy = sy - ph * gh;
-          const AxisTap t = axis_decode(sample_pos(start_h, ph, bin_h, iy, gh), H);
-          const unsigned slo = seq0 + (unsigned)(t.lo - ya), shi = seq0 + (unsigned)(t.hi - ya);
+        for (int k = 0; k < nsy; ++k) {
+          const RowRec rr = __ldg(rows + k);
+          const unsigned slo = seq0 + ((rr.x & 0xffffu) - (unsigned)ya), shi = seq0 + ((rr.x >> 16) - (unsigned)ya);
           const unsigned row_lo = ring_base + lane_off + (slo - __umulhi(slo, p.ring_magic) * (unsigned)p.ring) * row_bytes;
           const unsigned row_hi = ring_base + lane_off + (shi - __umulhi(shi, p.ring_magic) * (unsigned)p.ring) * row_bytes;
-          const float ly = t.wl, hy = t.wh;
+          const float ly = __uint_as_float(rr.y), hy = __fsub_rn(1.0f, ly);
           if (GWT > 0) {
 #pragma unroll
             for (int pw = 0; pw < PWT; ++pw) {
 #pragma unroll
               for (int ix = 0; ix < GWT; ++ix) {
-                const ColRec c = __ldg(cols + pw * GWT + ix);
-                if (c.x != kColInvalid) {
-                  const unsigned olo = (c.x & 0xffffu) << 2, ohi = (c.x >> 16) << 2;
-                  const float lx = __uint_as_float(c.y), hx = __fsub_rn(1.0f, lx);
-                  const float v1 = lds_f32(row_lo + olo), v2 = lds_f32(row_lo + ohi);
-                  const float v3 = lds_f32(row_hi + olo), v4 = lds_f32(row_hi + ohi);
-                  const float s = tap_sum(__fmul_rn(hy, hx), v1, __fmul_rn(hy, lx), v2, __fmul_rn(ly, hx), v3,
-                                          __fmul_rn(ly, lx), v4);
-                  acc[pw] = __fadd_rn(acc[pw], s);
-                }
+                const ColRec4 c = __ldg(cols4 + pw * GWT + ix);
+                const float lx = __uint_as_float(c.z), hx = __uint_as_float(c.w);
+                const float v1 = lds_f32(row_lo + c.x), v2 = lds_f32(row_lo + c.y);
+                const float v3 = lds_f32(row_hi + c.x), v4 = lds_f32(row_hi + c.y);
+                const float s = tap_sum(__fmul_rn(hy, hx), v1, __fmul_rn(hy, lx), v2, __fmul_rn(ly, hx), v3,
+                                        __fmul_rn(ly, lx), v4);
+                acc[pw] = __fadd_rn(acc[pw], s);
               }
             }
           } else {
@@ -524,7 +562,8 @@ sweep_fwd_kernel(const SweepParams p) {
         }
         if (flags & 2u) {
           // ---- the bin row is complete: divide, transpose through shared memory, store ----
-          const int cnt_i = gh * gw;
+          const int cnt_i = (int)(gc.x & 0xffffu) * (int)(gc.x >> 16);
+          const float count = __uint_as_float(gc.y);
           const bool pow2 = (cnt_i & (cnt_i - 1)) == 0;
           const float inv = __fdiv_rn(1.0f, count);
           __syncwarp();
@@ -540,7 +579,7 @@ sweep_fwd_kernel(const SweepParams p) {
             const int c = f / PWT, pw = f - c * PWT;
             if (c < cvalid) {
               const float v = stage[c * p.pwp + pw];
-              float* dst = o + (size_t)c * bins + pw;
+              float* dst = o + c * bins + pw;
               *dst = p.accumulate ? __fadd_rn(*dst, v) : v;
             }
           }
@@ -548,7 +587,7 @@ sweep_fwd_kernel(const SweepParams p) {
           // ---- hand the running sums to the successor item ------------------------------
 #pragma unroll
           for (int pw = 0; pw < PWT; ++pw) st_cg(scr + pw * 32, acc[pw]);
-          __threadfence();
+          fence_gpu();
           __syncwarp();
           if (lane == 0) {
             const unsigned long long bit = (unsigned long long)idx * (unsigned)p.ncg + (unsigned)cg;
@@ -566,7 +605,7 @@ sweep_fwd_kernel(const SweepParams p) {
 // ---- host side ------------------------------------------------------------------------------
 struct SweepLayout {
   size_t zero_bytes;     // leading part of the workspace that is cleared per call
-  size_t cnt, start, unit_rows, unit_counter, done, hdr, cols, items, scratch, total;
+  size_t cnt, start, unit_rows, unit_counter, done, hdr, cols, rows, items, scratch, total;
   long long item_cap;
   int m;                 // N * segs * H
 };
@@ -587,7 +626,9 @@ SweepLayout sweep_layout(const RoiAlignArgs& a, const SweepPlan& plan) {
   L.zero_bytes = off;
   L.start = off;        off = align_up(off + (size_t)(L.m + 1) * 4, 256);
   L.hdr = off;          off = align_up(off + (size_t)a.num_rois * sizeof(SweepHdr), 256);
-  L.cols = off;         off = align_up(off + (size_t)a.num_rois * plan.colcap * sizeof(ColRec), 256);
+  L.cols = off;
+  off = align_up(off + (size_t)a.num_rois * plan.colcap * (a.sampling_ratio == 2 ? sizeof(ColRec4) : sizeof(ColRec)), 256);
+  L.rows = off;         off = align_up(off + (size_t)a.num_rois * plan.rowcap * sizeof(RowRec), 256);
   L.items = off;        off = align_up(off + (size_t)L.item_cap * sizeof(ItemRec), 256);
   L.scratch = off;
   off = align_up(off + (size_t)a.num_rois * a.pooled_h * ncg * a.pooled_w * 32 * sizeof(float), 256);
@@ -612,8 +653,8 @@ bool sweep_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_opti
   if (a.num_images <= 0 || a.num_images > 4096 || a.num_rois <= 0) return false;
   if (a.width > 65535 || a.height > kMaxPlaneH || a.pooled_w > kMaxPooledW || a.pooled_h > 16383) return false;
   if ((long long)a.pooled_h * (a.sampling_ratio > 0 ? a.sampling_ratio : 1024) > 65535) return false;
-  plan->vec4 = (a.width % 4 == 0 && (reinterpret_cast<uintptr_t>(plane_ptr) & 15u) == 0) ? 1 : 0;
-  plan->pitch = a.width | 1;             // odd: the 32 channels of a pixel hit the 32 banks
+  (void)plane_ptr;
+  plan->pitch = (a.width + 1) | 1;       // odd: the 32 channels of a pixel hit the 32 banks; >= 1 pad word
   plan->rowf = 32 * plan->pitch;
   plan->pwp = a.pooled_w | 1;
   const size_t fixed = (size_t)kConsumers * 32 * plan->pwp * 4 + 2 * kMaxRing * 8 + 64;
@@ -648,6 +689,7 @@ bool sweep_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_opti
   if (const char* e = getenv("MOBULA_SWEEP_SEGS")) plan->segs = max(1, min(atoi(e), a.height));   // experiments
   plan->colcap = a.sampling_ratio > 0 ? ((a.pooled_w * a.sampling_ratio + 1) & ~1)
                                       : ((max(a.pooled_w, 2 * a.width + 3) + 2) & ~1);
+  plan->rowcap = a.sampling_ratio > 0 ? a.pooled_h * a.sampling_ratio : 2 * a.height + 3 + a.pooled_h;
   return true;
 }
 
@@ -675,7 +717,8 @@ cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void*
   p.accumulate = accumulate;
   p.data = data;
   p.pitch = plan.pitch;
-  p.vec4 = plan.vec4;
+  p.fill_mode = (a.width % 4 == 0 && (reinterpret_cast<uintptr_t>(data) & 15u) == 0) ? 0 : 1;
+  if (const char* e = getenv("MOBULA_SWEEP_FILL")) p.fill_mode = atoi(e) ? 1 : p.fill_mode;   // experiments
   p.rowf = plan.rowf;
   p.ring = plan.ring;
   p.span = plan.span;
@@ -683,6 +726,7 @@ cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void*
   p.pwp = plan.pwp;
   p.segs = plan.segs;
   p.colcap = plan.colcap;
+  p.rowcap = plan.rowcap;
   p.compact = a.sampling_ratio == 2 ? 0 : 1;
   p.cnt = reinterpret_cast<int*>(ws + L.cnt);
   p.start = reinterpret_cast<int*>(ws + L.start);
@@ -691,6 +735,7 @@ cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void*
   p.done = reinterpret_cast<unsigned*>(ws + L.done);
   p.hdr = reinterpret_cast<SweepHdr*>(ws + L.hdr);
   p.cols = reinterpret_cast<ColRec*>(ws + L.cols);
+  p.rows = reinterpret_cast<RowRec*>(ws + L.rows);
   p.items = reinterpret_cast<ItemRec*>(ws + L.items);
   p.scratch = reinterpret_cast<float*>(ws + L.scratch);
 
@@ -718,8 +763,8 @@ cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void*
   if (e != cudaSuccess) return e;
   if ((e = checkpoint("pass 2")) != cudaSuccess) return e;
   if (debug)
-    fprintf(stderr, "[sweep] pitch %d vec4 %d rowf %d ring %d span %d segs %d colcap %d smem %zu units %lld\n",
-            plan.pitch, plan.vec4, plan.rowf, plan.ring, plan.span, plan.segs, plan.colcap, plan.smem,
+    fprintf(stderr, "[sweep] pitch %d rowf %d ring %d span %d segs %d colcap %d smem %zu units %lld\n",
+            plan.pitch, plan.rowf, plan.ring, plan.span, plan.segs, plan.colcap, plan.smem,
             (long long)a.num_images * plan.segs * p.ncg);
   const long long units = (long long)a.num_images * plan.segs * p.ncg;
   const dim3 grid((unsigned)(units < num_sms ? units : num_sms));

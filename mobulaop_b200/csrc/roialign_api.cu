@@ -242,9 +242,14 @@ static int forward_device(DeviceState& st, int device, cudaStream_t stream, cons
   if (algo > MOBULA_ROIALIGN_ALGO_SWEEP)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown forward algorithm %u", algo);
   const bool no_tables = (flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) != 0;
+  ResidentPlan rplan;
+  const bool resident_ok = !no_tables && resident_supported(a, data, st.smem_optin, &rplan);
   {
+    // sweep kernels: on request, and automatically wherever the resident kernels do not apply
+    // (adaptive grids, planes beyond one SM's shared memory) instead of the global-memory gather
     SweepPlan splan;
-    const bool want = algo == MOBULA_ROIALIGN_ALGO_SWEEP || (algo == MOBULA_ROIALIGN_ALGO_AUTO && prefer_sweep());
+    const bool want = algo == MOBULA_ROIALIGN_ALGO_SWEEP ||
+                      (algo == MOBULA_ROIALIGN_ALGO_AUTO && (prefer_sweep() || !resident_ok));
     const bool sweep_ok = want && !no_tables && sweep_supported(a, data, st.smem_optin, st.num_sms, &splan);
     if (algo == MOBULA_ROIALIGN_ALGO_SWEEP && !sweep_ok)
       return fail(MOBULA_ERR_UNSUPPORTED,
@@ -259,8 +264,6 @@ static int forward_device(DeviceState& st, int device, cudaStream_t stream, cons
       return release_tables(st, stream);
     }
   }
-  ResidentPlan rplan;
-  const bool resident_ok = !no_tables && resident_supported(a, data, st.smem_optin, &rplan);
   if (algo == MOBULA_ROIALIGN_ALGO_RESIDENT && !resident_ok)
     return fail(MOBULA_ERR_UNSUPPORTED,
                 "resident algorithm needs num_images in [0, 4096], sampling_ratio in [1, 4], at most "
@@ -303,13 +306,31 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward mode %d", mode);
   if (algo > MOBULA_ROIALIGN_ALGO_SWEEP)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward algorithm %u", algo);
-  if (algo == MOBULA_ROIALIGN_ALGO_SWEEP) algo = MOBULA_ROIALIGN_ALGO_AUTO;   // no sweep backward yet
+  const bool want_tile = algo == MOBULA_ROIALIGN_ALGO_SWEEP;
   if (!accumulate && a.num_images < 0)
     return fail(MOBULA_ERR_INVALID_ARGUMENT,
                 "backward without MOBULA_ROIALIGN_ACCUMULATE needs num_images >= 0");
   const bool deterministic = mode == MOBULA_ROIALIGN_BWD_DETERMINISTIC;
   if (deterministic && algo == MOBULA_ROIALIGN_ALGO_GATHER)
     return fail(MOBULA_ERR_UNSUPPORTED, "the gather backward uses global atomics: not deterministic");
+  auto run_tile = [&](const TilePlan& tplan) -> int {
+    t_algo[1] = deterministic ? "tile-canonical" : "tile";
+    void* ws = nullptr;
+    int rc = prepare_workspace(st, tile_bwd_workspace(a, tplan), stream, &ws);
+    if (rc) return rc;
+    CUDA_TRY(launch_bwd_tile(a, tplan, ws, dy, dx, accumulate, deterministic, st.num_sms, stream));
+    return release_tables(st, stream);
+  };
+  TilePlan tplan;
+  const bool tile_ok = !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && a.num_images >= 0 &&
+                       tile_supported(a, st.smem_optin, st.num_sms, &tplan);
+  if (want_tile) {
+    if (!tile_ok)
+      return fail(MOBULA_ERR_UNSUPPORTED,
+                  "sweep (row tile) backward needs num_images in [1, 4096], pooled_w <= 16 and two %d-pixel "
+                  "rows of 32 channels within %d bytes of shared memory", a.width, st.smem_optin);
+    return run_tile(tplan);
+  }
   {
     // resident kernels: fast (merged weights) or deterministic (canonical order) variant
     ResidentPlan rplan;
@@ -329,6 +350,8 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
       return release_tables(st, stream);
     }
   }
+  // any sampling grid, any plane that leaves room for two tile rows: the row-tile kernel
+  if (tile_ok && algo == MOBULA_ROIALIGN_ALGO_AUTO) return run_tile(tplan);
   if (deterministic || algo == MOBULA_ROIALIGN_ALGO_PLANE) {
     PlanePlan plan;
     if (!plane_supported(a, dx, st.smem_optin, &plan))

@@ -162,4 +162,15 @@ size_t sweep_fwd_workspace(const RoiAlignArgs& a, const SweepPlan& plan);
 cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void* workspace, const float* data,
                              float* out, int accumulate, int num_sms, cudaStream_t stream);
 
+// backward of the sweep family: dX row tiles in shared memory, strip-owner warps, ROIs visited in
+// ascending order; deterministic = every tap added separately in the reference's order
+struct TilePlan {
+  int pitch, tr, strip, pwp, colcap, rowcap;
+  size_t smem;
+};
+bool tile_supported(const RoiAlignArgs& a, int smem_optin, int num_sms, TilePlan* plan);
+size_t tile_bwd_workspace(const RoiAlignArgs& a, const TilePlan& plan);
+cudaError_t launch_bwd_tile(const RoiAlignArgs& a, const TilePlan& plan, void* workspace, const float* dy,
+                            float* dx, int accumulate, int deterministic, int num_sms, cudaStream_t stream);
+
 }  // namespace mobula_b200

@@ -61,7 +61,7 @@ struct __align__(16) SweepHdr {
   int batch;             // image, -1: batch index outside [0, N)
   int grid;              // grid_h | grid_w << 16
   float count;           // (float)(grid_h * grid_w)
-  float start_h, bin_h;
+  unsigned yr, xr;       // plane rows / columns the ROI's samples touch: min | max << 16 (0xffff | 0: none)
   unsigned col_base;     // first column record of this ROI
   int ncols;             // compacted tables: number of (valid) column records
   unsigned short cstart[16];   // compacted tables: first record of bin column pw (end = next / ncols)
@@ -119,6 +119,9 @@ struct SweepParams {
   SweepHdr* hdr;         // [R]
   ColRec* cols;          // [R * colcap] (ColRec4 when !compact)
   RowRec* rows;          // [R * rowcap]
+  uint2* phr;            // [R * PH] bin row: first | end row record, first tap row | last tap row << 16 (backward)
+  uint2* pwr;            // [R * 16] bin column: first | end column record, first | last tap column (backward)
+  int tables_only;       // pass 1 builds the per-ROI tables and no items (backward)
   ItemRec* items;
   float* scratch;        // running sums of chained items: [(roi * PH + ph) * ncg + cg][PW][32]
 };
@@ -144,21 +147,23 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
       h->batch = n;
       h->grid = g.grid_h | (g.grid_w << 16);
       h->count = g.count;
-      h->start_h = g.start_h;
-      h->bin_h = g.bin_h;
       h->col_base = col_base;
     }
     if (n < 0) {
       // a ROI that points at no image reads nothing: its output rows are zero
-      if (!p.accumulate) {
+      if (!p.accumulate && !p.tables_only) {
         const size_t per = (size_t)p.c_work * PH * PW;
         float* o = p.out + (size_t)r * p.channels * PH * PW;
         for (size_t i = lane; i < per; i += 32) o[i] = 0.0f;
       }
-      if (lane == 0) h->ncols = 0;
+      if (lane == 0) {
+        h->ncols = 0;
+        h->yr = h->xr = 0xffffu;
+      }
       return;
     }
     ColRec* cols = p.cols + col_base;
+    int xmin = 0xffff, xmax = 0;
     if (!p.compact) {
       ColRec4* cols4 = reinterpret_cast<ColRec4*>(p.cols) + col_base;
       const int gw = g.grid_w, total = PW * gw;
@@ -166,8 +171,11 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
         const int pw = k / gw, ix = k - pw * gw;
         const AxisTap t = axis_decode(sample_pos(g.start_w, pw, g.bin_w, ix, gw), W);
         ColRec4 c = make_uint4((unsigned)W * 4u, (unsigned)W * 4u, 0u, 0u);      // the zero pad column
-        if (t.valid)
+        if (t.valid) {
           c = make_uint4((unsigned)t.lo * 4u, (unsigned)t.hi * 4u, __float_as_uint(t.wl), __float_as_uint(t.wh));
+          xmin = min(xmin, t.lo);
+          xmax = max(xmax, t.hi);
+        }
         cols4[k] = c;
       }
       if (lane == 0) h->ncols = total;
@@ -177,6 +185,8 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
       int base = 0;
       for (int pw = 0; pw < PW; ++pw) {
         if (lane == 0 && pw < 16) h->cstart[pw] = (unsigned short)base;
+        const int bin_first = base;
+        int bmin = 0xffff, bmax = 0;
         for (int i0 = 0; i0 < g.grid_w; i0 += 32) {
           const int ix = i0 + lane;
           bool valid = false;
@@ -184,7 +194,13 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
           if (ix < g.grid_w) {
             const AxisTap t = axis_decode(sample_pos(g.start_w, pw, g.bin_w, ix, g.grid_w), W);
             valid = t.valid;
-            if (valid) c = make_uint2((unsigned)t.lo | ((unsigned)t.hi << 16), __float_as_uint(t.wl));
+            if (valid) {
+              c = make_uint2((unsigned)t.lo | ((unsigned)t.hi << 16), __float_as_uint(t.wl));
+              xmin = min(xmin, t.lo);
+              xmax = max(xmax, t.hi);
+              bmin = min(bmin, t.lo);
+              bmax = max(bmax, t.hi);
+            }
           }
           const unsigned m = __ballot_sync(0xffffffffu, valid);
           if (valid) {
@@ -193,6 +209,16 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
           }
           base += __popc(m);
         }
+        if (p.pwr) {
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            bmin = min(bmin, __shfl_xor_sync(0xffffffffu, bmin, d));
+            bmax = max(bmax, __shfl_xor_sync(0xffffffffu, bmax, d));
+          }
+          if (lane == 0 && pw < 16)
+            p.pwr[(size_t)r * 16 + pw] = make_uint2((unsigned)bin_first | ((unsigned)min(base, p.colcap) << 16),
+                                                    (unsigned)(bmin & 0xffff) | ((unsigned)bmax << 16));
+        }
       }
       if (base > p.colcap) base = p.colcap;     // cannot happen (see the bound above)
       if (lane == 0) {
@@ -200,21 +226,30 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
         h->ncols = base;
       }
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, d));
+      xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, d));
+    }
+    if (lane == 0) h->xr = (unsigned)xmin | ((unsigned)xmax << 16);
   }
   if (n < 0) return;
   // ---- items: lane = bin row --------------------------------------------------------------
   RowRec* rows = p.rows + (size_t)r * p.rowcap;
+  int ymin = 0xffff, ymax = 0;
   int ord_base = 0;       // sample rows inside the plane in the bin rows before this chunk of 32
   for (int ph0 = 0; ph0 < PH; ph0 += 32) {
     const int ph = ph0 + lane;
     // pass A: the last sample row inside the plane decides the segment of the bin row; the
     // number of rows inside the plane gives the ordinal of its first row record
-    int last_lo = -1, inside = 0;
+    int last_lo = -1, inside = 0, first_lo = -1, last_hi = 0;
     if (ph < PH)
       for (int iy = 0; iy < g.grid_h; ++iy) {
         const AxisTap t = axis_decode(sample_pos(g.start_h, ph, g.bin_h, iy, g.grid_h), H);
         if (t.valid) {
+          if (first_lo < 0) first_lo = t.lo;
           last_lo = t.lo;
+          last_hi = t.hi;
           ++inside;
         }
       }
@@ -226,6 +261,21 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
     }
     int ord = ord_base + incl - inside;
     ord_base += __shfl_sync(0xffffffffu, incl, 31);
+    if (PASS == 1 && p.phr && ph < PH)
+      p.phr[(size_t)r * PH + ph] = make_uint2((unsigned)ord | ((unsigned)(ord + inside) << 16),
+                                              (unsigned)(first_lo < 0 ? 0 : first_lo) | ((unsigned)last_hi << 16));
+    if (PASS == 1 && p.tables_only) {
+      if (ph < PH)
+        for (int iy = 0; iy < g.grid_h; ++iy) {
+          const AxisTap t = axis_decode(sample_pos(g.start_h, ph, g.bin_h, iy, g.grid_h), H);
+          if (!t.valid) continue;
+          if (ord < p.rowcap) rows[ord] = make_uint2((unsigned)t.lo | ((unsigned)t.hi << 16), __float_as_uint(t.wl));
+          ymin = min(ymin, t.lo);
+          ymax = max(ymax, t.hi);
+          ++ord;
+        }
+      continue;
+    }
     if (ph >= PH) continue;
     const int seg = last_lo < 0 ? 0 : seg_of_row(last_lo, p.segs, H);
     const int unit = n * p.segs + seg;
@@ -255,6 +305,8 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
       if (!t.valid) continue;
       if (PASS == 1 && ord < p.rowcap)
         rows[ord] = make_uint2((unsigned)t.lo | ((unsigned)t.hi << 16), __float_as_uint(t.wl));
+      ymin = min(ymin, t.lo);
+      ymax = max(ymax, t.hi);
       if (open_key >= 0 && t.hi - open_key + 1 > p.span) {
         emit(false);
         open_key = -1;
@@ -274,6 +326,14 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
       open_hi = 0;
     }
     emit(true);
+  }
+  if (PASS == 1) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, d));
+      ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, d));
+    }
+    if (lane == 0) p.hdr[r].yr = (unsigned)ymin | ((unsigned)ymax << 16);
   }
 }
 
@@ -602,6 +662,221 @@ sweep_fwd_kernel(const SweepParams p) {
   }
 }
 
+// one tap of the backward: shared-memory read-modify-write by the pixel's only writer
+template <bool DET>
+__device__ __forceinline__ void tap_add(unsigned addr, float g, float w, float count, float inv, bool pow2) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  if (DET) {
+    const float t = __fmul_rn(g, w);                              // dtop * w, then / count (ROIAlign.cpp:143-146)
+    v = __fadd_rn(v, pow2 ? __fmul_rn(t, inv) : __fdiv_rn(t, count));
+  } else {
+    v = fmaf(g, w, v);
+  }
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// the four taps of one sample when they are four different pixels of this warp's strip
+template <bool DET>
+__device__ __forceinline__ void taps4(unsigned a1, unsigned a2, unsigned a3, unsigned a4, float g, float w1, float w2,
+                                      float w3, float w4, float count, float inv, bool pow2) {
+  float v1, v2, v3, v4;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(a1) : "memory");
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v2) : "r"(a2));
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v3) : "r"(a3));
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4) : "r"(a4));
+  if (DET) {
+    const float t1 = __fmul_rn(g, w1), t2 = __fmul_rn(g, w2), t3 = __fmul_rn(g, w3), t4 = __fmul_rn(g, w4);
+    v1 = __fadd_rn(v1, pow2 ? __fmul_rn(t1, inv) : __fdiv_rn(t1, count));
+    v2 = __fadd_rn(v2, pow2 ? __fmul_rn(t2, inv) : __fdiv_rn(t2, count));
+    v3 = __fadd_rn(v3, pow2 ? __fmul_rn(t3, inv) : __fdiv_rn(t3, count));
+    v4 = __fadd_rn(v4, pow2 ? __fmul_rn(t4, inv) : __fdiv_rn(t4, count));
+  } else {
+    v1 = fmaf(g, w1, v1);
+    v2 = fmaf(g, w2, v2);
+    v3 = fmaf(g, w3, v3);
+    v4 = fmaf(g, w4, v4);
+  }
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a1), "f"(v1));
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a2), "f"(v2));
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a3), "f"(v3));
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a4), "f"(v4) : "memory");
+}
+
+// ---- the backward: row tiles, strip-owner warps ------------------------------------------------
+// dX is cut into tiles of `tr` full-width rows of 32 channels that live in shared memory as
+// [row][channel][pitch] (the forward's layout: lane = channel, conflict-free); a CTA takes
+// (image, channel group, tile) units from a queue.  Each of its 16 warps OWNS a strip of columns
+// of the tile -- every pixel has exactly one writer, so there are no atomics -- and walks the
+// image's ROIs in ascending order; for every bin row of a ROI that reaches into the tile it
+// fetches the 32 x PW gradients (transposed through shared memory), then visits the samples in
+// the reference's order (bin column, sample row, sample column; ROIAlign.cpp:126-157) and adds
+// the taps that fall into its strip and the tile's rows.  A finished tile is written once,
+// coalesced; the zero-fill of ROIAlign.py:33-34 is fused.
+//   DET: every tap is added separately as v += (dtop * (wy * wx)) / count -- each pixel receives
+//        exactly the single-thread reference's sequence of additions: bit-identical dX;
+//   else: v = fma(dtop / count, wy * wx, v): same order, contracted arithmetic.
+// Any sampling grid; the tables are the forward's (pass 1 with compacted column records).
+constexpr int kTileWarps = 16;
+
+struct TileParams {
+  const float* dy;
+  float* dx;
+  int num_images, channels, c_work, ncg;
+  int height, width, pooled_h, pooled_w;
+  int accumulate;
+  int pitch, tr, strip;     // floats between channels of a tile row (odd), rows per tile, columns per warp
+  int pwp;
+  int colcap, rowcap;
+  const int* img_start;     // [N + 2] grouped position of the first ROI of every image
+  const int* order;         // [R] ROI rows grouped by image, ascending inside an image
+  const SweepHdr* hdr;
+  const ColRec* cols;
+  const RowRec* rows;
+  const uint2* phr;
+  const uint2* pwr;
+  int* unit_counter;
+};
+
+template <int PWT, bool DET>
+__global__ void __launch_bounds__(kTileWarps * 32, 1) tile_bwd_kernel(const TileParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);
+  const int rowf = 32 * p.pitch;
+  float* stage_all = tile + (size_t)p.tr * rowf;
+  __shared__ int s_unit;
+  ptx::chain_enter();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* stage = stage_all + warp * 32 * p.pwp;
+  const int H = p.height, W = p.width, PH = p.pooled_h;
+  const int bins = PH * PWT;
+  const int tiles = (H + p.tr - 1) / p.tr;
+  const int units = p.num_images * p.ncg * tiles;
+  const unsigned tile_base = ptx::smem_addr(tile) + (unsigned)(lane * p.pitch * 4);
+  const int sx0 = warp * p.strip, sx1 = min(W, sx0 + p.strip);
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_unit = atomicAdd(p.unit_counter, 1);
+    __syncthreads();
+    const int u = s_unit;
+    if (u >= units) break;
+    const int cg = u % p.ncg, t = (u / p.ncg) % tiles, n = u / (p.ncg * tiles);
+    const int r0 = t * p.tr, r1 = min(H, r0 + p.tr), c0 = cg * 32;
+    for (int i = threadIdx.x; i < (r1 - r0) * rowf; i += kTileWarps * 32) tile[i] = 0.0f;
+    __syncthreads();
+    if (sx0 < sx1) {
+      const int j0 = __ldg(p.img_start + n), j1 = __ldg(p.img_start + n + 1);
+      // 32 ROIs at a time: lane = ROI for the range tests, then the hits one by one in ascending order
+      for (int jb = j0; jb < j1; jb += 32) {
+        int roi_l = -1;
+        bool hit = false;
+        if (jb + lane < j1) {
+          roi_l = __ldg(p.order + jb + lane);
+          const uint2 rng = __ldg(reinterpret_cast<const uint2*>(p.hdr + roi_l) + 2);    // yr, xr
+          hit = (int)(rng.x >> 16) >= r0 && (int)(rng.x & 0xffffu) < r1 && (int)(rng.y >> 16) >= sx0 &&
+                (int)(rng.y & 0xffffu) < sx1;
+        }
+        unsigned hits = __ballot_sync(0xffffffffu, hit);
+        while (hits) {
+          const int b = __ffs(hits) - 1;
+          hits &= hits - 1;
+          const int roi = __shfl_sync(0xffffffffu, roi_l, b);
+          // bin columns (lane = pw): record range and tap columns; which of them reach into the strip
+          uint2 cr = make_uint2(0u, 0u);
+          if (lane < PWT) cr = __ldg(p.pwr + (size_t)roi * 16 + lane);
+          const bool chit = (cr.x & 0xffffu) < (cr.x >> 16) && (int)(cr.y >> 16) >= sx0 && (int)(cr.y & 0xffffu) < sx1;
+          const unsigned cmask = __ballot_sync(0xffffffffu, chit);
+          if (!cmask) continue;
+          const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(p.hdr + roi));           // roi, batch, grid, count
+          const float count = __uint_as_float(h0.w);
+          const int cnt_i = (int)(h0.z & 0xffffu) * (int)(h0.z >> 16);
+          const bool pow2 = (cnt_i & (cnt_i - 1)) == 0;
+          const float inv = __fdiv_rn(1.0f, count);
+          const ColRec* cols = p.cols + (size_t)roi * p.colcap;
+          const RowRec* rows = p.rows + (size_t)roi * p.rowcap;
+          for (int ph0 = 0; ph0 < PH; ph0 += 32) {
+            // bin rows (lane = ph): which of them reach into the tile
+            uint2 rr0 = make_uint2(0u, 0u);
+            if (ph0 + lane < PH) rr0 = __ldg(p.phr + (size_t)roi * PH + ph0 + lane);
+            const bool rhit = (rr0.x & 0xffffu) < (rr0.x >> 16) && (int)(rr0.y >> 16) >= r0 && (int)(rr0.y & 0xffffu) < r1;
+            unsigned rmask = __ballot_sync(0xffffffffu, rhit);
+            while (rmask) {
+              const int bl = __ffs(rmask) - 1;
+              rmask &= rmask - 1;
+              const int ph = ph0 + bl;
+              const unsigned ox = __shfl_sync(0xffffffffu, rr0.x, bl);
+              const int o0 = (int)(ox & 0xffffu), o1 = (int)(ox >> 16);
+              // the 32 x PW gradients of this bin row, [channel][bin column] -> lane = channel
+              float g[PWT];
+              {
+                const float* src = p.dy + ((size_t)roi * p.channels + c0) * bins + ph * PWT;
+                const int cvalid = min(32, p.c_work - c0);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < PWT; ++k) {
+                  const int f = k * 32 + lane;
+                  const int c = f / PWT, pw = f - c * PWT;
+                  if (c < cvalid) stage[c * p.pwp + pw] = __ldg(src + c * bins + pw);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int pw = 0; pw < PWT; ++pw) {
+                  const float v = stage[lane * p.pwp + pw];
+                  g[pw] = DET ? v : (pow2 ? __fmul_rn(v, inv) : __fdiv_rn(v, count));
+                }
+              }
+#pragma unroll
+              for (int pw = 0; pw < PWT; ++pw) {
+                const unsigned kx = __shfl_sync(0xffffffffu, cr.x, pw);
+                if (!((cmask >> pw) & 1u)) continue;
+                const int k0 = (int)(kx & 0xffffu), k1 = (int)(kx >> 16);
+                const float gp = g[pw];
+                for (int o = o0; o < o1; ++o) {
+                  const RowRec rr = __ldg(rows + o);
+                  const int ylo = (int)(rr.x & 0xffffu), yhi = (int)(rr.x >> 16);
+                  if (yhi < r0 || ylo >= r1) continue;
+                  const float ly = __uint_as_float(rr.y), hy = __fsub_rn(1.0f, ly);
+                  const bool lo_in = ylo >= r0, hi_in = yhi < r1;
+                  const unsigned row_lo = tile_base + (unsigned)((ylo - r0) * rowf * 4);
+                  const unsigned row_hi = tile_base + (unsigned)((yhi - r0) * rowf * 4);
+                  for (int k = k0; k < k1; ++k) {
+                    const ColRec c = __ldg(cols + k);
+                    const int xlo = (int)(c.x & 0xffffu), xhi = (int)(c.x >> 16);
+                    if (xhi < sx0 || xlo >= sx1) continue;
+                    const float lx = __uint_as_float(c.y), hx = __fsub_rn(1.0f, lx);
+                    const bool xl_in = xlo >= sx0, xh_in = xhi < sx1;
+                    const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
+                    if (lo_in && hi_in && xl_in && xh_in && xlo != xhi && ylo != yhi) {
+                      // four different pixels, all ours: the read-modify-writes overlap
+                      taps4<DET>(row_lo + (unsigned)xlo * 4u, row_lo + (unsigned)xhi * 4u, row_hi + (unsigned)xlo * 4u,
+                                 row_hi + (unsigned)xhi * 4u, gp, w1, w2, w3, w4, count, inv, pow2);
+                    } else {
+                      // taps in the reference's order: (lo,lo) (lo,hi) (hi,lo) (hi,hi), ROIAlign.cpp:149-156
+                      if (lo_in && xl_in) tap_add<DET>(row_lo + (unsigned)xlo * 4u, gp, w1, count, inv, pow2);
+                      if (lo_in && xh_in) tap_add<DET>(row_lo + (unsigned)xhi * 4u, gp, w2, count, inv, pow2);
+                      if (hi_in && xl_in) tap_add<DET>(row_hi + (unsigned)xlo * 4u, gp, w3, count, inv, pow2);
+                      if (hi_in && xh_in) tap_add<DET>(row_hi + (unsigned)xhi * 4u, gp, w4, count, inv, pow2);
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- write the tile: every (row, channel) is one coalesced run of W floats ----------------
+    const int cvalid = min(32, p.c_work - c0);
+    for (int rc = warp; rc < (r1 - r0) * cvalid; rc += kTileWarps) {
+      const int rr = rc / cvalid, c = rc - rr * cvalid;
+      const float* srow = tile + (size_t)rr * rowf + c * p.pitch;
+      float* drow = p.dx + (((size_t)n * p.channels + c0 + c) * H + r0 + rr) * W;
+      for (int x = lane; x < W; x += 32) drow[x] = p.accumulate ? __fadd_rn(drow[x], srow[x]) : srow[x];
+    }
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 struct SweepLayout {
   size_t zero_bytes;     // leading part of the workspace that is cleared per call
@@ -700,7 +975,7 @@ cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void*
   const SweepLayout L = sweep_layout(a, plan);
   char* ws = static_cast<char*>(workspace);
   const int c_work = a.c_count > 0 ? a.c_count : a.channels;
-  SweepParams p;
+  SweepParams p = {};
   p.rois = a.rois;
   p.out = out;
   p.num_rois = a.num_rois;
@@ -786,6 +1061,160 @@ cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void*
     case 14: return launch_main<14>(gwt, grid, plan.smem, stream, p);
     case 15: return launch_main<15>(gwt, grid, plan.smem, stream, p);
     default: return launch_main<16>(gwt, grid, plan.smem, stream, p);
+  }
+}
+
+// ---- backward (row tiles) ----------------------------------------------------------------------
+namespace {
+
+struct TileLayout {
+  size_t counter, img_start, order, hdr, cols, rows, phr, pwr, total;
+};
+
+TileLayout tile_layout(const RoiAlignArgs& a, const TilePlan& plan) {
+  TileLayout L;
+  size_t off = 0;
+  L.counter = off;   off = align_up(off + 16, 16);
+  L.img_start = off; off = align_up(off + (size_t)(a.num_images + 2) * 4, 16);
+  L.order = off;     off = align_up(off + (size_t)a.num_rois * 4, 256);
+  L.hdr = off;       off = align_up(off + (size_t)a.num_rois * sizeof(SweepHdr), 256);
+  L.cols = off;      off = align_up(off + (size_t)a.num_rois * plan.colcap * sizeof(ColRec), 256);
+  L.rows = off;      off = align_up(off + (size_t)a.num_rois * plan.rowcap * sizeof(RowRec), 256);
+  L.phr = off;       off = align_up(off + (size_t)a.num_rois * a.pooled_h * sizeof(uint2), 256);
+  L.pwr = off;       off = align_up(off + (size_t)a.num_rois * 16 * sizeof(uint2), 256);
+  L.total = off;
+  return L;
+}
+
+template <int PWT>
+cudaError_t launch_tile(bool det, dim3 grid, size_t smem, cudaStream_t stream, const TileParams& p) {
+  auto go = [&](auto kernel) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    count_launch();
+    return chained_launch(kernel, grid, dim3(kTileWarps * 32), smem, stream, p);
+  };
+  return det ? go(tile_bwd_kernel<PWT, true>) : go(tile_bwd_kernel<PWT, false>);
+}
+
+}  // namespace
+
+bool tile_supported(const RoiAlignArgs& a, int smem_optin, int num_sms, TilePlan* plan) {
+  if (a.num_images <= 0 || a.num_images > 4096 || a.num_rois < 0) return false;
+  if (a.width > 65535 || a.height > kMaxPlaneH || a.pooled_w > kMaxPooledW || a.pooled_h > 16383) return false;
+  if ((long long)a.pooled_h * (a.sampling_ratio > 0 ? a.sampling_ratio : 1024) > 65535) return false;
+  plan->pitch = (a.width + 1) | 1;
+  plan->pwp = a.pooled_w | 1;
+  const size_t fixed = (size_t)kTileWarps * 32 * plan->pwp * 4 + 256;
+  const size_t row_bytes = (size_t)32 * plan->pitch * 4;
+  if ((size_t)smem_optin < fixed + 2 * row_bytes) return false;
+  int tr = (int)(((size_t)smem_optin - fixed) / row_bytes);
+  // enough tiles to keep every SM busy, as tall as that allows (fewer ROI scans, fewer bin rows cut)
+  const int c_work = a.c_count > 0 ? a.c_count : a.channels;
+  const long long per_row_units = (long long)a.num_images * ((c_work + 31) / 32);
+  const long long want_tiles = (2LL * num_sms + per_row_units - 1) / per_row_units;
+  const int balanced = (int)max(2LL, (a.height + want_tiles - 1) / want_tiles);
+  if (tr > balanced) tr = balanced;
+  if (tr > a.height) tr = a.height;
+  if (tr > 32) tr = 32;
+  plan->tr = tr;
+  plan->strip = (a.width + kTileWarps - 1) / kTileWarps;
+  plan->smem = fixed + (size_t)tr * row_bytes;
+  plan->colcap = a.sampling_ratio > 0 ? ((a.pooled_w * a.sampling_ratio + 1) & ~1)
+                                      : ((max(a.pooled_w, 2 * a.width + 3) + 2) & ~1);
+  plan->rowcap = a.sampling_ratio > 0 ? a.pooled_h * a.sampling_ratio : 2 * a.height + 3 + a.pooled_h;
+  return true;
+}
+
+size_t tile_bwd_workspace(const RoiAlignArgs& a, const TilePlan& plan) { return tile_layout(a, plan).total; }
+
+cudaError_t launch_bwd_tile(const RoiAlignArgs& a, const TilePlan& plan, void* workspace, const float* dy,
+                            float* dx, int accumulate, int deterministic, int num_sms, cudaStream_t stream) {
+  const TileLayout L = tile_layout(a, plan);
+  char* ws = static_cast<char*>(workspace);
+  const int c_work = a.c_count > 0 ? a.c_count : a.channels;
+  cudaError_t e = cudaMemsetAsync(ws + L.counter, 0, 16, stream);
+  if (e != cudaSuccess) return e;
+  int* img_start = reinterpret_cast<int*>(ws + L.img_start);
+  int* order = reinterpret_cast<int*>(ws + L.order);
+  e = launch_roi_group(a, img_start, order, stream);
+  if (e != cudaSuccess) return e;
+  if (a.num_rois > 0) {
+    SweepParams sp = {};
+    sp.rois = a.rois;
+    sp.num_rois = a.num_rois;
+    sp.num_images = a.num_images;
+    sp.channels = a.channels;
+    sp.c_work = c_work;
+    sp.ncg = (c_work + 31) / 32;
+    sp.height = a.height;
+    sp.width = a.width;
+    sp.pooled_h = a.pooled_h;
+    sp.pooled_w = a.pooled_w;
+    sp.scale = a.scale;
+    sp.sampling_ratio = a.sampling_ratio;
+    sp.accumulate = 1;
+    sp.segs = 1;
+    sp.span = 2;
+    sp.colcap = plan.colcap;
+    sp.rowcap = plan.rowcap;
+    sp.compact = 1;
+    sp.tables_only = 1;
+    sp.hdr = reinterpret_cast<SweepHdr*>(ws + L.hdr);
+    sp.cols = reinterpret_cast<ColRec*>(ws + L.cols);
+    sp.rows = reinterpret_cast<RowRec*>(ws + L.rows);
+    sp.phr = reinterpret_cast<uint2*>(ws + L.phr);
+    sp.pwr = reinterpret_cast<uint2*>(ws + L.pwr);
+    count_launch();
+    e = chained_launch(sweep_roi_kernel<1>, dim3((a.num_rois + 7) / 8), dim3(256), 0, stream, sp);
+    if (e != cudaSuccess) return e;
+  }
+  TileParams p = {};
+  p.dy = dy;
+  p.dx = dx;
+  p.num_images = a.num_images;
+  p.channels = a.channels;
+  p.c_work = c_work;
+  p.ncg = (c_work + 31) / 32;
+  p.height = a.height;
+  p.width = a.width;
+  p.pooled_h = a.pooled_h;
+  p.pooled_w = a.pooled_w;
+  p.accumulate = accumulate;
+  p.pitch = plan.pitch;
+  p.tr = plan.tr;
+  p.strip = plan.strip;
+  p.pwp = plan.pwp;
+  p.colcap = plan.colcap;
+  p.rowcap = plan.rowcap;
+  p.img_start = img_start;
+  p.order = order;
+  p.hdr = reinterpret_cast<const SweepHdr*>(ws + L.hdr);
+  p.cols = reinterpret_cast<const ColRec*>(ws + L.cols);
+  p.rows = reinterpret_cast<const RowRec*>(ws + L.rows);
+  p.phr = reinterpret_cast<const uint2*>(ws + L.phr);
+  p.pwr = reinterpret_cast<const uint2*>(ws + L.pwr);
+  p.unit_counter = reinterpret_cast<int*>(ws + L.counter);
+  const long long units = (long long)a.num_images * p.ncg * ((a.height + plan.tr - 1) / plan.tr);
+  const dim3 grid((unsigned)(units < num_sms ? units : num_sms));
+  const bool det = deterministic != 0;
+  switch (a.pooled_w) {
+    case 1: return launch_tile<1>(det, grid, plan.smem, stream, p);
+    case 2: return launch_tile<2>(det, grid, plan.smem, stream, p);
+    case 3: return launch_tile<3>(det, grid, plan.smem, stream, p);
+    case 4: return launch_tile<4>(det, grid, plan.smem, stream, p);
+    case 5: return launch_tile<5>(det, grid, plan.smem, stream, p);
+    case 6: return launch_tile<6>(det, grid, plan.smem, stream, p);
+    case 7: return launch_tile<7>(det, grid, plan.smem, stream, p);
+    case 8: return launch_tile<8>(det, grid, plan.smem, stream, p);
+    case 9: return launch_tile<9>(det, grid, plan.smem, stream, p);
+    case 10: return launch_tile<10>(det, grid, plan.smem, stream, p);
+    case 11: return launch_tile<11>(det, grid, plan.smem, stream, p);
+    case 12: return launch_tile<12>(det, grid, plan.smem, stream, p);
+    case 13: return launch_tile<13>(det, grid, plan.smem, stream, p);
+    case 14: return launch_tile<14>(det, grid, plan.smem, stream, p);
+    case 15: return launch_tile<15>(det, grid, plan.smem, stream, p);
+    default: return launch_tile<16>(det, grid, plan.smem, stream, p);
   }
 }
 

@@ -2,7 +2,7 @@
 # sweep kernels: parity first (hard time limits: a ring-protocol bug would hang), then bench lines
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" || exit 1
-timeout -s KILL ${PYTEST_LIMIT:-200} python -m pytest tests -m gpu -v -x --timeout 60 -k "${PYTEST_K:-sweep}" > gpurun_out/sw_pytest.log 2>&1
+timeout -s KILL ${PYTEST_LIMIT:-200} python -m pytest tests -m gpu -v -x --timeout 60 -k "${PYTEST_K:-sweep or deterministic_golden}" > gpurun_out/sw_pytest.log 2>&1
 echo "pytest rc=$?"; tail -${PYTEST_TAIL:-30} gpurun_out/sw_pytest.log
 for spec in ${BENCHES:-C2:sweep C2:auto C4:sweep C3:sweep C5:sweep}; do
   wl=${spec%%:*}; algo=${spec##*:}

@@ -147,8 +147,15 @@ def test_backward_deterministic_golden_bit_exact(direct, name):
     # sampling_ratio 2 takes the resident kernel's canonical-order variant, anything else the
     # whole-plane canonical kernel; both must give the single-thread reference's bits
     from mobulaop_b200 import _native
-    expect = 'resident-canonical' if g['sr'] == 2 and max(g['pooled']) <= 16 else 'plane-canonical'
+    # sampling_ratio 2 takes the resident kernel's canonical-order variant, anything else the
+    # row-tile kernel's; both must give the single-thread reference's bits (as must the old
+    # whole-plane canonical kernel, below)
+    expect = 'resident-canonical' if g['sr'] == 2 and max(g['pooled']) <= 16 else 'tile-canonical'
     assert _native.last_algo(True) == expect
+    tile = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], mode='deterministic',
+                           algo='sweep')
+    assert _native.last_algo(True) == 'tile-canonical'
+    assert_bit_exact(tile, g['dx'])
     plane = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], mode='deterministic',
                             algo='plane')
     assert _native.last_algo(True) == 'plane-canonical'
@@ -262,7 +269,7 @@ SWEEP_SHAPES = [
 
 
 @pytest.mark.parametrize('shape', SWEEP_SHAPES, ids=lambda s: 'x'.join(str(v) for v in s[:5]) + '-p%dx%d-sr%d' % (s[5] + (s[7],)))
-def test_sweep_forward_against_the_oracle(direct, oracle, shape):
+def test_sweep_family_against_the_oracle(direct, oracle, shape):
     from mobulaop_b200 import _native
     N, C, H, W, k, pooled, scale, sr = shape
     wl = WL.Workload('sweep', N, C, H, W, k, pooled, scale, sr, min_box=2.0, max_box=4.0 * max(H, W) / scale,
@@ -284,6 +291,22 @@ def test_sweep_forward_against_the_oracle(direct, oracle, shape):
     expect = base.copy()
     expect[np.arange(len(rois)) != 1] += y_ref
     assert_bit_exact(acc, expect)
+    # the backward of the family: dX row tiles, strip-owner warps
+    dy = rng.standard_normal(y.shape).astype(np.float32)
+    dyg = np.ascontiguousarray(np.delete(dy, 1, axis=0))
+    good = np.delete(rois, 1, axis=0)
+    dx_ref = oracle.backward(dyg, good, data.shape, scale, sr)
+    dx_abs = oracle.backward(np.abs(dyg), good, data.shape, scale, sr)
+    dx = direct.backward(dy, rois, data.shape, scale, sr, algo='sweep')
+    assert _native.last_algo(True) == 'tile'
+    assert_scatter_close(dx, dx_ref, dx_abs, rtol=1e-5)
+    dxd = direct.backward(dy, rois, data.shape, scale, sr, algo='sweep', mode='deterministic')
+    assert _native.last_algo(True) == 'tile-canonical'
+    assert_bit_exact(dxd, dx_ref)
+    dbase = rng.standard_normal(data.shape).astype(np.float32)
+    dacc = direct.backward(dy, rois, data.shape, scale, sr, algo='sweep', mode='deterministic',
+                           accumulate_into=dbase.copy())
+    assert_bit_exact(dacc, (dbase + dx_ref).astype(np.float32))
 
 
 def test_sweep_rejects_what_it_cannot_do(direct):

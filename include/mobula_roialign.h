@@ -53,6 +53,10 @@ extern "C" {
 #define MOBULA_ROIALIGN_HOST_BUFFERS 2u /* all pointers are HOST memory: the library stages
                                            them to the device, runs, copies the result back
                                            and synchronises before returning               */
+#define MOBULA_ROIALIGN_ALIGNED 4u      /* half-pixel box coordinates, boxes not forced to one pixel:
+                                           torchvision.ops.roi_align(aligned=True) / detectron2
+                                           ROIAlignV2 instead of the reference operator's convention.
+                                           Served by the sweep / row-tile kernels (pooled_w <= 16)   */
 /* testing aid: build no ROI tables, every kernel decodes ROIs on the fly (slow path) */
 #define MOBULA_ROIALIGN_DEBUG_NO_TABLES 0x10000u
 /* algorithm selection, bits 8..11 (0 = automatic) */

@@ -19,6 +19,7 @@ BWD_DETERMINISTIC = 1
 
 FLAG_ACCUMULATE = 1
 FLAG_HOST_BUFFERS = 2
+FLAG_ALIGNED = 4
 ALGO_SHIFT = 8
 ALGO_AUTO, ALGO_GATHER, ALGO_PLANE, ALGO_RESIDENT, ALGO_SWEEP = 0, 1, 2, 3, 4
 ALGOS = {'auto': ALGO_AUTO, 'gather': ALGO_GATHER, 'plane': ALGO_PLANE, 'resident': ALGO_RESIDENT,
@@ -109,8 +110,10 @@ def check(status):
 FLAG_DEBUG_NO_TABLES = 0x10000
 
 
-def make_flags(accumulate=False, host=False, algo='auto', no_tables=False):
+def make_flags(accumulate=False, host=False, algo='auto', no_tables=False, aligned=False):
     flags = (FLAG_ACCUMULATE if accumulate else 0) | (FLAG_HOST_BUFFERS if host else 0)
+    if aligned:
+        flags |= FLAG_ALIGNED
     if no_tables:
         flags |= FLAG_DEBUG_NO_TABLES
     return flags | (ALGOS[algo] << ALGO_SHIFT)

@@ -248,12 +248,12 @@ static int forward_device(DeviceState& st, int device, cudaStream_t stream, cons
     // sweep kernels: on request, and automatically wherever the resident kernels do not apply
     // (adaptive grids, planes beyond one SM's shared memory) instead of the global-memory gather
     SweepPlan splan;
-    const bool want = algo == MOBULA_ROIALIGN_ALGO_SWEEP ||
+    const bool want = algo == MOBULA_ROIALIGN_ALGO_SWEEP || a.aligned ||
                       (algo == MOBULA_ROIALIGN_ALGO_AUTO && (prefer_sweep() || !resident_ok));
     const bool sweep_ok = want && !no_tables && sweep_supported(a, data, st.smem_optin, st.num_sms, &splan);
-    if (algo == MOBULA_ROIALIGN_ALGO_SWEEP && !sweep_ok)
+    if ((algo == MOBULA_ROIALIGN_ALGO_SWEEP || a.aligned) && !sweep_ok)
       return fail(MOBULA_ERR_UNSUPPORTED,
-                  "sweep algorithm needs num_images in [1, 4096], pooled_w <= 16 and at least four "
+                  "sweep algorithm (and MOBULA_ROIALIGN_ALIGNED) needs num_images in [1, 4096], pooled_w <= 16 and at least four "
                   "%d-pixel rows of 32 channels within %d bytes of shared memory", a.width, st.smem_optin);
     if (sweep_ok) {
       t_algo[0] = "sweep";
@@ -306,7 +306,7 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward mode %d", mode);
   if (algo > MOBULA_ROIALIGN_ALGO_SWEEP)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward algorithm %u", algo);
-  const bool want_tile = algo == MOBULA_ROIALIGN_ALGO_SWEEP;
+  const bool want_tile = algo == MOBULA_ROIALIGN_ALGO_SWEEP || a.aligned;
   if (!accumulate && a.num_images < 0)
     return fail(MOBULA_ERR_INVALID_ARGUMENT,
                 "backward without MOBULA_ROIALIGN_ACCUMULATE needs num_images >= 0");
@@ -391,6 +391,7 @@ static RoiAlignArgs make_args(const float* rois, int num_rois, int num_images, i
   a.pooled_w = pooled_w;
   a.scale = scale;
   a.sampling_ratio = sampling_ratio;
+  a.aligned = 0;
   return a;
 }
 
@@ -453,7 +454,7 @@ static int host_chunk(int channels, size_t tensor_bytes, bool backward) {
 static bool resident_forward_applies(DeviceState& st, const RoiAlignArgs& a, const void* data, unsigned flags) {
   const unsigned algo = algo_of(flags);
   ResidentPlan plan;
-  return !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) &&
+  return !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && !a.aligned &&
          (algo == MOBULA_ROIALIGN_ALGO_AUTO || algo == MOBULA_ROIALIGN_ALGO_RESIDENT) &&
          resident_supported(a, data, st.smem_optin, &plan);
 }
@@ -463,7 +464,7 @@ static bool resident_backward_applies(DeviceState& st, const RoiAlignArgs& a, co
   const unsigned algo = algo_of(flags);
   ResidentPlan plan;
   (void)mode;
-  return !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) &&
+  return !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && !a.aligned &&
          (algo == MOBULA_ROIALIGN_ALGO_AUTO || algo == MOBULA_ROIALIGN_ALGO_RESIDENT) &&
          resident_supported(a, dx, st.smem_optin, &plan) && plan.bwd_ok;
 }
@@ -490,8 +491,9 @@ MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, cons
   cudaStream_t stream = (cudaStream_t)stream_;
 
   if (!(flags & MOBULA_ROIALIGN_HOST_BUFFERS)) {
-    const RoiAlignArgs a = make_args(bottom_rois, num_rois, num_images, channels, height, width,
-                                     pooled_height, pooled_width, spatial_scale, sampling_ratio);
+    RoiAlignArgs a = make_args(bottom_rois, num_rois, num_images, channels, height, width,
+                               pooled_height, pooled_width, spatial_scale, sampling_ratio);
+    a.aligned = (flags & MOBULA_ROIALIGN_ALIGNED) ? 1 : 0;
     return forward_device(st, device, stream, bottom_data, bottom_rois, top_data, a, flags);
   }
 
@@ -508,6 +510,7 @@ MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, cons
   float* d_out = (float*)st.stage[2].ptr;
   RoiAlignArgs a = make_args(d_rois, num_rois, n_img, channels, height, width, pooled_height,
                              pooled_width, spatial_scale, sampling_ratio);
+  a.aligned = (flags & MOBULA_ROIALIGN_ALIGNED) ? 1 : 0;
   const int cc = resident_forward_applies(st, a, d_data, flags) ? host_chunk(channels, data_bytes, false) : 0;
   if (cc > 0) {
     if ((rc = pipeline_setup(st))) return rc;
@@ -578,8 +581,9 @@ MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream_, con
   cudaStream_t stream = (cudaStream_t)stream_;
 
   if (!(flags & MOBULA_ROIALIGN_HOST_BUFFERS)) {
-    const RoiAlignArgs a = make_args(bottom_rois, num_rois, num_images, channels, height, width,
-                                     pooled_height, pooled_width, spatial_scale, sampling_ratio);
+    RoiAlignArgs a = make_args(bottom_rois, num_rois, num_images, channels, height, width,
+                               pooled_height, pooled_width, spatial_scale, sampling_ratio);
+    a.aligned = (flags & MOBULA_ROIALIGN_ALIGNED) ? 1 : 0;
     return backward_device(st, device, stream, top_diff, bottom_rois, bottom_diff, a, mode, flags);
   }
 
@@ -595,6 +599,7 @@ MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream_, con
   float* d_dx = (float*)st.stage[2].ptr;
   RoiAlignArgs a = make_args(d_rois, num_rois, n_img, channels, height, width, pooled_height,
                              pooled_width, spatial_scale, sampling_ratio);
+  a.aligned = (flags & MOBULA_ROIALIGN_ALIGNED) ? 1 : 0;
   const int cc = resident_backward_applies(st, a, d_dx, mode, flags) ? host_chunk(channels, dx_bytes, true) : 0;
   if (cc > 0) {
     if ((rc = pipeline_setup(st))) return rc;

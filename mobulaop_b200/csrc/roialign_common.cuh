@@ -24,18 +24,32 @@ struct RoiGeom {
   float count;          // ROIAlign.cpp:54
 };
 
+// aligned = the half-pixel variant of torchvision / detectron2 (roi_align(aligned=True)): box
+// coordinates are shifted by -0.5 after scaling and the box is NOT forced to be at least one
+// pixel wide (torchvision/csrc/ops/cpu/roi_align_kernel.cpp); false = the reference operator.
 __device__ __forceinline__ RoiGeom roi_decode(const float* __restrict__ roi, float scale,
-                                              int pooled_h, int pooled_w, int sampling_ratio) {
+                                              int pooled_h, int pooled_w, int sampling_ratio,
+                                              bool aligned = false) {
   RoiGeom g;
   const float r0 = __ldg(roi + 0), r1 = __ldg(roi + 1), r2 = __ldg(roi + 2);
   const float r3 = __ldg(roi + 3), r4 = __ldg(roi + 4);
   g.batch = __float2int_rz(r0);
   g.start_w = __fmul_rn(r1, scale);
   g.start_h = __fmul_rn(r2, scale);
-  const float end_w = __fmul_rn(r3, scale);
-  const float end_h = __fmul_rn(r4, scale);
-  const float roi_w = fmaxf(__fsub_rn(end_w, g.start_w), 1.0f);
-  const float roi_h = fmaxf(__fsub_rn(end_h, g.start_h), 1.0f);
+  float end_w = __fmul_rn(r3, scale);
+  float end_h = __fmul_rn(r4, scale);
+  float roi_w, roi_h;
+  if (aligned) {
+    g.start_w = __fsub_rn(g.start_w, 0.5f);
+    g.start_h = __fsub_rn(g.start_h, 0.5f);
+    end_w = __fsub_rn(end_w, 0.5f);
+    end_h = __fsub_rn(end_h, 0.5f);
+    roi_w = __fsub_rn(end_w, g.start_w);
+    roi_h = __fsub_rn(end_h, g.start_h);
+  } else {
+    roi_w = fmaxf(__fsub_rn(end_w, g.start_w), 1.0f);
+    roi_h = fmaxf(__fsub_rn(end_h, g.start_h), 1.0f);
+  }
   g.bin_h = __fdiv_rn(roi_h, (float)pooled_h);
   g.bin_w = __fdiv_rn(roi_w, (float)pooled_w);
   float gh = (float)sampling_ratio, gw = (float)sampling_ratio;
@@ -49,7 +63,10 @@ __device__ __forceinline__ RoiGeom roi_decode(const float* __restrict__ roi, flo
   // ROIAlign.cpp:47-51).  Such a ROI is moved outside the plane: every sample is rejected
   // (bilinear.h:15-18), its output rows are zero and it scatters nothing.
   const float probe = (g.start_w + g.start_h) + (g.bin_w + g.bin_h);
-  if (!(gh <= kMaxAdaptiveGrid && gw <= kMaxAdaptiveGrid) || !(fabsf(probe) <= 3.0e38f)) {
+  // (aligned boxes may be empty: an adaptive grid of zero samples pools to 0 / max(count, 1) = 0)
+  // (an aligned box with x2 < x1 or y2 < y1 would be sampled backwards by torchvision; here it pools to 0)
+  if (!(gh <= kMaxAdaptiveGrid && gw <= kMaxAdaptiveGrid) || !(fabsf(probe) <= 3.0e38f) || gh < 1.0f ||
+      gw < 1.0f || roi_w < 0.0f || roi_h < 0.0f) {
     g.start_w = g.start_h = -1.0e30f;
     g.bin_w = g.bin_h = 0.0f;
     gh = gw = 1.0f;

@@ -15,6 +15,7 @@ struct RoiAlignArgs {
   int pooled_h, pooled_w;
   float scale;
   int sampling_ratio;
+  int aligned;         // half-pixel box coordinates (torchvision aligned=True); sweep / tile kernels only
 };
 
 void count_launch();

@@ -96,6 +96,7 @@ struct SweepParams {
   int height, width, pooled_h, pooled_w;
   float scale;
   int sampling_ratio;
+  int aligned;
   int accumulate;
   const float* data;
   // shared-memory geometry
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= p.num_rois) return;
-  const RoiGeom g = roi_decode(p.rois + (size_t)r * 5, p.scale, p.pooled_h, p.pooled_w, p.sampling_ratio);
+  const RoiGeom g = roi_decode(p.rois + (size_t)r * 5, p.scale, p.pooled_h, p.pooled_w, p.sampling_ratio, p.aligned != 0);
   const int n = (g.batch >= 0 && g.batch < p.num_images) ? g.batch : -1;
   const int PH = p.pooled_h, PW = p.pooled_w, H = p.height, W = p.width;
   if (PASS == 1) {
@@ -989,6 +990,7 @@ cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void*
   p.pooled_w = a.pooled_w;
   p.scale = a.scale;
   p.sampling_ratio = a.sampling_ratio;
+  p.aligned = a.aligned;
   p.accumulate = accumulate;
   p.data = data;
   p.pitch = plan.pitch;
@@ -1153,6 +1155,7 @@ cudaError_t launch_bwd_tile(const RoiAlignArgs& a, const TilePlan& plan, void* w
     sp.pooled_w = a.pooled_w;
     sp.scale = a.scale;
     sp.sampling_ratio = a.sampling_ratio;
+    sp.aligned = a.aligned;
     sp.accumulate = 1;
     sp.segs = 1;
     sp.span = 2;

@@ -15,7 +15,8 @@ returns when the result is in host memory.
 
 Extra keyword-only arguments (absent from the reference): `mode` ('atomic' |
 'deterministic', backward only), `accumulate` (default True for backward = the
-reference semantics "adds into a caller-zeroed buffer", False for forward), `algo`.
+reference semantics "adds into a caller-zeroed buffer", False for forward), `algo`,
+`aligned` (half-pixel box coordinates = torchvision.ops.roi_align(aligned=True)).
 """
 import ctypes
 
@@ -89,6 +90,7 @@ class MobulaFunc(object):
         mode = kwargs.pop('mode', None)
         accumulate = kwargs.pop('accumulate', None)
         algo = kwargs.pop('algo', None)
+        aligned = bool(kwargs.pop('aligned', False))
         args = self._collect(args, kwargs)
         if kwargs:
             raise TypeError('%s: unexpected arguments %s' % (self.name, sorted(kwargs)))
@@ -133,7 +135,7 @@ class MobulaFunc(object):
                     raise ValueError('%s: host and device tensors mixed in one call' % self.name)
         launcher = _launch_forward if self.name == 'roi_align_forward' else _launch_backward
         launcher(values, tensors, -1 if dev_id is None else dev_id, stream, host, mode, accumulate,
-                 algo or config.ROIALIGN_ALGO)
+                 algo or config.ROIALIGN_ALGO, aligned)
         for t in tensors.values():
             t.finish()
         return None
@@ -153,7 +155,7 @@ def _vp(p):
     return p if isinstance(p, ctypes.c_void_p) else ctypes.c_void_p(p)
 
 
-def _launch_forward(v, t, dev_id, stream, host, mode, accumulate, algo):
+def _launch_forward(v, t, dev_id, stream, host, mode, accumulate, algo, aligned=False):
     if mode is not None:
         raise TypeError('roi_align_forward has no `mode`')
     lib = _native.load()
@@ -161,14 +163,14 @@ def _launch_forward(v, t, dev_id, stream, host, mode, accumulate, algo):
     num_rois = _rows(v)
     shape = data.view.shape
     num_images = shape[0] if len(shape) == 4 else -1
-    flags = _native.make_flags(accumulate=bool(accumulate), host=host, algo=algo)
+    flags = _native.make_flags(accumulate=bool(accumulate), host=host, algo=algo, aligned=aligned)
     _native.check(lib.mobula_roialign_forward_f32(
         dev_id, _vp(stream), _vp(data.resolve(False)), _vp(rois.resolve(False)),
         _vp(out.resolve(True)), num_rois, num_images, v['channels'], v['height'], v['width'],
         v['pooled_height'], v['pooled_width'], v['spatial_scale'], v['sampling_ratio'], flags))
 
 
-def _launch_backward(v, t, dev_id, stream, host, mode, accumulate, algo):
+def _launch_backward(v, t, dev_id, stream, host, mode, accumulate, algo, aligned=False):
     lib = _native.load()
     dy, rois, dx = t['top_diff'], t['bottom_rois'], t['bottom_diff']
     if mode is None:
@@ -180,7 +182,7 @@ def _launch_backward(v, t, dev_id, stream, host, mode, accumulate, algo):
     num_rois = _rows(v)
     shape = dx.view.shape
     num_images = shape[0] if len(shape) == 4 else -1
-    flags = _native.make_flags(accumulate=bool(accumulate), host=host, algo=algo)
+    flags = _native.make_flags(accumulate=bool(accumulate), host=host, algo=algo, aligned=aligned)
     _native.check(lib.mobula_roialign_backward_f32(
         dev_id, _vp(stream), _vp(dy.resolve(False)), _vp(rois.resolve(False)),
         _vp(dx.resolve(True)), num_rois, num_images, v['channels'], v['height'], v['width'],

@@ -8,7 +8,8 @@ coordinates, output [R, C, PH, PW].  Write requests follow the reference: 'null'
 'add' accumulates, anything else overwrites.  The gradient with respect to `rois` is zero.
 
 Beyond the reference: `deterministic` (None = follow mobula.config.ROIALIGN_DETERMINISTIC)
-selects the bit-reproducible backward; the dX zero-fill of the reference
+selects the bit-reproducible backward; `aligned=True` uses half-pixel box coordinates (the
+convention of torchvision.ops.roi_align(aligned=True) and detectron2's ROIAlignV2); the dX zero-fill of the reference
 (ROIAlign.py:33-34, a separate full-tensor pass) is done inside the native call.
 """
 import mobulaop_b200 as mobula
@@ -17,7 +18,7 @@ from mobulaop_b200.const import req
 
 @mobula.op.register
 class ROIAlign:
-    def __init__(self, pooled_size, spatial_scale, sampling_ratio, deterministic=None):
+    def __init__(self, pooled_size, spatial_scale, sampling_ratio, deterministic=None, aligned=False):
         if isinstance(pooled_size, int):
             pooled_size = (pooled_size, pooled_size)
         assert len(pooled_size) == 2, 'pooled_size is (pooled_height, pooled_width)'
@@ -25,6 +26,7 @@ class ROIAlign:
         self.spatial_scale = float(spatial_scale)
         self.sampling_ratio = int(sampling_ratio)
         self.deterministic = deterministic
+        self.aligned = bool(aligned)
 
     @staticmethod
     def _numel(t):
@@ -40,7 +42,7 @@ class ROIAlign:
         mobula.func.roi_align_forward(
             self._numel(out), data, self.spatial_scale, data.shape[1], data.shape[2],
             data.shape[3], self.pooled_size[0], self.pooled_size[1], self.sampling_ratio, rois, out,
-            accumulate=self.req[0] == req.add)
+            accumulate=self.req[0] == req.add, aligned=self.aligned)
 
     def backward(self, dy):
         if self.req[0] != req.null:
@@ -51,7 +53,7 @@ class ROIAlign:
             mobula.func.roi_align_backward(
                 self._numel(dy), dy, self.spatial_scale, data.shape[1], data.shape[2],
                 data.shape[3], self.pooled_size[0], self.pooled_size[1], self.sampling_ratio,
-                self.dX[0], rois, accumulate=self.req[0] == req.add, mode=mode)
+                self.dX[0], rois, accumulate=self.req[0] == req.add, mode=mode, aligned=self.aligned)
         if len(self.req) > 1 and self.req[1] not in (req.null, req.add):
             self.dX[1][:] = 0
 

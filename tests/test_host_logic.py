@@ -279,3 +279,29 @@ def test_pinned_pool_is_bounded():
     assert pinned._pool_take(100) == 0xC0                        # most recently released first
     assert pinned._pool_take(100) == 0xB0
     assert pinned._pool_take(100) is None and pinned.pooled_bytes() == 0
+
+
+def test_fpn_level_assignment_matches_the_paper_and_torchvision():
+    """k = floor(k0 + log2(sqrt(wh) / 224)), clamped: 224^2 boxes map to level 4, 112^2 to 3,
+    448^2 to 5, anything smaller than 112 to 2; same answers as torchvision's LevelMapper."""
+    import torch
+    from mobulaop_b200 import fpn
+    sizes = np.array([20, 111.9, 112, 223.9, 224, 447.9, 448, 2000], np.float32)
+    rois = np.stack([np.zeros_like(sizes), np.zeros_like(sizes), np.zeros_like(sizes), sizes, sizes], 1)
+    want = [2, 2, 3, 3, 4, 4, 5, 5]
+    assert fpn.assign_levels(rois, 2, 5).tolist() == want
+    assert fpn.assign_levels(torch.from_numpy(rois), 2, 5).tolist() == want
+    try:
+        from torchvision.ops.poolers import LevelMapper
+    except Exception:
+        LevelMapper = None
+    if LevelMapper is not None:
+        rng = np.random.default_rng(0)
+        xy = rng.uniform(0, 600, (500, 2)).astype(np.float32)
+        wh = np.exp(rng.uniform(np.log(4), np.log(900), (500, 2))).astype(np.float32)
+        boxes = np.concatenate([xy, xy + wh], 1)
+        tv = LevelMapper(2, 5)([torch.from_numpy(boxes)]) + 2
+        mine = fpn.assign_levels(np.concatenate([np.zeros((500, 1), np.float32), boxes], 1), 2, 5)
+        assert (tv.numpy() == mine).mean() > 0.995          # ties at exact powers of two aside
+    parts = fpn.split_by_level(np.array([2, 5, 3, 2, 5]), 2, 5)
+    assert [p.tolist() for p in parts] == [[0, 3], [2], [], [1, 4]]

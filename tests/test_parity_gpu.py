@@ -805,3 +805,52 @@ def test_graph_replay_survives_workspace_growth(api, torch, oracle):
     torch.cuda.synchronize(dev)
     assert_bit_exact(y.cpu().numpy(), oracle.forward(data, rois_h, wl.pooled, wl.scale, wl.sampling_ratio))
     assert_bit_exact(by.cpu().numpy(), oracle.forward(bdata, brois, big.pooled, big.scale, big.sampling_ratio))
+
+
+# ---- aligned=True (half-pixel) variant: torchvision on the CPU is the stated oracle for it ----------
+@pytest.mark.parametrize('sr', [2, 0])
+def test_aligned_variant_matches_torchvision(api, torch, sr):
+    tv = pytest.importorskip('torchvision')
+    from torchvision.ops import roi_align as tv_roi_align
+    wl = WL.Workload('aligned', 2, 37, 50, 68, 60, (7, 7), 0.25, sr, min_box=2.0, max_box=400.0)
+    data, rois, dy = WL.make_inputs(wl, seed=41)
+    rois[3, 3] = rois[3, 1] + 0.3                      # narrower than a pixel: NOT widened when aligned
+    x_cpu = torch.from_numpy(data).requires_grad_(True)
+    y_ref = tv_roi_align(x_cpu, torch.from_numpy(rois), wl.pooled, wl.scale, sr, aligned=True)
+    y_ref.backward(torch.from_numpy(dy))
+    dev = torch.device('cuda', 0)
+    x = torch.from_numpy(data).to(dev).requires_grad_(True)
+    y = api.op.ROIAlign(x, torch.from_numpy(rois).to(dev), pooled_size=wl.pooled, spatial_scale=wl.scale,
+                        sampling_ratio=sr, aligned=True, deterministic=True)
+    y.backward(torch.from_numpy(dy).to(dev))
+    from mobulaop_b200 import _native
+    assert _native.last_algo(False) == 'sweep' and _native.last_algo(True) == 'tile-canonical'
+    # same operations in the same order as torchvision's CPU kernel (no FMA in either): bit for bit
+    assert_within_ulp_or_rel(y.detach().cpu().numpy(), y_ref.detach().numpy(), ulp=2, rtol=1e-6)
+    assert_bit_exact(y.detach().cpu().numpy(), y_ref.detach().numpy())
+    np.testing.assert_allclose(x.grad.cpu().numpy(), x_cpu.grad.numpy(), rtol=1e-5, atol=1e-5)
+    # and it differs from the reference convention (aligned=False), as it must
+    y0 = api.op.ROIAlign(x, torch.from_numpy(rois).to(dev), pooled_size=wl.pooled, spatial_scale=wl.scale,
+                         sampling_ratio=sr)
+    assert not np.array_equal(y0.detach().cpu().numpy(), y.detach().cpu().numpy())
+
+
+def test_fpn_pooler_rows_equal_single_level_calls(api, torch, oracle):
+    from mobulaop_b200 import fpn
+    rng = np.random.default_rng(12)
+    N, C = 2, 5
+    shapes = [(64, 88), (32, 44), (16, 22), (8, 11)]
+    scales = [0.25, 0.125, 0.0625, 0.03125]
+    feats = [rng.standard_normal((N, C) + s).astype(np.float32) for s in shapes]
+    xy = rng.uniform(0, 250, (90, 2)).astype(np.float32)
+    wh = np.exp(rng.uniform(np.log(8), np.log(600), (90, 2))).astype(np.float32)
+    rois = np.concatenate([rng.integers(0, N, (90, 1)).astype(np.float32), xy, xy + wh], 1).astype(np.float32)
+    dev = torch.device('cuda', 0)
+    y = fpn.roi_align_fpn([torch.from_numpy(f).to(dev) for f in feats], torch.from_numpy(rois).to(dev), 7, scales)
+    levels = fpn.assign_levels(rois, 2, 5)
+    assert len(set(levels.tolist())) >= 3
+    y = y.cpu().numpy()
+    for k, (f, s) in enumerate(zip(feats, scales)):
+        idx = np.nonzero(levels == 2 + k)[0]
+        if len(idx):
+            assert_bit_exact(y[idx], oracle.forward(f, np.ascontiguousarray(rois[idx]), (7, 7), s, 2))

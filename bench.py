@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument('--no-secondary', action='store_true')
     ap.add_argument('--e2e-torch-steps', type=int, default=200)
     ap.add_argument('--mode', default='atomic', choices=['atomic', 'deterministic'])
-    ap.add_argument('--algo', default='auto', choices=['auto', 'gather', 'plane', 'resident', 'sweep'])
+    ap.add_argument('--algo', default='auto', choices=['auto', 'gather', 'plane', 'resident', 'sweep', 'pull'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=5)

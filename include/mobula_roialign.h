@@ -75,6 +75,12 @@ extern "C" {
                                           in shared memory, bank-conflict-free taps, any
                                           sampling grid; needs pooled width <= 16 and a known
                                           num_images                                        */
+#define MOBULA_ROIALIGN_ALGO_PULL 5u   /* backward only, fixed sampling ratio: per-pixel lists of
+                                          (roi, bin, weight) contributions built once per call, one
+                                          warp per pixel sums them over 32..128 channels per pass
+                                          (lane = channel): no atomics, every dX element written
+                                          once; merged-tap and bit-exact deterministic variants.
+                                          As a forward algorithm it means AUTO                  */
 
 /* ------------------------------------------------------------------------- *
  * 1. Drop-in symbols (reference ABI)                                         *

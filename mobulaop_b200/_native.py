@@ -21,9 +21,9 @@ FLAG_ACCUMULATE = 1
 FLAG_HOST_BUFFERS = 2
 FLAG_ALIGNED = 4
 ALGO_SHIFT = 8
-ALGO_AUTO, ALGO_GATHER, ALGO_PLANE, ALGO_RESIDENT, ALGO_SWEEP = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_GATHER, ALGO_PLANE, ALGO_RESIDENT, ALGO_SWEEP, ALGO_PULL = 0, 1, 2, 3, 4, 5
 ALGOS = {'auto': ALGO_AUTO, 'gather': ALGO_GATHER, 'plane': ALGO_PLANE, 'resident': ALGO_RESIDENT,
-         'sweep': ALGO_SWEEP}
+         'sweep': ALGO_SWEEP, 'pull': ALGO_PULL}
 
 # every symbol include/mobula_roialign.h declares
 EXPORTED_SYMBOLS = (

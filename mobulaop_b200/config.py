@@ -10,7 +10,7 @@ _LIVE = dict(
     # backward algorithm: False = fastest (rounding order not reproducible),
     # True = bit-exact canonical order (== single-thread reference)
     ROIALIGN_DETERMINISTIC=False,
-    # kernel family: 'auto' | 'gather' | 'plane' | 'resident' | 'sweep'
+    # kernel family: 'auto' | 'gather' | 'plane' | 'resident' | 'sweep' | 'pull'
     ROIALIGN_ALGO='auto',
     # the reference dispatches on this (func.py:143); only 'cuda' exists here
     GPU_BACKEND='cuda',
@@ -49,7 +49,7 @@ class Config(object):
                             'target %s vs value %s.' % (name, want, got))
         if name == 'GPU_BACKEND' and value != 'cuda':
             raise ValueError("only the 'cuda' (sm_100a) backend exists in this build")
-        if name == 'ROIALIGN_ALGO' and value not in ('auto', 'gather', 'plane', 'resident', 'sweep'):
+        if name == 'ROIALIGN_ALGO' and value not in ('auto', 'gather', 'plane', 'resident', 'sweep', 'pull'):
             raise ValueError('unknown ROIAlign algorithm %r' % (value,))
         values[name] = value
 

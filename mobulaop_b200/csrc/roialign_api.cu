@@ -158,6 +158,14 @@ static bool prefer_sweep() {
   return v;
 }
 
+// MOBULA_ROIALIGN_PREFER_PULL=0 keeps the automatic choice of the backward on the resident kernels
+// The pull kernels get their parallelism from the pixels (one warp per eight pixels and 128 channels): small
+// planes with many channels (the reference benchmark's 14 x 14 x 1024) stay on the resident kernels.
+static bool prefer_pull(const RoiAlignArgs& a) {
+  static const bool v = [] { const char* e = getenv("MOBULA_ROIALIGN_PREFER_PULL"); return e ? atoi(e) != 0 : true; }();
+  return v && (long long)a.num_images * a.height * a.width >= 32768;
+}
+
 static unsigned algo_of(unsigned flags) {
   return (flags & MOBULA_ROIALIGN_ALGO_MASK) >> MOBULA_ROIALIGN_ALGO_SHIFT;
 }
@@ -238,9 +246,10 @@ static int forward_device(DeviceState& st, int device, cudaStream_t stream, cons
   (void)device;
   (void)rois;
   const int accumulate = (flags & MOBULA_ROIALIGN_ACCUMULATE) ? 1 : 0;
-  const unsigned algo = algo_of(flags);
-  if (algo > MOBULA_ROIALIGN_ALGO_SWEEP)
+  unsigned algo = algo_of(flags);
+  if (algo > MOBULA_ROIALIGN_ALGO_PULL)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown forward algorithm %u", algo);
+  if (algo == MOBULA_ROIALIGN_ALGO_PULL) algo = MOBULA_ROIALIGN_ALGO_AUTO;     // a backward formulation
   const bool no_tables = (flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) != 0;
   ResidentPlan rplan;
   const bool resident_ok = !no_tables && resident_supported(a, data, st.smem_optin, &rplan);
@@ -304,7 +313,7 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
   unsigned algo = algo_of(flags);
   if (mode != MOBULA_ROIALIGN_BWD_ATOMIC && mode != MOBULA_ROIALIGN_BWD_DETERMINISTIC)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward mode %d", mode);
-  if (algo > MOBULA_ROIALIGN_ALGO_SWEEP)
+  if (algo > MOBULA_ROIALIGN_ALGO_PULL)
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown backward algorithm %u", algo);
   const bool want_tile = algo == MOBULA_ROIALIGN_ALGO_SWEEP || a.aligned;
   if (!accumulate && a.num_images < 0)
@@ -321,6 +330,22 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
     CUDA_TRY(launch_bwd_tile(a, tplan, ws, dy, dx, accumulate, deterministic, st.num_sms, stream));
     return release_tables(st, stream);
   };
+  {
+    // pull kernels (per-pixel contribution lists, lane = channel): fixed sampling ratios
+    const bool pull_ok = !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && a.num_images >= 1 && pull_supported(a);
+    if (algo == MOBULA_ROIALIGN_ALGO_PULL && !pull_ok)
+      return fail(MOBULA_ERR_UNSUPPORTED,
+                  "pull backward needs num_images >= 1, a fixed sampling_ratio with at most 64 samples per "
+                  "ROI axis, pooled_h * pooled_w <= 1600 and a plane within 4095 x 4095");
+    if (pull_ok && (algo == MOBULA_ROIALIGN_ALGO_PULL || (algo == MOBULA_ROIALIGN_ALGO_AUTO && prefer_pull(a)))) {
+      t_algo[1] = deterministic ? "pull-canonical" : "pull";
+      void* ws = nullptr;
+      int rc = prepare_workspace(st, pull_bwd_workspace(a), stream, &ws);
+      if (rc) return rc;
+      CUDA_TRY(launch_bwd_pull(a, ws, dy, dx, accumulate, deterministic, st.num_sms, stream));
+      return release_tables(st, stream);
+    }
+  }
   TilePlan tplan;
   const bool tile_ok = !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && a.num_images >= 0 &&
                        tile_supported(a, st.smem_optin, st.num_sms, &tplan);
@@ -464,6 +489,10 @@ static bool resident_backward_applies(DeviceState& st, const RoiAlignArgs& a, co
   const unsigned algo = algo_of(flags);
   ResidentPlan plan;
   (void)mode;
+  // (the pull kernels take a channel range too)
+  if (!(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && a.num_images >= 1 && pull_supported(a) &&
+      (algo == MOBULA_ROIALIGN_ALGO_PULL || (algo == MOBULA_ROIALIGN_ALGO_AUTO && prefer_pull(a))))
+    return true;
   return !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && !a.aligned &&
          (algo == MOBULA_ROIALIGN_ALGO_AUTO || algo == MOBULA_ROIALIGN_ALGO_RESIDENT) &&
          resident_supported(a, dx, st.smem_optin, &plan) && plan.bwd_ok;

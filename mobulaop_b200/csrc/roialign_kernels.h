@@ -174,4 +174,11 @@ size_t tile_bwd_workspace(const RoiAlignArgs& a, const TilePlan& plan);
 cudaError_t launch_bwd_tile(const RoiAlignArgs& a, const TilePlan& plan, void* workspace, const float* dy,
                             float* dx, int accumulate, int deterministic, int num_sms, cudaStream_t stream);
 
+// ---- pull family (roialign_pull.cu): backward as a gather over per-pixel contribution lists,
+// lane = channel; fixed sampling ratios -------------------------------------------------------
+bool pull_supported(const RoiAlignArgs& a);
+size_t pull_bwd_workspace(const RoiAlignArgs& a);
+cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, const float* dy, float* dx, int accumulate,
+                            int deterministic, int num_sms, cudaStream_t stream);
+
 }  // namespace mobula_b200

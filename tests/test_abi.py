@@ -54,7 +54,7 @@ def test_library_exports_every_declared_symbol(native):
 def test_abi_version_and_pure_host_entry_points(native):
     assert native.mobula_roialign_abi_version() == 1
     assert isinstance(native.mobula_roialign_launch_count(), int)
-    assert native.mobula_roialign_last_algo(0) in (b'none', b'gather', b'plane', b'resident')
+    assert native.mobula_roialign_last_algo(0) in (b'none', b'gather', b'plane', b'resident', b'sweep')
 
 
 def test_invalid_arguments_are_rejected_before_any_cuda_call(native):

@@ -20,7 +20,7 @@ from mobulaop_b200.testing import (assert_bit_exact, assert_scatter_close,
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not has_cuda(), reason='needs a CUDA device')]
 
-ALGOS = ['gather', 'plane', 'resident', 'sweep', 'auto']
+ALGOS = ['gather', 'plane', 'resident', 'sweep', 'pull', 'auto']
 
 
 def _skip_unless_supported(algo, pooled, sr, backward=False, width=None):
@@ -30,6 +30,12 @@ def _skip_unless_supported(algo, pooled, sr, backward=False, width=None):
     if algo == 'sweep':
         if pooled[1] > 16:
             pytest.skip('sweep kernels: pooled width <= 16 only')
+        return
+    if algo == 'pull':
+        if not backward:
+            pytest.skip('pull is a backward formulation (as a forward algorithm it means auto)')
+        if sr < 1 or max(pooled) * sr > 64:
+            pytest.skip('pull kernels: fixed sampling ratio, at most 64 samples per ROI axis')
         return
     if algo != 'resident':
         return
@@ -150,8 +156,19 @@ def test_backward_deterministic_golden_bit_exact(direct, name):
     # sampling_ratio 2 takes the resident kernel's canonical-order variant, anything else the
     # row-tile kernel's; both must give the single-thread reference's bits (as must the old
     # whole-plane canonical kernel, below)
-    expect = 'resident-canonical' if g['sr'] == 2 and max(g['pooled']) <= 16 else 'tile-canonical'
+    # fixed sampling ratios take the pull kernel's canonical-order variant, adaptive grids the
+    # row-tile kernel's; the resident / whole-plane canonical kernels must give the same bits
+    N, _, H, W = g['data'].shape
+    if g['sr'] >= 1 and N * H * W >= 32768:
+        expect = 'pull-canonical'
+    else:
+        expect = 'resident-canonical' if g['sr'] == 2 and max(g['pooled']) <= 16 else 'tile-canonical'
     assert _native.last_algo(True) == expect
+    if g['sr'] >= 1 and max(g['pooled']) * g['sr'] <= 64:
+        pull = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], mode='deterministic',
+                               algo='pull')
+        assert _native.last_algo(True) == 'pull-canonical'
+        assert_bit_exact(pull, g['dx'])
     tile = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], mode='deterministic',
                            algo='sweep')
     assert _native.last_algo(True) == 'tile-canonical'
@@ -307,6 +324,62 @@ def test_sweep_family_against_the_oracle(direct, oracle, shape):
     dacc = direct.backward(dy, rois, data.shape, scale, sr, algo='sweep', mode='deterministic',
                            accumulate_into=dbase.copy())
     assert_bit_exact(dacc, (dbase + dx_ref).astype(np.float32))
+
+
+PULL_SHAPES = [
+    # N, C, H, W, rois/img, pooled, scale, sr
+    (3, 5, 21, 32, 17, (7, 7), 0.25, 2),        # one channel per lane, ragged group
+    (2, 40, 40, 52, 23, (16, 16), 0.125, 2),    # 32 samples per axis
+    (2, 4, 33, 36, 19, (1, 1), 0.5, 2),         # a single bin
+    (2, 2, 18, 20, 9, (9, 3), 0.5, 2),          # PH > PW
+    (1, 70, 150, 200, 40, (7, 7), 0.25, 2),     # two channels per lane (72 padded), ragged
+    (1, 3, 37, 271, 30, (7, 7), 0.25, 2),       # odd width: ragged last 32-pixel segment, unaligned rows
+    (1, 2, 31, 300, 25, (14, 14), 0.25, 2),     # odd height: the last row band is half empty
+    (2, 3, 24, 28, 11, (7, 7), 0.25, 1),        # sampling ratio 1 / 4 / 3 (count 9: true division)
+    (2, 3, 24, 28, 11, (5, 6), 0.25, 4),
+    (2, 3, 64, 48, 31, (6, 5), 0.25, 3),
+    (2, 130, 50, 68, 48, (7, 7), 0.25, 2),      # four channels per lane, two groups, the second ragged (2 of 128)
+    (2, 3, 50, 68, 600, (7, 7), 0.25, 2),       # many ROIs per image: long lists, several mask words
+    (2, 8, 14, 14, 64, (7, 7), 1.0, 2),         # the reference benchmark's plane: every sample clamps or overlaps
+    (5, 3, 9, 11, 3, (2, 2), 1.0, 2),           # tiny
+]
+
+
+@pytest.mark.parametrize('shape', PULL_SHAPES, ids=lambda s: 'x'.join(str(v) for v in s[:5]) + '-p%dx%d-sr%d' % (s[5] + (s[7],)))
+def test_pull_backward_against_the_oracle(direct, oracle, shape):
+    """The per-pixel-list backward: merged taps within 1e-5, canonical variant bit-exact, both
+    reproducible; unsorted ROIs, an image without ROIs, a ROI that points at no image."""
+    from mobulaop_b200 import _native
+    N, C, H, W, k, pooled, scale, sr = shape
+    wl = WL.Workload('pull', N, C, H, W, k, pooled, scale, sr, min_box=2.0, max_box=4.0 * max(H, W) / scale)
+    data, rois, dy = WL.make_inputs(wl, seed=37)
+    rng = np.random.default_rng(8)
+    perm = rng.permutation(len(rois))
+    rois = np.ascontiguousarray(rois[perm])
+    if N > 2:
+        rois[rois[:, 0] == N - 1, 0] = 0
+    rois[1, 0] = N + 2
+    dyg = np.ascontiguousarray(np.delete(dy, 1, axis=0))
+    good = np.delete(rois, 1, axis=0)
+    dx_ref = oracle.backward(dyg, good, data.shape, scale, sr)
+    dx_abs = oracle.backward(np.abs(dyg), good, data.shape, scale, sr)
+    dx = direct.backward(dy, rois, data.shape, scale, sr, algo='pull')
+    assert _native.last_algo(True) == 'pull'
+    assert_scatter_close(dx, dx_ref, dx_abs, rtol=1e-5)
+    assert_bit_exact(direct.backward(dy, rois, data.shape, scale, sr, algo='pull'), dx)
+    dxd = direct.backward(dy, rois, data.shape, scale, sr, algo='pull', mode='deterministic')
+    assert _native.last_algo(True) == 'pull-canonical'
+    assert_bit_exact(dxd, dx_ref)
+    dbase = rng.standard_normal(data.shape).astype(np.float32)
+    dacc = direct.backward(dy, rois, data.shape, scale, sr, algo='pull', mode='deterministic',
+                           accumulate_into=dbase.copy())
+    assert_bit_exact(dacc, (dbase + dx_ref).astype(np.float32))
+
+
+def test_pull_rejects_adaptive_grids(direct):
+    rois = np.array([[0, 1, 1, 9, 9]], np.float32)
+    with pytest.raises(NotImplementedError):
+        direct.backward(np.zeros((1, 2, 2, 2), np.float32), rois, (1, 2, 8, 20), 1.0, 0, algo='pull')
 
 
 def test_sweep_rejects_what_it_cannot_do(direct):
@@ -520,7 +593,7 @@ def test_host_buffer_path_is_pipelined_over_channel_chunks(api, native, oracle):
     dx_ref = oracle.backward(dyg, rois[good], data.shape, wl.scale, wl.sampling_ratio)
     dx_abs = oracle.backward(np.abs(dyg), rois[good], data.shape, wl.scale, wl.sampling_ratio)
     assert_scatter_close(dx, dx_ref, dx_abs, rtol=1e-5)
-    assert _native.last_algo(False) == 'resident' and _native.last_algo(True) == 'resident'
+    assert _native.last_algo(False) == 'resident' and _native.last_algo(True) == 'pull'      # 2 x 200 x 272 pixels
     # accumulating variants (req = 'add') through the v2 entry points with host pointers
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     N, C, H, W = data.shape

@@ -28,6 +28,7 @@
 // Fixed sampling ratios only (an adaptive grid has up to H * W taps per ROI; those run on the
 // dense kernels, roialign_dense.cu).
 #include <cstdio>
+#include <cstdlib>
 
 #include "roialign_kernels.h"
 #include "roialign_common.cuh"
@@ -64,7 +65,8 @@ struct PullParams {
   unsigned* rowmask;     // [H][tw]
   uint2* ptr;            // [pixels] first entry and number of entries of every pixel
   unsigned* cursor;      // entries handed out so far (zeroed by the geometry kernel)
-  uint2* entries;        // x = ((roi * PH + ph) * PW + pw) * cw * 4 = byte offset of the bin's channel row in dyt, y = weight
+  uint2* entries;        // x = byte offset of the bin's channel row in dyt, ((roi * PH + ph) * PW + pw) * cw * 4 (a
+                         // multiple of 16) | pixel & 7 | 8 on the last entry of the pixel; y = weight
   float* dyt;            // [R * PH * PW][cw] channel-last copy of dy
   const float* dy;
   float* dx;
@@ -293,7 +295,7 @@ __device__ __forceinline__ unsigned pull_walk(const PullParams& p, int n, int y,
         const unsigned base = (unsigned)__ldg(p.order + pos) * (unsigned)B;
         const uint2* yt = p.ytap + (size_t)pos * p.capy;
         const uint2* xt = p.xtap + (size_t)pos * p.capx;
-        const unsigned cwb = (unsigned)(p.cw * 4);
+        const unsigned cwb = (unsigned)(p.cw * 4), pxbits = (unsigned)(x & 7);     // cwb is a multiple of 16
         if (!DET) {
           for (int a = ra; a < rb; ++a) {
             const uint2 ya = __ldg(yt + a);
@@ -301,7 +303,7 @@ __device__ __forceinline__ unsigned pull_walk(const PullParams& p, int n, int y,
             const float wy = __uint_as_float(ya.y);
             for (int c = ca; c < cb; ++c) {
               const uint2 xc = __ldg(xt + c);
-              *out++ = make_uint2((base + ph * (unsigned)p.pooled_w + (xc.x >> 16)) * cwb,
+              *out++ = make_uint2((base + ph * (unsigned)p.pooled_w + (xc.x >> 16)) * cwb | pxbits,
                                   __float_as_uint(wy * __uint_as_float(xc.y)));
             }
           }
@@ -318,7 +320,7 @@ __device__ __forceinline__ unsigned pull_walk(const PullParams& p, int n, int y,
               const unsigned pw = ((__ldg(&xt[c0].x) >> 17) & 0x7fu) / (unsigned)G;
               int c1 = c0 + 1;
               while (c1 < cb && ((__ldg(&xt[c1].x) >> 17) & 0x7fu) / (unsigned)G == pw) ++c1;
-              const unsigned id = (base + ph * (unsigned)p.pooled_w + pw) * cwb;
+              const unsigned id = (base + ph * (unsigned)p.pooled_w + pw) * cwb | pxbits;
               int a = a0;
               while (a < a1) {                                   // taps of one sample row: 1 or 2
                 const unsigned sa = __ldg(&yt[a].x) >> 17;
@@ -351,11 +353,10 @@ __device__ __forceinline__ unsigned pull_walk(const PullParams& p, int n, int y,
 // of the entry array for all of them (one atomic: WHERE a list lives varies from run to run, what
 // it holds does not), and writes them on a second walk over tables that are in the cache by then.
 template <bool DET>
-__global__ void __launch_bounds__(256) pull_list_kernel(const PullParams p) {
-  ptx::chain_enter();
+__device__ __forceinline__ void pull_list_block(const PullParams& p, unsigned block) {
   const int lane = threadIdx.x & 31;
   const int segs = (p.width + 31) >> 5;
-  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long wid = (long long)block * 8 + (threadIdx.x >> 5);
   if (wid >= (long long)p.num_images * p.height * segs) return;
   const int seg = (int)(wid % segs);
   const int row = (int)(wid / segs);               // n * H + y
@@ -375,6 +376,7 @@ __global__ void __launch_bounds__(256) pull_list_kernel(const PullParams p) {
   const unsigned begin = base + incl - total;
   if (x0 + lane < p.width) p.ptr[(long long)row * p.width + x0 + lane] = make_uint2(begin, total);
   if (warp_total) pull_walk<true, DET>(p, n, y, x0, lane, p.entries + begin);
+  if (total) p.entries[begin + total - 1].x |= 8u;       // the last entry of the pixel (written by this thread)
 }
 
 // ---- channel-last copy of dy: [R][C][B] -> [R * B][cw] -------------------------------------
@@ -383,12 +385,10 @@ __global__ void __launch_bounds__(256) pull_list_kernel(const PullParams p) {
 // is conflict-free) and leaves as B rows of 128 consecutive channels.
 // kTrChannels = 128 for box-head bins (49 per channel), 32 for the mask head's 196: more blocks per SM
 template <int kTrChannels>
-__global__ void __launch_bounds__(256) pull_transpose_kernel(const PullParams p) {
-  extern __shared__ float s_t[];      // [kTrChannels][pitch], pitch = B | 1
-  ptx::chain_enter();
+__device__ __forceinline__ void pull_transpose_block(const PullParams& p, unsigned block, float* s_t) {
   const int B = p.pooled_h * p.pooled_w, pitch = B | 1;
   const int groups = (p.cw + kTrChannels - 1) / kTrChannels;
-  const int r = blockIdx.x / groups, c0 = (blockIdx.x - r * groups) * kTrChannels;
+  const int r = block / groups, c0 = (block - r * groups) * kTrChannels;
   const int nc = min(kTrChannels, p.c_work - c0);          // real channels of this block
   const int ncw = min(kTrChannels, p.cw - c0);             // incl. the zero pad channels
   const float* src = p.dy + ((size_t)r * p.channels + c0) * B;
@@ -422,6 +422,29 @@ __global__ void __launch_bounds__(256) pull_transpose_kernel(const PullParams p)
     for (int bb = threadIdx.x / kTrChannels; bb < B; bb += 256 / kTrChannels)
       dst[(size_t)bb * p.cw + c] = real ? mine[bb] : 0.0f;
   }
+}
+
+// The lists and the channel-last copy in ONE grid: building lists is latency-bound index work,
+// the copy is pure bandwidth, and neither depends on the other -- side by side the copy is free.
+// Block roles are interleaved (`lblocks` list blocks, `tblocks` copy blocks) so both progress.
+template <bool DET, int kTrChannels>
+__global__ void __launch_bounds__(256) pull_tables_kernel(const PullParams p, const unsigned lblocks,
+                                                          const unsigned tblocks) {
+  extern __shared__ float s_t[];      // copy blocks: [kTrChannels][B | 1]
+  ptx::chain_enter();
+  const unsigned i = blockIdx.x;
+  const unsigned few = min(lblocks, tblocks), many = max(lblocks, tblocks);
+  bool is_few = false;
+  unsigned idx = i;
+  if (few > 0) {
+    const unsigned q = many / few + 1;               // one block of the smaller set every q blocks
+    const unsigned few_before = min(few, (i + q - 1) / q);
+    is_few = i % q == 0 && i / q < few;
+    idx = is_few ? i / q : i - few_before;
+  }
+  const bool list_role = (lblocks <= tblocks) == is_few;      // the smaller set is the list set iff lblocks <= tblocks
+  if (few == 0 ? lblocks > 0 : list_role) pull_list_block<DET>(p, idx);
+  else pull_transpose_block<kTrChannels>(p, idx, s_t);
 }
 
 // ---- the main kernel ------------------------------------------------------------------------
@@ -464,12 +487,28 @@ __device__ __forceinline__ void add_term(float (&acc)[CPL], const float (&g)[CPL
   }
 }
 
-template <int CPL, bool DET, bool ACC>
+// One group of U terms: entries from the warp's shared-memory ring, every gradient load issued
+// before the first use.
+template <int CPL, bool DET, int U>
+__device__ __forceinline__ void term_group(float (&acc)[CPL], const uint2* se, const char* dyt, float count,
+                                           float inv, int pow2) {
+  uint2 en[U];
+  float g[U][CPL];
+#pragma unroll
+  for (int u = 0; u < U; ++u) en[u] = se[u];
+#pragma unroll
+  for (int u = 0; u < U; ++u) load_vec<CPL>(reinterpret_cast<const float*>(dyt + en[u].x), g[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) add_term<CPL, DET>(acc, g[u], __uint_as_float(en[u].y), count, inv, pow2);
+}
+
+template <int CPL, bool DET, bool ACC, int U>
 __global__ void __launch_bounds__(kPullThreads) pull_bwd_kernel(const PullParams p, const float count, const float inv,
                                                                 const int pow2) {
   constexpr int CG = 32 * CPL;                        // channels per CTA
-  __shared__ __align__(16) float tile[kPullRows * 32 * CG];
-  __shared__ uint2 s_ent[kPullThreads / 32][kEntChunk];
+  // per warp: its 8 pixels x CG channels, [pixel][channel slot], and a ring of list entries
+  __shared__ __align__(16) float s_tile[kPullThreads / 32][8 * CG];
+  __shared__ uint2 s_ent[kPullThreads / 32][2 * kEntChunk];
   ptx::chain_enter();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int segs = (p.width + 31) >> 5, bands = (p.height + kPullRows - 1) / kPullRows;
@@ -477,93 +516,108 @@ __global__ void __launch_bounds__(kPullThreads) pull_bwd_kernel(const PullParams
   const int band = (blockIdx.x / segs) % bands;
   const int n = blockIdx.x / (segs * bands);
   const int c0 = blockIdx.y * CG;
-  const int ty = warp >> 2, y = band * kPullRows + ty;
-  const int x0 = seg * 32, xw = x0 + (warp & 3) * 8;
+  const int y = band * kPullRows + (warp >> 2);
+  const int xw = seg * 32 + (warp & 3) * 8;
+  if (y >= p.height || xw >= p.width) return;         // no block-wide barrier below: warps are independent
   const bool lane_on = c0 + lane * CPL < p.cw;
   const char* dyt = reinterpret_cast<const char*>(p.dyt + (lane_on ? c0 + lane * CPL : 0));
+  float* tile = s_tile[warp];
+  uint2* ring = s_ent[warp];
 
-  if (y < p.height && xw < p.width) {
-    const long long pix0 = ((long long)n * p.height + y) * p.width + xw;
-    const int npx = min(8, p.width - xw);
-    // entry ranges of the warp's pixels (one contiguous run): lane i holds the range of pixel i
-    uint2 my_ptr = make_uint2(0u, 0u);
-    if (lane < npx) my_ptr = __ldg(p.ptr + pix0 + lane);
-    const unsigned end_all = __shfl_sync(0xffffffffu, my_ptr.x + my_ptr.y, npx - 1);
-    unsigned have_lo = 0, have_hi = 0;               // entries [have_lo, have_hi) are in s_ent[warp]
-    uint2* ring = s_ent[warp];
-    for (int i = 0; i < npx; ++i) {
-      unsigned e = __shfl_sync(0xffffffffu, my_ptr.x, i);
-      const unsigned end = e + __shfl_sync(0xffffffffu, my_ptr.y, i);
-      float acc[CPL];
+  const long long pix0 = ((long long)n * p.height + y) * p.width + xw;
+  const int npx = min(8, p.width - xw);
+  // The entries of the warp's pixels are ONE contiguous run [e0, end_all) of the entry array.  It
+  // is walked in groups of U terms whatever the pixel boundaries (U gradient loads in flight even
+  // where a pixel has only a few entries); an entry carries its pixel (low three bits) and a flag
+  // on the last entry of the pixel, where the running sums go to the tile.
+  uint2 my_ptr = make_uint2(0u, 0u);
+  if (lane < npx) my_ptr = __ldg(p.ptr + pix0 + lane);
+  const unsigned e0 = __shfl_sync(0xffffffffu, my_ptr.x, 0);
+  const unsigned end_all = __shfl_sync(0xffffffffu, my_ptr.x + my_ptr.y, npx - 1);
+  // tile[pixel][slot]: the lane's CPL channels as one vector; pixels 4 .. 7 swap the halves of the
+  // row (slot ^ 16 channels) so that the read-out below is conflict-free.  Zero first: a pixel
+  // without entries is never stored.
+  float* tlane = tile + CPL * lane;
+  constexpr int kSwap = CPL * (16 / CPL);           // 16 channels, in floats
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) acc[k] = 0.0f;
-      while (e < end) {
-        const unsigned n4 = min(4u, end - e);
-        if (e + n4 > have_hi) {
-          __syncwarp();
-          have_lo = e;
-          have_hi = min(e + (unsigned)kEntChunk, end_all);
+  for (int i = 0; i < 8; ++i) {
+    float* trow = tlane + i * CG;
+    if (CPL == 4) *reinterpret_cast<float4*>(trow) = make_float4(0.f, 0.f, 0.f, 0.f);
+    else if (CPL == 2) *reinterpret_cast<float2*>(trow) = make_float2(0.f, 0.f);
+    else trow[0] = 0.f;
+  }
+  float acc[CPL];
 #pragma unroll
-          for (int k = 0; k < kEntChunk; k += 32)
-            if (e + k + lane < have_hi) ring[k + lane] = __ldg(p.entries + e + k + lane);
-          __syncwarp();
-        }
-        const uint2* se = ring + (e - have_lo);
-        if (n4 == 4) {
-          uint2 en[4];
-          float g[4][CPL];
+  for (int k = 0; k < CPL; ++k) acc[k] = 0.0f;
+  auto flush = [&](unsigned bits) {
+    const int px = (int)(bits & 7u);
+    float* trow = tile + px * CG + ((CPL * lane) ^ ((px & 4) ? kSwap : 0));
+    if (CPL == 4) *reinterpret_cast<float4*>(trow) = make_float4(acc[0], acc[1 % CPL], acc[2 % CPL], acc[3 % CPL]);
+    else if (CPL == 2) *reinterpret_cast<float2*>(trow) = make_float2(acc[0], acc[1 % CPL]);
+    else trow[0] = acc[0];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) en[u] = se[u];
+    for (int k = 0; k < CPL; ++k) acc[k] = 0.0f;
+  };
+  // the ring holds two chunks of entries; the next chunk is fetched into registers while the
+  // current one is consumed
+  uint2 nxt[kEntChunk / 32];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) load_vec<CPL>(reinterpret_cast<const float*>(dyt + en[u].x), g[u]);
+  for (int k = 0; k < kEntChunk / 32; ++k) {
+    const unsigned i = e0 + k * 32 + lane;
+    if (i < end_all) ring[k * 32 + lane] = __ldg(p.entries + i);
+  }
+  __syncwarp();
+  int buf = 0;
+  for (unsigned cbase = e0; cbase < end_all; cbase += kEntChunk, buf ^= 1) {
+    const unsigned cn = min((unsigned)kEntChunk, end_all - cbase);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) add_term<CPL, DET>(acc, g[u], __uint_as_float(en[u].y), count, inv, pow2);
-        } else {
-          for (unsigned u = 0; u < n4; ++u) {
-            const uint2 en = se[u];
-            float g[CPL];
-            load_vec<CPL>(reinterpret_cast<const float*>(dyt + en.x), g);
-            add_term<CPL, DET>(acc, g, __uint_as_float(en.y), count, inv, pow2);
-          }
-        }
-        e += n4;
-      }
-      // tile[pixel][channel ^ (pixel & 31)]: the write below is one vector store per lane, the
-      // read-out (lane = pixel, one channel) finds its 32 pixels in 32 different banks
-      const int px = (warp & 3) * 8 + i;               // pixel inside the row segment (0 .. 31)
-      float* trow = tile + (size_t)(ty * 32 + px) * CG;
-      if (CPL == 4) {
-        const int sw = px & 3;
-        const float4 v = make_float4(acc[sw % CPL], acc[(1 ^ sw) % CPL], acc[(2 ^ sw) % CPL], acc[(3 ^ sw) % CPL]);
-        *reinterpret_cast<float4*>(trow + 4 * (lane ^ (px >> 2))) = v;
-      } else if (CPL == 2) {
-        const int sw = px & 1;
-        const float2 v = make_float2(acc[sw % CPL], acc[(1 ^ sw) % CPL]);
-        *reinterpret_cast<float2*>(trow + 2 * (lane ^ (px >> 1))) = v;
-      } else {
-        trow[lane ^ px] = acc[0];
+    for (int k = 0; k < kEntChunk / 32; ++k) {
+      const unsigned i = cbase + kEntChunk + k * 32 + lane;
+      nxt[k] = i < end_all ? __ldg(p.entries + i) : make_uint2(0u, 0u);
+    }
+    const uint2* se = ring + buf * kEntChunk;
+    unsigned t = 0;
+    for (; t + U <= cn; t += U) {
+      uint2 en[U];
+      float g[U][CPL];
+#pragma unroll
+      for (int u = 0; u < U; ++u) en[u] = se[t + u];
+#pragma unroll
+      for (int u = 0; u < U; ++u) load_vec<CPL>(reinterpret_cast<const float*>(dyt + (en[u].x & ~15u)), g[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        add_term<CPL, DET>(acc, g[u], __uint_as_float(en[u].y), count, inv, pow2);
+        if (en[u].x & 8u) flush(en[u].x);
       }
     }
+    for (; t < cn; ++t) {
+      const uint2 en = se[t];
+      float g[CPL];
+      load_vec<CPL>(reinterpret_cast<const float*>(dyt + (en.x & ~15u)), g);
+      add_term<CPL, DET>(acc, g, __uint_as_float(en.y), count, inv, pow2);
+      if (en.x & 8u) flush(en.x);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kEntChunk / 32; ++k) ring[(buf ^ 1) * kEntChunk + k * 32 + lane] = nxt[k];
+    __syncwarp();
   }
-  __syncthreads();
-  // read-out: every dX element of the tile is written once
+  __syncwarp();
+  // read-out by the warp itself: every dX element of its 8 pixels is written once
   const size_t plane = (size_t)p.height * p.width;
-  const int nch = min(CG, p.c_work - c0), rows = min(kPullRows, p.height - band * kPullRows);
-  float* base = p.dx + ((size_t)n * p.channels + c0) * plane + (size_t)(band * kPullRows) * p.width + x0;
-  if ((p.width & 3) == 0 && x0 + 32 <= p.width && (reinterpret_cast<uintptr_t>(p.dx) & 15u) == 0) {
-    // a warp step = 4 channels x 32 pixels of one row: lane = (pixel quad q, channel cs), four
-    // conflict-free reads ((4 g + cs) ^ (4 q + j) takes 32 different values mod 32), one 16-byte store
-    const int q = lane & 7, cs = lane >> 3;
-    for (int step = warp; step < (CG / 4) * kPullRows; step += kPullThreads / 32) {
-      const int r = step / (CG / 4), c = 4 * (step - r * (CG / 4)) + cs;
-      if (r >= rows || c >= nch) continue;
-      const float* trow = tile + (size_t)(r * 32 + 4 * q) * CG;
-      float4 v;
-      v.x = trow[c ^ (4 * q)];
-      v.y = trow[CG + (c ^ (4 * q + 1))];
-      v.z = trow[2 * CG + (c ^ (4 * q + 2))];
-      v.w = trow[3 * CG + (c ^ (4 * q + 3))];
-      float4* dst = reinterpret_cast<float4*>(base + (size_t)c * plane + (size_t)r * p.width + 4 * q);
+  const int nch = min(CG, p.c_work - c0);
+  float* base = p.dx + ((size_t)n * p.channels + c0) * plane + (size_t)y * p.width + xw;
+  if (npx == 8 && (p.width & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dx) & 15u) == 0) {
+    // a step = 16 channels x 8 pixels: lane = (channel k, pixel quad h); four conflict-free reads
+    // (banks k ^ 16 h), one 16-byte store per lane = sixteen full 32-byte sectors per step
+    const int k = lane >> 1, h = lane & 1;
+#pragma unroll 2
+    for (int cb = 0; cb < CG; cb += 16) {
+      const int c = cb + k;
+      if (c >= nch) continue;
+      const float* t = tile + (4 * h) * CG + (c ^ (16 * h));
+      float4 v = make_float4(t[0], t[CG], t[2 * CG], t[3 * CG]);
+      float4* dst = reinterpret_cast<float4*>(base + (size_t)c * plane + 4 * h);
       if (ACC) {
         const float4 o = *dst;
         v.x = __fadd_rn(o.x, v.x);
@@ -573,15 +627,15 @@ __global__ void __launch_bounds__(kPullThreads) pull_bwd_kernel(const PullParams
       }
       *dst = v;
     }
-  } else if (x0 + lane < p.width) {
-    // ragged segment / unaligned rows: warp = channel, lane = pixel
-    for (int c = warp; c < nch; c += kPullThreads / 32) {
-      float* dst = base + (size_t)c * plane + lane;
-      for (int r = 0; r < rows; ++r, dst += p.width) {
-        const float v = tile[(size_t)(r * 32 + lane) * CG + (c ^ lane)];
+  } else {
+    // ragged group / unaligned rows: lane = (channel, pixel) pairs, four channels per step
+    const int px = lane & 7, k = lane >> 3;
+    if (px < npx)
+      for (int c = k; c < nch; c += 4) {
+        const float v = tile[px * CG + (c ^ ((px & 4) ? 16 : 0))];
+        float* dst = base + (size_t)c * plane + px;
         *dst = ACC ? __fadd_rn(*dst, v) : v;
       }
-    }
   }
 }
 
@@ -697,18 +751,6 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, const float*
     if (det) chained_launch(pull_geom_kernel<true>, gblocks, kGeomWarps * 32, 0, stream, p);
     else chained_launch(pull_geom_kernel<false>, gblocks, kGeomWarps * 32, 0, stream, p);
     count_launch();
-    // channel-last copy of dy
-    const int tc = B <= 64 ? 128 : 32;
-    const int groups = (L.cw + tc - 1) / tc;
-    const size_t tsmem = (size_t)tc * (B | 1) * sizeof(float);
-    if (tc == 128) {
-      chained_launch(pull_transpose_kernel<128>, (unsigned)(a.num_rois * groups), 256, tsmem, stream, p);
-    } else {
-      if (tsmem > 48 * 1024)      // per device, cheap: set on every call
-        cudaFuncSetAttribute(pull_transpose_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-      chained_launch(pull_transpose_kernel<32>, (unsigned)(a.num_rois * groups), 256, tsmem, stream, p);
-    }
-    count_launch();
   }
   {
     const long long warps = (long long)a.height * L.tw;
@@ -716,11 +758,29 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, const float*
     count_launch();
   }
   const long long segs = (a.width + 31) / 32;
-  const long long lwarps = (long long)a.num_images * a.height * segs;
-  const unsigned lblocks = (unsigned)((lwarps + 7) / 8);
-  if (det) chained_launch(pull_list_kernel<true>, lblocks, 256, 0, stream, p);
-  else chained_launch(pull_list_kernel<false>, lblocks, 256, 0, stream, p);
-  count_launch();
+  {
+    // per-pixel lists + channel-last copy of dy, one grid
+    const long long lwarps = (long long)a.num_images * a.height * segs;
+    const unsigned lblocks = (unsigned)((lwarps + 7) / 8);
+    const int tc = B <= 64 ? 128 : 32;
+    const unsigned tblocks = (unsigned)(a.num_rois * ((L.cw + tc - 1) / tc));
+    const size_t tsmem = a.num_rois > 0 ? (size_t)tc * (B | 1) * sizeof(float) : 0;
+#define PULL_TABLES(DET, TC)                                                                                       \
+  do {                                                                                                             \
+    if (tsmem > 48 * 1024) /* per device, cheap: set on every call */                                              \
+      cudaFuncSetAttribute(pull_tables_kernel<DET, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);  \
+    chained_launch(pull_tables_kernel<DET, TC>, lblocks + tblocks, 256, tsmem, stream, p, lblocks, tblocks);       \
+  } while (0)
+    if (tc == 128) {
+      if (det) PULL_TABLES(true, 128);
+      else PULL_TABLES(false, 128);
+    } else {
+      if (det) PULL_TABLES(true, 32);
+      else PULL_TABLES(false, 32);
+    }
+#undef PULL_TABLES
+    count_launch();
+  }
 
   const int G = a.sampling_ratio, cnt_i = G * G;
   const float count = (float)cnt_i;
@@ -729,8 +789,17 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, const float*
   const int cpl = (L.cw >= 128) ? 4 : (L.cw >= 64 ? 2 : 1);
   const long long bands = (a.height + kPullRows - 1) / kPullRows;
   const dim3 grid((unsigned)(segs * bands * a.num_images), (unsigned)((L.cw + 32 * cpl - 1) / (32 * cpl)));
-#define PULL_LAUNCH(CPL, DET, ACC) \
-  chained_launch(pull_bwd_kernel<CPL, DET, ACC>, grid, dim3(kPullThreads), 0, stream, p, count, inv, pow2)
+  // MOBULA_PULL_UNROLL = terms per group (4 or 8): gradient loads in flight per warp
+  static const int unroll = [] { const char* e = getenv("MOBULA_PULL_UNROLL"); return e ? atoi(e) : 8; }();
+  static const int carveout = [] { const char* e = getenv("MOBULA_PULL_CARVEOUT"); return e ? atoi(e) : -1; }();
+#define PULL_LAUNCH(CPL, DET, ACC)                                                                                   \
+  do {                                                                                                               \
+    auto k8 = pull_bwd_kernel<CPL, DET, ACC, 8>;                                                                     \
+    auto k4 = pull_bwd_kernel<CPL, DET, ACC, 4>;                                                                     \
+    auto kk = unroll == 4 ? k4 : k8;                                                                                 \
+    if (carveout >= 0) cudaFuncSetAttribute(kk, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);           \
+    chained_launch(kk, grid, dim3(kPullThreads), 0, stream, p, count, inv, pow2);                                    \
+  } while (0)
 #define PULL_MODE(CPL)                                       \
   do {                                                       \
     if (det) {                                               \

@@ -113,6 +113,7 @@ struct DeviceState {
   cudaEvent_t ws_done = nullptr;   // recorded after the last kernel that reads the workspace
   cudaStream_t ws_stream = nullptr;
   bool ws_used = false;
+  unsigned long long pull_entries_hint = 0;   // adaptive-grid pull backward: list entries the last call needed
   Buffer stage[4];             // host-buffer path: data/dy, rois, out/dx, spare
   // host-buffer path, pipelined over channel chunks: copy-in / copy-out streams and events
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -332,18 +333,44 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
   };
   {
     // pull kernels (per-pixel contribution lists, lane = channel): fixed sampling ratios
-    const bool pull_ok = !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && a.num_images >= 1 && pull_supported(a);
+    // (adaptive grids read one counter back: not inside a stream capture)
+    const bool adaptive = a.sampling_ratio <= 0;
+    const bool pull_ok = !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && a.num_images >= 1 && pull_supported(a) &&
+                         !(adaptive && is_capturing(stream));
     if (algo == MOBULA_ROIALIGN_ALGO_PULL && !pull_ok)
       return fail(MOBULA_ERR_UNSUPPORTED,
-                  "pull backward needs num_images >= 1, a fixed sampling_ratio with at most 64 samples per "
-                  "ROI axis, pooled_h * pooled_w <= 1600 and a plane within 4095 x 4095");
+                  "pull backward needs num_images >= 1, pooled sizes <= 64, pooled_h * pooled_w <= 1600 and either a "
+                  "fixed sampling_ratio with at most 64 samples per ROI axis on a plane within 4095 x 4095, or an "
+                  "adaptive grid on a plane within 2048 x 2048 outside stream capture");
     if (pull_ok && (algo == MOBULA_ROIALIGN_ALGO_PULL || (algo == MOBULA_ROIALIGN_ALGO_AUTO && prefer_pull(a)))) {
-      t_algo[1] = deterministic ? "pull-canonical" : "pull";
-      void* ws = nullptr;
-      int rc = prepare_workspace(st, pull_bwd_workspace(a), stream, &ws);
-      if (rc) return rc;
-      CUDA_TRY(launch_bwd_pull(a, ws, dy, dx, accumulate, deterministic, st.num_sms, stream));
-      return release_tables(st, stream);
+      // adaptive grids: start from what the last call on this device needed (else 256 entries per ROI and bin)
+      unsigned long long entries = 0;
+      if (adaptive)
+        entries = st.pull_entries_hint ? st.pull_entries_hint
+                                       : (unsigned long long)a.num_rois * a.pooled_h * a.pooled_w * 256ull;
+      bool done = false;
+      for (int attempt = 0; attempt < 2 && !done; ++attempt) {
+        void* ws = nullptr;
+        int rc = prepare_workspace(st, pull_bwd_workspace(a, deterministic, entries), stream, &ws);
+        if (rc) return rc;
+        unsigned long long need = 0;
+        CUDA_TRY(launch_bwd_pull(a, ws, entries, dy, dx, accumulate, deterministic, st.num_sms, stream, &need));
+        if (need == 0) {
+          done = true;
+        } else if (need == ~0ull) {
+          break;                                   // lists beyond 32 bits: the row-tile kernel below
+        } else {
+          entries = need + need / 8;               // the tables are rebuilt in the larger workspace
+          st.pull_entries_hint = entries;
+        }
+      }
+      if (done) {
+        t_algo[1] = deterministic ? "pull-canonical" : "pull";
+        return release_tables(st, stream);
+      }
+      if (algo == MOBULA_ROIALIGN_ALGO_PULL)
+        return fail(MOBULA_ERR_UNSUPPORTED, "pull backward: the contribution lists of this call exceed 2^32 entries");
+      { const int rc = release_tables(st, stream); if (rc) return rc; }
     }
   }
   TilePlan tplan;

@@ -176,9 +176,13 @@ cudaError_t launch_bwd_tile(const RoiAlignArgs& a, const TilePlan& plan, void* w
 
 // ---- pull family (roialign_pull.cu): backward as a gather over per-pixel contribution lists,
 // lane = channel; fixed sampling ratios -------------------------------------------------------
+// lane = channel; fixed sampling ratios and adaptive grids.  `entries` = capacity of the list array (adaptive
+// grids: the exact number is known only after the geometry kernel; launch_bwd_pull reports it in
+// *need_entries -- and launches nothing else -- when the workspace is too small; ~0ull: beyond 32-bit lists)
 bool pull_supported(const RoiAlignArgs& a);
-size_t pull_bwd_workspace(const RoiAlignArgs& a);
-cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, const float* dy, float* dx, int accumulate,
-                            int deterministic, int num_sms, cudaStream_t stream);
+size_t pull_bwd_workspace(const RoiAlignArgs& a, int deterministic, unsigned long long entries);
+cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned long long entries, const float* dy,
+                            float* dx, int accumulate, int deterministic, int num_sms, cudaStream_t stream,
+                            unsigned long long* need_entries);
 
 }  // namespace mobula_b200

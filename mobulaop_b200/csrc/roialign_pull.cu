@@ -38,9 +38,9 @@ namespace mobula_b200 {
 
 namespace {
 
-constexpr int kMaxSamples = 64;               // samples per axis: PH * G, PW * G
-constexpr int kMaxTaps = 2 * kMaxSamples;     // taps per axis
-constexpr int kGeomWarps = 4;
+constexpr int kMaxFixedSamples = 64;          // fixed sampling ratio: samples per axis, PH * G and PW * G
+constexpr int kMaxAdaptiveExtent = 2048;      // adaptive grids: plane height / width the geometry kernel's scratch covers
+constexpr int kMaxGeomWarps = 4;
 
 struct PullParams {
   const float* rois;
@@ -48,25 +48,33 @@ struct PullParams {
   int channels;          // channel stride of dy / dx
   int c_work;            // channels this call works on
   int cw;                // channels per row of the channel-last copy of dy (c_work rounded up to 4)
-  int height, width, pooled_h, pooled_w, grid;
+  int height, width, pooled_h, pooled_w;
+  int grid;              // sampling ratio; <= 0: adaptive, ceil(bin) samples per bin and axis (ROIAlign.cpp:47-51)
   float scale;
   int aligned;
   int accumulate;
-  int capy, capx;        // taps per ROI and axis: 2 * PH * G, 2 * PW * G
+  int caps;              // valid samples per ROI and axis the tables have room for
+  int capy, capx;        // taps per ROI and axis
+  int geom_warps;        // warps per block of the geometry kernel
   int tw;                // row-mask words per feature-map row
   long long pixels;      // N * H * W
   const int* img_start;  // [N + 2]
   const int* order;      // [R] ROI rows grouped by image, ascending inside an image
-  uint2* gbox;           // [R] by grouped position: rows min | max << 16, columns min | max << 16
-  unsigned char* yidx;   // [R][H + 2] by grouped position: first tap of row (ymin + q)
-  unsigned char* xidx;   // [R][W + 2]
-  uint2* ytap;           // [R][capy] taps sorted by row: x = row | info << 16, y = weight
+  uint4* gbox;           // [R] by grouped position: rows min | max << 16, columns min | max << 16,
+                         // grid_h | grid_w << 16, count (float bits)
+  unsigned short* yidx;  // [R][H + 2] by grouped position: first tap of row (ymin + q)
+  unsigned short* xidx;  // [R][W + 2]
+  uint2* ytap;           // [R][capy] taps sorted by row: x = row | high << 12 | i << 13 | p << 23 (sample i of
+                         // bin p; merged taps: row | p << 23), y = weight
   uint2* xtap;           // [R][capx]
   unsigned* rowmask;     // [H][tw]
   uint2* ptr;            // [pixels] first entry and number of entries of every pixel
   unsigned* cursor;      // entries handed out so far (zeroed by the geometry kernel)
-  uint2* entries;        // x = byte offset of the bin's channel row in dyt, ((roi * PH + ph) * PW + pw) * cw * 4 (a
-                         // multiple of 16) | pixel & 7 | 8 on the last entry of the pixel; y = weight
+  unsigned long long* need;   // entries this call needs: sum over the ROIs of row taps x column taps
+  void* entries;         // uint2: x = byte offset of the bin's channel row in dyt, ((roi * PH + ph) * PW + pw) * cw * 4
+                         // (a multiple of 16) | pixel & 7 | 8 on the last entry of the pixel; y = weight.
+                         // Deterministic mode on adaptive grids: uint4, z = count, w = 1 / count if that is exact, else 0
+  unsigned entry_cap;    // entries the array has room for
   float* dyt;            // [R * PH * PW][cw] channel-last copy of dy
   const float* dy;
   float* dx;
@@ -79,133 +87,190 @@ __device__ __forceinline__ int mask_word0(const int* __restrict__ img_start, int
 }
 
 // ---- geometry: one warp per ROI (grouped position) ------------------------------------------
-// One axis: the taps of the P * G samples, sorted by (pixel, sample, low/high) [DET] or merged per
-// (pixel, bin) [!DET], and the index "pixel -> first tap".  Returns min | max << 16 of the touched
-// pixels (0xffff | 0: none).
+// Scratch of one warp in shared memory, for `caps` samples.
+struct AxisScratch {
+  unsigned short* lo;    // [caps] pixel of the low tap of valid sample j (samples in ascending order)
+  unsigned short* hi;    // [caps]
+  unsigned* info;        // [caps] i << 13 | p << 23
+  float* frac;           // [caps] weight of the high tap
+  unsigned* skey;        // [2 caps] sorted taps: x word of the tap record
+  float* sw;             // [2 caps]
+};
+
+__host__ __device__ inline size_t axis_scratch_bytes(int caps) { return (size_t)caps * 28 + 64; }
+
+__device__ __forceinline__ AxisScratch carve_scratch(unsigned char* base, int caps) {
+  AxisScratch a;
+  a.skey = reinterpret_cast<unsigned*>(base);
+  a.sw = reinterpret_cast<float*>(a.skey + 2 * caps);
+  a.info = reinterpret_cast<unsigned*>(a.sw + 2 * caps);
+  a.frac = reinterpret_cast<float*>(a.info + caps);
+  a.lo = reinterpret_cast<unsigned short*>(a.frac + caps);
+  a.hi = a.lo + caps;
+  return a;
+}
+
+// One axis: the taps of the ROI's samples inside the plane, sorted by (pixel, sample, low/high)
+// [DET] or merged per (pixel, bin) [!DET], and the index "pixel -> first tap".  Returns the number
+// of taps written; *range = min | max << 16 of the touched pixels.
+//
+// Sample positions ascend with the sample index, hence so do the low and the high pixels, and the
+// position of a tap in the sorted order is a count of two prefixes:
+//   low tap of sample j : j + #{j' < j : hi[j'] <= lo[j]}          (low taps before it + high taps before it)
+//   high tap of sample j: j + #{j' : lo[j'] < hi[j]} (>= j + 1)    (high taps before it + low taps before it)
+// both found by binary search.  Should rounding ever break the ascent (bins narrower than an ulp
+// of the coordinate), the warp falls back to counting smaller keys one by one.
 template <bool DET>
-__device__ unsigned pull_axis(float start, float bin, int pooled, int grid, int extent, float wscale, int lane,
-                              unsigned* s_key, float* s_w, unsigned* s_skey, float* s_sw, uint2* __restrict__ taps,
-                              unsigned char* __restrict__ idx) {
+__device__ int pull_axis(float start, float bin, int pooled, int grid, int extent, float wscale, int caps, int lane,
+                         const AxisScratch& sc, uint2* __restrict__ taps, unsigned short* __restrict__ idx,
+                         unsigned* range) {
   const int ns = pooled * grid;
-  // raw taps: sample s -> slots 2 s (low) and 2 s + 1 (high); key = pixel << 8 | s << 1 | high
-  for (int s = lane; s < kMaxSamples; s += 32) {
-    unsigned k0 = 0xffffffffu, k1 = 0xffffffffu;
-    float w0 = 0.0f, w1 = 0.0f;
+  // ---- the valid samples, in order ----
+  int nv = 0;
+  for (int s0 = 0; s0 < ns; s0 += 32) {
+    const int s = s0 + lane;
+    AxisTap t;
+    t.valid = false;
+    int p = 0, i = 0;
     if (s < ns) {
-      const int p = s / grid, i = s - p * grid;
-      const AxisTap t = axis_decode(sample_pos(start, p, bin, i, grid), extent);
-      if (t.valid) {
-        k0 = ((unsigned)t.lo << 8) | ((unsigned)s << 1);
-        k1 = ((unsigned)t.hi << 8) | ((unsigned)s << 1) | 1u;
-        w0 = t.wh;      // weight of the low tap (1 - fraction)
-        w1 = t.wl;      // weight of the high tap (the fraction)
-        if (!DET && t.hi == t.lo) k1 = 0xffffffffu;      // clamped sample: its high tap adds 0 to the same pixel
+      p = s / grid;
+      i = s - p * grid;
+      t = axis_decode(sample_pos(start, p, bin, i, grid), extent);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, t.valid);
+    if (t.valid) {
+      const int j = nv + __popc(m & ((1u << lane) - 1u));
+      if (j < caps) {
+        sc.lo[j] = (unsigned short)t.lo;
+        sc.hi[j] = (unsigned short)t.hi;
+        sc.info[j] = ((unsigned)i << 13) | ((unsigned)p << 23);
+        sc.frac[j] = t.wl;
       }
     }
-    s_key[2 * s] = k0;
-    s_key[2 * s + 1] = k1;
-    s_w[2 * s] = w0;
-    s_w[2 * s + 1] = w1;
+    nv += __popc(m);
   }
+  nv = min(nv, caps);
   __syncwarp();
-  // rank sort (valid keys are unique)
-  const int nall = 2 * ns;
-  int nvalid = 0;
-  for (int e0 = 0; e0 < nall; e0 += 32) {
-    const int e = e0 + lane;
-    const unsigned key = e < nall ? s_key[e] : 0xffffffffu;
-    const bool valid = key != 0xffffffffu;
-    if (valid) {
-      int rank = 0;
-      for (int k = 0; k < nall; ++k) rank += s_key[k] < key ? 1 : 0;
-      s_skey[rank] = key;
-      s_sw[rank] = s_w[e];
+  *range = 0xffffu;
+  if (nv == 0) return 0;
+  // ---- ascending? ----
+  bool bad = false;
+  for (int j = lane; j + 1 < nv; j += 32) bad |= sc.lo[j] > sc.lo[j + 1] || sc.hi[j] > sc.hi[j + 1];
+  const bool ascending = !__any_sync(0xffffffffu, bad);
+  // ---- sorted position of every tap ----
+  for (int j = lane; j < nv; j += 32) {
+    const unsigned lo = sc.lo[j], hi = sc.hi[j];
+    const float f = sc.frac[j];
+    const unsigned base = sc.info[j];
+    int ra, rb;
+    if (ascending) {
+      int a = 0, b = j;                        // first j' in [0, j) with hi[j'] > lo
+      while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (sc.hi[mid] > lo) b = mid;
+        else a = mid + 1;
+      }
+      ra = j + a;
+      a = j + 1;
+      b = nv;                                  // first j' in (j, nv) with lo[j'] >= hi
+      while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (sc.lo[mid] >= hi) b = mid;
+        else a = mid + 1;
+      }
+      rb = j + a;
+    } else {
+      ra = rb = 0;
+      for (int k = 0; k < nv; ++k) {
+        const unsigned klo = sc.lo[k], khi = sc.hi[k];
+        // keys: (pixel, sample, high)
+        ra += (klo < lo || (klo == lo && k < j)) ? 1 : 0;            // low taps before my low tap
+        ra += (khi < lo || (khi == lo && k < j)) ? 1 : 0;            // high taps before my low tap
+        rb += (klo < hi || (klo == hi && k <= j)) ? 1 : 0;           // low taps before my high tap
+        rb += (khi < hi || (khi == hi && k < j)) ? 1 : 0;            // high taps before my high tap
+      }
     }
-    nvalid += __popc(__ballot_sync(0xffffffffu, valid));
+    sc.skey[ra] = lo | base;
+    sc.sw[ra] = __fsub_rn(1.0f, f);            // weight of the low tap
+    sc.skey[rb] = hi | base | (1u << 12);
+    sc.sw[rb] = f;
   }
   __syncwarp();
-  int nfinal = nvalid;
+  const int nt = 2 * nv;
+  int nfinal = nt;
   if (DET) {
-    for (int e = lane; e < nvalid; e += 32) {
-      const unsigned key = s_skey[e];
-      taps[e] = make_uint2((key >> 8) | ((key & 0xffu) << 16), __float_as_uint(s_sw[e]));
-    }
+    for (int e = lane; e < nt; e += 32) taps[e] = make_uint2(sc.skey[e], __float_as_uint(sc.sw[e]));
   } else {
-    // runs of one (pixel, bin) become one tap with the summed weight
+    // runs of one (pixel, bin) become one tap with the summed weight; the merged x words go back
+    // to the front of skey (never ahead of the reader: a run is at least one tap long)
     int out_base = 0;
-    for (int e0 = 0; e0 < nvalid; e0 += 32) {
+    for (int e0 = 0; e0 < nt; e0 += 32) {
       const int e = e0 + lane;
       bool head = false;
       unsigned id = 0;
-      if (e < nvalid) {
-        const unsigned key = s_skey[e];
-        id = ((key >> 8) << 8) | (((key & 0xffu) >> 1) / (unsigned)grid);
-        if (e == 0) head = true;
-        else {
-          const unsigned pk = s_skey[e - 1];
-          head = (((pk >> 8) << 8) | (((pk & 0xffu) >> 1) / (unsigned)grid)) != id;
+      float w = 0.0f;
+      if (e < nt) {
+        id = sc.skey[e] & 0xff800fffu;         // pixel and bin
+        head = e == 0 || (sc.skey[e - 1] & 0xff800fffu) != id;
+        if (head) {
+          w = sc.sw[e];
+          for (int k = e + 1; k < nt && (sc.skey[k] & 0xff800fffu) == id; ++k) w += sc.sw[k];
         }
       }
       const unsigned heads = __ballot_sync(0xffffffffu, head);
+      __syncwarp();
       if (head) {
-        float w = s_sw[e];
-        for (int k = e + 1; k < nvalid; ++k) {
-          const unsigned nk = s_skey[k];
-          if ((((nk >> 8) << 8) | (((nk & 0xffu) >> 1) / (unsigned)grid)) != id) break;
-          w += s_sw[k];
-        }
         const int pos = out_base + __popc(heads & ((1u << lane) - 1u));
-        taps[pos] = make_uint2((id >> 8) | ((id & 0xffu) << 16), __float_as_uint(w * wscale));
-        s_key[pos] = id >> 8;           // pixel of the merged tap (for the index below)
+        taps[pos] = make_uint2(id, __float_as_uint(w * wscale));
+        sc.skey[pos] = id;
       }
       out_base += __popc(heads);
+      __syncwarp();
     }
     nfinal = out_base;
-    __syncwarp();
   }
-  if (nfinal == 0) return 0xffffu;
-  const unsigned* pixkey = DET ? s_skey : s_key;
-  const int shift = DET ? 8 : 0;
-  const int pmin = (int)(pixkey[0] >> shift), pmax = (int)(pixkey[nfinal - 1] >> shift);
+  const int pmin = (int)(sc.skey[0] & 0xfffu), pmax = (int)(sc.skey[nfinal - 1] & 0xfffu);
   // idx[q] = first tap whose pixel is >= pmin + q, q = 0 .. pmax - pmin + 1
   for (int q = lane; q <= pmax - pmin + 1; q += 32) {
     const unsigned want = (unsigned)(pmin + q);
-    int lo = 0, hi = nfinal;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if ((pixkey[mid] >> shift) < want) lo = mid + 1;
-      else hi = mid;
+    int a = 0, b = nfinal;
+    while (a < b) {
+      const int mid = (a + b) >> 1;
+      if ((sc.skey[mid] & 0xfffu) < want) a = mid + 1;
+      else b = mid;
     }
-    idx[q] = (unsigned char)lo;
+    idx[q] = (unsigned short)a;
   }
   __syncwarp();
-  return (unsigned)pmin | ((unsigned)pmax << 16);
+  *range = (unsigned)pmin | ((unsigned)pmax << 16);
+  return nfinal;
 }
 
 template <bool DET>
-__global__ void __launch_bounds__(kGeomWarps * 32) pull_geom_kernel(const PullParams p) {
-  __shared__ unsigned s_key[kGeomWarps][kMaxTaps];
-  __shared__ float s_w[kGeomWarps][kMaxTaps];
-  __shared__ unsigned s_skey[kGeomWarps][kMaxTaps];
-  __shared__ float s_sw[kGeomWarps][kMaxTaps];
+__global__ void __launch_bounds__(kMaxGeomWarps * 32) pull_geom_kernel(const PullParams p) {
+  extern __shared__ __align__(16) unsigned char s_geom[];
   ptx::chain_enter();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int pos = blockIdx.x * kGeomWarps + wib;
+  const int pos = blockIdx.x * p.geom_warps + wib;
   if (blockIdx.x == 0 && threadIdx.x == 0) *p.cursor = 0u;
   if (pos >= p.num_rois) return;
-  uint2 box = make_uint2(0xffffu, 0xffffu);
+  const AxisScratch sc = carve_scratch(s_geom + (size_t)wib * axis_scratch_bytes(p.caps), p.caps);
+  uint4 box = make_uint4(0xffffu, 0xffffu, 0u, 0u);
   if (pos < __ldg(p.img_start + p.num_images)) {       // rows with a batch index outside [0, N) scatter nothing
     const int r = __ldg(p.order + pos);
     const RoiGeom g = roi_decode(p.rois + (size_t)r * 5, p.scale, p.pooled_h, p.pooled_w, p.grid, p.aligned != 0);
     const float inv_count = __fdiv_rn(1.0f, g.count);
-    const unsigned yr = pull_axis<DET>(g.start_h, g.bin_h, p.pooled_h, p.grid, p.height, 1.0f, lane, s_key[wib],
-                                       s_w[wib], s_skey[wib], s_sw[wib], p.ytap + (size_t)pos * p.capy,
-                                       p.yidx + (size_t)pos * (p.height + 2));
+    unsigned yr, xr;
+    const int nyt = pull_axis<DET>(g.start_h, g.bin_h, p.pooled_h, g.grid_h, p.height, 1.0f, p.caps, lane, sc,
+                                   p.ytap + (size_t)pos * p.capy, p.yidx + (size_t)pos * (p.height + 2), &yr);
     __syncwarp();
-    const unsigned xr = pull_axis<DET>(g.start_w, g.bin_w, p.pooled_w, p.grid, p.width, inv_count, lane, s_key[wib],
-                                       s_w[wib], s_skey[wib], s_sw[wib], p.xtap + (size_t)pos * p.capx,
-                                       p.xidx + (size_t)pos * (p.width + 2));
-    if (yr != 0xffffu && xr != 0xffffu) box = make_uint2(yr, xr);
+    const int nxt = pull_axis<DET>(g.start_w, g.bin_w, p.pooled_w, g.grid_w, p.width, inv_count, p.caps, lane, sc,
+                                   p.xtap + (size_t)pos * p.capx, p.xidx + (size_t)pos * (p.width + 2), &xr);
+    if (nyt > 0 && nxt > 0) {
+      box = make_uint4(yr, xr, (unsigned)g.grid_h | ((unsigned)g.grid_w << 16), __float_as_uint(g.count));
+      // every (row tap, column tap) pair is one entry of exactly one pixel
+      if (lane == 0) atomicAdd(p.need, (unsigned long long)nyt * (unsigned long long)nxt);
+    }
   }
   if (lane == 0) p.gbox[pos] = box;
 }
@@ -238,14 +303,25 @@ __global__ void __launch_bounds__(256) pull_rowmask_kernel(const PullParams p) {
 }
 
 // ---- per-pixel lists: one thread per pixel, a warp = 32 consecutive pixels of one row ----------
+template <bool WIDE>
+struct EntryOf {
+  typedef uint2 type;
+};
+template <>
+struct EntryOf<true> {
+  typedef uint4 type;
+};
+
 // walk<FILL = false> counts the entries of the lane's pixel, walk<true> writes them: both visit
 // the ROIs of the row in ascending order, so a list is written in its final order by one thread.
-template <bool FILL, bool DET>
-__device__ __forceinline__ unsigned pull_walk(const PullParams& p, int n, int y, int x0, int lane, uint2* out) {
+// WIDE (deterministic mode on adaptive grids): the entry carries the ROI's sample count.
+template <bool FILL, bool DET, bool WIDE>
+__device__ __forceinline__ unsigned pull_walk(const PullParams& p, int n, int y, int x0, int lane,
+                                              typename EntryOf<WIDE>::type* out) {
   const int x = x0 + lane;
   const bool in = x < p.width;
   const int w_lo = mask_word0(p.img_start, n), w_hi = mask_word0(p.img_start, n + 1);
-  const int B = p.pooled_h * p.pooled_w, G = p.grid;
+  const int B = p.pooled_h * p.pooled_w;
   unsigned total = 0;
   for (int wbase = w_lo; wbase < w_hi; wbase += 32) {
     // 32 mask words at a time, one per lane; then the words with a bit set, one after the other
@@ -258,18 +334,18 @@ __device__ __forceinline__ unsigned pull_walk(const PullParams& p, int n, int y,
       const unsigned m = __shfl_sync(0xffffffffu, my_word, wj);
       // the <= 32 ROIs of this word, one per lane: does it reach this row segment, and which of its
       // row taps sit on row y?  (independent loads across the lanes instead of a serial chain)
-      unsigned my_r = 0, my_x = 0;               // ra | rb << 8, xmin | xmax << 16
+      unsigned my_r = 0, my_x = 0;               // ra | rb << 16, xmin | xmax << 16
       bool cand = (m >> lane) & 1u;
       if (cand) {
         const int pos = ((wg - n) << 5) + lane;
-        const uint2 box = __ldg(p.gbox + pos);
+        const uint2 box = __ldg(reinterpret_cast<const uint2*>(p.gbox + pos));
         const int xmin = (int)(box.y & 0xffffu), xmax = (int)(box.y >> 16);
         cand = !(xmax < x0 || xmin > x0 + 31);
         if (cand) {
-          const unsigned char* yi = p.yidx + (size_t)pos * (p.height + 2) + (y - (int)(box.x & 0xffffu));
+          const unsigned short* yi = p.yidx + (size_t)pos * (p.height + 2) + (y - (int)(box.x & 0xffffu));
           const unsigned ra = __ldg(yi), rb = __ldg(yi + 1);
           cand = ra != rb;
-          my_r = ra | (rb << 8);
+          my_r = ra | (rb << 16);
           my_x = box.y;
         }
       }
@@ -279,11 +355,11 @@ __device__ __forceinline__ unsigned pull_walk(const PullParams& p, int n, int y,
         live &= live - 1;
         const int pos = ((wg - n) << 5) + b;
         const unsigned rr = __shfl_sync(0xffffffffu, my_r, b), xx = __shfl_sync(0xffffffffu, my_x, b);
-        const int ra = (int)(rr & 0xffu), rb = (int)(rr >> 8);
+        const int ra = (int)(rr & 0xffffu), rb = (int)(rr >> 16);
         const int xmin = (int)(xx & 0xffffu), xmax = (int)(xx >> 16);
         int ca = 0, cb = 0;
         if (in && x >= xmin && x <= xmax) {
-          const unsigned char* xi = p.xidx + (size_t)pos * (p.width + 2) + (x - xmin);
+          const unsigned short* xi = p.xidx + (size_t)pos * (p.width + 2) + (x - xmin);
           ca = __ldg(xi);
           cb = __ldg(xi + 1);
         }
@@ -296,15 +372,26 @@ __device__ __forceinline__ unsigned pull_walk(const PullParams& p, int n, int y,
         const uint2* yt = p.ytap + (size_t)pos * p.capy;
         const uint2* xt = p.xtap + (size_t)pos * p.capx;
         const unsigned cwb = (unsigned)(p.cw * 4), pxbits = (unsigned)(x & 7);     // cwb is a multiple of 16
+        unsigned cnt_bits = 0, inv_bits = 0;
+        if (WIDE) {
+          const uint2 gc = __ldg(reinterpret_cast<const uint2*>(p.gbox + pos) + 1);   // grid sizes, count
+          const unsigned cnt_i = (gc.x & 0xffffu) * (gc.x >> 16);
+          cnt_bits = gc.y;
+          if ((cnt_i & (cnt_i - 1u)) == 0u) inv_bits = __float_as_uint(__fdiv_rn(1.0f, __uint_as_float(gc.y)));
+        }
+        auto emit = [&](unsigned id, float w) {
+          if (WIDE) *reinterpret_cast<uint4*>(out) = make_uint4(id, __float_as_uint(w), cnt_bits, inv_bits);
+          else *reinterpret_cast<uint2*>(out) = make_uint2(id, __float_as_uint(w));
+          ++out;
+        };
         if (!DET) {
           for (int a = ra; a < rb; ++a) {
             const uint2 ya = __ldg(yt + a);
-            const unsigned ph = ya.x >> 16;
+            const unsigned ph = ya.x >> 23;
             const float wy = __uint_as_float(ya.y);
             for (int c = ca; c < cb; ++c) {
               const uint2 xc = __ldg(xt + c);
-              *out++ = make_uint2((base + ph * (unsigned)p.pooled_w + (xc.x >> 16)) * cwb | pxbits,
-                                  __float_as_uint(wy * __uint_as_float(xc.y)));
+              emit((base + ph * (unsigned)p.pooled_w + (xc.x >> 23)) * cwb | pxbits, wy * __uint_as_float(xc.y));
             }
           }
         } else {
@@ -312,27 +399,26 @@ __device__ __forceinline__ unsigned pull_walk(const PullParams& p, int n, int y,
           // then the four taps (low/low, low/high, high/low, high/high); ROIAlign.cpp:126-157
           int a0 = ra;
           while (a0 < rb) {
-            const unsigned ph = ((__ldg(&yt[a0].x) >> 17) & 0x7fu) / (unsigned)G;
+            const unsigned ph = __ldg(&yt[a0].x) >> 23;
             int a1 = a0 + 1;
-            while (a1 < rb && ((__ldg(&yt[a1].x) >> 17) & 0x7fu) / (unsigned)G == ph) ++a1;
+            while (a1 < rb && (__ldg(&yt[a1].x) >> 23) == ph) ++a1;
             int c0 = ca;
             while (c0 < cb) {
-              const unsigned pw = ((__ldg(&xt[c0].x) >> 17) & 0x7fu) / (unsigned)G;
+              const unsigned pw = __ldg(&xt[c0].x) >> 23;
               int c1 = c0 + 1;
-              while (c1 < cb && ((__ldg(&xt[c1].x) >> 17) & 0x7fu) / (unsigned)G == pw) ++c1;
+              while (c1 < cb && (__ldg(&xt[c1].x) >> 23) == pw) ++c1;
               const unsigned id = (base + ph * (unsigned)p.pooled_w + pw) * cwb | pxbits;
               int a = a0;
               while (a < a1) {                                   // taps of one sample row: 1 or 2
-                const unsigned sa = __ldg(&yt[a].x) >> 17;
-                const int a2 = (a + 1 < a1 && (__ldg(&yt[a + 1].x) >> 17) == sa) ? a + 2 : a + 1;
+                const unsigned sa = __ldg(&yt[a].x) >> 13;
+                const int a2 = (a + 1 < a1 && (__ldg(&yt[a + 1].x) >> 13) == sa) ? a + 2 : a + 1;
                 int c = c0;
                 while (c < c1) {                                 // taps of one sample column
-                  const unsigned sc = __ldg(&xt[c].x) >> 17;
-                  const int c2 = (c + 1 < c1 && (__ldg(&xt[c + 1].x) >> 17) == sc) ? c + 2 : c + 1;
+                  const unsigned sc = __ldg(&xt[c].x) >> 13;
+                  const int c2 = (c + 1 < c1 && (__ldg(&xt[c + 1].x) >> 13) == sc) ? c + 2 : c + 1;
                   for (int aa = a; aa < a2; ++aa) {
                     const float wy = __uint_as_float(__ldg(&yt[aa].y));
-                    for (int cc = c; cc < c2; ++cc)
-                      *out++ = make_uint2(id, __float_as_uint(__fmul_rn(wy, __uint_as_float(__ldg(&xt[cc].y)))));
+                    for (int cc = c; cc < c2; ++cc) emit(id, __fmul_rn(wy, __uint_as_float(__ldg(&xt[cc].y))));
                   }
                   c = c2;
                 }
@@ -352,8 +438,9 @@ __device__ __forceinline__ unsigned pull_walk(const PullParams& p, int n, int y,
 // Count, reserve, fill in one kernel: the warp counts the entries of its 32 pixels, takes one run
 // of the entry array for all of them (one atomic: WHERE a list lives varies from run to run, what
 // it holds does not), and writes them on a second walk over tables that are in the cache by then.
-template <bool DET>
+template <bool DET, bool WIDE>
 __device__ __forceinline__ void pull_list_block(const PullParams& p, unsigned block) {
+  typedef typename EntryOf<WIDE>::type Entry;
   const int lane = threadIdx.x & 31;
   const int segs = (p.width + 31) >> 5;
   const long long wid = (long long)block * 8 + (threadIdx.x >> 5);
@@ -362,7 +449,7 @@ __device__ __forceinline__ void pull_list_block(const PullParams& p, unsigned bl
   const int row = (int)(wid / segs);               // n * H + y
   const int n = row / p.height, y = row - n * p.height;
   const int x0 = seg * 32;
-  const unsigned total = pull_walk<false, DET>(p, n, y, x0, lane, nullptr);
+  const unsigned total = pull_walk<false, DET, WIDE>(p, n, y, x0, lane, nullptr);
   unsigned incl = total;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -373,10 +460,14 @@ __device__ __forceinline__ void pull_list_block(const PullParams& p, unsigned bl
   unsigned base = 0;
   if (lane == 0 && warp_total) base = atomicAdd(p.cursor, warp_total);
   base = __shfl_sync(0xffffffffu, base, 0);
+  // (the host sized the array from the geometry kernel's count, or from the bound R * capy * capx)
+  const bool fits = (unsigned long long)base + warp_total <= p.entry_cap;
   const unsigned begin = base + incl - total;
-  if (x0 + lane < p.width) p.ptr[(long long)row * p.width + x0 + lane] = make_uint2(begin, total);
-  if (warp_total) pull_walk<true, DET>(p, n, y, x0, lane, p.entries + begin);
-  if (total) p.entries[begin + total - 1].x |= 8u;       // the last entry of the pixel (written by this thread)
+  if (x0 + lane < p.width) p.ptr[(long long)row * p.width + x0 + lane] = make_uint2(begin, fits ? total : 0u);
+  if (!warp_total || !fits) return;
+  Entry* mine = static_cast<Entry*>(p.entries) + begin;
+  pull_walk<true, DET, WIDE>(p, n, y, x0, lane, mine);
+  if (total) mine[total - 1].x |= 8u;       // the last entry of the pixel (written by this thread)
 }
 
 // ---- channel-last copy of dy: [R][C][B] -> [R * B][cw] -------------------------------------
@@ -427,7 +518,7 @@ __device__ __forceinline__ void pull_transpose_block(const PullParams& p, unsign
 // The lists and the channel-last copy in ONE grid: building lists is latency-bound index work,
 // the copy is pure bandwidth, and neither depends on the other -- side by side the copy is free.
 // Block roles are interleaved (`lblocks` list blocks, `tblocks` copy blocks) so both progress.
-template <bool DET, int kTrChannels>
+template <bool DET, bool WIDE, int kTrChannels>
 __global__ void __launch_bounds__(256) pull_tables_kernel(const PullParams p, const unsigned lblocks,
                                                           const unsigned tblocks) {
   extern __shared__ float s_t[];      // copy blocks: [kTrChannels][B | 1]
@@ -443,7 +534,7 @@ __global__ void __launch_bounds__(256) pull_tables_kernel(const PullParams p, co
     idx = is_few ? i / q : i - few_before;
   }
   const bool list_role = (lblocks <= tblocks) == is_few;      // the smaller set is the list set iff lblocks <= tblocks
-  if (few == 0 ? lblocks > 0 : list_role) pull_list_block<DET>(p, idx);
+  if (few == 0 ? lblocks > 0 : list_role) pull_list_block<DET, WIDE>(p, idx);
   else pull_transpose_block<kTrChannels>(p, idx, s_t);
 }
 
@@ -487,29 +578,32 @@ __device__ __forceinline__ void add_term(float (&acc)[CPL], const float (&g)[CPL
   }
 }
 
-// One group of U terms: entries from the warp's shared-memory ring, every gradient load issued
-// before the first use.
-template <int CPL, bool DET, int U>
-__device__ __forceinline__ void term_group(float (&acc)[CPL], const uint2* se, const char* dyt, float count,
-                                           float inv, int pow2) {
-  uint2 en[U];
-  float g[U][CPL];
-#pragma unroll
-  for (int u = 0; u < U; ++u) en[u] = se[u];
-#pragma unroll
-  for (int u = 0; u < U; ++u) load_vec<CPL>(reinterpret_cast<const float*>(dyt + en[u].x), g[u]);
-#pragma unroll
-  for (int u = 0; u < U; ++u) add_term<CPL, DET>(acc, g[u], __uint_as_float(en[u].y), count, inv, pow2);
+__device__ __forceinline__ uint2 zero_entry(uint2*) { return make_uint2(0u, 0u); }
+__device__ __forceinline__ uint4 zero_entry(uint4*) { return make_uint4(0u, 0u, 0u, 0u); }
+// sample count of the term's ROI: a kernel constant for fixed sampling ratios, in the entry otherwise
+__device__ __forceinline__ void count_of(const uint2&, float& count, float& inv, int& pow2) {
+  (void)count;
+  (void)inv;
+  (void)pow2;
+}
+__device__ __forceinline__ void count_of(const uint4& en, float& count, float& inv, int& pow2) {
+  count = __uint_as_float(en.z);
+  inv = __uint_as_float(en.w);
+  pow2 = en.w != 0u;
 }
 
-template <int CPL, bool DET, bool ACC, int U>
-__global__ void __launch_bounds__(kPullThreads) pull_bwd_kernel(const PullParams p, const float count, const float inv,
-                                                                const int pow2) {
+template <int CPL, bool DET, bool ACC, int U, bool WIDE>
+__global__ void __launch_bounds__(kPullThreads) pull_bwd_kernel(const PullParams p, const float count0,
+                                                                const float inv0, const int pow20) {
+  typedef typename EntryOf<WIDE>::type Entry;
   constexpr int CG = 32 * CPL;                        // channels per CTA
   // per warp: its 8 pixels x CG channels, [pixel][channel slot], and a ring of list entries
   __shared__ __align__(16) float s_tile[kPullThreads / 32][8 * CG];
-  __shared__ uint2 s_ent[kPullThreads / 32][2 * kEntChunk];
+  __shared__ __align__(16) Entry s_ent[kPullThreads / 32][2 * kEntChunk];
   ptx::chain_enter();
+  const Entry* entries = static_cast<const Entry*>(p.entries);
+  float count = count0, inv = inv0;
+  int pow2 = pow20;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int segs = (p.width + 31) >> 5, bands = (p.height + kPullRows - 1) / kPullRows;
   const int seg = blockIdx.x % segs;
@@ -522,7 +616,7 @@ __global__ void __launch_bounds__(kPullThreads) pull_bwd_kernel(const PullParams
   const bool lane_on = c0 + lane * CPL < p.cw;
   const char* dyt = reinterpret_cast<const char*>(p.dyt + (lane_on ? c0 + lane * CPL : 0));
   float* tile = s_tile[warp];
-  uint2* ring = s_ent[warp];
+  Entry* ring = s_ent[warp];
 
   const long long pix0 = ((long long)n * p.height + y) * p.width + xw;
   const int npx = min(8, p.width - xw);
@@ -560,11 +654,11 @@ __global__ void __launch_bounds__(kPullThreads) pull_bwd_kernel(const PullParams
   };
   // the ring holds two chunks of entries; the next chunk is fetched into registers while the
   // current one is consumed
-  uint2 nxt[kEntChunk / 32];
+  Entry nxt[kEntChunk / 32];
 #pragma unroll
   for (int k = 0; k < kEntChunk / 32; ++k) {
     const unsigned i = e0 + k * 32 + lane;
-    if (i < end_all) ring[k * 32 + lane] = __ldg(p.entries + i);
+    if (i < end_all) ring[k * 32 + lane] = __ldg(entries + i);
   }
   __syncwarp();
   int buf = 0;
@@ -573,12 +667,12 @@ __global__ void __launch_bounds__(kPullThreads) pull_bwd_kernel(const PullParams
 #pragma unroll
     for (int k = 0; k < kEntChunk / 32; ++k) {
       const unsigned i = cbase + kEntChunk + k * 32 + lane;
-      nxt[k] = i < end_all ? __ldg(p.entries + i) : make_uint2(0u, 0u);
+      nxt[k] = i < end_all ? __ldg(entries + i) : zero_entry(static_cast<Entry*>(nullptr));
     }
-    const uint2* se = ring + buf * kEntChunk;
+    const Entry* se = ring + buf * kEntChunk;
     unsigned t = 0;
     for (; t + U <= cn; t += U) {
-      uint2 en[U];
+      Entry en[U];
       float g[U][CPL];
 #pragma unroll
       for (int u = 0; u < U; ++u) en[u] = se[t + u];
@@ -586,14 +680,16 @@ __global__ void __launch_bounds__(kPullThreads) pull_bwd_kernel(const PullParams
       for (int u = 0; u < U; ++u) load_vec<CPL>(reinterpret_cast<const float*>(dyt + (en[u].x & ~15u)), g[u]);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
+        count_of(en[u], count, inv, pow2);
         add_term<CPL, DET>(acc, g[u], __uint_as_float(en[u].y), count, inv, pow2);
         if (en[u].x & 8u) flush(en[u].x);
       }
     }
     for (; t < cn; ++t) {
-      const uint2 en = se[t];
+      const Entry en = se[t];
       float g[CPL];
       load_vec<CPL>(reinterpret_cast<const float*>(dyt + (en.x & ~15u)), g);
+      count_of(en, count, inv, pow2);
       add_term<CPL, DET>(acc, g, __uint_as_float(en.y), count, inv, pow2);
       if (en.x & 8u) flush(en.x);
     }
@@ -640,20 +736,42 @@ __global__ void __launch_bounds__(kPullThreads) pull_bwd_kernel(const PullParams
 }
 
 struct PullLayout {
-  size_t img_start, order, gbox, yidx, xidx, ytap, xtap, rowmask, ptr, cursor, entries, dyt, total;
-  int capy, capx, tw, cw;
+  size_t img_start, order, gbox, yidx, xidx, ytap, xtap, rowmask, ptr, cursor, need, dyt, entries, total;
+  int caps, capy, capx, tw, cw, geom_warps;
+  size_t entry_bytes;
+  unsigned long long entry_cap;
   long long pixels;
 };
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-PullLayout pull_layout(const RoiAlignArgs& a) {
+// `entries`: capacity of the entry array (fixed sampling ratios: ignored, the exact bound
+// R * capy * capx is used)
+PullLayout pull_layout(const RoiAlignArgs& a, bool deterministic, unsigned long long entries) {
   PullLayout L;
   const int G = a.sampling_ratio;
+  const bool adaptive = G <= 0;
   const size_t R = (size_t)a.num_rois;
   const int cwork = a.c_count > 0 ? a.c_count : a.channels;
-  L.capy = 2 * a.pooled_h * G;
-  L.capx = 2 * a.pooled_w * G;
+  if (adaptive) {
+    // valid samples per axis: spacing bin / ceil(bin) > 1/2 over [-1, extent], or `pooled` samples when bin <= 1
+    const int sy = 2 * a.height + a.pooled_h + 4, sx = 2 * a.width + a.pooled_w + 4;
+    L.caps = sy > sx ? sy : sx;
+    L.capy = 2 * sy;
+    L.capx = 2 * sx;
+    L.entry_cap = entries;
+  } else {
+    const int sy = a.pooled_h * G, sx = a.pooled_w * G;
+    L.caps = sy > sx ? sy : sx;
+    L.capy = 2 * sy;
+    L.capx = 2 * sx;
+    L.entry_cap = (unsigned long long)R * L.capy * L.capx;
+  }
+  L.entry_bytes = (deterministic && adaptive) ? sizeof(uint4) : sizeof(uint2);
+  const size_t per_warp = axis_scratch_bytes(L.caps);
+  L.geom_warps = (int)((200 * 1024) / per_warp);
+  if (L.geom_warps > kMaxGeomWarps) L.geom_warps = kMaxGeomWarps;
+  if (L.geom_warps < 1) L.geom_warps = 1;
   L.tw = (a.num_rois >> 5) + a.num_images + 1;
   L.cw = (cwork + 3) & ~3;
   L.pixels = (long long)a.num_images * a.height * a.width;
@@ -665,16 +783,17 @@ PullLayout pull_layout(const RoiAlignArgs& a) {
   };
   L.img_start = take((size_t)(a.num_images + 2) * sizeof(int));
   L.order = take(R * sizeof(int));
-  L.gbox = take(R * sizeof(uint2));
-  L.yidx = take(R * (size_t)(a.height + 2));
-  L.xidx = take(R * (size_t)(a.width + 2));
+  L.gbox = take(R * sizeof(uint4));
+  L.yidx = take(R * (size_t)(a.height + 2) * sizeof(unsigned short));
+  L.xidx = take(R * (size_t)(a.width + 2) * sizeof(unsigned short));
   L.ytap = take(R * (size_t)L.capy * sizeof(uint2));
   L.xtap = take(R * (size_t)L.capx * sizeof(uint2));
   L.rowmask = take((size_t)a.height * L.tw * sizeof(unsigned));
   L.ptr = take((size_t)L.pixels * sizeof(uint2));
   L.cursor = take(sizeof(unsigned));
-  L.entries = take(R * (size_t)L.capy * L.capx * sizeof(uint2));
+  L.need = take(sizeof(unsigned long long));
   L.dyt = take(R * (size_t)a.pooled_h * a.pooled_w * L.cw * sizeof(float));
+  L.entries = take((size_t)L.entry_cap * L.entry_bytes);
   L.total = off;
   return L;
 }
@@ -683,28 +802,43 @@ PullLayout pull_layout(const RoiAlignArgs& a) {
 
 bool pull_supported(const RoiAlignArgs& a) {
   const int G = a.sampling_ratio;
-  if (G < 1 || a.num_images < 1 || a.num_images > 65535) return false;
-  if (a.pooled_h * G > kMaxSamples || a.pooled_w * G > kMaxSamples) return false;
-  if (a.height > 4095 || a.width > 4095) return false;
+  if (a.num_images < 1 || a.num_images > 65535) return false;
+  if (a.pooled_h > 64 || a.pooled_w > 64) return false;
+  if (G > 0) {
+    if (a.pooled_h * G > kMaxFixedSamples || a.pooled_w * G > kMaxFixedSamples) return false;
+    if (a.height > 4095 || a.width > 4095) return false;
+    if ((long long)a.num_rois * 4 * a.pooled_h * G * a.pooled_w * G >= (1LL << 31)) return false;
+  } else {
+    if (a.height > kMaxAdaptiveExtent || a.width > kMaxAdaptiveExtent) return false;
+  }
   if (a.pooled_h * a.pooled_w > 1600) return false;       // the transpose block: 32 channels x bins in shared memory
   const int cwork = a.c_count > 0 ? a.c_count : a.channels;
   if (cwork < 1) return false;
-  // entry ids and list positions are 32-bit
+  // entry offsets and list positions are 32-bit
   if ((long long)a.num_rois * a.pooled_h * a.pooled_w * ((cwork + 3) & ~3) * 4 >= (1LL << 32)) return false;
-  if ((long long)a.num_rois * 4 * a.pooled_h * G * a.pooled_w * G >= (1LL << 31)) return false;
   const long long segs = ((long long)a.width + 31) / 32, bands = ((long long)a.height + kPullRows - 1) / kPullRows;
   if (segs * bands * a.num_images >= (1LL << 31)) return false;
   return true;
 }
 
-size_t pull_bwd_workspace(const RoiAlignArgs& a) { return pull_layout(a).total; }
+size_t pull_bwd_workspace(const RoiAlignArgs& a, int deterministic, unsigned long long entries) {
+  return pull_layout(a, deterministic != 0, entries).total;
+}
 
-cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, const float* dy, float* dx, int accumulate,
-                            int deterministic, int num_sms, cudaStream_t stream) {
+// Fixed sampling ratios: everything is launched, nothing is read back.  Adaptive grids: the number
+// of entries is only known once the geometry kernel has run; the host waits for it (one 8-byte
+// read-back).  If the workspace has no room for that many entries, nothing else is launched,
+// *need_entries says how many are needed and the caller comes back with a larger workspace
+// (~0ull: more than this formulation can index).
+cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned long long entry_cap, const float* dy,
+                            float* dx, int accumulate, int deterministic, int num_sms, cudaStream_t stream,
+                            unsigned long long* need_entries) {
   (void)num_sms;
+  *need_entries = 0;
   const int cwork = a.c_count > 0 ? a.c_count : a.channels;
   if (cwork <= 0 || a.num_images <= 0) return cudaSuccess;
-  const PullLayout L = pull_layout(a);
+  const bool det = deterministic != 0, adaptive = a.sampling_ratio <= 0;
+  const PullLayout L = pull_layout(a, det, entry_cap);
   char* base = static_cast<char*>(workspace);
   PullParams p;
   p.rois = a.rois;
@@ -721,36 +855,64 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, const float*
   p.scale = a.scale;
   p.aligned = a.aligned;
   p.accumulate = accumulate;
+  p.caps = L.caps;
   p.capy = L.capy;
   p.capx = L.capx;
+  p.geom_warps = L.geom_warps;
   p.tw = L.tw;
   p.pixels = L.pixels;
   int* img_start = reinterpret_cast<int*>(base + L.img_start);
   int* order = reinterpret_cast<int*>(base + L.order);
   p.img_start = img_start;
   p.order = order;
-  p.gbox = reinterpret_cast<uint2*>(base + L.gbox);
-  p.yidx = reinterpret_cast<unsigned char*>(base + L.yidx);
-  p.xidx = reinterpret_cast<unsigned char*>(base + L.xidx);
+  p.gbox = reinterpret_cast<uint4*>(base + L.gbox);
+  p.yidx = reinterpret_cast<unsigned short*>(base + L.yidx);
+  p.xidx = reinterpret_cast<unsigned short*>(base + L.xidx);
   p.ytap = reinterpret_cast<uint2*>(base + L.ytap);
   p.xtap = reinterpret_cast<uint2*>(base + L.xtap);
   p.rowmask = reinterpret_cast<unsigned*>(base + L.rowmask);
   p.ptr = reinterpret_cast<uint2*>(base + L.ptr);
   p.cursor = reinterpret_cast<unsigned*>(base + L.cursor);
-  p.entries = reinterpret_cast<uint2*>(base + L.entries);
+  p.need = reinterpret_cast<unsigned long long*>(base + L.need);
+  p.entries = base + L.entries;
+  p.entry_cap = (unsigned)(L.entry_cap > 0xffffffffull ? 0xffffffffull : L.entry_cap);
   p.dyt = reinterpret_cast<float*>(base + L.dyt);
   p.dy = dy;
   p.dx = dx;
 
-  cudaError_t e = launch_roi_group(a, img_start, order, stream);
+  cudaError_t e = cudaMemsetAsync(p.need, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-  const bool det = deterministic != 0;
+  e = launch_roi_group(a, img_start, order, stream);
+  if (e != cudaSuccess) return e;
   const int B = a.pooled_h * a.pooled_w;
   if (a.num_rois > 0) {
-    const unsigned gblocks = (unsigned)((a.num_rois + kGeomWarps - 1) / kGeomWarps);
-    if (det) chained_launch(pull_geom_kernel<true>, gblocks, kGeomWarps * 32, 0, stream, p);
-    else chained_launch(pull_geom_kernel<false>, gblocks, kGeomWarps * 32, 0, stream, p);
+    const unsigned gblocks = (unsigned)((a.num_rois + L.geom_warps - 1) / L.geom_warps);
+    const size_t gsmem = (size_t)L.geom_warps * axis_scratch_bytes(L.caps);
+    if (det) {
+      if (gsmem > 48 * 1024)
+        cudaFuncSetAttribute(pull_geom_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
+      chained_launch(pull_geom_kernel<true>, gblocks, L.geom_warps * 32, gsmem, stream, p);
+    } else {
+      if (gsmem > 48 * 1024)
+        cudaFuncSetAttribute(pull_geom_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
+      chained_launch(pull_geom_kernel<false>, gblocks, L.geom_warps * 32, gsmem, stream, p);
+    }
     count_launch();
+  }
+  if (adaptive && a.num_rois > 0) {
+    unsigned long long need = 0;
+    e = cudaMemcpyAsync(&need, p.need, sizeof(need), cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return e;
+    if (need >= 0xfffffff0ull) {
+      *need_entries = ~0ull;
+      return cudaSuccess;
+    }
+    if (need > L.entry_cap) {
+      *need_entries = need;
+      return cudaSuccess;
+    }
   }
   {
     const long long warps = (long long)a.height * L.tw;
@@ -758,6 +920,7 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, const float*
     count_launch();
   }
   const long long segs = (a.width + 31) / 32;
+  const bool wide = det && adaptive;
   {
     // per-pixel lists + channel-last copy of dy, one grid
     const long long lwarps = (long long)a.num_images * a.height * segs;
@@ -765,24 +928,27 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, const float*
     const int tc = B <= 64 ? 128 : 32;
     const unsigned tblocks = (unsigned)(a.num_rois * ((L.cw + tc - 1) / tc));
     const size_t tsmem = a.num_rois > 0 ? (size_t)tc * (B | 1) * sizeof(float) : 0;
-#define PULL_TABLES(DET, TC)                                                                                       \
+#define PULL_TABLES(DET, WIDE, TC)                                                                                 \
   do {                                                                                                             \
+    auto kk = pull_tables_kernel<DET, WIDE, TC>;                                                                   \
     if (tsmem > 48 * 1024) /* per device, cheap: set on every call */                                              \
-      cudaFuncSetAttribute(pull_tables_kernel<DET, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);  \
-    chained_launch(pull_tables_kernel<DET, TC>, lblocks + tblocks, 256, tsmem, stream, p, lblocks, tblocks);       \
+      cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);                           \
+    chained_launch(kk, lblocks + tblocks, 256, tsmem, stream, p, lblocks, tblocks);                                \
   } while (0)
-    if (tc == 128) {
-      if (det) PULL_TABLES(true, 128);
-      else PULL_TABLES(false, 128);
-    } else {
-      if (det) PULL_TABLES(true, 32);
-      else PULL_TABLES(false, 32);
-    }
+#define PULL_TABLES_TC(TC)                        \
+  do {                                            \
+    if (wide) PULL_TABLES(true, true, TC);        \
+    else if (det) PULL_TABLES(true, false, TC);   \
+    else PULL_TABLES(false, false, TC);           \
+  } while (0)
+    if (tc == 128) PULL_TABLES_TC(128);
+    else PULL_TABLES_TC(32);
+#undef PULL_TABLES_TC
 #undef PULL_TABLES
     count_launch();
   }
 
-  const int G = a.sampling_ratio, cnt_i = G * G;
+  const int G = a.sampling_ratio, cnt_i = adaptive ? 1 : G * G;
   const float count = (float)cnt_i;
   const int pow2 = (cnt_i & (cnt_i - 1)) == 0 ? 1 : 0;
   const float inv = 1.0f / count;
@@ -791,24 +957,25 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, const float*
   const dim3 grid((unsigned)(segs * bands * a.num_images), (unsigned)((L.cw + 32 * cpl - 1) / (32 * cpl)));
   // MOBULA_PULL_UNROLL = terms per group (4 or 8): gradient loads in flight per warp
   static const int unroll = [] { const char* e = getenv("MOBULA_PULL_UNROLL"); return e ? atoi(e) : 8; }();
-  static const int carveout = [] { const char* e = getenv("MOBULA_PULL_CARVEOUT"); return e ? atoi(e) : -1; }();
-#define PULL_LAUNCH(CPL, DET, ACC)                                                                                   \
-  do {                                                                                                               \
-    auto k8 = pull_bwd_kernel<CPL, DET, ACC, 8>;                                                                     \
-    auto k4 = pull_bwd_kernel<CPL, DET, ACC, 4>;                                                                     \
-    auto kk = unroll == 4 ? k4 : k8;                                                                                 \
-    if (carveout >= 0) cudaFuncSetAttribute(kk, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);           \
-    chained_launch(kk, grid, dim3(kPullThreads), 0, stream, p, count, inv, pow2);                                    \
+#define PULL_LAUNCH(CPL, DET, ACC, WIDE)                                                  \
+  do {                                                                                    \
+    auto k8 = pull_bwd_kernel<CPL, DET, ACC, 8, WIDE>;                                    \
+    auto k4 = pull_bwd_kernel<CPL, DET, ACC, 4, WIDE>;                                    \
+    auto kk = unroll == 4 ? k4 : k8;                                                      \
+    chained_launch(kk, grid, dim3(kPullThreads), 0, stream, p, count, inv, pow2);         \
   } while (0)
-#define PULL_MODE(CPL)                                       \
-  do {                                                       \
-    if (det) {                                               \
-      if (accumulate) PULL_LAUNCH(CPL, true, true);          \
-      else PULL_LAUNCH(CPL, true, false);                    \
-    } else {                                                 \
-      if (accumulate) PULL_LAUNCH(CPL, false, true);         \
-      else PULL_LAUNCH(CPL, false, false);                   \
-    }                                                        \
+#define PULL_MODE(CPL)                                              \
+  do {                                                              \
+    if (wide) {                                                     \
+      if (accumulate) PULL_LAUNCH(CPL, true, true, true);           \
+      else PULL_LAUNCH(CPL, true, false, true);                     \
+    } else if (det) {                                               \
+      if (accumulate) PULL_LAUNCH(CPL, true, true, false);          \
+      else PULL_LAUNCH(CPL, true, false, false);                    \
+    } else {                                                        \
+      if (accumulate) PULL_LAUNCH(CPL, false, true, false);         \
+      else PULL_LAUNCH(CPL, false, false, false);                   \
+    }                                                               \
   } while (0)
   if (cpl == 4) PULL_MODE(4);
   else if (cpl == 2) PULL_MODE(2);

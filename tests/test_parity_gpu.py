@@ -34,8 +34,8 @@ def _skip_unless_supported(algo, pooled, sr, backward=False, width=None):
     if algo == 'pull':
         if not backward:
             pytest.skip('pull is a backward formulation (as a forward algorithm it means auto)')
-        if sr < 1 or max(pooled) * sr > 64:
-            pytest.skip('pull kernels: fixed sampling ratio, at most 64 samples per ROI axis')
+        if max(pooled) * max(sr, 1) > 64:
+            pytest.skip('pull kernels: at most 64 samples per ROI axis at a fixed sampling ratio, pooled sizes <= 64')
         return
     if algo != 'resident':
         return
@@ -159,12 +159,12 @@ def test_backward_deterministic_golden_bit_exact(direct, name):
     # fixed sampling ratios take the pull kernel's canonical-order variant, adaptive grids the
     # row-tile kernel's; the resident / whole-plane canonical kernels must give the same bits
     N, _, H, W = g['data'].shape
-    if g['sr'] >= 1 and N * H * W >= 32768:
+    if N * H * W >= 32768:
         expect = 'pull-canonical'
     else:
         expect = 'resident-canonical' if g['sr'] == 2 and max(g['pooled']) <= 16 else 'tile-canonical'
     assert _native.last_algo(True) == expect
-    if g['sr'] >= 1 and max(g['pooled']) * g['sr'] <= 64:
+    if max(g['pooled']) * max(g['sr'], 1) <= 64:
         pull = direct.backward(g['dy'], g['rois'], g['data'].shape, g['scale'], g['sr'], mode='deterministic',
                                algo='pull')
         assert _native.last_algo(True) == 'pull-canonical'
@@ -342,6 +342,10 @@ PULL_SHAPES = [
     (2, 3, 50, 68, 600, (7, 7), 0.25, 2),       # many ROIs per image: long lists, several mask words
     (2, 8, 14, 14, 64, (7, 7), 1.0, 2),         # the reference benchmark's plane: every sample clamps or overlaps
     (5, 3, 9, 11, 3, (2, 2), 1.0, 2),           # tiny
+    (1, 33, 150, 200, 30, (5, 12), 0.25, 0),    # adaptive grids: per-ROI sample counts, degenerate and outside boxes
+    (2, 3, 50, 68, 600, (7, 7), 0.25, 0),       # ... many ROIs per image
+    (1, 3, 37, 271, 30, (7, 7), 0.25, 0),       # ... odd width
+    (2, 130, 40, 52, 40, (7, 7), 0.25, 0),      # ... four channels per lane
 ]
 
 
@@ -351,7 +355,8 @@ def test_pull_backward_against_the_oracle(direct, oracle, shape):
     reproducible; unsorted ROIs, an image without ROIs, a ROI that points at no image."""
     from mobulaop_b200 import _native
     N, C, H, W, k, pooled, scale, sr = shape
-    wl = WL.Workload('pull', N, C, H, W, k, pooled, scale, sr, min_box=2.0, max_box=4.0 * max(H, W) / scale)
+    wl = WL.Workload('pull', N, C, H, W, k, pooled, scale, sr, min_box=2.0, max_box=4.0 * max(H, W) / scale,
+                     stress=sr == 0)
     data, rois, dy = WL.make_inputs(wl, seed=37)
     rng = np.random.default_rng(8)
     perm = rng.permutation(len(rois))
@@ -376,10 +381,10 @@ def test_pull_backward_against_the_oracle(direct, oracle, shape):
     assert_bit_exact(dacc, (dbase + dx_ref).astype(np.float32))
 
 
-def test_pull_rejects_adaptive_grids(direct):
+def test_pull_rejects_what_it_cannot_do(direct):
     rois = np.array([[0, 1, 1, 9, 9]], np.float32)
-    with pytest.raises(NotImplementedError):
-        direct.backward(np.zeros((1, 2, 2, 2), np.float32), rois, (1, 2, 8, 20), 1.0, 0, algo='pull')
+    with pytest.raises(NotImplementedError):            # 70 samples per ROI axis at a fixed ratio
+        direct.backward(np.zeros((1, 2, 35, 2), np.float32), rois, (1, 2, 8, 20), 1.0, 2, algo='pull')
 
 
 def test_sweep_rejects_what_it_cannot_do(direct):

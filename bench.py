@@ -275,6 +275,9 @@ def timed_steps(run, flush_l2, barrier, steps, warmup, clocks_index=None):
     bwd_ms = np.array([ev[k][1].elapsed_time(ev[k][2]) for k in range(steps)])
     return dict(step_ms=float((fwd_ms + bwd_ms).mean()), fwd_ms=float(fwd_ms.mean()),
                 bwd_ms=float(bwd_ms.mean()), launches=native.launch_count() - launches0, wall=wall,
+                spread=dict(fwd_ms_min=float(fwd_ms.min()), fwd_ms_median=float(np.median(fwd_ms)),
+                            fwd_ms_max=float(fwd_ms.max()), bwd_ms_min=float(bwd_ms.min()),
+                            bwd_ms_median=float(np.median(bwd_ms)), bwd_ms_max=float(bwd_ms.max())),
                 clocks=sampler.summary() if sampler else None,
                 algo_fwd=native.last_algo(False), algo_bwd=native.last_algo(True))
 
@@ -419,7 +422,7 @@ def run_ours(args):
             parallelism='roi-shard-by-image x%d (%s scaling)' % (world, args.scaling),
             backward_mode=args.mode, algo=args.algo,
             shard_ms=dict(max=step_ms, mean=float(allr[:, 0].mean()), per_rank=[float(v) for v in allr[:, 0]]),
-            fwd_ms_max=fwd_max, bwd_ms_max=bwd_max,
+            fwd_ms_max=fwd_max, bwd_ms_max=bwd_max, rank0_step_spread=res['spread'],
             l2='256 MB buffer written, then another 256 MB read, between timed steps (outside the CUDA '
                'events): cold L2 without dirty flush lines; a rank\'s step moves %.0f MB > 126 MB L2' % (b_step / 1e6),
             compare_with='profiles/r1_bench_C4.json (round 1, C4 on one GPU: 3.47 M ROIs/s, 16.8 %% of '

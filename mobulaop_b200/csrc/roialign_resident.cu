@@ -107,7 +107,19 @@ resident_fwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
   if (k < 2 * ypairs) {
     s.lo_off = (unsigned)((height + 1) * pitch * unit);
     s.l = 0.0f;
-    if (k < 2 * pooled_h) s = make_sample(g.start_h, k >> 1, g.bin_h, k & 1, 2, height, pitch * unit);
+    if (k < 2 * pooled_h) {
+      s = make_sample(g.start_h, k >> 1, g.bin_h, k & 1, 2, height, pitch * unit);
+      // Row reuse (the offsets are multiples of 16, the code sits in their low two bits): how the
+      // taps of this sample row relate to those of the previous sample row of the ROI --
+      //   2: the same two plane rows (nothing to load), 1: its low row is the previous high row
+      //   (one row to load), 0: both rows are new.  Sample rows closer than a pixel are the rule
+      //   for small ROIs (bin_h / 2 < 1 below 14 feature-map rows at 7 x 7).
+      if (k > 0) {
+        const AxisSample prev = make_sample(g.start_h, (k - 1) >> 1, g.bin_h, (k - 1) & 1, 2, height, pitch * unit);
+        if (s.lo_off == prev.lo_off) s.lo_off |= 2u;
+        else if (s.lo_off == prev.lo_off + (unsigned)(pitch * unit)) s.lo_off |= 1u;
+      }
+    }
   } else {
     const int kk = k - 2 * ypairs;
     s.lo_off = (unsigned)((width + 1) * unit);
@@ -339,6 +351,41 @@ __device__ __forceinline__ float lds_at4(unsigned addr, unsigned epoch) {
   return v;
 }
 
+// The four taps of one sample column in the two plane rows of a sample row, kept in registers
+// from one sample row to the next: (lo, hi) = columns x, x + 1 of the sample's low row `p` and of
+// its high row `c`.  `code` (warp-half uniform, from the table): 0 = load both rows, 1 = the low
+// row is the previous sample row's high row (registers move, one row is loaded), 2 = the same two
+// rows as the previous sample row (nothing is loaded).  The loads are predicated, not branched
+// around: the two half-warps of a warp work on different ROIs / bin rows, and a half-warp that
+// loads nothing also takes no part in the bank conflicts of the other one's load.
+struct Taps {
+  float plo, phi, clo, chi;
+};
+__device__ __forceinline__ void taps_advance(Taps& t, unsigned a, unsigned b, unsigned code, unsigned epoch) {
+  asm("{\n\t.reg .pred pl, ps, ph;\n\t"
+      "setp.eq.u32 pl, %6, 0;\n\tsetp.eq.u32 ps, %6, 1;\n\tsetp.ne.u32 ph, %6, 2;\n\t"
+      "@ps mov.f32 %0, %2;\n\t@ps mov.f32 %1, %3;\n\t"
+      "@pl ld.shared.f32 %0, [%4];\n\t@pl ld.shared.f32 %1, [%4+4];\n\t"
+      "@ph ld.shared.f32 %2, [%5];\n\t@ph ld.shared.f32 %3, [%5+4];\n\t}"
+      : "+f"(t.plo), "+f"(t.phi), "+f"(t.clo), "+f"(t.chi)
+      : "r"(a), "r"(b), "r"(code), "r"(epoch));
+}
+// the same for a channel pair (float2 per pixel)
+struct Taps2 {
+  float2 plo, phi, clo, chi;
+};
+__device__ __forceinline__ void taps2_advance(Taps2& t, unsigned a, unsigned b, unsigned code, unsigned epoch) {
+  asm("{\n\t.reg .pred pl, ps, ph;\n\t"
+      "setp.eq.u32 pl, %10, 0;\n\tsetp.eq.u32 ps, %10, 1;\n\tsetp.ne.u32 ph, %10, 2;\n\t"
+      "@ps mov.f32 %0, %4;\n\t@ps mov.f32 %1, %5;\n\t@ps mov.f32 %2, %6;\n\t@ps mov.f32 %3, %7;\n\t"
+      "@pl ld.shared.v2.f32 {%0, %1}, [%8];\n\t@pl ld.shared.v2.f32 {%2, %3}, [%8+8];\n\t"
+      "@ph ld.shared.v2.f32 {%4, %5}, [%9];\n\t@ph ld.shared.v2.f32 {%6, %7}, [%9+8];\n\t}"
+      : "+f"(t.plo.x), "+f"(t.plo.y), "+f"(t.phi.x), "+f"(t.phi.y), "+f"(t.clo.x), "+f"(t.clo.y), "+f"(t.chi.x),
+        "+f"(t.chi.y)
+      : "r"(a), "r"(b), "r"(code), "r"(epoch));
+}
+constexpr unsigned kRowCodeMask = 3u;
+
 #ifndef MOBULA_FWD2_WARPS
 #define MOBULA_FWD2_WARPS 16
 #endif
@@ -360,7 +407,7 @@ __device__ __forceinline__ void load_roi2(Roi2Regs<ITERS, NCH>& r, const uint2* 
                                           int last_col) {
   const uint4* ent_y = reinterpret_cast<const uint4*>(ent);
 #pragma unroll
-  for (int it = 0; it < ITERS; ++it) r.y[it] = __ldg(ent_y + min(2 * it + h, last_row));
+  for (int it = 0; it < ITERS; ++it) r.y[it] = __ldg(ent_y + min(ITERS * h + it, last_row));
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) r.x[ch] = __ldg(ent + 4 * ITERS + min(16 * ch + q, last_col));
   r.roi = __ldg(order_j);
@@ -427,22 +474,32 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
         lx2[ch] = make_float2(lx, lx);
         hx2[ch] = make_float2(hx, hx);
       }
-      // this lane's first output: bin (h, q / 2) of chunk 0
-      float* optr = out + ((size_t)cur.roi * channels + w.c) * bins + h * pooled_w + (q >> 1);
+      // this lane's first output: bin (ITERS * h, q / 2) of chunk 0 -- half-warp h works on the
+      // bin rows [ITERS * h, ITERS * h + ITERS), one after the other (row reuse, see Taps)
+      float* optr = out + ((size_t)cur.roi * channels + w.c) * bins + (ITERS * h) * pooled_w + (q >> 1);
+      Taps tp[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) tp[ch].plo = tp[ch].phi = tp[ch].clo = tp[ch].chi = 0.0f;
 #pragma unroll
       for (int it = 0; it < ITERS; ++it) {
         const uint4 ey = cur.y[it];
         const float2 ly2 = make_float2(__uint_as_float(ey.y), __uint_as_float(ey.w));
         const float2 hy2 = make_float2(__fsub_rn(1.0f, ly2.x), __fsub_rn(1.0f, ly2.y));
-        const bool row_ok = 2 * it + h < pooled_h;
+        const bool row_ok = ITERS * h + it < pooled_h;
+        // the first sample row of a half-warp has no predecessor in its registers
+        const unsigned y0 = ey.x & ~kRowCodeMask, y1 = ey.z & ~kRowCodeMask;
+        const unsigned code0 = it == 0 ? 0u : (ey.x & kRowCodeMask), code1 = ey.z & kRowCodeMask;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
           // taps of sample iy = 0 in .x, of iy = 1 in .y: v1 v2 / v3 v4 as in bilinear.h:50-53
-          const unsigned a0 = xa[ch] + ey.x, b0 = xb[ch] + ey.x, a1 = xa[ch] + ey.z, b1 = xb[ch] + ey.z;
-          const float2 v1 = make_float2(lds_at(a0, epoch), lds_at(a1, epoch));
-          const float2 v2 = make_float2(lds_at4(a0, epoch), lds_at4(a1, epoch));
-          const float2 v3 = make_float2(lds_at(b0, epoch), lds_at(b1, epoch));
-          const float2 v4 = make_float2(lds_at4(b0, epoch), lds_at4(b1, epoch));
+          taps_advance(tp[ch], xa[ch] + y0, xb[ch] + y0, code0, epoch);
+          const Taps t0 = tp[ch];
+          taps_advance(tp[ch], xa[ch] + y1, xb[ch] + y1, code1, epoch);
+          const Taps t1 = tp[ch];
+          const float2 v1 = make_float2(t0.plo, t1.plo);
+          const float2 v2 = make_float2(t0.phi, t1.phi);
+          const float2 v3 = make_float2(t0.clo, t1.clo);
+          const float2 v4 = make_float2(t0.chi, t1.chi);
           const float2 w1 = __fmul2_rn(hy2, hx2[ch]), w2 = __fmul2_rn(hy2, lx2[ch]);
           const float2 w3 = __fmul2_rn(ly2, hx2[ch]), w4 = __fmul2_rn(ly2, lx2[ch]);
           // the sums stay scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
@@ -460,7 +517,7 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
           t = __fadd_rn(t, s1n);
           const float y = __fmul_rn(t, 0.25f);     // count = 4: an exact scaling
           if (stores[ch] && row_ok) {
-            float* o = optr + (2 * it) * pooled_w + 8 * ch;
+            float* o = optr + it * pooled_w + 8 * ch;
             if (ACC) *o = __fadd_rn(*o, y);
             else *o = y;
           }
@@ -572,19 +629,27 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
       }
       // this lane's first output: bin (0, q / 2) of chunk 0 of its half-warp's ROI
       float* optr = out + ((size_t)roi * channels + w.c) * bins + (q >> 1);
+      Taps tp[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) tp[ch].plo = tp[ch].phi = tp[ch].clo = tp[ch].chi = 0.0f;
 #pragma unroll
       for (int it = 0; it < PH; ++it) {
         const uint4 ey = ys[it];
         const float2 ly2 = make_float2(__uint_as_float(ey.y), __uint_as_float(ey.w));
         const float2 hy2 = make_float2(__fsub_rn(1.0f, ly2.x), __fsub_rn(1.0f, ly2.y));
+        const unsigned y0 = ey.x & ~kRowCodeMask, y1 = ey.z & ~kRowCodeMask;
+        const unsigned code0 = it == 0 ? 0u : (ey.x & kRowCodeMask), code1 = ey.z & kRowCodeMask;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
           // taps of sample iy = 0 in .x, of iy = 1 in .y: v1 v2 / v3 v4 as in bilinear.h:50-53
-          const unsigned a0 = xa[ch] + ey.x, b0 = xb[ch] + ey.x, a1 = xa[ch] + ey.z, b1 = xb[ch] + ey.z;
-          const float2 v1 = make_float2(lds_at(a0, epoch), lds_at(a1, epoch));
-          const float2 v2 = make_float2(lds_at4(a0, epoch), lds_at4(a1, epoch));
-          const float2 v3 = make_float2(lds_at(b0, epoch), lds_at(b1, epoch));
-          const float2 v4 = make_float2(lds_at4(b0, epoch), lds_at4(b1, epoch));
+          taps_advance(tp[ch], xa[ch] + y0, xb[ch] + y0, code0, epoch);
+          const Taps t0 = tp[ch];
+          taps_advance(tp[ch], xa[ch] + y1, xb[ch] + y1, code1, epoch);
+          const Taps t1 = tp[ch];
+          const float2 v1 = make_float2(t0.plo, t1.plo);
+          const float2 v2 = make_float2(t0.phi, t1.phi);
+          const float2 v3 = make_float2(t0.clo, t1.clo);
+          const float2 v4 = make_float2(t0.chi, t1.chi);
           const float2 w1 = __fmul2_rn(hy2, hx2[ch]), w2 = __fmul2_rn(hy2, lx2[ch]);
           const float2 w3 = __fmul2_rn(ly2, hx2[ch]), w4 = __fmul2_rn(ly2, lx2[ch]);
           // scalar sums: see resident_fwd2_kernel
@@ -722,21 +787,25 @@ resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, c
         lx[ch] = __uint_as_float(cur.x[ch].y);
         hx[ch] = __fsub_rn(1.0f, lx[ch]);
       }
-      float* optr = out + ((size_t)cur.roi * channels + c) * bins + h * pooled_w + (q >> 1);
+      // half-warp h: bin rows [ITERS * h, ITERS * h + ITERS), see resident_fwd2_kernel
+      float* optr = out + ((size_t)cur.roi * channels + c) * bins + (ITERS * h) * pooled_w + (q >> 1);
+      Taps2 tp[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) tp[ch].plo = tp[ch].phi = tp[ch].clo = tp[ch].chi = make_float2(0.f, 0.f);
 #pragma unroll
       for (int it = 0; it < ITERS; ++it) {
         const uint4 ey = cur.y[it];
         const float ly0 = __uint_as_float(ey.y), ly1 = __uint_as_float(ey.w);
         const float hy0 = __fsub_rn(1.0f, ly0), hy1 = __fsub_rn(1.0f, ly1);
-        const bool row_ok = 2 * it + h < pooled_h;
+        const bool row_ok = ITERS * h + it < pooled_h;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
           // one bilinear sample of both channels (.x / .y); products packed over the pair, sums
           // scalar (see resident_fwd2_kernel), order as in bilinear.h:50-56
-          auto sample = [&](unsigned row, float hy, float ly) {
-            const unsigned a = xa[ch] + row, b = xb[ch] + row;
-            const float2 v1 = lds2_at(a, epoch), v2 = lds2_at8(a, epoch);
-            const float2 v3 = lds2_at(b, epoch), v4 = lds2_at8(b, epoch);
+          auto sample = [&](unsigned row_code, bool first, float hy, float ly) {
+            const unsigned row = row_code & ~kRowCodeMask;
+            taps2_advance(tp[ch], xa[ch] + row, xb[ch] + row, first ? 0u : (row_code & kRowCodeMask), epoch);
+            const float2 v1 = tp[ch].plo, v2 = tp[ch].phi, v3 = tp[ch].clo, v4 = tp[ch].chi;
             const float w1 = __fmul_rn(hy, hx[ch]), w2 = __fmul_rn(hy, lx[ch]);
             const float w3 = __fmul_rn(ly, hx[ch]), w4 = __fmul_rn(ly, lx[ch]);
             const float2 p1 = __fmul2_rn(make_float2(w1, w1), v1), p2 = __fmul2_rn(make_float2(w2, w2), v2);
@@ -746,7 +815,7 @@ resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, c
             s.y = __fadd_rn(__fadd_rn(__fadd_rn(p1.y, p2.y), p3.y), p4.y);
             return s;
           };
-          const float2 s0 = sample(ey.x, hy0, ly0), s1 = sample(ey.z, hy1, ly1);
+          const float2 s0 = sample(ey.x, it == 0, hy0, ly0), s1 = sample(ey.z, false, hy1, ly1);
           float2 t;
           t.x = __fadd_rn(0.0f, s0.x);
           t.y = __fadd_rn(0.0f, s0.y);
@@ -757,7 +826,7 @@ resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, c
           t.x = __fadd_rn(t.x, __shfl_down_sync(0xffffffffu, s1.x, 1));
           t.y = __fadd_rn(t.y, __shfl_down_sync(0xffffffffu, s1.y, 1));
           if (stores[ch] && row_ok) {
-            float* o = optr + (2 * it) * pooled_w + 8 * ch;
+            float* o = optr + it * pooled_w + 8 * ch;
             const float y0 = __fmul_rn(t.x, 0.25f), y1 = __fmul_rn(t.y, 0.25f);     // count = 4: exact
             if (ACC) {
               o[0] = __fadd_rn(o[0], y0);
@@ -851,6 +920,9 @@ resident_fwd2pr_kernel(const float* __restrict__ data, float* __restrict__ out, 
         hx[ch] = __fsub_rn(1.0f, lx[ch]);
       }
       float* optr = out + ((size_t)cur.roi * channels + c) * bins + (q >> 1);
+      Taps2 tp[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) tp[ch].plo = tp[ch].phi = tp[ch].clo = tp[ch].chi = make_float2(0.f, 0.f);
 #pragma unroll
       for (int it = 0; it < PH; ++it) {
         const uint4 ey = cur.y[it];
@@ -860,10 +932,10 @@ resident_fwd2pr_kernel(const float* __restrict__ data, float* __restrict__ out, 
         for (int ch = 0; ch < NCH; ++ch) {
           // one bilinear sample of both channels (.x / .y); products packed over the pair, sums
           // scalar (see resident_fwd2_kernel), order as in bilinear.h:50-56
-          auto sample = [&](unsigned row, float hy, float ly) {
-            const unsigned a = xa[ch] + row, b = xb[ch] + row;
-            const float2 v1 = lds2_at(a, epoch), v2 = lds2_at8(a, epoch);
-            const float2 v3 = lds2_at(b, epoch), v4 = lds2_at8(b, epoch);
+          auto sample = [&](unsigned row_code, bool first, float hy, float ly) {
+            const unsigned row = row_code & ~kRowCodeMask;
+            taps2_advance(tp[ch], xa[ch] + row, xb[ch] + row, first ? 0u : (row_code & kRowCodeMask), epoch);
+            const float2 v1 = tp[ch].plo, v2 = tp[ch].phi, v3 = tp[ch].clo, v4 = tp[ch].chi;
             const float w1 = __fmul_rn(hy, hx[ch]), w2 = __fmul_rn(hy, lx[ch]);
             const float w3 = __fmul_rn(ly, hx[ch]), w4 = __fmul_rn(ly, lx[ch]);
             const float2 p1 = __fmul2_rn(make_float2(w1, w1), v1), p2 = __fmul2_rn(make_float2(w2, w2), v2);
@@ -873,7 +945,7 @@ resident_fwd2pr_kernel(const float* __restrict__ data, float* __restrict__ out, 
             s.y = __fadd_rn(__fadd_rn(__fadd_rn(p1.y, p2.y), p3.y), p4.y);
             return s;
           };
-          const float2 s0 = sample(ey.x, hy0, ly0), s1 = sample(ey.z, hy1, ly1);
+          const float2 s0 = sample(ey.x, it == 0, hy0, ly0), s1 = sample(ey.z, false, hy1, ly1);
           float2 t;
           t.x = __fadd_rn(0.0f, s0.x);
           t.y = __fadd_rn(0.0f, s0.y);

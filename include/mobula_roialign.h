@@ -173,6 +173,40 @@ const char* mobula_roialign_last_algo(int backward);
 /* Frees the per-device workspaces. */
 void mobula_roialign_release(void);
 
+/* ------------------------------------------------------------------------- *
+ * 3. im2col / col2im of the opzoo Convolution operator     *
+ * ------------------------------------------------------------------------- */
+
+/* Drop-in symbols: replace the generated wrappers around im2col_kernel<float>
+ * (/root/reference/opzoo/Convolution/Convolution.cpp:14-45) and col2im_kernel<float>
+ * (:48-87).  Both kernels have the same C signature, hence the same hash
+ * (mobula/func.py:13-50).  device_id < 0: host pointers, staged through the current
+ * GPU; synchronous like the reference.
+ *   im2col: n = C * KH * KW * OH * OW elements of data_col [C*KH*KW, OH, OW];
+ *   col2im: n = C * H * W elements of data_im; every pixel is the sum of the column
+ *           entries copied from it, added in ascending (h_col, w_col) order. */
+void im2col_341af5d3(const int device_id, const int n, const float* data_im, const int height,
+                     const int width, const int kernel_h, const int kernel_w, const int pad_h,
+                     const int pad_w, const int stride_h, const int stride_w, const int dilation_h,
+                     const int dilation_w, const int height_col, const int width_col,
+                     float* data_col);
+void col2im_341af5d3(const int device_id, const int n, const float* data_col, const int height,
+                     const int width, const int kernel_h, const int kernel_w, const int pad_h,
+                     const int pad_w, const int stride_h, const int stride_w, const int dilation_h,
+                     const int dilation_w, const int height_col, const int width_col,
+                     float* data_im);
+
+/* v2: status code, explicit stream, asynchronous on device pointers.  `channels` is
+ * explicit (the reference derives it from n).  flags: MOBULA_ROIALIGN_HOST_BUFFERS. */
+int mobula_im2col_f32(int device_id, void* stream, const float* data_im, int channels, int height,
+                      int width, int kernel_h, int kernel_w, int pad_h, int pad_w, int stride_h,
+                      int stride_w, int dilation_h, int dilation_w, int height_col, int width_col,
+                      float* data_col, unsigned flags);
+int mobula_col2im_f32(int device_id, void* stream, const float* data_col, int channels, int height,
+                      int width, int kernel_h, int kernel_w, int pad_h, int pad_w, int stride_h,
+                      int stride_w, int dilation_h, int dilation_w, int height_col, int width_col,
+                      float* data_im, unsigned flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     'mobula_roialign_backward_f32', 'mobula_roialign_bookkeeping_f32', 'mobula_host_alloc',
     'mobula_host_free', 'mobula_roialign_launch_count', 'mobula_roialign_last_algo',
     'mobula_roialign_release',
+    'im2col_341af5d3', 'col2im_341af5d3', 'mobula_im2col_f32', 'mobula_col2im_f32',
 )
 
 
@@ -69,6 +70,13 @@ def _declare(lib):
     # explicit ctypes instances (mobula/func.py:248-255, 335-337)
     lib.roi_align_forward_ab78de3c.restype = None
     lib.roi_align_backward_f318a24e.restype = None
+    lib.im2col_341af5d3.restype = None
+    lib.col2im_341af5d3.restype = None
+    conv = [i32, vp, vp] + [i32] * 13 + [vp, u32]
+    lib.mobula_im2col_f32.restype = i32
+    lib.mobula_im2col_f32.argtypes = conv
+    lib.mobula_col2im_f32.restype = i32
+    lib.mobula_col2im_f32.argtypes = conv
 
 
 def library_path():

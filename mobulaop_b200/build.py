@@ -17,7 +17,7 @@ LIB_NAME = 'libmobula_roialign_sm100.so'
 LIB_PATH = os.path.join(LIB_DIR, LIB_NAME)
 
 SOURCES = ['roialign_api.cu', 'roialign_gather.cu', 'roialign_tables.cu', 'roialign_plane.cu', 'roialign_resident.cu',
-           'roialign_sweep.cu', 'roialign_pull.cu']
+           'roialign_sweep.cu', 'roialign_pull.cu', 'im2col.cu']
 HEADERS = ['roialign_kernels.h', 'roialign_common.cuh', 'ptx_sm100.cuh',
            os.path.join('..', '..', 'include', 'mobula_roialign.h')]
 

@@ -832,6 +832,115 @@ MOBULA_EXPORT void roi_align_backward_f318a24e(const int device_id, const int nt
   if (rc != MOBULA_OK) die_like_reference("roi_align_backward", rc);
 }
 
+// ---------------------------------------------------------------------------------------
+// im2col / col2im (opzoo Convolution)
+// ---------------------------------------------------------------------------------------
+static int conv_call(bool to_col, int device_id, void* stream_, const float* src, int channels, int height,
+                     int width, int kernel_h, int kernel_w, int pad_h, int pad_w, int stride_h, int stride_w,
+                     int dilation_h, int dilation_w, int height_col, int width_col, float* dst, unsigned flags) {
+  if (channels < 0 || height <= 0 || width <= 0 || kernel_h <= 0 || kernel_w <= 0 || pad_h < 0 || pad_w < 0 ||
+      stride_h <= 0 || stride_w <= 0 || dilation_h <= 0 || dilation_w <= 0 || height_col < 0 || width_col < 0)
+    return fail(MOBULA_ERR_INVALID_ARGUMENT, "bad convolution geometry");
+  const long long im_elems = (long long)channels * height * width;
+  const long long col_elems = (long long)channels * kernel_h * kernel_w * height_col * width_col;
+  if (im_elems > 0x7fffffffLL || col_elems > 0x7fffffffLL)      // the reference indexes with int n
+    return fail(MOBULA_ERR_UNSUPPORTED, "im2col / col2im: more than 2^31 - 1 elements");
+  const long long n_src = to_col ? im_elems : col_elems, n_dst = to_col ? col_elems : im_elems;
+  if (n_dst == 0) return MOBULA_OK;
+  if (!dst || (n_src > 0 && !src)) return fail(MOBULA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  DeviceGuard guard(device_id);
+  if (guard.status() != cudaSuccess)
+    return fail(MOBULA_ERR_CUDA, "cannot select device %d: %s", device_id, cudaGetErrorString(guard.status()));
+  const int device = guard.current(device_id);
+  if (device < 0 || device >= kMaxDevices) return fail(MOBULA_ERR_INVALID_ARGUMENT, "device %d", device);
+  DeviceState& st = g_dev[device];
+  std::lock_guard<std::mutex> lock(st.mu);
+  int rc = probe(st, device);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const float* d_src = src;
+  float* d_dst = dst;
+  const bool host = (flags & MOBULA_ROIALIGN_HOST_BUFFERS) != 0;
+  if (host) {
+    CUDA_TRY(st.stage[0].reserve((size_t)(n_src > 0 ? n_src : 1) * sizeof(float), stream));
+    CUDA_TRY(st.stage[2].reserve((size_t)n_dst * sizeof(float), stream));
+    d_src = (const float*)st.stage[0].ptr;
+    d_dst = (float*)st.stage[2].ptr;
+    if (n_src > 0)
+      CUDA_TRY(cudaMemcpyAsync(st.stage[0].ptr, src, (size_t)n_src * sizeof(float), cudaMemcpyHostToDevice, stream));
+  }
+  if (to_col)
+    CUDA_TRY(launch_im2col(d_src, channels, height, width, kernel_h, kernel_w, pad_h, pad_w, stride_h, stride_w,
+                           dilation_h, dilation_w, height_col, width_col, d_dst, st.num_sms, stream));
+  else
+    CUDA_TRY(launch_col2im(d_src, channels, height, width, kernel_h, kernel_w, pad_h, pad_w, stride_h, stride_w,
+                           dilation_h, dilation_w, height_col, width_col, d_dst, st.num_sms, stream));
+  if (host) {
+    CUDA_TRY(cudaMemcpyAsync(dst, d_dst, (size_t)n_dst * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+  }
+  return MOBULA_OK;
+}
+
+MOBULA_EXPORT int mobula_im2col_f32(int device_id, void* stream, const float* data_im, int channels, int height,
+                                    int width, int kernel_h, int kernel_w, int pad_h, int pad_w, int stride_h,
+                                    int stride_w, int dilation_h, int dilation_w, int height_col, int width_col,
+                                    float* data_col, unsigned flags) {
+  return conv_call(true, device_id, stream, data_im, channels, height, width, kernel_h, kernel_w, pad_h, pad_w,
+                   stride_h, stride_w, dilation_h, dilation_w, height_col, width_col, data_col, flags);
+}
+
+MOBULA_EXPORT int mobula_col2im_f32(int device_id, void* stream, const float* data_col, int channels, int height,
+                                    int width, int kernel_h, int kernel_w, int pad_h, int pad_w, int stride_h,
+                                    int stride_w, int dilation_h, int dilation_w, int height_col, int width_col,
+                                    float* data_im, unsigned flags) {
+  return conv_call(false, device_id, stream, data_col, channels, height, width, kernel_h, kernel_w, pad_h, pad_w,
+                   stride_h, stride_w, dilation_h, dilation_w, height_col, width_col, data_im, flags);
+}
+
+// the reference ABI passes the element count n of the OUTPUT and no channel count
+static void conv_dropin(bool to_col, const char* where, int device_id, int n, const float* src, int height,
+                        int width, int kernel_h, int kernel_w, int pad_h, int pad_w, int stride_h, int stride_w,
+                        int dilation_h, int dilation_w, int height_col, int width_col, float* dst) {
+  if (n <= 0) return;
+  const long long per_channel = to_col ? (long long)kernel_h * kernel_w * height_col * width_col
+                                       : (long long)height * width;
+  int rc = MOBULA_OK;
+  if (per_channel <= 0 || n % per_channel != 0) {
+    rc = fail(MOBULA_ERR_INVALID_ARGUMENT, "n = %d is not a whole number of channels", n);
+  } else {
+    const unsigned flags = host_context(device_id) ? MOBULA_ROIALIGN_HOST_BUFFERS : 0u;
+    rc = conv_call(to_col, device_id, nullptr, src, (int)(n / per_channel), height, width, kernel_h, kernel_w,
+                   pad_h, pad_w, stride_h, stride_w, dilation_h, dilation_w, height_col, width_col, dst, flags);
+    if (rc == MOBULA_OK && !host_context(device_id)) {
+      DeviceGuard guard(device_id);
+      if (cudaStreamSynchronize(nullptr) != cudaSuccess) {
+        fail(MOBULA_ERR_CUDA, "synchronize: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = MOBULA_ERR_CUDA;
+      }
+    }
+  }
+  if (rc != MOBULA_OK) die_like_reference(where, rc);
+}
+
+MOBULA_EXPORT void im2col_341af5d3(const int device_id, const int n, const float* data_im, const int height,
+                                   const int width, const int kernel_h, const int kernel_w, const int pad_h,
+                                   const int pad_w, const int stride_h, const int stride_w, const int dilation_h,
+                                   const int dilation_w, const int height_col, const int width_col,
+                                   float* data_col) {
+  conv_dropin(true, "im2col", device_id, n, data_im, height, width, kernel_h, kernel_w, pad_h, pad_w, stride_h,
+              stride_w, dilation_h, dilation_w, height_col, width_col, data_col);
+}
+
+MOBULA_EXPORT void col2im_341af5d3(const int device_id, const int n, const float* data_col, const int height,
+                                   const int width, const int kernel_h, const int kernel_w, const int pad_h,
+                                   const int pad_w, const int stride_h, const int stride_w, const int dilation_h,
+                                   const int dilation_w, const int height_col, const int width_col,
+                                   float* data_im) {
+  conv_dropin(false, "col2im", device_id, n, data_col, height, width, kernel_h, kernel_w, pad_h, pad_w, stride_h,
+              stride_w, dilation_h, dilation_w, height_col, width_col, data_im);
+}
+
 MOBULA_EXPORT void set_device(const int device_id) {
   if (device_id < 0) return;
   int current = -1;

@@ -185,4 +185,12 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
                             float* dx, int accumulate, int deterministic, int num_sms, cudaStream_t stream,
                             unsigned long long* need_entries);
 
+// ---- im2col / col2im (im2col.cu): the opzoo Convolution operator's kernels -----------------
+cudaError_t launch_im2col(const float* im, int channels, int height, int width, int kernel_h, int kernel_w,
+                          int pad_h, int pad_w, int stride_h, int stride_w, int dilation_h, int dilation_w,
+                          int height_col, int width_col, float* col, int num_sms, cudaStream_t stream);
+cudaError_t launch_col2im(const float* col, int channels, int height, int width, int kernel_h, int kernel_w,
+                          int pad_h, int pad_w, int stride_h, int stride_w, int dilation_h, int dilation_w,
+                          int height_col, int width_col, float* im, int num_sms, cudaStream_t stream);
+
 }  // namespace mobula_b200

@@ -1,4 +1,4 @@
-"""`mobula.func.<kernel>` launch path for the ROIAlign kernels.
+"""`mobula.func.<kernel>` launch path for the prebuilt kernels (ROIAlign; im2col / col2im).
 
 Keeps the calling convention of the reference's dispatcher
 (/root/reference/mobula/func.py:190-265 `MobulaFunc.__call__`, :138-164
@@ -38,6 +38,12 @@ _SIGNATURES = {
     'roi_align_backward': [('nthreads', _INT), ('top_diff', _IN_T)] + _COMMON +
                           [('bottom_diff', _OUT_T), ('bottom_rois', _IN_T)],
 }
+
+# im2col_kernel / col2im_kernel (/root/reference/opzoo/Convolution/Convolution.cpp:14-24, 48-56)
+_CONV_GEOM = [(n, _INT) for n in ('height', 'width', 'kernel_h', 'kernel_w', 'pad_h', 'pad_w', 'stride_h',
+                                  'stride_w', 'dilation_h', 'dilation_w', 'height_col', 'width_col')]
+_SIGNATURES['im2col'] = [('n', _INT), ('data_im', _IN_T)] + _CONV_GEOM + [('data_col', _OUT_T)]
+_SIGNATURES['col2im'] = [('n', _INT), ('data_col', _IN_T)] + _CONV_GEOM + [('data_im', _OUT_T)]
 
 _SUPPORTED_T = (ctypes.c_float,)
 
@@ -133,9 +139,14 @@ class MobulaFunc(object):
             for t in tensors.values():
                 if t.view.dev_id is None:
                     raise ValueError('%s: host and device tensors mixed in one call' % self.name)
-        launcher = _launch_forward if self.name == 'roi_align_forward' else _launch_backward
-        launcher(values, tensors, -1 if dev_id is None else dev_id, stream, host, mode, accumulate,
-                 algo or config.ROIALIGN_ALGO, aligned)
+        if self.name in ('im2col', 'col2im'):
+            if mode is not None or accumulate is not None or algo is not None or aligned:
+                raise TypeError('%s takes no mode / accumulate / algo / aligned' % self.name)
+            _launch_conv(self.name, values, tensors, -1 if dev_id is None else dev_id, stream, host)
+        else:
+            launcher = _launch_forward if self.name == 'roi_align_forward' else _launch_backward
+            launcher(values, tensors, -1 if dev_id is None else dev_id, stream, host, mode, accumulate,
+                     algo or config.ROIALIGN_ALGO, aligned)
         for t in tensors.values():
             t.finish()
         return None
@@ -188,6 +199,24 @@ def _launch_backward(v, t, dev_id, stream, host, mode, accumulate, algo, aligned
         _vp(dx.resolve(True)), num_rois, num_images, v['channels'], v['height'], v['width'],
         v['pooled_height'], v['pooled_width'], v['spatial_scale'], v['sampling_ratio'],
         _native.BWD_DETERMINISTIC if mode == 'deterministic' else _native.BWD_ATOMIC, flags))
+
+
+def _launch_conv(name, v, t, dev_id, stream, host):
+    """im2col / col2im: `n` counts the elements of the output, the channel count is implied
+    (Convolution.cpp:97-104, 117-124)."""
+    lib = _native.load()
+    to_col = name == 'im2col'
+    src, dst = (t['data_im'], t['data_col']) if to_col else (t['data_col'], t['data_im'])
+    per_channel = (v['kernel_h'] * v['kernel_w'] * v['height_col'] * v['width_col'] if to_col
+                   else v['height'] * v['width'])
+    if per_channel <= 0 or v['n'] % per_channel:
+        raise ValueError('%s: n = %d is not a whole number of channels' % (name, v['n']))
+    entry = lib.mobula_im2col_f32 if to_col else lib.mobula_col2im_f32
+    _native.check(entry(
+        dev_id, _vp(stream), _vp(src.resolve(False)), v['n'] // per_channel, v['height'], v['width'],
+        v['kernel_h'], v['kernel_w'], v['pad_h'], v['pad_w'], v['stride_h'], v['stride_w'],
+        v['dilation_h'], v['dilation_w'], v['height_col'], v['width_col'], _vp(dst.resolve(True)),
+        _native.make_flags(host=host)))
 
 
 _bound = {}

@@ -17,7 +17,8 @@ from .. import func
 OPZOO = os.path.normpath(os.path.join(os.path.dirname(__file__), '..', 'opzoo'))
 
 # operator -> kernels of the native library it launches
-PREBUILT = {'ROIAlign': ('roi_align_forward', 'roi_align_backward')}
+PREBUILT = {'ROIAlign': ('roi_align_forward', 'roi_align_backward'),
+            'Convolution': ('im2col', 'col2im')}
 
 _loaded = {}
 

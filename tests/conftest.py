@@ -16,7 +16,20 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz'))
+    """ROIAlign vectors (tests/golden/gen_golden.py)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and not f.startswith('conv_'))
+
+
+def conv_golden_names():
+    """im2col / col2im vectors (tests/golden/gen_conv_golden.py)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and f.startswith('conv_'))
+
+
+def load_conv_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+    pair = lambda k: tuple(int(v) for v in z[k])
+    return dict(im=z['im'], colg=z['colg'], kernel=pair('kernel'), pad=pair('pad'), stride=pair('stride'),
+                dilation=pair('dilation'), col=z['col'], im_grad=z['im_grad'])
 
 
 def load_golden(name):

@@ -166,10 +166,28 @@ template <int THREADS>
 __device__ __forceinline__ void roi_group_block(const float* __restrict__ rois, int num_rois, int num_images,
                                                 int seg, int* __restrict__ img_start, int* __restrict__ order,
                                                 int* warp_sums /* [THREADS / 32] */) {
-  int before = 0;
-  for (int r = threadIdx.x; r < num_rois; r += THREADS) before += segment_of(rois, r, num_images) < seg ? 1 : 0;
-  int start;
+  // one pass: rows before this segment, rows of this segment, and whether the table is already
+  // grouped (batch indices never decrease -- what every detection pipeline emits)
+  int before = 0, mine_n = 0, unsorted = 0;
+  for (int r = threadIdx.x; r < num_rois; r += THREADS) {
+    const int sg = segment_of(rois, r, num_images);
+    before += sg < seg ? 1 : 0;
+    mine_n += sg == seg ? 1 : 0;
+    if (r > 0) unsorted |= segment_of(rois, r - 1, num_images) > sg ? 1 : 0;
+  }
+  int start, count;
   block_exclusive_scan<THREADS>(before, &start, warp_sums);
+  block_exclusive_scan<THREADS>(mine_n, &count, warp_sums);
+  if (threadIdx.x == 0) {
+    img_start[seg] = start;
+    if (seg == num_images) img_start[seg + 1] = num_rois;
+  }
+  if (!__syncthreads_or(unsorted)) {
+    // grouped already: the rows of this segment are [start, start + count), in place
+    for (int i = threadIdx.x; i < count; i += THREADS) order[start + i] = start + i;
+    return;
+  }
+  // any order: stable partition, THREADS rows per block-wide scan
   int running = start;
   for (int base = 0; base < num_rois; base += THREADS) {
     const int r = base + threadIdx.x;
@@ -178,10 +196,6 @@ __device__ __forceinline__ void roi_group_block(const float* __restrict__ rois, 
     const int pos = block_exclusive_scan<THREADS>(mine, &total, warp_sums);
     if (mine) order[running + pos] = r;
     running += total;
-  }
-  if (threadIdx.x == 0) {
-    img_start[seg] = start;
-    if (seg == num_images) img_start[seg + 1] = num_rois;
   }
 }
 

@@ -147,6 +147,33 @@ int mobula_roialign_backward_f32(int device_id, void* stream, const float* top_d
                                  int pooled_height, int pooled_width, float spatial_scale,
                                  int sampling_ratio, int mode, unsigned flags);
 
+/* Half-precision and channel-last pooled tensors (the consumers of the
+ * [R, C, PH, PW] tensor -- box-head FC, mask-head conv -- take fp16 / bf16, often channel-last).
+ * The arithmetic stays fp32 and in the reference's order: the forward output is the fp32 result
+ * rounded ONCE to nearest-even when it is stored, the backward widens dy exactly when it loads
+ * it.  Feature map, ROIs and bottom_diff stay fp32 NCHW.
+ *   top_dtype : MOBULA_DTYPE_F32 | _F16 | _BF16
+ *   top_layout: MOBULA_LAYOUT_RCHW = [R, C, PH, PW] (the reference)
+ *               MOBULA_LAYOUT_RHWC = [R, PH, PW, C] (channel-last)
+ * Forward: sampling_ratio 2 resident kernels (any type, RCHW) or the sweep kernels (any type, either
+ * layout; pooled width <= 16); MOBULA_ROIALIGN_ACCUMULATE needs (F32, RCHW).  Backward: the pull
+ * kernels, whose copy stage reads any type / layout (a channel-last dy skips their transpose). */
+#define MOBULA_DTYPE_F32 0
+#define MOBULA_DTYPE_F16 1
+#define MOBULA_DTYPE_BF16 2
+#define MOBULA_LAYOUT_RCHW 0
+#define MOBULA_LAYOUT_RHWC 1
+int mobula_roialign_forward_ex(int device_id, void* stream, const float* bottom_data,
+                               const float* bottom_rois, void* top_data, int top_dtype, int top_layout,
+                               int num_rois, int num_images, int channels, int height, int width,
+                               int pooled_height, int pooled_width, float spatial_scale,
+                               int sampling_ratio, unsigned flags);
+int mobula_roialign_backward_ex(int device_id, void* stream, const void* top_diff, int top_dtype,
+                                int top_layout, const float* bottom_rois, float* bottom_diff,
+                                int num_rois, int num_images, int channels, int height, int width,
+                                int pooled_height, int pooled_width, float spatial_scale,
+                                int sampling_ratio, int mode, unsigned flags);
+
 /* ROI bookkeeping as the kernels compute it, for bit-exact checking against the
  * oracle (same layout as oracle_roi_align_bookkeeping_f32):
  *   geom_i [R,4]  = batch, grid_h, grid_w, 0

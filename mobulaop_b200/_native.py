@@ -17,6 +17,11 @@ ERR_UNSUPPORTED = 3
 BWD_ATOMIC = 0
 BWD_DETERMINISTIC = 1
 
+# element type / layout of the pooled tensor (mobula_roialign_{forward,backward}_ex)
+DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
+LAYOUT_RCHW, LAYOUT_RHWC = 0, 1
+LAYOUTS = {'RCHW': LAYOUT_RCHW, 'RHWC': LAYOUT_RHWC}
+
 FLAG_ACCUMULATE = 1
 FLAG_HOST_BUFFERS = 2
 FLAG_ALIGNED = 4
@@ -33,6 +38,7 @@ EXPORTED_SYMBOLS = (
     'mobula_host_free', 'mobula_roialign_launch_count', 'mobula_roialign_last_algo',
     'mobula_roialign_release',
     'im2col_341af5d3', 'col2im_341af5d3', 'mobula_im2col_f32', 'mobula_col2im_f32',
+    'mobula_roialign_forward_ex', 'mobula_roialign_backward_ex',
 )
 
 
@@ -53,6 +59,12 @@ def _declare(lib):
     lib.mobula_roialign_backward_f32.restype = i32
     lib.mobula_roialign_backward_f32.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32,
                                                  i32, f32, i32, i32, u32]
+    lib.mobula_roialign_forward_ex.restype = i32
+    lib.mobula_roialign_forward_ex.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32,
+                                               i32, f32, i32, u32]
+    lib.mobula_roialign_backward_ex.restype = i32
+    lib.mobula_roialign_backward_ex.argtypes = [i32, vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32,
+                                                i32, f32, i32, i32, u32]
     lib.mobula_roialign_bookkeeping_f32.restype = i32
     lib.mobula_roialign_bookkeeping_f32.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, f32, i32,
                                                     vp, vp, i32, vp, vp]

@@ -16,6 +16,7 @@
 
 #include "../../include/mobula_roialign.h"
 #include "roialign_kernels.h"
+#include "roialign_common.cuh"
 
 #define MOBULA_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -252,18 +253,27 @@ static int forward_device(DeviceState& st, int device, cudaStream_t stream, cons
     return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown forward algorithm %u", algo);
   if (algo == MOBULA_ROIALIGN_ALGO_PULL) algo = MOBULA_ROIALIGN_ALGO_AUTO;     // a backward formulation
   const bool no_tables = (flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) != 0;
+  // a half-precision or channel-last output: the sampling_ratio == 2 resident kernels (type only)
+  // and the sweep kernels write it; nothing else does
+  const bool typed = a.top_dtype != 0 || a.top_layout != 0;
+  if (typed && accumulate)
+    return fail(MOBULA_ERR_UNSUPPORTED, "MOBULA_ROIALIGN_ACCUMULATE needs an fp32 [R, C, PH, PW] output");
   ResidentPlan rplan;
-  const bool resident_ok = !no_tables && resident_supported(a, data, st.smem_optin, &rplan);
+  bool resident_ok = !no_tables && resident_supported(a, data, st.smem_optin, &rplan);
+  if (typed && resident_ok && (!rplan.fwd_two || a.top_layout != 0)) resident_ok = false;
+  if (typed && (algo == MOBULA_ROIALIGN_ALGO_GATHER || algo == MOBULA_ROIALIGN_ALGO_PLANE))
+    return fail(MOBULA_ERR_UNSUPPORTED, "the gather / plane kernels write fp32 [R, C, PH, PW] only");
   {
     // sweep kernels: on request, and automatically wherever the resident kernels do not apply
     // (adaptive grids, planes beyond one SM's shared memory) instead of the global-memory gather
     SweepPlan splan;
-    const bool want = algo == MOBULA_ROIALIGN_ALGO_SWEEP || a.aligned ||
+    const bool want = algo == MOBULA_ROIALIGN_ALGO_SWEEP || a.aligned || (typed && !resident_ok) ||
                       (algo == MOBULA_ROIALIGN_ALGO_AUTO && (prefer_sweep() || !resident_ok));
     const bool sweep_ok = want && !no_tables && sweep_supported(a, data, st.smem_optin, st.num_sms, &splan);
-    if ((algo == MOBULA_ROIALIGN_ALGO_SWEEP || a.aligned) && !sweep_ok)
+    if ((algo == MOBULA_ROIALIGN_ALGO_SWEEP || a.aligned || (typed && !resident_ok)) && !sweep_ok)
       return fail(MOBULA_ERR_UNSUPPORTED,
-                  "sweep algorithm (and MOBULA_ROIALIGN_ALIGNED) needs num_images in [1, 4096], pooled_w <= 16 and at least four "
+                  "sweep algorithm (and MOBULA_ROIALIGN_ALIGNED, and fp16 / bf16 / channel-last outputs "
+                  "outside the sampling_ratio 2 resident kernels) needs num_images in [1, 4096], pooled_w <= 16 and at least four "
                   "%d-pixel rows of 32 channels within %d bytes of shared memory", a.width, st.smem_optin);
     if (sweep_ok) {
       t_algo[0] = "sweep";
@@ -321,6 +331,10 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
     return fail(MOBULA_ERR_INVALID_ARGUMENT,
                 "backward without MOBULA_ROIALIGN_ACCUMULATE needs num_images >= 0");
   const bool deterministic = mode == MOBULA_ROIALIGN_BWD_DETERMINISTIC;
+  // a half-precision or channel-last dy is read by the pull kernels only (their copy stage widens it)
+  const bool typed = a.top_dtype != 0 || a.top_layout != 0;
+  if (typed && algo != MOBULA_ROIALIGN_ALGO_AUTO && algo != MOBULA_ROIALIGN_ALGO_PULL)
+    return fail(MOBULA_ERR_UNSUPPORTED, "an fp16 / bf16 / channel-last dy needs the pull backward");
   if (deterministic && algo == MOBULA_ROIALIGN_ALGO_GATHER)
     return fail(MOBULA_ERR_UNSUPPORTED, "the gather backward uses global atomics: not deterministic");
   auto run_tile = [&](const TilePlan& tplan) -> int {
@@ -337,12 +351,12 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
     const bool adaptive = a.sampling_ratio <= 0;
     const bool pull_ok = !(flags & MOBULA_ROIALIGN_DEBUG_NO_TABLES) && a.num_images >= 1 && pull_supported(a) &&
                          !(adaptive && is_capturing(stream));
-    if (algo == MOBULA_ROIALIGN_ALGO_PULL && !pull_ok)
+    if ((algo == MOBULA_ROIALIGN_ALGO_PULL || typed) && !pull_ok)
       return fail(MOBULA_ERR_UNSUPPORTED,
                   "pull backward needs num_images >= 1, pooled sizes <= 64, pooled_h * pooled_w <= 1600 and either a "
                   "fixed sampling_ratio with at most 64 samples per ROI axis on a plane within 4095 x 4095, or an "
                   "adaptive grid on a plane within 2048 x 2048 outside stream capture");
-    if (pull_ok && (algo == MOBULA_ROIALIGN_ALGO_PULL || (algo == MOBULA_ROIALIGN_ALGO_AUTO && prefer_pull(a)))) {
+    if (pull_ok && (algo == MOBULA_ROIALIGN_ALGO_PULL || typed || (algo == MOBULA_ROIALIGN_ALGO_AUTO && prefer_pull(a)))) {
       // adaptive grids: start from what the last call on this device needed (else 256 entries per ROI and bin)
       unsigned long long entries = 0;
       if (adaptive)
@@ -368,7 +382,7 @@ static int backward_device(DeviceState& st, int device, cudaStream_t stream, con
         t_algo[1] = deterministic ? "pull-canonical" : "pull";
         return release_tables(st, stream);
       }
-      if (algo == MOBULA_ROIALIGN_ALGO_PULL)
+      if (algo == MOBULA_ROIALIGN_ALGO_PULL || typed)
         return fail(MOBULA_ERR_UNSUPPORTED, "pull backward: the contribution lists of this call exceed 2^32 entries");
       { const int rc = release_tables(st, stream); if (rc) return rc; }
     }
@@ -444,6 +458,8 @@ static RoiAlignArgs make_args(const float* rois, int num_rois, int num_images, i
   a.scale = scale;
   a.sampling_ratio = sampling_ratio;
   a.aligned = 0;
+  a.top_dtype = 0;
+  a.top_layout = 0;
   return a;
 }
 
@@ -525,13 +541,21 @@ static bool resident_backward_applies(DeviceState& st, const RoiAlignArgs& a, co
          resident_supported(a, dx, st.smem_optin, &plan) && plan.bwd_ok;
 }
 
-MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, const float* bottom_data,
-                                              const float* bottom_rois, float* top_data,
-                                              int num_rois, int num_images, int channels, int height,
-                                              int width, int pooled_height, int pooled_width,
-                                              float spatial_scale, int sampling_ratio,
-                                              unsigned flags) {
-  int rc = check_common(bottom_data, bottom_rois, top_data, num_rois, channels, height, width,
+static int check_top(int dtype, int layout) {
+  if (dtype < MOBULA_DTYPE_F32 || dtype > MOBULA_DTYPE_BF16 || layout < MOBULA_LAYOUT_RCHW || layout > MOBULA_LAYOUT_RHWC)
+    return fail(MOBULA_ERR_INVALID_ARGUMENT, "unknown element type %d / layout %d of the pooled tensor", dtype, layout);
+  return MOBULA_OK;
+}
+
+// `top_data` is typed by `top_dtype`; the float* is only a carrier
+static int forward_impl(int device_id, void* stream_, const float* bottom_data, const float* bottom_rois,
+                        float* top_data, int top_dtype, int top_layout, int num_rois, int num_images,
+                        int channels, int height, int width, int pooled_height, int pooled_width,
+                        float spatial_scale, int sampling_ratio, unsigned flags) {
+  int rc = check_top(top_dtype, top_layout);
+  if (rc) return rc;
+  const size_t esz = top_elem_bytes(top_dtype);
+  rc = check_common(bottom_data, bottom_rois, top_data, num_rois, channels, height, width,
                         pooled_height, pooled_width);
   if (rc) return rc;
   if (num_rois == 0 || channels == 0) return MOBULA_OK;
@@ -550,6 +574,8 @@ MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, cons
     RoiAlignArgs a = make_args(bottom_rois, num_rois, num_images, channels, height, width,
                                pooled_height, pooled_width, spatial_scale, sampling_ratio);
     a.aligned = (flags & MOBULA_ROIALIGN_ALIGNED) ? 1 : 0;
+    a.top_dtype = top_dtype;
+    a.top_layout = top_layout;
     return forward_device(st, device, stream, bottom_data, bottom_rois, top_data, a, flags);
   }
 
@@ -557,7 +583,7 @@ MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, cons
   const int n_img = num_images >= 0 ? num_images : images_from_host_rois(bottom_rois, num_rois);
   const size_t data_bytes = (size_t)n_img * channels * height * width * sizeof(float);
   const size_t rois_bytes = (size_t)num_rois * 5 * sizeof(float);
-  const size_t out_bytes = (size_t)num_rois * channels * pooled_height * pooled_width * sizeof(float);
+  const size_t out_bytes = (size_t)num_rois * channels * pooled_height * pooled_width * esz;
   CUDA_TRY(st.stage[0].reserve(data_bytes, stream));
   CUDA_TRY(st.stage[1].reserve(rois_bytes, stream));
   CUDA_TRY(st.stage[2].reserve(out_bytes, stream));
@@ -567,11 +593,16 @@ MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, cons
   RoiAlignArgs a = make_args(d_rois, num_rois, n_img, channels, height, width, pooled_height,
                              pooled_width, spatial_scale, sampling_ratio);
   a.aligned = (flags & MOBULA_ROIALIGN_ALIGNED) ? 1 : 0;
-  const int cc = resident_forward_applies(st, a, d_data, flags) ? host_chunk(channels, data_bytes, false) : 0;
+  a.top_dtype = top_dtype;
+  a.top_layout = top_layout;
+  // (channel chunks are runs of an [R, C, PH, PW] output; a channel-last one is staged whole)
+  const int cc = (top_layout == 0 && resident_forward_applies(st, a, d_data, flags)) ? host_chunk(channels, data_bytes, false) : 0;
   if (cc > 0) {
     if ((rc = pipeline_setup(st))) return rc;
     const size_t hw = (size_t)height * width, bins = (size_t)pooled_height * pooled_width;
-    const size_t row_pitch = (size_t)channels * bins * sizeof(float);
+    const size_t row_pitch = (size_t)channels * bins * esz;
+    char* const h_top = reinterpret_cast<char*>(top_data);
+    char* const d_top = reinterpret_cast<char*>(d_out);
     const size_t img_pitch = (size_t)channels * hw * sizeof(float);
     CUDA_TRY(cudaMemcpyAsync(d_rois, bottom_rois, rois_bytes, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaEventRecord(st.ev_start, stream));
@@ -585,18 +616,19 @@ MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, cons
         CUDA_TRY(cudaMemcpy2DAsync(d_data + c0 * hw, img_pitch, bottom_data + c0 * hw, img_pitch,
                                    (size_t)cn * hw * sizeof(float), n_img, cudaMemcpyHostToDevice, st.s_in));
       if ((flags & MOBULA_ROIALIGN_ACCUMULATE) && num_rois > 0)
-        CUDA_TRY(cudaMemcpy2DAsync(d_out + c0 * bins, row_pitch, top_data + c0 * bins, row_pitch,
-                                   (size_t)cn * bins * sizeof(float), num_rois, cudaMemcpyHostToDevice, st.s_in));
+        CUDA_TRY(cudaMemcpy2DAsync(d_top + c0 * bins * esz, row_pitch, h_top + c0 * bins * esz, row_pitch,
+                                   (size_t)cn * bins * esz, num_rois, cudaMemcpyHostToDevice, st.s_in));
       CUDA_TRY(cudaEventRecord(st.ev_in[k], st.s_in));
       CUDA_TRY(cudaStreamWaitEvent(stream, st.ev_in[k], 0));
       a.c_count = cn;
-      if ((rc = forward_device(st, device, stream, d_data + c0 * hw, d_rois, d_out + c0 * bins, a, flags)))
+      if ((rc = forward_device(st, device, stream, d_data + c0 * hw, d_rois,
+                               reinterpret_cast<float*>(d_top + c0 * bins * esz), a, flags)))
         return rc;
       CUDA_TRY(cudaEventRecord(st.ev_done[k], stream));
       CUDA_TRY(cudaStreamWaitEvent(st.s_out, st.ev_done[k], 0));
       if (num_rois > 0)
-        CUDA_TRY(cudaMemcpy2DAsync(top_data + c0 * bins, row_pitch, d_out + c0 * bins, row_pitch,
-                                   (size_t)cn * bins * sizeof(float), num_rois, cudaMemcpyDeviceToHost, st.s_out));
+        CUDA_TRY(cudaMemcpy2DAsync(h_top + c0 * bins * esz, row_pitch, d_top + c0 * bins * esz, row_pitch,
+                                   (size_t)cn * bins * esz, num_rois, cudaMemcpyDeviceToHost, st.s_out));
     }
     CUDA_TRY(cudaStreamSynchronize(st.s_out));
     CUDA_TRY(cudaStreamSynchronize(stream));
@@ -612,13 +644,35 @@ MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream_, cons
   return MOBULA_OK;
 }
 
-MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream_, const float* top_diff,
-                                               const float* bottom_rois, float* bottom_diff,
-                                               int num_rois, int num_images, int channels,
-                                               int height, int width, int pooled_height,
-                                               int pooled_width, float spatial_scale,
-                                               int sampling_ratio, int mode, unsigned flags) {
-  int rc = check_common(top_diff, bottom_rois, bottom_diff, num_rois, channels, height, width,
+MOBULA_EXPORT int mobula_roialign_forward_f32(int device_id, void* stream, const float* bottom_data,
+                                              const float* bottom_rois, float* top_data,
+                                              int num_rois, int num_images, int channels, int height,
+                                              int width, int pooled_height, int pooled_width,
+                                              float spatial_scale, int sampling_ratio,
+                                              unsigned flags) {
+  return forward_impl(device_id, stream, bottom_data, bottom_rois, top_data, MOBULA_DTYPE_F32, MOBULA_LAYOUT_RCHW,
+                      num_rois, num_images, channels, height, width, pooled_height, pooled_width, spatial_scale,
+                      sampling_ratio, flags);
+}
+
+MOBULA_EXPORT int mobula_roialign_forward_ex(int device_id, void* stream, const float* bottom_data,
+                                             const float* bottom_rois, void* top_data, int top_dtype,
+                                             int top_layout, int num_rois, int num_images, int channels,
+                                             int height, int width, int pooled_height, int pooled_width,
+                                             float spatial_scale, int sampling_ratio, unsigned flags) {
+  return forward_impl(device_id, stream, bottom_data, bottom_rois, static_cast<float*>(top_data), top_dtype,
+                      top_layout, num_rois, num_images, channels, height, width, pooled_height, pooled_width,
+                      spatial_scale, sampling_ratio, flags);
+}
+
+static int backward_impl(int device_id, void* stream_, const float* top_diff, int top_dtype, int top_layout,
+                         const float* bottom_rois, float* bottom_diff, int num_rois, int num_images, int channels,
+                         int height, int width, int pooled_height, int pooled_width, float spatial_scale,
+                         int sampling_ratio, int mode, unsigned flags) {
+  int rc = check_top(top_dtype, top_layout);
+  if (rc) return rc;
+  const size_t esz = top_elem_bytes(top_dtype);
+  rc = check_common(top_diff, bottom_rois, bottom_diff, num_rois, channels, height, width,
                         pooled_height, pooled_width);
   if (rc) return rc;
   const bool accumulate = flags & MOBULA_ROIALIGN_ACCUMULATE;
@@ -640,13 +694,15 @@ MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream_, con
     RoiAlignArgs a = make_args(bottom_rois, num_rois, num_images, channels, height, width,
                                pooled_height, pooled_width, spatial_scale, sampling_ratio);
     a.aligned = (flags & MOBULA_ROIALIGN_ALIGNED) ? 1 : 0;
+    a.top_dtype = top_dtype;
+    a.top_layout = top_layout;
     return backward_device(st, device, stream, top_diff, bottom_rois, bottom_diff, a, mode, flags);
   }
 
   const int n_img = num_images >= 0 ? num_images : images_from_host_rois(bottom_rois, num_rois);
   const size_t dx_bytes = (size_t)n_img * channels * height * width * sizeof(float);
   const size_t rois_bytes = (size_t)num_rois * 5 * sizeof(float);
-  const size_t dy_bytes = (size_t)num_rois * channels * pooled_height * pooled_width * sizeof(float);
+  const size_t dy_bytes = (size_t)num_rois * channels * pooled_height * pooled_width * esz;
   CUDA_TRY(st.stage[0].reserve(dy_bytes, stream));
   CUDA_TRY(st.stage[1].reserve(rois_bytes, stream));
   CUDA_TRY(st.stage[2].reserve(dx_bytes, stream));
@@ -656,11 +712,15 @@ MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream_, con
   RoiAlignArgs a = make_args(d_rois, num_rois, n_img, channels, height, width, pooled_height,
                              pooled_width, spatial_scale, sampling_ratio);
   a.aligned = (flags & MOBULA_ROIALIGN_ALIGNED) ? 1 : 0;
-  const int cc = resident_backward_applies(st, a, d_dx, mode, flags) ? host_chunk(channels, dx_bytes, true) : 0;
+  a.top_dtype = top_dtype;
+  a.top_layout = top_layout;
+  const int cc = (top_layout == 0 && resident_backward_applies(st, a, d_dx, mode, flags)) ? host_chunk(channels, dx_bytes, true) : 0;
   if (cc > 0) {
     if ((rc = pipeline_setup(st))) return rc;
     const size_t hw = (size_t)height * width, bins = (size_t)pooled_height * pooled_width;
-    const size_t row_pitch = (size_t)channels * bins * sizeof(float);
+    const size_t row_pitch = (size_t)channels * bins * esz;
+    const char* const h_top = reinterpret_cast<const char*>(top_diff);
+    char* const d_top = reinterpret_cast<char*>(d_dy);
     const size_t img_pitch = (size_t)channels * hw * sizeof(float);
     if (rois_bytes) CUDA_TRY(cudaMemcpyAsync(d_rois, bottom_rois, rois_bytes, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaEventRecord(st.ev_start, stream));
@@ -670,15 +730,16 @@ MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream_, con
     for (int c0 = 0; c0 < channels; c0 += cc, ++k) {
       const int cn = channels - c0 < cc ? channels - c0 : cc;
       if (num_rois > 0)
-        CUDA_TRY(cudaMemcpy2DAsync(d_dy + c0 * bins, row_pitch, top_diff + c0 * bins, row_pitch,
-                                   (size_t)cn * bins * sizeof(float), num_rois, cudaMemcpyHostToDevice, st.s_in));
+        CUDA_TRY(cudaMemcpy2DAsync(d_top + c0 * bins * esz, row_pitch, h_top + c0 * bins * esz, row_pitch,
+                                   (size_t)cn * bins * esz, num_rois, cudaMemcpyHostToDevice, st.s_in));
       if (accumulate && n_img > 0)
         CUDA_TRY(cudaMemcpy2DAsync(d_dx + c0 * hw, img_pitch, bottom_diff + c0 * hw, img_pitch,
                                    (size_t)cn * hw * sizeof(float), n_img, cudaMemcpyHostToDevice, st.s_in));
       CUDA_TRY(cudaEventRecord(st.ev_in[k], st.s_in));
       CUDA_TRY(cudaStreamWaitEvent(stream, st.ev_in[k], 0));
       a.c_count = cn;
-      if ((rc = backward_device(st, device, stream, d_dy + c0 * bins, d_rois, d_dx + c0 * hw, a, mode, flags)))
+      if ((rc = backward_device(st, device, stream, reinterpret_cast<const float*>(d_top + c0 * bins * esz), d_rois,
+                                d_dx + c0 * hw, a, mode, flags)))
         return rc;
       CUDA_TRY(cudaEventRecord(st.ev_done[k], stream));
       CUDA_TRY(cudaStreamWaitEvent(st.s_out, st.ev_done[k], 0));
@@ -698,6 +759,27 @@ MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream_, con
   if (dx_bytes) CUDA_TRY(cudaMemcpyAsync(bottom_diff, d_dx, dx_bytes, cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
   return MOBULA_OK;
+}
+
+MOBULA_EXPORT int mobula_roialign_backward_f32(int device_id, void* stream, const float* top_diff,
+                                               const float* bottom_rois, float* bottom_diff,
+                                               int num_rois, int num_images, int channels,
+                                               int height, int width, int pooled_height,
+                                               int pooled_width, float spatial_scale,
+                                               int sampling_ratio, int mode, unsigned flags) {
+  return backward_impl(device_id, stream, top_diff, MOBULA_DTYPE_F32, MOBULA_LAYOUT_RCHW, bottom_rois, bottom_diff,
+                       num_rois, num_images, channels, height, width, pooled_height, pooled_width, spatial_scale,
+                       sampling_ratio, mode, flags);
+}
+
+MOBULA_EXPORT int mobula_roialign_backward_ex(int device_id, void* stream, const void* top_diff, int top_dtype,
+                                              int top_layout, const float* bottom_rois, float* bottom_diff,
+                                              int num_rois, int num_images, int channels, int height, int width,
+                                              int pooled_height, int pooled_width, float spatial_scale,
+                                              int sampling_ratio, int mode, unsigned flags) {
+  return backward_impl(device_id, stream, static_cast<const float*>(top_diff), top_dtype, top_layout, bottom_rois,
+                       bottom_diff, num_rois, num_images, channels, height, width, pooled_height, pooled_width,
+                       spatial_scale, sampling_ratio, mode, flags);
 }
 
 MOBULA_EXPORT int mobula_roialign_bookkeeping_f32(int device_id, void* stream_, const float* bottom_rois,

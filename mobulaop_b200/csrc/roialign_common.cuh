@@ -9,6 +9,8 @@
 // Reference arithmetic: /root/reference/opzoo/ROIAlign/ROIAlign.cpp:24-65 and
 // /root/reference/opzoo/ROIAlign/bilinear.h:15-54.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -128,6 +130,26 @@ struct CountDiv {
     return pow2 ? __fmul_rn(x, inv) : __fdiv_rn(x, count);
   }
 };
+
+// ---- element type of the pooled tensor (forward output / backward dy) ---------------------------
+// 0 = fp32 (the reference), 1 = fp16, 2 = bf16.  The arithmetic is fp32 whatever
+// the storage type: a result is rounded once (to nearest even) when it is stored, a gradient is
+// widened exactly when it is loaded.
+constexpr int kTopF32 = 0, kTopF16 = 1, kTopBF16 = 2;
+
+__device__ __forceinline__ void store_top(void* base, size_t idx, float v, int dtype) {
+  if (dtype == kTopF32) static_cast<float*>(base)[idx] = v;
+  else if (dtype == kTopF16) static_cast<__half*>(base)[idx] = __float2half_rn(v);
+  else static_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float load_top(const void* base, size_t idx, int dtype) {
+  if (dtype == kTopF32) return __ldg(static_cast<const float*>(base) + idx);
+  if (dtype == kTopF16) return __half2float(__ldg(static_cast<const __half*>(base) + idx));
+  return __bfloat162float(__ldg(static_cast<const __nv_bfloat16*>(base) + idx));
+}
+
+__host__ __device__ inline size_t top_elem_bytes(int dtype) { return dtype == kTopF32 ? 4 : 2; }
 
 // ---- ROI rows grouped by image ----------------------------------------------------------------
 // image of ROI row r, or num_images for a batch index outside [0, N) (such rows read nothing)

@@ -16,6 +16,10 @@ struct RoiAlignArgs {
   float scale;
   int sampling_ratio;
   int aligned;         // half-pixel box coordinates (torchvision aligned=True); sweep / tile kernels only
+  // the pooled tensor (forward output / backward dy): element type 0 fp32 | 1 fp16 | 2 bf16 and
+  // layout 0 [R, C, PH, PW] (the reference) | 1 [R, PH, PW, C] (channel-last); anything but (0, 0)
+  // runs on the sampling_ratio == 2 resident forward (type only), the sweep forward and the pull backward
+  int top_dtype, top_layout;
 };
 
 void count_launch();

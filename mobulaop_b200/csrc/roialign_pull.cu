@@ -75,8 +75,9 @@ struct PullParams {
                          // (a multiple of 16) | pixel & 7 | 8 on the last entry of the pixel; y = weight.
                          // Deterministic mode on adaptive grids: uint4, z = count, w = 1 / count if that is exact, else 0
   unsigned entry_cap;    // entries the array has room for
-  float* dyt;            // [R * PH * PW][cw] channel-last copy of dy
-  const float* dy;
+  float* dyt;            // [R * PH * PW][cw] channel-last fp32 copy of dy
+  const void* dy;
+  int dy_dtype, dy_layout;   // RoiAlignArgs::top_dtype / top_layout of dy
   float* dx;
 };
 
@@ -482,9 +483,31 @@ __device__ __forceinline__ void pull_transpose_block(const PullParams& p, unsign
   const int r = block / groups, c0 = (block - r * groups) * kTrChannels;
   const int nc = min(kTrChannels, p.c_work - c0);          // real channels of this block
   const int ncw = min(kTrChannels, p.cw - c0);             // incl. the zero pad channels
-  const float* src = p.dy + ((size_t)r * p.channels + c0) * B;
+  if (p.dy_layout != 0) {
+    // dy is channel-last already ([R, PH, PW, C], any element type): widen and copy, coalesced both ways
+    const int c = threadIdx.x & (kTrChannels - 1);
+    if (c < ncw)
+      for (int bb = threadIdx.x / kTrChannels; bb < B; bb += 256 / kTrChannels)
+        p.dyt[((size_t)r * B + bb) * p.cw + c0 + c] =
+            c < nc ? load_top(p.dy, ((size_t)r * B + bb) * p.channels + c0 + c, p.dy_dtype) : 0.0f;
+    return;
+  }
+  const size_t src0 = ((size_t)r * p.channels + c0) * B;    // element index of the block's source run
+  const float* src = static_cast<const float*>(p.dy) + src0;
   const int total = nc * B;
-  if (pitch == B && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+  if (p.dy_dtype != kTopF32) {
+    const int dc = 256 / B, db = 256 - dc * B;
+    int c = threadIdx.x / B, bb = threadIdx.x - c * B;
+    for (int i = threadIdx.x; i < total; i += 256) {
+      s_t[c * pitch + bb] = load_top(p.dy, src0 + i, p.dy_dtype);
+      c += dc;
+      bb += db;
+      if (bb >= B) {
+        bb -= B;
+        ++c;
+      }
+    }
+  } else if (pitch == B && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
     // odd B: the shared-memory image is the source run itself, copied 16 bytes at a time
     const int quads = total >> 2;
     float4* dst4 = reinterpret_cast<float4*>(s_t);
@@ -878,6 +901,8 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
   p.entry_cap = (unsigned)(L.entry_cap > 0xffffffffull ? 0xffffffffull : L.entry_cap);
   p.dyt = reinterpret_cast<float*>(base + L.dyt);
   p.dy = dy;
+  p.dy_dtype = a.top_dtype;
+  p.dy_layout = a.top_layout;
   p.dx = dx;
 
   cudaError_t e = cudaMemsetAsync(p.need, 0, sizeof(unsigned long long), stream);

@@ -192,13 +192,13 @@ __device__ __forceinline__ void cta_share(long long total, long long& u0, long l
 // are zero (the reference would read out of bounds, ROIAlign.cpp:43-44).
 __device__ __forceinline__ void zero_rows_of_invalid_rois(float* __restrict__ out, const int* __restrict__ order,
                                                           const int* __restrict__ img_start, int num_images,
-                                                          long long row_stride, long long row_count) {
+                                                          long long row_stride, long long row_count, int odt = kTopF32) {
   const int i0 = __ldg(img_start + num_images), i1 = __ldg(img_start + num_images + 1);
   long long z0, z1;
   cta_share((long long)(i1 - i0) * row_count, z0, z1);
   for (long long z = z0 + threadIdx.x; z < z1; z += blockDim.x) {
     const int jj = (int)(z / row_count);
-    out[(size_t)__ldg(order + i0 + jj) * row_stride + (size_t)(z - jj * row_count)] = 0.0f;
+    store_top(out, (size_t)__ldg(order + i0 + jj) * row_stride + (size_t)(z - jj * row_count), 0.0f, odt);
   }
 }
 
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(kFwd2Threads, 1)
 resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                      const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
                      int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w,
-                     int vec16) {
+                     int vec16, int odt) {
   ptx::chain_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* plane = reinterpret_cast<float*>(smem_raw);
@@ -434,7 +434,7 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
   __syncthreads();
   if (!ACC)
     zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
-                              (long long)c_count * bins);
+                              (long long)c_count * bins, odt);
 
   // which of this lane's results are outputs: the first sample column of a bin, of an
   // existing bin row
@@ -519,7 +519,7 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
           if (stores[ch] && row_ok) {
             float* o = optr + it * pooled_w + 8 * ch;
             if (ACC) *o = __fadd_rn(*o, y);
-            else *o = y;
+            else store_top(out, (size_t)(o - out), y, odt);
           }
         }
       }
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(kFwd2Threads, 1)
 resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                       const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
                       int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w,
-                      int vec16) {
+                      int vec16, int odt) {
   ptx::chain_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* plane = reinterpret_cast<float*>(smem_raw);
@@ -578,7 +578,7 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
   __syncthreads();
   if (!ACC)
     zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
-                              (long long)c_count * bins);
+                              (long long)c_count * bins, odt);
 
   bool stores[NCH];
 #pragma unroll
@@ -668,7 +668,7 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
           if (stores[ch] && have) {
             float* o = optr + it * pooled_w + 8 * ch;
             if (ACC) *o = __fadd_rn(*o, y);
-            else *o = y;
+            else store_top(out, (size_t)(o - out), y, odt);
           }
         }
       }
@@ -730,7 +730,7 @@ template <int ITERS, int NCH, bool ACC>
 __global__ void __launch_bounds__(kFwd2Threads, 1)
 resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                       const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
-                      int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w) {
+                      int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w, int odt) {
   ptx::chain_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* plane = reinterpret_cast<float2*>(smem_raw);
@@ -748,7 +748,7 @@ resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, c
   __syncthreads();
   if (!ACC)
     zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
-                              (long long)c_count * bins);
+                              (long long)c_count * bins, odt);
 
   bool stores[NCH];
 #pragma unroll
@@ -832,8 +832,8 @@ resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, c
               o[0] = __fadd_rn(o[0], y0);
               if (two) o[bins] = __fadd_rn(o[bins], y1);
             } else {
-              o[0] = y0;
-              if (two) o[bins] = y1;
+              store_top(out, (size_t)(o - out), y0, odt);
+              if (two) store_top(out, (size_t)(o - out) + bins, y1, odt);
             }
           }
         }
@@ -847,7 +847,7 @@ template <int PH, int NCH, bool ACC>
 __global__ void __launch_bounds__(kFwd2Threads, 1)
 resident_fwd2pr_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                       const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
-                      int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w) {
+                      int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w, int odt) {
   ptx::chain_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* plane = reinterpret_cast<float2*>(smem_raw);
@@ -867,7 +867,7 @@ resident_fwd2pr_kernel(const float* __restrict__ data, float* __restrict__ out, 
   __syncthreads();
   if (!ACC)
     zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
-                              (long long)c_count * bins);
+                              (long long)c_count * bins, odt);
 
   bool stores[NCH];
 #pragma unroll
@@ -962,8 +962,8 @@ resident_fwd2pr_kernel(const float* __restrict__ data, float* __restrict__ out, 
               o[0] = __fadd_rn(o[0], y0);
               if (two) o[bins] = __fadd_rn(o[bins], y1);
             } else {
-              o[0] = y0;
-              if (two) o[bins] = y1;
+              store_top(out, (size_t)(o - out), y0, odt);
+              if (two) store_top(out, (size_t)(o - out) + bins, y1, odt);
             }
           }
         }
@@ -2061,7 +2061,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
       if (e != cudaSuccess) return e;                                                                \
       chained_launch(resident_fwd2p_kernel<ITERS, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream,          \
           data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,     \
-          plan.pitch, a.pooled_h, a.pooled_w);                                                       \
+          plan.pitch, a.pooled_h, a.pooled_w, a.top_dtype);                                          \
       break;                                                                                         \
     }                                                                                                \
     e = resident_grid(resident_fwd2_kernel<ITERS, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms,   \
@@ -2069,7 +2069,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     if (e != cudaSuccess) return e;                                                                  \
     chained_launch(resident_fwd2_kernel<ITERS, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream,             \
         data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,       \
-        plan.pitch, a.pooled_h, a.pooled_w, plan.vec16);                                          \
+        plan.pitch, a.pooled_h, a.pooled_w, plan.vec16, a.top_dtype);                             \
   } while (0)
 #define MOBULA_FWD2_NCH(ITERS, NCH)                  \
   do {                                               \
@@ -2090,14 +2090,14 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
       if (e != cudaSuccess) return e;                                                                \
       chained_launch(resident_fwd2pr_kernel<PH, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream, \
           data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,     \
-          plan.pitch, a.pooled_h, a.pooled_w);                                                       \
+          plan.pitch, a.pooled_h, a.pooled_w, a.top_dtype);                                          \
       break;                                                                                         \
     }                                                                                                \
     e = resident_grid(resident_fwd2r_kernel<PH, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms, work, &grid); \
     if (e != cudaSuccess) return e;                                                                  \
     chained_launch(resident_fwd2r_kernel<PH, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream,   \
         data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,       \
-        plan.pitch, a.pooled_h, a.pooled_w, plan.vec16);                                             \
+        plan.pitch, a.pooled_h, a.pooled_w, plan.vec16, a.top_dtype);                                \
   } while (0)
 #define MOBULA_FWD2R_PH(PH)                                          \
   do {                                                               \

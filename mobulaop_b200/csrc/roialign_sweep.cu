@@ -98,6 +98,7 @@ struct SweepParams {
   int sampling_ratio;
   int aligned;
   int accumulate;
+  int top_dtype, top_layout;   // element type / layout of `out` (RoiAlignArgs::top_dtype, top_layout)
   const float* data;
   // shared-memory geometry
   int pitch;             // floats between channels of a ring row (odd, >= width)
@@ -153,9 +154,14 @@ __global__ void __launch_bounds__(256) sweep_roi_kernel(SweepParams p) {
     if (n < 0) {
       // a ROI that points at no image reads nothing: its output rows are zero
       if (!p.accumulate && !p.tables_only) {
-        const size_t per = (size_t)p.c_work * PH * PW;
-        float* o = p.out + (size_t)r * p.channels * PH * PW;
-        for (size_t i = lane; i < per; i += 32) o[i] = 0.0f;
+        const size_t row0 = (size_t)r * p.channels * PH * PW;
+        if (p.top_layout == 0) {
+          const size_t per = (size_t)p.c_work * PH * PW;
+          for (size_t i = lane; i < per; i += 32) store_top(p.out, row0 + i, 0.0f, p.top_dtype);
+        } else {
+          for (int b = 0; b < PH * PW; ++b)
+            for (int c = lane; c < p.c_work; c += 32) store_top(p.out, row0 + (size_t)b * p.channels + c, 0.0f, p.top_dtype);
+        }
       }
       if (lane == 0) {
         h->ncols = 0;
@@ -627,21 +633,33 @@ sweep_fwd_kernel(const SweepParams p) {
           const float count = __uint_as_float(gc.y);
           const bool pow2 = (cnt_i & (cnt_i - 1)) == 0;
           const float inv = __fdiv_rn(1.0f, count);
-          __syncwarp();
-#pragma unroll
-          for (int pw = 0; pw < PWT; ++pw)
-            stage[lane * p.pwp + pw] = pow2 ? __fmul_rn(acc[pw], inv) : __fdiv_rn(acc[pw], count);
-          __syncwarp();
-          float* o = p.out + ((size_t)roi * p.channels + c0) * bins + ph * PWT;
           const int cvalid = min(32, p.c_work - c0);
+          if (p.top_layout != 0) {
+            // channel-last output [R, PH, PW, C]: the lanes ARE the channels, one coalesced store per bin
+            const size_t o = (((size_t)roi * PH + ph) * PWT) * p.channels + c0 + lane;
+            if (lane < cvalid) {
 #pragma unroll
-          for (int k = 0; k < PWT; ++k) {
-            const int f = k * 32 + lane;
-            const int c = f / PWT, pw = f - c * PWT;
-            if (c < cvalid) {
-              const float v = stage[c * p.pwp + pw];
-              float* dst = o + c * bins + pw;
-              *dst = p.accumulate ? __fadd_rn(*dst, v) : v;
+              for (int pw = 0; pw < PWT; ++pw)
+                store_top(p.out, o + (size_t)pw * p.channels, pow2 ? __fmul_rn(acc[pw], inv) : __fdiv_rn(acc[pw], count),
+                          p.top_dtype);
+            }
+          } else {
+            __syncwarp();
+#pragma unroll
+            for (int pw = 0; pw < PWT; ++pw)
+              stage[lane * p.pwp + pw] = pow2 ? __fmul_rn(acc[pw], inv) : __fdiv_rn(acc[pw], count);
+            __syncwarp();
+            const size_t o = ((size_t)roi * p.channels + c0) * bins + ph * PWT;
+#pragma unroll
+            for (int k = 0; k < PWT; ++k) {
+              const int f = k * 32 + lane;
+              const int c = f / PWT, pw = f - c * PWT;
+              if (c < cvalid) {
+                const float v = stage[c * p.pwp + pw];
+                const size_t at = o + (size_t)c * bins + pw;
+                if (p.accumulate) p.out[at] = __fadd_rn(p.out[at], v);      // fp32 only (checked by the caller)
+                else store_top(p.out, at, v, p.top_dtype);
+              }
             }
           }
         } else {
@@ -992,6 +1010,8 @@ cudaError_t launch_fwd_sweep(const RoiAlignArgs& a, const SweepPlan& plan, void*
   p.sampling_ratio = a.sampling_ratio;
   p.aligned = a.aligned;
   p.accumulate = accumulate;
+  p.top_dtype = a.top_dtype;
+  p.top_layout = a.top_layout;
   p.data = data;
   p.pitch = plan.pitch;
   p.fill_mode = (a.width % 4 == 0 && (reinterpret_cast<uintptr_t>(data) & 15u) == 0) ? 0 : 1;

@@ -16,7 +16,9 @@ returns when the result is in host memory.
 Extra keyword-only arguments (absent from the reference): `mode` ('atomic' |
 'deterministic', backward only), `accumulate` (default True for backward = the
 reference semantics "adds into a caller-zeroed buffer", False for forward), `algo`,
-`aligned` (half-pixel box coordinates = torchvision.ops.roi_align(aligned=True)).
+`aligned` (half-pixel box coordinates = torchvision.ops.roi_align(aligned=True)), `layout`
+('RCHW' = the reference's [R, C, PH, PW], 'RHWC' = channel-last [R, PH, PW, C]); the pooled tensor
+(`top_data` / `top_diff`) may be float16 or bfloat16 -- the arithmetic stays fp32.
 """
 import ctypes
 
@@ -46,6 +48,10 @@ _SIGNATURES['im2col'] = [('n', _INT), ('data_im', _IN_T)] + _CONV_GEOM + [('data
 _SIGNATURES['col2im'] = [('n', _INT), ('data_col', _IN_T)] + _CONV_GEOM + [('data_im', _OUT_T)]
 
 _SUPPORTED_T = (ctypes.c_float,)
+# the pooled tensor of ROIAlign may be stored in half precision (include/mobula_roialign.h, `_ex` entry points)
+_TOP_NAMES = ('top_data', 'top_diff')
+_TOP_DTYPES = {ctypes.c_float: _native.DTYPE_F32, glue.common.c_half: _native.DTYPE_F16,
+               glue.common.c_bfloat16: _native.DTYPE_BF16}
 
 
 class _TensorArg(object):
@@ -97,6 +103,7 @@ class MobulaFunc(object):
         accumulate = kwargs.pop('accumulate', None)
         algo = kwargs.pop('algo', None)
         aligned = bool(kwargs.pop('aligned', False))
+        layout = kwargs.pop('layout', None)
         args = self._collect(args, kwargs)
         if kwargs:
             raise TypeError('%s: unexpected arguments %s' % (self.name, sorted(kwargs)))
@@ -115,7 +122,9 @@ class MobulaFunc(object):
                                     'tensor, got %s' % (self.name, name, type(var)))
                 view = glue_mod.Tensor(var)
                 ctype = view.ctype
-                if bound_t is None:
+                if name in _TOP_NAMES and ctype in _TOP_DTYPES:
+                    values['__top_dtype__'] = _TOP_DTYPES[ctype]      # fp32 arithmetic, typed storage
+                elif bound_t is None:
                     bound_t = ctype
                 elif ctype is not bound_t:
                     raise TypeError('Expected Type %s instead of %s for `%s`' % (bound_t, ctype, name))
@@ -139,9 +148,13 @@ class MobulaFunc(object):
             for t in tensors.values():
                 if t.view.dev_id is None:
                     raise ValueError('%s: host and device tensors mixed in one call' % self.name)
+        if layout is not None:
+            if layout not in _native.LAYOUTS:
+                raise ValueError("layout must be 'RCHW' ([R, C, PH, PW]) or 'RHWC' ([R, PH, PW, C])")
+            values['__top_layout__'] = _native.LAYOUTS[layout]
         if self.name in ('im2col', 'col2im'):
-            if mode is not None or accumulate is not None or algo is not None or aligned:
-                raise TypeError('%s takes no mode / accumulate / algo / aligned' % self.name)
+            if mode is not None or accumulate is not None or algo is not None or aligned or layout is not None:
+                raise TypeError('%s takes no mode / accumulate / algo / aligned / layout' % self.name)
             _launch_conv(self.name, values, tensors, -1 if dev_id is None else dev_id, stream, host)
         else:
             launcher = _launch_forward if self.name == 'roi_align_forward' else _launch_backward
@@ -175,10 +188,11 @@ def _launch_forward(v, t, dev_id, stream, host, mode, accumulate, algo, aligned=
     shape = data.view.shape
     num_images = shape[0] if len(shape) == 4 else -1
     flags = _native.make_flags(accumulate=bool(accumulate), host=host, algo=algo, aligned=aligned)
-    _native.check(lib.mobula_roialign_forward_f32(
+    _native.check(lib.mobula_roialign_forward_ex(
         dev_id, _vp(stream), _vp(data.resolve(False)), _vp(rois.resolve(False)),
-        _vp(out.resolve(True)), num_rois, num_images, v['channels'], v['height'], v['width'],
-        v['pooled_height'], v['pooled_width'], v['spatial_scale'], v['sampling_ratio'], flags))
+        _vp(out.resolve(True)), v.get('__top_dtype__', 0), v.get('__top_layout__', 0), num_rois, num_images,
+        v['channels'], v['height'], v['width'], v['pooled_height'], v['pooled_width'], v['spatial_scale'],
+        v['sampling_ratio'], flags))
 
 
 def _launch_backward(v, t, dev_id, stream, host, mode, accumulate, algo, aligned=False):
@@ -194,9 +208,9 @@ def _launch_backward(v, t, dev_id, stream, host, mode, accumulate, algo, aligned
     shape = dx.view.shape
     num_images = shape[0] if len(shape) == 4 else -1
     flags = _native.make_flags(accumulate=bool(accumulate), host=host, algo=algo, aligned=aligned)
-    _native.check(lib.mobula_roialign_backward_f32(
-        dev_id, _vp(stream), _vp(dy.resolve(False)), _vp(rois.resolve(False)),
-        _vp(dx.resolve(True)), num_rois, num_images, v['channels'], v['height'], v['width'],
+    _native.check(lib.mobula_roialign_backward_ex(
+        dev_id, _vp(stream), _vp(dy.resolve(False)), v.get('__top_dtype__', 0), v.get('__top_layout__', 0),
+        _vp(rois.resolve(False)), _vp(dx.resolve(True)), num_rois, num_images, v['channels'], v['height'], v['width'],
         v['pooled_height'], v['pooled_width'], v['spatial_scale'], v['sampling_ratio'],
         _native.BWD_DETERMINISTIC if mode == 'deterministic' else _native.BWD_ATOMIC, flags))
 

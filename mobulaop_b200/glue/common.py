@@ -154,7 +154,16 @@ TENSOR_VIEWS = dict(
     dx=property(lambda self: _first(self.in_grad)), dy=property(lambda self: _first(self.out_grad)),
 )
 
+class c_half(ctypes.c_uint16):
+    """IEEE binary16 storage (no ctypes equivalent); only the pooled tensor of ROIAlign may have it."""
+
+
+class c_bfloat16(ctypes.c_uint16):
+    """bfloat16 storage."""
+
+
 _NP_NAME_TO_CTYPE = {
+    'float16': c_half,
     'int8': ctypes.c_int8, 'int16': ctypes.c_int16, 'int32': ctypes.c_int32,
     'int64': ctypes.c_int64, 'float32': ctypes.c_float, 'float64': ctypes.c_double,
 }

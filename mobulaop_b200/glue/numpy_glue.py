@@ -59,7 +59,8 @@ def make_array_op_class(op, name, xp, suffix):
         dtype = self.in_data[0].dtype
         self.req = ['write'] * len(self.in_data)
         out_shapes = self.infer_shape(shapes_of(self.in_data))[1]
-        self.out_data = [new_empty(tuple(s), dtype) for s in out_shapes]
+        odt = self.infer_out_dtype(dtype, xp) if hasattr(self, 'infer_out_dtype') else dtype
+        self.out_data = [new_empty(tuple(s), odt) for s in out_shapes]
         result = self._forward(*inputs)
         if result is not None:
             result = result if isinstance(result, (list, tuple)) else [result]
@@ -79,7 +80,7 @@ def make_array_op_class(op, name, xp, suffix):
             in_grad = [in_grad]
         self.in_grad = in_grad
         if out_grad is None:
-            out_grad = [xp.ones(d.shape, dtype=dtype) for d in self.out_data]
+            out_grad = [xp.ones(d.shape, dtype=d.dtype) for d in self.out_data]
         elif not isinstance(out_grad, (list, tuple)):
             out_grad = [out_grad]
         self.out_grad = out_grad

@@ -18,13 +18,13 @@ import ctypes
 import torch
 from torch.autograd.function import once_differentiable
 
-from .common import (MobulaTensor, TENSOR_VIEWS, assign, forward_input_names, shapes_of,
+from .common import (MobulaTensor, TENSOR_VIEWS, assign, c_bfloat16, c_half, forward_input_names, shapes_of,
                      split_inputs)
 
 F = torch
 
 _CTYPES = {torch.int32: ctypes.c_int, torch.float32: ctypes.c_float, torch.float64: ctypes.c_double,
-           torch.int64: ctypes.c_int64}
+           torch.int64: ctypes.c_int64, torch.float16: c_half, torch.bfloat16: c_bfloat16}
 
 
 class TorchTensor(MobulaTensor):
@@ -80,7 +80,9 @@ def _make_classes(op, name):
             dtype = first.dtype if first is not None else torch.float32
             device = first.device if first is not None else torch.device('cpu')
             out_shapes = record.infer_shape(shapes_of(inputs))[1]
-            record.out_data = [torch.empty(tuple(s), dtype=dtype, device=device) for s in out_shapes]
+            # an operator may store its outputs in another element type (ROIAlign: out_dtype)
+            odt = record.infer_out_dtype(dtype, torch) if hasattr(record, 'infer_out_dtype') else dtype
+            record.out_data = [torch.empty(tuple(s), dtype=odt, device=device) for s in out_shapes]
             result = record._forward(*inputs)
             if result is not None:
                 result = result if isinstance(result, (list, tuple)) else [result]

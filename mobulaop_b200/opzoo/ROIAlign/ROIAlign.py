@@ -8,7 +8,8 @@ coordinates, output [R, C, PH, PW].  Write requests follow the reference: 'null'
 'add' accumulates, anything else overwrites.  The gradient with respect to `rois` is zero.
 
 Beyond the reference: `deterministic` (None = follow mobula.config.ROIALIGN_DETERMINISTIC)
-selects the bit-reproducible backward; `aligned=True` uses half-pixel box coordinates (the
+selects the bit-reproducible backward; `out_dtype` / `layout` store the pooled tensor in
+float16 / bfloat16 and / or channel-last [R, PH, PW, C] (fp32 arithmetic, one rounding at the store); `aligned=True` uses half-pixel box coordinates (the
 convention of torchvision.ops.roi_align(aligned=True) and detectron2's ROIAlignV2); the dX zero-fill of the reference
 (ROIAlign.py:33-34, a separate full-tensor pass) is done inside the native call.
 """
@@ -18,7 +19,8 @@ from mobulaop_b200.const import req
 
 @mobula.op.register
 class ROIAlign:
-    def __init__(self, pooled_size, spatial_scale, sampling_ratio, deterministic=None, aligned=False):
+    def __init__(self, pooled_size, spatial_scale, sampling_ratio, deterministic=None, aligned=False,
+                 out_dtype=None, layout='RCHW'):
         if isinstance(pooled_size, int):
             pooled_size = (pooled_size, pooled_size)
         assert len(pooled_size) == 2, 'pooled_size is (pooled_height, pooled_width)'
@@ -27,6 +29,12 @@ class ROIAlign:
         self.sampling_ratio = int(sampling_ratio)
         self.deterministic = deterministic
         self.aligned = bool(aligned)
+        # storage of the pooled tensor: None = the input's type; 'float16' / 'bfloat16' (or the
+        # framework's dtype object) halve its bytes, the arithmetic stays fp32; layout 'RHWC' makes
+        # it channel-last [R, PH, PW, C] for consumers that want the channels innermost
+        self.out_dtype = out_dtype
+        assert layout in ('RCHW', 'RHWC'), "layout is 'RCHW' or 'RHWC'"
+        self.layout = layout
 
     @staticmethod
     def _numel(t):
@@ -42,7 +50,7 @@ class ROIAlign:
         mobula.func.roi_align_forward(
             self._numel(out), data, self.spatial_scale, data.shape[1], data.shape[2],
             data.shape[3], self.pooled_size[0], self.pooled_size[1], self.sampling_ratio, rois, out,
-            accumulate=self.req[0] == req.add, aligned=self.aligned)
+            accumulate=self.req[0] == req.add, aligned=self.aligned, layout=self.layout)
 
     def backward(self, dy):
         if self.req[0] != req.null:
@@ -53,7 +61,8 @@ class ROIAlign:
             mobula.func.roi_align_backward(
                 self._numel(dy), dy, self.spatial_scale, data.shape[1], data.shape[2],
                 data.shape[3], self.pooled_size[0], self.pooled_size[1], self.sampling_ratio,
-                self.dX[0], rois, accumulate=self.req[0] == req.add, mode=mode, aligned=self.aligned)
+                self.dX[0], rois, accumulate=self.req[0] == req.add, mode=mode, aligned=self.aligned,
+                layout=self.layout)
         if len(self.req) > 1 and self.req[1] not in (req.null, req.add):
             self.dX[1][:] = 0
 
@@ -62,5 +71,15 @@ class ROIAlign:
         assert len(dshape) == 4
         assert len(rshape) == 2
         assert rshape[1] == 5
-        oshape = [rshape[0], dshape[1], self.pooled_size[0], self.pooled_size[1]]
+        if self.layout == 'RHWC':
+            oshape = [rshape[0], self.pooled_size[0], self.pooled_size[1], dshape[1]]
+        else:
+            oshape = [rshape[0], dshape[1], self.pooled_size[0], self.pooled_size[1]]
         return [dshape, rshape], [oshape]
+
+    def infer_out_dtype(self, in_dtype, F):
+        if self.out_dtype is None:
+            return in_dtype
+        if isinstance(self.out_dtype, str):
+            return getattr(F, self.out_dtype)
+        return self.out_dtype

@@ -52,6 +52,10 @@ def parse_args():
     ap.add_argument('--e2e-torch-steps', type=int, default=200)
     ap.add_argument('--mode', default='atomic', choices=['atomic', 'deterministic'])
     ap.add_argument('--algo', default='auto', choices=['auto', 'gather', 'plane', 'resident', 'sweep', 'pull'])
+    ap.add_argument('--top-dtype', default='float32', choices=['float32', 'float16', 'bfloat16'],
+                    help='storage type of the pooled tensor (output / dy); the arithmetic is fp32')
+    ap.add_argument('--layout', default='RCHW', choices=['RCHW', 'RHWC'],
+                    help='layout of the pooled tensor: [R,C,PH,PW] (reference) or channel-last [R,PH,PW,C]')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=5)
@@ -204,7 +208,8 @@ def run_reference_arm(args):
 class DeviceRun(object):
     """One rank's share of a workload, resident in HBM, launched through the C-ABI."""
 
-    def __init__(self, lib, torch, dev, local_rank, wl, rois_np, mode, algo, seed):
+    def __init__(self, lib, torch, dev, local_rank, wl, rois_np, mode, algo, seed, top_dtype='float32',
+                 layout='RCHW'):
         import ctypes
         from mobulaop_b200 import _native
         self.lib, self.torch, self.dev, self.wl = lib, torch, dev, wl
@@ -216,9 +221,13 @@ class DeviceRun(object):
                                      device=dev).reshape(wl.data_shape)
         else:
             self.data = torch.randn(wl.data_shape, dtype=torch.float32, device=dev, generator=gen)
-        self.dy = torch.randn(wl.out_shape, dtype=torch.float32, device=dev, generator=gen)
+        tdt = getattr(torch, top_dtype)
+        oshape = wl.out_shape if layout == 'RCHW' else (wl.R,) + tuple(wl.pooled) + (wl.C,)
+        self.dy = torch.randn(oshape, dtype=torch.float32, device=dev, generator=gen).to(tdt)
         self.rois = torch.from_numpy(rois_np).to(dev)
-        self.out = torch.empty(wl.out_shape, dtype=torch.float32, device=dev)
+        self.out = torch.empty(oshape, dtype=tdt, device=dev)
+        self.top = (dict(float32=0, float16=1, bfloat16=2)[top_dtype], dict(RCHW=0, RHWC=1)[layout])
+        self.top_bytes = 4 if top_dtype == 'float32' else 2
         self.dx = torch.empty(wl.data_shape, dtype=torch.float32, device=dev)
         self.stream = torch.cuda.current_stream(dev)
         self.sp = ctypes.c_void_p(self.stream.cuda_stream)
@@ -229,14 +238,16 @@ class DeviceRun(object):
 
     def fwd(self):
         wl, vp = self.wl, self._vp
-        self._native.check(self.lib.mobula_roialign_forward_f32(
-            self.local_rank, self.sp, vp(self.data), vp(self.rois), vp(self.out), wl.R, wl.N, wl.C,
+        self._native.check(self.lib.mobula_roialign_forward_ex(
+            self.local_rank, self.sp, vp(self.data), vp(self.rois), vp(self.out), self.top[0], self.top[1],
+            wl.R, wl.N, wl.C,
             wl.H, wl.W, wl.pooled[0], wl.pooled[1], wl.scale, wl.sampling_ratio, self.flags))
 
     def bwd(self):
         wl, vp = self.wl, self._vp
-        self._native.check(self.lib.mobula_roialign_backward_f32(
-            self.local_rank, self.sp, vp(self.dy), vp(self.rois), vp(self.dx), wl.R, wl.N, wl.C,
+        self._native.check(self.lib.mobula_roialign_backward_ex(
+            self.local_rank, self.sp, vp(self.dy), self.top[0], self.top[1], vp(self.rois), vp(self.dx),
+            wl.R, wl.N, wl.C,
             wl.H, wl.W, wl.pooled[0], wl.pooled[1], wl.scale, wl.sampling_ratio, self.mode, self.flags))
 
     def free(self):
@@ -294,8 +305,8 @@ def rank_stats(torch, dist, dev, world, local):
     return allr
 
 
-def roofline_record(wl, res, peak, peak_src, traffic):
-    b_fwd, b_bwd = wl.bytes_forward(), wl.bytes_backward()
+def roofline_record(wl, res, peak, peak_src, traffic, top_bytes=4):
+    b_fwd, b_bwd = wl.bytes_forward(top_bytes=top_bytes), wl.bytes_backward(top_bytes=top_bytes)
     fwd_ms, bwd_ms, step_ms = res['fwd_ms'], res['bwd_ms'], res['step_ms']
     if bwd_ms >= fwd_ms:
         kname, kbytes, kms = 'backward (%s)' % res['algo_bwd'], b_bwd, bwd_ms
@@ -371,7 +382,8 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     K, W = max(args.steps, 1), max(args.warmup, 3)
-    run = DeviceRun(lib, torch, dev, local_rank, wl, shard.rois, args.mode, args.algo, 1234 + rank)
+    run = DeviceRun(lib, torch, dev, local_rank, wl, shard.rois, args.mode, args.algo, 1234 + rank,
+                    args.top_dtype, args.layout)
     res = timed_steps(run, flush_l2, barrier, K, W, clocks_index=local_rank)
     allr = rank_stats(torch, dist, dev, world, [res['step_ms'], res['fwd_ms'], res['bwd_ms'],
                                                 float(res['launches'])])
@@ -382,7 +394,8 @@ def run_ours(args):
 
     peak, peak_src = measured_peaks()
     traffic = load_traffic()
-    roofline = roofline_record(wl, res, peak, peak_src, traffic)      # this rank's launches
+    run_top_bytes = run.top_bytes
+    roofline = roofline_record(wl, res, peak, peak_src, traffic, run_top_bytes)      # this rank's launches
 
     # ---- end to end through the public API --------------------------------------------------
     e2e = e2e_torch = None
@@ -416,11 +429,11 @@ def run_ours(args):
             cpu = dict(value=None, unit=UNIT, cores=0, kind='unavailable', sample=str(err))
 
     if rank == 0:
-        b_step = wl.bytes_forward() + wl.bytes_backward()
+        b_step = wl.bytes_forward(top_bytes=run_top_bytes) + wl.bytes_backward(top_bytes=run_top_bytes)
         details = dict(
             images_total=glob.N, rois_total=total_rois, images_per_rank=wl.N, rois_per_rank=wl.R,
             parallelism='roi-shard-by-image x%d (%s scaling)' % (world, args.scaling),
-            backward_mode=args.mode, algo=args.algo,
+            backward_mode=args.mode, algo=args.algo, pooled_tensor=dict(dtype=args.top_dtype, layout=args.layout),
             shard_ms=dict(max=step_ms, mean=float(allr[:, 0].mean()), per_rank=[float(v) for v in allr[:, 0]]),
             fwd_ms_max=fwd_max, bwd_ms_max=bwd_max, rank0_step_spread=res['spread'],
             l2='256 MB buffer written, then another 256 MB read, between timed steps (outside the CUDA '
@@ -454,7 +467,9 @@ def run_e2e_torch(args, wl, run, world, dev, total_rois):
     def step():
         x.grad = None
         y = mobula.op.ROIAlign(x, run.rois, pooled_size=wl.pooled, spatial_scale=wl.scale,
-                               sampling_ratio=wl.sampling_ratio, deterministic=deterministic)
+                               sampling_ratio=wl.sampling_ratio, deterministic=deterministic,
+                               out_dtype=None if args.top_dtype == 'float32' else args.top_dtype,
+                               layout=args.layout)
         y.backward(run.dy)
 
     with mobula.config.TempConfig(ROIALIGN_ALGO=args.algo):
@@ -491,27 +506,34 @@ def run_e2e(args, wl, shard, world, dev, total_rois):
     from mobulaop_b200 import _native
     lib = _native.load()
     mobula.op.load('ROIAlign')
+    if args.top_dtype == 'bfloat16':
+        return None                     # NumPy has no bfloat16: the host-buffer API takes float32 / float16
 
-    def pinned(shape):
+    def pinned(shape, dtype=np.float32):
         n = int(np.prod(shape))
-        ptr = lib.mobula_host_alloc(n * 4)
+        nbytes = n * np.dtype(dtype).itemsize
+        ptr = lib.mobula_host_alloc(nbytes)
         if not ptr:
             raise MemoryError('mobula_host_alloc')
-        buf = (ctypes.c_float * n).from_address(ptr)
-        return np.frombuffer(buf, dtype=np.float32).reshape(shape), ptr
+        buf = (ctypes.c_char * nbytes).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(99)
+    tdt = np.dtype(args.top_dtype)
+    oshape = wl.out_shape if args.layout == 'RCHW' else (wl.R,) + tuple(wl.pooled) + (wl.C,)
     data, p0 = pinned(wl.data_shape)
-    dy, p1 = pinned(wl.out_shape)
+    dy, p1 = pinned(oshape, tdt)
     # synthetic N(0,1) inputs, generated on the device and copied into the pinned host arrays
     torch.from_numpy(data).copy_(torch.randn(wl.data_shape, dtype=torch.float32, device=dev, generator=gen))
-    torch.from_numpy(dy).copy_(torch.randn(wl.out_shape, dtype=torch.float32, device=dev, generator=gen))
+    torch.from_numpy(dy).copy_(torch.randn(oshape, dtype=torch.float32, device=dev, generator=gen))
     torch.cuda.empty_cache()
     rois = shard.rois
     op = mobula.op.ROIAlign[np.ndarray](pooled_size=wl.pooled, spatial_scale=wl.scale,
                                         sampling_ratio=wl.sampling_ratio,
-                                        deterministic=args.mode == 'deterministic')
+                                        deterministic=args.mode == 'deterministic',
+                                        out_dtype=None if args.top_dtype == 'float32' else args.top_dtype,
+                                        layout=args.layout)
     with mobula.config.TempConfig(ROIALIGN_ALGO=args.algo):
         for _ in range(2):
             y = op(data, rois)

@@ -84,6 +84,8 @@ class MobulaFunc(object):
         self.name = name
         self.params = list(params)
         self.arg_names = [p[0] for p in self.params]
+        self._conv = name in ('im2col', 'col2im')
+        self._launcher = None if self._conv else (_launch_forward if name == 'roi_align_forward' else _launch_backward)
 
     def __repr__(self):
         return '<mobula.func.%s(%s)>' % (self.name, ', '.join('%s %s' % (k, n) for n, k in self.params))
@@ -99,69 +101,77 @@ class MobulaFunc(object):
         return args
 
     def __call__(self, *args, **kwargs):
-        mode = kwargs.pop('mode', None)
-        accumulate = kwargs.pop('accumulate', None)
-        algo = kwargs.pop('algo', None)
-        aligned = bool(kwargs.pop('aligned', False))
-        layout = kwargs.pop('layout', None)
-        args = self._collect(args, kwargs)
+        # (this is the per-call dispatch path: plain loops and locals, no helper objects)
         if kwargs:
-            raise TypeError('%s: unexpected arguments %s' % (self.name, sorted(kwargs)))
+            mode = kwargs.pop('mode', None)
+            accumulate = kwargs.pop('accumulate', None)
+            algo = kwargs.pop('algo', None)
+            aligned = bool(kwargs.pop('aligned', False))
+            layout = kwargs.pop('layout', None)
+        else:
+            mode = accumulate = algo = layout = None
+            aligned = False
+        if kwargs or len(args) != len(self.params):
+            args = self._collect(args, kwargs)
+            if kwargs:
+                raise TypeError('%s: unexpected arguments %s' % (self.name, sorted(kwargs)))
 
         values = {}
         tensors = {}
         bound_t = None
         dev_id = None
-        any_tensor_dev = False
-        stream = 0
+        dev_view = None
+        n_host = 0
+        type_glue = glue.backend.get_var_type_glue
         for (name, kind), var in zip(self.params, args):
-            if kind in (_IN_T, _OUT_T):
-                glue_mod = glue.backend.get_var_glue(var)
+            if kind is _INT:
+                values[name] = int(var)
+            elif kind is _SCALAR_T:
+                values[name] = float(var.value) if hasattr(var, '_type_') else float(var)
+            else:
+                glue_mod = type_glue(type(var))
                 if glue_mod is None:
                     raise TypeError('Unmatched parameters list of the function `%s`: `%s` must be a '
                                     'tensor, got %s' % (self.name, name, type(var)))
                 view = glue_mod.Tensor(var)
                 ctype = view.ctype
-                if name in _TOP_NAMES and ctype in _TOP_DTYPES:
-                    values['__top_dtype__'] = _TOP_DTYPES[ctype]      # fp32 arithmetic, typed storage
-                elif bound_t is None:
-                    bound_t = ctype
-                elif ctype is not bound_t:
-                    raise TypeError('Expected Type %s instead of %s for `%s`' % (bound_t, ctype, name))
+                if ctype is not bound_t:
+                    if name in _TOP_NAMES and ctype in _TOP_DTYPES:
+                        values['__top_dtype__'] = _TOP_DTYPES[ctype]      # fp32 arithmetic, typed storage
+                    elif bound_t is None:
+                        bound_t = ctype
+                    else:
+                        raise TypeError('Expected Type %s instead of %s for `%s`' % (bound_t, ctype, name))
                 tdev = view.dev_id
-                if tdev is not None:
-                    if dev_id is not None and tdev != dev_id:
-                        raise ValueError("Don't use multiple devices in a call :-(")
+                if tdev is None:
+                    n_host += 1
+                elif dev_id is None:
                     dev_id = tdev
-                    stream = view.stream
-                    any_tensor_dev = True
+                    dev_view = view
+                elif tdev != dev_id:
+                    raise ValueError("Don't use multiple devices in a call :-(")
                 tensors[name] = _TensorArg(var, view)
-            elif kind == _INT:
-                values[name] = int(var)
-            else:
-                values[name] = float(var.value) if hasattr(var, '_type_') else float(var)
         if bound_t not in _SUPPORTED_T:
             raise TypeError('%s is instantiated for float only (no %s kernel in '
                             'libmobula_roialign_sm100)' % (self.name, bound_t))
-        host = not any_tensor_dev
-        if not host:
-            for t in tensors.values():
-                if t.view.dev_id is None:
-                    raise ValueError('%s: host and device tensors mixed in one call' % self.name)
+        host = dev_view is None
+        if not host and n_host:
+            raise ValueError('%s: host and device tensors mixed in one call' % self.name)
+        stream = 0 if host else dev_view.stream
         if layout is not None:
             if layout not in _native.LAYOUTS:
                 raise ValueError("layout must be 'RCHW' ([R, C, PH, PW]) or 'RHWC' ([R, PH, PW, C])")
             values['__top_layout__'] = _native.LAYOUTS[layout]
-        if self.name in ('im2col', 'col2im'):
+        if self._conv:
             if mode is not None or accumulate is not None or algo is not None or aligned or layout is not None:
                 raise TypeError('%s takes no mode / accumulate / algo / aligned / layout' % self.name)
-            _launch_conv(self.name, values, tensors, -1 if dev_id is None else dev_id, stream, host)
+            _launch_conv(self.name, values, tensors, -1 if host else dev_id, stream, host)
         else:
-            launcher = _launch_forward if self.name == 'roi_align_forward' else _launch_backward
-            launcher(values, tensors, -1 if dev_id is None else dev_id, stream, host, mode, accumulate,
-                     algo or config.ROIALIGN_ALGO, aligned)
+            self._launcher(values, tensors, -1 if host else dev_id, stream, host, mode, accumulate,
+                           algo or config.ROIALIGN_ALGO, aligned)
         for t in tensors.values():
-            t.finish()
+            if t.writeback:
+                t.finish()
         return None
 
     def build(self, ctx=None, template_types=None):

@@ -23,6 +23,7 @@ _KNOWN = {
 
 
 def register_glue(glue_name, type_names):
+    _NOT_TENSORS.clear()
     assert type_names, ValueError('type_names should be not empty')
     pkgs = set(name.split('.')[0] for name in type_names)
     assert len(pkgs) == 1, TypeError('types of one adapter must share a package: %s' % type_names)
@@ -55,12 +56,21 @@ def _activate(glue_name, type_names):
     return mod
 
 
+_NOT_TENSORS = set()       # types already found to belong to no adapter (int, float, tuple, str, ...)
+
+
 def get_var_type_glue(vtype):
     mod = _TYPE_TO_GLUE.get(vtype)
     if mod is not None:
         return mod
+    if vtype in _NOT_TENSORS:
+        return None
     pkg = getattr(vtype, '__module__', '').split('.')[0]
     if pkg not in _KNOWN:
+        try:
+            _NOT_TENSORS.add(vtype)
+        except TypeError:      # unhashable type object: look it up again next time
+            pass
         return None
     _activate(*_KNOWN[pkg])
     for known, mod in _TYPE_TO_GLUE.items():

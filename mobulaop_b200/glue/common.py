@@ -16,9 +16,22 @@ OP_MODULE_GLOBALS = None     # set by mobulaop_b200.op to its module dict
 backend = None               # set by glue/__init__.py
 
 
+_FORWARD_SPECS = {}
+
+
+def _forward_spec(op):
+    """(input names, number of trailing inputs with a default) of `op.forward`, looked up once per
+    operator class: inspect.getfullargspec costs tens of microseconds, every call came through it."""
+    spec = _FORWARD_SPECS.get(op)
+    if spec is None:
+        full = inspect.getfullargspec(op.forward)
+        spec = _FORWARD_SPECS[op] = (full.args[1:], len(full.defaults or ()))
+    return spec
+
+
 def forward_input_names(op):
     """Names of the tensor inputs = parameters of `op.forward` after self."""
-    return inspect.getfullargspec(op.forward).args[1:]
+    return _forward_spec(op)[0]
 
 
 def split_inputs(op, args, kwargs):
@@ -27,9 +40,7 @@ def split_inputs(op, args, kwargs):
     Returns (inputs, ctor_args, ctor_kwargs).  Inputs may be given positionally or by
     name; trailing inputs with defaults may be omitted (reference: common.py:68-105).
     """
-    spec = inspect.getfullargspec(op.forward)
-    names = spec.args[1:]
-    n_default = len(spec.defaults or ())
+    names, n_default = _forward_spec(op)
     kwargs = dict(kwargs)
     if len(args) >= len(names):
         return list(args[:len(names)]), list(args[len(names):]), kwargs

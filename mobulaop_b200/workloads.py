@@ -45,12 +45,13 @@ class Workload(object):
                     sampling_ratio=self.sampling_ratio)
 
     # algorithmic (useful) bytes, SURVEY.md 8(d), with U = N*C*H*W unless given
-    def bytes_forward(self, unique_elements=None):
+    def bytes_forward(self, unique_elements=None, top_bytes=4):
+        """`top_bytes`: bytes per element of the pooled tensor (4 = fp32, 2 = fp16 / bf16)."""
         u = self.N * self.C * self.H * self.W if unique_elements is None else unique_elements
-        return 4 * u + 4 * self.R * self.C * self.pooled[0] * self.pooled[1] + 20 * self.R
+        return 4 * u + top_bytes * self.R * self.C * self.pooled[0] * self.pooled[1] + 20 * self.R
 
-    def bytes_backward(self):
-        return (4 * self.R * self.C * self.pooled[0] * self.pooled[1]
+    def bytes_backward(self, top_bytes=4):
+        return (top_bytes * self.R * self.C * self.pooled[0] * self.pooled[1]
                 + 4 * self.N * self.C * self.H * self.W + 20 * self.R)
 
 

@@ -174,6 +174,24 @@ int mobula_roialign_backward_ex(int device_id, void* stream, const void* top_dif
                                 int pooled_height, int pooled_width, float spatial_scale,
                                 int sampling_ratio, int mode, unsigned flags);
 
+/* Prepared ROI tables: what depends on the ROI table alone -- validation, a
+ * private device copy of the [R, 5] rows and their stable partition by image -- is done once per
+ * table and shared by the forward and the backward of a step (and by every call that pools the same
+ * boxes).  The caller may reuse or free `bottom_rois` as soon as the stream has passed the prepare
+ * call.  Device pointers only; `flags`: MOBULA_ROIALIGN_ALIGNED.  A plan belongs to its device;
+ * destroy it with mobula_roialign_plan_destroy (which waits for the device).  The prepared calls
+ * take the same flags as the v2 entry points (ACCUMULATE, algorithm selection) and obey the same
+ * stream-capture rules. */
+int mobula_roialign_prepare_f32(int device_id, void* stream, const float* bottom_rois, int num_rois,
+                                int num_images, int height, int width, int pooled_height,
+                                int pooled_width, float spatial_scale, int sampling_ratio,
+                                unsigned flags, void** plan);
+int mobula_roialign_forward_prepared_f32(void* plan, void* stream, const float* bottom_data,
+                                         float* top_data, int channels, unsigned flags);
+int mobula_roialign_backward_prepared_f32(void* plan, void* stream, const float* top_diff,
+                                          float* bottom_diff, int channels, int mode, unsigned flags);
+void mobula_roialign_plan_destroy(void* plan);
+
 /* ROI bookkeeping as the kernels compute it, for bit-exact checking against the
  * oracle (same layout as oracle_roi_align_bookkeeping_f32):
  *   geom_i [R,4]  = batch, grid_h, grid_w, 0

@@ -39,6 +39,8 @@ EXPORTED_SYMBOLS = (
     'mobula_roialign_release',
     'im2col_341af5d3', 'col2im_341af5d3', 'mobula_im2col_f32', 'mobula_col2im_f32',
     'mobula_roialign_forward_ex', 'mobula_roialign_backward_ex',
+    'mobula_roialign_prepare_f32', 'mobula_roialign_forward_prepared_f32',
+    'mobula_roialign_backward_prepared_f32', 'mobula_roialign_plan_destroy',
 )
 
 
@@ -65,6 +67,15 @@ def _declare(lib):
     lib.mobula_roialign_backward_ex.restype = i32
     lib.mobula_roialign_backward_ex.argtypes = [i32, vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32,
                                                 i32, f32, i32, i32, u32]
+    lib.mobula_roialign_prepare_f32.restype = i32
+    lib.mobula_roialign_prepare_f32.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, u32,
+                                                ctypes.POINTER(vp)]
+    lib.mobula_roialign_forward_prepared_f32.restype = i32
+    lib.mobula_roialign_forward_prepared_f32.argtypes = [vp, vp, vp, vp, i32, u32]
+    lib.mobula_roialign_backward_prepared_f32.restype = i32
+    lib.mobula_roialign_backward_prepared_f32.argtypes = [vp, vp, vp, vp, i32, i32, u32]
+    lib.mobula_roialign_plan_destroy.restype = None
+    lib.mobula_roialign_plan_destroy.argtypes = [vp]
     lib.mobula_roialign_bookkeeping_f32.restype = i32
     lib.mobula_roialign_bookkeeping_f32.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, f32, i32,
                                                     vp, vp, i32, vp, vp]
@@ -145,3 +156,34 @@ def launch_count():
 
 def last_algo(backward=False):
     return load().mobula_roialign_last_algo(1 if backward else 0).decode()
+
+
+class RoiPlan(object):
+    """Prepared ROI table (mobula_roialign_prepare_f32): validated, copied and grouped by image
+    once, then shared by forward and backward calls.  `rois`: device pointer of the [R, 5] table."""
+
+    def __init__(self, device_id, stream, rois_ptr, num_rois, num_images, height, width, pooled, scale,
+                 sampling_ratio, aligned=False):
+        lib = load()
+        self._lib = lib
+        self.handle = ctypes.c_void_p()
+        check(lib.mobula_roialign_prepare_f32(device_id, stream, rois_ptr, num_rois, num_images, height, width,
+                                              pooled[0], pooled[1], scale, sampling_ratio,
+                                              FLAG_ALIGNED if aligned else 0, ctypes.byref(self.handle)))
+
+    def forward(self, stream, data_ptr, out_ptr, channels, flags=0):
+        check(self._lib.mobula_roialign_forward_prepared_f32(self.handle, stream, data_ptr, out_ptr, channels, flags))
+
+    def backward(self, stream, dy_ptr, dx_ptr, channels, mode=BWD_ATOMIC, flags=0):
+        check(self._lib.mobula_roialign_backward_prepared_f32(self.handle, stream, dy_ptr, dx_ptr, channels, mode, flags))
+
+    def close(self):
+        if self.handle:
+            self._lib.mobula_roialign_plan_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

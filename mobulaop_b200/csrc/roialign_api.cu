@@ -460,6 +460,8 @@ static RoiAlignArgs make_args(const float* rois, int num_rois, int num_images, i
   a.aligned = 0;
   a.top_dtype = 0;
   a.top_layout = 0;
+  a.pre_img_start = nullptr;
+  a.pre_order = nullptr;
   return a;
 }
 
@@ -780,6 +782,123 @@ MOBULA_EXPORT int mobula_roialign_backward_ex(int device_id, void* stream, const
   return backward_impl(device_id, stream, static_cast<const float*>(top_diff), top_dtype, top_layout, bottom_rois,
                        bottom_diff, num_rois, num_images, channels, height, width, pooled_height, pooled_width,
                        spatial_scale, sampling_ratio, mode, flags);
+}
+
+// ---- prepared ROI tables -------------------------------------------------------------------
+// What depends on the ROI table alone -- its validation, a private copy and the stable partition
+// of its rows by image -- done once and shared by the forward and the backward of a step.
+struct RoiPlan {
+  unsigned magic;
+  int device;
+  RoiAlignArgs a;        // rois -> the plan's own copy
+  float* rois;           // [R, 5]
+  int* img_start;        // [N + 2]
+  int* order;            // [R]
+};
+constexpr unsigned kPlanMagic = 0x524f4950u;   // "ROIP"
+
+static RoiPlan* plan_of(void* handle) {
+  RoiPlan* p = static_cast<RoiPlan*>(handle);
+  return (p && p->magic == kPlanMagic) ? p : nullptr;
+}
+
+MOBULA_EXPORT int mobula_roialign_prepare_f32(int device_id, void* stream_, const float* bottom_rois, int num_rois,
+                                              int num_images, int height, int width, int pooled_height,
+                                              int pooled_width, float spatial_scale, int sampling_ratio,
+                                              unsigned flags, void** plan_out) {
+  if (!plan_out) return fail(MOBULA_ERR_INVALID_ARGUMENT, "null plan pointer");
+  *plan_out = nullptr;
+  if (flags & MOBULA_ROIALIGN_HOST_BUFFERS)
+    return fail(MOBULA_ERR_UNSUPPORTED, "prepared ROI tables take device pointers");
+  if (num_images < 0) return fail(MOBULA_ERR_INVALID_ARGUMENT, "prepare needs num_images >= 0");
+  int rc = check_common(bottom_rois, bottom_rois, bottom_rois, num_rois, 1, height, width, pooled_height, pooled_width);
+  if (rc) return rc;
+  DeviceGuard guard(device_id);
+  if (guard.status() != cudaSuccess)
+    return fail(MOBULA_ERR_CUDA, "cannot select device %d: %s", device_id, cudaGetErrorString(guard.status()));
+  const int device = guard.current(device_id);
+  if (device < 0 || device >= kMaxDevices) return fail(MOBULA_ERR_INVALID_ARGUMENT, "device %d", device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RoiPlan* p = new RoiPlan();
+  p->magic = kPlanMagic;
+  p->device = device;
+  p->rois = nullptr;
+  p->img_start = p->order = nullptr;
+  // one allocation: rois copy | img_start | order
+  const size_t rois_bytes = ((size_t)num_rois * 5 * sizeof(float) + 255) & ~(size_t)255;
+  const size_t start_bytes = ((size_t)(num_images + 2) * sizeof(int) + 255) & ~(size_t)255;
+  const size_t order_bytes = ((size_t)num_rois * sizeof(int) + 255) & ~(size_t)255;
+  char* base = nullptr;
+  cudaError_t e = cudaMalloc(&base, rois_bytes + start_bytes + order_bytes + 256);
+  if (e != cudaSuccess) {
+    delete p;
+    return fail(MOBULA_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+  }
+  p->rois = reinterpret_cast<float*>(base);
+  p->img_start = reinterpret_cast<int*>(base + rois_bytes);
+  p->order = reinterpret_cast<int*>(base + rois_bytes + start_bytes);
+  p->a = make_args(p->rois, num_rois, num_images, 0, height, width, pooled_height, pooled_width, spatial_scale,
+                   sampling_ratio);
+  p->a.aligned = (flags & MOBULA_ROIALIGN_ALIGNED) ? 1 : 0;
+  if (num_rois > 0)
+    e = cudaMemcpyAsync(p->rois, bottom_rois, (size_t)num_rois * 5 * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+  if (e == cudaSuccess) e = launch_roi_group(p->a, p->img_start, p->order, stream);
+  if (e != cudaSuccess) {
+    cudaFree(base);
+    delete p;
+    return fail(MOBULA_ERR_CUDA, "prepare: %s", cudaGetErrorString(e));
+  }
+  p->a.pre_img_start = p->img_start;
+  p->a.pre_order = p->order;
+  *plan_out = p;
+  return MOBULA_OK;
+}
+
+MOBULA_EXPORT int mobula_roialign_forward_prepared_f32(void* plan, void* stream_, const float* bottom_data,
+                                                       float* top_data, int channels, unsigned flags) {
+  RoiPlan* p = plan_of(plan);
+  if (!p) return fail(MOBULA_ERR_INVALID_ARGUMENT, "not a plan of mobula_roialign_prepare_f32");
+  if (flags & MOBULA_ROIALIGN_HOST_BUFFERS) return fail(MOBULA_ERR_UNSUPPORTED, "prepared calls take device pointers");
+  RoiAlignArgs a = p->a;
+  a.channels = channels;
+  int rc = check_common(bottom_data, a.rois, top_data, a.num_rois, channels, a.height, a.width, a.pooled_h, a.pooled_w);
+  if (rc) return rc;
+  if (a.num_rois == 0 || channels == 0) return MOBULA_OK;
+  DeviceGuard guard(p->device);
+  if (guard.status() != cudaSuccess) return fail(MOBULA_ERR_CUDA, "cannot select device %d", p->device);
+  DeviceState& st = g_dev[p->device];
+  std::lock_guard<std::mutex> lock(st.mu);
+  if ((rc = probe(st, p->device))) return rc;
+  return forward_device(st, p->device, (cudaStream_t)stream_, bottom_data, a.rois, top_data, a, flags);
+}
+
+MOBULA_EXPORT int mobula_roialign_backward_prepared_f32(void* plan, void* stream_, const float* top_diff,
+                                                        float* bottom_diff, int channels, int mode, unsigned flags) {
+  RoiPlan* p = plan_of(plan);
+  if (!p) return fail(MOBULA_ERR_INVALID_ARGUMENT, "not a plan of mobula_roialign_prepare_f32");
+  if (flags & MOBULA_ROIALIGN_HOST_BUFFERS) return fail(MOBULA_ERR_UNSUPPORTED, "prepared calls take device pointers");
+  RoiAlignArgs a = p->a;
+  a.channels = channels;
+  int rc = check_common(top_diff, a.rois, bottom_diff, a.num_rois, channels, a.height, a.width, a.pooled_h, a.pooled_w);
+  if (rc) return rc;
+  if (channels == 0) return MOBULA_OK;
+  if (a.num_rois == 0 && ((flags & MOBULA_ROIALIGN_ACCUMULATE) || a.num_images <= 0)) return MOBULA_OK;
+  if (!bottom_diff) return fail(MOBULA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  DeviceGuard guard(p->device);
+  if (guard.status() != cudaSuccess) return fail(MOBULA_ERR_CUDA, "cannot select device %d", p->device);
+  DeviceState& st = g_dev[p->device];
+  std::lock_guard<std::mutex> lock(st.mu);
+  if ((rc = probe(st, p->device))) return rc;
+  return backward_device(st, p->device, (cudaStream_t)stream_, top_diff, a.rois, bottom_diff, a, mode, flags);
+}
+
+MOBULA_EXPORT void mobula_roialign_plan_destroy(void* plan) {
+  RoiPlan* p = plan_of(plan);
+  if (!p) return;
+  DeviceGuard guard(p->device);
+  cudaFree(p->rois);       // (synchronises with the device: in-flight users finish first)
+  p->magic = 0;
+  delete p;
 }
 
 MOBULA_EXPORT int mobula_roialign_bookkeeping_f32(int device_id, void* stream_, const float* bottom_rois,

@@ -20,6 +20,10 @@ struct RoiAlignArgs {
   // layout 0 [R, C, PH, PW] (the reference) | 1 [R, PH, PW, C] (channel-last); anything but (0, 0)
   // runs on the sampling_ratio == 2 resident forward (type only), the sweep forward and the pull backward
   int top_dtype, top_layout;
+  // grouping of the ROI rows by image prepared earlier (mobula_roialign_prepare_f32): when set,
+  // launch_roi_group copies it instead of recomputing it
+  const int* pre_img_start;
+  const int* pre_order;
 };
 
 void count_launch();

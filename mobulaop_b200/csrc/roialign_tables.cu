@@ -200,6 +200,13 @@ RoiTables roi_tables_carve(const RoiAlignArgs& a, unsigned need, int pitch, void
 
 cudaError_t launch_roi_group(const RoiAlignArgs& a, int* img_start, int* order, cudaStream_t stream) {
   if (a.num_rois == 0) return cudaMemsetAsync(img_start, 0, (size_t)(a.num_images + 2) * sizeof(int), stream);
+  if (a.pre_img_start && a.pre_order) {
+    // prepared once for this ROI table (forward and backward share it): two small copies
+    cudaError_t e = cudaMemcpyAsync(img_start, a.pre_img_start, (size_t)(a.num_images + 2) * sizeof(int),
+                                    cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(order, a.pre_order, (size_t)a.num_rois * sizeof(int), cudaMemcpyDeviceToDevice, stream);
+  }
   chained_launch(roi_group_kernel, a.num_images + 1, kGroupThreads, 0, stream, a.rois, a.num_rois, a.num_images,
                                                                    img_start, order);
   count_launch();

@@ -78,6 +78,7 @@ struct PullParams {
   float* dyt;            // [R * PH * PW][cw] channel-last fp32 copy of dy
   const void* dy;
   int dy_dtype, dy_layout;   // RoiAlignArgs::top_dtype / top_layout of dy
+  int widen_flat;            // copy blocks run pull_widen_block (channel-last half-precision dy, whole rows)
   float* dx;
 };
 
@@ -485,6 +486,7 @@ __device__ __forceinline__ void pull_transpose_block(const PullParams& p, unsign
   const int ncw = min(kTrChannels, p.cw - c0);             // incl. the zero pad channels
   if (p.dy_layout != 0) {
     // dy is channel-last already ([R, PH, PW, C], any element type): widen and copy, coalesced both ways
+    // (a half-precision dy whose rows are whole, cw == C, goes through pull_widen_block instead)
     const int c = threadIdx.x & (kTrChannels - 1);
     if (c < ncw)
       for (int bb = threadIdx.x / kTrChannels; bb < B; bb += 256 / kTrChannels)
@@ -496,15 +498,29 @@ __device__ __forceinline__ void pull_transpose_block(const PullParams& p, unsign
   const float* src = static_cast<const float*>(p.dy) + src0;
   const int total = nc * B;
   if (p.dy_dtype != kTopF32) {
+    // 2-byte elements, widened on the way into shared memory (the type test stays outside the loop)
+    const unsigned short* src16 = static_cast<const unsigned short*>(p.dy) + src0;
     const int dc = 256 / B, db = 256 - dc * B;
     int c = threadIdx.x / B, bb = threadIdx.x - c * B;
-    for (int i = threadIdx.x; i < total; i += 256) {
-      s_t[c * pitch + bb] = load_top(p.dy, src0 + i, p.dy_dtype);
-      c += dc;
-      bb += db;
-      if (bb >= B) {
-        bb -= B;
-        ++c;
+    if (p.dy_dtype == kTopF16) {
+      for (int i = threadIdx.x; i < total; i += 256) {
+        s_t[c * pitch + bb] = __half2float(__ushort_as_half(__ldg(src16 + i)));
+        c += dc;
+        bb += db;
+        if (bb >= B) {
+          bb -= B;
+          ++c;
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < total; i += 256) {
+        s_t[c * pitch + bb] = __uint_as_float((unsigned)__ldg(src16 + i) << 16);      // bf16 -> fp32: exact
+        c += dc;
+        bb += db;
+        if (bb >= B) {
+          bb -= B;
+          ++c;
+        }
       }
     }
   } else if (pitch == B && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
@@ -538,6 +554,35 @@ __device__ __forceinline__ void pull_transpose_block(const PullParams& p, unsign
   }
 }
 
+// A channel-last half-precision dy whose rows are whole (cw == C == c_work): the "copy" is a flat
+// widening of R * B * C elements, 8 per thread (one 16-byte load, two 16-byte stores).
+__device__ __forceinline__ void pull_widen_block(const PullParams& p, unsigned block) {
+  const size_t total = (size_t)p.num_rois * p.pooled_h * p.pooled_w * p.cw;
+  const size_t i = ((size_t)block * 256 + threadIdx.x) * 8;
+  if (i >= total) return;
+  const unsigned short* src = static_cast<const unsigned short*>(p.dy) + i;
+  float v[8];
+  if (i + 8 <= total && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src));
+    const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (p.dy_dtype == kTopF16) {
+        v[2 * k] = __half2float(__ushort_as_half((unsigned short)(w[k] & 0xffffu)));
+        v[2 * k + 1] = __half2float(__ushort_as_half((unsigned short)(w[k] >> 16)));
+      } else {
+        v[2 * k] = __uint_as_float(w[k] << 16);
+        v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(p.dyt + i);      // cw % 4 == 0 and i % 8 == 0: 16-byte aligned
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    for (size_t k = i; k < total && k < i + 8; ++k) p.dyt[k] = load_top(p.dy, k, p.dy_dtype);
+  }
+}
+
 // The lists and the channel-last copy in ONE grid: building lists is latency-bound index work,
 // the copy is pure bandwidth, and neither depends on the other -- side by side the copy is free.
 // Block roles are interleaved (`lblocks` list blocks, `tblocks` copy blocks) so both progress.
@@ -558,6 +603,7 @@ __global__ void __launch_bounds__(256) pull_tables_kernel(const PullParams p, co
   }
   const bool list_role = (lblocks <= tblocks) == is_few;      // the smaller set is the list set iff lblocks <= tblocks
   if (few == 0 ? lblocks > 0 : list_role) pull_list_block<DET, WIDE>(p, idx);
+  else if (p.widen_flat) pull_widen_block(p, idx);
   else pull_transpose_block<kTrChannels>(p, idx, s_t);
 }
 
@@ -951,8 +997,22 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
     const long long lwarps = (long long)a.num_images * a.height * segs;
     const unsigned lblocks = (unsigned)((lwarps + 7) / 8);
     const int tc = B <= 64 ? 128 : 32;
-    const unsigned tblocks = (unsigned)(a.num_rois * ((L.cw + tc - 1) / tc));
-    const size_t tsmem = a.num_rois > 0 ? (size_t)tc * (B | 1) * sizeof(float) : 0;
+    unsigned tblocks = (unsigned)(a.num_rois * ((L.cw + tc - 1) / tc));
+    size_t tsmem = a.num_rois > 0 ? (size_t)tc * (B | 1) * sizeof(float) : 0;
+    // a channel-last dy with whole rows (cw == C == the channels worked on): fp32 is the copy the
+    // main kernel wants -- it reads dy in place, no copy blocks at all; half precision is widened flat
+    p.widen_flat = 0;
+    if (a.top_layout != 0 && L.cw == a.channels && cwork == a.channels) {
+      if (a.top_dtype == 0 && (reinterpret_cast<uintptr_t>(dy) & 15u) == 0) {
+        p.dyt = const_cast<float*>(dy);
+        tblocks = 0;
+      } else if (a.top_dtype != 0) {
+        p.widen_flat = 1;
+        const unsigned long long elems = (unsigned long long)a.num_rois * B * L.cw;
+        tblocks = (unsigned)((elems + 2047) / 2048);
+      }
+      if (!tblocks || p.widen_flat) tsmem = 0;
+    }
 #define PULL_TABLES(DET, WIDE, TC)                                                                                 \
   do {                                                                                                             \
     auto kk = pull_tables_kernel<DET, WIDE, TC>;                                                                   \

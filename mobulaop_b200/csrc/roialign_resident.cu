@@ -413,7 +413,7 @@ __device__ __forceinline__ void load_roi2(Roi2Regs<ITERS, NCH>& r, const uint2* 
   r.roi = __ldg(order_j);
 }
 
-template <int ITERS, int NCH, bool ACC>
+template <int ITERS, int NCH, bool ACC, bool TYPED>
 __global__ void __launch_bounds__(kFwd2Threads, 1)
 resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                      const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
@@ -434,7 +434,7 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
   __syncthreads();
   if (!ACC)
     zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
-                              (long long)c_count * bins, odt);
+                              (long long)c_count * bins, TYPED ? odt : kTopF32);
 
   // which of this lane's results are outputs: the first sample column of a bin, of an
   // existing bin row
@@ -519,7 +519,8 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
           if (stores[ch] && row_ok) {
             float* o = optr + it * pooled_w + 8 * ch;
             if (ACC) *o = __fadd_rn(*o, y);
-            else store_top(out, (size_t)(o - out), y, odt);
+            else if (TYPED) store_top(out, (size_t)(o - out), y, odt);      // fp16 / bf16 storage
+            else *o = y;
           }
         }
       }
@@ -555,7 +556,7 @@ __device__ __forceinline__ void load_roi_head(RoiHead<PH, NCH>& r, const uint2* 
   r.roi = __ldg(order_j);
 }
 
-template <int PH, int NCH, bool ACC>
+template <int PH, int NCH, bool ACC, bool TYPED>
 __global__ void __launch_bounds__(kFwd2Threads, 1)
 resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                       const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
@@ -578,7 +579,7 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
   __syncthreads();
   if (!ACC)
     zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
-                              (long long)c_count * bins, odt);
+                              (long long)c_count * bins, TYPED ? odt : kTopF32);
 
   bool stores[NCH];
 #pragma unroll
@@ -668,7 +669,8 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
           if (stores[ch] && have) {
             float* o = optr + it * pooled_w + 8 * ch;
             if (ACC) *o = __fadd_rn(*o, y);
-            else store_top(out, (size_t)(o - out), y, odt);
+            else if (TYPED) store_top(out, (size_t)(o - out), y, odt);      // fp16 / bf16 storage
+            else *o = y;
           }
         }
       }
@@ -726,7 +728,7 @@ __device__ __forceinline__ void load_padded_pair(float2* plane, const float* __r
   __syncthreads();
 }
 
-template <int ITERS, int NCH, bool ACC>
+template <int ITERS, int NCH, bool ACC, bool TYPED>
 __global__ void __launch_bounds__(kFwd2Threads, 1)
 resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                       const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
@@ -748,7 +750,7 @@ resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, c
   __syncthreads();
   if (!ACC)
     zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
-                              (long long)c_count * bins, odt);
+                              (long long)c_count * bins, TYPED ? odt : kTopF32);
 
   bool stores[NCH];
 #pragma unroll
@@ -831,9 +833,12 @@ resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, c
             if (ACC) {
               o[0] = __fadd_rn(o[0], y0);
               if (two) o[bins] = __fadd_rn(o[bins], y1);
-            } else {
+            } else if (TYPED) {      // fp16 / bf16 storage
               store_top(out, (size_t)(o - out), y0, odt);
               if (two) store_top(out, (size_t)(o - out) + bins, y1, odt);
+            } else {
+              o[0] = y0;
+              if (two) o[bins] = y1;
             }
           }
         }
@@ -843,7 +848,7 @@ resident_fwd2p_kernel(const float* __restrict__ data, float* __restrict__ out, c
 }
 
 // The channel-pair forward for odd pooled heights: two ROIs per warp, as resident_fwd2r_kernel.
-template <int PH, int NCH, bool ACC>
+template <int PH, int NCH, bool ACC, bool TYPED>
 __global__ void __launch_bounds__(kFwd2Threads, 1)
 resident_fwd2pr_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                       const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
@@ -867,7 +872,7 @@ resident_fwd2pr_kernel(const float* __restrict__ data, float* __restrict__ out, 
   __syncthreads();
   if (!ACC)
     zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
-                              (long long)c_count * bins, odt);
+                              (long long)c_count * bins, TYPED ? odt : kTopF32);
 
   bool stores[NCH];
 #pragma unroll
@@ -961,9 +966,12 @@ resident_fwd2pr_kernel(const float* __restrict__ data, float* __restrict__ out, 
             if (ACC) {
               o[0] = __fadd_rn(o[0], y0);
               if (two) o[bins] = __fadd_rn(o[bins], y1);
-            } else {
+            } else if (TYPED) {      // fp16 / bf16 storage
               store_top(out, (size_t)(o - out), y0, odt);
               if (two) store_top(out, (size_t)(o - out) + bins, y1, odt);
+            } else {
+              o[0] = y0;
+              if (two) o[bins] = y1;
             }
           }
         }
@@ -2053,28 +2061,29 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
         a.rois, order, img_start, a.num_images, a.height, a.width, plan.pitch, plan.fwd_pair ? 8 : 4,
         a.pooled_h, a.pooled_w, a.scale, plan.ypairs, plan.xslots, entries);
     count_launch();
-#define MOBULA_FWD2(ITERS, NCH, ACC)                                                                 \
+#define MOBULA_FWD2(ITERS, NCH, ACC, TYPED)                                                                 \
   do {                                                                                               \
     if (plan.fwd_pair) {                                                                             \
-      e = resident_grid(resident_fwd2p_kernel<ITERS, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms, \
+      e = resident_grid(resident_fwd2p_kernel<ITERS, NCH, ACC, TYPED>, kFwd2Threads, plan.fwd_smem, num_sms, \
                         (work + 1) / 2, &grid);                                                      \
       if (e != cudaSuccess) return e;                                                                \
-      chained_launch(resident_fwd2p_kernel<ITERS, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream,          \
+      chained_launch(resident_fwd2p_kernel<ITERS, NCH, ACC, TYPED>, grid, kFwd2Threads, plan.fwd_smem, stream,          \
           data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,     \
           plan.pitch, a.pooled_h, a.pooled_w, a.top_dtype);                                          \
       break;                                                                                         \
     }                                                                                                \
-    e = resident_grid(resident_fwd2_kernel<ITERS, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms,   \
+    e = resident_grid(resident_fwd2_kernel<ITERS, NCH, ACC, TYPED>, kFwd2Threads, plan.fwd_smem, num_sms,   \
                       work, &grid);                                                                  \
     if (e != cudaSuccess) return e;                                                                  \
-    chained_launch(resident_fwd2_kernel<ITERS, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream,             \
+    chained_launch(resident_fwd2_kernel<ITERS, NCH, ACC, TYPED>, grid, kFwd2Threads, plan.fwd_smem, stream,             \
         data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,       \
         plan.pitch, a.pooled_h, a.pooled_w, plan.vec16, a.top_dtype);                             \
   } while (0)
-#define MOBULA_FWD2_NCH(ITERS, NCH)                  \
-  do {                                               \
-    if (accumulate) MOBULA_FWD2(ITERS, NCH, true);   \
-    else MOBULA_FWD2(ITERS, NCH, false);             \
+#define MOBULA_FWD2_NCH(ITERS, NCH)                               \
+  do {                                                            \
+    if (accumulate) MOBULA_FWD2(ITERS, NCH, true, false);         \
+    else if (a.top_dtype != 0) MOBULA_FWD2(ITERS, NCH, false, true); \
+    else MOBULA_FWD2(ITERS, NCH, false, false);                   \
   } while (0)
 #define MOBULA_FWD2_ITERS(ITERS)                             \
   do {                                                       \
@@ -2082,31 +2091,33 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
     else MOBULA_FWD2_NCH(ITERS, 2);                          \
   } while (0)
     const bool pairs_of_rois = (a.pooled_h & 1) && a.pooled_h <= 7;
-#define MOBULA_FWD2R(PH, NCH, ACC)                                                                    \
+#define MOBULA_FWD2R(PH, NCH, ACC, TYPED)                                                                    \
   do {                                                                                               \
     if (plan.fwd_pair) {                                                                             \
-      e = resident_grid(resident_fwd2pr_kernel<PH, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms,  \
+      e = resident_grid(resident_fwd2pr_kernel<PH, NCH, ACC, TYPED>, kFwd2Threads, plan.fwd_smem, num_sms,  \
                         (work + 1) / 2, &grid);                                                      \
       if (e != cudaSuccess) return e;                                                                \
-      chained_launch(resident_fwd2pr_kernel<PH, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream, \
+      chained_launch(resident_fwd2pr_kernel<PH, NCH, ACC, TYPED>, grid, kFwd2Threads, plan.fwd_smem, stream, \
           data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,     \
           plan.pitch, a.pooled_h, a.pooled_w, a.top_dtype);                                          \
       break;                                                                                         \
     }                                                                                                \
-    e = resident_grid(resident_fwd2r_kernel<PH, NCH, ACC>, kFwd2Threads, plan.fwd_smem, num_sms, work, &grid); \
+    e = resident_grid(resident_fwd2r_kernel<PH, NCH, ACC, TYPED>, kFwd2Threads, plan.fwd_smem, num_sms, work, &grid); \
     if (e != cudaSuccess) return e;                                                                  \
-    chained_launch(resident_fwd2r_kernel<PH, NCH, ACC>, grid, kFwd2Threads, plan.fwd_smem, stream,   \
+    chained_launch(resident_fwd2r_kernel<PH, NCH, ACC, TYPED>, grid, kFwd2Threads, plan.fwd_smem, stream,   \
         data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,       \
         plan.pitch, a.pooled_h, a.pooled_w, plan.vec16, a.top_dtype);                                \
   } while (0)
 #define MOBULA_FWD2R_PH(PH)                                          \
   do {                                                               \
     if (plan.xslots == 16) {                                         \
-      if (accumulate) MOBULA_FWD2R(PH, 1, true);                     \
-      else MOBULA_FWD2R(PH, 1, false);                               \
+      if (accumulate) MOBULA_FWD2R(PH, 1, true, false);              \
+      else if (a.top_dtype != 0) MOBULA_FWD2R(PH, 1, false, true);   \
+      else MOBULA_FWD2R(PH, 1, false, false);                        \
     } else {                                                         \
-      if (accumulate) MOBULA_FWD2R(PH, 2, true);                     \
-      else MOBULA_FWD2R(PH, 2, false);                               \
+      if (accumulate) MOBULA_FWD2R(PH, 2, true, false);              \
+      else if (a.top_dtype != 0) MOBULA_FWD2R(PH, 2, false, true);   \
+      else MOBULA_FWD2R(PH, 2, false, false);                        \
     }                                                                \
   } while (0)
     if (pairs_of_rois) {

@@ -13,14 +13,16 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason='needs 
 
 @pytest.mark.parametrize('name', ['fpn_14x14_sr2', 'wide_w280_sr2', 'edges_sr0', 'ref_value_test'])
 @pytest.mark.parametrize('shuffle', [False, True])
-def test_forward_and_backward_share_one_plan(native, name, shuffle):
+def test_forward_and_backward_share_one_plan(native, oracle, name, shuffle):
     import torch
     from mobulaop_b200 import _native
     g = load_golden(name)
-    rois_np, y_ref, dy_np = g['rois'], g['y'], g['dy']
+    rois_np, y_ref, dy_np, dx_ref = g['rois'], g['y'], g['dy'], g['dx']
     if shuffle:          # rows of different images interleaved: the plan's partition is not the identity
         perm = np.random.default_rng(1).permutation(rois_np.shape[0])
-        rois_np, y_ref, dy_np = rois_np[perm], y_ref[perm], dy_np[perm]
+        rois_np, y_ref, dy_np = np.ascontiguousarray(rois_np[perm]), y_ref[perm], np.ascontiguousarray(dy_np[perm])
+        # (the canonical accumulation order follows the rows of the table: ask the oracle again)
+        dx_ref = oracle.backward(dy_np, rois_np, g['data'].shape, g['scale'], g['sr'])
     dev = torch.device('cuda', 0)
     data = torch.from_numpy(g['data']).to(dev)
     rois = torch.from_numpy(np.ascontiguousarray(rois_np)).to(dev)
@@ -39,7 +41,7 @@ def test_forward_and_backward_share_one_plan(native, name, shuffle):
     torch.cuda.synchronize()
     assert _native.launch_count() > launches
     assert_bit_exact(out.cpu().numpy(), y_ref)
-    assert_bit_exact(dx.cpu().numpy(), g['dx'])
+    assert_bit_exact(dx.cpu().numpy(), dx_ref)
     plan.close()
     plan.close()                                  # idempotent
 

@@ -465,14 +465,13 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
                   pooled_h - 1, 2 * pooled_w - 1);
 
       unsigned xa[NCH], xb[NCH];      // shared-memory address of the low column in row 0 / row 1
-      float2 lx2[NCH], hx2[NCH];
+      float2 hl2[NCH];                // (hx, lx)
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         xa[ch] = sbase + cur.x[ch].x;
         xb[ch] = xa[ch] + row_bytes;
         const float lx = __uint_as_float(cur.x[ch].y), hx = __fsub_rn(1.0f, lx);
-        lx2[ch] = make_float2(lx, lx);
-        hx2[ch] = make_float2(hx, hx);
+        hl2[ch] = make_float2(hx, lx);
       }
       // this lane's first output: bin (ITERS * h, q / 2) of chunk 0 -- half-warp h works on the
       // bin rows [ITERS * h, ITERS * h + ITERS), one after the other (row reuse, see Taps)
@@ -491,24 +490,26 @@ resident_fwd2_kernel(const float* __restrict__ data, float* __restrict__ out, co
         const unsigned code0 = it == 0 ? 0u : (ey.x & kRowCodeMask), code1 = ey.z & kRowCodeMask;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
-          // taps of sample iy = 0 in .x, of iy = 1 in .y: v1 v2 / v3 v4 as in bilinear.h:50-53
-          taps_advance(tp[ch], xa[ch] + y0, xb[ch] + y0, code0, epoch);
-          const Taps t0 = tp[ch];
-          taps_advance(tp[ch], xa[ch] + y1, xb[ch] + y1, code1, epoch);
-          const Taps t1 = tp[ch];
-          const float2 v1 = make_float2(t0.plo, t1.plo);
-          const float2 v2 = make_float2(t0.phi, t1.phi);
-          const float2 v3 = make_float2(t0.clo, t1.clo);
-          const float2 v4 = make_float2(t0.chi, t1.chi);
-          const float2 w1 = __fmul2_rn(hy2, hx2[ch]), w2 = __fmul2_rn(hy2, lx2[ch]);
-          const float2 w3 = __fmul2_rn(ly2, hx2[ch]), w4 = __fmul2_rn(ly2, lx2[ch]);
-          // the sums stay scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
-          // (it honours .rn only for the scalar forms), which would change the rounding
-          const float2 p1 = __fmul2_rn(w1, v1), p2 = __fmul2_rn(w2, v2);
-          const float2 p3 = __fmul2_rn(w3, v3), p4 = __fmul2_rn(w4, v4);
+          // one sample at a time (its taps are consumed before the registers move on to the next
+          // sample row); the packed multiplies pair the two columns of a row: (w1, w2) = hy * (hx, lx),
+          // (w3, w4) = ly * (hx, lx), products (w1 v1, w2 v2) and (w3 v3, w4 v4) as in bilinear.h:50-53.
+          // The sums stay scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it
+          // honours .rn only for the scalar forms), which would change the rounding
           float2 s;
-          s.x = __fadd_rn(__fadd_rn(__fadd_rn(p1.x, p2.x), p3.x), p4.x);
-          s.y = __fadd_rn(__fadd_rn(__fadd_rn(p1.y, p2.y), p3.y), p4.y);
+          {
+            taps_advance(tp[ch], xa[ch] + y0, xb[ch] + y0, code0, epoch);
+            const float2 wa = __fmul2_rn(make_float2(hy2.x, hy2.x), hl2[ch]), wb = __fmul2_rn(make_float2(ly2.x, ly2.x), hl2[ch]);
+            const float2 pa = __fmul2_rn(wa, make_float2(tp[ch].plo, tp[ch].phi));
+            const float2 pb = __fmul2_rn(wb, make_float2(tp[ch].clo, tp[ch].chi));
+            s.x = __fadd_rn(__fadd_rn(__fadd_rn(pa.x, pa.y), pb.x), pb.y);
+          }
+          {
+            taps_advance(tp[ch], xa[ch] + y1, xb[ch] + y1, code1, epoch);
+            const float2 wa = __fmul2_rn(make_float2(hy2.y, hy2.y), hl2[ch]), wb = __fmul2_rn(make_float2(ly2.y, ly2.y), hl2[ch]);
+            const float2 pa = __fmul2_rn(wa, make_float2(tp[ch].plo, tp[ch].phi));
+            const float2 pb = __fmul2_rn(wb, make_float2(tp[ch].clo, tp[ch].chi));
+            s.y = __fadd_rn(__fadd_rn(__fadd_rn(pa.x, pa.y), pb.x), pb.y);
+          }
           const float s0n = __shfl_down_sync(0xffffffffu, s.x, 1);
           const float s1n = __shfl_down_sync(0xffffffffu, s.y, 1);
           float t = __fadd_rn(0.0f, s.x);
@@ -619,14 +620,13 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
                       2 * pooled_w - 1);
 
       unsigned xa[NCH], xb[NCH];      // shared-memory address of the low column in row 0 / row 1
-      float2 lx2[NCH], hx2[NCH];
+      float2 hl2[NCH];                // (hx, lx)
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         xa[ch] = sbase + xs[ch].x;
         xb[ch] = xa[ch] + row_bytes;
         const float lx = __uint_as_float(xs[ch].y), hx = __fsub_rn(1.0f, lx);
-        lx2[ch] = make_float2(lx, lx);
-        hx2[ch] = make_float2(hx, hx);
+        hl2[ch] = make_float2(hx, lx);
       }
       // this lane's first output: bin (0, q / 2) of chunk 0 of its half-warp's ROI
       float* optr = out + ((size_t)roi * channels + w.c) * bins + (q >> 1);
@@ -642,23 +642,26 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
         const unsigned code0 = it == 0 ? 0u : (ey.x & kRowCodeMask), code1 = ey.z & kRowCodeMask;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
-          // taps of sample iy = 0 in .x, of iy = 1 in .y: v1 v2 / v3 v4 as in bilinear.h:50-53
-          taps_advance(tp[ch], xa[ch] + y0, xb[ch] + y0, code0, epoch);
-          const Taps t0 = tp[ch];
-          taps_advance(tp[ch], xa[ch] + y1, xb[ch] + y1, code1, epoch);
-          const Taps t1 = tp[ch];
-          const float2 v1 = make_float2(t0.plo, t1.plo);
-          const float2 v2 = make_float2(t0.phi, t1.phi);
-          const float2 v3 = make_float2(t0.clo, t1.clo);
-          const float2 v4 = make_float2(t0.chi, t1.chi);
-          const float2 w1 = __fmul2_rn(hy2, hx2[ch]), w2 = __fmul2_rn(hy2, lx2[ch]);
-          const float2 w3 = __fmul2_rn(ly2, hx2[ch]), w4 = __fmul2_rn(ly2, lx2[ch]);
-          // scalar sums: see resident_fwd2_kernel
-          const float2 p1 = __fmul2_rn(w1, v1), p2 = __fmul2_rn(w2, v2);
-          const float2 p3 = __fmul2_rn(w3, v3), p4 = __fmul2_rn(w4, v4);
+          // one sample at a time (its taps are consumed before the registers move on to the next
+          // sample row); the packed multiplies pair the two columns of a row: (w1, w2) = hy * (hx, lx),
+          // (w3, w4) = ly * (hx, lx), products (w1 v1, w2 v2) and (w3 v3, w4 v4) as in bilinear.h:50-53.
+          // The sums stay scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it
+          // honours .rn only for the scalar forms), which would change the rounding
           float2 sm;
-          sm.x = __fadd_rn(__fadd_rn(__fadd_rn(p1.x, p2.x), p3.x), p4.x);
-          sm.y = __fadd_rn(__fadd_rn(__fadd_rn(p1.y, p2.y), p3.y), p4.y);
+          {
+            taps_advance(tp[ch], xa[ch] + y0, xb[ch] + y0, code0, epoch);
+            const float2 wa = __fmul2_rn(make_float2(hy2.x, hy2.x), hl2[ch]), wb = __fmul2_rn(make_float2(ly2.x, ly2.x), hl2[ch]);
+            const float2 pa = __fmul2_rn(wa, make_float2(tp[ch].plo, tp[ch].phi));
+            const float2 pb = __fmul2_rn(wb, make_float2(tp[ch].clo, tp[ch].chi));
+            sm.x = __fadd_rn(__fadd_rn(__fadd_rn(pa.x, pa.y), pb.x), pb.y);
+          }
+          {
+            taps_advance(tp[ch], xa[ch] + y1, xb[ch] + y1, code1, epoch);
+            const float2 wa = __fmul2_rn(make_float2(hy2.y, hy2.y), hl2[ch]), wb = __fmul2_rn(make_float2(ly2.y, ly2.y), hl2[ch]);
+            const float2 pa = __fmul2_rn(wa, make_float2(tp[ch].plo, tp[ch].phi));
+            const float2 pb = __fmul2_rn(wb, make_float2(tp[ch].clo, tp[ch].chi));
+            sm.y = __fadd_rn(__fadd_rn(__fadd_rn(pa.x, pa.y), pb.x), pb.y);
+          }
           const float s0n = __shfl_down_sync(0xffffffffu, sm.x, 1);
           const float s1n = __shfl_down_sync(0xffffffffu, sm.y, 1);
           float t = __fadd_rn(0.0f, sm.x);

@@ -410,10 +410,34 @@ __device__ __forceinline__ float ld_cg(const float* p) {
 __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_cg(float* p, float v) { asm volatile("st.global.cg.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
+// A finished bin row in a half-precision and / or channel-last output (RoiAlignArgs::top_dtype,
+// top_layout); `vals` = the lane's channel, one value per bin column.
+__device__ __noinline__ void sweep_store_typed(const SweepParams& p, const float* vals, int pooled_w, float* stage,
+                                               int roi, int ph, int c0, int cvalid, int bins, int lane) {
+  if (p.top_layout != 0) {
+    // channel-last [R, PH, PW, C]: the lanes ARE the channels, one coalesced store per bin
+    const size_t o = (((size_t)roi * p.pooled_h + ph) * pooled_w) * p.channels + c0 + lane;
+    if (lane < cvalid)
+      for (int pw = 0; pw < pooled_w; ++pw) store_top(p.out, o + (size_t)pw * p.channels, vals[pw], p.top_dtype);
+    return;
+  }
+  __syncwarp();
+  for (int pw = 0; pw < pooled_w; ++pw) stage[lane * p.pwp + pw] = vals[pw];
+  __syncwarp();
+  const size_t o = ((size_t)roi * p.channels + c0) * bins + ph * pooled_w;
+  for (int f = lane; f < 32 * pooled_w; f += 32) {
+    const int c = f / pooled_w, pw = f - c * pooled_w;
+    if (c < cvalid) store_top(p.out, o + (size_t)c * bins + pw, stage[c * p.pwp + pw], p.top_dtype);
+  }
+}
+
 // ---- the forward sweep ---------------------------------------------------------------------
 // PWT: pooled width.  GWT > 0: fixed sampling ratio, column records at k = pw * GWT + ix;
 // GWT == 0: compacted column records with per-bin ranges (adaptive grids).
-template <int PWT, int GWT>
+// TYPED: the output is half precision and / or channel-last (a variant of its own: the reference's
+// format keeps exactly the code -- and the register allocation -- it had without the feature; a
+// run-time test in the epilogue alone cost the adaptive-grid workload 25 %).
+template <int PWT, int GWT, bool TYPED>
 __global__ void __launch_bounds__(kSweepThreads, 1)
 sweep_fwd_kernel(const SweepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -634,31 +658,28 @@ sweep_fwd_kernel(const SweepParams p) {
           const bool pow2 = (cnt_i & (cnt_i - 1)) == 0;
           const float inv = __fdiv_rn(1.0f, count);
           const int cvalid = min(32, p.c_work - c0);
-          if (p.top_layout != 0) {
-            // channel-last output [R, PH, PW, C]: the lanes ARE the channels, one coalesced store per bin
-            const size_t o = (((size_t)roi * PH + ph) * PWT) * p.channels + c0 + lane;
-            if (lane < cvalid) {
+          if (TYPED) {
+            // half-precision and / or channel-last output: out of line, the reference's format below
+            // keeps the code it always had
+            float vals[PWT];
 #pragma unroll
-              for (int pw = 0; pw < PWT; ++pw)
-                store_top(p.out, o + (size_t)pw * p.channels, pow2 ? __fmul_rn(acc[pw], inv) : __fdiv_rn(acc[pw], count),
-                          p.top_dtype);
-            }
+            for (int pw = 0; pw < PWT; ++pw) vals[pw] = pow2 ? __fmul_rn(acc[pw], inv) : __fdiv_rn(acc[pw], count);
+            sweep_store_typed(p, vals, PWT, stage, roi, ph, c0, cvalid, bins, lane);
           } else {
             __syncwarp();
 #pragma unroll
             for (int pw = 0; pw < PWT; ++pw)
               stage[lane * p.pwp + pw] = pow2 ? __fmul_rn(acc[pw], inv) : __fdiv_rn(acc[pw], count);
             __syncwarp();
-            const size_t o = ((size_t)roi * p.channels + c0) * bins + ph * PWT;
+            float* o = p.out + ((size_t)roi * p.channels + c0) * bins + ph * PWT;
 #pragma unroll
             for (int k = 0; k < PWT; ++k) {
               const int f = k * 32 + lane;
               const int c = f / PWT, pw = f - c * PWT;
               if (c < cvalid) {
                 const float v = stage[c * p.pwp + pw];
-                const size_t at = o + (size_t)c * bins + pw;
-                if (p.accumulate) p.out[at] = __fadd_rn(p.out[at], v);      // fp32 only (checked by the caller)
-                else store_top(p.out, at, v, p.top_dtype);
+                float* dst = o + c * bins + pw;
+                *dst = p.accumulate ? __fadd_rn(*dst, v) : v;
               }
             }
           }
@@ -938,7 +959,9 @@ cudaError_t launch_main(int gwt, dim3 grid, size_t smem, cudaStream_t stream, co
     count_launch();
     return chained_launch(kernel, grid, dim3(kSweepThreads), smem, stream, p);
   };
-  return gwt == 2 ? go(sweep_fwd_kernel<PWT, 2>) : go(sweep_fwd_kernel<PWT, 0>);
+  if ((p.top_dtype | p.top_layout) != 0)
+    return gwt == 2 ? go(sweep_fwd_kernel<PWT, 2, true>) : go(sweep_fwd_kernel<PWT, 0, true>);
+  return gwt == 2 ? go(sweep_fwd_kernel<PWT, 2, false>) : go(sweep_fwd_kernel<PWT, 0, false>);
 }
 
 }  // namespace

@@ -613,6 +613,11 @@ __global__ void __launch_bounds__(256) pull_tables_kernel(const PullParams p, co
 // to shared memory 64 at a time (coalesced) and reads them back as broadcasts, so the only
 // global load on the dependent path of a term is its gradient line.
 constexpr int kPullThreads = 256;
+// resident CTAs per SM the main kernel is compiled for: the merged-tap kernel is bound by the latency
+// of its gradient loads, a fourth CTA (<= 64 registers, a few spilled words) is worth 5-14 %; the
+// canonical-order kernel keeps more state per term and loses with anything tighter than three
+// (measured 3 / 4 / 5 CTAs: C2 150 / 143 / 156 us, C3 2.40 / 2.07 / 2.59 ms, C4 3.51 / 3.30 / 3.56 ms)
+constexpr int pull_min_blocks(bool det) { return det ? 3 : 4; }
 constexpr int kPullRows = 2;
 constexpr int kEntChunk = 64;
 
@@ -662,7 +667,7 @@ __device__ __forceinline__ void count_of(const uint4& en, float& count, float& i
 }
 
 template <int CPL, bool DET, bool ACC, int U, bool WIDE>
-__global__ void __launch_bounds__(kPullThreads) pull_bwd_kernel(const PullParams p, const float count0,
+__global__ void __launch_bounds__(kPullThreads, pull_min_blocks(DET)) pull_bwd_kernel(const PullParams p, const float count0,
                                                                 const float inv0, const int pow20) {
   typedef typename EntryOf<WIDE>::type Entry;
   constexpr int CG = 32 * CPL;                        // channels per CTA

@@ -586,8 +586,14 @@ __device__ __forceinline__ void pull_widen_block(const PullParams& p, unsigned b
 // The lists and the channel-last copy in ONE grid: building lists is latency-bound index work,
 // the copy is pure bandwidth, and neither depends on the other -- side by side the copy is free.
 // Block roles are interleaved (`lblocks` list blocks, `tblocks` copy blocks) so both progress.
+// resident CTAs per SM the kernel is compiled for: the list walk waits on dependent table loads,
+// a fifth CTA (<= 48 registers, four spilled words) hides more of them (measured 4 / 5 / 6 CTAs on the
+// whole backward: C3 2.07 / 1.96 / 1.96 ms, C4 3.30 / 3.18 / 3.19 ms, C2 143 / 143 / 147 us)
+#ifndef MOBULA_TABLES_MINBLOCKS
+#define MOBULA_TABLES_MINBLOCKS 5
+#endif
 template <bool DET, bool WIDE, int kTrChannels>
-__global__ void __launch_bounds__(256) pull_tables_kernel(const PullParams p, const unsigned lblocks,
+__global__ void __launch_bounds__(256, MOBULA_TABLES_MINBLOCKS) pull_tables_kernel(const PullParams p, const unsigned lblocks,
                                                           const unsigned tblocks) {
   extern __shared__ float s_t[];      // copy blocks: [kTrChannels][B | 1]
   ptx::chain_enter();

@@ -328,9 +328,10 @@ resident_fwd_kernel(const float* __restrict__ data, float* __restrict__ out, con
 }
 
 // ---- sampling_ratio == 2 forward (every BASELINE configuration but the adaptive one) -------
-// lane = one sample column of one row of bins.  Half-warp h works on bin row ph = 2 * it + h,
-// its 16 lanes on the sample columns sx = 2 * pw + ix of a chunk of 8 bins; a lane computes the
-// two samples (iy = 0, 1) of its column.  One warp instruction therefore reads two
+// lane = one sample column of one row of bins.  Half-warp h works on the bin rows
+// [ITERS * h, ITERS * h + ITERS) one after the other (consecutive rows: the taps a lane holds carry
+// over from one sample row to the next, see Taps), its 16 lanes on the sample columns
+// sx = 2 * pw + ix of a chunk of 8 bins; a lane computes the two samples (iy = 0, 1) of its column.  One warp instruction therefore reads two
 // feature-map rows at <= 16 columns each; a lane's column record stays in registers for the
 // whole ROI; the row records (one 16-byte broadcast load per half-warp and iteration) of the
 // NEXT ROI are fetched while the current one is computed, so no load latency is exposed.  The

@@ -614,7 +614,8 @@ __global__ void __launch_bounds__(256, MOBULA_TABLES_MINBLOCKS) pull_tables_kern
 }
 
 // ---- the main kernel ------------------------------------------------------------------------
-// CTA = 2 rows x 32 pixels x (32 * CPL) channels; warp w: row w / 4, pixels 8 (w % 4) .. + 7.
+// CTA = kPullRows x kPullCols pixels (8 x 8) x (32 * CPL) channels; warp w: row w / kPullWarpsPerRow,
+// 8 consecutive pixels of it.
 // The entries of a warp's eight pixels are one contiguous run of the list: the warp brings them
 // to shared memory 64 at a time (coalesced) and reads them back as broadcasts, so the only
 // global load on the dependent path of a term is its gradient line.
@@ -624,7 +625,16 @@ constexpr int kPullThreads = 256;
 // canonical-order kernel keeps more state per term and loses with anything tighter than three
 // (measured 3 / 4 / 5 CTAs: C2 150 / 143 / 156 us, C3 2.40 / 2.07 / 2.59 ms, C4 3.51 / 3.30 / 3.56 ms)
 constexpr int pull_min_blocks(bool det) { return det ? 3 : 4; }
-constexpr int kPullRows = 2;
+// Tile shape: the pixels of a CTA re-read the gradient lines of the bins they share out of L1, and a
+// square tile meets fewer bins per ROI than a strip (bins of 6 x 6 pixels: 5.4 against 8.4 lines per
+// ROI).  Measured 2 x 32 / 4 x 16 / 8 x 8 on the whole backward: C2 143 / 140 / 137 us,
+// C3 1.96 / 1.90 / 1.79 ms, C4 3.18 / 3.08 / 3.01 ms.
+#ifndef MOBULA_PULL_ROWS
+#define MOBULA_PULL_ROWS 8
+#endif
+constexpr int kPullRows = MOBULA_PULL_ROWS;                     // rows of a CTA's pixel tile: 2, 4 or 8
+constexpr int kPullWarpsPerRow = (kPullThreads / 32) / kPullRows;
+constexpr int kPullCols = 8 * kPullWarpsPerRow;                 // columns of the tile (a warp = 8 pixels of one row)
 constexpr int kEntChunk = 64;
 
 template <int CPL>
@@ -685,13 +695,13 @@ __global__ void __launch_bounds__(kPullThreads, pull_min_blocks(DET)) pull_bwd_k
   float count = count0, inv = inv0;
   int pow2 = pow20;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int segs = (p.width + 31) >> 5, bands = (p.height + kPullRows - 1) / kPullRows;
+  const int segs = (p.width + kPullCols - 1) / kPullCols, bands = (p.height + kPullRows - 1) / kPullRows;
   const int seg = blockIdx.x % segs;
   const int band = (blockIdx.x / segs) % bands;
   const int n = blockIdx.x / (segs * bands);
   const int c0 = blockIdx.y * CG;
-  const int y = band * kPullRows + (warp >> 2);
-  const int xw = seg * 32 + (warp & 3) * 8;
+  const int y = band * kPullRows + warp / kPullWarpsPerRow;
+  const int xw = seg * kPullCols + (warp % kPullWarpsPerRow) * 8;
   if (y >= p.height || xw >= p.width) return;         // no block-wide barrier below: warps are independent
   const bool lane_on = c0 + lane * CPL < p.cw;
   const char* dyt = reinterpret_cast<const char*>(p.dyt + (lane_on ? c0 + lane * CPL : 0));
@@ -896,7 +906,7 @@ bool pull_supported(const RoiAlignArgs& a) {
   if (cwork < 1) return false;
   // entry offsets and list positions are 32-bit
   if ((long long)a.num_rois * a.pooled_h * a.pooled_w * ((cwork + 3) & ~3) * 4 >= (1LL << 32)) return false;
-  const long long segs = ((long long)a.width + 31) / 32, bands = ((long long)a.height + kPullRows - 1) / kPullRows;
+  const long long segs = ((long long)a.width + kPullCols - 1) / kPullCols, bands = ((long long)a.height + kPullRows - 1) / kPullRows;
   if (segs * bands * a.num_images >= (1LL << 31)) return false;
   return true;
 }
@@ -1049,8 +1059,8 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
   const int pow2 = (cnt_i & (cnt_i - 1)) == 0 ? 1 : 0;
   const float inv = 1.0f / count;
   const int cpl = (L.cw >= 128) ? 4 : (L.cw >= 64 ? 2 : 1);
-  const long long bands = (a.height + kPullRows - 1) / kPullRows;
-  const dim3 grid((unsigned)(segs * bands * a.num_images), (unsigned)((L.cw + 32 * cpl - 1) / (32 * cpl)));
+  const long long bands = (a.height + kPullRows - 1) / kPullRows, tile_cols = (a.width + kPullCols - 1) / kPullCols;
+  const dim3 grid((unsigned)(tile_cols * bands * a.num_images), (unsigned)((L.cw + 32 * cpl - 1) / (32 * cpl)));
   // MOBULA_PULL_UNROLL = terms per group (4 or 8): gradient loads in flight per warp
   static const int unroll = [] { const char* e = getenv("MOBULA_PULL_UNROLL"); return e ? atoi(e) : 8; }();
 #define PULL_LAUNCH(CPL, DET, ACC, WIDE)                                                  \

@@ -619,12 +619,15 @@ __global__ void __launch_bounds__(256, MOBULA_TABLES_MINBLOCKS) pull_tables_kern
 // The entries of a warp's eight pixels are one contiguous run of the list: the warp brings them
 // to shared memory 64 at a time (coalesced) and reads them back as broadcasts, so the only
 // global load on the dependent path of a term is its gradient line.
-constexpr int kPullThreads = 256;
+#ifndef MOBULA_PULL_THREADS
+#define MOBULA_PULL_THREADS 256
+#endif
+constexpr int kPullThreads = MOBULA_PULL_THREADS;
 // resident CTAs per SM the main kernel is compiled for: the merged-tap kernel is bound by the latency
 // of its gradient loads, a fourth CTA (<= 64 registers, a few spilled words) is worth 5-14 %; the
 // canonical-order kernel keeps more state per term and loses with anything tighter than three
 // (measured 3 / 4 / 5 CTAs: C2 150 / 143 / 156 us, C3 2.40 / 2.07 / 2.59 ms, C4 3.51 / 3.30 / 3.56 ms)
-constexpr int pull_min_blocks(bool det) { return det ? 3 : 4; }
+constexpr int pull_min_blocks(bool det) { return (det ? 3 : 4) * 256 / kPullThreads > 0 ? (det ? 3 : 4) * 256 / kPullThreads : 1; }
 // Tile shape: the pixels of a CTA re-read the gradient lines of the bins they share out of L1, and a
 // square tile meets fewer bins per ROI than a strip (bins of 6 x 6 pixels: 5.4 against 8.4 lines per
 // ROI).  Measured 2 x 32 / 4 x 16 / 8 x 8 on the whole backward: C2 143 / 140 / 137 us,
@@ -688,8 +691,10 @@ __global__ void __launch_bounds__(kPullThreads, pull_min_blocks(DET)) pull_bwd_k
   typedef typename EntryOf<WIDE>::type Entry;
   constexpr int CG = 32 * CPL;                        // channels per CTA
   // per warp: its 8 pixels x CG channels, [pixel][channel slot], and a ring of list entries
-  __shared__ __align__(16) float s_tile[kPullThreads / 32][8 * CG];
-  __shared__ __align__(16) Entry s_ent[kPullThreads / 32][2 * kEntChunk];
+  extern __shared__ __align__(16) unsigned char s_pull[];
+  float (*s_tile)[8 * CG] = reinterpret_cast<float (*)[8 * CG]>(s_pull);
+  Entry (*s_ent)[2 * kEntChunk] =
+      reinterpret_cast<Entry (*)[2 * kEntChunk]>(s_pull + sizeof(float) * (kPullThreads / 32) * 8 * CG);
   ptx::chain_enter();
   const Entry* entries = static_cast<const Entry*>(p.entries);
   float count = count0, inv = inv0;
@@ -1068,7 +1073,10 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
     auto k8 = pull_bwd_kernel<CPL, DET, ACC, 8, WIDE>;                                    \
     auto k4 = pull_bwd_kernel<CPL, DET, ACC, 4, WIDE>;                                    \
     auto kk = unroll == 4 ? k4 : k8;                                                      \
-    chained_launch(kk, grid, dim3(kPullThreads), 0, stream, p, count, inv, pow2);         \
+    const size_t smem = (size_t)(kPullThreads / 32) * (8 * 32 * CPL * sizeof(float) +    \
+                                                       2 * kEntChunk * (WIDE ? 16 : 8));  \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    chained_launch(kk, grid, dim3(kPullThreads), smem, stream, p, count, inv, pow2);      \
   } while (0)
 #define PULL_MODE(CPL)                                              \
   do {                                                              \

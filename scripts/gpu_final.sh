@@ -38,15 +38,7 @@ for wl in C4 C2 C3 C5; do
 done
 python scripts/ncu_traffic.py C4-batch-sharded gpurun_out/${TAG}_launches_C4.csv C2-box-head gpurun_out/${TAG}_launches_C2.csv \
     C3-mask-head gpurun_out/${TAG}_launches_C3.csv C5-stress-adaptive gpurun_out/${TAG}_launches_C5.csv > gpurun_out/${TAG}_traffic.json
-# full captures: the two main kernels and the table kernel of the default workload, the C2 pair, the C5 forward
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-secondary --workload C4"
-ncu --set full --clock-control none --import-source on -k regex:'resident_fwd2r_kernel|pull_bwd_kernel|pull_tables_kernel' -s 9 -c 3 -f -o gpurun_out/prof_${TAG}_C4 $CMD > gpurun_out/${TAG}_ncu_full_C4.log 2>&1
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-secondary --workload C2"
-ncu --set full --clock-control none --import-source on -k regex:'resident_fwd2r_kernel|pull_bwd_kernel|pull_tables_kernel' -s 9 -c 3 -f -o gpurun_out/prof_${TAG}_C2 $CMD > gpurun_out/${TAG}_ncu_full_C2.log 2>&1
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-secondary --workload C3"
-ncu --set full --clock-control none --import-source on -k regex:'resident_fwd2p_kernel|pull_bwd_kernel' -s 6 -c 2 -f -o gpurun_out/prof_${TAG}_C3 $CMD > gpurun_out/${TAG}_ncu_full_C3.log 2>&1
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-secondary --workload C5"
-ncu --set full --clock-control none --import-source on -k regex:'sweep_fwd_kernel|pull_bwd_kernel' -s 6 -c 2 -f -o gpurun_out/prof_${TAG}_C5 $CMD > gpurun_out/${TAG}_ncu_full_C5.log 2>&1
+if [ -n "$SKIP_FULL" ]; then echo "(full ncu captures skipped: run scripts/gpu_final_ncu.sh)"; else bash scripts/gpu_final_ncu.sh $TAG; fi
 for f in gpurun_out/${TAG}_bench_*.json; do python - "$f" <<'PY'
 import json, sys
 try:

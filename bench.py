@@ -342,7 +342,8 @@ def run_ours(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
+    from mobulaop_b200.testing import cuda_ready
+    if not cuda_ready():
         raise SystemExit('bench.py needs a CUDA device: the ROIAlign path has no CPU fallback')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)

@@ -5,6 +5,8 @@ absolute error against `atol`, then relative error |a-b| / (|b| + eps) against `
 `ulp_distance` / `assert_within_ulp_or_rel` express the stricter gates of this build:
 forward within 2 ULP or 1e-6 relative, backward within 1e-5 relative.
 """
+import os
+
 import numpy as np
 
 
@@ -105,3 +107,44 @@ def assert_scatter_close(a, b, abs_sum, rtol=1e-5):
         raise AssertionError('%d elements exceed %g x sum|summands|; worst at %s: %r vs %r '
                              '(error %g, sum|summands| %g)'
                              % (bad.sum(), rtol, idx, a[idx], b[idx], err[idx], s[idx]))
+
+
+def cuda_ready(timeout_s=45.0):
+    """True when a CUDA device is usable.  On a box that has just been started the first driver
+    initialisation can fail ("CUDA driver initialization failed") and succeed seconds later; a failed
+    first attempt sticks to the process that made it, so the driver is probed in short-lived child
+    processes (cuInit through ctypes, ~50 ms each) until it answers or `timeout_s` has passed, and only
+    then is torch asked.  Without a driver library (the CPU build container) this returns at once."""
+    import ctypes.util
+    import subprocess
+    import sys
+    import time
+    import glob
+    if not glob.glob('/dev/nvidia[0-9]*') and not os.environ.get('MOBULA_ASSUME_GPU'):
+        return False                    # no device node: nothing to wait for
+    if ctypes.util.find_library('cuda') is None:
+        try:
+            ctypes.CDLL('libcuda.so.1')
+        except OSError:
+            return False
+    probe = ("import ctypes, sys\n"
+             "lib = ctypes.CDLL('libcuda.so.1')\n"
+             "n = ctypes.c_int(0)\n"
+             "rc = lib.cuInit(0) or lib.cuDeviceGetCount(ctypes.byref(n))\n"
+             "sys.exit(0 if rc == 0 and n.value > 0 else (3 if rc == 0 else 4))\n")
+    deadline = time.time() + timeout_s
+    while True:
+        try:
+            rc = subprocess.run([sys.executable, '-c', probe], timeout=20).returncode
+        except Exception:
+            rc = 4
+        if rc == 0:
+            break
+        if rc == 3 or time.time() >= deadline:      # initialised, but no device / gave up
+            return False
+        time.sleep(1.0)
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except Exception:
+        return False

@@ -52,9 +52,13 @@ def native():
     return _native.load()
 
 
+_HAS_CUDA = None
+
+
 def has_cuda():
-    try:
-        import torch
-        return torch.cuda.is_available()
-    except Exception:
-        return False
+    """Cached; waits out the driver's start-up on a freshly started GPU box (see cuda_ready)."""
+    global _HAS_CUDA
+    if _HAS_CUDA is None:
+        from mobulaop_b200.testing import cuda_ready
+        _HAS_CUDA = cuda_ready()
+    return _HAS_CUDA

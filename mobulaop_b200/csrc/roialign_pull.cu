@@ -529,6 +529,26 @@ __device__ __forceinline__ void pull_transpose_block(const PullParams& p, unsign
     float4* dst4 = reinterpret_cast<float4*>(s_t);
     for (int q = threadIdx.x; q < quads; q += 256) dst4[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
     for (int i = (quads << 2) + threadIdx.x; i < total; i += 256) s_t[i] = __ldg(src + i);
+  } else if ((B & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    // B a multiple of 4 (the mask head's 14 x 14): 16-byte loads that never straddle two channels;
+    // (channel, bin) of a thread's quad advance by (1024 / B, 1024 % B) per step
+    const int quads = total >> 2;
+    const int dc = 1024 / B, db = 1024 - dc * B;
+    int c = (4 * threadIdx.x) / B, bb = 4 * threadIdx.x - c * B;
+    for (int q = threadIdx.x; q < quads; q += 256) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+      float* d = s_t + c * pitch + bb;
+      d[0] = v.x;
+      d[1] = v.y;
+      d[2] = v.z;
+      d[3] = v.w;
+      c += dc;
+      bb += db;
+      if (bb >= B) {
+        bb -= B;
+        ++c;
+      }
+    }
   } else {
     // (channel, bin) of element i advance by (256 / B, 256 % B) per step: no division in the loop
     const int dc = 256 / B, db = 256 - dc * B;
@@ -544,13 +564,20 @@ __device__ __forceinline__ void pull_transpose_block(const PullParams& p, unsign
     }
   }
   __syncthreads();
-  float* dst = p.dyt + (size_t)r * B * p.cw + c0;
   const int c = threadIdx.x & (kTrChannels - 1);
   if (c < ncw) {
-    const float* mine = s_t + c * pitch;
-    const bool real = c < nc;
-    for (int bb = threadIdx.x / kTrChannels; bb < B; bb += 256 / kTrChannels)
-      dst[(size_t)bb * p.cw + c] = real ? mine[bb] : 0.0f;
+    // pointers stepped per row of the copy: no 64-bit multiply in the loop
+    constexpr int kStep = 256 / kTrChannels;
+    int bb = threadIdx.x / kTrChannels;
+    float* d = p.dyt + ((size_t)r * B + bb) * p.cw + c0 + c;
+    const size_t dstep = (size_t)kStep * p.cw;
+    if (c < nc) {
+      const float* m = s_t + c * pitch + bb;
+#pragma unroll 4
+      for (; bb < B; bb += kStep, d += dstep, m += kStep) *d = *m;
+    } else {
+      for (; bb < B; bb += kStep, d += dstep) *d = 0.0f;
+    }
   }
 }
 

@@ -56,10 +56,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst_smem)), "l"(src_gmem) : "memory");
 }
-// 4-byte asynchronous copy global -> shared (LDGSTS.32): no register staging, any 4-byte placement
-__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst_smem)), "l"(src_gmem) : "memory");
-}
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }

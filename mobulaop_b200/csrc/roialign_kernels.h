@@ -131,9 +131,6 @@ struct ResidentPlan {
   int per_roi;         // sample entries per ROI: (PH + PW) * grid
   int fwd_two;         // the sampling_ratio == 2 forward (lane = sample column) applies
   int fwd_pair;        // ... on a channel pair (two padded planes fit shared memory)
-  int fwd_band;        // ... on row bands of a channel pair (a pair does not fit; resident_fwd2b_kernel)
-  int band_count, band_rows, band_stride, band_forced;
-  size_t band_smem;
   int ypairs, xslots;  // its table: row records (pairs) and column records per ROI
   size_t plane_bytes;  // (H + 1) * pitch * 4
   size_t fwd_smem;

@@ -23,8 +23,6 @@
 //
 // forward : products and sums in the reference's order (bilinear.h:50-56, ROIAlign.cpp:56-74)
 //           -> bit-identical output.
-#include <cstdlib>
-
 #include "roialign_kernels.h"
 #include "roialign_common.cuh"
 #include "ptx_sm100.cuh"
@@ -129,118 +127,6 @@ resident_fwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
     if (kk < 2 * pooled_w) s = make_sample(g.start_w, kk >> 1, g.bin_w, kk & 1, 2, width, unit);
   }
   entries[t] = make_uint2(s.lo_off, __float_as_uint(s.l));
-}
-
-// ---- banded channel-pair forward (resident_fwd2b_kernel): tables per (ROI, row band) ----------------
-// A plane too large for two channels to sit in shared memory together (the 200 x 272 box-head map) is
-// cut into `nb` overlapping bands of `band_rows` rows, `band_stride` rows apart.  A bin row of a ROI
-// belongs to the FIRST band that holds every plane row its two sample rows touch (its samples outside
-// the plane touch nothing); a bin row no band can hold -- its sample rows are further apart than the
-// bands overlap: a ROI several times the plane -- is marked "slow" and computed from global memory
-// by band 0's visit.  Band b sees band-relative row offsets; rows it does not own point at the
-// band's zero rows.
-struct BandGeom {
-  int nb, band_rows, band_stride;
-};
-
-// band of bin row ph: 0 .. nb - 1, or -1 = slow
-__device__ __forceinline__ int band_of_bin_row(const RoiGeom& g, int ph, int height, const BandGeom& bg) {
-  const AxisTap t0 = axis_decode(sample_pos(g.start_h, ph, g.bin_h, 0, 2), height);
-  const AxisTap t1 = axis_decode(sample_pos(g.start_h, ph, g.bin_h, 1, 2), height);
-  if (!t0.valid && !t1.valid) return 0;
-  const int lo = t0.valid ? (t1.valid ? min(t0.lo, t1.lo) : t0.lo) : t1.lo;
-  const int hi = t0.valid ? (t1.valid ? max(t0.lo, t1.lo) : t0.lo) : t1.lo;
-  for (int b = 0; b < bg.nb; ++b) {
-    const int b0 = b * bg.band_stride;
-    if (lo >= b0 && hi + 1 <= b0 + bg.band_rows) return b;       // the high tap row is hi + 1
-  }
-  return -1;
-}
-
-// per (ROI at grouped position j, band b): `ypairs` 16-byte row records, `xslots` 8-byte column
-// records (as resident_fwd2_table_kernel, 8 bytes per pixel), then one 16-byte record
-// {mask of the bin rows this band owns, mask of the slow bin rows (band 0 only), 0, 0}
-__global__ void __launch_bounds__(256)
-resident_fwd2b_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
-                            const int* __restrict__ img_start, int num_images, int height, int width,
-                            int pitch, int pooled_h, int pooled_w, float scale, int ypairs, int xslots,
-                            BandGeom bg, uint2* __restrict__ entries) {
-  ptx::chain_enter();
-  const int per = 2 * ypairs + xslots + 2;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int valid = __ldg(img_start + num_images);
-  if (t >= (long long)valid * bg.nb * per) return;
-  const int k = (int)(t % per);
-  const long long jb = t / per;
-  const int b = (int)(jb % bg.nb), j = (int)(jb / bg.nb);
-  const int roi = __ldg(order + j);
-  const RoiGeom g = roi_decode(rois + (size_t)roi * 5, scale, pooled_h, pooled_w, 2);
-  const unsigned row_stride = (unsigned)(pitch * 8);
-  const unsigned zero_row = (unsigned)(bg.band_rows + 1) * row_stride;
-  const int b0 = b * bg.band_stride;
-  uint2 rec;
-  if (k < 2 * ypairs) {
-    rec = make_uint2(zero_row, 0u);
-    const int ph = k >> 1;
-    if (k < 2 * pooled_h && band_of_bin_row(g, ph, height, bg) == b) {
-      const AxisTap ty = axis_decode(sample_pos(g.start_h, ph, g.bin_h, k & 1, 2), height);
-      if (ty.valid) rec = make_uint2((unsigned)(ty.lo - b0) * row_stride, __float_as_uint(ty.wl));
-      // row reuse code against the previous sample row of this band's walk (see resident_fwd2_table_kernel)
-      bool have_prev = (k & 1) != 0;
-      if (!have_prev && ph > 0) have_prev = band_of_bin_row(g, ph - 1, height, bg) == b;
-      if (have_prev) {
-        const AxisTap tp = axis_decode(sample_pos(g.start_h, (k - 1) >> 1, g.bin_h, (k - 1) & 1, 2), height);
-        const unsigned prev = tp.valid ? (unsigned)(tp.lo - b0) * row_stride : zero_row;
-        if (rec.x == prev) rec.x |= 2u;
-        else if (rec.x == prev + row_stride) rec.x |= 1u;
-      }
-    }
-  } else if (k < 2 * ypairs + xslots) {
-    const int kk = k - 2 * ypairs;
-    AxisSample sx;
-    sx.lo_off = (unsigned)((width + 1) * 8);
-    sx.l = 0.0f;
-    if (kk < 2 * pooled_w) sx = make_sample(g.start_w, kk >> 1, g.bin_w, kk & 1, 2, width, 8);
-    rec = make_uint2(sx.lo_off, __float_as_uint(sx.l));
-  } else if (k == 2 * ypairs + xslots) {
-    unsigned own = 0u, slow = 0u;
-    for (int ph = 0; ph < pooled_h; ++ph) {
-      const int bb = band_of_bin_row(g, ph, height, bg);
-      if (bb == b) own |= 1u << ph;
-      if (bb < 0 && b == 0) slow |= 1u << ph;
-    }
-    rec = make_uint2(own, slow);
-  } else {
-    rec = make_uint2(0u, 0u);
-  }
-  entries[t] = rec;
-}
-
-// per (image, band): the ROIs (grouped positions, ascending) with a bin row of their own in the band
-// -- or, for band 0, a slow one -- so that the main kernel pairs ROIs that are both at work there.
-// list of segment s = (n, b) at lists[img_start[n] * nb + b * (ROIs of n)], its length in len[s]
-__global__ void __launch_bounds__(256)
-resident_fwd2b_lists_kernel(const int* __restrict__ img_start, int num_images, int per, int mask_at, int nb,
-                            const uint2* __restrict__ entries, int* __restrict__ lists, int* __restrict__ len) {
-  ptx::chain_enter();
-  __shared__ int warp_sums[8];
-  const int sgm = blockIdx.x, n = sgm / nb, b = sgm - n * nb;
-  const int j0 = __ldg(img_start + n), j1 = __ldg(img_start + n + 1);
-  int* mine = lists + (size_t)j0 * nb + (size_t)b * (j1 - j0);
-  int running = 0;
-  for (int base = j0; base < j1; base += 256) {
-    const int j = base + threadIdx.x;
-    int flag = 0;
-    if (j < j1) {
-      const uint2 m = __ldg(entries + ((size_t)j * nb + b) * per + mask_at);
-      flag = (m.x | m.y) != 0u ? 1 : 0;
-    }
-    int total;
-    const int pos = block_exclusive_scan<256>(flag, &total, warp_sums);
-    if (flag) mine[running + pos] = j;
-    running += total;
-  }
-  if (threadIdx.x == 0) len[sgm] = running;
 }
 
 // ---- plane movement ----------------------------------------------------------------------
@@ -1079,274 +965,6 @@ resident_fwd2pr_kernel(const float* __restrict__ data, float* __restrict__ out, 
           t.x = __fadd_rn(t.x, __shfl_down_sync(0xffffffffu, s1.x, 1));
           t.y = __fadd_rn(t.y, __shfl_down_sync(0xffffffffu, s1.y, 1));
           if (stores[ch] && have) {
-            float* o = optr + it * pooled_w + 8 * ch;
-            const float y0 = __fmul_rn(t.x, 0.25f), y1 = __fmul_rn(t.y, 0.25f);     // count = 4: exact
-            if (ACC) {
-              o[0] = __fadd_rn(o[0], y0);
-              if (two) o[bins] = __fadd_rn(o[bins], y1);
-            } else if (TYPED) {      // fp16 / bf16 storage
-              store_top(out, (size_t)(o - out), y0, odt);
-              if (two) store_top(out, (size_t)(o - out) + bins, y1, odt);
-            } else {
-              o[0] = y0;
-              if (two) o[bins] = y1;
-            }
-          }
-        }
-      }
-    }
-  }
-}
-
-// ---- the channel-pair forward on ROW BANDS of a plane too large for a resident pair -------------
-// (the 200 x 272 box-head map: two padded planes are 435 KB).  Same scheme as
-// resident_fwd2pr_kernel -- 8-byte taps that serve two channels, served per half-warp so a load
-// touches one feature-map row and the two half-warps never conflict, weights and addresses shared by
-// the pair -- on the bands of resident_fwd2b_table_kernel: a unit is (image, channel pair, band),
-// a ROI is visited by every band of its image and computes there the bin rows that band owns.
-// rows [0, nload) of the band's shared-memory image come from the plane, row nload repeats the last
-// one when the band ends at the plane's bottom; rows band_rows + 1, + 2 are zero
-__device__ __forceinline__ void load_band_pair(float2* plane, const float* __restrict__ src0,
-                                               const float* __restrict__ src1, int nload, int width, int pitch,
-                                               bool bottom) {
-  // 4-byte asynchronous copies (a pixel's two channels come from two planes): nothing is staged in
-  // registers, every thread has its whole share in flight at once -- the band arrives at the rate
-  // of the memory system, not one L2 latency per loop trip
-  {
-    const int total = nload * width;
-    int r = threadIdx.x / width, x = threadIdx.x - r * width;
-    const int dr = blockDim.x / width, dx = blockDim.x - dr * width;
-    float* dst = reinterpret_cast<float*>(plane);
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      float* d = dst + 2 * ((size_t)r * pitch + x);
-      ptx::cp_async4(d, src0 + i);
-      if (src1) ptx::cp_async4(d + 1, src1 + i);
-      else d[1] = 0.0f;
-      r += dr;
-      x += dx;
-      if (x >= width) {
-        x -= width;
-        ++r;
-      }
-    }
-    ptx::cp_async_wait_all();
-  }
-  __syncthreads();
-  for (int r = threadIdx.x; r < nload; r += blockDim.x) plane[r * pitch + width] = plane[r * pitch + width - 1];
-  __syncthreads();
-  if (bottom)
-    for (int x = threadIdx.x; x <= width; x += blockDim.x) plane[nload * pitch + x] = plane[(nload - 1) * pitch + x];
-  __syncthreads();
-}
-
-// a bin row no band can hold, straight from global memory (reference order; rare: ROIs several
-// times the height of the plane); lane q of the half-warp = bin column q
-__device__ __forceinline__ void band_slow_rows(unsigned slow, int q, const float* __restrict__ rois, int roi, float scale,
-                                               const float* __restrict__ src0, const float* __restrict__ src1,
-                                               int height, int width, int pooled_h, int pooled_w, float* __restrict__ out,
-                                               size_t o_base, int bins, bool accumulate, bool typed, int odt) {
-  if (q >= pooled_w) return;
-  const RoiGeom g = roi_decode(rois + (size_t)roi * 5, scale, pooled_h, pooled_w, 2);
-  for (int ph = 0; ph < pooled_h; ++ph) {
-    if (!((slow >> ph) & 1u)) continue;
-    float acc0 = 0.0f, acc1 = 0.0f;
-    for (int iy = 0; iy < 2; ++iy) {
-      const AxisTap ty = axis_decode(sample_pos(g.start_h, ph, g.bin_h, iy, 2), height);
-      if (!ty.valid) continue;
-      for (int ix = 0; ix < 2; ++ix) {
-        const AxisTap tx = axis_decode(sample_pos(g.start_w, q, g.bin_w, ix, 2), width);
-        if (!tx.valid) continue;
-        const float w1 = __fmul_rn(ty.wh, tx.wh), w2 = __fmul_rn(ty.wh, tx.wl);
-        const float w3 = __fmul_rn(ty.wl, tx.wh), w4 = __fmul_rn(ty.wl, tx.wl);
-        const int o1 = ty.lo * width + tx.lo, o2 = ty.lo * width + tx.hi;
-        const int o3 = ty.hi * width + tx.lo, o4 = ty.hi * width + tx.hi;
-        acc0 = __fadd_rn(acc0, tap_sum(w1, __ldg(src0 + o1), w2, __ldg(src0 + o2), w3, __ldg(src0 + o3), w4, __ldg(src0 + o4)));
-        if (src1)
-          acc1 = __fadd_rn(acc1, tap_sum(w1, __ldg(src1 + o1), w2, __ldg(src1 + o2), w3, __ldg(src1 + o3), w4, __ldg(src1 + o4)));
-      }
-    }
-    const size_t at = o_base + (size_t)ph * pooled_w + q;
-    const float y0 = __fmul_rn(acc0, 0.25f), y1 = __fmul_rn(acc1, 0.25f);
-    if (accumulate) {
-      out[at] = __fadd_rn(out[at], y0);
-      if (src1) out[at + bins] = __fadd_rn(out[at + bins], y1);
-    } else if (typed) {
-      store_top(out, at, y0, odt);
-      if (src1) store_top(out, at + bins, y1, odt);
-    } else {
-      out[at] = y0;
-      if (src1) out[at + bins] = y1;
-    }
-  }
-}
-
-template <int PH, int NCH, bool ACC, bool TYPED>
-__global__ void __launch_bounds__(kFwd2Threads, 1)
-resident_fwd2b_kernel(const float* __restrict__ data, float* __restrict__ out, const float* __restrict__ rois,
-                      const int* __restrict__ order, const int* __restrict__ img_start,
-                      const uint2* __restrict__ entries, const int* __restrict__ lists, const int* __restrict__ len,
-                      int num_images, int channels, int c_count, int height,
-                      int width, int pitch, int pooled_h, int pooled_w, float scale, BandGeom bg, int odt) {
-  ptx::chain_enter();
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2* plane = reinterpret_cast<float2*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int bins = pooled_h * pooled_w;
-  constexpr int kIters = (PH + 1) / 2;
-  constexpr int kPerRoi = 4 * kIters + 16 * NCH + 2;      // uint2 records per (ROI, band)
-  const size_t plane_elems = (size_t)height * width;
-  const int h = lane >> 4, q = lane & 15;
-  const unsigned sbase = ptx::smem_addr(smem_raw);
-  const unsigned row_bytes = (unsigned)pitch * 8u;
-  const int cpairs = (c_count + 1) >> 1;
-  const int nb = bg.nb;
-
-  // columns beyond W + 1 of the band's rows and its two zero rows (band_rows + 1, + 2)
-  zero_padding(reinterpret_cast<float*>(smem_raw), bg.band_rows, 2 * width + 1, 2 * pitch);
-  __syncthreads();
-  if (!ACC)
-    zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
-                              (long long)c_count * bins, TYPED ? odt : kTopF32);
-
-  bool stores[NCH];
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) stores[ch] = (q & 1) == 0 && 8 * ch + (q >> 1) < pooled_w;
-
-  // prefix sums of the segment lengths (segments = (image, band) pairs), behind the band in shared memory
-  int* seg_at = reinterpret_cast<int*>(smem_raw + (size_t)(bg.band_rows + 3) * pitch * 8);
-  const int nseg = num_images * nb;
-  if (tid == 0) {
-    int run = 0;
-    for (int sg = 0; sg < nseg; ++sg) {
-      seg_at[sg] = run;
-      run += __ldg(len + sg);
-    }
-    seg_at[nseg] = run;
-  }
-  __syncthreads();
-  long long u, u1;
-  cta_share((long long)cpairs * seg_at[nseg], u, u1);
-  int sgm = 0;
-  unsigned epoch = 0;
-  while (u < u1) {
-    // the next (segment, channel pair, list range) of this CTA's share
-    while ((long long)cpairs * seg_at[sgm + 1] <= u) ++sgm;
-    PlaneWork w;
-    w.n = sgm / nb;
-    const int b = sgm - w.n * nb;
-    const int seg_len = seg_at[sgm + 1] - seg_at[sgm];
-    {
-      const long long rel = u - (long long)cpairs * seg_at[sgm];
-      w.c = (int)(rel / seg_len);
-      w.jj0 = (int)(rel - (long long)w.c * seg_len);
-      w.jj1 = (int)min((long long)seg_len, w.jj0 + (u1 - u));
-      u += w.jj1 - w.jj0;
-    }
-    const int img_j0 = __ldg(img_start + w.n);
-    const int* list = lists + (size_t)img_j0 * nb + (size_t)b * (__ldg(img_start + w.n + 1) - img_j0);
-    const int cp = w.c;
-    const int c = 2 * cp;
-    const bool two = c + 1 < c_count;
-    const int b0 = b * bg.band_stride;
-    const int nload = min(bg.band_rows + 1, height - b0);
-    __syncthreads();   // every warp is done reading the previous band
-    const float* src0 = data + ((size_t)w.n * channels + c) * plane_elems;
-    const float* src1 = two ? src0 + plane_elems : nullptr;
-    // (a band that ends exactly on the plane's last row has no room, and no use, for the repeated row)
-    load_band_pair(plane, src0 + (size_t)b0 * width, two ? src1 + (size_t)b0 * width : nullptr, nload, width, pitch,
-                   b0 + nload == height && nload <= bg.band_rows);
-    ++epoch;
-
-    // two ROIs per warp, half-warp h on its own ROI (see resident_fwd2r_kernel); the records of
-    // the NEXT pair (masks, first row records, column records, output row) are fetched a pair ahead
-    // (list positions -> grouped positions: one more load, issued with the next pair's records)
-    auto mine = [&](int pair_jj) { return __ldg(list + min(pair_jj + h, w.jj1 - 1)); };
-    constexpr int kHead = PH < kRowsAhead ? PH : kRowsAhead;
-    struct BandHead {
-      const uint2* ent;
-      uint2 masks;
-      uint4 y[kHead];
-      uint2 x[NCH];
-      int roi;
-    };
-    auto load_head = [&](BandHead& hd, int pair_jj) {
-      const int j = mine(pair_jj);
-      const uint2* ent = entries + ((size_t)j * nb + b) * kPerRoi;
-      hd.ent = ent;
-      hd.masks = __ldg(ent + 4 * kIters + 16 * NCH);
-#pragma unroll
-      for (int it = 0; it < kHead; ++it) hd.y[it] = __ldg(reinterpret_cast<const uint4*>(ent) + it);
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) hd.x[ch] = __ldg(ent + 4 * kIters + min(16 * ch + q, 2 * pooled_w - 1));
-      hd.roi = __ldg(order + j);
-    };
-    int jj = w.jj0 + 2 * warp;
-    BandHead nxt;
-    if (jj < w.jj1) load_head(nxt, jj);
-    for (; jj < w.jj1; jj += 2 * kFwd2Warps) {
-      const bool have = jj + h < w.jj1;
-      const BandHead cur = nxt;
-      const uint4* ent_y = reinterpret_cast<const uint4*>(cur.ent);
-      if (jj + 2 * kFwd2Warps < w.jj1) load_head(nxt, jj + 2 * kFwd2Warps);
-      const unsigned own = have ? cur.masks.x : 0u, slow = have ? cur.masks.y : 0u;
-      if (!__any_sync(0xffffffffu, (own | slow) != 0u)) continue;      // neither ROI has a bin row in this band
-      const int roi = cur.roi;
-      const size_t o_base = ((size_t)roi * channels + c) * bins;
-      if (slow) band_slow_rows(slow, q, rois, roi, scale, src0, src1, height, width, pooled_h, pooled_w, out, o_base,
-                               bins, ACC, TYPED, odt);
-      if (!__any_sync(0xffffffffu, own != 0u)) continue;
-      uint4 ys[PH];
-#pragma unroll
-      for (int it = 0; it < kHead; ++it) ys[it] = cur.y[it];
-#pragma unroll
-      for (int it = kHead; it < PH; ++it) ys[it] = __ldg(ent_y + it);
-      unsigned xa[NCH], xb[NCH];      // shared-memory address of the low column in row 0 / row 1
-      float lx[NCH], hx[NCH];
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        xa[ch] = sbase + cur.x[ch].x;
-        xb[ch] = xa[ch] + row_bytes;
-        lx[ch] = __uint_as_float(cur.x[ch].y);
-        hx[ch] = __fsub_rn(1.0f, lx[ch]);
-      }
-      float* optr = out + o_base + (q >> 1);
-      Taps2 tp[NCH];
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) tp[ch].plo = tp[ch].phi = tp[ch].clo = tp[ch].chi = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int it = 0; it < PH; ++it) {
-        const bool act = (own >> it) & 1u;
-        if (!__any_sync(0xffffffffu, act)) continue;       // this bin row belongs to another band for both ROIs
-        const uint4 ey = ys[it];
-        const float ly0 = __uint_as_float(ey.y), ly1 = __uint_as_float(ey.w);
-        const float hy0 = __fsub_rn(1.0f, ly0), hy1 = __fsub_rn(1.0f, ly1);
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          // (a half-warp whose ROI does not own this row reads the band's zero rows: its records say so)
-          auto sample = [&](unsigned row_code, float hy, float ly) {
-            const unsigned row = row_code & ~kRowCodeMask;
-            taps2_advance(tp[ch], xa[ch] + row, xb[ch] + row, row_code & kRowCodeMask, epoch);
-            const float2 v1 = tp[ch].plo, v2 = tp[ch].phi, v3 = tp[ch].clo, v4 = tp[ch].chi;
-            const float w1 = __fmul_rn(hy, hx[ch]), w2 = __fmul_rn(hy, lx[ch]);
-            const float w3 = __fmul_rn(ly, hx[ch]), w4 = __fmul_rn(ly, lx[ch]);
-            const float2 p1 = __fmul2_rn(make_float2(w1, w1), v1), p2 = __fmul2_rn(make_float2(w2, w2), v2);
-            const float2 p3 = __fmul2_rn(make_float2(w3, w3), v3), p4 = __fmul2_rn(make_float2(w4, w4), v4);
-            float2 sm;
-            sm.x = __fadd_rn(__fadd_rn(__fadd_rn(p1.x, p2.x), p3.x), p4.x);
-            sm.y = __fadd_rn(__fadd_rn(__fadd_rn(p1.y, p2.y), p3.y), p4.y);
-            return sm;
-          };
-          const float2 s0 = sample(ey.x, hy0, ly0), s1 = sample(ey.z, hy1, ly1);
-          float2 t;
-          t.x = __fadd_rn(0.0f, s0.x);
-          t.y = __fadd_rn(0.0f, s0.y);
-          t.x = __fadd_rn(t.x, __shfl_down_sync(0xffffffffu, s0.x, 1));
-          t.y = __fadd_rn(t.y, __shfl_down_sync(0xffffffffu, s0.y, 1));
-          t.x = __fadd_rn(t.x, s1.x);
-          t.y = __fadd_rn(t.y, s1.y);
-          t.x = __fadd_rn(t.x, __shfl_down_sync(0xffffffffu, s1.x, 1));
-          t.y = __fadd_rn(t.y, __shfl_down_sync(0xffffffffu, s1.y, 1));
-          if (stores[ch] && act) {
             float* o = optr + it * pooled_w + 8 * ch;
             const float y0 = __fmul_rn(t.x, 0.25f), y1 = __fmul_rn(t.y, 0.25f);     // count = 4: exact
             if (ACC) {
@@ -2368,37 +1986,6 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
   plan->fwd_two = two ? 1 : 0;
   // channel-pair variant of the sampling_ratio == 2 forward: two padded planes must fit
   plan->fwd_pair = (two && 2 * plane_bytes + 64 <= (size_t)smem_optin) ? 1 : 0;
-  {
-    // MOBULA_FWD_PAIR=0: single-plane kernels even where a channel pair fits (experiments)
-    static const int pair_ok = [] { const char* e = getenv("MOBULA_FWD_PAIR"); return e ? atoi(e) : 1; }();
-    if (!pair_ok) plan->fwd_pair = 0;
-  }
-  // banded channel pair (resident_fwd2b_kernel): a pair does not fit, odd pooled heights up to 7;
-  // bands as short as an overlap of kBandOverlap rows allows (fewer rows loaded twice), at least two
-  plan->fwd_band = 0;
-  plan->band_count = plan->band_rows = plan->band_stride = 0;
-  if (two && !plan->fwd_pair && (a.pooled_h & 1) && a.pooled_h <= 7 && a.num_images >= 1 && a.num_images <= 1024) {
-    constexpr int kBandOverlap = 16;
-    const size_t row_bytes = (size_t)pitch * 8;
-    // (+ repeat row + two zero rows; 16 KB stay free for the segment prefix sums: <= 4 bands x 1024 images)
-    const int max_rows = (int)(((size_t)smem_optin - 64 - 16 * 1024) / row_bytes) - 3;
-    if (max_rows > 2 * kBandOverlap) {
-      int nb = 2;
-      while ((long long)nb * max_rows - (long long)(nb - 1) * kBandOverlap < a.height) ++nb;
-      const int rows = (a.height + (nb - 1) * kBandOverlap + nb - 1) / nb;       // <= max_rows
-      plan->fwd_band = nb <= 4 ? 1 : 0;
-      plan->band_count = nb;
-      plan->band_rows = rows;
-      plan->band_stride = rows - kBandOverlap;
-      plan->band_smem = (size_t)(rows + 3) * row_bytes;
-    }
-  }
-  {
-    // MOBULA_FWD_BAND=0 / 1: force the single-plane / the banded pair kernels (default: see launch_fwd_resident)
-    static const int band_env = [] { const char* e = getenv("MOBULA_FWD_BAND"); return e ? atoi(e) : -1; }();
-    if (band_env == 0) plan->fwd_band = 0;
-    plan->band_forced = band_env == 1 ? 1 : 0;
-  }
   plan->ypairs = 2 * ((a.pooled_h + 1) / 2);
   plan->xslots = 16 * ((2 * a.pooled_w + 15) / 16);
   plan->plane_bytes = plane_bytes;
@@ -2450,17 +2037,9 @@ bool resident_supported(const RoiAlignArgs& a, const void* plane_ptr, int smem_o
   return true;
 }
 
-static bool use_band(const ResidentPlan& plan) { return plan.fwd_band && plan.band_forced; }
-
 size_t resident_fwd_workspace(const RoiAlignArgs& a, const ResidentPlan& plan) {
-  size_t per_roi = plan.fwd_two ? (size_t)(2 * plan.ypairs + plan.xslots) * sizeof(uint2)
-                                : (size_t)plan.per_roi * sizeof(uint4);
-  if (use_band(plan)) {
-    per_roi = (size_t)plan.band_count * (2 * plan.ypairs + plan.xslots + 2) * sizeof(uint2);
-    // + the per-(image, band) ROI lists and their lengths
-    return fwd_layout(a, per_roi).total + align_up((size_t)a.num_rois * plan.band_count * sizeof(int), 256) +
-           align_up((size_t)(a.num_images * plan.band_count + 2) * sizeof(int), 256) + 512;
-  }
+  const size_t per_roi = plan.fwd_two ? (size_t)(2 * plan.ypairs + plan.xslots) * sizeof(uint2)
+                                      : (size_t)plan.per_roi * sizeof(uint4);
   return fwd_layout(a, per_roi).total;
 }
 
@@ -2470,9 +2049,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   if (a.num_rois == 0 || a.channels == 0) return cudaSuccess;
   const size_t per_roi_bytes = plan.fwd_two ? (size_t)(2 * plan.ypairs + plan.xslots) * sizeof(uint2)
                                             : (size_t)plan.per_roi * sizeof(uint4);
-  const bool band = use_band(plan);
-  const FwdLayout l = fwd_layout(a, band ? (size_t)plan.band_count * (2 * plan.ypairs + plan.xslots + 2) * sizeof(uint2)
-                                         : per_roi_bytes);
+  const FwdLayout l = fwd_layout(a, per_roi_bytes);
   char* base = (char*)workspace;
   int* img_start = (int*)(base + l.img_start);
   int* order = (int*)(base + l.order);
@@ -2481,59 +2058,6 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   const int cc = a.c_count > 0 ? a.c_count : a.channels;      // channels worked on (stride: a.channels)
   const long long work = (long long)a.num_rois * cc;
   unsigned grid = 0;
-  if (band) {
-    uint2* entries = (uint2*)(base + l.entries);
-    BandGeom bg;
-    bg.nb = plan.band_count;
-    bg.band_rows = plan.band_rows;
-    bg.band_stride = plan.band_stride;
-    const int per = 2 * plan.ypairs + plan.xslots + 2;
-    const long long threads = (long long)a.num_rois * bg.nb * per;
-    chained_launch(resident_fwd2b_table_kernel, (unsigned)((threads + 255) / 256), 256, 0, stream, a.rois, order,
-                   img_start, a.num_images, a.height, a.width, plan.pitch, a.pooled_h, a.pooled_w, a.scale,
-                   plan.ypairs, plan.xslots, bg, entries);
-    count_launch();
-    // per (image, band) ROI lists + lengths, behind the records
-    const size_t ent_bytes = align_up((size_t)a.num_rois * bg.nb * per * sizeof(uint2), 256);
-    int* lists = (int*)(base + l.entries + ent_bytes);
-    int* seg_len = (int*)(base + l.entries + ent_bytes + align_up((size_t)a.num_rois * bg.nb * sizeof(int), 256));
-    chained_launch(resident_fwd2b_lists_kernel, (unsigned)(a.num_images * bg.nb), 256, 0, stream, img_start,
-                   a.num_images, per, 2 * plan.ypairs + plan.xslots, bg.nb, (const uint2*)entries, lists, seg_len);
-    count_launch();
-    const long long units = (long long)a.num_rois * ((cc + 1) / 2) * bg.nb;       // an upper bound: sizes the grid only
-    const size_t bsmem = plan.band_smem + (size_t)(a.num_images * bg.nb + 1) * sizeof(int);
-#define MOBULA_FWD2B(PH, NCH, ACC, TYPED)                                                                          \
-  do {                                                                                                             \
-    e = resident_grid(resident_fwd2b_kernel<PH, NCH, ACC, TYPED>, kFwd2Threads, bsmem, num_sms, units, &grid);     \
-    if (e != cudaSuccess) return e;                                                                                \
-    chained_launch(resident_fwd2b_kernel<PH, NCH, ACC, TYPED>, grid, kFwd2Threads, bsmem, stream, data,            \
-                   out, a.rois, order, img_start, entries, (const int*)lists, (const int*)seg_len, a.num_images,   \
-                   a.channels, cc, a.height, a.width, plan.pitch, a.pooled_h, a.pooled_w, a.scale, bg,             \
-                   a.top_dtype);                                                                                   \
-  } while (0)
-#define MOBULA_FWD2B_PH(PH)                                          \
-  do {                                                               \
-    if (plan.xslots == 16) {                                         \
-      if (accumulate) MOBULA_FWD2B(PH, 1, true, false);              \
-      else if (a.top_dtype != 0) MOBULA_FWD2B(PH, 1, false, true);   \
-      else MOBULA_FWD2B(PH, 1, false, false);                        \
-    } else {                                                         \
-      if (accumulate) MOBULA_FWD2B(PH, 2, true, false);              \
-      else if (a.top_dtype != 0) MOBULA_FWD2B(PH, 2, false, true);   \
-      else MOBULA_FWD2B(PH, 2, false, false);                        \
-    }                                                                \
-  } while (0)
-    switch (a.pooled_h) {
-      case 1: MOBULA_FWD2B_PH(1); break;
-      case 3: MOBULA_FWD2B_PH(3); break;
-      case 5: MOBULA_FWD2B_PH(5); break;
-      default: MOBULA_FWD2B_PH(7); break;
-    }
-#undef MOBULA_FWD2B_PH
-#undef MOBULA_FWD2B
-    count_launch();
-    return cudaGetLastError();
-  }
   if (plan.fwd_two) {
     uint2* entries = (uint2*)(base + l.entries);
     const long long threads = (long long)a.num_rois * (2 * plan.ypairs + plan.xslots);

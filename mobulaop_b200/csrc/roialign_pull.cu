@@ -472,6 +472,148 @@ __device__ __forceinline__ void pull_list_block(const PullParams& p, unsigned bl
   if (total) mine[total - 1].x |= 8u;       // the last entry of the pixel (written by this thread)
 }
 
+// ---- grouped lists (merged taps only): one entry per (ROI, bin, row) and GROUP of 8 pixels -------
+// A bin of a box-head ROI covers ~3.4 consecutive pixels of a row, and the per-pixel kernel loads
+// the bin's gradient line once for each of them (its LSU data pipe is 88 % busy with those loads).
+// Here the 8 pixels a warp of the main kernel owns share ONE entry per bin: the line's offset and
+// the 8 weights (0 where the bin does not reach the pixel).  The line is loaded once and multiplied
+// into 8 accumulator sets held in registers.  A pixel meets its bins in the same order as in the
+// per-pixel lists (ROI ascending, row tap, bin column), so the sums are the same fused
+// multiply-adds in the same order -- bit-identical to the per-pixel merged kernel.
+struct GroupEntry {
+  unsigned hdr;        // byte offset of the bin's channel row in dyt (a multiple of 16) | pixel-pair mask:
+                       // bit q set = pixel 2q or 2q + 1 has a non-zero weight
+  unsigned pad[3];
+  float w[8];
+};
+static_assert(sizeof(GroupEntry) == 48, "GroupEntry is three 16-byte words");
+
+// Same walk as pull_walk, lane = pixel; the 8 lanes of a group execute in lock step (what they
+// branch on is the same for the whole group) and write one weight each.
+template <bool FILL>
+__device__ __forceinline__ unsigned pull_walk8(const PullParams& p, int n, int y, int x0, int lane, GroupEntry* out) {
+  const int x = x0 + lane;
+  const bool in = x < p.width;
+  const int j = lane & 7, gshift = lane & ~7;
+  const int xg0 = x0 + gshift, xg1 = xg0 + 7;
+  const unsigned gmask = 0xffu << gshift;
+  const int w_lo = mask_word0(p.img_start, n), w_hi = mask_word0(p.img_start, n + 1);
+  const int B = p.pooled_h * p.pooled_w;
+  unsigned total = 0;
+  for (int wbase = w_lo; wbase < w_hi; wbase += 32) {
+    const unsigned my_word = wbase + lane < w_hi ? __ldg(p.rowmask + (size_t)y * p.tw + wbase + lane) : 0u;
+    unsigned words = __ballot_sync(0xffffffffu, my_word != 0u);
+    while (words) {
+      const int wj = __ffs(words) - 1;
+      words &= words - 1;
+      const int wg = wbase + wj;
+      const unsigned m = __shfl_sync(0xffffffffu, my_word, wj);
+      unsigned my_r = 0, my_x = 0;
+      bool cand = (m >> lane) & 1u;
+      if (cand) {
+        const int pos = ((wg - n) << 5) + lane;
+        const uint2 box = __ldg(reinterpret_cast<const uint2*>(p.gbox + pos));
+        const int xmin = (int)(box.y & 0xffffu), xmax = (int)(box.y >> 16);
+        cand = !(xmax < x0 || xmin > x0 + 31);
+        if (cand) {
+          const unsigned short* yi = p.yidx + (size_t)pos * (p.height + 2) + (y - (int)(box.x & 0xffffu));
+          const unsigned ra = __ldg(yi), rb = __ldg(yi + 1);
+          cand = ra != rb;
+          my_r = ra | (rb << 16);
+          my_x = box.y;
+        }
+      }
+      unsigned live = __ballot_sync(0xffffffffu, cand);
+      while (live) {
+        const int b = __ffs(live) - 1;
+        live &= live - 1;
+        const int pos = ((wg - n) << 5) + b;
+        const unsigned rr = __shfl_sync(0xffffffffu, my_r, b), xx = __shfl_sync(0xffffffffu, my_x, b);
+        const int ra = (int)(rr & 0xffffu), rb = (int)(rr >> 16);
+        const int xmin = (int)(xx & 0xffffu), xmax = (int)(xx >> 16);
+        const unsigned short* xi = p.xidx + (size_t)pos * (p.width + 2);
+        const uint2* xt = p.xtap + (size_t)pos * p.capx;
+        // the bin columns that reach the group: the taps of its pixels are one run, sorted by
+        // (pixel, bin column), and every bin column between the first and the last one is present
+        int npw = 0, pwf = 0;
+        const int glo = max(xg0, xmin), ghi = min(xg1, xmax);
+        if (glo <= ghi) {
+          const int ga = __ldg(xi + (glo - xmin)), gb = __ldg(xi + (ghi + 1 - xmin));
+          if (gb > ga) {
+            pwf = (int)(__ldg(&xt[ga].x) >> 23);
+            npw = (int)(__ldg(&xt[gb - 1].x) >> 23) - pwf + 1;
+          }
+        }
+        if (!FILL) {
+          total += (unsigned)((rb - ra) * npw);
+          continue;
+        }
+        if (npw == 0) continue;
+        int ca = 0, cb = 0;
+        if (in && x >= xmin && x <= xmax) {
+          ca = __ldg(xi + (x - xmin));
+          cb = __ldg(xi + (x - xmin) + 1);
+        }
+        const unsigned base = (unsigned)__ldg(p.order + pos) * (unsigned)B;
+        const uint2* yt = p.ytap + (size_t)pos * p.capy;
+        const unsigned cwb = (unsigned)(p.cw * 4);
+        for (int a = ra; a < rb; ++a) {
+          const uint2 ya = __ldg(yt + a);
+          const unsigned ph = ya.x >> 23;
+          const float wy = __uint_as_float(ya.y);
+          int c = ca;
+          for (int q = 0; q < npw; ++q) {
+            float w = 0.0f;
+            if (c < cb) {
+              const uint2 xc = __ldg(xt + c);
+              if ((int)(xc.x >> 23) == pwf + q) {
+                w = wy * __uint_as_float(xc.y);
+                ++c;
+              }
+            }
+            const unsigned nz = (__ballot_sync(gmask, w != 0.0f) >> gshift) & 0xffu;
+            out->w[j] = w;
+            if (j == 0) {
+              const unsigned pairs = ((nz & 0x03u) ? 1u : 0u) | ((nz & 0x0cu) ? 2u : 0u) | ((nz & 0x30u) ? 4u : 0u) |
+                                     ((nz & 0xc0u) ? 8u : 0u);
+              out->hdr = (base + ph * (unsigned)p.pooled_w + (unsigned)(pwf + q)) * cwb | pairs;
+            }
+            ++out;
+          }
+        }
+      }
+    }
+  }
+  return total;
+}
+
+// p.ptr is indexed by group here: ((n * H + y) * ceil(W / 8) + x / 8) -> first entry, entries
+__device__ __forceinline__ void pull_list_block8(const PullParams& p, unsigned block) {
+  const int lane = threadIdx.x & 31;
+  const int segs = (p.width + 31) >> 5, segs8 = (p.width + 7) >> 3;
+  const long long wid = (long long)block * 8 + (threadIdx.x >> 5);
+  if (wid >= (long long)p.num_images * p.height * segs) return;
+  const int seg = (int)(wid % segs);
+  const int row = (int)(wid / segs);               // n * H + y
+  const int n = row / p.height, y = row - n * p.height;
+  const int x0 = seg * 32;
+  const unsigned total = pull_walk8<false>(p, n, y, x0, lane, nullptr);     // the same on the 8 lanes of a group
+  const unsigned t0 = __shfl_sync(0xffffffffu, total, 0), t1 = __shfl_sync(0xffffffffu, total, 8),
+                 t2 = __shfl_sync(0xffffffffu, total, 16), t3 = __shfl_sync(0xffffffffu, total, 24);
+  const unsigned warp_total = t0 + t1 + t2 + t3;
+  const int g = lane >> 3;
+  const unsigned before = (g > 0 ? t0 : 0u) + (g > 1 ? t1 : 0u) + (g > 2 ? t2 : 0u);
+  unsigned base = 0;
+  if (lane == 0 && warp_total) base = atomicAdd(p.cursor, warp_total);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  const bool fits = (unsigned long long)base + warp_total <= p.entry_cap;
+  const unsigned begin = base + before;
+  if ((lane & 7) == 0 && x0 + lane < p.width)
+    p.ptr[(long long)row * segs8 + ((x0 + lane) >> 3)] = make_uint2(begin, fits ? total : 0u);
+  if (!warp_total || !fits) return;
+  pull_walk8<true>(p, n, y, x0, lane, static_cast<GroupEntry*>(p.entries) + begin);
+}
+
 // ---- channel-last copy of dy: [R][C][B] -> [R * B][cw] -------------------------------------
 // One block per (ROI, 128 channels): the block's source is one contiguous run of 128 * B floats.
 // It goes to shared memory as [channel][pitch] (pitch odd: the transposed read, lane = channel,
@@ -619,7 +761,7 @@ __device__ __forceinline__ void pull_widen_block(const PullParams& p, unsigned b
 #ifndef MOBULA_TABLES_MINBLOCKS
 #define MOBULA_TABLES_MINBLOCKS 5
 #endif
-template <bool DET, bool WIDE, int kTrChannels>
+template <bool DET, bool WIDE, int kTrChannels, bool GRP>
 __global__ void __launch_bounds__(256, MOBULA_TABLES_MINBLOCKS) pull_tables_kernel(const PullParams p, const unsigned lblocks,
                                                           const unsigned tblocks) {
   extern __shared__ float s_t[];      // copy blocks: [kTrChannels][B | 1]
@@ -635,7 +777,10 @@ __global__ void __launch_bounds__(256, MOBULA_TABLES_MINBLOCKS) pull_tables_kern
     idx = is_few ? i / q : i - few_before;
   }
   const bool list_role = (lblocks <= tblocks) == is_few;      // the smaller set is the list set iff lblocks <= tblocks
-  if (few == 0 ? lblocks > 0 : list_role) pull_list_block<DET, WIDE>(p, idx);
+  if (few == 0 ? lblocks > 0 : list_role) {
+    if (GRP) pull_list_block8(p, idx);
+    else pull_list_block<DET, WIDE>(p, idx);
+  }
   else if (p.widen_flat) pull_widen_block(p, idx);
   else pull_transpose_block<kTrChannels>(p, idx, s_t);
 }
@@ -857,6 +1002,176 @@ __global__ void __launch_bounds__(kPullThreads, pull_min_blocks(DET)) pull_bwd_k
   }
 }
 
+// ---- the main kernel on grouped lists ---------------------------------------------------------
+// Same tiling (warp = 8 consecutive pixels x 32 * CPL channels).  An entry is one gradient line and
+// 8 weights: the line is loaded once (16 bytes per lane) and multiplied into the 8 pixels' sums,
+// held in registers as pairs of neighbouring pixels so that one FFMA2 serves two of them; a pair
+// whose two weights are zero is skipped (warp-uniform test on the entry's mask).
+constexpr int kG8Chunk = 64;                          // entries per half of a warp's ring (64 x 48 bytes)
+
+// U = gradient lines per batch, MINB = resident CTAs per SM the kernel is compiled for, PIPE = the
+// loads of the next batch are issued before the current batch is consumed
+template <int CPL, bool ACC, int U, int MINB, bool PIPE>
+__global__ void __launch_bounds__(kPullThreads, MINB) pull8_bwd_kernel(const PullParams p) {
+  constexpr int CG = 32 * CPL;
+  constexpr int kHalf = 3 * kG8Chunk;                 // uint4 words of one half of the ring
+  constexpr int kWarpBytes = (2 * kHalf * 16 > 8 * CG * 4) ? 2 * kHalf * 16 : 8 * CG * 4;
+  // per warp: the ring of entries; once the list is consumed, the same bytes hold the 8 x CG tile
+  extern __shared__ __align__(16) unsigned char s_pull[];
+  ptx::chain_enter();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int segs = (p.width + kPullCols - 1) / kPullCols, bands = (p.height + kPullRows - 1) / kPullRows;
+  const int seg = blockIdx.x % segs;
+  const int band = (blockIdx.x / segs) % bands;
+  const int n = blockIdx.x / (segs * bands);
+  const int c0 = blockIdx.y * CG;
+  const int y = band * kPullRows + warp / kPullWarpsPerRow;
+  const int xw = seg * kPullCols + (warp % kPullWarpsPerRow) * 8;
+  if (y >= p.height || xw >= p.width) return;         // warps are independent: no block-wide barrier below
+  const bool lane_on = c0 + lane * CPL < p.cw;
+  const char* dyt = reinterpret_cast<const char*>(p.dyt + (lane_on ? c0 + lane * CPL : 0));
+  uint4* ring = reinterpret_cast<uint4*>(s_pull + (size_t)warp * kWarpBytes);
+  float* tile = reinterpret_cast<float*>(ring);
+  const int npx = min(8, p.width - xw);
+  const int segs8 = (p.width + 7) >> 3;
+  const uint2 run = __ldg(p.ptr + ((long long)n * p.height + y) * segs8 + (xw >> 3));
+  const unsigned e0 = run.x, end_all = run.x + run.y;
+  const uint4* entries = static_cast<const uint4*>(p.entries);      // three words per entry
+
+  float2 acc[4][CPL];                                 // [pixel pair][channel]: .x = pixel 2q, .y = pixel 2q + 1
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) acc[q][k] = make_float2(0.0f, 0.0f);
+
+  // the ring is filled with 16-byte cp.async copies (no registers held across the loop)
+  auto fill = [&](unsigned first, int half) {
+    const unsigned long long w0 = 3ull * first, wend = 3ull * end_all;
+#pragma unroll
+    for (int k = 0; k < kHalf / 32; ++k) {
+      const unsigned long long i = w0 + k * 32 + lane;
+      if (i < wend) ptx::cp_async16(ring + half * kHalf + k * 32 + lane, entries + i);
+    }
+  };
+  fill(e0, 0);
+  ptx::cp_async_wait_all();
+  __syncwarp();
+  auto term = [&](const float (&g)[CPL], unsigned hdr, const uint4* e) {
+    const float4 wa = *reinterpret_cast<const float4*>(e + 1), wb = *reinterpret_cast<const float4*>(e + 2);
+    if (hdr & 1u) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) acc[0][k] = __ffma2_rn(make_float2(g[k], g[k]), make_float2(wa.x, wa.y), acc[0][k]);
+    }
+    if (hdr & 2u) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) acc[1][k] = __ffma2_rn(make_float2(g[k], g[k]), make_float2(wa.z, wa.w), acc[1][k]);
+    }
+    if (hdr & 4u) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) acc[2][k] = __ffma2_rn(make_float2(g[k], g[k]), make_float2(wb.x, wb.y), acc[2][k]);
+    }
+    if (hdr & 8u) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) acc[3][k] = __ffma2_rn(make_float2(g[k], g[k]), make_float2(wb.z, wb.w), acc[3][k]);
+    }
+  };
+  int buf = 0;
+  for (unsigned cbase = e0; cbase < end_all; cbase += kG8Chunk, buf ^= 1) {
+    const unsigned cn = min((unsigned)kG8Chunk, end_all - cbase);
+    fill(cbase + kG8Chunk, buf ^ 1);
+    const uint4* se = ring + buf * kHalf;
+    // a batch = U entries; entries behind the end of the chunk have header 0 (no pair, offset 0)
+    auto issue = [&](unsigned t, unsigned (&hdr)[U], float (&g)[U][CPL]) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) hdr[u] = t + u < cn ? se[3 * (t + u)].x : 0u;
+#pragma unroll
+      for (int u = 0; u < U; ++u) load_vec<CPL>(reinterpret_cast<const float*>(dyt + (hdr[u] & ~15u)), g[u]);
+    };
+    auto consume = [&](unsigned t, const unsigned (&hdr)[U], const float (&g)[U][CPL]) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) term(g[u], hdr[u], se + 3 * (t + u));
+    };
+    if (PIPE) {
+      unsigned ha[U], hb[U];
+      float ga[U][CPL], gb[U][CPL];
+      issue(0, ha, ga);
+      for (unsigned t = 0; t < cn; t += 2 * U) {
+        if (t + U < cn) issue(t + U, hb, gb);
+        consume(t, ha, ga);
+        if (t + U < cn) {
+          if (t + 2 * U < cn) issue(t + 2 * U, ha, ga);
+          consume(t + U, hb, gb);
+        }
+      }
+    } else {
+      for (unsigned t = 0; t < cn; t += U) {
+        unsigned ha[U];
+        float ga[U][CPL];
+        issue(t, ha, ga);
+        consume(t, ha, ga);
+      }
+    }
+    ptx::cp_async_wait_all();
+    __syncwarp();
+  }
+  __syncwarp();
+  // tile[pixel][slot] as in pull_bwd_kernel: pixels 4 .. 7 swap the halves of the row
+  constexpr int kSwap = CPL * (16 / CPL);
+#pragma unroll
+  for (int px = 0; px < 8; ++px) {
+    float* trow = tile + px * CG + ((CPL * lane) ^ ((px & 4) ? kSwap : 0));
+    float v[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) v[k] = (px & 1) ? acc[px >> 1][k].y : acc[px >> 1][k].x;
+    if (CPL == 4) *reinterpret_cast<float4*>(trow) = make_float4(v[0], v[1 % CPL], v[2 % CPL], v[3 % CPL]);
+    else if (CPL == 2) *reinterpret_cast<float2*>(trow) = make_float2(v[0], v[1 % CPL]);
+    else trow[0] = v[0];
+  }
+  __syncwarp();
+  const size_t plane = (size_t)p.height * p.width;
+  const int nch = min(CG, p.c_work - c0);
+  float* base = p.dx + ((size_t)n * p.channels + c0) * plane + (size_t)y * p.width + xw;
+  if (npx == 8 && (p.width & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dx) & 15u) == 0) {
+    const int k = lane >> 1, h = lane & 1;
+#pragma unroll 2
+    for (int cb = 0; cb < CG; cb += 16) {
+      const int c = cb + k;
+      if (c >= nch) continue;
+      const float* t = tile + (4 * h) * CG + (c ^ (16 * h));
+      float4 v = make_float4(t[0], t[CG], t[2 * CG], t[3 * CG]);
+      float4* dst = reinterpret_cast<float4*>(base + (size_t)c * plane + 4 * h);
+      if (ACC) {
+        const float4 o = *dst;
+        v.x = __fadd_rn(o.x, v.x);
+        v.y = __fadd_rn(o.y, v.y);
+        v.z = __fadd_rn(o.z, v.z);
+        v.w = __fadd_rn(o.w, v.w);
+      }
+      *dst = v;
+    }
+  } else {
+    const int px = lane & 7, k = lane >> 3;
+    if (px < npx)
+      for (int c = k; c < nch; c += 4) {
+        const float v = tile[px * CG + (c ^ ((px & 4) ? 16 : 0))];
+        float* dst = base + (size_t)c * plane + px;
+        *dst = ACC ? __fadd_rn(*dst, v) : v;
+      }
+  }
+}
+
+// grouped lists for the merged (non-deterministic) mode; MOBULA_PULL_GROUP=0 / 1 overrides the default
+#ifndef MOBULA_PULL8_VARIANT_DEFAULT
+#define MOBULA_PULL8_VARIANT_DEFAULT 0
+#endif
+#ifndef MOBULA_PULL_GROUP_DEFAULT
+#define MOBULA_PULL_GROUP_DEFAULT 0
+#endif
+static bool pull_grouped_enabled() {      // read on every call (one getenv): the tests switch it inside one process
+  const char* e = getenv("MOBULA_PULL_GROUP");
+  return e ? atoi(e) != 0 : MOBULA_PULL_GROUP_DEFAULT != 0;
+}
+
 struct PullLayout {
   size_t img_start, order, gbox, yidx, xidx, ytap, xtap, rowmask, ptr, cursor, need, dyt, entries, total;
   int caps, capy, capx, tw, cw, geom_warps;
@@ -890,6 +1205,8 @@ PullLayout pull_layout(const RoiAlignArgs& a, bool deterministic, unsigned long 
     L.entry_cap = (unsigned long long)R * L.capy * L.capx;
   }
   L.entry_bytes = (deterministic && adaptive) ? sizeof(uint4) : sizeof(uint2);
+  // grouped lists: never more entries than per-pixel ones (an entry stands for >= 1 of them)
+  if (!deterministic && pull_grouped_enabled()) L.entry_bytes = sizeof(GroupEntry);
   const size_t per_warp = axis_scratch_bytes(L.caps);
   L.geom_warps = (int)((200 * 1024) / per_warp);
   if (L.geom_warps > kMaxGeomWarps) L.geom_warps = kMaxGeomWarps;
@@ -1045,6 +1362,7 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
   }
   const long long segs = (a.width + 31) / 32;
   const bool wide = det && adaptive;
+  const bool grouped = !det && pull_grouped_enabled();
   {
     // per-pixel lists + channel-last copy of dy, one grid
     const long long lwarps = (long long)a.num_images * a.height * segs;
@@ -1066,18 +1384,19 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
       }
       if (!tblocks || p.widen_flat) tsmem = 0;
     }
-#define PULL_TABLES(DET, WIDE, TC)                                                                                 \
+#define PULL_TABLES(DET, WIDE, TC, GRP)                                                                            \
   do {                                                                                                             \
-    auto kk = pull_tables_kernel<DET, WIDE, TC>;                                                                   \
+    auto kk = pull_tables_kernel<DET, WIDE, TC, GRP>;                                                              \
     if (tsmem > 48 * 1024) /* per device, cheap: set on every call */                                              \
       cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);                           \
     chained_launch(kk, lblocks + tblocks, 256, tsmem, stream, p, lblocks, tblocks);                                \
   } while (0)
 #define PULL_TABLES_TC(TC)                        \
   do {                                            \
-    if (wide) PULL_TABLES(true, true, TC);        \
-    else if (det) PULL_TABLES(true, false, TC);   \
-    else PULL_TABLES(false, false, TC);           \
+    if (wide) PULL_TABLES(true, true, TC, false);        \
+    else if (det) PULL_TABLES(true, false, TC, false);   \
+    else if (grouped) PULL_TABLES(false, false, TC, true); \
+    else PULL_TABLES(false, false, TC, false);           \
   } while (0)
     if (tc == 128) PULL_TABLES_TC(128);
     else PULL_TABLES_TC(32);
@@ -1095,6 +1414,8 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
   const dim3 grid((unsigned)(tile_cols * bands * a.num_images), (unsigned)((L.cw + 32 * cpl - 1) / (32 * cpl)));
   // MOBULA_PULL_UNROLL = terms per group (4 or 8): gradient loads in flight per warp
   static const int unroll = [] { const char* e = getenv("MOBULA_PULL_UNROLL"); return e ? atoi(e) : 8; }();
+  // MOBULA_PULL_CARVEOUT = shared-memory share of the L1 / shared-memory array in percent (experiment knob)
+  static const int carveout = [] { const char* e = getenv("MOBULA_PULL_CARVEOUT"); return e ? atoi(e) : -1; }();
 #define PULL_LAUNCH(CPL, DET, ACC, WIDE)                                                  \
   do {                                                                                    \
     auto k8 = pull_bwd_kernel<CPL, DET, ACC, 8, WIDE>;                                    \
@@ -1103,6 +1424,7 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
     const size_t smem = (size_t)(kPullThreads / 32) * (8 * 32 * CPL * sizeof(float) +    \
                                                        2 * kEntChunk * (WIDE ? 16 : 8));  \
     if (smem > 48 * 1024) cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (carveout >= 0) cudaFuncSetAttribute(kk, cudaFuncAttributePreferredSharedMemoryCarveout, carveout); \
     chained_launch(kk, grid, dim3(kPullThreads), smem, stream, p, count, inv, pow2);      \
   } while (0)
 #define PULL_MODE(CPL)                                              \
@@ -1118,9 +1440,29 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
       else PULL_LAUNCH(CPL, false, false, false);                   \
     }                                                               \
   } while (0)
-  if (cpl == 4) PULL_MODE(4);
+  // MOBULA_PULL8_VARIANT: 0 = 4 lines per batch, 1 = 8 lines, 2 = 4 lines pipelined (two CTAs per SM each),
+  // 3 = 4 lines, three CTAs per SM
+  const int variant = [] { const char* e = getenv("MOBULA_PULL8_VARIANT"); return e ? atoi(e) : MOBULA_PULL8_VARIANT_DEFAULT; }();
+#define PULL8_KERNEL(CPL, ACC) \
+  (variant == 1 ? pull8_bwd_kernel<CPL, ACC, 8, 2, false> : variant == 2 ? pull8_bwd_kernel<CPL, ACC, 4, 2, true> : \
+   variant == 3 ? pull8_bwd_kernel<CPL, ACC, 4, 3, false> : pull8_bwd_kernel<CPL, ACC, 4, 2, false>)
+#define PULL8_LAUNCH(CPL)                                                                         \
+  do {                                                                                            \
+    const size_t ring = 2 * kG8Chunk * sizeof(GroupEntry), tile = 8 * 32 * CPL * sizeof(float);   \
+    const size_t smem = (size_t)(kPullThreads / 32) * (ring > tile ? ring : tile);                \
+    auto kk = accumulate ? PULL8_KERNEL(CPL, true) : PULL8_KERNEL(CPL, false);                    \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    chained_launch(kk, grid, dim3(kPullThreads), smem, stream, p);                                \
+  } while (0)
+  if (grouped) {
+    if (cpl == 4) PULL8_LAUNCH(4);
+    else if (cpl == 2) PULL8_LAUNCH(2);
+    else PULL8_LAUNCH(1);
+  } else if (cpl == 4) PULL_MODE(4);
   else if (cpl == 2) PULL_MODE(2);
   else PULL_MODE(1);
+#undef PULL8_LAUNCH
+#undef PULL8_KERNEL
 #undef PULL_MODE
 #undef PULL_LAUNCH
   count_launch();

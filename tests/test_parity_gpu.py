@@ -932,3 +932,31 @@ def test_fpn_pooler_rows_equal_single_level_calls(api, torch, oracle):
         idx = np.nonzero(levels == 2 + k)[0]
         if len(idx):
             assert_bit_exact(y[idx], oracle.forward(f, np.ascontiguousarray(rois[idx]), (7, 7), s, 2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', PULL_SHAPES, ids=lambda s: 'x'.join(str(v) for v in s[:5]) + '-p%dx%d-sr%d' % (s[5] + (s[7],)))
+def test_pull_grouped_lists_equal_per_pixel_lists(direct, oracle, shape, monkeypatch):
+    """Merged-tap pull backward on grouped lists (one entry per bin and group of 8 pixels, the
+    gradient line loaded once for the group) against the per-pixel lists: the same fused
+    multiply-adds in the same order per pixel, hence bit-identical; and within 1e-5 of the oracle."""
+    from mobulaop_b200 import _native
+    N, C, H, W, k, pooled, scale, sr = shape
+    wl = WL.Workload('pull', N, C, H, W, k, pooled, scale, sr, min_box=2.0, max_box=4.0 * max(H, W) / scale,
+                     stress=sr == 0)
+    data, rois, dy = WL.make_inputs(wl, seed=41)
+    rng = np.random.default_rng(9)
+    rois = np.ascontiguousarray(rois[rng.permutation(len(rois))])
+    dx_ref = oracle.backward(dy, rois, data.shape, scale, sr)
+    dx_abs = oracle.backward(np.abs(dy), rois, data.shape, scale, sr)
+    dbase = rng.standard_normal(data.shape).astype(np.float32)
+    got = {}
+    for grouped in ('0', '1'):
+        monkeypatch.setenv('MOBULA_PULL_GROUP', grouped)
+        dx = direct.backward(dy, rois, data.shape, scale, sr, algo='pull')
+        assert _native.last_algo(True) == 'pull'
+        assert_scatter_close(dx, dx_ref, dx_abs, rtol=1e-5)
+        acc = direct.backward(dy, rois, data.shape, scale, sr, algo='pull', accumulate_into=dbase.copy())
+        got[grouped] = (dx, acc)
+    assert_bit_exact(got['1'][0], got['0'][0])
+    assert_bit_exact(got['1'][1], got['0'][1])

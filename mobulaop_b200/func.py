@@ -21,6 +21,7 @@ reference semantics "adds into a caller-zeroed buffer", False for forward), `alg
 (`top_data` / `top_diff`) may be float16 or bfloat16 -- the arithmetic stays fp32.
 """
 import ctypes
+import sys
 
 from . import _native
 from . import glue
@@ -86,6 +87,7 @@ class MobulaFunc(object):
         self.arg_names = [p[0] for p in self.params]
         self._conv = name in ('im2col', 'col2im')
         self._launcher = None if self._conv else (_launch_forward if name == 'roi_align_forward' else _launch_backward)
+        self._fast = None if self._conv else (_fast_torch_forward if name == 'roi_align_forward' else _fast_torch_backward)
 
     def __repr__(self):
         return '<mobula.func.%s(%s)>' % (self.name, ', '.join('%s %s' % (k, n) for n, k in self.params))
@@ -115,6 +117,8 @@ class MobulaFunc(object):
             args = self._collect(args, kwargs)
             if kwargs:
                 raise TypeError('%s: unexpected arguments %s' % (self.name, sorted(kwargs)))
+        if self._fast is not None and self._fast(args, mode, accumulate, algo, aligned, layout):
+            return None
 
         values = {}
         tensors = {}
@@ -223,6 +227,109 @@ def _launch_backward(v, t, dev_id, stream, host, mode, accumulate, algo, aligned
         _vp(rois.resolve(False)), _vp(dx.resolve(True)), num_rois, num_images, v['channels'], v['height'], v['width'],
         v['pooled_height'], v['pooled_width'], v['spatial_scale'], v['sampling_ratio'],
         _native.BWD_DETERMINISTIC if mode == 'deterministic' else _native.BWD_ATOMIC, flags))
+
+
+# ---- the common case without adapter objects: three contiguous torch tensors of the expected
+# types on one device.  Anything else (other frameworks, copies to make, errors to report) returns
+# False and takes the general path above, which owns the error messages.
+_INT_POSITIONS = (0, 3, 4, 5, 6, 7, 8)      # nthreads, channels .. sampling_ratio in both signatures
+_TORCH_TOP = None          # torch dtype -> DTYPE_* of the pooled tensor, filled on first use
+
+
+def _torch_fast_setup(torch):
+    global _TORCH_TOP, _raw_stream
+    _TORCH_TOP = {torch.float32: _native.DTYPE_F32, torch.float16: _native.DTYPE_F16,
+                  torch.bfloat16: _native.DTYPE_BF16}
+    raw = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+    if raw is None:
+        raw = lambda index: torch.cuda.current_stream(index).cuda_stream
+    _raw_stream = raw
+
+
+def _fast_torch_common(args, ia, ib, ic, top, layout):
+    """(lib, dev_id, stream, host, top_dtype, top_layout, num_rois, num_images) or None"""
+    torch = sys.modules.get('torch')
+    if torch is None:
+        return None
+    a, b, c = args[ia], args[ib], args[ic]
+    T = torch.Tensor
+    if type(a) is not T or type(b) is not T or type(c) is not T:
+        return None
+    if _TORCH_TOP is None:
+        _torch_fast_setup(torch)
+    f32 = torch.float32
+    t = args[top]
+    top_dtype = _TORCH_TOP.get(t.dtype)
+    if top_dtype is None:
+        return None
+    for x in (a, b, c):
+        if x is not t and x.dtype is not f32:
+            return None
+    dev = a.device
+    if b.device != dev or c.device != dev:
+        return None
+    if not (a.is_contiguous() and b.is_contiguous() and c.is_contiguous()):
+        return None
+    scale = args[2]
+    if type(scale) is not float and type(scale) is not int:
+        return None
+    for k in _INT_POSITIONS:
+        if type(args[k]) is not int:
+            return None
+    if layout is None:
+        top_layout = 0
+    else:
+        top_layout = _native.LAYOUTS.get(layout)
+        if top_layout is None:
+            return None
+    if dev.type == 'cuda':
+        dev_id = dev.index
+        if dev_id is None:
+            dev_id = torch.cuda.current_device()
+        stream = _raw_stream(dev_id)
+        host = False
+    elif dev.type == 'cpu':
+        dev_id, stream, host = -1, 0, True
+    else:
+        return None
+    per_roi = args[3] * args[6] * args[7]
+    num_rois = args[0] // per_roi if per_roi > 0 else 0
+    return _native.load(), dev_id, stream, host, top_dtype, top_layout, num_rois
+
+
+def _fast_torch_forward(args, mode, accumulate, algo, aligned, layout):
+    if mode is not None:
+        return False
+    r = _fast_torch_common(args, 1, 9, 10, 10, layout)
+    if r is None:
+        return False
+    lib, dev_id, stream, host, top_dtype, top_layout, num_rois = r
+    data = args[1]
+    flags = _native.make_flags(bool(accumulate), host, algo or config.ROIALIGN_ALGO, False, aligned)
+    _native.check(lib.mobula_roialign_forward_ex(
+        dev_id, stream, data.data_ptr(), args[9].data_ptr(), args[10].data_ptr(), top_dtype, top_layout, num_rois,
+        data.shape[0] if data.dim() == 4 else -1, args[3], args[4], args[5], args[6], args[7], float(args[2]),
+        args[8], flags))
+    return True
+
+
+def _fast_torch_backward(args, mode, accumulate, algo, aligned, layout):
+    if mode is None:
+        mode = 'deterministic' if config.ROIALIGN_DETERMINISTIC else 'atomic'
+    elif mode != 'atomic' and mode != 'deterministic':
+        return False
+    r = _fast_torch_common(args, 1, 9, 10, 1, layout)
+    if r is None:
+        return False
+    lib, dev_id, stream, host, top_dtype, top_layout, num_rois = r
+    dx = args[9]
+    flags = _native.make_flags(True if accumulate is None else bool(accumulate), host, algo or config.ROIALIGN_ALGO,
+                               False, aligned)
+    _native.check(lib.mobula_roialign_backward_ex(
+        dev_id, stream, args[1].data_ptr(), top_dtype, top_layout, args[10].data_ptr(), dx.data_ptr(), num_rois,
+        dx.shape[0] if dx.dim() == 4 else -1, args[3], args[4], args[5], args[6], args[7], float(args[2]), args[8],
+        _native.BWD_DETERMINISTIC if mode == 'deterministic' else _native.BWD_ATOMIC, flags))
+    return True
 
 
 def _launch_conv(name, v, t, dev_id, stream, host):

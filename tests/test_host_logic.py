@@ -305,3 +305,77 @@ def test_fpn_level_assignment_matches_the_paper_and_torchvision():
         assert (tv.numpy() == mine).mean() > 0.995          # ties at exact powers of two aside
     parts = fpn.split_by_level(np.array([2, 5, 3, 2, 5]), 2, 5)
     assert [p.tolist() for p in parts] == [[0, 3], [2], [], [1, 4]]
+
+
+class _RecordingLib(object):
+    """Stands in for the native library: records the arguments of every entry point called."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        def entry(*args):
+            self.calls.append((name, tuple((a.value or 0) if hasattr(a, 'value') else a for a in args)))   # c_void_p(0).value is None
+            return 0
+        return entry
+
+
+def test_torch_fast_dispatch_passes_the_same_arguments_as_the_general_path(mobula, monkeypatch):
+    """`mobula.func.roi_align_*` on three contiguous torch tensors skips the adapter objects; the
+    native call it makes must be the one the general path makes, and everything the fast path does
+    not cover (copies to make, other scalar types, errors) must still reach the general path."""
+    import torch
+    from mobulaop_b200 import _native, func as F
+    mobula.op.load('ROIAlign')
+    lib = _RecordingLib()
+    monkeypatch.setattr(_native, '_lib', lib)
+    monkeypatch.setattr(_native, 'load', lambda: lib)
+    N, C, H, W, R, PH, PW = 2, 3, 9, 11, 5, 2, 4
+    x = torch.zeros(N, C, H, W)
+    rois = torch.zeros(R, 5)
+    y = torch.zeros(R, C, PH, PW)
+    dx = torch.zeros_like(x)
+    n = y.numel()
+
+    def both(call):
+        """the call through the fast path and with the fast path switched off"""
+        lib.calls.clear()
+        call()
+        fast = list(lib.calls)
+        lib.calls.clear()
+        saved = {}
+        for fn in (F.roi_align_forward, F.roi_align_backward):
+            saved[fn] = fn._fast
+            fn._fast = None
+        try:
+            call()
+        finally:
+            for fn, f in saved.items():
+                fn._fast = f
+        general = list(lib.calls)
+        lib.calls.clear()
+        return fast, general
+
+    for kw in ({}, {'accumulate': True}, {'aligned': True}, {'layout': 'RHWC'}, {'algo': 'sweep'}):
+        fast, general = both(lambda: F.roi_align_forward(n, x, 0.25, C, H, W, PH, PW, 2, rois, y, **kw))
+        assert len(fast) == 1 and fast == general, (kw, fast, general)
+    for kw in ({}, {'accumulate': False}, {'mode': 'deterministic'}, {'aligned': True}, {'layout': 'RHWC'}):
+        fast, general = both(lambda: F.roi_align_backward(n, y, 0.25, C, H, W, PH, PW, 2, dx, rois, **kw))
+        assert len(fast) == 1 and fast == general, (kw, fast, general)
+    # a half-precision pooled tensor is a typed top, not a type error
+    fast, general = both(lambda: F.roi_align_forward(n, x, 0.25, C, H, W, PH, PW, 2, rois, y.half()))
+    assert fast == general and fast[0][1][5] == _native.DTYPE_F16
+    # the fast path declines: a non-contiguous tensor (the general path copies and writes back) ...
+    calls = []
+    monkeypatch.setattr(F.roi_align_forward, '_fast',
+                        lambda *a: calls.append(F._fast_torch_forward(*a)) or calls[-1])
+    yt = torch.zeros(R, C, PW, PH).transpose(2, 3)
+    F.roi_align_forward(n, x, 0.25, C, H, W, PH, PW, 2, rois, yt)
+    assert calls == [False] and len(lib.calls) == 1
+    # ... and the errors are still the general path's
+    with pytest.raises(TypeError):
+        F.roi_align_forward(n, x.double(), 0.25, C, H, W, PH, PW, 2, rois, y)
+    with pytest.raises(ValueError):
+        F.roi_align_backward(n, y, 0.25, C, H, W, PH, PW, 2, dx, rois, mode='fast')
+    with pytest.raises(ValueError):
+        F.roi_align_forward(n, x, 0.25, C, H, W, PH, PW, 2, rois, y, layout='NHWC')

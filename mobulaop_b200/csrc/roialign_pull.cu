@@ -79,6 +79,7 @@ struct PullParams {
   const void* dy;
   int dy_dtype, dy_layout;   // RoiAlignArgs::top_dtype / top_layout of dy
   int widen_flat;            // copy blocks run pull_widen_block (channel-last half-precision dy, whole rows)
+  int tables_q;              // list / copy grid: cap of the interleaving period (0 = none), see pull_tables_kernel
   float* dx;
 };
 
@@ -771,7 +772,10 @@ __global__ void __launch_bounds__(256, MOBULA_TABLES_MINBLOCKS) pull_tables_kern
   bool is_few = false;
   unsigned idx = i;
   if (few > 0) {
-    const unsigned q = many / few + 1;               // one block of the smaller set every q blocks
+    // one block of the smaller set every q blocks; q = many / few + 1 spreads it over the whole grid, a
+    // smaller q (p.tables_q) runs it out earlier: the rest of the grid is blocks of the larger set only
+    unsigned q = many / few + 1;
+    if (lblocks <= tblocks && p.tables_q > 0 && (unsigned)p.tables_q < q) q = (unsigned)p.tables_q;
     const unsigned few_before = min(few, (i + q - 1) / q);
     is_few = i % q == 0 && i / q < few;
     idx = is_few ? i / q : i - few_before;
@@ -1272,7 +1276,6 @@ size_t pull_bwd_workspace(const RoiAlignArgs& a, int deterministic, unsigned lon
 cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned long long entry_cap, const float* dy,
                             float* dx, int accumulate, int deterministic, int num_sms, cudaStream_t stream,
                             unsigned long long* need_entries) {
-  (void)num_sms;
   *need_entries = 0;
   const int cwork = a.c_count > 0 ? a.c_count : a.channels;
   if (cwork <= 0 || a.num_images <= 0) return cudaSuccess;
@@ -1373,6 +1376,14 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
     // a channel-last dy with whole rows (cw == C == the channels worked on): fp32 is the copy the
     // main kernel wants -- it reads dy in place, no copy blocks at all; half precision is widened flat
     p.widen_flat = 0;
+    // List blocks are long (a dependent walk over the ROIs of the row), copy blocks short.  While the list
+    // blocks are few (up to three waves of resident CTAs) they go first, so that none of them starts late
+    // and is left running alone at the end (C2 backward 137 -> 129 us, C3 1.61 -> 1.51 ms, 8 images of
+    // C4: 413 -> 404 us); a long grid keeps them spread over the copy blocks (16 images: 782 against
+    // 787 us, C4: 2.99 against 3.07 ms with the list blocks first; profiles/r2_knob_experiments.txt).
+    // MOBULA_TABLES_Q = cap of the interleaving period (0 = none), see pull_tables_kernel.
+    static const int q_env = [] { const char* e = getenv("MOBULA_TABLES_Q"); return e ? atoi(e) : -1; }();
+    p.tables_q = q_env >= 0 ? q_env : (lblocks <= 3u * (unsigned)(num_sms > 0 ? num_sms : 148) * MOBULA_TABLES_MINBLOCKS ? 1 : 0);
     if (a.top_layout != 0 && L.cw == a.channels && cwork == a.channels) {
       if (a.top_dtype == 0 && (reinterpret_cast<uintptr_t>(dy) & 15u) == 0) {
         p.dyt = const_cast<float*>(dy);

@@ -62,7 +62,7 @@ struct PullParams {
   const int* order;      // [R] ROI rows grouped by image, ascending inside an image
   uint4* gbox;           // [R] by grouped position: rows min | max << 16, columns min | max << 16,
                          // grid_h | grid_w << 16, count (float bits)
-  unsigned short* yidx;  // [R][H + 2] by grouped position: first tap of row (ymin + q)
+  unsigned short* yidx;  // [R][H + 2] by grouped position: first tap of row y at [y], for ymin <= y <= ymax + 1
   unsigned short* xidx;  // [R][W + 2]
   uint2* ytap;           // [R][capy] taps sorted by row: x = row | high << 12 | i << 13 | p << 23 (sample i of
                          // bin p; merged taps: row | p << 23), y = weight
@@ -126,7 +126,7 @@ __device__ __forceinline__ AxisScratch carve_scratch(unsigned char* base, int ca
 template <bool DET>
 __device__ int pull_axis(float start, float bin, int pooled, int grid, int extent, float wscale, int caps, int lane,
                          const AxisScratch& sc, uint2* __restrict__ taps, unsigned short* __restrict__ idx,
-                         unsigned* range) {
+                         unsigned* range, bool absolute) {
   const int ns = pooled * grid;
   // ---- the valid samples, in order ----
   int nv = 0;
@@ -233,7 +233,10 @@ __device__ int pull_axis(float start, float bin, int pooled, int grid, int exten
     nfinal = out_base;
   }
   const int pmin = (int)(sc.skey[0] & 0xfffu), pmax = (int)(sc.skey[nfinal - 1] & 0xfffu);
-  // idx[q] = first tap whose pixel is >= pmin + q, q = 0 .. pmax - pmin + 1
+  // idx[q] = first tap whose pixel is >= pmin + q, q = 0 .. pmax - pmin + 1; `absolute`: the index is
+  // addressed by the pixel itself, idx[pmin + q] (the rows: a reader then needs nothing of the ROI to
+  // find its entry, so the load does not wait for the box)
+  idx += absolute ? pmin : 0;
   for (int q = lane; q <= pmax - pmin + 1; q += 32) {
     const unsigned want = (unsigned)(pmin + q);
     int a = 0, b = nfinal;
@@ -265,10 +268,10 @@ __global__ void __launch_bounds__(kMaxGeomWarps * 32) pull_geom_kernel(const Pul
     const float inv_count = __fdiv_rn(1.0f, g.count);
     unsigned yr, xr;
     const int nyt = pull_axis<DET>(g.start_h, g.bin_h, p.pooled_h, g.grid_h, p.height, 1.0f, p.caps, lane, sc,
-                                   p.ytap + (size_t)pos * p.capy, p.yidx + (size_t)pos * (p.height + 2), &yr);
+                                   p.ytap + (size_t)pos * p.capy, p.yidx + (size_t)pos * (p.height + 2), &yr, true);
     __syncwarp();
     const int nxt = pull_axis<DET>(g.start_w, g.bin_w, p.pooled_w, g.grid_w, p.width, inv_count, p.caps, lane, sc,
-                                   p.xtap + (size_t)pos * p.capx, p.xidx + (size_t)pos * (p.width + 2), &xr);
+                                   p.xtap + (size_t)pos * p.capx, p.xidx + (size_t)pos * (p.width + 2), &xr, false);
     if (nyt > 0 && nxt > 0) {
       box = make_uint4(yr, xr, (unsigned)g.grid_h | ((unsigned)g.grid_w << 16), __float_as_uint(g.count));
       // every (row tap, column tap) pair is one entry of exactly one pixel
@@ -341,37 +344,48 @@ __device__ __forceinline__ unsigned pull_walk(const PullParams& p, int n, int y,
       bool cand = (m >> lane) & 1u;
       if (cand) {
         const int pos = ((wg - n) << 5) + lane;
-        const uint2 box = __ldg(reinterpret_cast<const uint2*>(p.gbox + pos));
-        const int xmin = (int)(box.y & 0xffffu), xmax = (int)(box.y >> 16);
-        cand = !(xmax < x0 || xmin > x0 + 31);
-        if (cand) {
-          const unsigned short* yi = p.yidx + (size_t)pos * (p.height + 2) + (y - (int)(box.x & 0xffffu));
-          const unsigned ra = __ldg(yi), rb = __ldg(yi + 1);
-          cand = ra != rb;
-          my_r = ra | (rb << 16);
-          my_x = box.y;
-        }
+        // (the row index is addressed by y itself: its loads do not wait for the box)
+        const unsigned xr = __ldg(&p.gbox[pos].y);
+        const unsigned short* yi = p.yidx + (size_t)pos * (p.height + 2) + y;
+        const unsigned ra = __ldg(yi), rb = __ldg(yi + 1);
+        const int xmin = (int)(xr & 0xffffu), xmax = (int)(xr >> 16);
+        cand = !(xmax < x0 || xmin > x0 + 31) && ra != rb;
+        my_r = ra | (rb << 16);
+        my_x = xr;
       }
       unsigned live = __ballot_sync(0xffffffffu, cand);
-      while (live) {
+      // The live ROIs one after the other, software-pipelined: the index loads of the next one (its column
+      // taps for this pixel, its row in the ROI table) are in flight while the current one is worked on.
+      int n_pos = 0, n_ra = 0, n_rb = 0, n_ca = 0, n_cb = 0;
+      unsigned n_row = 0;
+      auto fetch = [&]() {                       // pops the lowest live ROI into n_*
         const int b = __ffs(live) - 1;
         live &= live - 1;
-        const int pos = ((wg - n) << 5) + b;
+        n_pos = ((wg - n) << 5) + b;
         const unsigned rr = __shfl_sync(0xffffffffu, my_r, b), xx = __shfl_sync(0xffffffffu, my_x, b);
-        const int ra = (int)(rr & 0xffffu), rb = (int)(rr >> 16);
+        n_ra = (int)(rr & 0xffffu);
+        n_rb = (int)(rr >> 16);
         const int xmin = (int)(xx & 0xffffu), xmax = (int)(xx >> 16);
-        int ca = 0, cb = 0;
+        n_ca = n_cb = 0;
         if (in && x >= xmin && x <= xmax) {
-          const unsigned short* xi = p.xidx + (size_t)pos * (p.width + 2) + (x - xmin);
-          ca = __ldg(xi);
-          cb = __ldg(xi + 1);
+          const unsigned short* xi = p.xidx + (size_t)n_pos * (p.width + 2) + (x - xmin);
+          n_ca = __ldg(xi);
+          n_cb = __ldg(xi + 1);
         }
+        if (FILL) n_row = (unsigned)__ldg(p.order + n_pos);
+      };
+      bool have = live != 0u;
+      if (have) fetch();
+      while (have) {
+        const int pos = n_pos, ra = n_ra, rb = n_rb, ca = n_ca, cb = n_cb;
+        const unsigned base = n_row * (unsigned)B;
+        have = live != 0u;
+        if (have) fetch();
         if (!FILL) {
           total += (unsigned)((rb - ra) * (cb - ca));
           continue;
         }
         if (ca == cb) continue;
-        const unsigned base = (unsigned)__ldg(p.order + pos) * (unsigned)B;
         const uint2* yt = p.ytap + (size_t)pos * p.capy;
         const uint2* xt = p.xtap + (size_t)pos * p.capx;
         const unsigned cwb = (unsigned)(p.cw * 4), pxbits = (unsigned)(x & 7);     // cwb is a multiple of 16
@@ -513,16 +527,14 @@ __device__ __forceinline__ unsigned pull_walk8(const PullParams& p, int n, int y
       bool cand = (m >> lane) & 1u;
       if (cand) {
         const int pos = ((wg - n) << 5) + lane;
-        const uint2 box = __ldg(reinterpret_cast<const uint2*>(p.gbox + pos));
-        const int xmin = (int)(box.y & 0xffffu), xmax = (int)(box.y >> 16);
-        cand = !(xmax < x0 || xmin > x0 + 31);
-        if (cand) {
-          const unsigned short* yi = p.yidx + (size_t)pos * (p.height + 2) + (y - (int)(box.x & 0xffffu));
-          const unsigned ra = __ldg(yi), rb = __ldg(yi + 1);
-          cand = ra != rb;
-          my_r = ra | (rb << 16);
-          my_x = box.y;
-        }
+        // (the row index is addressed by y itself: its loads do not wait for the box)
+        const unsigned xr = __ldg(&p.gbox[pos].y);
+        const unsigned short* yi = p.yidx + (size_t)pos * (p.height + 2) + y;
+        const unsigned ra = __ldg(yi), rb = __ldg(yi + 1);
+        const int xmin = (int)(xr & 0xffffu), xmax = (int)(xr >> 16);
+        cand = !(xmax < x0 || xmin > x0 + 31) && ra != rb;
+        my_r = ra | (rb << 16);
+        my_x = xr;
       }
       unsigned live = __ballot_sync(0xffffffffu, cand);
       while (live) {

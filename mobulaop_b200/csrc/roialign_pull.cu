@@ -281,13 +281,15 @@ __global__ void __launch_bounds__(kMaxGeomWarps * 32) pull_geom_kernel(const Pul
   if (lane == 0) p.gbox[pos] = box;
 }
 
-// ---- row mask: one warp per (feature-map row, mask word), lane = ROI ---------------------------
+// ---- row mask: one warp per (mask word = 32 ROIs, chunk of 32 rows), lane = ROI -----------------
+// (a warp per (row, word) spent its time on the binary search and one dependent load: C4 40 us)
 __global__ void __launch_bounds__(256) pull_rowmask_kernel(const PullParams p) {
   ptx::chain_enter();
   const int lane = threadIdx.x & 31;
+  const int chunks = (p.height + 31) >> 5;
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (wid >= (long long)p.height * p.tw) return;
-  const int y = (int)(wid / p.tw), wg = (int)(wid - (long long)y * p.tw);
+  if (wid >= (long long)p.tw * chunks) return;
+  const int wg = (int)(wid / chunks), y0 = (int)(wid - (long long)wg * chunks) * 32;
   // image of this word: the last n with mask_word0(n) <= wg
   int lo = 0, hi = p.num_images;        // answer in [lo, hi]; hi == num_images: behind the last image
   while (lo < hi) {
@@ -296,16 +298,24 @@ __global__ void __launch_bounds__(256) pull_rowmask_kernel(const PullParams p) {
     else hi = mid - 1;
   }
   const int n = lo;
-  bool hit = false;
+  int ymin = 0x7fffffff, ymax = -1;     // no row
   if (n < p.num_images) {
     const int pos = ((wg - n) << 5) + lane;
     if (pos >= __ldg(p.img_start + n) && pos < __ldg(p.img_start + n + 1)) {
       const unsigned yr = __ldg(&p.gbox[pos].x);
-      hit = (int)(yr & 0xffffu) <= y && y <= (int)(yr >> 16);
+      ymin = (int)(yr & 0xffffu);       // a ROI without taps has ymin = 0xffff > every row
+      ymax = (int)(yr >> 16);
     }
   }
-  const unsigned m = __ballot_sync(0xffffffffu, hit);
-  if (lane == 0) p.rowmask[wid] = m;
+  // lane l gathers the word of row y0 + l: the 32 stores of the chunk are one instruction
+  unsigned mine = 0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int y = y0 + k;
+    const unsigned m = __ballot_sync(0xffffffffu, ymin <= y && y <= ymax);
+    if (lane == k) mine = m;
+  }
+  if (y0 + lane < p.height) p.rowmask[(size_t)(y0 + lane) * p.tw + wg] = mine;
 }
 
 // ---- per-pixel lists: one thread per pixel, a warp = 32 consecutive pixels of one row ----------
@@ -1371,7 +1381,7 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
     }
   }
   {
-    const long long warps = (long long)a.height * L.tw;
+    const long long warps = (long long)L.tw * ((a.height + 31) / 32);
     chained_launch(pull_rowmask_kernel, (unsigned)((warps + 7) / 8), 256, 0, stream, p);
     count_launch();
   }

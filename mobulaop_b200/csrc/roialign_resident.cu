@@ -23,6 +23,7 @@
 //
 // forward : products and sums in the reference's order (bilinear.h:50-56, ROIAlign.cpp:56-74)
 //           -> bit-identical output.
+#include <cstdlib>
 #include "roialign_kernels.h"
 #include "roialign_common.cuh"
 #include "ptx_sm100.cuh"
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(256)
 resident_fwd2_table_kernel(const float* __restrict__ rois, const int* __restrict__ order,
                            const int* __restrict__ img_start, int num_images, int height, int width,
                            int pitch, int unit, int pooled_h, int pooled_w, float scale, int ypairs,
-                           int xslots, uint2* __restrict__ entries) {
+                           int xslots, uint2* __restrict__ entries, int dense) {
   ptx::chain_enter();
   // `unit` = bytes per pixel of the shared-memory plane: 4, or 8 for a channel pair
   const int per_roi = 2 * ypairs + xslots;
@@ -124,7 +125,21 @@ resident_fwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
     const int kk = k - 2 * ypairs;
     s.lo_off = (unsigned)((width + 1) * unit);
     s.l = 0.0f;
-    if (kk < 2 * pooled_w) s = make_sample(g.start_w, kk >> 1, g.bin_w, kk & 1, 2, width, unit);
+    if (dense) {
+      // dense plane (pitch == width: no repeated column, no zero columns): the record says so itself --
+      // bit 0: the sample is rejected (both weights are 0, any column will do), bit 1: the column is
+      // clamped, its high tap is the low tap (bilinear.h:27-31)
+      s.lo_off = 1u;
+      if (kk < 2 * pooled_w) {
+        const AxisTap t = axis_decode(sample_pos(g.start_w, kk >> 1, g.bin_w, kk & 1, 2), width);
+        if (t.valid) {
+          s.lo_off = (unsigned)(t.lo * unit) | (t.hi == t.lo ? 2u : 0u);
+          s.l = t.wl;
+        }
+      }
+    } else if (kk < 2 * pooled_w) {
+      s = make_sample(g.start_w, kk >> 1, g.bin_w, kk & 1, 2, width, unit);
+    }
   }
   entries[t] = make_uint2(s.lo_off, __float_as_uint(s.l));
 }
@@ -371,6 +386,17 @@ __device__ __forceinline__ void taps_advance(Taps& t, unsigned a, unsigned b, un
       : "+f"(t.plo), "+f"(t.phi), "+f"(t.clo), "+f"(t.chi)
       : "r"(a), "r"(b), "r"(code), "r"(epoch));
 }
+// dense plane: the high column has an address of its own (the low one again where the column is clamped)
+__device__ __forceinline__ void taps_advance_d(Taps& t, unsigned a, unsigned ah, unsigned b, unsigned bh, unsigned code,
+                                               unsigned epoch) {
+  asm("{\n\t.reg .pred pl, ps, ph;\n\t"
+      "setp.eq.u32 pl, %8, 0;\n\tsetp.eq.u32 ps, %8, 1;\n\tsetp.ne.u32 ph, %8, 2;\n\t"
+      "@ps mov.f32 %0, %2;\n\t@ps mov.f32 %1, %3;\n\t"
+      "@pl ld.shared.f32 %0, [%4];\n\t@pl ld.shared.f32 %1, [%5];\n\t"
+      "@ph ld.shared.f32 %2, [%6];\n\t@ph ld.shared.f32 %3, [%7];\n\t}"
+      : "+f"(t.plo), "+f"(t.phi), "+f"(t.clo), "+f"(t.chi)
+      : "r"(a), "r"(ah), "r"(b), "r"(bh), "r"(code), "r"(epoch));
+}
 // the same for a channel pair (float2 per pixel)
 struct Taps2 {
   float2 plo, phi, clo, chi;
@@ -387,6 +413,9 @@ __device__ __forceinline__ void taps2_advance(Taps2& t, unsigned a, unsigned b, 
 }
 constexpr unsigned kRowCodeMask = 3u;
 
+#ifndef MOBULA_FWD_DENSE_DEFAULT
+#define MOBULA_FWD_DENSE_DEFAULT 1
+#endif
 #ifndef MOBULA_FWD2_WARPS
 #define MOBULA_FWD2_WARPS 16
 #endif
@@ -558,7 +587,11 @@ __device__ __forceinline__ void load_roi_head(RoiHead<PH, NCH>& r, const uint2* 
   r.roi = __ldg(order_j);
 }
 
-template <int PH, int NCH, bool ACC, bool TYPED>
+// DENSE: the plane sits in shared memory as it sits in global memory (pitch == width, rows H + 1 and
+// H + 2 zero, row H = row H - 1) and arrives through a handful of bulk copies (UBLKCP: no LSU work, no
+// registers) instead of 13.6 K 16-byte cp.async per plane, whose issue alone took ~13 % of the kernel.
+// What the padding columns did is done by the column records (see resident_fwd2_table_kernel).
+template <int PH, int NCH, bool ACC, bool TYPED, bool DENSE = false>
 __global__ void __launch_bounds__(kFwd2Threads, 1)
 resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, const int* __restrict__ order,
                       const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
@@ -577,7 +610,18 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
   const unsigned sbase = ptx::smem_addr(smem_raw);
   const unsigned row_bytes = (unsigned)pitch * 4u;
 
-  zero_padding(plane, height, width, pitch);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)(height + 3) * pitch * 4 + 16 + 7) & ~(size_t)7));
+  unsigned parity = 0;
+  if (DENSE) {
+    // rows H + 1, H + 2 and the four floats behind them (high column of the last pixel)
+    for (int x = tid; x < 2 * pitch + 4; x += blockDim.x) plane[(height + 1) * pitch + x] = 0.0f;
+    if (tid == 0) {
+      ptx::mbar_init(bar, 1);
+      ptx::fence_mbar_init();
+    }
+  } else {
+    zero_padding(plane, height, width, pitch);
+  }
   __syncthreads();
   if (!ACC)
     zero_rows_of_invalid_rois(out, order, img_start, num_images, (long long)channels * bins,
@@ -594,8 +638,25 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
   while (u < u1) {
     const PlaneWork w = next_plane(img_start, c_count, u, u1, n);
     __syncthreads();   // every warp is done reading the previous plane
-    load_padded_plane(plane, data + ((size_t)w.n * channels + w.c) * plane_elems, height, width, pitch,
-                      vec16);
+    if (DENSE) {
+      if (tid == 0) {
+        const float* src = data + ((size_t)w.n * channels + w.c) * plane_elems;
+        const unsigned row_b = (unsigned)width * 4u;
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive_expect_tx(bar, (unsigned)(height + 1) * row_b);
+        // a few large copies: 32 rows each
+        for (int r = 0; r < height; r += 32) {
+          const int nr = min(32, height - r);
+          ptx::bulk_g2s(plane + (size_t)r * width, src + (size_t)r * width, (unsigned)nr * row_b, bar);
+        }
+        ptx::bulk_g2s(plane + (size_t)height * width, src + (size_t)(height - 1) * width, row_b, bar);   // row H
+      }
+      ptx::mbar_wait(bar, parity);
+      parity ^= 1u;
+    } else {
+      load_padded_plane(plane, data + ((size_t)w.n * channels + w.c) * plane_elems, height, width, pitch,
+                        vec16);
+    }
     ++epoch;
 
     // pair p of this warp: ROIs jj and jj + 1; a half-warp without a ROI of its own repeats the
@@ -621,12 +682,20 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
                       2 * pooled_w - 1);
 
       unsigned xa[NCH], xb[NCH];      // shared-memory address of the low column in row 0 / row 1
+      unsigned xah[NCH], xbh[NCH];    // DENSE: of the high column
       float2 hl2[NCH];                // (hx, lx)
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
-        xa[ch] = sbase + xs[ch].x;
+        const unsigned xo = xs[ch].x;
+        xa[ch] = sbase + (DENSE ? (xo & ~3u) : xo);
         xb[ch] = xa[ch] + row_bytes;
-        const float lx = __uint_as_float(xs[ch].y), hx = __fsub_rn(1.0f, lx);
+        float lx = __uint_as_float(xs[ch].y), hx = __fsub_rn(1.0f, lx);
+        if (DENSE) {
+          const unsigned dcol = (xo & 2u) ? 0u : 4u;
+          xah[ch] = xa[ch] + dcol;
+          xbh[ch] = xb[ch] + dcol;
+          if (xo & 1u) hx = lx = 0.0f;       // rejected sample column: weights 0 (products +-0, sums unchanged)
+        }
         hl2[ch] = make_float2(hx, lx);
       }
       // this lane's first output: bin (0, q / 2) of chunk 0 of its half-warp's ROI
@@ -650,14 +719,16 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
           // honours .rn only for the scalar forms), which would change the rounding
           float2 sm;
           {
-            taps_advance(tp[ch], xa[ch] + y0, xb[ch] + y0, code0, epoch);
+            if (DENSE) taps_advance_d(tp[ch], xa[ch] + y0, xah[ch] + y0, xb[ch] + y0, xbh[ch] + y0, code0, epoch);
+            else taps_advance(tp[ch], xa[ch] + y0, xb[ch] + y0, code0, epoch);
             const float2 wa = __fmul2_rn(make_float2(hy2.x, hy2.x), hl2[ch]), wb = __fmul2_rn(make_float2(ly2.x, ly2.x), hl2[ch]);
             const float2 pa = __fmul2_rn(wa, make_float2(tp[ch].plo, tp[ch].phi));
             const float2 pb = __fmul2_rn(wb, make_float2(tp[ch].clo, tp[ch].chi));
             sm.x = __fadd_rn(__fadd_rn(__fadd_rn(pa.x, pa.y), pb.x), pb.y);
           }
           {
-            taps_advance(tp[ch], xa[ch] + y1, xb[ch] + y1, code1, epoch);
+            if (DENSE) taps_advance_d(tp[ch], xa[ch] + y1, xah[ch] + y1, xb[ch] + y1, xbh[ch] + y1, code1, epoch);
+            else taps_advance(tp[ch], xa[ch] + y1, xb[ch] + y1, code1, epoch);
             const float2 wa = __fmul2_rn(make_float2(hy2.y, hy2.y), hl2[ch]), wb = __fmul2_rn(make_float2(ly2.y, ly2.y), hl2[ch]);
             const float2 pa = __fmul2_rn(wa, make_float2(tp[ch].plo, tp[ch].phi));
             const float2 pb = __fmul2_rn(wb, make_float2(tp[ch].clo, tp[ch].chi));
@@ -2058,12 +2129,19 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   const int cc = a.c_count > 0 ? a.c_count : a.channels;      // channels worked on (stride: a.channels)
   const long long work = (long long)a.num_rois * cc;
   unsigned grid = 0;
+  // dense plane + bulk copies: the box-head kernel (7 x 7, fp32, plain store) on planes whose rows are
+  // 16-byte multiples; MOBULA_FWD_DENSE=0 / 1 overrides the default
+  const int dense_env = [] { const char* e = getenv("MOBULA_FWD_DENSE"); return e ? atoi(e) : MOBULA_FWD_DENSE_DEFAULT; }();
+  const size_t dense_smem = (size_t)(a.height + 3) * a.width * sizeof(float) + 64;
+  const bool dense = dense_env != 0 && plan.fwd_two && !plan.fwd_pair && plan.vec16 && a.pooled_h == 7 &&
+                     plan.xslots == 16 && !accumulate && a.top_dtype == 0 && dense_smem <= plan.fwd_smem + 64 &&
+                     (size_t)(a.height + 1) * a.width * sizeof(float) < (1u << 20);   // one barrier phase counts < 2^20 bytes
   if (plan.fwd_two) {
     uint2* entries = (uint2*)(base + l.entries);
     const long long threads = (long long)a.num_rois * (2 * plan.ypairs + plan.xslots);
     chained_launch(resident_fwd2_table_kernel, (unsigned)((threads + 255) / 256), 256, 0, stream, 
-        a.rois, order, img_start, a.num_images, a.height, a.width, plan.pitch, plan.fwd_pair ? 8 : 4,
-        a.pooled_h, a.pooled_w, a.scale, plan.ypairs, plan.xslots, entries);
+        a.rois, order, img_start, a.num_images, a.height, a.width, dense ? a.width : plan.pitch, plan.fwd_pair ? 8 : 4,
+        a.pooled_h, a.pooled_w, a.scale, plan.ypairs, plan.xslots, entries, dense ? 1 : 0);
     count_launch();
 #define MOBULA_FWD2(ITERS, NCH, ACC, TYPED)                                                                 \
   do {                                                                                               \
@@ -2104,6 +2182,14 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
       chained_launch(resident_fwd2pr_kernel<PH, NCH, ACC, TYPED>, grid, kFwd2Threads, plan.fwd_smem, stream, \
           data, out, order, img_start, entries, a.num_images, a.channels, cc, a.height, a.width,     \
           plan.pitch, a.pooled_h, a.pooled_w, a.top_dtype);                                          \
+      break;                                                                                         \
+    }                                                                                                \
+    if (dense && PH == 7 && NCH == 1 && !ACC && !TYPED) {                                            \
+      auto kd = resident_fwd2r_kernel<7, 1, false, false, true>;                                     \
+      e = resident_grid(kd, kFwd2Threads, dense_smem, num_sms, work, &grid);                         \
+      if (e != cudaSuccess) return e;                                                                \
+      chained_launch(kd, grid, kFwd2Threads, dense_smem, stream, data, out, order, img_start, entries, \
+          a.num_images, a.channels, cc, a.height, a.width, a.width, a.pooled_h, a.pooled_w, plan.vec16, a.top_dtype); \
       break;                                                                                         \
     }                                                                                                \
     e = resident_grid(resident_fwd2r_kernel<PH, NCH, ACC, TYPED>, kFwd2Threads, plan.fwd_smem, num_sms, work, &grid); \

@@ -960,3 +960,37 @@ def test_pull_grouped_lists_equal_per_pixel_lists(direct, oracle, shape, monkeyp
         got[grouped] = (dx, acc)
     assert_bit_exact(got['1'][0], got['0'][0])
     assert_bit_exact(got['1'][1], got['0'][1])
+
+
+DENSE_SHAPES = [
+    # N, C, H, W, rois/img, scale: pooled 7 x 7, sampling ratio 2, rows of W % 4 == 0 floats
+    (2, 3, 50, 68, 40, 0.25),
+    (1, 5, 24, 28, 64, 0.5),
+    (3, 2, 33, 36, 19, 1.0),         # boxes far larger than the plane: rejected samples, clamped rows / columns
+    (1, 2, 200, 272, 48, 0.25),      # the box-head plane
+    (2, 4, 14, 16, 32, 1.0),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', DENSE_SHAPES, ids=lambda s: 'x'.join(str(v) for v in s[:5]))
+def test_dense_plane_forward_equals_padded_plane_forward(direct, oracle, shape, monkeypatch):
+    """The 7 x 7 forward on a dense shared-memory plane (pitch == width, brought in by bulk copies; the
+    column records carry the clamped / rejected flags the padding columns stood for) against the padded
+    plane and the oracle: bit-identical, including boxes that hang over every edge of the plane."""
+    from mobulaop_b200 import _native
+    N, C, H, W, k, scale = shape
+    wl = WL.Workload('dense', N, C, H, W, k, (7, 7), scale, 2, min_box=1.0, max_box=3.0 * max(H, W) / scale, stress=True)
+    data, rois, _ = WL.make_inputs(wl, seed=53)
+    rng = np.random.default_rng(11)
+    # boxes that start left of / above the plane and boxes that end beyond it
+    rois[::5, 1:3] -= rng.uniform(0, 0.5 * W / scale, (len(rois[::5]), 2)).astype(np.float32)
+    rois[1::5, 3:5] += rng.uniform(0, 0.5 * W / scale, (len(rois[1::5]), 2)).astype(np.float32)
+    y_ref = oracle.forward(data, rois, (7, 7), scale, 2)
+    got = {}
+    for dense in ('0', '1'):
+        monkeypatch.setenv('MOBULA_FWD_DENSE', dense)
+        got[dense] = direct.forward(data, rois, (7, 7), scale, 2, algo='resident')
+        assert _native.last_algo(False) == 'resident'
+        assert_bit_exact(got[dense], y_ref)
+    assert_bit_exact(got['1'], got['0'])

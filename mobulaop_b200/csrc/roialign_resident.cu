@@ -644,9 +644,9 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
         const unsigned row_b = (unsigned)width * 4u;
         ptx::fence_proxy_async();
         ptx::mbar_arrive_expect_tx(bar, (unsigned)(height + 1) * row_b);
-        // a few large copies: 32 rows each
-        for (int r = 0; r < height; r += 32) {
-          const int nr = min(32, height - r);
+        // a few large copies: `vec16` rows each (DENSE: the argument carries the chunk height)
+        for (int r = 0; r < height; r += vec16) {
+          const int nr = min(vec16, height - r);
           ptx::bulk_g2s(plane + (size_t)r * width, src + (size_t)r * width, (unsigned)nr * row_b, bar);
         }
         ptx::bulk_g2s(plane + (size_t)height * width, src + (size_t)(height - 1) * width, row_b, bar);   // row H
@@ -2132,6 +2132,9 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
   // dense plane + bulk copies: the box-head kernel (7 x 7, fp32, plain store) on planes whose rows are
   // 16-byte multiples; MOBULA_FWD_DENSE=0 / 1 overrides the default
   const int dense_env = [] { const char* e = getenv("MOBULA_FWD_DENSE"); return e ? atoi(e) : MOBULA_FWD_DENSE_DEFAULT; }();
+  // rows per bulk copy (MOBULA_FWD_DENSE_ROWS)
+  static const int dense_rows_env = [] { const char* e = getenv("MOBULA_FWD_DENSE_ROWS"); return e ? atoi(e) : 32; }();
+  const int dense_rows = dense_rows_env > 0 ? dense_rows_env : 32;
   const size_t dense_smem = (size_t)(a.height + 3) * a.width * sizeof(float) + 64;
   const bool dense = dense_env != 0 && plan.fwd_two && !plan.fwd_pair && plan.vec16 && a.pooled_h == 7 &&
                      plan.xslots == 16 && !accumulate && a.top_dtype == 0 && dense_smem <= plan.fwd_smem + 64 &&
@@ -2189,7 +2192,7 @@ cudaError_t launch_fwd_resident(const RoiAlignArgs& a, const ResidentPlan& plan,
       e = resident_grid(kd, kFwd2Threads, dense_smem, num_sms, work, &grid);                         \
       if (e != cudaSuccess) return e;                                                                \
       chained_launch(kd, grid, kFwd2Threads, dense_smem, stream, data, out, order, img_start, entries, \
-          a.num_images, a.channels, cc, a.height, a.width, a.width, a.pooled_h, a.pooled_w, plan.vec16, a.top_dtype); \
+          a.num_images, a.channels, cc, a.height, a.width, a.width, a.pooled_h, a.pooled_w, dense_rows, a.top_dtype); \
       break;                                                                                         \
     }                                                                                                \
     e = resident_grid(resident_fwd2r_kernel<PH, NCH, ACC, TYPED>, kFwd2Threads, plan.fwd_smem, num_sms, work, &grid); \

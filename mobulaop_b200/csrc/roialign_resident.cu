@@ -127,7 +127,7 @@ resident_fwd2_table_kernel(const float* __restrict__ rois, const int* __restrict
     s.l = 0.0f;
     if (dense) {
       // dense plane (pitch == width: no repeated column, no zero columns): the record says so itself --
-      // bit 0: the sample is rejected (both weights are 0, any column will do), bit 1: the column is
+      // bit 0: the sample is rejected (the lane loads nothing, its taps are 0), bit 1: the column is
       // clamped, its high tap is the low tap (bilinear.h:27-31)
       s.lo_off = 1u;
       if (kk < 2 * pooled_w) {
@@ -386,16 +386,19 @@ __device__ __forceinline__ void taps_advance(Taps& t, unsigned a, unsigned b, un
       : "+f"(t.plo), "+f"(t.phi), "+f"(t.clo), "+f"(t.chi)
       : "r"(a), "r"(b), "r"(code), "r"(epoch));
 }
-// dense plane: the high column has an address of its own (the low one again where the column is clamped)
+// dense plane: the high column has an address of its own (the low one again where the column is clamped);
+// a lane whose sample column is rejected (`live` == 0) loads nothing: its taps stay 0, what the zero
+// columns of the padded plane delivered
 __device__ __forceinline__ void taps_advance_d(Taps& t, unsigned a, unsigned ah, unsigned b, unsigned bh, unsigned code,
-                                               unsigned epoch) {
-  asm("{\n\t.reg .pred pl, ps, ph;\n\t"
-      "setp.eq.u32 pl, %8, 0;\n\tsetp.eq.u32 ps, %8, 1;\n\tsetp.ne.u32 ph, %8, 2;\n\t"
+                                               unsigned live, unsigned epoch) {
+  asm("{\n\t.reg .pred pl, ps, ph, pv;\n\t"
+      "setp.ne.u32 pv, %9, 0;\n\t"
+      "setp.eq.and.u32 pl, %8, 0, pv;\n\tsetp.eq.u32 ps, %8, 1;\n\tsetp.ne.and.u32 ph, %8, 2, pv;\n\t"
       "@ps mov.f32 %0, %2;\n\t@ps mov.f32 %1, %3;\n\t"
       "@pl ld.shared.f32 %0, [%4];\n\t@pl ld.shared.f32 %1, [%5];\n\t"
       "@ph ld.shared.f32 %2, [%6];\n\t@ph ld.shared.f32 %3, [%7];\n\t}"
       : "+f"(t.plo), "+f"(t.phi), "+f"(t.clo), "+f"(t.chi)
-      : "r"(a), "r"(ah), "r"(b), "r"(bh), "r"(code), "r"(epoch));
+      : "r"(a), "r"(ah), "r"(b), "r"(bh), "r"(code), "r"(live), "r"(epoch));
 }
 // the same for a channel pair (float2 per pixel)
 struct Taps2 {
@@ -683,18 +686,19 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
 
       unsigned xa[NCH], xb[NCH];      // shared-memory address of the low column in row 0 / row 1
       unsigned xah[NCH], xbh[NCH];    // DENSE: of the high column
+      unsigned live[NCH];             // DENSE: 0 = the sample column is rejected
       float2 hl2[NCH];                // (hx, lx)
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         const unsigned xo = xs[ch].x;
         xa[ch] = sbase + (DENSE ? (xo & ~3u) : xo);
         xb[ch] = xa[ch] + row_bytes;
-        float lx = __uint_as_float(xs[ch].y), hx = __fsub_rn(1.0f, lx);
+        const float lx = __uint_as_float(xs[ch].y), hx = __fsub_rn(1.0f, lx);
         if (DENSE) {
           const unsigned dcol = (xo & 2u) ? 0u : 4u;
           xah[ch] = xa[ch] + dcol;
           xbh[ch] = xb[ch] + dcol;
-          if (xo & 1u) hx = lx = 0.0f;       // rejected sample column: weights 0 (products +-0, sums unchanged)
+          live[ch] = (xo & 1u) ^ 1u;         // a rejected sample column loads nothing: its taps are 0
         }
         hl2[ch] = make_float2(hx, lx);
       }
@@ -719,7 +723,7 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
           // honours .rn only for the scalar forms), which would change the rounding
           float2 sm;
           {
-            if (DENSE) taps_advance_d(tp[ch], xa[ch] + y0, xah[ch] + y0, xb[ch] + y0, xbh[ch] + y0, code0, epoch);
+            if (DENSE) taps_advance_d(tp[ch], xa[ch] + y0, xah[ch] + y0, xb[ch] + y0, xbh[ch] + y0, code0, live[ch], epoch);
             else taps_advance(tp[ch], xa[ch] + y0, xb[ch] + y0, code0, epoch);
             const float2 wa = __fmul2_rn(make_float2(hy2.x, hy2.x), hl2[ch]), wb = __fmul2_rn(make_float2(ly2.x, ly2.x), hl2[ch]);
             const float2 pa = __fmul2_rn(wa, make_float2(tp[ch].plo, tp[ch].phi));
@@ -727,7 +731,7 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
             sm.x = __fadd_rn(__fadd_rn(__fadd_rn(pa.x, pa.y), pb.x), pb.y);
           }
           {
-            if (DENSE) taps_advance_d(tp[ch], xa[ch] + y1, xah[ch] + y1, xb[ch] + y1, xbh[ch] + y1, code1, epoch);
+            if (DENSE) taps_advance_d(tp[ch], xa[ch] + y1, xah[ch] + y1, xb[ch] + y1, xbh[ch] + y1, code1, live[ch], epoch);
             else taps_advance(tp[ch], xa[ch] + y1, xb[ch] + y1, code1, epoch);
             const float2 wa = __fmul2_rn(make_float2(hy2.y, hy2.y), hl2[ch]), wb = __fmul2_rn(make_float2(ly2.y, ly2.y), hl2[ch]);
             const float2 pa = __fmul2_rn(wa, make_float2(tp[ch].plo, tp[ch].phi));

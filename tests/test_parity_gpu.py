@@ -994,3 +994,32 @@ def test_dense_plane_forward_equals_padded_plane_forward(direct, oracle, shape, 
         assert _native.last_algo(False) == 'resident'
         assert_bit_exact(got[dense], y_ref)
     assert_bit_exact(got['1'], got['0'])
+
+
+@pytest.mark.gpu
+def test_dense_plane_forward_with_nonfinite_feature_map(direct, oracle, monkeypatch):
+    """A rejected sample column must contribute a literal 0 (bilinear.h:15-18) whatever the feature map
+    holds: with Inf / NaN in the border columns and rows, the dense-plane kernel (rejected lanes load
+    nothing) equals the padded-plane kernel (they read zero columns) and the oracle bit for bit."""
+    N, C, H, W, scale = 2, 3, 24, 28, 0.5
+    wl = WL.Workload('dense-nan', N, C, H, W, 48, (7, 7), scale, 2, min_box=1.0, max_box=3.0 * W / scale, stress=True)
+    data, rois, _ = WL.make_inputs(wl, seed=59)
+    rng = np.random.default_rng(13)
+    rois[::3, 1:3] -= rng.uniform(0, 0.6 * W / scale, (len(rois[::3]), 2)).astype(np.float32)
+    rois[1::3, 3:5] += rng.uniform(0, 0.6 * W / scale, (len(rois[1::3]), 2)).astype(np.float32)
+    data[:, :, :, 0] = np.inf
+    data[:, :, :, -1] = -np.inf
+    data[:, :, 0, 1:-1] = np.nan
+    data[:, :, -1, 5] = np.inf
+    with np.errstate(invalid='ignore'):
+        y_ref = oracle.forward(data, rois, (7, 7), scale, 2)
+    assert np.isfinite(y_ref).any() and not np.isfinite(y_ref).all()
+    got = {}
+    for dense in ('0', '1'):
+        monkeypatch.setenv('MOBULA_FWD_DENSE', dense)
+        got[dense] = direct.forward(data, rois, (7, 7), scale, 2, algo='resident')
+    # NaN payloads are not pinned by IEEE 754: compare where the values are numbers, and the NaN masks
+    for a in (got['0'], got['1']):
+        assert np.array_equal(np.isnan(a), np.isnan(y_ref))
+        ok = ~np.isnan(y_ref)
+        assert_bit_exact(a[ok], y_ref[ok])

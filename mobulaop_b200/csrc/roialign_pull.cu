@@ -1404,7 +1404,7 @@ cudaError_t launch_bwd_pull(const RoiAlignArgs& a, void* workspace, unsigned lon
     // C4: 413 -> 404 us); a long grid keeps them spread over the copy blocks (16 images: 782 against
     // 787 us, C4: 2.99 against 3.07 ms with the list blocks first; profiles/r2_knob_experiments.txt).
     // MOBULA_TABLES_Q = cap of the interleaving period (0 = none), see pull_tables_kernel.
-    static const int q_env = [] { const char* e = getenv("MOBULA_TABLES_Q"); return e ? atoi(e) : -1; }();
+    const int q_env = [] { const char* e = getenv("MOBULA_TABLES_Q"); return e ? atoi(e) : -1; }();   // per call: the tests switch it
     p.tables_q = q_env >= 0 ? q_env : (lblocks <= 3u * (unsigned)(num_sms > 0 ? num_sms : 148) * MOBULA_TABLES_MINBLOCKS ? 1 : 0);
     if (a.top_layout != 0 && L.cw == a.channels && cwork == a.channels) {
       if (a.top_dtype == 0 && (reinterpret_cast<uintptr_t>(dy) & 15u) == 0) {

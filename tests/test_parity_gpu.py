@@ -1023,3 +1023,19 @@ def test_dense_plane_forward_with_nonfinite_feature_map(direct, oracle, monkeypa
         assert np.array_equal(np.isnan(a), np.isnan(y_ref))
         ok = ~np.isnan(y_ref)
         assert_bit_exact(a[ok], y_ref[ok])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mode', ['atomic', 'deterministic'])
+def test_pull_backward_does_not_depend_on_the_block_order_of_the_list_grid(direct, mode, monkeypatch):
+    """The list / copy grid of the pull backward hands out list blocks first, spread out, or in
+    between (MOBULA_TABLES_Q): where a pixel's list lives in the entry array changes with it, what
+    the list holds and the order of its entries do not -- dX is bit-identical."""
+    wl = WL.Workload('order', 3, 40, 50, 68, 90, (7, 7), 0.25, 2, min_box=2.0, max_box=300.0)
+    data, rois, dy = WL.make_inputs(wl, seed=61)
+    got = []
+    for q in ('0', '1', '3'):
+        monkeypatch.setenv('MOBULA_TABLES_Q', q)
+        got.append(direct.backward(dy, rois, data.shape, wl.scale, wl.sampling_ratio, algo='pull', mode=mode))
+    assert_bit_exact(got[1], got[0])
+    assert_bit_exact(got[2], got[0])

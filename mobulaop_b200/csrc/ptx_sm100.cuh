@@ -93,6 +93,17 @@ __device__ __forceinline__ void chain_enter() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// The two halves of chain_enter() for a kernel that has work to do which does not depend on its
+// predecessor (e.g. fetching its first tile): chain_trigger() at the top, chain_wait() before the
+// first read of what the predecessor wrote.  Whatever ran before the predecessor is complete by
+// then: the predecessor itself waited for it before it let this kernel be scheduled.
+__device__ __forceinline__ void chain_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void chain_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 }  // namespace ptx
 
 template <typename... Params, typename... Args>

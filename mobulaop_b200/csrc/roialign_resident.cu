@@ -600,7 +600,11 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
                       const int* __restrict__ img_start, const uint2* __restrict__ entries, int num_images,
                       int channels, int c_count, int height, int width, int pitch, int pooled_h, int pooled_w,
                       int vec16, int odt) {
-  ptx::chain_enter();
+  // DENSE: the first plane is on its way before the kernel waits for the table kernel (the planes and
+  // the grouping by image -- written by the kernel before the table kernel -- do not depend on it)
+  if (DENSE) ptx::chain_trigger();
+  else ptx::chain_enter();
+  bool waited = !DENSE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* plane = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -653,6 +657,10 @@ resident_fwd2r_kernel(const float* __restrict__ data, float* __restrict__ out, c
           ptx::bulk_g2s(plane + (size_t)r * width, src + (size_t)r * width, (unsigned)nr * row_b, bar);
         }
         ptx::bulk_g2s(plane + (size_t)height * width, src + (size_t)(height - 1) * width, row_b, bar);   // row H
+      }
+      if (!waited) {
+        ptx::chain_wait();
+        waited = true;
       }
       ptx::mbar_wait(bar, parity);
       parity ^= 1u;
